@@ -1,0 +1,273 @@
+// Shared device-side definitions: plane bit layout, kernel parameter block, Philox
+// stream ids, and the per-agent rules (game, probe, child) every kernel uses.
+//
+// Citations are /root/reference/src/model.py.  The rules implement the EFFECTIVE
+// semantics written down in DESIGN.md ("Semantics"); the NumPy oracle (oracle/pd_oracle.py)
+// restates the same reference functions independently on an agent list.
+#pragma once
+#include <stdint.h>
+#include "philox.cuh"
+
+namespace pd {
+
+// ---- tf plane bits ---------------------------------------------------------------------
+// Canonical (between steps): OCC | trait.  Transient meanings per phase:
+//   tfA during play      : bits 3-6 = D code of an at-risk agent (0 none, c+1 = dies in sub-step c)
+//   tfB/tfA during travel: GHOST = cell was occupied at step start but is empty now (still
+//                          blocks movers, quirk B-13), CLAIM|DIR = mover claiming direction DIR
+//   tfB during reproduce : CLAIM|DIR = parent claiming direction DIR
+//   tfA after reproduce  : NEWBORN (same bit as GHOST) until the cull has run
+constexpr uint32_t TF_TRAIT = 0x03u;
+constexpr uint32_t TF_GHOST = 0x04u;
+constexpr uint32_t TF_NEWBORN = 0x04u;
+constexpr uint32_t TF_DIR_SHIFT = 3u;
+constexpr uint32_t TF_DIR = 0x38u;
+constexpr uint32_t TF_CLAIM = 0x40u;
+constexpr uint32_t TF_OCC = 0x80u;
+constexpr uint32_t TF_D_SHIFT = 3u;
+constexpr uint32_t TF_D = 0x78u;
+
+// ---- Philox stream ids (counter word 3); must equal oracle/pd_oracle.py -----------------
+constexpr uint32_t S_ROLL = 0;    // x: pair-ordering roll (:364)  y: travel priority (:806)  z>>29: travel start dir (:810)
+constexpr uint32_t S_GAME0 = 1;   // +c; keyed by the RESPONDER's cell: x my noise (:611) y challenger noise (:612)
+                                  //     z>>31 challenger RANDOM coin (:631)  w>>31 my RANDOM coin (:664)
+constexpr uint32_t S_REPRO = 9;   // x: reproduction claim priority (:1076)  y>>29: start dir (:1079)
+constexpr uint32_t S_MUT = 10;    // mutation rolls (:1263, :1278, :1291-1292), keyed by the parent's cell
+constexpr uint32_t S_PICK = 11;   // replacement picks (:1265, :1281, :1303, :1314)
+constexpr uint32_t S_CULL = 12;   // x: newborn cull priority, keyed by the child's cell (replaces :1343/:1354)
+constexpr uint32_t S_ENERGY = 13; // child energy normal deviate (:1236), keyed by the parent's cell
+constexpr uint32_t INIT_STEP = 0xFFFFFFFFu;
+constexpr uint32_t I_PLACE = 0;   // x: placement priority (:1438-1450)  y>>30: trait (:1467)
+constexpr uint32_t I_STRAT = 1;   // strategy draws (:1473-1497)
+constexpr uint32_t I_ENERGY = 2;  // initial energy normal deviate (:1460-1465)
+
+// 1 / (2^32 * sqrt(24 + 1/12)) -- scale of the integer-exact normal stand-in
+#define PD_NORMAL_SCALE 0x1.a15286234fcddp-35
+
+// Moore offsets (:302-307); the opposite of direction i is 7-i.
+// x: {-1,-1,-1,0,0,1,1,1}  y: {-1,0,1,-1,1,-1,0,1} -- row-major 3x3 minus the centre, so with
+// e = d + (d >= 4):  dx = e / 3 - 1,  dy = e % 3 - 1  (folds to constants in unrolled loops).
+__host__ __device__ constexpr int DX(int d) { return (d + (d >= 4 ? 1 : 0)) / 3 - 1; }
+__host__ __device__ constexpr int DY(int d) { return (d + (d >= 4 ? 1 : 0)) % 3 - 1; }
+static_assert(DX(0) == -1 && DX(2) == -1 && DX(3) == 0 && DX(4) == 0 && DX(5) == 1 && DX(7) == 1, "dx");
+static_assert(DY(0) == -1 && DY(1) == 0 && DY(2) == 1 && DY(3) == -1 && DY(4) == 1 && DY(5) == -1 &&
+              DY(6) == 0 && DY(7) == 1, "dy");
+
+// ---- device-resident counters -----------------------------------------------------------
+struct Counters {
+    // zeroed at the start of every step (k_begin_step)
+    unsigned int mv_n, rp_n, nb_n, risk_next_n;
+    unsigned int mv_active[8], rp_active[8];
+    unsigned long long n_old, births, culled, living_deaths;
+    unsigned long long st_play_deaths, st_movers, st_moved, st_travel_deaths;
+    unsigned long long bins[16];
+    unsigned int hist[8][256];
+    // persistent across steps
+    unsigned int risk_n;
+    unsigned int overflow;
+    unsigned int barrier[2];
+    unsigned long long n_agents;
+    unsigned long long agents_start;
+    unsigned long long last_bins[16];
+    unsigned long long last_stats[12];
+};
+
+// ---- kernel parameter block (lives in the constant bank as a __grid_constant__ arg) ------
+struct Params {
+    uint32_t W, H, row0, log2W;
+    uint32_t k0, k1, step;
+    float pay[4];  // index (i_coop << 1) | challenger_coop: {dd, dc, cd, cc} seen by the responder
+    float max_energy, travel_cost, cost_of_living, reproduce_min_energy, reproduce_cost;
+    float inherit, e_mu, e_sigma, e_min, risk_thr, mutation_rate;
+    unsigned long long noise_thr, mut_thr, strat_thr[3];
+    unsigned long long max_agents;
+    uint32_t pure, per_trait, max_children, want_counts, stats;
+    uint32_t list_cap, sparse_ctas;
+    // planes
+    float* E0;       // caller-bound energy (state between steps)
+    float* E1;       // scratch energy (state between play and the final sweep)
+    uint8_t* strat;  // caller-bound
+    uint8_t* tfA;    // caller-bound
+    uint8_t* tfB;    // scratch
+    // sparse lists
+    uint32_t* risk_cur; uint32_t* risk_next; float* risk_e; uint32_t* risk_roll;
+    uint32_t* mv_cell; uint8_t* mv_state; uint8_t* mv_aux;
+    uint32_t* rp_cell; uint8_t* rp_state; uint8_t* rp_aux;
+    uint32_t* nb_cell; uint32_t* nb_prio;
+    Counters* ctr;
+};
+
+__device__ __forceinline__ Words rng(const Params& p, uint64_t gcell, uint32_t stream) {
+    return philox4x32_10((uint32_t)gcell, (uint32_t)(gcell >> 32), p.step, stream, p.k0, p.k1);
+}
+__device__ __forceinline__ Words rng_init(const Params& p, uint64_t gcell, uint32_t stream) {
+    return philox4x32_10((uint32_t)gcell, (uint32_t)(gcell >> 32), INIT_STEP, stream, p.k0, p.k1);
+}
+
+// global cell index (x + y*env_max, :339) of local cell (x, y) and of its neighbours
+__device__ __forceinline__ uint64_t gcell_of(const Params& p, uint32_t x, uint32_t y) {
+    return ((uint64_t)(p.row0 + y) << p.log2W) | x;
+}
+// local plane index of the neighbour of local (x,y) in direction d, wrapping (:311-312)
+__device__ __forceinline__ uint32_t nb_local(const Params& p, uint32_t x, uint32_t y, int d) {
+    const uint32_t nx = (x + (uint32_t)DX(d)) & (p.W - 1);
+    const uint32_t ny = (y + (uint32_t)DY(d)) & (p.H - 1);
+    return (ny << p.log2W) | nx;
+}
+__device__ __forceinline__ uint64_t nb_gcell(const Params& p, uint32_t x, uint32_t y, int d) {
+    const uint32_t nx = (x + (uint32_t)DX(d)) & (p.W - 1);
+    const uint32_t gy = (p.row0 + y + (uint32_t)DY(d)) & (p.W - 1);
+    return ((uint64_t)gy << p.log2W) | nx;
+}
+
+// ---- the game as the RESPONDER sees it (play_response, :599-689) --------------------------
+// strategies: 0 COOP, 1 DEFECT, 2 TFT (== COOP: its memory is submodel-local and every pair
+// plays once per step, :621-629/:646-661), 3 RANDOM.
+__device__ __forceinline__ float game_payoff(const Params& p, uint64_t my_gcell, int c,
+                                             uint32_t my_strat, uint32_t my_trait,
+                                             uint32_t ch_strat, uint32_t ch_trait) {
+    const uint32_t mine = (my_strat >> (2 * ch_trait)) & 3u;    // :599
+    const uint32_t theirs = (ch_strat >> (2 * my_trait)) & 3u;  // :600
+    bool i_coop = mine != 1u;
+    bool ch_coop = theirs != 1u;
+    if (p.noise_thr != 0ull || mine == 3u || theirs == 3u) {
+        const Words w = rng(p, my_gcell, S_GAME0 + (uint32_t)c);  // :611-612
+        if (theirs == 3u) ch_coop = (w.z >> 31) != 0u;             // :630-635
+        if (mine == 3u) i_coop = (w.w >> 31) != 0u;                // :663-668
+        if ((unsigned long long)w.y < p.noise_thr) ch_coop = !ch_coop;  // :638-640
+        if ((unsigned long long)w.x < p.noise_thr) i_coop = !i_coop;    // :672-674
+    }
+    return p.pay[((uint32_t)i_coop << 1) | (uint32_t)ch_coop];  // :677-689 (my side only)
+}
+
+// ---- triangular probe (:826-839, :1088-1101) ---------------------------------------------
+// blocked: bit d set = direction d not free.  l = start direction, seq = probes used so far.
+// Returns the direction found or -1; on success the caller stores next start (l+1)&7 and seq.
+__device__ __forceinline__ int probe(uint32_t blocked, int& l, int& seq) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        ++seq;
+        if (seq > 8) return -1;
+        l = (l + i) & 7;
+        if (!((blocked >> l) & 1u)) return l;
+    }
+    return -1;
+}
+// number of probes a FIRST attempt starting at s needed to reach direction d
+__device__ __forceinline__ int probe_pos(int s, int d) {
+    int l = s;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        l = (l + i) & 7;
+        if (l == d) return i + 1;
+    }
+    return 8;
+}
+
+// ---- integer-exact N(0,1) stand-in (see oracle.normal_from_words) -------------------------
+__device__ __forceinline__ float normal_from_words(const Words& w) {
+    const long long pc = (long long)(__popc(w.x) + __popc(w.y) + __popc(w.z)) - 48ll;
+    const long long zi = pc * 4294967296ll + ((long long)w.w - 2147483648ll);
+    return __double2float_rn(__dmul_rn((double)zi, PD_NORMAL_SCALE));
+}
+
+__device__ __forceinline__ uint32_t mutate(uint32_t s, uint32_t pick_word) {
+    return (s + 1u + (uint32_t)(((unsigned long long)pick_word * 3ull) >> 32)) & 3u;
+}
+
+// ---- the child (god_multiply, :1224-1326) --------------------------------------------------
+// parent_energy_after_cost is only used in inheritance mode (:1242).
+__device__ __forceinline__ void make_child(const Params& p, uint64_t parent_gcell,
+                                           uint32_t parent_strat, uint32_t parent_trait,
+                                           float parent_energy_after_cost, float& child_energy,
+                                           uint32_t& child_strat) {
+    float ce;
+    if (p.inherit <= 0.0f || p.inherit > 1.0f) {  // :1231-1238
+        const float z = normal_from_words(rng(p, parent_gcell, S_ENERGY));
+        ce = __fadd_rn(__fmul_rn(z, p.e_sigma), p.e_mu);
+    } else {
+        ce = __fmul_rn(p.inherit, parent_energy_after_cost);  // :1242
+    }
+    if (ce < p.e_min) ce = p.e_min;  // :1245-1249
+    else if (ce > p.max_energy) ce = p.max_energy;
+    child_energy = ce;
+    uint32_t cs = parent_strat;
+    if (p.mutation_rate > 0.0f) {
+        const Words m = rng(p, parent_gcell, S_MUT);
+        const Words k = rng(p, parent_gcell, S_PICK);
+        if (p.pure) {  // :1259-1271 -- the roll is drawn but never compared (quirk B-7)
+            const uint32_t s = mutate(parent_strat & 3u, k.x);
+            cs = s * 0x55u;
+        } else if (p.per_trait) {  // :1273-1286
+            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+            const uint32_t kw[4] = {k.x, k.y, k.z, k.w};
+            cs = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint32_t s = (parent_strat >> (2 * i)) & 3u;
+                if ((unsigned long long)mw[i] < p.mut_thr) s = mutate(s, kw[i]);
+                cs |= s << (2 * i);
+            }
+        } else {  // kin / other, :1287-1326
+            const uint32_t first_other = parent_trait == 0u ? 1u : 0u;
+            uint32_t s_my = (parent_strat >> (2 * parent_trait)) & 3u;
+            uint32_t s_ot = (parent_strat >> (2 * first_other)) & 3u;
+            if ((unsigned long long)m.x < p.mut_thr) s_my = mutate(s_my, k.x);
+            if ((unsigned long long)m.y < p.mut_thr) s_ot = mutate(s_ot, k.y);
+            cs = (s_ot * 0x55u) & ~(3u << (2 * parent_trait));
+            cs |= s_my << (2 * parent_trait);
+        }
+    } else if (p.pure) {
+        cs = (parent_strat & 3u) * 0x55u;  // all four slots = slot 0 (:1260, :1268-1270)
+    } else if (!p.per_trait) {
+        // kin/other without mutation still rewrites every "other" slot from the first one (:1296-1323)
+        const uint32_t first_other = parent_trait == 0u ? 1u : 0u;
+        const uint32_t s_my = (parent_strat >> (2 * parent_trait)) & 3u;
+        const uint32_t s_ot = (parent_strat >> (2 * first_other)) & 3u;
+        cs = ((s_ot * 0x55u) & ~(3u << (2 * parent_trait))) | (s_my << (2 * parent_trait));
+    }
+    child_strat = cs & 0xFFu;
+}
+
+// strategy-count bin of an agent: 4*my + other (:1413-1419, :1501-1511), derived (B-8)
+__device__ __forceinline__ uint32_t count_bin(uint32_t strat, uint32_t trait) {
+    const uint32_t my = (strat >> (2 * trait)) & 3u;
+    const uint32_t other = (strat >> (2 * (trait == 0u ? 1u : 0u))) & 3u;
+    return 4u * my + other;
+}
+
+// ---- software grid barrier for the persistent sparse kernels ------------------------------
+// Co-residency is guaranteed by cudaLaunchCooperativeKernel (or by nblk == 1).
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int nblk) {
+    __syncthreads();
+    if (nblk > 1) {
+        if (threadIdx.x == 0) {
+            volatile unsigned int* vgen = bar + 1;
+            const unsigned int gen = *vgen;
+            __threadfence();
+            if (atomicAdd(bar, 1u) == nblk - 1u) {
+                atomicExch(bar, 0u);
+                __threadfence();
+                atomicAdd(bar + 1, 1u);
+            } else {
+                while (*vgen == gen) __nanosleep(64);
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+}
+
+// warp-aggregated append: every lane of the (converged) warp must call this
+__device__ __forceinline__ uint32_t warp_append(unsigned int* counter, bool pred) {
+    const unsigned int m = __ballot_sync(0xFFFFFFFFu, pred);
+    if (m == 0u) return 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    return pred ? base + (unsigned int)__popc(m & ((1u << lane) - 1u)) : 0xFFFFFFFFu;
+}
+
+}  // namespace pd

@@ -1,0 +1,913 @@
+// The per-step pipeline as CUDA kernels for sm_100a.
+//
+// One model step (main layers 1-7, /root/reference/src/model.py:2140-2163) is
+//   k_begin_step    zero the per-step counters
+//   k_risk_resolve  sparse: exact death sub-step of the few agents that CAN die in play
+//   k_play_travel   dense sweep 1: roll + roles + 8 play sub-steps + mover decision + travel claim
+//   k_move_commit   dense sweep 2: resolve travel claims (round 1), pull movers into targets
+//   k_move_retry    sparse: travel rounds 2..8 for the claim losers
+//   k_repro_claim   dense sweep 3: eligibility + reproduction claim
+//   k_repro_commit  dense sweep 4: resolve claims (round 1), births, cost of living, death, counts
+//   k_repro_retry   sparse: reproduction rounds 2..8 (gated by the carrying capacity)
+//   k_finalize      sparse: newborn cull (exact k-th selection), deferred living cost, counts
+// Every dense sweep is a pure GATHER: a cell reads its neighbourhood and writes only itself,
+// so there are no claim planes, no atomics on cells and no clears (DESIGN.md "Kernels").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pd_device.cuh"
+
+namespace pd {
+
+constexpr int NT = 256;  // threads per CTA of the dense sweeps
+
+// ------------------------------------------------------------------------------------------
+// tile loader: (TH + 2*HALO) x (TW + 2*HALO) bytes of a u8 plane into shared memory, wrapping
+// ------------------------------------------------------------------------------------------
+template <int TW, int TH, int HALO>
+__device__ __forceinline__ void load_tile_u8(const Params& p, const uint8_t* __restrict__ plane,
+                                             uint8_t* s, uint32_t x0, uint32_t y0) {
+    constexpr int SW = TW + 2 * HALO;
+    constexpr int SH = TH + 2 * HALO;
+    for (int i = threadIdx.x; i < SW * SH; i += NT) {
+        const int r = i / SW, c = i - r * SW;
+        const uint32_t gx = (x0 + (uint32_t)(c - HALO)) & (p.W - 1);
+        const uint32_t gy = (y0 + (uint32_t)(r - HALO)) & (p.H - 1);
+        s[i] = plane[((size_t)gy << p.log2W) | gx];
+    }
+}
+
+// contest key of a claimant: (priority word, global cell) -- higher wins (:929, :1192)
+struct Key {
+    uint32_t prio;
+    uint64_t gcell;
+};
+__device__ __forceinline__ bool key_gt(const Key& a, const Key& b) {
+    return a.prio > b.prio || (a.prio == b.prio && a.gcell > b.gcell);
+}
+__device__ __forceinline__ Key travel_key(const Params& p, uint64_t g) {
+    Key k; k.prio = rng(p, g, S_ROLL).y; k.gcell = g; return k;  // :806
+}
+__device__ __forceinline__ Key repro_key(const Params& p, uint64_t g) {
+    Key k; k.prio = rng(p, g, S_REPRO).x; k.gcell = g; return k;  // :1076
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_begin_step(Counters* ctr) {
+    // zero everything up to (not including) risk_n
+    unsigned int* w = reinterpret_cast<unsigned int*>(ctr);
+    const size_t nwords = offsetof(Counters, risk_n) / sizeof(unsigned int);
+    for (size_t i = threadIdx.x; i < nwords; i += blockDim.x) w[i] = 0u;
+    if (threadIdx.x == 0) ctr->agents_start = ctr->n_agents;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_risk_resolve: the agents whose energy is so low that a run of negative payoffs could kill
+// them during play (list built by the previous step).  A responder that dies in sub-step c
+// (:695-697) neither challenges nor responds afterwards, so its neighbours' games depend on
+// WHEN it dies.  Eight lock-stepped rounds over the sparse list reproduce exit_play_fn's
+// iterations (:1527-1556) exactly; the result (D code) is written into the agent's tf byte so
+// the dense play sweep knows for every neighbour whether it is still alive in sub-step c.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_risk_resolve(const __grid_constant__ Params p) {
+    Counters* ctr = p.ctr;
+    const unsigned int n = ctr->risk_n;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n == 0) return;
+    for (int c = 0; c < 8; ++c) {
+        const int d = 7 - c;  // my direction towards whoever challenges me in sub-step c (:477)
+        for (unsigned int i = t0; i < n; i += stride) {
+            const uint32_t cell = p.risk_cur[i];
+            const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
+            const uint32_t t = __ldcg(p.tfA + cell);
+            const uint64_t g = gcell_of(p, x, y);
+            float e;
+            uint32_t roll;
+            if (c == 0) {
+                e = p.E0[cell];
+                roll = rng(p, g, S_ROLL).x;
+                p.risk_e[i] = e;
+                p.risk_roll[i] = roll;
+            } else {
+                e = p.risk_e[i];
+                roll = p.risk_roll[i];
+            }
+            if (!(t & TF_OCC) || (t & TF_D)) continue;  // empty (stale entry) or already dead
+            const uint32_t nc = nb_local(p, x, y, d);
+            const uint32_t tn = __ldcg(p.tfA + nc);
+            if (!(tn & TF_OCC)) continue;
+            const uint64_t gn = nb_gcell(p, x, y, d);
+            const uint32_t rn = rng(p, gn, S_ROLL).x;
+            if (!(rn > roll || (rn == roll && gn > g))) continue;  // I am the challenger (:413)
+            const uint32_t dn = (tn & TF_D) >> TF_D_SHIFT;
+            if (dn != 0u && (int)dn - 1 < c) continue;  // challenger died in an earlier sub-step
+            const float pay = game_payoff(p, g, c, p.strat[cell], t & TF_TRAIT, p.strat[nc], tn & TF_TRAIT);
+            e = __fadd_rn(e, pay);
+            if (e <= 0.0f) {
+                p.tfA[cell] = (uint8_t)(t | ((uint32_t)(c + 1) << TF_D_SHIFT));
+            } else {
+                p.risk_e[i] = fminf(e, p.max_energy);
+            }
+        }
+        grid_sync(ctr->barrier, gridDim.x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_play_travel (dense sweep 1).  Fuses search_for_neighbours (:352-372), get_game_list
+// (:373-440), the 8 iterations of play_challenge/play_response (:450-734) with exit_play_fn's
+// terminal rule, and the first move_request (:784-872).  tfA, strat (1-cell halo) -> tfB, E1.
+// ------------------------------------------------------------------------------------------
+template <int TW, int TH>
+__global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Params p) {
+    constexpr int SW = TW + 2, SH = TH + 2;
+    __shared__ uint8_t s_tf[SW * SH];
+    __shared__ uint8_t s_st[SW * SH];
+    __shared__ uint32_t s_roll[SW * SH];
+    const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    load_tile_u8<TW, TH, 1>(p, p.tfA, s_tf, x0, y0);
+    load_tile_u8<TW, TH, 1>(p, p.strat, s_st, x0, y0);
+    __syncthreads();
+    // per-step die roll of every occupied cell of the tile + halo (:364) -- recomputed, not communicated
+    for (int i = threadIdx.x; i < SW * SH; i += NT) {
+        uint32_t roll = 0;
+        if (s_tf[i] & TF_OCC) {
+            const int r = i / SW, c = i - r * SW;
+            const uint32_t gx = (x0 + (uint32_t)(c - 1)) & (p.W - 1);
+            const uint32_t gy = (p.row0 + y0 + (uint32_t)(r - 1)) & (p.W - 1);
+            roll = rng(p, ((uint64_t)gy << p.log2W) | gx, S_ROLL).x;
+        }
+        s_roll[i] = roll;
+    }
+    __syncthreads();
+    unsigned int n_play_deaths = 0, n_movers = 0, n_travel_deaths = 0;
+    for (int i = threadIdx.x; i < TW * TH; i += NT) {
+        const int ly = i / TW, lx = i - ly * TW;
+        const int si = (ly + 1) * SW + lx + 1;
+        const uint32_t x = x0 + lx, y = y0 + ly;
+        const size_t cell = ((size_t)y << p.log2W) | x;
+        const uint32_t t = s_tf[si];
+        uint32_t out = 0;
+        float e_out = 0.0f;
+        if (t & TF_OCC) {
+            const uint32_t trait = t & TF_TRAIT;
+            const uint32_t strat = s_st[si];
+            const uint32_t roll = s_roll[si];
+            const uint64_t g = gcell_of(p, x, y);
+            float e = p.E0[cell];
+            uint32_t occ_mask = 0;
+            int games = 0;
+            bool dead = false, act7_challenge = false, act0_respond = false;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int d = 7 - c;
+                const int sn = si + DY(d) * SW + DX(d);
+                const uint32_t tn = s_tf[sn];
+                if (!(tn & TF_OCC)) continue;
+                occ_mask |= 1u << d;
+                const uint32_t rn = s_roll[sn];
+                bool n_higher = rn > roll;
+                if (rn == roll) n_higher = nb_gcell(p, x, y, d) > g;  // tie -> cell index (:413)
+                if (d == 7) act7_challenge = !n_higher;
+                if (d == 0) act0_respond = n_higher;
+                if (!n_higher || dead) continue;
+                const uint32_t dn = (tn & TF_D) >> TF_D_SHIFT;
+                if (dn != 0u && (int)dn - 1 < c) continue;  // challenger already dead
+                const float pay = game_payoff(p, g, c, strat, trait, s_st[sn], tn & TF_TRAIT);
+                e = __fadd_rn(e, pay);                       // :679-688
+                if (e <= 0.0f) dead = true;                  // :695-697
+                else { e = fminf(e, p.max_energy); ++games; }  // :698-710
+            }
+            if (dead) {
+                out = TF_GHOST;
+                ++n_play_deaths;
+            } else {
+                // terminal rule (:547-556, :719-730, :486-496) or no neighbours (:429-433)
+                const bool mover = occ_mask == 0u || (games == 0 && (act7_challenge || act0_respond));
+                out = TF_OCC | trait;
+                if (mover) {
+                    ++n_movers;
+                    e = __fsub_rn(e, p.travel_cost);  // :800
+                    if (e <= 0.0f) {                  // :801-804
+                        out = TF_GHOST;
+                        e = 0.0f;
+                        ++n_travel_deaths;
+                    } else {
+                        const Words w = rng(p, g, S_ROLL);
+                        int l = (int)(w.z >> 29), seq = 0;  // :810
+                        const int dir = probe(occ_mask, l, seq);
+                        if (dir >= 0) out |= TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT);
+                    }
+                }
+                e_out = e;
+            }
+        }
+        p.tfB[cell] = (uint8_t)out;
+        p.E1[cell] = e_out;
+    }
+    if (p.stats) {
+        if (n_play_deaths) atomicAdd(&p.ctr->st_play_deaths, (unsigned long long)n_play_deaths);
+        if (n_movers) atomicAdd(&p.ctr->st_movers, (unsigned long long)n_movers);
+        if (n_travel_deaths) atomicAdd(&p.ctr->st_travel_deaths, (unsigned long long)n_travel_deaths);
+    }
+}
+
+// does the claimant at smem index sn (2-halo tile) point at the cell that is `j` away from it?
+// i.e. is neighbour j OF THE TARGET a claimant of the target: its dir must be 7-j.
+__device__ __forceinline__ bool claims_dir(uint32_t t, int dir) {
+    return (t & TF_CLAIM) && (int)((t & TF_DIR) >> TF_DIR_SHIFT) == dir;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_move_commit (dense sweep 2): move_response (:881-960), round 1.  tfB (2-cell halo) -> tfA.
+// An empty cell looks for claimants among its 8 neighbours and PULLS the winner's state; a
+// claimant re-evaluates the contest at its target (same inputs, same answer) and either
+// vacates (leaving a GHOST that keeps blocking movers this step) or joins the loser list.
+// ------------------------------------------------------------------------------------------
+template <int TW, int TH>
+__global__ void __launch_bounds__(NT) k_move_commit(const __grid_constant__ Params p) {
+    constexpr int SW = TW + 4;
+    __shared__ uint8_t s_tf[SW * (TH + 4)];
+    const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    load_tile_u8<TW, TH, 2>(p, p.tfB, s_tf, x0, y0);
+    __syncthreads();
+    unsigned int n_moved = 0;
+    constexpr int ITERS = (TW * TH + NT - 1) / NT;
+    for (int it = 0; it < ITERS; ++it) {
+        const int i = it * NT + threadIdx.x;
+        const bool valid = i < TW * TH;
+        const int ly = valid ? i / TW : 0, lx = valid ? i - ly * TW : 0;
+        const int si = (ly + 2) * SW + lx + 2;
+        const uint32_t x = x0 + lx, y = y0 + ly;
+        const size_t cell = ((size_t)y << p.log2W) | x;
+        const uint32_t t = valid ? s_tf[si] : 0u;
+        uint32_t out = t & (TF_OCC | TF_GHOST | TF_TRAIT);
+        bool lost = false;
+        uint32_t loser_state = 0;
+        if (valid && (t & TF_CLAIM)) {
+            const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
+            const int st = si + DY(d) * SW + DX(d);  // target
+            const uint32_t tx = x + (uint32_t)DX(d), ty = y + (uint32_t)DY(d);  // unwrapped
+            bool win = true, have_key = false;
+            Key mine;
+            const uint64_t g = gcell_of(p, x, y);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j == 7 - d) continue;  // that is me
+                const uint32_t tn = s_tf[st + DY(j) * SW + DX(j)];
+                if (!claims_dir(tn, 7 - j)) continue;
+                if (!have_key) { mine = travel_key(p, g); have_key = true; }
+                const Key other = travel_key(p, nb_gcell(p, tx & (p.W - 1), ty & (p.H - 1), j));
+                if (key_gt(other, mine)) win = false;
+            }
+            if (win) {
+                out = TF_GHOST;  // moved away; the cell still counts as occupied for movers (B-13)
+            } else {
+                lost = true;     // :940-943 -> retry with the same roll, next start = d+1 (:848)
+                const int s = (int)(rng(p, g, S_ROLL).z >> 29);
+                loser_state = 0x80u | (uint32_t)((d + 1) & 7) | ((uint32_t)probe_pos(s, d) << 3);
+            }
+        } else if (valid && !(t & (TF_OCC | TF_GHOST))) {
+            int best = -1;
+            Key bk;
+            int ncl = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t tn = s_tf[si + DY(j) * SW + DX(j)];
+                if (!claims_dir(tn, 7 - j)) continue;
+                ++ncl;
+                if (ncl == 1) { best = j; continue; }
+                if (ncl == 2) bk = travel_key(p, nb_gcell(p, x, y, best));
+                const Key k = travel_key(p, nb_gcell(p, x, y, j));
+                if (key_gt(k, bk)) { bk = k; best = j; }
+            }
+            if (best >= 0) {  // the winner relocates here (:946-956)
+                const uint32_t src = nb_local(p, x, y, best);
+                const uint32_t tn = s_tf[si + DY(best) * SW + DX(best)];
+                p.E1[cell] = p.E1[src];
+                p.strat[cell] = p.strat[src];
+                out = TF_OCC | (tn & TF_TRAIT);
+                ++n_moved;
+            }
+        }
+        const uint32_t slot = warp_append(&p.ctr->mv_n, lost);
+        if (lost) {
+            if (slot < p.list_cap) { p.mv_cell[slot] = (uint32_t)cell; p.mv_state[slot] = (uint8_t)loser_state; }
+            else atomicExch(&p.ctr->overflow, 1u);
+        }
+        if (valid) p.tfA[cell] = (uint8_t)out;
+    }
+    if (p.stats && n_moved) atomicAdd(&p.ctr->st_moved, (unsigned long long)n_moved);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_move_retry (sparse, persistent): travel rounds 2..8 (exit_move_fn, :1559-1576) for the
+// losers of round 1.  Three phases per round separated by grid barriers:
+//   request  (:784-872)  probe from the saved direction over blocked = OCC|GHOST, post the claim
+//   response (:881-960)  every claimant evaluates the contest at its target
+//   apply                winners relocate, losers drop their claim
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_move_retry(const __grid_constant__ Params p) {
+    Counters* ctr = p.ctr;
+    unsigned int n = ctr->mv_n;
+    if (n > p.list_cap) n = p.list_cap;
+    if (n == 0) return;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int round = 1; round < 8; ++round) {
+        // ---- request
+        for (unsigned int i = t0; i < n; i += stride) {
+            const uint32_t st = p.mv_state[i];
+            if (!(st & 0x80u)) continue;
+            const uint32_t cell = p.mv_cell[i];
+            const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
+            uint32_t blocked = 0;
+#pragma unroll
+            for (int d = 0; d < 8; ++d)
+                if (__ldcg(p.tfA + nb_local(p, x, y, d)) & (TF_OCC | TF_GHOST)) blocked |= 1u << d;
+            int l = (int)(st & 7u), seq = (int)((st >> 3) & 15u);
+            const int dir = probe(blocked, l, seq);
+            if (dir < 0) {
+                p.mv_state[i] = 0;  // no free space: stays put (:842-846)
+            } else {
+                const uint32_t t = __ldcg(p.tfA + cell);
+                p.tfA[cell] = (uint8_t)((t & (TF_OCC | TF_TRAIT)) | TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT));
+                p.mv_state[i] = (uint8_t)(0x80u | (uint32_t)((dir + 1) & 7) | ((uint32_t)seq << 3));
+                p.mv_aux[i] = (uint8_t)dir;
+            }
+        }
+        grid_sync(ctr->barrier, gridDim.x);
+        // ---- response
+        for (unsigned int i = t0; i < n; i += stride) {
+            if (!(p.mv_state[i] & 0x80u)) continue;
+            const uint32_t cell = p.mv_cell[i];
+            const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
+            const int d = (int)(p.mv_aux[i] & 7u);
+            const uint32_t tx = (x + (uint32_t)DX(d)) & (p.W - 1);
+            const uint32_t ty = (y + (uint32_t)DY(d)) & (p.H - 1);
+            bool win = true, have_key = false;
+            Key mine;
+            for (int j = 0; j < 8; ++j) {
+                if (j == 7 - d) continue;
+                const uint32_t tn = __ldcg(p.tfA + nb_local(p, tx, ty, j));
+                if (!claims_dir(tn, 7 - j)) continue;
+                if (!have_key) { mine = travel_key(p, gcell_of(p, x, y)); have_key = true; }
+                if (key_gt(travel_key(p, nb_gcell(p, tx, ty, j)), mine)) win = false;
+            }
+            p.mv_aux[i] = (uint8_t)((uint32_t)d | (win ? 0x80u : 0u));
+        }
+        grid_sync(ctr->barrier, gridDim.x);
+        // ---- apply
+        unsigned int still = 0;
+        for (unsigned int i = t0; i < n; i += stride) {
+            if (!(p.mv_state[i] & 0x80u)) continue;
+            const uint32_t cell = p.mv_cell[i];
+            const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
+            const uint32_t aux = p.mv_aux[i];
+            const uint32_t t = __ldcg(p.tfA + cell);
+            if (aux & 0x80u) {
+                const uint32_t tgt = nb_local(p, x, y, (int)(aux & 7u));
+                p.E1[tgt] = __ldcg(p.E1 + cell);
+                p.strat[tgt] = __ldcg(p.strat + cell);
+                p.tfA[tgt] = (uint8_t)(TF_OCC | (t & TF_TRAIT));
+                p.tfA[cell] = (uint8_t)TF_GHOST;
+                p.mv_state[i] = 0;
+                if (p.stats) atomicAdd(&ctr->st_moved, 1ull);
+            } else {
+                p.tfA[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
+                ++still;
+            }
+        }
+        if (still) atomicAdd(&ctr->mv_active[round], still);
+        grid_sync(ctr->barrier, gridDim.x);
+        if (__ldcg(&ctr->mv_active[round]) == 0u) break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_repro_claim (dense sweep 3): neighbourhood_update (:975-1031) + first god_go_forth
+// (:1042-1134).  tfA (1-cell halo; GHOSTs are free again) + E1 -> tfB.
+// ------------------------------------------------------------------------------------------
+template <int TW, int TH>
+__global__ void __launch_bounds__(NT) k_repro_claim(const __grid_constant__ Params p) {
+    constexpr int SW = TW + 2;
+    __shared__ uint8_t s_tf[SW * (TH + 2)];
+    const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    load_tile_u8<TW, TH, 1>(p, p.tfA, s_tf, x0, y0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < TW * TH; i += NT) {
+        const int ly = i / TW, lx = i - ly * TW;
+        const int si = (ly + 1) * SW + lx + 1;
+        const uint32_t x = x0 + lx, y = y0 + ly;
+        const size_t cell = ((size_t)y << p.log2W) | x;
+        const uint32_t t = s_tf[si];
+        uint32_t out = 0;
+        if (t & TF_OCC) {
+            out = TF_OCC | (t & TF_TRAIT);
+            if (p.max_children > 0u && p.E1[cell] >= p.reproduce_min_energy) {  // :978-979, :1054
+                uint32_t occ_mask = 0;
+#pragma unroll
+                for (int d = 0; d < 8; ++d)
+                    if (s_tf[si + DY(d) * SW + DX(d)] & TF_OCC) occ_mask |= 1u << d;
+                if (occ_mask != 0xFFu) {  // :1024-1027
+                    const Words w = rng(p, gcell_of(p, x, y), S_REPRO);
+                    int l = (int)(w.y >> 29), seq = 0;  // :1079
+                    const int dir = probe(occ_mask, l, seq);
+                    if (dir >= 0) out |= TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT);
+                }
+            }
+        }
+        p.tfB[cell] = (uint8_t)out;
+    }
+}
+
+// living cost for one agent (environmental_punishment, :1357-1368); returns false if it dies
+__device__ __forceinline__ bool punish(const Params& p, float& e) {
+    e = __fsub_rn(fminf(e, p.max_energy), p.cost_of_living);
+    return e > 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_repro_commit (dense sweep 4): god_multiply round 1 (:1144-1335) + environmental_punishment
+// (:1339-1371) + step_fn's counts (:1405-1419).  tfB (2-cell halo), E1, strat -> tfA, E0, strat.
+// Claim losers are appended to the repro-loser list and their living cost is deferred to
+// k_finalize (a retry round may still charge them the reproduction cost first).
+// ------------------------------------------------------------------------------------------
+template <int TW, int TH>
+__global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Params p) {
+    constexpr int SW = TW + 4;
+    __shared__ uint8_t s_tf[SW * (TH + 4)];
+    __shared__ unsigned int s_bins[16];
+    __shared__ unsigned int s_cnt[3];  // n_old, births, living_deaths
+    const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    if (threadIdx.x < 16) s_bins[threadIdx.x] = 0;
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    load_tile_u8<TW, TH, 2>(p, p.tfB, s_tf, x0, y0);
+    __syncthreads();
+    unsigned int n_old = 0, n_births = 0, n_dead = 0;
+    constexpr int ITERS = (TW * TH + NT - 1) / NT;
+    for (int it = 0; it < ITERS; ++it) {
+        const int i = it * NT + threadIdx.x;
+        const bool valid = i < TW * TH;
+        const int ly = valid ? i / TW : 0, lx = valid ? i - ly * TW : 0;
+        const int si = (ly + 2) * SW + lx + 2;
+        const uint32_t x = x0 + lx, y = y0 + ly;
+        const size_t cell = ((size_t)y << p.log2W) | x;
+        const uint32_t t = valid ? s_tf[si] : 0u;
+        uint32_t out = 0;
+        float e_out = 0.0f;
+        bool lost = false, newborn = false, at_risk = false;
+        uint32_t loser_state = 0;
+        if (t & TF_OCC) {
+            ++n_old;
+            const uint32_t trait = t & TF_TRAIT;
+            float e = p.E1[cell];
+            if (t & TF_CLAIM) {
+                const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
+                const int st = si + DY(d) * SW + DX(d);
+                const uint32_t tx = (x + (uint32_t)DX(d)) & (p.W - 1);
+                const uint32_t ty = (y + (uint32_t)DY(d)) & (p.H - 1);
+                const uint64_t g = gcell_of(p, x, y);
+                bool win = true, have_key = false;
+                Key mine;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j == 7 - d) continue;
+                    const uint32_t tn = s_tf[st + DY(j) * SW + DX(j)];
+                    if (!claims_dir(tn, 7 - j)) continue;
+                    if (!have_key) { mine = repro_key(p, g); have_key = true; }
+                    if (key_gt(repro_key(p, nb_gcell(p, tx, ty, j)), mine)) win = false;
+                }
+                if (win) {
+                    e = __fsub_rn(e, p.reproduce_cost);  // :1211-1213
+                } else {
+                    lost = true;  // stays ATTEMPTING_REPRODUCTION (:1203-1205)
+                    const int s = (int)(rng(p, g, S_REPRO).y >> 29);
+                    loser_state = 0x80u | (uint32_t)((d + 1) & 7) | ((uint32_t)probe_pos(s, d) << 3);
+                }
+            }
+            if (lost) {
+                out = TF_OCC | trait;
+                e_out = e;
+            } else if (punish(p, e)) {
+                out = TF_OCC | trait;
+                e_out = e;
+                at_risk = e <= p.risk_thr;
+                if (p.want_counts) atomicAdd(&s_bins[count_bin(p.strat[cell], trait)], 1u);
+            } else {
+                ++n_dead;
+            }
+        } else if (valid) {
+            int best = -1, ncl = 0;
+            Key bk;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t tn = s_tf[si + DY(j) * SW + DX(j)];
+                if (!claims_dir(tn, 7 - j)) continue;
+                ++ncl;
+                if (ncl == 1) { best = j; continue; }
+                if (ncl == 2) bk = repro_key(p, nb_gcell(p, x, y, best));
+                const Key k = repro_key(p, nb_gcell(p, x, y, j));
+                if (key_gt(k, bk)) { bk = k; best = j; }
+            }
+            if (best >= 0) {  // a child is born here (:1216-1328)
+                const uint32_t src = nb_local(p, x, y, best);
+                const uint32_t tn = s_tf[si + DY(best) * SW + DX(best)];
+                const float pe = __fsub_rn(p.E1[src], p.reproduce_cost);
+                uint32_t cs;
+                make_child(p, nb_gcell(p, x, y, best), p.strat[src], tn & TF_TRAIT, pe, e_out, cs);
+                p.strat[cell] = (uint8_t)cs;
+                out = TF_OCC | TF_NEWBORN | (tn & TF_TRAIT);
+                newborn = true;
+                ++n_births;
+            }
+        }
+        uint32_t slot = warp_append(&p.ctr->rp_n, lost);
+        if (lost) {
+            if (slot < p.list_cap) { p.rp_cell[slot] = (uint32_t)cell; p.rp_state[slot] = (uint8_t)loser_state; }
+            else atomicExch(&p.ctr->overflow, 1u);
+        }
+        slot = warp_append(&p.ctr->nb_n, newborn);
+        if (newborn) {
+            if (slot < p.list_cap) p.nb_cell[slot] = (uint32_t)cell;
+            else atomicExch(&p.ctr->overflow, 1u);
+        }
+        slot = warp_append(&p.ctr->risk_next_n, at_risk);
+        if (at_risk) {
+            if (slot < p.list_cap) p.risk_next[slot] = (uint32_t)cell;
+            else atomicExch(&p.ctr->overflow, 1u);
+        }
+        if (valid) {
+            p.tfA[cell] = (uint8_t)out;
+            p.E0[cell] = e_out;
+        }
+    }
+    if (n_old) atomicAdd(&s_cnt[0], n_old);
+    if (n_births) atomicAdd(&s_cnt[1], n_births);
+    if (n_dead) atomicAdd(&s_cnt[2], n_dead);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_cnt[0]) atomicAdd(&p.ctr->n_old, (unsigned long long)s_cnt[0]);
+        if (s_cnt[1]) atomicAdd(&p.ctr->births, (unsigned long long)s_cnt[1]);
+        if (s_cnt[2]) atomicAdd(&p.ctr->living_deaths, (unsigned long long)s_cnt[2]);
+    }
+    if (p.want_counts && threadIdx.x < 16 && s_bins[threadIdx.x])
+        atomicAdd(&p.ctr->bins[threadIdx.x], (unsigned long long)s_bins[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_repro_retry (sparse, persistent): reproduction rounds 2..8 (exit_god_fn, :1607-1627).
+// Runs only while the population (olds + births so far) does not exceed max_agents.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_repro_retry(const __grid_constant__ Params p) {
+    Counters* ctr = p.ctr;
+    unsigned int n = ctr->rp_n;
+    if (n > p.list_cap) n = p.list_cap;
+    if (n == 0) return;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int round = 1; round < 8; ++round) {
+        // overpopulated gate, evaluated after every round (:1616, :1621-1625)
+        if (__ldcg(&ctr->n_old) + __ldcg(&ctr->births) > p.max_agents) break;
+        // ---- go forth
+        for (unsigned int i = t0; i < n; i += stride) {
+            const uint32_t st = p.rp_state[i];
+            if (!(st & 0x80u)) continue;
+            const uint32_t cell = p.rp_cell[i];
+            const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
+            uint32_t blocked = 0;
+#pragma unroll
+            for (int d = 0; d < 8; ++d)
+                if (__ldcg(p.tfA + nb_local(p, x, y, d)) & TF_OCC) blocked |= 1u << d;
+            int l = (int)(st & 7u), seq = (int)((st >> 3) & 15u);
+            const int dir = probe(blocked, l, seq);  // also covers reproduce_sequence >= 8 (:1067)
+            if (dir < 0) {
+                p.rp_state[i] = 0x40u;  // REPRODUCTION_IMPOSSIBLE (:1104-1108); living cost still due
+            } else {
+                const uint32_t t = __ldcg(p.tfA + cell);
+                p.tfA[cell] = (uint8_t)((t & (TF_OCC | TF_TRAIT)) | TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT));
+                p.rp_state[i] = (uint8_t)(0x80u | (uint32_t)((dir + 1) & 7) | ((uint32_t)seq << 3));
+                p.rp_aux[i] = (uint8_t)dir;
+            }
+        }
+        grid_sync(ctr->barrier, gridDim.x);
+        // ---- multiply: contest
+        for (unsigned int i = t0; i < n; i += stride) {
+            if (!(p.rp_state[i] & 0x80u)) continue;
+            const uint32_t cell = p.rp_cell[i];
+            const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
+            const int d = (int)(p.rp_aux[i] & 7u);
+            const uint32_t tx = (x + (uint32_t)DX(d)) & (p.W - 1);
+            const uint32_t ty = (y + (uint32_t)DY(d)) & (p.H - 1);
+            bool win = true, have_key = false;
+            Key mine;
+            for (int j = 0; j < 8; ++j) {
+                if (j == 7 - d) continue;
+                const uint32_t tn = __ldcg(p.tfA + nb_local(p, tx, ty, j));
+                if (!claims_dir(tn, 7 - j)) continue;
+                if (!have_key) { mine = repro_key(p, gcell_of(p, x, y)); have_key = true; }
+                if (key_gt(repro_key(p, nb_gcell(p, tx, ty, j)), mine)) win = false;
+            }
+            p.rp_aux[i] = (uint8_t)((uint32_t)d | (win ? 0x80u : 0u));
+        }
+        grid_sync(ctr->barrier, gridDim.x);
+        // ---- multiply: apply
+        unsigned int still = 0, born = 0;
+        for (unsigned int i = t0; i < n; i += stride) {
+            if (!(p.rp_state[i] & 0x80u)) continue;
+            const uint32_t cell = p.rp_cell[i];
+            const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
+            const uint32_t aux = p.rp_aux[i];
+            const uint32_t t = __ldcg(p.tfA + cell);
+            p.tfA[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
+            if (aux & 0x80u) {
+                const uint32_t tgt = nb_local(p, x, y, (int)(aux & 7u));
+                const float pe = __fsub_rn(__ldcg(p.E0 + cell), p.reproduce_cost);
+                p.E0[cell] = pe;
+                float ce;
+                uint32_t cs;
+                make_child(p, gcell_of(p, x, y), __ldcg(p.strat + cell), t & TF_TRAIT, pe, ce, cs);
+                p.E0[tgt] = ce;
+                p.strat[tgt] = (uint8_t)cs;
+                p.tfA[tgt] = (uint8_t)(TF_OCC | TF_NEWBORN | (t & TF_TRAIT));
+                const unsigned int slot = atomicAdd(&ctr->nb_n, 1u);
+                if (slot < p.list_cap) p.nb_cell[slot] = tgt;
+                else atomicExch(&ctr->overflow, 1u);
+                p.rp_state[i] = 0x40u;  // REPRODUCTION_COMPLETE; living cost still due
+                ++born;
+            } else {
+                ++still;
+            }
+        }
+        if (born) atomicAdd(&ctr->births, (unsigned long long)born);
+        if (still) atomicAdd(&ctr->rp_active[round], still);
+        grid_sync(ctr->barrier, gridDim.x);
+        if (__ldcg(&ctr->rp_active[round]) == 0u) break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_finalize (sparse, persistent): the carrying-capacity cull, the deferred living cost of
+// the repro-loser list, the newborns' counts and the bookkeeping for the next step.
+// Cull (replaces the list-index rule :1343/:1354, SURVEY B-4): if olds + births exceed
+// max_agents, only the K = max_agents - olds newborns with the highest (Philox cull priority,
+// cell) keys survive.  The K-th largest 64-bit key is found exactly by an 8-pass radix select.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Params p) {
+    Counters* ctr = p.ctr;
+    __shared__ unsigned int s_hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned long long s_krem;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int nb = ctr->nb_n;
+    if (nb > p.list_cap) nb = p.list_cap;
+    unsigned int nrp = ctr->rp_n;
+    if (nrp > p.list_cap) nrp = p.list_cap;
+    const unsigned long long n_old = ctr->n_old;
+    const unsigned long long births = ctr->births;
+    // ---- cull threshold
+    bool cull = n_old + births > p.max_agents;
+    unsigned long long keep = 0;
+    unsigned long long tau = 0;  // survive iff key >= tau
+    if (cull) {
+        keep = p.max_agents > n_old ? p.max_agents - n_old : 0ull;
+        if (keep >= births) cull = false;
+    }
+    if (cull && keep > 0) {
+        if (threadIdx.x == 0) { s_prefix = 0ull; s_krem = keep; }
+        for (int pass = 0; pass < 8; ++pass) {
+            const int shift = 56 - 8 * pass;
+            if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
+            __syncthreads();
+            const unsigned long long prefix = s_prefix;
+            for (unsigned int i = t0; i < nb; i += stride) {
+                const uint32_t cell = p.nb_cell[i];
+                uint32_t prio;
+                const uint64_t g = gcell_of(p, cell & (p.W - 1), cell >> p.log2W);
+                if (pass == 0) { prio = rng(p, g, S_CULL).x; p.nb_prio[i] = prio; }
+                else prio = p.nb_prio[i];
+                const unsigned long long key = ((unsigned long long)prio << 32) | (uint32_t)g;
+                if (pass == 0 || (key >> (shift + 8)) == prefix)
+                    atomicAdd(&s_hist[(unsigned int)(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x < 256 && s_hist[threadIdx.x])
+                atomicAdd(&ctr->hist[pass][threadIdx.x], s_hist[threadIdx.x]);
+            grid_sync(ctr->barrier, gridDim.x);
+            if (threadIdx.x == 0) {
+                unsigned long long krem = s_krem, cum = 0;
+                int digit = 0;
+                for (int b = 255; b >= 0; --b) {
+                    const unsigned long long h = __ldcg(&ctr->hist[pass][b]);
+                    if (cum + h >= krem) { digit = b; break; }
+                    cum += h;
+                }
+                s_krem = krem - cum;
+                s_prefix = (prefix << 8) | (unsigned long long)digit;
+            }
+            __syncthreads();
+        }
+        tau = s_prefix;
+    }
+    // ---- newborns: cull or admit (no living cost in the birth step, :1343)
+    unsigned int n_culled = 0;
+    for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nb; i0 += stride) {
+        const unsigned int i = i0 + threadIdx.x;
+        bool at_risk = false;
+        if (i < nb) {
+            const uint32_t cell = p.nb_cell[i];
+            bool survive = true;
+            if (cull) {
+                if (keep == 0) survive = false;
+                else {
+                    const uint64_t g = gcell_of(p, cell & (p.W - 1), cell >> p.log2W);
+                    const unsigned long long key = ((unsigned long long)p.nb_prio[i] << 32) | (uint32_t)g;
+                    survive = key >= tau;
+                }
+            }
+            if (survive) {
+                const uint32_t t = __ldcg(p.tfA + cell);
+                p.tfA[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
+                at_risk = __ldcg(p.E0 + cell) <= p.risk_thr;
+                if (p.want_counts) atomicAdd(&ctr->bins[count_bin(__ldcg(p.strat + cell), t & TF_TRAIT)], 1ull);
+            } else {
+                p.tfA[cell] = 0;
+                p.E0[cell] = 0.0f;
+                ++n_culled;
+            }
+        }
+        const uint32_t slot = warp_append(&ctr->risk_next_n, at_risk);
+        if (at_risk) {
+            if (slot < p.list_cap) p.risk_next[slot] = p.nb_cell[i];
+            else atomicExch(&ctr->overflow, 1u);
+        }
+    }
+    if (n_culled) atomicAdd(&ctr->culled, (unsigned long long)n_culled);
+    // ---- deferred living cost of the parents that lost round 1 (:1357-1368)
+    unsigned int n_dead = 0;
+    for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nrp; i0 += stride) {
+        const unsigned int i = i0 + threadIdx.x;
+        bool at_risk = false;
+        if (i < nrp) {
+            const uint32_t cell = p.rp_cell[i];
+            const uint32_t t = __ldcg(p.tfA + cell);
+            float e = __ldcg(p.E0 + cell);
+            if (punish(p, e)) {
+                p.E0[cell] = e;
+                p.tfA[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
+                at_risk = e <= p.risk_thr;
+                if (p.want_counts) atomicAdd(&ctr->bins[count_bin(__ldcg(p.strat + cell), t & TF_TRAIT)], 1ull);
+            } else {
+                p.E0[cell] = 0.0f;
+                p.tfA[cell] = 0;
+                ++n_dead;
+            }
+        }
+        const uint32_t slot = warp_append(&ctr->risk_next_n, at_risk);
+        if (at_risk) {
+            if (slot < p.list_cap) p.risk_next[slot] = p.rp_cell[i];
+            else atomicExch(&ctr->overflow, 1u);
+        }
+    }
+    if (n_dead) atomicAdd(&ctr->living_deaths, (unsigned long long)n_dead);
+    grid_sync(ctr->barrier, gridDim.x);
+    // ---- bookkeeping (one thread)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long culled = __ldcg(&ctr->culled);
+        const unsigned long long ld = __ldcg(&ctr->living_deaths);
+        const unsigned long long b = __ldcg(&ctr->births);
+        ctr->n_agents = n_old + b - culled - ld;
+        unsigned int rn = __ldcg(&ctr->risk_next_n);
+        ctr->risk_n = rn > p.list_cap ? p.list_cap : rn;
+        if (p.want_counts)
+            for (int k = 0; k < 16; ++k) ctr->last_bins[k] = __ldcg(&ctr->bins[k]);
+        unsigned long long* s = ctr->last_stats;
+        s[0] = ctr->agents_start; s[1] = ctr->n_agents;
+        s[2] = __ldcg(&ctr->st_play_deaths); s[3] = __ldcg(&ctr->st_movers);
+        s[4] = __ldcg(&ctr->st_moved); s[5] = __ldcg(&ctr->st_travel_deaths);
+        s[6] = b; s[7] = culled; s[8] = ld;
+        s[9] = rn; s[10] = __ldcg(&ctr->mv_n); s[11] = __ldcg(&ctr->rp_n);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_scan_state: rebuild the at-risk list, the population count and the strategy counts from the
+// bound planes (after init or after the caller wrote the planes); canonicalises tf.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_scan_state(const __grid_constant__ Params p, size_t cells) {
+    __shared__ unsigned int s_bins[16];
+    __shared__ unsigned int s_n;
+    if (threadIdx.x < 16) s_bins[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    unsigned int n = 0;
+    const size_t stride = (size_t)gridDim.x * NT;
+    for (size_t i0 = (size_t)blockIdx.x * NT; i0 < cells; i0 += stride) {
+        const size_t i = i0 + threadIdx.x;
+        bool at_risk = false;
+        if (i < cells) {
+            const uint32_t t = p.tfA[i];
+            if (t & TF_OCC) {
+                ++n;
+                p.tfA[i] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
+                at_risk = p.E0[i] <= p.risk_thr;
+                atomicAdd(&s_bins[count_bin(p.strat[i], t & TF_TRAIT)], 1u);
+            } else {
+                p.tfA[i] = 0;
+                p.E0[i] = 0.0f;
+            }
+        }
+        const uint32_t slot = warp_append(&p.ctr->risk_next_n, at_risk);
+        if (at_risk) {
+            if (slot < p.list_cap) p.risk_next[slot] = (uint32_t)i;
+            else atomicExch(&p.ctr->overflow, 1u);
+        }
+    }
+    if (n) atomicAdd(&s_n, n);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_n) atomicAdd(&p.ctr->n_old, (unsigned long long)s_n);
+    if (threadIdx.x < 16 && s_bins[threadIdx.x])
+        atomicAdd(&p.ctr->bins[threadIdx.x], (unsigned long long)s_bins[threadIdx.x]);
+}
+__global__ void k_scan_finish(Counters* ctr, uint32_t list_cap) {
+    if (threadIdx.x == 0) {
+        ctr->n_agents = ctr->n_old;
+        const unsigned int rn = ctr->risk_next_n;
+        ctr->risk_n = rn > list_cap ? list_cap : rn;
+        for (int k = 0; k < 16; ++k) ctr->last_bins[k] = ctr->bins[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Population init (init_fn, :1423-1524) on the GPU.  Exactly n cells -- those with the n
+// smallest (placement priority, cell) keys -- are occupied: an 8-pass radix select over all
+// cells finds the n-th smallest key, then one sweep writes the agents.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long place_key(const Params& p, uint64_t g) {
+    return ((unsigned long long)rng_init(p, g, I_PLACE).x << 32) | (uint32_t)g;
+}
+// one histogram pass; prefix/k state lives in ctr->hist bookkeeping done by k_init_pick
+__global__ void __launch_bounds__(NT) k_init_hist(const __grid_constant__ Params p, size_t cells, int pass,
+                                                   unsigned long long prefix) {
+    __shared__ unsigned int s_hist[256];
+    s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int shift = 56 - 8 * pass;
+    const size_t stride = (size_t)gridDim.x * NT;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < cells; i += stride) {
+        const uint64_t g = gcell_of(p, (uint32_t)(i & (p.W - 1)), (uint32_t)(i >> p.log2W));
+        const unsigned long long key = place_key(p, g);
+        if (pass == 0 || (key >> (shift + 8)) == prefix)
+            atomicAdd(&s_hist[(unsigned int)(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (s_hist[threadIdx.x]) atomicAdd(&p.ctr->hist[pass][threadIdx.x], s_hist[threadIdx.x]);
+}
+__global__ void __launch_bounds__(NT) k_init_write(const __grid_constant__ Params p, size_t cells,
+                                                    unsigned long long tau, int none) {
+    const size_t stride = (size_t)gridDim.x * NT;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < cells; i += stride) {
+        const uint64_t g = gcell_of(p, (uint32_t)(i & (p.W - 1)), (uint32_t)(i >> p.log2W));
+        const Words w = rng_init(p, g, I_PLACE);
+        const unsigned long long key = ((unsigned long long)w.x << 32) | (uint32_t)g;
+        uint8_t tf = 0, st = 0;
+        float e = 0.0f;
+        if (!none && key <= tau) {
+            const uint32_t trait = w.y >> 30;  // :1467
+            const float z = normal_from_words(rng_init(p, g, I_ENERGY));
+            e = __fadd_rn(__fmul_rn(z, p.e_sigma), p.e_mu);  // :1460-1462
+            e = fmaxf(e, p.e_min);
+            if (p.max_energy > 0.0f) e = fminf(e, p.max_energy);  // :1463-1464
+            const Words sw = rng_init(p, g, I_STRAT);
+            const uint32_t words[4] = {sw.x, sw.y, sw.z, sw.w};
+            uint32_t draw[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                draw[k] = (uint32_t)((unsigned long long)words[k] >= p.strat_thr[0]) +
+                          (uint32_t)((unsigned long long)words[k] >= p.strat_thr[1]) +
+                          (uint32_t)((unsigned long long)words[k] >= p.strat_thr[2]);
+            uint32_t s;
+            if (p.pure) s = draw[0] * 0x55u;                                   // :1473-1477
+            else if (p.per_trait) s = draw[0] | (draw[1] << 2) | (draw[2] << 4) | (draw[3] << 6);  // :1478-1482
+            else s = ((draw[1] * 0x55u) & ~(3u << (2 * trait))) | (draw[0] << (2 * trait));       // :1483-1497
+            st = (uint8_t)s;
+            tf = (uint8_t)(TF_OCC | trait);
+        }
+        p.tfA[i] = tf;
+        p.strat[i] = st;
+        p.E0[i] = e;
+    }
+}
+
+// Philox known-answer probe for the tests
+__global__ void k_philox_kat(const uint32_t* in, uint32_t* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const Words w = philox4x32_10(in[6 * i], in[6 * i + 1], in[6 * i + 2], in[6 * i + 3], in[6 * i + 4], in[6 * i + 5]);
+        out[4 * i] = w.x; out[4 * i + 1] = w.y; out[4 * i + 2] = w.z; out[4 * i + 3] = w.w;
+    }
+}
+
+}  // namespace pd

@@ -1,0 +1,456 @@
+// libpdabm.so -- host side of the C ABI declared in include/pdabm.h.
+//
+// Builds the kernel parameter block from pd_config (the reference's environment properties,
+// /root/reference/src/model.py:1678-1743), owns the scratch planes and sparse lists, and
+// issues the kernels of one model step in the order of the reference's main layers
+// (model.py:2140-2163).  No torch types, no exceptions across the boundary.
+#include "../../include/pdabm.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+
+#include "pd_kernels.cuh"
+
+using namespace pd;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(PD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+unsigned long long prob_threshold(float p) {
+    // P(event) = p  <=>  (u32 word) < threshold  (same arithmetic as oracle.prob_threshold)
+    const double v = (double)p * 4294967296.0;
+    if (!(v > 0.0)) return 0ull;
+    const double f = floor(v);
+    return f >= 4294967296.0 ? 4294967296ull : (unsigned long long)f;
+}
+
+struct HostOut {  // pinned staging for read-backs
+    unsigned long long bins[16];
+    unsigned long long stats[12];
+    unsigned long long n_agents;
+    unsigned int overflow;
+    unsigned int hist[256];
+};
+
+}  // namespace
+
+struct pd_sim {
+    pd_config cfg;
+    Params P;
+    size_t cells;
+    bool bound, ready;
+    uint32_t step;
+    int risk_cur;
+    uint32_t* risk[2];
+    int n_sms;
+    int sparse_ctas, sparse_threads;
+    bool big_tiles;
+    dim3 grid;
+    HostOut* h;  // pinned
+    bool lists_allocated;
+};
+
+namespace {
+
+int alloc_lists(pd_sim* s, uint64_t n_agents_hint) {
+    if (s->lists_allocated) {
+        if (n_agents_hint + 1024 <= s->P.list_cap || s->P.list_cap == s->cells) return PD_OK;
+        // grow: free and reallocate
+        cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.risk_roll);
+        cudaFree(s->P.mv_cell); cudaFree(s->P.mv_state); cudaFree(s->P.mv_aux);
+        cudaFree(s->P.rp_cell); cudaFree(s->P.rp_state); cudaFree(s->P.rp_aux);
+        cudaFree(s->P.nb_cell); cudaFree(s->P.nb_prio);
+        s->lists_allocated = false;
+    }
+    uint64_t cap = s->cfg.max_agents > n_agents_hint ? s->cfg.max_agents : n_agents_hint;
+    cap += 1024;
+    if (cap > s->cells) cap = s->cells;
+    s->P.list_cap = (uint32_t)cap;
+    CK(cudaMalloc(&s->risk[0], cap * 4));
+    CK(cudaMalloc(&s->risk[1], cap * 4));
+    CK(cudaMalloc(&s->P.risk_e, cap * 4));
+    CK(cudaMalloc(&s->P.risk_roll, cap * 4));
+    CK(cudaMalloc(&s->P.mv_cell, cap * 4));
+    CK(cudaMalloc(&s->P.mv_state, cap));
+    CK(cudaMalloc(&s->P.mv_aux, cap));
+    CK(cudaMalloc(&s->P.rp_cell, cap * 4));
+    CK(cudaMalloc(&s->P.rp_state, cap));
+    CK(cudaMalloc(&s->P.rp_aux, cap));
+    CK(cudaMalloc(&s->P.nb_cell, cap * 4));
+    CK(cudaMalloc(&s->P.nb_prio, cap * 4));
+    s->lists_allocated = true;
+    return PD_OK;
+}
+
+template <typename K>
+int launch_sparse(pd_sim* s, K kernel, cudaStream_t st) {
+    void* args[] = {(void*)&s->P};
+    if (s->sparse_ctas == 1) {
+        CK(cudaLaunchKernel((const void*)kernel, dim3(1), dim3(s->sparse_threads), args, 0, st));
+    } else {
+        CK(cudaLaunchCooperativeKernel((const void*)kernel, dim3(s->sparse_ctas), dim3(s->sparse_threads),
+                                       args, 0, st));
+    }
+    return PD_OK;
+}
+
+int run_scan(pd_sim* s, cudaStream_t st) {
+    s->P.risk_cur = s->risk[s->risk_cur];
+    s->P.risk_next = s->risk[s->risk_cur ^ 1];
+    k_begin_step<<<1, 256, 0, st>>>(s->P.ctr);
+    const int blocks = (int)((s->cells + NT - 1) / NT < (size_t)(s->n_sms * 16) ? (s->cells + NT - 1) / NT
+                                                                                  : (size_t)(s->n_sms * 16));
+    k_scan_state<<<blocks, NT, 0, st>>>(s->P, s->cells);
+    k_scan_finish<<<1, 32, 0, st>>>(s->P.ctr, s->P.list_cap);
+    CK(cudaGetLastError());
+    s->risk_cur ^= 1;
+    return PD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pd_last_error(void) { return g_err.c_str(); }
+int pd_abi_version(void) { return PDABM_ABI_VERSION; }
+
+int pd_default_config(pd_config* c, uint32_t width) {
+    if (!c) return fail(PD_ERR_INVALID, "cfg is NULL");
+    memset(c, 0, sizeof *c);
+    c->struct_size = (uint32_t)sizeof *c;
+    c->width = width;
+    c->row0 = 0;
+    c->rows = width;
+    c->seed = 12345;
+    const uint64_t cells = (uint64_t)width * width;
+    c->max_agents = (uint64_t)((double)cells * 0.5);  // model.py:49
+    c->payoff_cc = 3.0f; c->payoff_dc = 5.0f; c->payoff_cd = -1.0f; c->payoff_dd = 0.0f;
+    c->env_noise = 0.0f;
+    c->cost_of_living = 1.0f;
+    c->travel_cost = 0.5f;
+    c->reproduce_min_energy = 100.0f;
+    c->reproduce_cost = 50.0f;
+    c->reproduction_inheritence = 0.0f;
+    c->init_energy_mu = 50.0f; c->init_energy_sigma = 10.0f; c->init_energy_min = 5.0f;
+    c->max_energy = 150.0f;
+    c->mutation_rate = 0.0f;
+    for (int i = 0; i < 4; ++i) c->strategy_weights[i] = 0.25f;
+    c->strategy_pure = 0; c->strategy_per_trait = 0; c->max_children_per_step = 1;
+    c->collect_stats = 0;
+    c->device = 0;
+    c->sparse_ctas = 0;
+    return PD_OK;
+}
+
+int pd_create(const pd_config* cfg, pd_sim** out) {
+    if (!cfg || !out) return fail(PD_ERR_INVALID, "NULL argument");
+    if (cfg->struct_size != sizeof(pd_config))
+        return fail(PD_ERR_INVALID, "pd_config.struct_size %u != %zu (ABI mismatch)", cfg->struct_size, sizeof(pd_config));
+    const uint32_t W = cfg->width;
+    if (W < 16 || (W & (W - 1))) return fail(PD_ERR_INVALID, "width must be a power of two >= 16 (got %u)", W);
+    if (W > 65536) return fail(PD_ERR_INVALID, "width > 65536 not supported");
+    if (cfg->row0 != 0 || cfg->rows != W)
+        return fail(PD_ERR_INVALID, "row-slab decomposition (row0=%u rows=%u) is not built yet: pass row0=0, rows=width", cfg->row0, cfg->rows);
+    double wsum = 0;
+    for (int i = 0; i < 4; ++i) {
+        if (!(cfg->strategy_weights[i] >= 0.0f)) return fail(PD_ERR_INVALID, "strategy_weights must be >= 0");
+        wsum += (double)cfg->strategy_weights[i];
+    }
+    if (!(wsum > 0)) return fail(PD_ERR_INVALID, "strategy_weights sum to 0");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(PD_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+    CK(cudaSetDevice(cfg->device));
+    pd_sim* s = new pd_sim();
+    memset(s, 0, sizeof *s);
+    s->cfg = *cfg;
+    s->cells = (size_t)cfg->rows * W;
+    Params& P = s->P;
+    P.W = W; P.H = cfg->rows; P.row0 = cfg->row0;
+    P.log2W = 0;
+    while ((1u << P.log2W) < W) ++P.log2W;
+    P.k0 = (uint32_t)cfg->seed; P.k1 = (uint32_t)(cfg->seed >> 32);
+    P.pay[0] = cfg->payoff_dd; P.pay[1] = cfg->payoff_dc; P.pay[2] = cfg->payoff_cd; P.pay[3] = cfg->payoff_cc;
+    P.max_energy = cfg->max_energy; P.travel_cost = cfg->travel_cost; P.cost_of_living = cfg->cost_of_living;
+    P.reproduce_min_energy = cfg->reproduce_min_energy; P.reproduce_cost = cfg->reproduce_cost;
+    P.inherit = cfg->reproduction_inheritence;
+    P.e_mu = cfg->init_energy_mu; P.e_sigma = cfg->init_energy_sigma; P.e_min = cfg->init_energy_min;
+    P.mutation_rate = cfg->mutation_rate;
+    P.noise_thr = prob_threshold(cfg->env_noise);
+    P.mut_thr = prob_threshold(cfg->mutation_rate);
+    double cum = 0;
+    for (int i = 0; i < 3; ++i) {
+        cum += (double)cfg->strategy_weights[i];
+        const double f = floor(cum / wsum * 4294967296.0);
+        P.strat_thr[i] = f >= 4294967296.0 ? 4294967296ull : (unsigned long long)f;
+    }
+    float m = 0.0f;
+    for (int i = 0; i < 4; ++i) m = fminf(m, P.pay[i]);
+    // an agent above this energy cannot die during the (at most 8) games of one step
+    P.risk_thr = m < 0.0f ? (float)(8.0 * fabs((double)m) * 1.0001 + 1e-3) : -1.0f;
+    P.max_agents = cfg->max_agents;
+    P.pure = cfg->strategy_pure ? 1u : 0u;
+    P.per_trait = cfg->strategy_per_trait ? 1u : 0u;
+    P.max_children = cfg->max_children_per_step;
+    P.stats = cfg->collect_stats ? 1u : 0u;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    s->n_sms = prop.multiProcessorCount;
+    s->big_tiles = W >= 128;
+    s->grid = s->big_tiles ? dim3(W / 128, cfg->rows / 16) : dim3(W / 16, cfg->rows / 16);
+    if (cfg->sparse_ctas > 0) s->sparse_ctas = cfg->sparse_ctas;
+    else s->sparse_ctas = s->cells <= ((size_t)1 << 22) ? 1 : s->n_sms;
+    if (s->sparse_ctas > 1 && !prop.cooperativeLaunch) s->sparse_ctas = 1;
+    s->sparse_threads = s->sparse_ctas == 1 ? 1024 : 512;
+    if (s->sparse_ctas > s->n_sms * 2) s->sparse_ctas = s->n_sms * 2;
+    P.sparse_ctas = (uint32_t)s->sparse_ctas;
+    CK(cudaMalloc(&P.E1, s->cells * sizeof(float)));
+    CK(cudaMalloc(&P.tfB, s->cells));
+    CK(cudaMalloc(&P.ctr, sizeof(Counters)));
+    CK(cudaMemset(P.ctr, 0, sizeof(Counters)));
+    CK(cudaMallocHost(&s->h, sizeof(HostOut)));
+    memset(s->h, 0, sizeof(HostOut));
+    *out = s;
+    return PD_OK;
+}
+
+int pd_destroy(pd_sim* s) {
+    if (!s) return PD_OK;
+    cudaSetDevice(s->cfg.device);
+    cudaDeviceSynchronize();
+    cudaFree(s->P.E1); cudaFree(s->P.tfB); cudaFree(s->P.ctr);
+    if (s->lists_allocated) {
+        cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.risk_roll);
+        cudaFree(s->P.mv_cell); cudaFree(s->P.mv_state); cudaFree(s->P.mv_aux);
+        cudaFree(s->P.rp_cell); cudaFree(s->P.rp_state); cudaFree(s->P.rp_aux);
+        cudaFree(s->P.nb_cell); cudaFree(s->P.nb_prio);
+    }
+    cudaFreeHost(s->h);
+    delete s;
+    return PD_OK;
+}
+
+int pd_bind_planes(pd_sim* s, float* energy, uint8_t* strat, uint8_t* tf) {
+    if (!s || !energy || !strat || !tf) return fail(PD_ERR_INVALID, "NULL argument");
+    cudaPointerAttributes a;
+    const void* ptrs[3] = {energy, strat, tf};
+    for (int i = 0; i < 3; ++i) {
+        CK(cudaPointerGetAttributes(&a, ptrs[i]));
+        if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged)
+            return fail(PD_ERR_INVALID, "plane %d is not device memory", i);
+    }
+    s->P.E0 = energy; s->P.strat = strat; s->P.tfA = tf;
+    s->bound = true;
+    s->ready = false;
+    return PD_OK;
+}
+
+int pd_sync_state(pd_sim* s, void* stream) {
+    if (!s || !s->bound) return fail(PD_ERR_STATE, "planes not bound");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(s->cfg.device));
+    if (!s->lists_allocated) {
+        int rc = alloc_lists(s, 0);
+        if (rc) return rc;
+    }
+    int rc = run_scan(s, st);
+    if (rc) return rc;
+    // make sure the lists are large enough for the population actually found
+    CK(cudaMemcpyAsync(&s->h->n_agents, &s->P.ctr->n_agents, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (s->h->n_agents + 1024 > s->P.list_cap && s->P.list_cap < s->cells) {
+        rc = alloc_lists(s, s->h->n_agents);
+        if (rc) return rc;
+        rc = run_scan(s, st);
+        if (rc) return rc;
+    }
+    s->ready = true;
+    return PD_OK;
+}
+
+int pd_init_population(pd_sim* s, uint64_t n_agents, void* stream) {
+    if (!s || !s->bound) return fail(PD_ERR_STATE, "planes not bound");
+    if (n_agents > s->cells) return fail(PD_ERR_INVALID, "n_agents %llu > cells %zu", (unsigned long long)n_agents, s->cells);
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(s->cfg.device));
+    int rc = alloc_lists(s, n_agents);
+    if (rc) return rc;
+    const int blocks = (int)((s->cells + NT - 1) / NT < (size_t)(s->n_sms * 16) ? (s->cells + NT - 1) / NT
+                                                                                  : (size_t)(s->n_sms * 16));
+    unsigned long long tau = 0;
+    const int none = n_agents == 0;
+    if (n_agents > 0 && n_agents < s->cells) {
+        // n-th SMALLEST (priority, cell) key by an 8-pass radix select (model.py:1438-1450 restated)
+        k_begin_step<<<1, 256, 0, st>>>(s->P.ctr);
+        unsigned long long prefix = 0, krem = n_agents;
+        for (int pass = 0; pass < 8; ++pass) {
+            k_init_hist<<<blocks, NT, 0, st>>>(s->P, s->cells, pass, prefix);
+            CK(cudaMemcpyAsync(s->h->hist, s->P.ctr->hist[pass], sizeof s->h->hist, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            unsigned long long cum = 0;
+            int digit = 255;
+            for (int b = 0; b < 256; ++b) {
+                if (cum + s->h->hist[b] >= krem) { digit = b; break; }
+                cum += s->h->hist[b];
+            }
+            krem -= cum;
+            prefix = (prefix << 8) | (unsigned long long)digit;
+        }
+        tau = prefix;
+    } else if (n_agents == s->cells) {
+        tau = ~0ull;
+    }
+    k_init_write<<<blocks, NT, 0, st>>>(s->P, s->cells, tau, none);
+    CK(cudaGetLastError());
+    s->step = 0;
+    rc = run_scan(s, st);
+    if (rc) return rc;
+    s->ready = true;
+    return PD_OK;
+}
+
+int pd_step(pd_sim* s, uint32_t n_steps, void* stream, int want_counts) {
+    if (!s || !s->ready) return fail(PD_ERR_STATE, "pd_step before pd_init_population / pd_sync_state");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(s->cfg.device));
+    for (uint32_t k = 0; k < n_steps; ++k) {
+        Params& P = s->P;
+        P.step = s->step;
+        P.want_counts = (want_counts && k + 1 == n_steps) ? 1u : 0u;
+        P.risk_cur = s->risk[s->risk_cur];
+        P.risk_next = s->risk[s->risk_cur ^ 1];
+        k_begin_step<<<1, 256, 0, st>>>(P.ctr);
+        int rc = launch_sparse(s, k_risk_resolve, st);
+        if (rc) return rc;
+        if (s->big_tiles) {
+            k_play_travel<128, 16><<<s->grid, NT, 0, st>>>(P);
+            k_move_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
+        } else {
+            k_play_travel<16, 16><<<s->grid, NT, 0, st>>>(P);
+            k_move_commit<16, 16><<<s->grid, NT, 0, st>>>(P);
+        }
+        rc = launch_sparse(s, k_move_retry, st);
+        if (rc) return rc;
+        if (s->big_tiles) {
+            k_repro_claim<128, 16><<<s->grid, NT, 0, st>>>(P);
+            k_repro_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
+        } else {
+            k_repro_claim<16, 16><<<s->grid, NT, 0, st>>>(P);
+            k_repro_commit<16, 16><<<s->grid, NT, 0, st>>>(P);
+        }
+        rc = launch_sparse(s, k_repro_retry, st);
+        if (rc) return rc;
+        rc = launch_sparse(s, k_finalize, st);
+        if (rc) return rc;
+        s->risk_cur ^= 1;
+        s->step += 1;
+    }
+    CK(cudaGetLastError());
+    return PD_OK;
+}
+
+static int read_back(pd_sim* s, cudaStream_t st) {
+    CK(cudaSetDevice(s->cfg.device));
+    Counters* c = s->P.ctr;
+    CK(cudaMemcpyAsync(s->h->bins, c->last_bins, sizeof s->h->bins, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s->h->stats, c->last_stats, sizeof s->h->stats, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&s->h->n_agents, &c->n_agents, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&s->h->overflow, &c->overflow, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (s->h->overflow)
+        return fail(PD_ERR_OVERFLOW, "a sparse list overflowed its capacity (%u entries); results are invalid", s->P.list_cap);
+    return PD_OK;
+}
+
+int pd_read_counts(pd_sim* s, uint64_t counts[16], uint64_t* n_agents, void* stream) {
+    if (!s || !s->ready) return fail(PD_ERR_STATE, "no state");
+    int rc = read_back(s, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (counts) for (int k = 0; k < 16; ++k) counts[k] = s->h->bins[k];
+    if (n_agents) *n_agents = s->h->n_agents;
+    return PD_OK;
+}
+
+int pd_read_stats(pd_sim* s, pd_step_stats* o, void* stream) {
+    if (!s || !s->ready || !o) return fail(PD_ERR_STATE, "no state");
+    int rc = read_back(s, (cudaStream_t)stream);
+    if (rc) return rc;
+    const unsigned long long* v = s->h->stats;
+    o->agents_start = v[0]; o->agents_end = v[1]; o->play_deaths = v[2]; o->movers = v[3];
+    o->moved = v[4]; o->travel_deaths = v[5]; o->births = v[6]; o->culled = v[7];
+    o->living_deaths = v[8]; o->risk_list = v[9]; o->move_losers = v[10]; o->repro_losers = v[11];
+    return PD_OK;
+}
+
+int pd_get_step(pd_sim* s, uint32_t* step) {
+    if (!s || !step) return fail(PD_ERR_INVALID, "NULL argument");
+    *step = s->step;
+    return PD_OK;
+}
+int pd_set_step(pd_sim* s, uint32_t step) {
+    if (!s) return fail(PD_ERR_INVALID, "NULL argument");
+    s->step = step;
+    return PD_OK;
+}
+
+int pd_step_host(pd_sim* s, const float* h_e, const uint8_t* h_s, const uint8_t* h_t, uint32_t n_steps,
+                 float* o_e, uint8_t* o_s, uint8_t* o_t, uint64_t counts[16], uint64_t* n_agents, void* stream) {
+    if (!s || !s->bound) return fail(PD_ERR_STATE, "planes not bound");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(s->cfg.device));
+    if (h_e && h_s && h_t) {
+        CK(cudaMemcpyAsync(s->P.E0, h_e, s->cells * sizeof(float), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s->P.strat, h_s, s->cells, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s->P.tfA, h_t, s->cells, cudaMemcpyHostToDevice, st));
+        int rc = pd_sync_state(s, stream);
+        if (rc) return rc;
+    } else if (h_e || h_s || h_t) {
+        return fail(PD_ERR_INVALID, "pass all three input planes or none");
+    }
+    int rc = pd_step(s, n_steps, stream, counts != NULL);
+    if (rc) return rc;
+    if (o_e) CK(cudaMemcpyAsync(o_e, s->P.E0, s->cells * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (o_s) CK(cudaMemcpyAsync(o_s, s->P.strat, s->cells, cudaMemcpyDeviceToHost, st));
+    if (o_t) CK(cudaMemcpyAsync(o_t, s->P.tfA, s->cells, cudaMemcpyDeviceToHost, st));
+    return pd_read_counts(s, counts, n_agents, stream);
+}
+
+// test hook: Philox known-answer vectors through the device implementation
+int pd_debug_philox(const uint32_t* ctr_key6, uint32_t* out4, int n) {
+    uint32_t *d_in = nullptr, *d_out = nullptr;
+    CK(cudaMalloc(&d_in, (size_t)n * 6 * 4));
+    CK(cudaMalloc(&d_out, (size_t)n * 4 * 4));
+    CK(cudaMemcpy(d_in, ctr_key6, (size_t)n * 6 * 4, cudaMemcpyHostToDevice));
+    k_philox_kat<<<(n + 127) / 128, 128>>>(d_in, d_out, n);
+    CK(cudaMemcpy(out4, d_out, (size_t)n * 4 * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_in); cudaFree(d_out);
+    return PD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,201 @@
+"""Host-side handle over libpdabm.so: the Python object that takes the place of
+``pyflamegpu.CUDASimulation`` for this model (/root/reference/src/model.py:1780-1798, :2176).
+
+torch is used for device buffers and streams only; every computation of the step happens in
+the hand-written CUDA kernels behind the C ABI (include/pdabm.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field, asdict
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import pd_config, pd_step_stats, PD_TF_OCCUPIED, PD_TF_TRAIT_MASK
+
+
+class PdabmError(RuntimeError):
+    pass
+
+
+@dataclass
+class SimConfig:
+    """The reference's tunables under their environment-property names
+    (model.py:1678-1743; module constants model.py:39-169)."""
+    width: int = 512                       # ENV_MAX (:211)
+    seed: int = 12345                      # RANDOM_SEED (:39)
+    init_agent_count: int = -1             # INIT_AGENT_COUNT (:45); -1 = int(cells * 0.16)
+    max_agents: int = -1                   # AGENT_HARD_LIMIT (:49); -1 = int(cells * 0.5)
+    payoff_cc: float = 3.0
+    payoff_dc: float = 5.0
+    payoff_cd: float = -1.0
+    payoff_dd: float = 0.0
+    env_noise: float = 0.0
+    cost_of_living: float = 1.0
+    travel_cost: float = 0.5
+    reproduce_min_energy: float = 100.0
+    reproduce_cost: float = 50.0
+    reproduction_inheritence: float = 0.0
+    max_children_per_step: int = 1
+    max_energy: float = 150.0
+    init_energy_mu: float = 50.0
+    init_energy_sigma: float = 10.0
+    init_energy_min: float = 5.0
+    mutation_rate: float = 0.0
+    strategy_pure: int = 0
+    strategy_per_trait: int = 0
+    strategy_weights: List[float] = field(default_factory=lambda: [0.25, 0.25, 0.25, 0.25])
+    device: int = 0
+    collect_stats: bool = False
+    sparse_ctas: int = 0
+
+    def __post_init__(self):
+        cells = self.width * self.width
+        if self.init_agent_count < 0:
+            self.init_agent_count = int(cells * 0.16)
+        if self.max_agents < 0:
+            self.max_agents = int(cells * 0.5)
+
+    def to_c(self) -> pd_config:
+        c = pd_config()
+        c.struct_size = C.sizeof(pd_config)
+        c.width = self.width
+        c.row0 = 0
+        c.rows = self.width
+        c.seed = self.seed & 0xFFFFFFFFFFFFFFFF
+        c.max_agents = self.max_agents
+        for k in ("payoff_cc", "payoff_cd", "payoff_dc", "payoff_dd", "env_noise", "travel_cost",
+                  "cost_of_living", "reproduce_min_energy", "reproduce_cost",
+                  "reproduction_inheritence", "init_energy_mu", "init_energy_sigma",
+                  "init_energy_min", "max_energy", "mutation_rate"):
+            setattr(c, k, float(getattr(self, k)))
+        for i in range(4):
+            c.strategy_weights[i] = float(self.strategy_weights[i])
+        c.strategy_pure = int(bool(self.strategy_pure))
+        c.strategy_per_trait = int(bool(self.strategy_per_trait))
+        c.max_children_per_step = int(self.max_children_per_step)
+        c.collect_stats = int(bool(self.collect_stats))
+        c.device = int(self.device)
+        c.sparse_ctas = int(self.sparse_ctas)
+        return c
+
+
+def pack_strategies(strat4: np.ndarray) -> np.ndarray:
+    """[..., 4] strategies (0..3) -> packed u8 plane (slot t at bits 2t..2t+1)."""
+    s = np.asarray(strat4, dtype=np.uint8)
+    return (s[..., 0] | (s[..., 1] << 2) | (s[..., 2] << 4) | (s[..., 3] << 6)).astype(np.uint8)
+
+
+def unpack_strategies(packed: np.ndarray) -> np.ndarray:
+    p = np.asarray(packed, dtype=np.uint8)
+    return np.stack([(p >> (2 * t)) & 3 for t in range(4)], axis=-1).astype(np.uint8)
+
+
+class Simulation:
+    """One world on one GPU.  ``energy``, ``strat`` and ``tf`` are torch CUDA tensors of
+    shape [width, width] ([y, x]) that the library borrows (pd_bind_planes)."""
+
+    def __init__(self, config: SimConfig, stream=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise PdabmError("CUDA device required: the agent pipeline has no CPU path")
+        self.cfg = config
+        self.lib = _lib.load()
+        self.torch = torch
+        self.device = torch.device("cuda", config.device)
+        W = config.width
+        with torch.cuda.device(self.device):
+            self.energy = torch.zeros((W, W), dtype=torch.float32, device=self.device)
+            self.strat = torch.zeros((W, W), dtype=torch.uint8, device=self.device)
+            self.tf = torch.zeros((W, W), dtype=torch.uint8, device=self.device)
+            torch.cuda.synchronize(self.device)
+        self._stream = stream
+        self._h = C.c_void_p()
+        ccfg = config.to_c()
+        self._check(self.lib.pd_create(C.byref(ccfg), C.byref(self._h)))
+        self._check(self.lib.pd_bind_planes(self._h, self.energy.data_ptr(), self.strat.data_ptr(),
+                                            self.tf.data_ptr()))
+
+    # -- plumbing
+    def _check(self, rc: int):
+        if rc != 0:
+            raise PdabmError(f"libpdabm error {rc}: {self.lib.pd_last_error().decode()}")
+
+    @property
+    def stream_ptr(self) -> int:
+        return 0 if self._stream is None else int(self._stream.cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.pd_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- the reference-facing surface
+    def init_population(self, n_agents: Optional[int] = None):
+        """init_fn (model.py:1423-1524)."""
+        n = self.cfg.init_agent_count if n_agents is None else n_agents
+        self._check(self.lib.pd_init_population(self._h, n, self.stream_ptr))
+
+    def set_state(self, occ, energy, trait, strat4):
+        """Upload a world given as NumPy planes ([y,x]; strat4 is [y,x,4])."""
+        torch = self.torch
+        tf = (np.asarray(occ, np.uint8) * np.uint8(PD_TF_OCCUPIED)) | (np.asarray(trait, np.uint8) & 3)
+        tf = np.where(np.asarray(occ) != 0, tf, 0).astype(np.uint8)
+        self.tf.copy_(torch.from_numpy(tf))
+        self.energy.copy_(torch.from_numpy(np.asarray(energy, np.float32)))
+        self.strat.copy_(torch.from_numpy(pack_strategies(strat4)))
+        torch.cuda.synchronize(self.device)
+        self._check(self.lib.pd_sync_state(self._h, self.stream_ptr))
+
+    def step(self, n_steps: int = 1, want_counts: bool = True):
+        """Main layers 1-7 (model.py:2140-2163) n_steps times; asynchronous."""
+        self._check(self.lib.pd_step(self._h, int(n_steps), self.stream_ptr, int(bool(want_counts))))
+
+    def counts(self):
+        """(population_strat_count[16], agent count) -- step_fn (model.py:1405-1419) and logCount (:185)."""
+        arr = (C.c_uint64 * 16)()
+        n = C.c_uint64()
+        self._check(self.lib.pd_read_counts(self._h, arr, C.byref(n), self.stream_ptr))
+        return np.array(list(arr), dtype=np.int64), int(n.value)
+
+    def stats(self) -> Dict[str, int]:
+        st = pd_step_stats()
+        self._check(self.lib.pd_read_stats(self._h, C.byref(st), self.stream_ptr))
+        return {n: int(getattr(st, n)) for n, _ in pd_step_stats._fields_}
+
+    @property
+    def step_index(self) -> int:
+        v = C.c_uint32()
+        self._check(self.lib.pd_get_step(self._h, C.byref(v)))
+        return int(v.value)
+
+    def planes(self) -> Dict[str, np.ndarray]:
+        """Download the world as NumPy planes (same keys as the oracle's ``planes()``)."""
+        self.torch.cuda.synchronize(self.device)
+        tf = self.tf.cpu().numpy()
+        occ = (tf & PD_TF_OCCUPIED) != 0
+        return {
+            "occ": occ.astype(np.uint8),
+            "energy": np.where(occ, self.energy.cpu().numpy(), np.float32(0)).astype(np.float32),
+            "trait": np.where(occ, tf & PD_TF_TRAIT_MASK, 0).astype(np.uint8),
+            "strat": np.where(occ[..., None], unpack_strategies(self.strat.cpu().numpy()), 0).astype(np.uint8),
+            "tf_raw": tf,
+        }
+
+    def step_host(self, h_energy, h_strat, h_tf, n_steps=1, out_energy=None, out_strat=None, out_tf=None):
+        """pd_step_host: host buffers in, host buffers out (the e2e path of bench.py)."""
+        arr = (C.c_uint64 * 16)()
+        n = C.c_uint64()
+        ptr = lambda t: 0 if t is None else t.data_ptr()
+        self._check(self.lib.pd_step_host(self._h, ptr(h_energy), ptr(h_strat), ptr(h_tf), int(n_steps),
+                                          ptr(out_energy), ptr(out_strat), ptr(out_tf), arr, C.byref(n),
+                                          self.stream_ptr))
+        return np.array(list(arr), dtype=np.int64), int(n.value)

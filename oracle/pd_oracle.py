@@ -141,8 +141,14 @@ class Params:
 
 def strategy_cum_thresholds(weights) -> np.ndarray:
     """Three u64 thresholds t1<=t2<=t3; strategy = #(word >= t_k).  model.py:218-224, :1475."""
-    w = np.asarray(weights, dtype=np.float64)
-    cum = np.cumsum(w) / np.sum(w)
+    w = np.asarray(weights, dtype=np.float32).astype(np.float64)  # properties are float32
+    wsum = 0.0
+    for v in w:
+        wsum += float(v)
+    cum, acc = [], 0.0
+    for v in w:
+        acc += float(v)
+        cum.append(acc / wsum)
     return np.array([min(4294967296.0, np.floor(c * 4294967296.0)) for c in cum[:3]], dtype=np.uint64)
 
 

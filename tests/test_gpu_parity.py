@@ -1,0 +1,184 @@
+"""GPU parity: the CUDA pipeline (through the C ABI) against the NumPy oracle, step by step.
+
+Integer state (occupancy, trait, strategies, counts, event counters) must be bit-exact;
+energies must agree within 1e-5 relative (north star) -- in practice they are bit-exact too
+and the test reports which.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _require_gpu():
+    if not _have_gpu():
+        pytest.skip("no CUDA device")
+
+
+def _pair(**kw):
+    from pdabm_b200 import Simulation, SimConfig
+    from oracle.pd_oracle import Oracle, Params
+    sim = Simulation(SimConfig(collect_stats=True, **kw))
+    okw = {k: v for k, v in kw.items() if k != "sparse_ctas"}
+    orc = Oracle(Params(**okw))
+    return sim, orc
+
+
+def _compare(sim, orc, tag):
+    got, ref = sim.planes(), orc.planes()
+    for k in ("occ", "trait", "strat"):
+        if not np.array_equal(got[k], ref[k]):
+            bad = np.argwhere(got[k] != ref[k])
+            raise AssertionError(f"{tag}: plane {k} differs at {len(bad)} cells, first {bad[:5].tolist()}")
+    assert np.all((got["tf_raw"] & 0x7C) == 0), f"{tag}: transient tf bits left set"
+    e_exact = np.array_equal(got["energy"], ref["energy"])
+    if not e_exact:
+        np.testing.assert_allclose(got["energy"], ref["energy"], rtol=1e-5, atol=0, err_msg=tag)
+    counts, n = sim.counts()
+    assert n == orc.n, f"{tag}: agent count {n} != {orc.n}"
+    assert np.array_equal(counts, orc.population_strat_count), f"{tag}: strategy counts differ"
+    return e_exact
+
+
+def _run(steps, **kw):
+    sim, orc = _pair(**kw)
+    try:
+        sim.init_population()
+        orc.init_population()
+        exact = _compare(sim, orc, "init")
+        for s in range(steps):
+            sim.step(1)
+            st = orc.step()
+            exact &= _compare(sim, orc, f"step {s}")
+            gs = sim.stats()
+            for k_gpu, k_or in (("play_deaths", "play_deaths"), ("movers", "movers"), ("moved", "moved"),
+                                ("travel_deaths", "travel_deaths"), ("births", "births"),
+                                ("culled", "culled"), ("living_deaths", "living_deaths"),
+                                ("agents_start", "agents_start"), ("agents_end", "agents_end")):
+                assert gs[k_gpu] == st[k_or], f"step {s}: stat {k_gpu} gpu {gs[k_gpu]} != oracle {st[k_or]}"
+        assert exact, "energies agree only within tolerance, expected bit-exact"
+    finally:
+        sim.close()
+
+
+def test_philox_kat():
+    """Random123 known-answer vectors through the DEVICE Philox (csrc/philox.cuh)."""
+    from pdabm_b200 import _lib
+    lib = _lib.load()
+    vec = np.array([
+        [0, 0, 0, 0, 0, 0],
+        [0xFFFFFFFF] * 6,
+        [0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344, 0xA4093822, 0x299F31D0],
+    ], dtype=np.uint32)
+    out = np.zeros((3, 4), dtype=np.uint32)
+    rc = lib.pd_debug_philox(vec.ctypes.data, out.ctypes.data, 3)
+    assert rc == 0
+    exp = np.array([
+        [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8],
+        [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD],
+        [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1],
+    ], dtype=np.uint32)
+    assert np.array_equal(out, exp)
+
+
+@pytest.mark.parametrize("width", [16, 32, 64, 128, 256])
+def test_default_kin_other(width):
+    """Reference defaults (model.py:39-169): kin/other strategies, no noise, no mutation."""
+    _run(40 if width <= 64 else 25, width=width, seed=12345 + width)
+
+
+def test_default_long_saturation():
+    """Run past the carrying capacity (cap reached near step 60) so the cull is exercised."""
+    _run(90, width=64, seed=99)
+
+
+@pytest.mark.parametrize("mode", ["pure", "per_trait", "kin_other"])
+def test_modes_with_noise_and_mutation(mode):
+    kw = dict(width=128, seed=4242, env_noise=0.05, mutation_rate=0.01)
+    if mode == "pure":
+        kw["strategy_pure"] = 1
+    elif mode == "per_trait":
+        kw["strategy_per_trait"] = 1
+    _run(70, **kw)
+
+
+def test_inheritance_mode():
+    _run(70, width=64, seed=5, reproduction_inheritence=0.5, mutation_rate=0.2, env_noise=0.2)
+
+
+def test_harsh_world_many_deaths():
+    """Large negative payoffs and costs: most agents are at risk, play deaths chain."""
+    _run(30, width=64, seed=11, payoff_cd=-30.0, payoff_dd=-5.0, cost_of_living=3.0, travel_cost=4.0,
+         init_agent_count=2500)
+
+
+def test_dense_world_conflicts():
+    """Dense start: many travel/reproduction conflicts, retry rounds, full neighbourhoods."""
+    _run(30, width=64, seed=3, init_agent_count=3000, max_agents=3600, reproduce_min_energy=40.0,
+         reproduce_cost=10.0, payoff_cc=10.0)
+
+
+def test_multi_cta_sparse_path():
+    """Force the cooperative multi-CTA path of the persistent sparse kernels on a small world."""
+    _run(70, width=128, seed=77, env_noise=0.1, mutation_rate=0.05, sparse_ctas=8,
+         payoff_cd=-10.0, reproduce_min_energy=60.0)
+
+
+def test_config1_512_defaults():
+    """BASELINE config 1: 512x512, defaults, first 12 steps bit-exact (the full 100 steps run in
+    the bench's cpu_baseline leg)."""
+    _run(12, width=512, seed=12345)
+
+
+def test_size_independent_invariants_large():
+    """At a size the oracle cannot follow (4096^2) check the domain's invariants: population
+    bookkeeping N' = N + births - culled - deaths, <= 1 agent per cell by construction,
+    0 < energy <= max_energy, counts sum to the population, cap respected."""
+    from pdabm_b200 import Simulation, SimConfig
+    cfg = SimConfig(width=4096, seed=1, collect_stats=True, env_noise=0.05, mutation_rate=0.01)
+    sim = Simulation(cfg)
+    try:
+        sim.init_population()
+        counts, n = sim.counts()
+        assert n == cfg.init_agent_count and counts.sum() == n
+        for s in range(70):
+            sim.step(1)
+            st = sim.stats()
+            counts, n = sim.counts()
+            assert st["agents_end"] == n == counts.sum()
+            assert st["agents_end"] == (st["agents_start"] - st["play_deaths"] - st["travel_deaths"]
+                                        + st["births"] - st["culled"] - st["living_deaths"])
+            assert n <= cfg.max_agents
+        pl = sim.planes()
+        occ = pl["occ"].astype(bool)
+        assert occ.sum() == n
+        e = pl["energy"][occ]
+        assert e.min() > 0 and e.max() <= cfg.max_energy
+        assert n == cfg.max_agents or n > 0.95 * cfg.max_agents  # saturated by step 70
+    finally:
+        sim.close()
+
+
+def test_determinism_same_seed():
+    from pdabm_b200 import Simulation, SimConfig
+    outs = []
+    for ctas in (0, 4):
+        sim = Simulation(SimConfig(width=256, seed=321, env_noise=0.02, sparse_ctas=ctas))
+        sim.init_population()
+        sim.step(40)
+        pl = sim.planes()
+        outs.append((pl["tf_raw"].copy(), pl["energy"].copy(), pl["strat"].copy()))
+        sim.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
