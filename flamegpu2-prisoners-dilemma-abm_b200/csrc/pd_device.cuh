@@ -20,6 +20,8 @@ namespace pd {
 constexpr uint32_t TF_TRAIT = 0x03u;
 constexpr uint32_t TF_GHOST = 0x04u;
 constexpr uint32_t TF_NEWBORN = 0x04u;
+constexpr uint32_t TF_DYING = 0x08u;  // tfA after the final sweep: died of living cost, but still
+                                      // occupies its cell until the reproduction rounds are over
 constexpr uint32_t TF_DIR_SHIFT = 3u;
 constexpr uint32_t TF_DIR = 0x38u;
 constexpr uint32_t TF_CLAIM = 0x40u;
@@ -56,7 +58,7 @@ static_assert(DY(0) == -1 && DY(1) == 0 && DY(2) == 1 && DY(3) == -1 && DY(4) ==
 // ---- device-resident counters -----------------------------------------------------------
 struct Counters {
     // zeroed at the start of every step (k_begin_step)
-    unsigned int mv_n, rp_n, nb_n, risk_next_n;
+    unsigned int mv_n, rp_n, nb_n, risk_next_n, dead_n, pad0_;
     unsigned int mv_active[8], rp_active[8];
     unsigned long long n_old, births, culled, living_deaths;
     unsigned long long st_play_deaths, st_movers, st_moved, st_travel_deaths;
@@ -94,6 +96,7 @@ struct Params {
     uint32_t* mv_cell; uint8_t* mv_state; uint8_t* mv_aux;
     uint32_t* rp_cell; uint8_t* rp_state; uint8_t* rp_aux;
     uint32_t* nb_cell; uint32_t* nb_prio;
+    uint32_t* dead_cell;  // aliases mv_cell (the travel rounds are over when it is filled)
     Counters* ctr;
 };
 

@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Par
         const uint32_t t = valid ? s_tf[si] : 0u;
         uint32_t out = 0;
         float e_out = 0.0f;
-        bool lost = false, newborn = false, at_risk = false;
+        bool lost = false, newborn = false, at_risk = false, dying = false;
         uint32_t loser_state = 0;
         if (t & TF_OCC) {
             ++n_old;
@@ -496,6 +496,10 @@ __global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Par
                 at_risk = e <= p.risk_thr;
                 if (p.want_counts) atomicAdd(&s_bins[count_bin(p.strat[cell], trait)], 1u);
             } else {
+                // dies (:1364-1366) -- but environmental_punishment runs AFTER the god submodel, so the
+                // cell stays occupied for the reproduction retry rounds; k_finalize clears it
+                out = TF_OCC | TF_DYING;
+                dying = true;
                 ++n_dead;
             }
         } else if (valid) {
@@ -536,6 +540,11 @@ __global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Par
         slot = warp_append(&p.ctr->risk_next_n, at_risk);
         if (at_risk) {
             if (slot < p.list_cap) p.risk_next[slot] = (uint32_t)cell;
+            else atomicExch(&p.ctr->overflow, 1u);
+        }
+        slot = warp_append(&p.ctr->dead_n, dying);
+        if (dying) {
+            if (slot < p.list_cap) p.dead_cell[slot] = (uint32_t)cell;
             else atomicExch(&p.ctr->overflow, 1u);
         }
         if (valid) {
@@ -772,6 +781,10 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Param
         }
     }
     if (n_dead) atomicAdd(&ctr->living_deaths, (unsigned long long)n_dead);
+    // ---- the agents the final sweep killed finally leave their cells
+    unsigned int ndead = ctr->dead_n;
+    if (ndead > p.list_cap) ndead = p.list_cap;
+    for (unsigned int i = t0; i < ndead; i += stride) p.tfA[p.dead_cell[i]] = 0;
     grid_sync(ctr->barrier, gridDim.x);
     // ---- bookkeeping (one thread)
     if (blockIdx.x == 0 && threadIdx.x == 0) {

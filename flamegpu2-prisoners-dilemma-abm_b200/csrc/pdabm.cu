@@ -97,6 +97,7 @@ int alloc_lists(pd_sim* s, uint64_t n_agents_hint) {
     CK(cudaMalloc(&s->P.risk_e, cap * 4));
     CK(cudaMalloc(&s->P.risk_roll, cap * 4));
     CK(cudaMalloc(&s->P.mv_cell, cap * 4));
+    s->P.dead_cell = s->P.mv_cell;
     CK(cudaMalloc(&s->P.mv_state, cap));
     CK(cudaMalloc(&s->P.mv_aux, cap));
     CK(cudaMalloc(&s->P.rp_cell, cap * 4));
