@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s of the per-step agent pipeline (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload config3|config2|config1] [--presteps P]
+
+A "step" is ONE model step (main layers 1-7, /root/reference/src/model.py:2140-2163) of the
+workload's world.  Default workload = BASELINE.json configs[2], the HBM-roofline config:
+16384 x 16384 cells (2^28), per-trait strategies, measured in the saturated steady state
+(P untimed pre-steps from init, then W warm-up steps, then K timed steps).  With --gpus N
+(torchrun) every rank advances its own world of that size (ensemble partitioning, no
+communication on the data path) -> weak scaling; value = all ranks' agent-steps / max time.
+
+Keys of the JSON line beyond the base contract:
+  roofline      dominant kernel (k_play_travel): algorithmic bytes per launch / mean device
+                time of that launch (CUDA events recorded inside pd_step on the launch stream)
+  kernels       the same for every kernel of the step (ms per step, share, GB/s)
+  cpu_baseline  the NumPy oracle (a port of the reference's agent functions -- the reference
+                itself is CUDA-only) on the host cores, on a bounded sample of the workload
+  e2e           the same metric through the host-buffer C-ABI call pd_step_host: every step
+                uploads the three state planes from pinned host memory, runs the step and
+                downloads planes + counts
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (width, SimConfig overrides, description)
+    "config3": (16384, dict(strategy_per_trait=1),
+                "BASELINE configs[2]: 16384x16384 (2^28 cells), per-trait strategies, steady state"),
+    "config2": (1024, dict(env_noise=0.05, mutation_rate=0.01),
+                "BASELINE configs[1]: 1024x1024 (2^20 cells), noise 0.05, mutation 0.01, kin/other, counts every step"),
+    "config1": (512, dict(),
+                "BASELINE configs[0]: 512x512 (2^18 cells), model.py defaults (kin/other), counts every step"),
+}
+# algorithmic bytes per cell per launch of each dense sweep (DESIGN.md "Kernels"):
+#   play_travel : read tfA 1 + strat 1 + E0 4, write tfB 1 + E1 4
+#   move_commit : read tfB 1, write tfA 1
+#   repro_claim : read tfA 1 + E1 4, write tfB 1
+#   repro_commit: read tfB 1 + E1 4, write tfA 1 + E0 4   (+1 strat when counts are wanted)
+ALG_BYTES = {"play_travel": 11, "move_commit": 2, "repro_claim": 6, "repro_commit": 10}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.path = os.path.join(ROOT, "gpurun_out", f"clocks_{os.getpid()}.csv")
+
+    def start(self):
+        os.makedirs(os.path.dirname(self.path), exist_ok=True)
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- CPU side
+def _oracle_worker(args):
+    """One oracle world on one host core: returns (agent_steps, seconds) for the timed steps."""
+    width, overrides, seed, presteps, steps = args
+    from oracle.pd_oracle import Oracle, Params
+    kw = {k: v for k, v in overrides.items()}
+    orc = Oracle(Params(width=width, seed=seed, **kw))
+    orc.init_population()
+    for _ in range(presteps):
+        orc.step()
+    t0 = time.perf_counter()
+    agent_steps = 0
+    for _ in range(steps):
+        agent_steps += orc.n
+        orc.step()
+    return agent_steps, time.perf_counter() - t0
+
+
+def cpu_oracle_throughput(overrides, sample_width, presteps, steps, procs):
+    """agent-steps/s of the NumPy oracle: `procs` independent sample worlds, one per core."""
+    import multiprocessing as mp
+    jobs = [(sample_width, overrides, 12345 + i, presteps, steps) for i in range(procs)]
+    t0 = time.perf_counter()
+    if procs == 1:
+        res = [_oracle_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_oracle_worker, jobs)
+    wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    return total / slowest, total, slowest, wall
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference has no CPU implementation of this path (FLAMEGPU2 is
+    CUDA-only and pyflamegpu is not installable here), so the arm times the oracle PORT of its
+    agent functions on all host cores, on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    width, overrides, desc = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    sample_w = min(width, 256)
+    presteps = min(args.presteps, 70)
+    val, total, secs, wall = cpu_oracle_throughput(overrides, sample_w, presteps, max(1, args.steps), cores)
+    sample = (f"{cores} independent {sample_w}x{sample_w} worlds (one per host core) with the workload's "
+              f"parameters, {presteps} untimed pre-steps then {args.steps} timed steps each")
+    line = {
+        "impl": "reference", "metric": "agent-steps/sec", "value": val, "unit": "agent-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- GPU side
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from pdabm_b200 import Simulation, SimConfig
+
+    width, overrides, desc = WORKLOADS[args.workload]
+    if args.width:
+        width = args.width
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cfg = SimConfig(width=width, seed=12345 + rank, device=local_rank, **overrides)
+    sim = Simulation(cfg)
+    cells = width * width
+    want_counts = args.workload != "config3"  # config 3 logs first/last only
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    t_init0 = time.perf_counter()
+    sim.init_population()
+    sim.step(args.presteps, want_counts=False)   # untimed: reach the saturated steady state
+    sim.step(args.warmup, want_counts=want_counts)
+    _, n_before = sim.counts()
+    as0 = sim.agent_steps()
+    init_s = time.perf_counter() - t_init0
+
+    # ---- timed region: K steps, per-kernel CUDA events recorded inside pd_step
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    sim.set_profile(True)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        sim.step(1, want_counts=want_counts)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_ms, prof_steps = sim.read_profile()
+    sim.set_profile(False)
+    as1 = sim.agent_steps()
+    counts, n_after = sim.counts()
+    agent_steps = as1 - as0
+
+    # ---- e2e: the host-buffer C-ABI call, state round trip through pinned host memory each step
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h_e = torch.empty((width, width), dtype=torch.float32).pin_memory()
+    h_s = torch.empty((width, width), dtype=torch.uint8).pin_memory()
+    h_t = torch.empty((width, width), dtype=torch.uint8).pin_memory()
+    h_e.copy_(sim.energy)
+    h_s.copy_(sim.strat)
+    h_t.copy_(sim.tf)
+    torch.cuda.synchronize()
+    sim.step_host(h_e, h_s, h_t, 1, h_e, h_s, h_t)  # warm-up of the host path
+    barrier()
+    t0 = time.perf_counter()
+    as_a = sim.agent_steps()
+    for _ in range(e2e_steps):
+        sim.step_host(h_e, h_s, h_t, 1, h_e, h_s, h_t)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_agents = sim.agent_steps() - as_a
+    h2d = cells * 6
+    d2h = cells * 6 + 17 * 8
+
+    # ---- reduce over ranks: total agent-steps, max time
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        a = torch.tensor([agent_steps, e2e_agents], dtype=torch.float64, device="cuda")
+        dist.all_reduce(a, op=dist.ReduceOp.SUM)
+        ms, e2e_s = float(t[0]), float(t[1])
+        agent_steps, e2e_agents = float(a[0]), float(a[1])
+    if rank != 0:
+        sim.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    secs = ms / 1e3
+    kern = {}
+    step_ms_sum = sum(kernel_ms.values()) / max(1, prof_steps)
+    for k, v in kernel_ms.items():
+        per = v / max(1, prof_steps)
+        ent = {"ms_per_step": per, "share": per / step_ms_sum if step_ms_sum else None}
+        if k in ALG_BYTES:
+            b = ALG_BYTES[k] + (1 if (k == "repro_commit" and want_counts) else 0)
+            ent["alg_bytes_per_cell"] = b
+            ent["gbs"] = b * cells / (per * 1e-3) / 1e9 if per > 0 else None
+            ent["frac_of_hbm_peak"] = ent["gbs"] / peak if per > 0 else None
+        kern[k] = ent
+    dom = max(ALG_BYTES, key=lambda k: kern[k]["ms_per_step"])
+    total_alg = sum(ALG_BYTES.values()) + (1 if want_counts else 0)
+    step_gbs = total_alg * cells * args.steps / secs / 1e9
+
+    # ---- CPU baseline (rank 0, N == 1 only): bounded sample of the same workload
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sw = min(width, 256)
+        cval, ctotal, csecs, _ = cpu_oracle_throughput(overrides, sw, 70, 12, 1)
+        cpu = {"value": cval, "unit": "agent-steps/s", "cores": 1, "kind": "port",
+               "sample": f"NumPy oracle (oracle/pd_oracle.py), one {sw}x{sw} world with the workload's parameters, "
+                         f"70 untimed pre-steps then 12 timed steps ({csecs:.1f} s), single process"}
+
+    line = {
+        "metric": "agent-steps/sec", "value": agent_steps / secs, "unit": "agent-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": desc, "width": width, "cells": cells, "cells_per_gpu": cells,
+                   "partitioning": "one world per GPU (ensemble), no data-path collective" if world > 1 else "single world",
+                   "presteps": args.presteps, "agents_at_start": n_before, "agents_at_end": n_after,
+                   "density": n_after / cells, "counts_every_step": want_counts,
+                   "l2": "state (11 B/cell resident) larger than the 126 MB L2" if cells * 11 > 126e6
+                         else "state fits in L2: HBM roofline figures are not meaningful at this size"},
+        "cell_steps_per_s": cells * world * args.steps / secs,
+        "step_alg_bytes_per_cell": total_alg, "step_alg_gbs": step_gbs, "step_frac_of_hbm_peak": step_gbs / peak,
+        "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": kern[dom]["gbs"], "peak": peak,
+                     "unit": "GB/s", "frac": kern[dom]["frac_of_hbm_peak"], "traffic": None,
+                     "peak_source": peak_src, "alg_bytes_per_launch": ALG_BYTES[dom] * cells,
+                     "launch_ms": kern[dom]["ms_per_step"]},
+        "kernels": kern,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_agents / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                "call": "pd_step_host (host planes in, host planes + counts out)"},
+        "gpu_launches": 9 * args.steps,
+        "clocks": clocks,
+        "init_and_presteps_s": init_s,
+    }
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            tr = json.load(open(traffic_file))
+            line["roofline"]["traffic"] = tr.get("k_" + dom, {}).get(args.workload)
+        except Exception:
+            pass
+    print(json.dumps(line), flush=True)
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--width", type=int, default=0, help="override the workload's width (debug)")
+    ap.add_argument("--presteps", type=int, default=80)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

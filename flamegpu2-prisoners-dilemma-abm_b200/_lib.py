@@ -58,7 +58,8 @@ class pd_step_stats(C.Structure):
 EXPORTS = (
     "pd_last_error", "pd_abi_version", "pd_default_config", "pd_create", "pd_destroy",
     "pd_bind_planes", "pd_init_population", "pd_sync_state", "pd_step", "pd_read_counts",
-    "pd_read_stats", "pd_get_step", "pd_set_step", "pd_step_host",
+    "pd_read_stats", "pd_get_step", "pd_set_step", "pd_step_host", "pd_read_agent_steps",
+    "pd_set_profile", "pd_read_profile",
 )
 
 _lib = None
@@ -103,6 +104,12 @@ def load() -> C.CDLL:
     lib.pd_set_step.argtypes = [vp, u32]
     lib.pd_step_host.restype = i32
     lib.pd_step_host.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, C.POINTER(u64), C.POINTER(u64), vp]
+    lib.pd_read_agent_steps.restype = i32
+    lib.pd_read_agent_steps.argtypes = [vp, C.POINTER(u64), vp]
+    lib.pd_set_profile.restype = i32
+    lib.pd_set_profile.argtypes = [vp, i32]
+    lib.pd_read_profile.restype = i32
+    lib.pd_read_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u32), vp]
     lib.pd_debug_philox.restype = i32
     lib.pd_debug_philox.argtypes = [vp, vp, i32]
     _lib = lib

@@ -70,6 +70,7 @@ struct Counters {
     unsigned int barrier[2];
     unsigned long long n_agents;
     unsigned long long agents_start;
+    unsigned long long agent_steps;  // running sum of the population at the start of every step
     unsigned long long last_bins[16];
     unsigned long long last_stats[12];
 };

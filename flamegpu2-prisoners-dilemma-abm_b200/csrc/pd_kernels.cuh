@@ -53,12 +53,15 @@ __device__ __forceinline__ Key repro_key(const Params& p, uint64_t g) {
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void k_begin_step(Counters* ctr) {
+__global__ void k_begin_step(Counters* ctr, int count_step) {
     // zero everything up to (not including) risk_n
     unsigned int* w = reinterpret_cast<unsigned int*>(ctr);
     const size_t nwords = offsetof(Counters, risk_n) / sizeof(unsigned int);
     for (size_t i = threadIdx.x; i < nwords; i += blockDim.x) w[i] = 0u;
-    if (threadIdx.x == 0) ctr->agents_start = ctr->n_agents;
+    if (threadIdx.x == 0) {
+        ctr->agents_start = ctr->n_agents;
+        if (count_step) ctr->agent_steps += ctr->n_agents;
+    }
 }
 
 // ------------------------------------------------------------------------------------------

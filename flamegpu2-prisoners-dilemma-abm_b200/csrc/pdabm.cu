@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "pd_kernels.cuh"
 
@@ -74,6 +75,12 @@ struct pd_sim {
     dim3 grid;
     HostOut* h;  // pinned
     bool lists_allocated;
+    // optional per-kernel timing (pd_set_profile): events around every launch of a step
+    bool profile;
+    std::vector<cudaEvent_t> ev;   // 10 events per profiled step, consumed by pd_read_profile
+    size_t ev_used;
+    double kernel_ms[9];
+    uint32_t prof_steps;
 };
 
 namespace {
@@ -124,7 +131,7 @@ int launch_sparse(pd_sim* s, K kernel, cudaStream_t st) {
 int run_scan(pd_sim* s, cudaStream_t st) {
     s->P.risk_cur = s->risk[s->risk_cur];
     s->P.risk_next = s->risk[s->risk_cur ^ 1];
-    k_begin_step<<<1, 256, 0, st>>>(s->P.ctr);
+    k_begin_step<<<1, 256, 0, st>>>(s->P.ctr, 0);
     const int blocks = (int)((s->cells + NT - 1) / NT < (size_t)(s->n_sms * 16) ? (s->cells + NT - 1) / NT
                                                                                   : (size_t)(s->n_sms * 16));
     k_scan_state<<<blocks, NT, 0, st>>>(s->P, s->cells);
@@ -189,7 +196,6 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     if (cfg->device < 0 || cfg->device >= ndev) return fail(PD_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
     CK(cudaSetDevice(cfg->device));
     pd_sim* s = new pd_sim();
-    memset(s, 0, sizeof *s);
     s->cfg = *cfg;
     s->cells = (size_t)cfg->rows * W;
     Params& P = s->P;
@@ -253,6 +259,7 @@ int pd_destroy(pd_sim* s) {
         cudaFree(s->P.nb_cell); cudaFree(s->P.nb_prio);
     }
     cudaFreeHost(s->h);
+    for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
     delete s;
     return PD_OK;
 }
@@ -308,7 +315,7 @@ int pd_init_population(pd_sim* s, uint64_t n_agents, void* stream) {
     const int none = n_agents == 0;
     if (n_agents > 0 && n_agents < s->cells) {
         // n-th SMALLEST (priority, cell) key by an 8-pass radix select (model.py:1438-1450 restated)
-        k_begin_step<<<1, 256, 0, st>>>(s->P.ctr);
+        k_begin_step<<<1, 256, 0, st>>>(s->P.ctr, 0);
         unsigned long long prefix = 0, krem = n_agents;
         for (int pass = 0; pass < 8; ++pass) {
             k_init_hist<<<blocks, NT, 0, st>>>(s->P, s->cells, pass, prefix);
@@ -346,29 +353,42 @@ int pd_step(pd_sim* s, uint32_t n_steps, void* stream, int want_counts) {
         P.want_counts = (want_counts && k + 1 == n_steps) ? 1u : 0u;
         P.risk_cur = s->risk[s->risk_cur];
         P.risk_next = s->risk[s->risk_cur ^ 1];
-        k_begin_step<<<1, 256, 0, st>>>(P.ctr);
-        int rc = launch_sparse(s, k_risk_resolve, st);
-        if (rc) return rc;
-        if (s->big_tiles) {
-            k_play_travel<128, 16><<<s->grid, NT, 0, st>>>(P);
-            k_move_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
-        } else {
-            k_play_travel<16, 16><<<s->grid, NT, 0, st>>>(P);
-            k_move_commit<16, 16><<<s->grid, NT, 0, st>>>(P);
-        }
-        rc = launch_sparse(s, k_move_retry, st);
-        if (rc) return rc;
-        if (s->big_tiles) {
-            k_repro_claim<128, 16><<<s->grid, NT, 0, st>>>(P);
-            k_repro_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
-        } else {
-            k_repro_claim<16, 16><<<s->grid, NT, 0, st>>>(P);
-            k_repro_commit<16, 16><<<s->grid, NT, 0, st>>>(P);
-        }
-        rc = launch_sparse(s, k_repro_retry, st);
-        if (rc) return rc;
-        rc = launch_sparse(s, k_finalize, st);
-        if (rc) return rc;
+        int rc = PD_OK;
+        int mark = 0;
+        auto tick = [&]() -> int {  // event between two launches when profiling
+            if (!s->profile) return PD_OK;
+            if (s->ev_used >= s->ev.size()) {
+                cudaEvent_t e;
+                CK(cudaEventCreate(&e));
+                s->ev.push_back(e);
+            }
+            CK(cudaEventRecord(s->ev[s->ev_used++], st));
+            ++mark;
+            return PD_OK;
+        };
+        if ((rc = tick())) return rc;
+        k_begin_step<<<1, 256, 0, st>>>(P.ctr, 1);
+        if ((rc = tick())) return rc;
+        if ((rc = launch_sparse(s, k_risk_resolve, st))) return rc;
+        if ((rc = tick())) return rc;
+        if (s->big_tiles) k_play_travel<128, 16><<<s->grid, NT, 0, st>>>(P);
+        else k_play_travel<16, 16><<<s->grid, NT, 0, st>>>(P);
+        if ((rc = tick())) return rc;
+        if (s->big_tiles) k_move_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
+        else k_move_commit<16, 16><<<s->grid, NT, 0, st>>>(P);
+        if ((rc = tick())) return rc;
+        if ((rc = launch_sparse(s, k_move_retry, st))) return rc;
+        if ((rc = tick())) return rc;
+        if (s->big_tiles) k_repro_claim<128, 16><<<s->grid, NT, 0, st>>>(P);
+        else k_repro_claim<16, 16><<<s->grid, NT, 0, st>>>(P);
+        if ((rc = tick())) return rc;
+        if (s->big_tiles) k_repro_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
+        else k_repro_commit<16, 16><<<s->grid, NT, 0, st>>>(P);
+        if ((rc = tick())) return rc;
+        if ((rc = launch_sparse(s, k_repro_retry, st))) return rc;
+        if ((rc = tick())) return rc;
+        if ((rc = launch_sparse(s, k_finalize, st))) return rc;
+        if ((rc = tick())) return rc;
         s->risk_cur ^= 1;
         s->step += 1;
     }
@@ -406,6 +426,43 @@ int pd_read_stats(pd_sim* s, pd_step_stats* o, void* stream) {
     o->agents_start = v[0]; o->agents_end = v[1]; o->play_deaths = v[2]; o->movers = v[3];
     o->moved = v[4]; o->travel_deaths = v[5]; o->births = v[6]; o->culled = v[7];
     o->living_deaths = v[8]; o->risk_list = v[9]; o->move_losers = v[10]; o->repro_losers = v[11];
+    return PD_OK;
+}
+
+int pd_set_profile(pd_sim* s, int on) {
+    if (!s) return fail(PD_ERR_INVALID, "NULL argument");
+    s->profile = on != 0;
+    s->ev_used = 0;
+    s->prof_steps = 0;
+    for (int i = 0; i < 9; ++i) s->kernel_ms[i] = 0.0;
+    return PD_OK;
+}
+
+int pd_read_profile(pd_sim* s, double kernel_ms[9], uint32_t* steps, void* stream) {
+    if (!s || !kernel_ms) return fail(PD_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    for (size_t b = 0; b + 10 <= s->ev_used; b += 10) {
+        for (int i = 0; i < 9; ++i) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, s->ev[b + i], s->ev[b + i + 1]));
+            s->kernel_ms[i] += (double)ms;
+        }
+        s->prof_steps += 1;
+    }
+    s->ev_used = 0;
+    for (int i = 0; i < 9; ++i) kernel_ms[i] = s->kernel_ms[i];
+    if (steps) *steps = s->prof_steps;
+    return PD_OK;
+}
+
+int pd_read_agent_steps(pd_sim* s, uint64_t* agent_steps, void* stream) {
+    if (!s || !agent_steps) return fail(PD_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(s->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(&s->h->n_agents, &s->P.ctr->agent_steps, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *agent_steps = s->h->n_agents;
     return PD_OK;
 }
 

@@ -122,6 +122,18 @@ int pd_read_counts(pd_sim* sim, uint64_t counts[16], uint64_t* n_agents, void* s
 
 int pd_read_stats(pd_sim* sim, pd_step_stats* out, void* stream);
 
+/* Sum over all executed steps of the population at the START of the step (the numerator of
+ * the agent-steps/s metric).  Synchronises `stream`. */
+int pd_read_agent_steps(pd_sim* sim, uint64_t* agent_steps, void* stream);
+
+/* Per-kernel device timing: with profiling on, pd_step records a CUDA event between every
+ * two kernel launches; pd_read_profile synchronises `stream` and returns the accumulated
+ * milliseconds per kernel, in launch order: begin_step, risk_resolve, play_travel,
+ * move_commit, move_retry, repro_claim, repro_commit, repro_retry, finalize. */
+#define PDABM_NUM_KERNELS 9
+int pd_set_profile(pd_sim* sim, int on);
+int pd_read_profile(pd_sim* sim, double kernel_ms[PDABM_NUM_KERNELS], uint32_t* steps, void* stream);
+
 /* Step index of the next step to run (0-based; Philox counter word 2). */
 int pd_get_step(pd_sim* sim, uint32_t* step);
 int pd_set_step(pd_sim* sim, uint32_t step);
