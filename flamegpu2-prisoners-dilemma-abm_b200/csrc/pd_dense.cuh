@@ -1,0 +1,659 @@
+// The four dense sweeps of a step (v2: compacted work lists, shared-memory claim scatter).
+//
+//   k_play_travel   tfA, strat (1-halo), E0 -> tfB, E1     search/game list/8 play sub-steps/first move_request
+//   k_move_commit   tfB (2-halo)            -> tfA          move_response round 1 (winners are pulled)
+//   k_repro_claim   tfA (1-halo), E1        -> tfB          neighbourhood_update + first god_go_forth
+//   k_repro_commit  tfB (2-halo), E1, strat -> tfA, E0      god_multiply round 1 + environmental_punishment + counts
+//
+// Design rules (the v1 profile showed all four issue-bound at 8 of 32 lanes active, DRAM traffic
+// already equal to the algorithmic bytes -- profiles/README.md):
+//   * u8 planes enter shared memory as 16-byte chunks (interior at column 16 of a TW+32 wide row);
+//     the common path touches 4 cells per thread as one 32-bit word / one float4;
+//   * anything that needs a Philox call (rolls, RANDOM/noisy games, movers, parents, contests,
+//     births) is first COMPACTED into a shared-memory work list and then processed with all
+//     32 lanes busy;
+//   * claims are resolved by scattering one bit per claimant into a shared-memory byte per target
+//     (bit j = "my neighbour j claims me"); only cells with >= 2 bits need priorities;
+//   * global list appends are aggregated per CTA (one atomicAdd per list per CTA).
+// Every sweep is still a pure gather in global memory: a cell is written by its own tile only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pd_device.cuh"
+
+namespace pd {
+
+constexpr int NT = 256;  // threads per CTA of the dense sweeps
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+
+// contest key of a claimant: (priority word, global cell) -- higher wins (:929, :1192)
+struct Key {
+    uint32_t prio;
+    uint64_t gcell;
+};
+__device__ __forceinline__ bool key_gt(const Key& a, const Key& b) {
+    return a.prio > b.prio || (a.prio == b.prio && a.gcell > b.gcell);
+}
+struct TravelKey {
+    __device__ __forceinline__ Key operator()(const Params& p, uint64_t g) const {
+        Key k; k.prio = rng(p, g, S_ROLL).y; k.gcell = g; return k;  // :806
+    }
+};
+struct ReproKey {
+    __device__ __forceinline__ Key operator()(const Params& p, uint64_t g) const {
+        Key k; k.prio = rng(p, g, S_REPRO).x; k.gcell = g; return k;  // :1076
+    }
+};
+__device__ __forceinline__ bool claims_dir(uint32_t t, int dir) {
+    return (t & TF_CLAIM) && (int)((t & TF_DIR) >> TF_DIR_SHIFT) == dir;
+}
+// living cost for one agent (environmental_punishment, :1357-1368); returns false if it dies
+__device__ __forceinline__ bool punish(const Params& p, float& e) {
+    e = __fsub_rn(fminf(e, p.max_energy), p.cost_of_living);
+    return e > 0.0f;
+}
+
+// ---- shared-memory tile of a u8 plane: (TH + 2*HALO) rows of TW+32 bytes, interior at column 16
+template <int TW, int TH, int HALO>
+__device__ __forceinline__ void load_tile_vec(const Params& p, const uint8_t* __restrict__ plane,
+                                              uint8_t* s, uint32_t x0, uint32_t y0) {
+    constexpr int NCH = TW / 16 + 2;
+    constexpr int SW = TW + 32;
+    constexpr int SH = TH + 2 * HALO;
+    const uint32_t wch = p.W >> 4;  // 16-byte chunks per row
+    for (int i = threadIdx.x; i < SH * NCH; i += NT) {
+        const int r = i / NCH, j = i - r * NCH;
+        const uint32_t gy = (y0 + (uint32_t)(r - HALO)) & (p.H - 1);
+        const uint32_t cx = ((x0 >> 4) + (uint32_t)(j - 1)) & (wch - 1);
+        const uint4 v = *reinterpret_cast<const uint4*>(plane + ((size_t)gy << p.log2W) + ((size_t)cx << 4));
+        *reinterpret_cast<uint4*>(s + r * SW + j * 16) = v;
+    }
+}
+
+// warp-aggregated append to a shared- or global-memory counter; all 32 lanes must call
+__device__ __forceinline__ uint32_t wappend(unsigned int* counter, bool pred) {
+    const unsigned int m = __ballot_sync(FULL, pred);
+    if (m == 0u) return 0u;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    return base + (unsigned int)__popc(m & ((1u << lane) - 1u));
+}
+
+// reserve `n` slots of a global list for this CTA (one atomic), broadcast through shared memory
+__device__ __forceinline__ unsigned int cta_reserve(unsigned int* gcounter, unsigned int n, unsigned int* s_slot) {
+    if (threadIdx.x == 0) *s_slot = n ? atomicAdd(gcounter, n) : 0u;
+    __syncthreads();
+    const unsigned int b = *s_slot;
+    __syncthreads();
+    return b;
+}
+
+// the game of sub-step c as the responder at my_g sees it -> index into Params::pay
+__device__ __forceinline__ uint32_t game_outcome_rng(const Params& p, uint64_t my_g, int c, uint32_t mine,
+                                                     uint32_t theirs) {
+    bool i_coop = mine != 1u, ch_coop = theirs != 1u;
+    const Words w = rng(p, my_g, S_GAME0 + (uint32_t)c);            // :611-612
+    if (theirs == 3u) ch_coop = (w.z >> 31) != 0u;                   // :630-635
+    if (mine == 3u) i_coop = (w.w >> 31) != 0u;                      // :663-668
+    if ((unsigned long long)w.y < p.noise_thr) ch_coop = !ch_coop;   // :638-640
+    if ((unsigned long long)w.x < p.noise_thr) i_coop = !i_coop;     // :672-674
+    return ((uint32_t)i_coop << 1) | (uint32_t)ch_coop;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_play_travel (dense sweep 1).  Fuses search_for_neighbours (:352-372), get_game_list
+// (:373-440), the 8 iterations of play_challenge/play_response (:450-734) with exit_play_fn's
+// terminal rule, and the first move_request (:784-872).
+// ------------------------------------------------------------------------------------------
+template <int TW, int TH>
+__global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Params p) {
+    constexpr int SW = TW + 32, SH = TH + 2, NC = TW * TH, RW = TW + 2, NWARP = NT / 32;
+    __shared__ __align__(16) uint8_t s_tf[SH * SW];
+    __shared__ __align__(16) uint8_t s_st[SH * SW];
+    __shared__ uint32_t s_roll[SH * SW];
+    __shared__ __align__(16) float s_e[NC];
+    __shared__ __align__(16) uint8_t s_out[NC];
+    __shared__ uint16_t s_occ[SH * RW];   // occupied entries of tile + 1-ring (shared-memory index)
+    __shared__ uint16_t s_agent[NC];      // occupied interior cells (local cell index)
+    __shared__ uint16_t s_mover[NC];
+    __shared__ uint16_t s_q[NWARP][256];  // per-warp queue of games that need a Philox call
+    __shared__ uint8_t s_qo[NWARP][256];
+    __shared__ unsigned int s_n[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    if (tid < 4) s_n[tid] = 0;
+    load_tile_vec<TW, TH, 1>(p, p.tfA, s_tf, x0, y0);
+    load_tile_vec<TW, TH, 1>(p, p.strat, s_st, x0, y0);
+    for (int i = tid; i < NC / 4; i += NT) {
+        const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
+        reinterpret_cast<float4*>(s_e)[i] =
+            *reinterpret_cast<const float4*>(p.E0 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx);
+    }
+    for (int i = tid; i < NC / 16; i += NT) reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    // ---- compaction: occupied entries of the ring region, and the agents of this tile
+    for (int base = 0; base < SH * RW; base += NT) {
+        const int i = base + tid;
+        const bool valid = i < SH * RW;
+        const int r = valid ? i / RW : 0, c = valid ? i - r * RW : 0;
+        const int si = r * SW + 15 + c;
+        const bool occ = valid && (s_tf[si] & TF_OCC);
+        const bool interior = occ && r >= 1 && r <= TH && c >= 1 && c <= TW;
+        uint32_t slot = wappend(&s_n[0], occ);
+        if (occ) s_occ[slot] = (uint16_t)si;
+        slot = wappend(&s_n[1], interior);
+        if (interior) s_agent[slot] = (uint16_t)((r - 1) * TW + (c - 1));
+    }
+    __syncthreads();
+    // ---- per-step die roll (:364) of every occupied cell in reach -- recomputed, not communicated
+    const unsigned int n_occ = s_n[0], n_agent = s_n[1];
+    for (unsigned int k = tid; k < n_occ; k += NT) {
+        const int si = s_occ[k];
+        const int r = si / SW, c = si - r * SW;
+        const uint32_t gx = (x0 + (uint32_t)(c - 16)) & (p.W - 1);
+        const uint32_t gy = (p.row0 + y0 + (uint32_t)(r - 1)) & (p.W - 1);
+        s_roll[si] = rng(p, ((uint64_t)gy << p.log2W) | gx, S_ROLL).x;
+    }
+    __syncthreads();
+    // ---- agents, 32 per warp iteration
+    unsigned int n_play_deaths = 0, n_movers = 0;
+    for (unsigned int base = warp * 32; base < n_agent; base += NT) {
+        const unsigned int a = base + lane;
+        const bool valid = a < n_agent;
+        const int cl = valid ? s_agent[a] : 0;
+        const int ly = cl / TW, lx = cl - ly * TW;
+        const int si = (ly + 1) * SW + lx + 16;
+        const uint32_t x = x0 + lx, y = y0 + ly;
+        const uint32_t t = s_tf[si], trait = t & TF_TRAIT, strat = s_st[si], roll = s_roll[si];
+        const uint64_t g = gcell_of(p, x, y);
+        uint32_t occ_mask = 0, gm = 0, rngm = 0, outc = 0;
+        bool act7_challenge = false, act0_respond = false;
+        if (valid) {
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                const int c = 7 - d;  // sub-step in which neighbour d would challenge me (:477)
+                const int sn = si + DY(d) * SW + DX(d);
+                const uint32_t tn = s_tf[sn];
+                if (!(tn & TF_OCC)) continue;
+                occ_mask |= 1u << d;
+                const uint32_t rn = s_roll[sn];
+                bool n_higher = rn > roll;
+                if (rn == roll) n_higher = nb_gcell(p, x, y, d) > g;  // tie -> cell index (:413)
+                if (d == 7) act7_challenge = !n_higher;
+                if (d == 0) act0_respond = n_higher;
+                if (!n_higher) continue;
+                const uint32_t dn = (tn & TF_D) >> TF_D_SHIFT;
+                if (dn != 0u && (int)dn - 1 < c) continue;  // that challenger dies before sub-step c
+                const uint32_t mine = (strat >> (2 * (tn & TF_TRAIT))) & 3u;       // :599
+                const uint32_t theirs = ((uint32_t)s_st[sn] >> (2 * trait)) & 3u;  // :600
+                gm |= 1u << c;
+                if (p.noise_thr != 0ull || mine == 3u || theirs == 3u) rngm |= 1u << c;
+                else outc |= ((((uint32_t)(mine != 1u)) << 1) | (uint32_t)(theirs != 1u)) << (2 * c);
+            }
+        }
+        // ---- games that need random words: queue them warp-wide and draw with all lanes busy
+        const int cnt = __popc(rngm);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int off = incl - cnt;
+        const int total = __shfl_sync(FULL, incl, 31);
+        {
+            uint32_t m = rngm;
+            int k = off;
+            while (m) {
+                const int c = __ffs(m) - 1;
+                m &= m - 1;
+                s_q[warp][k++] = (uint16_t)((lane << 3) | c);
+            }
+        }
+        __syncwarp();
+        for (int q0 = 0; q0 < total; q0 += 32) {
+            const int q = q0 + lane;
+            const bool active = q < total;
+            const uint32_t ent = active ? s_q[warp][q] : 0u;
+            const int src = (int)(ent >> 3), c = (int)(ent & 7u);
+            const int si_l = __shfl_sync(FULL, si, src);
+            if (active) {
+                const int d = 7 - c;
+                const int sn = si_l + DY(d) * SW + DX(d);
+                const uint32_t tl = s_tf[si_l], tn = s_tf[sn];
+                const uint32_t mine = ((uint32_t)s_st[si_l] >> (2 * (tn & TF_TRAIT))) & 3u;
+                const uint32_t theirs = ((uint32_t)s_st[sn] >> (2 * (tl & TF_TRAIT))) & 3u;
+                const int rl = si_l / SW, cc = si_l - rl * SW;
+                const uint64_t gl = gcell_of(p, x0 + (uint32_t)(cc - 16), y0 + (uint32_t)(rl - 1));
+                s_qo[warp][q] = (uint8_t)game_outcome_rng(p, gl, c, mine, theirs);
+            }
+        }
+        __syncwarp();
+        {
+            uint32_t m = rngm;
+            int k = off;
+            while (m) {
+                const int c = __ffs(m) - 1;
+                m &= m - 1;
+                outc |= (uint32_t)s_qo[warp][k++] << (2 * c);
+            }
+        }
+        // ---- my games in sub-step order (:677-710), terminal rule, travel decision
+        bool mover = false;
+        if (valid) {
+            float e = s_e[cl];
+            int games = 0;
+            bool dead = false;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (!((gm >> c) & 1u) || dead) continue;
+                e = __fadd_rn(e, p.pay[(outc >> (2 * c)) & 3u]);   // :679-688
+                if (e <= 0.0f) dead = true;                        // :695-697
+                else { e = fminf(e, p.max_energy); ++games; }      // :698-710
+            }
+            if (dead) {
+                s_out[cl] = (uint8_t)TF_GHOST;
+                s_e[cl] = 0.0f;
+                ++n_play_deaths;
+            } else {
+                // terminal rule (:547-556, :719-730, :486-496) or no neighbours (:429-433)
+                mover = occ_mask == 0u || (games == 0 && (act7_challenge || act0_respond));
+                s_out[cl] = (uint8_t)(TF_OCC | trait);
+                s_e[cl] = e;
+            }
+        }
+        const uint32_t slot = wappend(&s_n[2], mover);
+        if (mover) { s_mover[slot] = (uint16_t)cl; ++n_movers; }
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- movers: travel cost, death, random start, probe, claim (:794-868)
+    const unsigned int n_mover = s_n[2];
+    unsigned int n_travel_deaths = 0;
+    for (unsigned int k = tid; k < n_mover; k += NT) {
+        const int cl = s_mover[k];
+        const int ly = cl / TW, lx = cl - ly * TW;
+        const int si = (ly + 1) * SW + lx + 16;
+        const float e = __fsub_rn(s_e[cl], p.travel_cost);  // :800
+        if (e <= 0.0f) {                                    // :801-804
+            s_out[cl] = (uint8_t)TF_GHOST;
+            s_e[cl] = 0.0f;
+            ++n_travel_deaths;
+            continue;
+        }
+        s_e[cl] = e;
+        uint32_t occ_mask = 0;
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+            if (s_tf[si + DY(d) * SW + DX(d)] & TF_OCC) occ_mask |= 1u << d;
+        const Words w = rng(p, gcell_of(p, x0 + lx, y0 + ly), S_ROLL);
+        int l = (int)(w.z >> 29), seq = 0;  // :810
+        const int dir = probe(occ_mask, l, seq);
+        if (dir >= 0) s_out[cl] = (uint8_t)(s_out[cl] | TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT));
+    }
+    __syncthreads();
+    // ---- coalesced stores
+    for (int i = tid; i < NC / 16; i += NT) {
+        const int ly = (i * 16) / TW, lx = (i * 16) - ly * TW;
+        *reinterpret_cast<uint4*>(p.tfB + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = reinterpret_cast<uint4*>(s_out)[i];
+    }
+    for (int i = tid; i < NC / 4; i += NT) {
+        const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
+        *reinterpret_cast<float4*>(p.E1 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = reinterpret_cast<float4*>(s_e)[i];
+    }
+    if (p.stats) {
+        if (n_play_deaths) atomicAdd(&p.ctr->st_play_deaths, (unsigned long long)n_play_deaths);
+        if (n_movers) atomicAdd(&p.ctr->st_movers, (unsigned long long)n_movers);
+        if (n_travel_deaths) atomicAdd(&p.ctr->st_travel_deaths, (unsigned long long)n_travel_deaths);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Claim resolution shared by k_move_commit and k_repro_commit.
+// s_tf: flags with a 2-cell halo; s_cl (same geometry, zeroed by the caller): on return every
+// cell of tile + 1-ring holds at most ONE bit: bit j set = "my neighbour j wins me".
+// A claimant with direction d therefore won iff bit (7-d) of its target's byte is set.
+// ------------------------------------------------------------------------------------------
+template <int TW, int TH, typename KeyFn>
+__device__ __forceinline__ void resolve_claims(const Params& p, const uint8_t* s_tf, uint8_t* s_cl,
+                                               uint16_t* s_list, unsigned int* s_cnt, uint32_t x0,
+                                               uint32_t y0, KeyFn keyfn) {
+    constexpr int SW = TW + 32, SH = TH + 4, RW2 = TW + 4, RW1 = TW + 2;
+    const int tid = threadIdx.x;
+    // scatter one bit per claimant (claimants are sparse: <= ~10 % of cells)
+    for (int i = tid; i < SH * RW2; i += NT) {
+        const int r = i / RW2, c = i - r * RW2;
+        const int si = r * SW + 14 + c;
+        const uint32_t t = s_tf[si];
+        if (!(t & TF_CLAIM)) continue;
+        const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
+        const int e = d + (d >= 4 ? 1 : 0);
+        const int dx = e / 3 - 1, dy = e - (e / 3) * 3 - 1;
+        const int rr = r + dy, cc = c + dx;
+        if (rr < 1 || rr > TH + 2 || cc < 1 || cc > TW + 2) continue;
+        const int st = si + dy * SW + dx;
+        atomicOr(reinterpret_cast<unsigned int*>(s_cl) + (st >> 2), (1u << (7 - d)) << (8 * (st & 3)));
+    }
+    __syncthreads();
+    // contested cells (>= 2 claimants) -> list
+    for (int base = 0; base < (TH + 2) * RW1; base += NT) {
+        const int i = base + tid;
+        const bool valid = i < (TH + 2) * RW1;
+        const int r = valid ? i / RW1 + 1 : 1, c = valid ? i - (i / RW1) * RW1 + 1 : 1;
+        const int si = r * SW + 14 + c;
+        const uint32_t m = valid ? s_cl[si] : 0u;
+        const bool contested = (m & (m - 1u)) != 0u;
+        const uint32_t slot = wappend(s_cnt, contested);
+        if (contested) s_list[slot] = (uint16_t)si;
+    }
+    __syncthreads();
+    const unsigned int n = *s_cnt;
+    for (unsigned int k = tid; k < n; k += NT) {
+        const int si = s_list[k];
+        const int r = si / SW, c = si - r * SW;
+        const uint32_t tx = (x0 + (uint32_t)(c - 16)) & (p.W - 1);
+        const uint32_t ty = (y0 + (uint32_t)(r - 2)) & (p.H - 1);
+        uint32_t m = s_cl[si];
+        int best = -1;
+        Key bk;
+        while (m) {  // highest (priority, cell) wins (:929, :1192)
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const Key k2 = keyfn(p, nb_gcell(p, tx, ty, j));
+            if (best < 0 || key_gt(k2, bk)) { bk = k2; best = j; }
+        }
+        s_cl[si] = (uint8_t)(1u << best);
+    }
+    __syncthreads();
+}
+
+// copy a CTA-local list of local cell indices to a global list (one atomic per CTA)
+template <int TW>
+__device__ __forceinline__ void flush_cells(const Params& p, const uint16_t* s_list, unsigned int n,
+                                            unsigned int* gcounter, uint32_t* gcell_list,
+                                            const uint8_t* s_state, uint8_t* gstate, uint32_t x0,
+                                            uint32_t y0, unsigned int* s_slot) {
+    const unsigned int base = cta_reserve(gcounter, n, s_slot);
+    if (n == 0) return;
+    if (base + n > p.list_cap) {
+        if (threadIdx.x == 0) atomicExch(&p.ctr->overflow, 1u);
+        return;
+    }
+    for (unsigned int k = threadIdx.x; k < n; k += NT) {
+        const int cl = s_list[k];
+        const int ly = cl / TW, lx = cl - ly * TW;
+        gcell_list[base + k] = ((y0 + ly) << p.log2W) | (x0 + lx);
+        if (gstate) gstate[base + k] = s_state[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_move_commit (dense sweep 2): move_response (:881-960), round 1.
+// ------------------------------------------------------------------------------------------
+template <int TW, int TH>
+__global__ void __launch_bounds__(NT) k_move_commit(const __grid_constant__ Params p) {
+    constexpr int SW = TW + 32, SH = TH + 4, NC = TW * TH;
+    __shared__ __align__(16) uint8_t s_tf[SH * SW];
+    __shared__ __align__(16) uint8_t s_cl[SH * SW];
+    __shared__ uint16_t s_list[(TH + 2) * (TW + 2)];
+    __shared__ uint16_t s_lost[NC];
+    __shared__ uint8_t s_lost_state[NC];
+    __shared__ unsigned int s_n[4];
+    const int tid = threadIdx.x;
+    const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    if (tid < 4) s_n[tid] = 0;
+    load_tile_vec<TW, TH, 2>(p, p.tfB, s_tf, x0, y0);
+    for (int i = tid; i < SH * SW / 16; i += NT) reinterpret_cast<uint4*>(s_cl)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    resolve_claims<TW, TH>(p, s_tf, s_cl, s_list, &s_n[0], x0, y0, TravelKey());
+    unsigned int n_moved = 0;
+    for (int i = tid; i < NC / 4; i += NT) {
+        const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
+        const int si = (ly + 2) * SW + lx + 16;
+        const uint32_t t4 = *reinterpret_cast<const uint32_t*>(s_tf + si);
+        const uint32_t c4 = *reinterpret_cast<const uint32_t*>(s_cl + si);
+        uint32_t out4 = t4 & 0x87878787u;  // OCC | GHOST | trait
+        if ((t4 & 0x40404040u) | c4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t t = (t4 >> (8 * k)) & 0xFFu, cl = (c4 >> (8 * k)) & 0xFFu;
+                const uint32_t x = x0 + lx + k, y = y0 + ly;
+                if (t & TF_CLAIM) {
+                    const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
+                    const int e = d + (d >= 4 ? 1 : 0);
+                    const int st = si + k + (e - (e / 3) * 3 - 1) * SW + (e / 3 - 1);
+                    if ((s_cl[st] >> (7 - d)) & 1u) {
+                        // moved away; the cell still blocks movers for the rest of the step (B-13)
+                        out4 = (out4 & ~(0xFFu << (8 * k))) | (TF_GHOST << (8 * k));
+                    } else {  // :940-943 -> retry with the same roll, next start = d+1 (:848)
+                        const int s = (int)(rng(p, gcell_of(p, x, y), S_ROLL).z >> 29);
+                        const unsigned int slot = atomicAdd(&s_n[1], 1u);
+                        s_lost[slot] = (uint16_t)(ly * TW + lx + k);
+                        s_lost_state[slot] = (uint8_t)(0x80u | (uint32_t)((d + 1) & 7) | ((uint32_t)probe_pos(s, d) << 3));
+                    }
+                } else if (cl) {  // the winner relocates here (:946-956)
+                    const int j = __ffs(cl) - 1;
+                    const int e = j + (j >= 4 ? 1 : 0);
+                    const uint32_t tn = s_tf[si + k + (e - (e / 3) * 3 - 1) * SW + (e / 3 - 1)];
+                    const uint32_t src = nb_local(p, x, y, j);
+                    const size_t cell = ((size_t)y << p.log2W) | x;
+                    p.E1[cell] = p.E1[src];
+                    p.strat[cell] = p.strat[src];
+                    out4 = (out4 & ~(0xFFu << (8 * k))) | ((TF_OCC | (tn & TF_TRAIT)) << (8 * k));
+                    ++n_moved;
+                }
+            }
+        }
+        *reinterpret_cast<uint32_t*>(p.tfA + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = out4;
+    }
+    __syncthreads();
+    flush_cells<TW>(p, s_lost, s_n[1], &p.ctr->mv_n, p.mv_cell, s_lost_state, p.mv_state, x0, y0, &s_n[2]);
+    if (p.stats && n_moved) atomicAdd(&p.ctr->st_moved, (unsigned long long)n_moved);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_repro_claim (dense sweep 3): neighbourhood_update (:975-1031) + first god_go_forth
+// (:1042-1134).  GHOSTs are free cells again.
+// ------------------------------------------------------------------------------------------
+template <int TW, int TH>
+__global__ void __launch_bounds__(NT) k_repro_claim(const __grid_constant__ Params p) {
+    constexpr int SW = TW + 32, SH = TH + 2, NC = TW * TH;
+    __shared__ __align__(16) uint8_t s_tf[SH * SW];
+    __shared__ __align__(16) uint8_t s_out[NC];
+    __shared__ uint16_t s_par[NC];
+    __shared__ unsigned int s_n[2];
+    const int tid = threadIdx.x;
+    const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    if (tid < 2) s_n[tid] = 0;
+    load_tile_vec<TW, TH, 1>(p, p.tfA, s_tf, x0, y0);
+    __syncthreads();
+    for (int base = 0; base < NC / 4; base += NT) {
+        const int i = base + tid;
+        const bool valid = i < NC / 4;
+        const int ly = valid ? (i * 4) / TW : 0, lx = valid ? (i * 4) - ly * TW : 0;
+        const int si = (ly + 1) * SW + lx + 16;
+        const uint32_t t4 = valid ? *reinterpret_cast<const uint32_t*>(s_tf + si) : 0u;
+        float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && (t4 & 0x80808080u))
+            e4 = *reinterpret_cast<const float4*>(p.E1 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx);
+        const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+        uint32_t out4 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t t = (t4 >> (8 * k)) & 0xFFu;
+            const bool occ = (t & TF_OCC) != 0u;
+            if (occ) out4 |= (TF_OCC | (t & TF_TRAIT)) << (8 * k);
+            const bool eligible = occ && p.max_children > 0u && ev[k] >= p.reproduce_min_energy;  // :978, :1054
+            const uint32_t slot = wappend(&s_n[0], eligible);
+            if (eligible) s_par[slot] = (uint16_t)(ly * TW + lx + k);
+        }
+        if (valid) *reinterpret_cast<uint32_t*>(s_out + i * 4) = out4;
+    }
+    __syncthreads();
+    const unsigned int n_par = s_n[0];
+    for (unsigned int k = tid; k < n_par; k += NT) {
+        const int cl = s_par[k];
+        const int ly = cl / TW, lx = cl - ly * TW;
+        const int si = (ly + 1) * SW + lx + 16;
+        uint32_t occ_mask = 0;
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+            if (s_tf[si + DY(d) * SW + DX(d)] & TF_OCC) occ_mask |= 1u << d;
+        if (occ_mask == 0xFFu) continue;  // REPRODUCTION_IMPOSSIBLE (:1028)
+        const Words w = rng(p, gcell_of(p, x0 + lx, y0 + ly), S_REPRO);
+        int l = (int)(w.y >> 29), seq = 0;  // :1079
+        const int dir = probe(occ_mask, l, seq);
+        if (dir >= 0) s_out[cl] = (uint8_t)(s_out[cl] | TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT));
+    }
+    __syncthreads();
+    for (int i = tid; i < NC / 16; i += NT) {
+        const int ly = (i * 16) / TW, lx = (i * 16) - ly * TW;
+        *reinterpret_cast<uint4*>(p.tfB + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = reinterpret_cast<uint4*>(s_out)[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_repro_commit (dense sweep 4): god_multiply round 1 (:1144-1335) + environmental_punishment
+// (:1339-1371) + step_fn's counts (:1405-1419).  Claim losers go to the repro-loser list and
+// their living cost is deferred to k_finalize (a retry round may still charge them the
+// reproduction cost first).  An agent that dies of living cost keeps its cell (DYING) until the
+// retry rounds are over, exactly like in the reference where the punishment layer runs after
+// the god submodel.
+// ------------------------------------------------------------------------------------------
+template <int TW, int TH>
+__global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Params p) {
+    constexpr int SW = TW + 32, SH = TH + 4, NC = TW * TH;
+    __shared__ __align__(16) uint8_t s_tf[SH * SW];
+    __shared__ __align__(16) uint8_t s_cl[SH * SW];
+    __shared__ uint16_t s_list[(TH + 2) * (TW + 2)];
+    __shared__ uint16_t s_birth[NC];  // cells that receive a child
+    __shared__ uint16_t s_lost[NC];
+    __shared__ uint8_t s_lost_state[NC];
+    __shared__ uint16_t s_risk[NC];
+    __shared__ uint16_t s_dead[NC];
+    __shared__ float s_ce[NC];        // child energy by cell (only written/read for birth cells)
+    __shared__ unsigned int s_bins[16];
+    __shared__ unsigned int s_n[8];   // 0 contested, 1 births, 2 lost, 3 risk, 4 dead, 5 n_old, 6 slot, 7 living deaths
+    const int tid = threadIdx.x;
+    const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    if (tid < 8) s_n[tid] = 0;
+    if (tid < 16) s_bins[tid] = 0;
+    load_tile_vec<TW, TH, 2>(p, p.tfB, s_tf, x0, y0);
+    for (int i = tid; i < SH * SW / 16; i += NT) reinterpret_cast<uint4*>(s_cl)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    resolve_claims<TW, TH>(p, s_tf, s_cl, s_list, &s_n[0], x0, y0, ReproKey());
+    // ---- cells of this tile that receive a child
+    for (int base = 0; base < NC; base += NT) {
+        const int cl = base + tid;  // NC is a multiple of NT
+        const int ly = cl / TW, lx = cl - ly * TW;
+        const bool born = s_cl[(ly + 2) * SW + lx + 16] != 0;
+        const uint32_t slot = wappend(&s_n[1], born);
+        if (born) s_birth[slot] = (uint16_t)cl;
+    }
+    __syncthreads();
+    const unsigned int n_birth = s_n[1];
+    // ---- the children (:1216-1328), all lanes busy
+    for (unsigned int k = tid; k < n_birth; k += NT) {
+        const int cl = s_birth[k];
+        const int ly = cl / TW, lx = cl - ly * TW;
+        const int si = (ly + 2) * SW + lx + 16;
+        const uint32_t x = x0 + lx, y = y0 + ly;
+        const int j = __ffs((uint32_t)s_cl[si]) - 1;  // the winning neighbour
+        const int e = j + (j >= 4 ? 1 : 0);
+        const uint32_t tn = s_tf[si + (e - (e / 3) * 3 - 1) * SW + (e / 3 - 1)];
+        const uint32_t src = nb_local(p, x, y, j);
+        const float pe = __fsub_rn(p.E1[src], p.reproduce_cost);
+        float ce;
+        uint32_t cs;
+        make_child(p, nb_gcell(p, x, y, j), p.strat[src], tn & TF_TRAIT, pe, ce, cs);
+        p.strat[((size_t)y << p.log2W) | x] = (uint8_t)cs;
+        s_ce[cl] = ce;
+    }
+    __syncthreads();
+    // ---- main loop, 4 cells per thread
+    unsigned int n_old = 0, n_dead = 0;
+    for (int i = tid; i < NC / 4; i += NT) {
+        const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
+        const int si = (ly + 2) * SW + lx + 16;
+        const size_t cell0 = ((size_t)(y0 + ly) << p.log2W) + x0 + lx;
+        const uint32_t t4 = *reinterpret_cast<const uint32_t*>(s_tf + si);
+        const uint32_t c4 = *reinterpret_cast<const uint32_t*>(s_cl + si);
+        float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t st4 = 0;
+        if (t4 & 0x80808080u) {
+            e4 = *reinterpret_cast<const float4*>(p.E1 + cell0);
+            if (p.want_counts) st4 = *reinterpret_cast<const uint32_t*>(p.strat + cell0);
+        }
+        float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+        uint32_t out4 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t t = (t4 >> (8 * k)) & 0xFFu, cb = (c4 >> (8 * k)) & 0xFFu;
+            const int cl = ly * TW + lx + k;
+            if (t & TF_OCC) {
+                ++n_old;
+                const uint32_t trait = t & TF_TRAIT;
+                float e = ev[k];
+                bool lost = false;
+                if (t & TF_CLAIM) {
+                    const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
+                    const int ee = d + (d >= 4 ? 1 : 0);
+                    const int st = si + k + (ee - (ee / 3) * 3 - 1) * SW + (ee / 3 - 1);
+                    if ((s_cl[st] >> (7 - d)) & 1u) {
+                        e = __fsub_rn(e, p.reproduce_cost);  // :1211-1213
+                    } else {  // stays ATTEMPTING_REPRODUCTION (:1203-1205): retry list, living cost deferred
+                        lost = true;
+                        const int s = (int)(rng(p, gcell_of(p, x0 + lx + k, y0 + ly), S_REPRO).y >> 29);
+                        const unsigned int slot = atomicAdd(&s_n[2], 1u);
+                        s_lost[slot] = (uint16_t)cl;
+                        s_lost_state[slot] = (uint8_t)(0x80u | (uint32_t)((d + 1) & 7) | ((uint32_t)probe_pos(s, d) << 3));
+                    }
+                }
+                if (lost) {
+                    out4 |= (TF_OCC | trait) << (8 * k);
+                    ev[k] = e;
+                } else if (punish(p, e)) {
+                    out4 |= (TF_OCC | trait) << (8 * k);
+                    ev[k] = e;
+                    if (e <= p.risk_thr) s_risk[atomicAdd(&s_n[3], 1u)] = (uint16_t)cl;
+                    if (p.want_counts) atomicAdd(&s_bins[count_bin((st4 >> (8 * k)) & 0xFFu, trait)], 1u);
+                } else {
+                    // dies (:1364-1366) -- but the punishment layer runs AFTER the god submodel, so the
+                    // cell stays occupied for the reproduction retry rounds; k_finalize clears it
+                    out4 |= (TF_OCC | TF_DYING) << (8 * k);
+                    ev[k] = 0.0f;
+                    s_dead[atomicAdd(&s_n[4], 1u)] = (uint16_t)cl;
+                    ++n_dead;
+                }
+            } else if (cb) {  // a child was born here: the winner's trait, energy from the birth pass
+                const int j = __ffs(cb) - 1;
+                const int e = j + (j >= 4 ? 1 : 0);
+                const uint32_t tn = s_tf[si + k + (e - (e / 3) * 3 - 1) * SW + (e / 3 - 1)];
+                out4 |= (TF_OCC | TF_NEWBORN | (tn & TF_TRAIT)) << (8 * k);
+                ev[k] = s_ce[cl];
+            } else {
+                ev[k] = 0.0f;
+            }
+        }
+        *reinterpret_cast<uint32_t*>(p.tfA + cell0) = out4;
+        *reinterpret_cast<float4*>(p.E0 + cell0) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+    }
+    if (n_old) atomicAdd(&s_n[5], n_old);
+    if (n_dead) atomicAdd(&s_n[7], n_dead);
+    __syncthreads();
+    flush_cells<TW>(p, s_lost, s_n[2], &p.ctr->rp_n, p.rp_cell, s_lost_state, p.rp_state, x0, y0, &s_n[6]);
+    flush_cells<TW>(p, s_birth, n_birth, &p.ctr->nb_n, p.nb_cell, nullptr, nullptr, x0, y0, &s_n[6]);
+    flush_cells<TW>(p, s_risk, s_n[3], &p.ctr->risk_next_n, p.risk_next, nullptr, nullptr, x0, y0, &s_n[6]);
+    flush_cells<TW>(p, s_dead, s_n[4], &p.ctr->dead_n, p.dead_cell, nullptr, nullptr, x0, y0, &s_n[6]);
+    if (tid == 0) {
+        if (s_n[5]) atomicAdd(&p.ctr->n_old, (unsigned long long)s_n[5]);
+        if (n_birth) atomicAdd(&p.ctr->births, (unsigned long long)n_birth);
+        if (s_n[7]) atomicAdd(&p.ctr->living_deaths, (unsigned long long)s_n[7]);
+    }
+    if (p.want_counts && tid < 16 && s_bins[tid]) atomicAdd(&p.ctr->bins[tid], (unsigned long long)s_bins[tid]);
+}
+
+}  // namespace pd

@@ -16,41 +16,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "pd_device.cuh"
+#include "pd_dense.cuh"
 
 namespace pd {
-
-constexpr int NT = 256;  // threads per CTA of the dense sweeps
-
-// ------------------------------------------------------------------------------------------
-// tile loader: (TH + 2*HALO) x (TW + 2*HALO) bytes of a u8 plane into shared memory, wrapping
-// ------------------------------------------------------------------------------------------
-template <int TW, int TH, int HALO>
-__device__ __forceinline__ void load_tile_u8(const Params& p, const uint8_t* __restrict__ plane,
-                                             uint8_t* s, uint32_t x0, uint32_t y0) {
-    constexpr int SW = TW + 2 * HALO;
-    constexpr int SH = TH + 2 * HALO;
-    for (int i = threadIdx.x; i < SW * SH; i += NT) {
-        const int r = i / SW, c = i - r * SW;
-        const uint32_t gx = (x0 + (uint32_t)(c - HALO)) & (p.W - 1);
-        const uint32_t gy = (y0 + (uint32_t)(r - HALO)) & (p.H - 1);
-        s[i] = plane[((size_t)gy << p.log2W) | gx];
-    }
-}
-
-// contest key of a claimant: (priority word, global cell) -- higher wins (:929, :1192)
-struct Key {
-    uint32_t prio;
-    uint64_t gcell;
-};
-__device__ __forceinline__ bool key_gt(const Key& a, const Key& b) {
-    return a.prio > b.prio || (a.prio == b.prio && a.gcell > b.gcell);
-}
-__device__ __forceinline__ Key travel_key(const Params& p, uint64_t g) {
-    Key k; k.prio = rng(p, g, S_ROLL).y; k.gcell = g; return k;  // :806
-}
-__device__ __forceinline__ Key repro_key(const Params& p, uint64_t g) {
-    Key k; k.prio = rng(p, g, S_REPRO).x; k.gcell = g; return k;  // :1076
-}
 
 // ------------------------------------------------------------------------------------------
 __global__ void k_begin_step(Counters* ctr, int count_step) {
@@ -118,193 +86,6 @@ __global__ void __launch_bounds__(1024) k_risk_resolve(const __grid_constant__ P
 }
 
 // ------------------------------------------------------------------------------------------
-// k_play_travel (dense sweep 1).  Fuses search_for_neighbours (:352-372), get_game_list
-// (:373-440), the 8 iterations of play_challenge/play_response (:450-734) with exit_play_fn's
-// terminal rule, and the first move_request (:784-872).  tfA, strat (1-cell halo) -> tfB, E1.
-// ------------------------------------------------------------------------------------------
-template <int TW, int TH>
-__global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Params p) {
-    constexpr int SW = TW + 2, SH = TH + 2;
-    __shared__ uint8_t s_tf[SW * SH];
-    __shared__ uint8_t s_st[SW * SH];
-    __shared__ uint32_t s_roll[SW * SH];
-    const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    load_tile_u8<TW, TH, 1>(p, p.tfA, s_tf, x0, y0);
-    load_tile_u8<TW, TH, 1>(p, p.strat, s_st, x0, y0);
-    __syncthreads();
-    // per-step die roll of every occupied cell of the tile + halo (:364) -- recomputed, not communicated
-    for (int i = threadIdx.x; i < SW * SH; i += NT) {
-        uint32_t roll = 0;
-        if (s_tf[i] & TF_OCC) {
-            const int r = i / SW, c = i - r * SW;
-            const uint32_t gx = (x0 + (uint32_t)(c - 1)) & (p.W - 1);
-            const uint32_t gy = (p.row0 + y0 + (uint32_t)(r - 1)) & (p.W - 1);
-            roll = rng(p, ((uint64_t)gy << p.log2W) | gx, S_ROLL).x;
-        }
-        s_roll[i] = roll;
-    }
-    __syncthreads();
-    unsigned int n_play_deaths = 0, n_movers = 0, n_travel_deaths = 0;
-    for (int i = threadIdx.x; i < TW * TH; i += NT) {
-        const int ly = i / TW, lx = i - ly * TW;
-        const int si = (ly + 1) * SW + lx + 1;
-        const uint32_t x = x0 + lx, y = y0 + ly;
-        const size_t cell = ((size_t)y << p.log2W) | x;
-        const uint32_t t = s_tf[si];
-        uint32_t out = 0;
-        float e_out = 0.0f;
-        if (t & TF_OCC) {
-            const uint32_t trait = t & TF_TRAIT;
-            const uint32_t strat = s_st[si];
-            const uint32_t roll = s_roll[si];
-            const uint64_t g = gcell_of(p, x, y);
-            float e = p.E0[cell];
-            uint32_t occ_mask = 0;
-            int games = 0;
-            bool dead = false, act7_challenge = false, act0_respond = false;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int d = 7 - c;
-                const int sn = si + DY(d) * SW + DX(d);
-                const uint32_t tn = s_tf[sn];
-                if (!(tn & TF_OCC)) continue;
-                occ_mask |= 1u << d;
-                const uint32_t rn = s_roll[sn];
-                bool n_higher = rn > roll;
-                if (rn == roll) n_higher = nb_gcell(p, x, y, d) > g;  // tie -> cell index (:413)
-                if (d == 7) act7_challenge = !n_higher;
-                if (d == 0) act0_respond = n_higher;
-                if (!n_higher || dead) continue;
-                const uint32_t dn = (tn & TF_D) >> TF_D_SHIFT;
-                if (dn != 0u && (int)dn - 1 < c) continue;  // challenger already dead
-                const float pay = game_payoff(p, g, c, strat, trait, s_st[sn], tn & TF_TRAIT);
-                e = __fadd_rn(e, pay);                       // :679-688
-                if (e <= 0.0f) dead = true;                  // :695-697
-                else { e = fminf(e, p.max_energy); ++games; }  // :698-710
-            }
-            if (dead) {
-                out = TF_GHOST;
-                ++n_play_deaths;
-            } else {
-                // terminal rule (:547-556, :719-730, :486-496) or no neighbours (:429-433)
-                const bool mover = occ_mask == 0u || (games == 0 && (act7_challenge || act0_respond));
-                out = TF_OCC | trait;
-                if (mover) {
-                    ++n_movers;
-                    e = __fsub_rn(e, p.travel_cost);  // :800
-                    if (e <= 0.0f) {                  // :801-804
-                        out = TF_GHOST;
-                        e = 0.0f;
-                        ++n_travel_deaths;
-                    } else {
-                        const Words w = rng(p, g, S_ROLL);
-                        int l = (int)(w.z >> 29), seq = 0;  // :810
-                        const int dir = probe(occ_mask, l, seq);
-                        if (dir >= 0) out |= TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT);
-                    }
-                }
-                e_out = e;
-            }
-        }
-        p.tfB[cell] = (uint8_t)out;
-        p.E1[cell] = e_out;
-    }
-    if (p.stats) {
-        if (n_play_deaths) atomicAdd(&p.ctr->st_play_deaths, (unsigned long long)n_play_deaths);
-        if (n_movers) atomicAdd(&p.ctr->st_movers, (unsigned long long)n_movers);
-        if (n_travel_deaths) atomicAdd(&p.ctr->st_travel_deaths, (unsigned long long)n_travel_deaths);
-    }
-}
-
-// does the claimant at smem index sn (2-halo tile) point at the cell that is `j` away from it?
-// i.e. is neighbour j OF THE TARGET a claimant of the target: its dir must be 7-j.
-__device__ __forceinline__ bool claims_dir(uint32_t t, int dir) {
-    return (t & TF_CLAIM) && (int)((t & TF_DIR) >> TF_DIR_SHIFT) == dir;
-}
-
-// ------------------------------------------------------------------------------------------
-// k_move_commit (dense sweep 2): move_response (:881-960), round 1.  tfB (2-cell halo) -> tfA.
-// An empty cell looks for claimants among its 8 neighbours and PULLS the winner's state; a
-// claimant re-evaluates the contest at its target (same inputs, same answer) and either
-// vacates (leaving a GHOST that keeps blocking movers this step) or joins the loser list.
-// ------------------------------------------------------------------------------------------
-template <int TW, int TH>
-__global__ void __launch_bounds__(NT) k_move_commit(const __grid_constant__ Params p) {
-    constexpr int SW = TW + 4;
-    __shared__ uint8_t s_tf[SW * (TH + 4)];
-    const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    load_tile_u8<TW, TH, 2>(p, p.tfB, s_tf, x0, y0);
-    __syncthreads();
-    unsigned int n_moved = 0;
-    constexpr int ITERS = (TW * TH + NT - 1) / NT;
-    for (int it = 0; it < ITERS; ++it) {
-        const int i = it * NT + threadIdx.x;
-        const bool valid = i < TW * TH;
-        const int ly = valid ? i / TW : 0, lx = valid ? i - ly * TW : 0;
-        const int si = (ly + 2) * SW + lx + 2;
-        const uint32_t x = x0 + lx, y = y0 + ly;
-        const size_t cell = ((size_t)y << p.log2W) | x;
-        const uint32_t t = valid ? s_tf[si] : 0u;
-        uint32_t out = t & (TF_OCC | TF_GHOST | TF_TRAIT);
-        bool lost = false;
-        uint32_t loser_state = 0;
-        if (valid && (t & TF_CLAIM)) {
-            const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
-            const int st = si + DY(d) * SW + DX(d);  // target
-            const uint32_t tx = x + (uint32_t)DX(d), ty = y + (uint32_t)DY(d);  // unwrapped
-            bool win = true, have_key = false;
-            Key mine;
-            const uint64_t g = gcell_of(p, x, y);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j == 7 - d) continue;  // that is me
-                const uint32_t tn = s_tf[st + DY(j) * SW + DX(j)];
-                if (!claims_dir(tn, 7 - j)) continue;
-                if (!have_key) { mine = travel_key(p, g); have_key = true; }
-                const Key other = travel_key(p, nb_gcell(p, tx & (p.W - 1), ty & (p.H - 1), j));
-                if (key_gt(other, mine)) win = false;
-            }
-            if (win) {
-                out = TF_GHOST;  // moved away; the cell still counts as occupied for movers (B-13)
-            } else {
-                lost = true;     // :940-943 -> retry with the same roll, next start = d+1 (:848)
-                const int s = (int)(rng(p, g, S_ROLL).z >> 29);
-                loser_state = 0x80u | (uint32_t)((d + 1) & 7) | ((uint32_t)probe_pos(s, d) << 3);
-            }
-        } else if (valid && !(t & (TF_OCC | TF_GHOST))) {
-            int best = -1;
-            Key bk;
-            int ncl = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t tn = s_tf[si + DY(j) * SW + DX(j)];
-                if (!claims_dir(tn, 7 - j)) continue;
-                ++ncl;
-                if (ncl == 1) { best = j; continue; }
-                if (ncl == 2) bk = travel_key(p, nb_gcell(p, x, y, best));
-                const Key k = travel_key(p, nb_gcell(p, x, y, j));
-                if (key_gt(k, bk)) { bk = k; best = j; }
-            }
-            if (best >= 0) {  // the winner relocates here (:946-956)
-                const uint32_t src = nb_local(p, x, y, best);
-                const uint32_t tn = s_tf[si + DY(best) * SW + DX(best)];
-                p.E1[cell] = p.E1[src];
-                p.strat[cell] = p.strat[src];
-                out = TF_OCC | (tn & TF_TRAIT);
-                ++n_moved;
-            }
-        }
-        const uint32_t slot = warp_append(&p.ctr->mv_n, lost);
-        if (lost) {
-            if (slot < p.list_cap) { p.mv_cell[slot] = (uint32_t)cell; p.mv_state[slot] = (uint8_t)loser_state; }
-            else atomicExch(&p.ctr->overflow, 1u);
-        }
-        if (valid) p.tfA[cell] = (uint8_t)out;
-    }
-    if (p.stats && n_moved) atomicAdd(&p.ctr->st_moved, (unsigned long long)n_moved);
-}
-
-// ------------------------------------------------------------------------------------------
 // k_move_retry (sparse, persistent): travel rounds 2..8 (exit_move_fn, :1559-1576) for the
 // losers of round 1.  Three phases per round separated by grid barriers:
 //   request  (:784-872)  probe from the saved direction over blocked = OCC|GHOST, post the claim
@@ -355,8 +136,8 @@ __global__ void __launch_bounds__(1024) k_move_retry(const __grid_constant__ Par
                 if (j == 7 - d) continue;
                 const uint32_t tn = __ldcg(p.tfA + nb_local(p, tx, ty, j));
                 if (!claims_dir(tn, 7 - j)) continue;
-                if (!have_key) { mine = travel_key(p, gcell_of(p, x, y)); have_key = true; }
-                if (key_gt(travel_key(p, nb_gcell(p, tx, ty, j)), mine)) win = false;
+                if (!have_key) { mine = TravelKey()(p, gcell_of(p, x, y)); have_key = true; }
+                if (key_gt(TravelKey()(p, nb_gcell(p, tx, ty, j)), mine)) win = false;
             }
             p.mv_aux[i] = (uint8_t)((uint32_t)d | (win ? 0x80u : 0u));
         }
@@ -386,186 +167,6 @@ __global__ void __launch_bounds__(1024) k_move_retry(const __grid_constant__ Par
         grid_sync(ctr->barrier, gridDim.x);
         if (__ldcg(&ctr->mv_active[round]) == 0u) break;
     }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_repro_claim (dense sweep 3): neighbourhood_update (:975-1031) + first god_go_forth
-// (:1042-1134).  tfA (1-cell halo; GHOSTs are free again) + E1 -> tfB.
-// ------------------------------------------------------------------------------------------
-template <int TW, int TH>
-__global__ void __launch_bounds__(NT) k_repro_claim(const __grid_constant__ Params p) {
-    constexpr int SW = TW + 2;
-    __shared__ uint8_t s_tf[SW * (TH + 2)];
-    const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    load_tile_u8<TW, TH, 1>(p, p.tfA, s_tf, x0, y0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < TW * TH; i += NT) {
-        const int ly = i / TW, lx = i - ly * TW;
-        const int si = (ly + 1) * SW + lx + 1;
-        const uint32_t x = x0 + lx, y = y0 + ly;
-        const size_t cell = ((size_t)y << p.log2W) | x;
-        const uint32_t t = s_tf[si];
-        uint32_t out = 0;
-        if (t & TF_OCC) {
-            out = TF_OCC | (t & TF_TRAIT);
-            if (p.max_children > 0u && p.E1[cell] >= p.reproduce_min_energy) {  // :978-979, :1054
-                uint32_t occ_mask = 0;
-#pragma unroll
-                for (int d = 0; d < 8; ++d)
-                    if (s_tf[si + DY(d) * SW + DX(d)] & TF_OCC) occ_mask |= 1u << d;
-                if (occ_mask != 0xFFu) {  // :1024-1027
-                    const Words w = rng(p, gcell_of(p, x, y), S_REPRO);
-                    int l = (int)(w.y >> 29), seq = 0;  // :1079
-                    const int dir = probe(occ_mask, l, seq);
-                    if (dir >= 0) out |= TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT);
-                }
-            }
-        }
-        p.tfB[cell] = (uint8_t)out;
-    }
-}
-
-// living cost for one agent (environmental_punishment, :1357-1368); returns false if it dies
-__device__ __forceinline__ bool punish(const Params& p, float& e) {
-    e = __fsub_rn(fminf(e, p.max_energy), p.cost_of_living);
-    return e > 0.0f;
-}
-
-// ------------------------------------------------------------------------------------------
-// k_repro_commit (dense sweep 4): god_multiply round 1 (:1144-1335) + environmental_punishment
-// (:1339-1371) + step_fn's counts (:1405-1419).  tfB (2-cell halo), E1, strat -> tfA, E0, strat.
-// Claim losers are appended to the repro-loser list and their living cost is deferred to
-// k_finalize (a retry round may still charge them the reproduction cost first).
-// ------------------------------------------------------------------------------------------
-template <int TW, int TH>
-__global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Params p) {
-    constexpr int SW = TW + 4;
-    __shared__ uint8_t s_tf[SW * (TH + 4)];
-    __shared__ unsigned int s_bins[16];
-    __shared__ unsigned int s_cnt[3];  // n_old, births, living_deaths
-    const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    if (threadIdx.x < 16) s_bins[threadIdx.x] = 0;
-    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
-    load_tile_u8<TW, TH, 2>(p, p.tfB, s_tf, x0, y0);
-    __syncthreads();
-    unsigned int n_old = 0, n_births = 0, n_dead = 0;
-    constexpr int ITERS = (TW * TH + NT - 1) / NT;
-    for (int it = 0; it < ITERS; ++it) {
-        const int i = it * NT + threadIdx.x;
-        const bool valid = i < TW * TH;
-        const int ly = valid ? i / TW : 0, lx = valid ? i - ly * TW : 0;
-        const int si = (ly + 2) * SW + lx + 2;
-        const uint32_t x = x0 + lx, y = y0 + ly;
-        const size_t cell = ((size_t)y << p.log2W) | x;
-        const uint32_t t = valid ? s_tf[si] : 0u;
-        uint32_t out = 0;
-        float e_out = 0.0f;
-        bool lost = false, newborn = false, at_risk = false, dying = false;
-        uint32_t loser_state = 0;
-        if (t & TF_OCC) {
-            ++n_old;
-            const uint32_t trait = t & TF_TRAIT;
-            float e = p.E1[cell];
-            if (t & TF_CLAIM) {
-                const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
-                const int st = si + DY(d) * SW + DX(d);
-                const uint32_t tx = (x + (uint32_t)DX(d)) & (p.W - 1);
-                const uint32_t ty = (y + (uint32_t)DY(d)) & (p.H - 1);
-                const uint64_t g = gcell_of(p, x, y);
-                bool win = true, have_key = false;
-                Key mine;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (j == 7 - d) continue;
-                    const uint32_t tn = s_tf[st + DY(j) * SW + DX(j)];
-                    if (!claims_dir(tn, 7 - j)) continue;
-                    if (!have_key) { mine = repro_key(p, g); have_key = true; }
-                    if (key_gt(repro_key(p, nb_gcell(p, tx, ty, j)), mine)) win = false;
-                }
-                if (win) {
-                    e = __fsub_rn(e, p.reproduce_cost);  // :1211-1213
-                } else {
-                    lost = true;  // stays ATTEMPTING_REPRODUCTION (:1203-1205)
-                    const int s = (int)(rng(p, g, S_REPRO).y >> 29);
-                    loser_state = 0x80u | (uint32_t)((d + 1) & 7) | ((uint32_t)probe_pos(s, d) << 3);
-                }
-            }
-            if (lost) {
-                out = TF_OCC | trait;
-                e_out = e;
-            } else if (punish(p, e)) {
-                out = TF_OCC | trait;
-                e_out = e;
-                at_risk = e <= p.risk_thr;
-                if (p.want_counts) atomicAdd(&s_bins[count_bin(p.strat[cell], trait)], 1u);
-            } else {
-                // dies (:1364-1366) -- but environmental_punishment runs AFTER the god submodel, so the
-                // cell stays occupied for the reproduction retry rounds; k_finalize clears it
-                out = TF_OCC | TF_DYING;
-                dying = true;
-                ++n_dead;
-            }
-        } else if (valid) {
-            int best = -1, ncl = 0;
-            Key bk;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t tn = s_tf[si + DY(j) * SW + DX(j)];
-                if (!claims_dir(tn, 7 - j)) continue;
-                ++ncl;
-                if (ncl == 1) { best = j; continue; }
-                if (ncl == 2) bk = repro_key(p, nb_gcell(p, x, y, best));
-                const Key k = repro_key(p, nb_gcell(p, x, y, j));
-                if (key_gt(k, bk)) { bk = k; best = j; }
-            }
-            if (best >= 0) {  // a child is born here (:1216-1328)
-                const uint32_t src = nb_local(p, x, y, best);
-                const uint32_t tn = s_tf[si + DY(best) * SW + DX(best)];
-                const float pe = __fsub_rn(p.E1[src], p.reproduce_cost);
-                uint32_t cs;
-                make_child(p, nb_gcell(p, x, y, best), p.strat[src], tn & TF_TRAIT, pe, e_out, cs);
-                p.strat[cell] = (uint8_t)cs;
-                out = TF_OCC | TF_NEWBORN | (tn & TF_TRAIT);
-                newborn = true;
-                ++n_births;
-            }
-        }
-        uint32_t slot = warp_append(&p.ctr->rp_n, lost);
-        if (lost) {
-            if (slot < p.list_cap) { p.rp_cell[slot] = (uint32_t)cell; p.rp_state[slot] = (uint8_t)loser_state; }
-            else atomicExch(&p.ctr->overflow, 1u);
-        }
-        slot = warp_append(&p.ctr->nb_n, newborn);
-        if (newborn) {
-            if (slot < p.list_cap) p.nb_cell[slot] = (uint32_t)cell;
-            else atomicExch(&p.ctr->overflow, 1u);
-        }
-        slot = warp_append(&p.ctr->risk_next_n, at_risk);
-        if (at_risk) {
-            if (slot < p.list_cap) p.risk_next[slot] = (uint32_t)cell;
-            else atomicExch(&p.ctr->overflow, 1u);
-        }
-        slot = warp_append(&p.ctr->dead_n, dying);
-        if (dying) {
-            if (slot < p.list_cap) p.dead_cell[slot] = (uint32_t)cell;
-            else atomicExch(&p.ctr->overflow, 1u);
-        }
-        if (valid) {
-            p.tfA[cell] = (uint8_t)out;
-            p.E0[cell] = e_out;
-        }
-    }
-    if (n_old) atomicAdd(&s_cnt[0], n_old);
-    if (n_births) atomicAdd(&s_cnt[1], n_births);
-    if (n_dead) atomicAdd(&s_cnt[2], n_dead);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_cnt[0]) atomicAdd(&p.ctr->n_old, (unsigned long long)s_cnt[0]);
-        if (s_cnt[1]) atomicAdd(&p.ctr->births, (unsigned long long)s_cnt[1]);
-        if (s_cnt[2]) atomicAdd(&p.ctr->living_deaths, (unsigned long long)s_cnt[2]);
-    }
-    if (p.want_counts && threadIdx.x < 16 && s_bins[threadIdx.x])
-        atomicAdd(&p.ctr->bins[threadIdx.x], (unsigned long long)s_bins[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -618,8 +219,8 @@ __global__ void __launch_bounds__(1024) k_repro_retry(const __grid_constant__ Pa
                 if (j == 7 - d) continue;
                 const uint32_t tn = __ldcg(p.tfA + nb_local(p, tx, ty, j));
                 if (!claims_dir(tn, 7 - j)) continue;
-                if (!have_key) { mine = repro_key(p, gcell_of(p, x, y)); have_key = true; }
-                if (key_gt(repro_key(p, nb_gcell(p, tx, ty, j)), mine)) win = false;
+                if (!have_key) { mine = ReproKey()(p, gcell_of(p, x, y)); have_key = true; }
+                if (key_gt(ReproKey()(p, nb_gcell(p, tx, ty, j)), mine)) win = false;
             }
             p.rp_aux[i] = (uint8_t)((uint32_t)d | (win ? 0x80u : 0u));
         }

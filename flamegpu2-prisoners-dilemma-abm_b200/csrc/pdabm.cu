@@ -273,6 +273,8 @@ int pd_bind_planes(pd_sim* s, float* energy, uint8_t* strat, uint8_t* tf) {
         if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged)
             return fail(PD_ERR_INVALID, "plane %d is not device memory", i);
     }
+    for (int i = 0; i < 3; ++i)
+        if (((uintptr_t)ptrs[i]) & 15u) return fail(PD_ERR_INVALID, "plane %d is not 16-byte aligned", i);
     s->P.E0 = energy; s->P.strat = strat; s->P.tfA = tf;
     s->bound = true;
     s->ready = false;
