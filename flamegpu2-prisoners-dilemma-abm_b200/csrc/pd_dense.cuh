@@ -107,55 +107,116 @@ __device__ __forceinline__ uint32_t game_outcome_rng(const Params& p, uint64_t m
 // k_play_travel (dense sweep 1).  Fuses search_for_neighbours (:352-372), get_game_list
 // (:373-440), the 8 iterations of play_challenge/play_response (:450-734) with exit_play_fn's
 // terminal rule, and the first move_request (:784-872).
+//
+// Per cell of tile + 1-ring a 32-bit word R is staged in shared memory: 0 for an empty cell,
+// 0x80000000 | roll >> 1 for an occupied one.  "Neighbour d is occupied AND challenges me" is then
+// the single comparison R[n] > R[me]; a (2^-31) tie of the truncated rolls falls back to the exact
+// (roll, cell) order.  The games found this way are queued warp-wide and evaluated 32 at a time;
+// those that need random words (RANDOM strategy or noise) are compacted once more so that the
+// Philox rounds always run with full lanes.
 // ------------------------------------------------------------------------------------------
+__constant__ int c_dir_dx[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+__constant__ int c_dir_dy[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+
+// exact "neighbour n (at direction d of local cell x,y) has the higher (roll, cell)" for the tie path
+__device__ __noinline__ bool exact_higher(const Params& p, uint32_t x, uint32_t y, int d) {
+    const uint64_t g = gcell_of(p, x, y), gn = nb_gcell(p, x, y, d);
+    const uint32_t r = rng(p, g, S_ROLL).x, rn = rng(p, gn, S_ROLL).x;
+    return rn > r || (rn == r && gn > g);  // :413, tie -> cell index
+}
+
+// append the byte indices (b0 + k) of the bytes of `occ4` that have bit 7 set; all 32 lanes call
+__device__ __forceinline__ void wappend4(unsigned int* cnt, uint16_t* list, uint32_t occ4, int b0) {
+    const int lane = threadIdx.x & 31;
+    const int n = __popc(occ4);
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) return;
+    unsigned int base = 0;
+    if (lane == 31) base = atomicAdd(cnt, (unsigned int)total);
+    base = __shfl_sync(FULL, base, 31);
+    unsigned int k = base + (unsigned int)(incl - n);
+    while (occ4) {
+        const int b = (__ffs(occ4) - 1) >> 3;
+        occ4 &= occ4 - 1;
+        list[k++] = (uint16_t)(b0 + b);
+    }
+}
+
 template <int TW, int TH>
 __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Params p) {
-    constexpr int SW = TW + 32, SH = TH + 2, NC = TW * TH, RW = TW + 2, NWARP = NT / 32;
+    constexpr int SW = TW + 32, SH = TH + 2, NC = TW * TH, NWARP = NT / 32;
+    constexpr int LOG_TW = TW == 128 ? 7 : 4;
+    static_assert(TW == 128 || TW == 16, "tile width");
     __shared__ __align__(16) uint8_t s_tf[SH * SW];
     __shared__ __align__(16) uint8_t s_st[SH * SW];
-    __shared__ uint32_t s_roll[SH * SW];
+    __shared__ __align__(16) uint32_t s_R[SH * SW];
     __shared__ __align__(16) float s_e[NC];
     __shared__ __align__(16) uint8_t s_out[NC];
-    __shared__ uint16_t s_occ[SH * RW];   // occupied entries of tile + 1-ring (shared-memory index)
-    __shared__ uint16_t s_agent[NC];      // occupied interior cells (local cell index)
+    __shared__ uint16_t s_cells[NC + 2 * (TW + 2) + 2 * TH];  // agents first (from 0), then ring cells
     __shared__ uint16_t s_mover[NC];
-    __shared__ uint16_t s_q[NWARP][256];  // per-warp queue of games that need a Philox call
-    __shared__ uint8_t s_qo[NWARP][256];
-    __shared__ unsigned int s_n[4];
+    __shared__ uint16_t s_q[NWARP][256];   // per-warp queue of games: lane << 3 | sub-step
+    __shared__ uint8_t s_qo[NWARP][256];   // their results: outcome | alive << 2
+    __shared__ uint16_t s_q2[NWARP][256];  // second level: queue slots that need a Philox call
+    __shared__ unsigned int s_n[4];        // 0 agents, 1 ring cells, 2 movers
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     if (tid < 4) s_n[tid] = 0;
     load_tile_vec<TW, TH, 1>(p, p.tfA, s_tf, x0, y0);
     load_tile_vec<TW, TH, 1>(p, p.strat, s_st, x0, y0);
     for (int i = tid; i < NC / 4; i += NT) {
-        const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
+        const int ly = (i * 4) >> LOG_TW, lx = (i * 4) & (TW - 1);
         reinterpret_cast<float4*>(s_e)[i] =
             *reinterpret_cast<const float4*>(p.E0 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx);
     }
     for (int i = tid; i < NC / 16; i += NT) reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < SH * SW / 4; i += NT) reinterpret_cast<uint4*>(s_R)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    // ---- compaction: occupied entries of the ring region, and the agents of this tile
-    for (int base = 0; base < SH * RW; base += NT) {
-        const int i = base + tid;
-        const bool valid = i < SH * RW;
-        const int r = valid ? i / RW : 0, c = valid ? i - r * RW : 0;
-        const int si = r * SW + 15 + c;
-        const bool occ = valid && (s_tf[si] & TF_OCC);
-        const bool interior = occ && r >= 1 && r <= TH && c >= 1 && c <= TW;
-        uint32_t slot = wappend(&s_n[0], occ);
-        if (occ) s_occ[slot] = (uint16_t)si;
-        slot = wappend(&s_n[1], interior);
-        if (interior) s_agent[slot] = (uint16_t)((r - 1) * TW + (c - 1));
+    // ---- compaction, 4 cells per lane: the agents of this tile ...
+    for (int base = 0; base < NC / 4; base += NT) {
+        const int i = base + tid;  // NC/4 is a multiple of 32, so whole warps are in or out
+        if (i < NC / 4) {
+            const int ly = (i * 4) >> LOG_TW, lx = (i * 4) & (TW - 1);
+            const int si = (ly + 1) * SW + lx + 16;
+            wappend4(&s_n[0], s_cells, *reinterpret_cast<const uint32_t*>(s_tf + si) & 0x80808080u, si);
+        }
+    }
+    __syncthreads();
+    // ... and the occupied cells of the 1-ring around it (they only need a roll)
+    const unsigned int n_agent = s_n[0];
+    {
+        constexpr int NRING = 2 * (TW + 2) + 2 * TH;
+        for (int base = 0; base < NRING; base += NT) {
+            const int i = base + tid;
+            int si = 0;
+            bool occ = false;
+            if (i < NRING) {
+                if (i < TW + 2) si = 15 + i;                                   // top row
+                else if (i < 2 * (TW + 2)) si = (SH - 1) * SW + 15 + (i - (TW + 2));  // bottom row
+                else {
+                    const int k = i - 2 * (TW + 2);                            // left / right columns
+                    si = (1 + (k >> 1)) * SW + ((k & 1) ? (16 + TW) : 15);
+                }
+                occ = (s_tf[si] & TF_OCC) != 0;
+            }
+            const uint32_t slot = wappend(&s_n[1], occ);
+            if (occ) s_cells[n_agent + slot] = (uint16_t)si;
+        }
     }
     __syncthreads();
     // ---- per-step die roll (:364) of every occupied cell in reach -- recomputed, not communicated
-    const unsigned int n_occ = s_n[0], n_agent = s_n[1];
-    for (unsigned int k = tid; k < n_occ; k += NT) {
-        const int si = s_occ[k];
+    const unsigned int n_roll = n_agent + s_n[1];
+    for (unsigned int k = tid; k < n_roll; k += NT) {
+        const int si = s_cells[k];
         const int r = si / SW, c = si - r * SW;
         const uint32_t gx = (x0 + (uint32_t)(c - 16)) & (p.W - 1);
         const uint32_t gy = (p.row0 + y0 + (uint32_t)(r - 1)) & (p.W - 1);
-        s_roll[si] = rng(p, ((uint64_t)gy << p.log2W) | gx, S_ROLL).x;
+        s_R[si] = 0x80000000u | (rng(p, ((uint64_t)gy << p.log2W) | gx, S_ROLL).x >> 1);
     }
     __syncthreads();
     // ---- agents, 32 per warp iteration
@@ -163,39 +224,22 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
     for (unsigned int base = warp * 32; base < n_agent; base += NT) {
         const unsigned int a = base + lane;
         const bool valid = a < n_agent;
-        const int cl = valid ? s_agent[a] : 0;
-        const int ly = cl / TW, lx = cl - ly * TW;
-        const int si = (ly + 1) * SW + lx + 16;
-        const uint32_t x = x0 + lx, y = y0 + ly;
-        const uint32_t t = s_tf[si], trait = t & TF_TRAIT, strat = s_st[si], roll = s_roll[si];
-        const uint64_t g = gcell_of(p, x, y);
-        uint32_t occ_mask = 0, gm = 0, rngm = 0, outc = 0;
-        bool act7_challenge = false, act0_respond = false;
-        if (valid) {
+        const int si = valid ? s_cells[a] : (SW + 16);
+        const int ly = si / SW - 1, lx = si - (ly + 1) * SW - 16;
+        const int cl = (ly << LOG_TW) | lx;
+        const uint32_t rme = valid ? s_R[si] : 0xFFFFFFFFu;
+        uint32_t occ_mask = 0, gm = 0;
 #pragma unroll
-            for (int d = 0; d < 8; ++d) {
-                const int c = 7 - d;  // sub-step in which neighbour d would challenge me (:477)
-                const int sn = si + DY(d) * SW + DX(d);
-                const uint32_t tn = s_tf[sn];
-                if (!(tn & TF_OCC)) continue;
-                occ_mask |= 1u << d;
-                const uint32_t rn = s_roll[sn];
-                bool n_higher = rn > roll;
-                if (rn == roll) n_higher = nb_gcell(p, x, y, d) > g;  // tie -> cell index (:413)
-                if (d == 7) act7_challenge = !n_higher;
-                if (d == 0) act0_respond = n_higher;
-                if (!n_higher) continue;
-                const uint32_t dn = (tn & TF_D) >> TF_D_SHIFT;
-                if (dn != 0u && (int)dn - 1 < c) continue;  // that challenger dies before sub-step c
-                const uint32_t mine = (strat >> (2 * (tn & TF_TRAIT))) & 3u;       // :599
-                const uint32_t theirs = ((uint32_t)s_st[sn] >> (2 * trait)) & 3u;  // :600
-                gm |= 1u << c;
-                if (p.noise_thr != 0ull || mine == 3u || theirs == 3u) rngm |= 1u << c;
-                else outc |= ((((uint32_t)(mine != 1u)) << 1) | (uint32_t)(theirs != 1u)) << (2 * c);
-            }
+        for (int d = 0; d < 8; ++d) {
+            const uint32_t rn = s_R[si + DY(d) * SW + DX(d)];
+            occ_mask |= (rn >> 31) << d;
+            bool hi = rn > rme;
+            if (rn == rme && valid) hi = exact_higher(p, x0 + lx, y0 + ly, d);  // 2^-31 per pair
+            gm |= (uint32_t)hi << (7 - d);  // bit c: neighbour 7-c challenges me in sub-step c (:477)
         }
-        // ---- games that need random words: queue them warp-wide and draw with all lanes busy
-        const int cnt = __popc(rngm);
+        if (!valid) { occ_mask = 0; gm = 0; }
+        // ---- queue my games (increasing sub-step order)
+        const int cnt = __popc(gm);
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -205,7 +249,7 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
         const int off = incl - cnt;
         const int total = __shfl_sync(FULL, incl, 31);
         {
-            uint32_t m = rngm;
+            uint32_t m = gm;
             int k = off;
             while (m) {
                 const int c = __ffs(m) - 1;
@@ -214,52 +258,75 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
             }
         }
         __syncwarp();
+        // ---- evaluate the games, 32 at a time; those that need random words go to the 2nd queue
+        const uint32_t pack = (uint32_t)si | ((uint32_t)cl << 16);
+        int n2 = 0;
         for (int q0 = 0; q0 < total; q0 += 32) {
             const int q = q0 + lane;
             const bool active = q < total;
             const uint32_t ent = active ? s_q[warp][q] : 0u;
-            const int src = (int)(ent >> 3), c = (int)(ent & 7u);
-            const int si_l = __shfl_sync(FULL, si, src);
+            const int c = (int)(ent & 7u), d = 7 - c;
+            const uint32_t pk = __shfl_sync(FULL, pack, (int)(ent >> 3));
+            bool need_rng = false;
             if (active) {
-                const int d = 7 - c;
-                const int sn = si_l + DY(d) * SW + DX(d);
+                const int si_l = (int)(pk & 0xFFFFu);
+                const int sn = si_l + c_dir_dy[d] * SW + c_dir_dx[d];
+                const uint32_t tl = s_tf[si_l], tn = s_tf[sn];
+                const uint32_t dn = (tn & TF_D) >> TF_D_SHIFT;
+                const uint32_t alive = (dn == 0u || (int)dn - 1 >= c) ? 4u : 0u;  // challenger still alive?
+                const uint32_t mine = ((uint32_t)s_st[si_l] >> (2 * (tn & TF_TRAIT))) & 3u;    // :599
+                const uint32_t theirs = ((uint32_t)s_st[sn] >> (2 * (tl & TF_TRAIT))) & 3u;    // :600
+                need_rng = alive && (p.noise_thr != 0ull || mine == 3u || theirs == 3u);
+                s_qo[warp][q] = (uint8_t)(alive | ((uint32_t)(mine != 1u) << 1) | (uint32_t)(theirs != 1u));
+            }
+            const unsigned int bal = __ballot_sync(FULL, need_rng);
+            if (need_rng) s_q2[warp][n2 + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)q;
+            n2 += __popc(bal);
+        }
+        __syncwarp();
+        for (int k0 = 0; k0 < n2; k0 += 32) {
+            const int k = k0 + lane;
+            const bool active = k < n2;
+            const int q = active ? s_q2[warp][k] : 0;
+            const uint32_t ent = s_q[warp][q];
+            const int c = (int)(ent & 7u), d = 7 - c;
+            const uint32_t pk = __shfl_sync(FULL, pack, (int)(ent >> 3));
+            if (active) {
+                const int si_l = (int)(pk & 0xFFFFu), cl_l = (int)(pk >> 16);
+                const int sn = si_l + c_dir_dy[d] * SW + c_dir_dx[d];
                 const uint32_t tl = s_tf[si_l], tn = s_tf[sn];
                 const uint32_t mine = ((uint32_t)s_st[si_l] >> (2 * (tn & TF_TRAIT))) & 3u;
                 const uint32_t theirs = ((uint32_t)s_st[sn] >> (2 * (tl & TF_TRAIT))) & 3u;
-                const int rl = si_l / SW, cc = si_l - rl * SW;
-                const uint64_t gl = gcell_of(p, x0 + (uint32_t)(cc - 16), y0 + (uint32_t)(rl - 1));
-                s_qo[warp][q] = (uint8_t)game_outcome_rng(p, gl, c, mine, theirs);
+                const uint64_t gl = gcell_of(p, x0 + (uint32_t)(cl_l & (TW - 1)), y0 + (uint32_t)(cl_l >> LOG_TW));
+                s_qo[warp][q] = (uint8_t)(4u | game_outcome_rng(p, gl, c, mine, theirs));
             }
         }
         __syncwarp();
-        {
-            uint32_t m = rngm;
-            int k = off;
-            while (m) {
-                const int c = __ffs(m) - 1;
-                m &= m - 1;
-                outc |= (uint32_t)s_qo[warp][k++] << (2 * c);
-            }
-        }
         // ---- my games in sub-step order (:677-710), terminal rule, travel decision
         bool mover = false;
         if (valid) {
             float e = s_e[cl];
             int games = 0;
             bool dead = false;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (!((gm >> c) & 1u) || dead) continue;
-                e = __fadd_rn(e, p.pay[(outc >> (2 * c)) & 3u]);   // :679-688
-                if (e <= 0.0f) dead = true;                        // :695-697
-                else { e = fminf(e, p.max_energy); ++games; }      // :698-710
+            for (int k = 0; k < cnt; ++k) {
+                const uint32_t o = s_qo[warp][off + k];
+                if (!(o & 4u)) continue;                      // the challenger died earlier: no message
+                e = __fadd_rn(e, p.pay[o & 3u]);              // :679-688
+                if (e <= 0.0f) { dead = true; break; }        // :695-697
+                e = fminf(e, p.max_energy);                   // :698-701
+                ++games;                                      // :710
             }
+            const uint32_t trait = s_tf[si] & TF_TRAIT;
             if (dead) {
                 s_out[cl] = (uint8_t)TF_GHOST;
                 s_e[cl] = 0.0f;
                 ++n_play_deaths;
             } else {
-                // terminal rule (:547-556, :719-730, :486-496) or no neighbours (:429-433)
+                // terminal rule (:547-556, :719-730, :486-496) or no neighbours (:429-433):
+                // act[7]==1 <=> neighbour 7 exists and does not challenge me (sub-step 0);
+                // act[0]==0 <=> neighbour 0 challenges me (sub-step 7)
+                const bool act7_challenge = ((occ_mask >> 7) & 1u) && !(gm & 1u);
+                const bool act0_respond = (gm >> 7) & 1u;
                 mover = occ_mask == 0u || (games == 0 && (act7_challenge || act0_respond));
                 s_out[cl] = (uint8_t)(TF_OCC | trait);
                 s_e[cl] = e;
@@ -275,7 +342,7 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
     unsigned int n_travel_deaths = 0;
     for (unsigned int k = tid; k < n_mover; k += NT) {
         const int cl = s_mover[k];
-        const int ly = cl / TW, lx = cl - ly * TW;
+        const int ly = cl >> LOG_TW, lx = cl & (TW - 1);
         const int si = (ly + 1) * SW + lx + 16;
         const float e = __fsub_rn(s_e[cl], p.travel_cost);  // :800
         if (e <= 0.0f) {                                    // :801-804
@@ -287,8 +354,7 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
         s_e[cl] = e;
         uint32_t occ_mask = 0;
 #pragma unroll
-        for (int d = 0; d < 8; ++d)
-            if (s_tf[si + DY(d) * SW + DX(d)] & TF_OCC) occ_mask |= 1u << d;
+        for (int d = 0; d < 8; ++d) occ_mask |= (s_R[si + DY(d) * SW + DX(d)] >> 31) << d;
         const Words w = rng(p, gcell_of(p, x0 + lx, y0 + ly), S_ROLL);
         int l = (int)(w.z >> 29), seq = 0;  // :810
         const int dir = probe(occ_mask, l, seq);
@@ -297,11 +363,11 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
     __syncthreads();
     // ---- coalesced stores
     for (int i = tid; i < NC / 16; i += NT) {
-        const int ly = (i * 16) / TW, lx = (i * 16) - ly * TW;
+        const int ly = (i * 16) >> LOG_TW, lx = (i * 16) & (TW - 1);
         *reinterpret_cast<uint4*>(p.tfB + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = reinterpret_cast<uint4*>(s_out)[i];
     }
     for (int i = tid; i < NC / 4; i += NT) {
-        const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
+        const int ly = (i * 4) >> LOG_TW, lx = (i * 4) & (TW - 1);
         *reinterpret_cast<float4*>(p.E1 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = reinterpret_cast<float4*>(s_e)[i];
     }
     if (p.stats) {
@@ -321,33 +387,36 @@ template <int TW, int TH, typename KeyFn>
 __device__ __forceinline__ void resolve_claims(const Params& p, const uint8_t* s_tf, uint8_t* s_cl,
                                                uint16_t* s_list, unsigned int* s_cnt, uint32_t x0,
                                                uint32_t y0, KeyFn keyfn) {
-    constexpr int SW = TW + 32, SH = TH + 4, RW2 = TW + 4, RW1 = TW + 2;
+    constexpr int SW = TW + 32, SH = TH + 4, NWORD = SH * SW / 4;
     const int tid = threadIdx.x;
-    // scatter one bit per claimant (claimants are sparse: <= ~10 % of cells)
-    for (int i = tid; i < SH * RW2; i += NT) {
-        const int r = i / RW2, c = i - r * RW2;
-        const int si = r * SW + 14 + c;
-        const uint32_t t = s_tf[si];
-        if (!(t & TF_CLAIM)) continue;
-        const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
-        const int e = d + (d >= 4 ? 1 : 0);
-        const int dx = e / 3 - 1, dy = e - (e / 3) * 3 - 1;
-        const int rr = r + dy, cc = c + dx;
-        if (rr < 1 || rr > TH + 2 || cc < 1 || cc > TW + 2) continue;
-        const int st = si + dy * SW + dx;
-        atomicOr(reinterpret_cast<unsigned int*>(s_cl) + (st >> 2), (1u << (7 - d)) << (8 * (st & 3)));
+    // scatter one bit per claimant; the tile is scanned 4 cells (one word) at a time and claimants
+    // are sparse (<= ~10 % of cells), so the common path is one load and one test per word
+    for (int w = tid; w < NWORD; w += NT) {
+        const uint32_t t4 = reinterpret_cast<const uint32_t*>(s_tf)[w];
+        uint32_t cm = t4 & 0x40404040u;
+        while (cm) {
+            const int b = (__ffs(cm) - 1) >> 3;
+            cm &= cm - 1;
+            const int si = w * 4 + b;
+            const int d = (int)(((t4 >> (8 * b)) & TF_DIR) >> TF_DIR_SHIFT);
+            const int r = si / SW, c = si - r * SW;
+            const int rr = r + c_dir_dy[d], cc = c + c_dir_dx[d];
+            // only targets inside tile + 1-ring matter (rows 1..TH+2, columns 15..TW+16)
+            if (rr < 1 || rr > TH + 2 || cc < 15 || cc > TW + 16) continue;
+            const int st = rr * SW + cc;
+            atomicOr(reinterpret_cast<unsigned int*>(s_cl) + (st >> 2), (1u << (7 - d)) << (8 * (st & 3)));
+        }
     }
     __syncthreads();
     // contested cells (>= 2 claimants) -> list
-    for (int base = 0; base < (TH + 2) * RW1; base += NT) {
-        const int i = base + tid;
-        const bool valid = i < (TH + 2) * RW1;
-        const int r = valid ? i / RW1 + 1 : 1, c = valid ? i - (i / RW1) * RW1 + 1 : 1;
-        const int si = r * SW + 14 + c;
-        const uint32_t m = valid ? s_cl[si] : 0u;
-        const bool contested = (m & (m - 1u)) != 0u;
-        const uint32_t slot = wappend(s_cnt, contested);
-        if (contested) s_list[slot] = (uint16_t)si;
+    for (int w = tid; w < NWORD; w += NT) {
+        const uint32_t c4 = reinterpret_cast<const uint32_t*>(s_cl)[w];
+        if (c4 == 0u) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t m = (c4 >> (8 * b)) & 0xFFu;
+            if (m & (m - 1u)) s_list[atomicAdd(s_cnt, 1u)] = (uint16_t)(w * 4 + b);
+        }
     }
     __syncthreads();
     const unsigned int n = *s_cnt;
@@ -368,6 +437,24 @@ __device__ __forceinline__ void resolve_claims(const Params& p, const uint8_t* s
         s_cl[si] = (uint8_t)(1u << best);
     }
     __syncthreads();
+}
+
+// copy a CTA-local list of local cell indices into its reserved range of a global list
+template <int TW>
+__device__ __forceinline__ void copy_cells(const Params& p, const uint16_t* s_list, unsigned int n,
+                                           unsigned int base, uint32_t* gcell_list, const uint8_t* s_state,
+                                           uint8_t* gstate, uint32_t x0, uint32_t y0) {
+    if (n == 0) return;
+    if (base + n > p.list_cap) {
+        if (threadIdx.x == 0) atomicExch(&p.ctr->overflow, 1u);
+        return;
+    }
+    for (unsigned int k = threadIdx.x; k < n; k += NT) {
+        const int cl = s_list[k];
+        const int ly = cl / TW, lx = cl - ly * TW;
+        gcell_list[base + k] = ((y0 + ly) << p.log2W) | (x0 + lx);
+        if (gstate) gstate[base + k] = s_state[k];
+    }
 }
 
 // copy a CTA-local list of local cell indices to a global list (one atomic per CTA)
@@ -391,17 +478,24 @@ __device__ __forceinline__ void flush_cells(const Params& p, const uint16_t* s_l
 }
 
 // ------------------------------------------------------------------------------------------
-// k_move_commit (dense sweep 2): move_response (:881-960), round 1.
+// k_move_commit (dense sweep 2): move_response (:881-960), round 1.  tfB (2-halo) -> tfA.
+// An empty cell that received claims PULLS the winner's energy/strategies; a claimant looks up
+// its target's winner bit and either vacates (leaving a GHOST that keeps blocking movers this
+// step, quirk B-13) or joins the loser list.  Claimants and claimed cells are rare, so the dense
+// scan only classifies words and queues them; the queue is then processed with full lanes.
+// Loser state byte: 0x80 active | 0x40 fresh | claimed direction (k_move_retry derives the rest).
 // ------------------------------------------------------------------------------------------
 template <int TW, int TH>
 __global__ void __launch_bounds__(NT) k_move_commit(const __grid_constant__ Params p) {
     constexpr int SW = TW + 32, SH = TH + 4, NC = TW * TH;
     __shared__ __align__(16) uint8_t s_tf[SH * SW];
     __shared__ __align__(16) uint8_t s_cl[SH * SW];
+    __shared__ __align__(16) uint8_t s_out[NC];
     __shared__ uint16_t s_list[(TH + 2) * (TW + 2)];
+    __shared__ uint16_t s_work[NC];
     __shared__ uint16_t s_lost[NC];
     __shared__ uint8_t s_lost_state[NC];
-    __shared__ unsigned int s_n[4];
+    __shared__ unsigned int s_n[4];  // 0 contested, 1 lost, 2 slot, 3 work
     const int tid = threadIdx.x;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     if (tid < 4) s_n[tid] = 0;
@@ -409,47 +503,60 @@ __global__ void __launch_bounds__(NT) k_move_commit(const __grid_constant__ Para
     for (int i = tid; i < SH * SW / 16; i += NT) reinterpret_cast<uint4*>(s_cl)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     resolve_claims<TW, TH>(p, s_tf, s_cl, s_list, &s_n[0], x0, y0, TravelKey());
-    unsigned int n_moved = 0;
     for (int i = tid; i < NC / 4; i += NT) {
         const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
         const int si = (ly + 2) * SW + lx + 16;
         const uint32_t t4 = *reinterpret_cast<const uint32_t*>(s_tf + si);
         const uint32_t c4 = *reinterpret_cast<const uint32_t*>(s_cl + si);
-        uint32_t out4 = t4 & 0x87878787u;  // OCC | GHOST | trait
-        if ((t4 & 0x40404040u) | c4) {
+        reinterpret_cast<uint32_t*>(s_out)[i] = t4 & 0x87878787u;  // OCC | GHOST | trait
+        // sp: bit 7 of byte b set <=> cell b is a claimant or received a claim
+        uint32_t sp = (t4 & 0x40404040u) << 1;
+        if (c4) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t t = (t4 >> (8 * k)) & 0xFFu, cl = (c4 >> (8 * k)) & 0xFFu;
-                const uint32_t x = x0 + lx + k, y = y0 + ly;
-                if (t & TF_CLAIM) {
-                    const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
-                    const int e = d + (d >= 4 ? 1 : 0);
-                    const int st = si + k + (e - (e / 3) * 3 - 1) * SW + (e / 3 - 1);
-                    if ((s_cl[st] >> (7 - d)) & 1u) {
-                        // moved away; the cell still blocks movers for the rest of the step (B-13)
-                        out4 = (out4 & ~(0xFFu << (8 * k))) | (TF_GHOST << (8 * k));
-                    } else {  // :940-943 -> retry with the same roll, next start = d+1 (:848)
-                        const int s = (int)(rng(p, gcell_of(p, x, y), S_ROLL).z >> 29);
-                        const unsigned int slot = atomicAdd(&s_n[1], 1u);
-                        s_lost[slot] = (uint16_t)(ly * TW + lx + k);
-                        s_lost_state[slot] = (uint8_t)(0x80u | (uint32_t)((d + 1) & 7) | ((uint32_t)probe_pos(s, d) << 3));
-                    }
-                } else if (cl) {  // the winner relocates here (:946-956)
-                    const int j = __ffs(cl) - 1;
-                    const int e = j + (j >= 4 ? 1 : 0);
-                    const uint32_t tn = s_tf[si + k + (e - (e / 3) * 3 - 1) * SW + (e / 3 - 1)];
-                    const uint32_t src = nb_local(p, x, y, j);
-                    const size_t cell = ((size_t)y << p.log2W) | x;
-                    p.E1[cell] = p.E1[src];
-                    p.strat[cell] = p.strat[src];
-                    out4 = (out4 & ~(0xFFu << (8 * k))) | ((TF_OCC | (tn & TF_TRAIT)) << (8 * k));
-                    ++n_moved;
-                }
-            }
+            for (int b = 0; b < 4; ++b)
+                if ((c4 >> (8 * b)) & 0xFFu) sp |= 0x80u << (8 * b);
         }
-        *reinterpret_cast<uint32_t*>(p.tfA + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = out4;
+        while (sp) {
+            const int b = (__ffs(sp) - 1) >> 3;
+            sp &= sp - 1;
+            s_work[atomicAdd(&s_n[3], 1u)] = (uint16_t)(i * 4 + b);
+        }
     }
     __syncthreads();
+    const unsigned int n_work = s_n[3];
+    unsigned int n_moved = 0;
+    for (unsigned int k = tid; k < n_work; k += NT) {
+        const int cl = s_work[k];
+        const int ly = cl / TW, lx = cl - ly * TW;
+        const int si = (ly + 2) * SW + lx + 16;
+        const uint32_t t = s_tf[si];
+        if (t & TF_CLAIM) {
+            const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
+            const int st = si + c_dir_dy[d] * SW + c_dir_dx[d];
+            if ((s_cl[st] >> (7 - d)) & 1u) {
+                s_out[cl] = (uint8_t)TF_GHOST;  // moved away; still blocks movers this step (B-13)
+            } else {                            // :940-943 -> retry with the same roll
+                const unsigned int slot = atomicAdd(&s_n[1], 1u);
+                s_lost[slot] = (uint16_t)cl;
+                s_lost_state[slot] = (uint8_t)(0xC0u | (uint32_t)d);
+            }
+        } else {  // the winner relocates here (:946-956)
+            const int j = __ffs((uint32_t)s_cl[si]) - 1;
+            const uint32_t tn = s_tf[si + c_dir_dy[j] * SW + c_dir_dx[j]];
+            const uint32_t x = x0 + lx, y = y0 + ly;
+            const uint32_t src = nb_local(p, x, y, j);
+            const size_t cell = ((size_t)y << p.log2W) | x;
+            p.E1[cell] = p.E1[src];
+            p.strat[cell] = p.strat[src];
+            s_out[cl] = (uint8_t)(TF_OCC | (tn & TF_TRAIT));
+            ++n_moved;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < NC / 16; i += NT) {
+        const int ly = (i * 16) / TW, lx = (i * 16) - ly * TW;
+        *reinterpret_cast<uint4*>(p.tfA + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = reinterpret_cast<uint4*>(s_out)[i];
+    }
     flush_cells<TW>(p, s_lost, s_n[1], &p.ctr->mv_n, p.mv_cell, s_lost_state, p.mv_state, x0, y0, &s_n[2]);
     if (p.stats && n_moved) atomicAdd(&p.ctr->st_moved, (unsigned long long)n_moved);
 }
@@ -470,27 +577,20 @@ __global__ void __launch_bounds__(NT) k_repro_claim(const __grid_constant__ Para
     if (tid < 2) s_n[tid] = 0;
     load_tile_vec<TW, TH, 1>(p, p.tfA, s_tf, x0, y0);
     __syncthreads();
-    for (int base = 0; base < NC / 4; base += NT) {
-        const int i = base + tid;
-        const bool valid = i < NC / 4;
-        const int ly = valid ? (i * 4) / TW : 0, lx = valid ? (i * 4) - ly * TW : 0;
+    for (int i = tid; i < NC / 4; i += NT) {
+        const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
         const int si = (ly + 1) * SW + lx + 16;
-        const uint32_t t4 = valid ? *reinterpret_cast<const uint32_t*>(s_tf + si) : 0u;
-        float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && (t4 & 0x80808080u))
-            e4 = *reinterpret_cast<const float4*>(p.E1 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx);
-        const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
-        uint32_t out4 = 0;
+        const uint32_t t4 = *reinterpret_cast<const uint32_t*>(s_tf + si);
+        const uint32_t occ4 = t4 & 0x80808080u;
+        reinterpret_cast<uint32_t*>(s_out)[i] = t4 & (occ4 | (occ4 >> 6) | (occ4 >> 7));  // OCC | trait of occupied cells
+        if (occ4 && p.max_children > 0u) {  // :1054
+            const float4 e4 = *reinterpret_cast<const float4*>(p.E1 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx);
+            const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t t = (t4 >> (8 * k)) & 0xFFu;
-            const bool occ = (t & TF_OCC) != 0u;
-            if (occ) out4 |= (TF_OCC | (t & TF_TRAIT)) << (8 * k);
-            const bool eligible = occ && p.max_children > 0u && ev[k] >= p.reproduce_min_energy;  // :978, :1054
-            const uint32_t slot = wappend(&s_n[0], eligible);
-            if (eligible) s_par[slot] = (uint16_t)(ly * TW + lx + k);
+            for (int k = 0; k < 4; ++k)
+                if (((occ4 >> (8 * k)) & 0x80u) && ev[k] >= p.reproduce_min_energy)  // :978-979
+                    s_par[atomicAdd(&s_n[0], 1u)] = (uint16_t)(i * 4 + k);
         }
-        if (valid) *reinterpret_cast<uint32_t*>(s_out + i * 4) = out4;
     }
     __syncthreads();
     const unsigned int n_par = s_n[0];
@@ -536,7 +636,8 @@ __global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Par
     __shared__ uint16_t s_dead[NC];
     __shared__ float s_ce[NC];        // child energy by cell (only written/read for birth cells)
     __shared__ unsigned int s_bins[16];
-    __shared__ unsigned int s_n[8];   // 0 contested, 1 births, 2 lost, 3 risk, 4 dead, 5 n_old, 6 slot, 7 living deaths
+    __shared__ unsigned int s_n[8];   // 0 contested, 1 births, 2 lost, 3 risk, 4 dead, 5 n_old, 6 -, 7 living deaths
+    __shared__ unsigned int s_base[4];
     const int tid = threadIdx.x;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     if (tid < 8) s_n[tid] = 0;
@@ -546,12 +647,13 @@ __global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Par
     __syncthreads();
     resolve_claims<TW, TH>(p, s_tf, s_cl, s_list, &s_n[0], x0, y0, ReproKey());
     // ---- cells of this tile that receive a child
-    for (int base = 0; base < NC; base += NT) {
-        const int cl = base + tid;  // NC is a multiple of NT
-        const int ly = cl / TW, lx = cl - ly * TW;
-        const bool born = s_cl[(ly + 2) * SW + lx + 16] != 0;
-        const uint32_t slot = wappend(&s_n[1], born);
-        if (born) s_birth[slot] = (uint16_t)cl;
+    for (int i = tid; i < NC / 4; i += NT) {
+        const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
+        const uint32_t c4 = *reinterpret_cast<const uint32_t*>(s_cl + (ly + 2) * SW + lx + 16);
+        if (c4 == 0u) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if ((c4 >> (8 * b)) & 0xFFu) s_birth[atomicAdd(&s_n[1], 1u)] = (uint16_t)(i * 4 + b);
     }
     __syncthreads();
     const unsigned int n_birth = s_n[1];
@@ -562,8 +664,7 @@ __global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Par
         const int si = (ly + 2) * SW + lx + 16;
         const uint32_t x = x0 + lx, y = y0 + ly;
         const int j = __ffs((uint32_t)s_cl[si]) - 1;  // the winning neighbour
-        const int e = j + (j >= 4 ? 1 : 0);
-        const uint32_t tn = s_tf[si + (e - (e / 3) * 3 - 1) * SW + (e / 3 - 1)];
+        const uint32_t tn = s_tf[si + c_dir_dy[j] * SW + c_dir_dx[j]];
         const uint32_t src = nb_local(p, x, y, j);
         const float pe = __fsub_rn(p.E1[src], p.reproduce_cost);
         float ce;
@@ -589,32 +690,29 @@ __global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Par
         }
         float ev[4] = {e4.x, e4.y, e4.z, e4.w};
         uint32_t out4 = 0;
+        n_old += __popc(t4 & 0x80808080u);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t t = (t4 >> (8 * k)) & 0xFFu, cb = (c4 >> (8 * k)) & 0xFFu;
-            const int cl = ly * TW + lx + k;
+            const int cl = i * 4 + k;
             if (t & TF_OCC) {
-                ++n_old;
                 const uint32_t trait = t & TF_TRAIT;
                 float e = ev[k];
                 bool lost = false;
                 if (t & TF_CLAIM) {
                     const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
-                    const int ee = d + (d >= 4 ? 1 : 0);
-                    const int st = si + k + (ee - (ee / 3) * 3 - 1) * SW + (ee / 3 - 1);
+                    const int st = si + k + c_dir_dy[d] * SW + c_dir_dx[d];
                     if ((s_cl[st] >> (7 - d)) & 1u) {
                         e = __fsub_rn(e, p.reproduce_cost);  // :1211-1213
                     } else {  // stays ATTEMPTING_REPRODUCTION (:1203-1205): retry list, living cost deferred
                         lost = true;
-                        const int s = (int)(rng(p, gcell_of(p, x0 + lx + k, y0 + ly), S_REPRO).y >> 29);
                         const unsigned int slot = atomicAdd(&s_n[2], 1u);
                         s_lost[slot] = (uint16_t)cl;
-                        s_lost_state[slot] = (uint8_t)(0x80u | (uint32_t)((d + 1) & 7) | ((uint32_t)probe_pos(s, d) << 3));
+                        s_lost_state[slot] = (uint8_t)(0xC0u | (uint32_t)d);
                     }
                 }
                 if (lost) {
                     out4 |= (TF_OCC | trait) << (8 * k);
-                    ev[k] = e;
                 } else if (punish(p, e)) {
                     out4 |= (TF_OCC | trait) << (8 * k);
                     ev[k] = e;
@@ -630,8 +728,7 @@ __global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Par
                 }
             } else if (cb) {  // a child was born here: the winner's trait, energy from the birth pass
                 const int j = __ffs(cb) - 1;
-                const int e = j + (j >= 4 ? 1 : 0);
-                const uint32_t tn = s_tf[si + k + (e - (e / 3) * 3 - 1) * SW + (e / 3 - 1)];
+                const uint32_t tn = s_tf[si + k + c_dir_dy[j] * SW + c_dir_dx[j]];
                 out4 |= (TF_OCC | TF_NEWBORN | (tn & TF_TRAIT)) << (8 * k);
                 ev[k] = s_ce[cl];
             } else {
@@ -644,10 +741,18 @@ __global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Par
     if (n_old) atomicAdd(&s_n[5], n_old);
     if (n_dead) atomicAdd(&s_n[7], n_dead);
     __syncthreads();
-    flush_cells<TW>(p, s_lost, s_n[2], &p.ctr->rp_n, p.rp_cell, s_lost_state, p.rp_state, x0, y0, &s_n[6]);
-    flush_cells<TW>(p, s_birth, n_birth, &p.ctr->nb_n, p.nb_cell, nullptr, nullptr, x0, y0, &s_n[6]);
-    flush_cells<TW>(p, s_risk, s_n[3], &p.ctr->risk_next_n, p.risk_next, nullptr, nullptr, x0, y0, &s_n[6]);
-    flush_cells<TW>(p, s_dead, s_n[4], &p.ctr->dead_n, p.dead_cell, nullptr, nullptr, x0, y0, &s_n[6]);
+    // one atomic per list per CTA, then plain copies
+    if (tid < 4) {
+        const unsigned int n = tid == 0 ? s_n[2] : tid == 1 ? n_birth : tid == 2 ? s_n[3] : s_n[4];
+        unsigned int* gc = tid == 0 ? &p.ctr->rp_n : tid == 1 ? &p.ctr->nb_n
+                         : tid == 2 ? &p.ctr->risk_next_n : &p.ctr->dead_n;
+        s_base[tid] = n ? atomicAdd(gc, n) : 0u;
+    }
+    __syncthreads();
+    copy_cells<TW>(p, s_lost, s_n[2], s_base[0], p.rp_cell, s_lost_state, p.rp_state, x0, y0);
+    copy_cells<TW>(p, s_birth, n_birth, s_base[1], p.nb_cell, nullptr, nullptr, x0, y0);
+    copy_cells<TW>(p, s_risk, s_n[3], s_base[2], p.risk_next, nullptr, nullptr, x0, y0);
+    copy_cells<TW>(p, s_dead, s_n[4], s_base[3], p.dead_cell, nullptr, nullptr, x0, y0);
     if (tid == 0) {
         if (s_n[5]) atomicAdd(&p.ctr->n_old, (unsigned long long)s_n[5]);
         if (n_birth) atomicAdd(&p.ctr->births, (unsigned long long)n_birth);

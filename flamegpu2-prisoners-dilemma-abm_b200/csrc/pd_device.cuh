@@ -58,12 +58,13 @@ static_assert(DY(0) == -1 && DY(1) == 0 && DY(2) == 1 && DY(3) == -1 && DY(4) ==
 // ---- device-resident counters -----------------------------------------------------------
 struct Counters {
     // zeroed at the start of every step (k_begin_step)
-    unsigned int mv_n, rp_n, nb_n, risk_next_n, dead_n, pad0_;
+    unsigned int mv_n, rp_n, nb_n, risk_next_n, dead_n, cand_n;
     unsigned int mv_active[8], rp_active[8];
     unsigned long long n_old, births, culled, living_deaths;
     unsigned long long st_play_deaths, st_movers, st_moved, st_travel_deaths;
     unsigned long long bins[16];
     unsigned int hist[8][256];
+    unsigned long long tau;
     // persistent across steps
     unsigned int risk_n;
     unsigned int overflow;

@@ -110,14 +110,19 @@ __global__ void __launch_bounds__(1024) k_move_retry(const __grid_constant__ Par
 #pragma unroll
             for (int d = 0; d < 8; ++d)
                 if (__ldcg(p.tfA + nb_local(p, x, y, d)) & (TF_OCC | TF_GHOST)) blocked |= 1u << d;
-            int l = (int)(st & 7u), seq = (int)((st >> 3) & 15u);
+            int l = (int)(st & 7u), seq = (int)((st >> 3) & 7u) + 1;  // state: 0x80 active | 0x40 fresh | (seq-1) << 3 | start
+            if (st & 0x40u) {  // fresh from round 1: it claimed direction l after probe_pos probes (:848-849)
+                const int s0 = (int)(rng(p, gcell_of(p, x, y), S_ROLL).z >> 29);
+                seq = probe_pos(s0, l);
+                l = (l + 1) & 7;
+            }
             const int dir = probe(blocked, l, seq);
             if (dir < 0) {
                 p.mv_state[i] = 0;  // no free space: stays put (:842-846)
             } else {
                 const uint32_t t = __ldcg(p.tfA + cell);
                 p.tfA[cell] = (uint8_t)((t & (TF_OCC | TF_TRAIT)) | TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT));
-                p.mv_state[i] = (uint8_t)(0x80u | (uint32_t)((dir + 1) & 7) | ((uint32_t)seq << 3));
+                p.mv_state[i] = (uint8_t)(0x80u | (uint32_t)((dir + 1) & 7) | ((uint32_t)(seq - 1) << 3));
                 p.mv_aux[i] = (uint8_t)dir;
             }
         }
@@ -193,14 +198,19 @@ __global__ void __launch_bounds__(1024) k_repro_retry(const __grid_constant__ Pa
 #pragma unroll
             for (int d = 0; d < 8; ++d)
                 if (__ldcg(p.tfA + nb_local(p, x, y, d)) & TF_OCC) blocked |= 1u << d;
-            int l = (int)(st & 7u), seq = (int)((st >> 3) & 15u);
+            int l = (int)(st & 7u), seq = (int)((st >> 3) & 7u) + 1;  // state: 0x80 active | 0x40 fresh | (seq-1) << 3 | start
+            if (st & 0x40u) {  // fresh from round 1: it claimed direction l after probe_pos probes (:1110-1111)
+                const int s0 = (int)(rng(p, gcell_of(p, x, y), S_REPRO).y >> 29);
+                seq = probe_pos(s0, l);
+                l = (l + 1) & 7;
+            }
             const int dir = probe(blocked, l, seq);  // also covers reproduce_sequence >= 8 (:1067)
             if (dir < 0) {
                 p.rp_state[i] = 0x40u;  // REPRODUCTION_IMPOSSIBLE (:1104-1108); living cost still due
             } else {
                 const uint32_t t = __ldcg(p.tfA + cell);
                 p.tfA[cell] = (uint8_t)((t & (TF_OCC | TF_TRAIT)) | TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT));
-                p.rp_state[i] = (uint8_t)(0x80u | (uint32_t)((dir + 1) & 7) | ((uint32_t)seq << 3));
+                p.rp_state[i] = (uint8_t)(0x80u | (uint32_t)((dir + 1) & 7) | ((uint32_t)(seq - 1) << 3));
                 p.rp_aux[i] = (uint8_t)dir;
             }
         }
@@ -265,13 +275,21 @@ __global__ void __launch_bounds__(1024) k_repro_retry(const __grid_constant__ Pa
 // the repro-loser list, the newborns' counts and the bookkeeping for the next step.
 // Cull (replaces the list-index rule :1343/:1354, SURVEY B-4): if olds + births exceed
 // max_agents, only the K = max_agents - olds newborns with the highest (Philox cull priority,
-// cell) keys survive.  The K-th largest 64-bit key is found exactly by an 8-pass radix select.
+// cell) keys survive.  The K-th largest 64-bit key is found exactly by a radix select: one
+// 2048-bin histogram of the top 11 bits over all newborns, compaction of the threshold bin's
+// few candidates, then 8-bit passes over the candidates only (CTA 0).
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long cull_key(const Params& p, uint32_t cell, uint32_t prio) {
+    const uint64_t g = gcell_of(p, cell & (p.W - 1), cell >> p.log2W);
+    return ((unsigned long long)prio << 32) | (uint32_t)g;
+}
+
 __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Params p) {
     Counters* ctr = p.ctr;
-    __shared__ unsigned int s_hist[256];
+    __shared__ unsigned int s_hist[2048];
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned long long s_krem;
+    __shared__ unsigned int s_digit;
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int nb = ctr->nb_n;
@@ -280,6 +298,8 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Param
     if (nrp > p.list_cap) nrp = p.list_cap;
     const unsigned long long n_old = ctr->n_old;
     const unsigned long long births = ctr->births;
+    unsigned int* g_hist = &ctr->hist[0][0];         // 2048 words
+    uint32_t* cand = p.risk_roll;                     // scratch: indices into the newborn list
     // ---- cull threshold
     bool cull = n_old + births > p.max_agents;
     unsigned long long keep = 0;
@@ -289,40 +309,79 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Param
         if (keep >= births) cull = false;
     }
     if (cull && keep > 0) {
-        if (threadIdx.x == 0) { s_prefix = 0ull; s_krem = keep; }
-        for (int pass = 0; pass < 8; ++pass) {
-            const int shift = 56 - 8 * pass;
-            if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
-            __syncthreads();
-            const unsigned long long prefix = s_prefix;
-            for (unsigned int i = t0; i < nb; i += stride) {
-                const uint32_t cell = p.nb_cell[i];
-                uint32_t prio;
-                const uint64_t g = gcell_of(p, cell & (p.W - 1), cell >> p.log2W);
-                if (pass == 0) { prio = rng(p, g, S_CULL).x; p.nb_prio[i] = prio; }
-                else prio = p.nb_prio[i];
-                const unsigned long long key = ((unsigned long long)prio << 32) | (uint32_t)g;
-                if (pass == 0 || (key >> (shift + 8)) == prefix)
-                    atomicAdd(&s_hist[(unsigned int)(key >> shift) & 255u], 1u);
-            }
-            __syncthreads();
-            if (threadIdx.x < 256 && s_hist[threadIdx.x])
-                atomicAdd(&ctr->hist[pass][threadIdx.x], s_hist[threadIdx.x]);
-            grid_sync(ctr->barrier, gridDim.x);
-            if (threadIdx.x == 0) {
-                unsigned long long krem = s_krem, cum = 0;
-                int digit = 0;
-                for (int b = 255; b >= 0; --b) {
-                    const unsigned long long h = __ldcg(&ctr->hist[pass][b]);
-                    if (cum + h >= krem) { digit = b; break; }
-                    cum += h;
-                }
-                s_krem = krem - cum;
-                s_prefix = (prefix << 8) | (unsigned long long)digit;
-            }
-            __syncthreads();
+        // pass A: priorities + histogram of the top 11 bits
+        for (unsigned int i = threadIdx.x; i < 2048; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        for (unsigned int i = t0; i < nb; i += stride) {
+            const uint32_t cell = p.nb_cell[i];
+            const uint32_t prio = rng(p, gcell_of(p, cell & (p.W - 1), cell >> p.log2W), S_CULL).x;
+            p.nb_prio[i] = prio;
+            atomicAdd(&s_hist[prio >> 21], 1u);
         }
-        tau = s_prefix;
+        __syncthreads();
+        for (unsigned int i = threadIdx.x; i < 2048; i += blockDim.x)
+            if (s_hist[i]) atomicAdd(&g_hist[i], s_hist[i]);
+        grid_sync(ctr->barrier, gridDim.x);
+        // threshold bin: every CTA computes it identically from the global histogram
+        for (unsigned int i = threadIdx.x; i < 2048; i += blockDim.x) s_hist[i] = __ldcg(&g_hist[i]);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long cum = 0;
+            int digit = 0;
+            for (int b = 2047; b >= 0; --b) {
+                const unsigned long long h = s_hist[b];
+                if (cum + h >= keep) { digit = b; break; }
+                cum += h;
+            }
+            s_digit = (unsigned int)digit;
+            s_krem = keep - cum;  // how many of the threshold bin's candidates survive
+        }
+        __syncthreads();
+        const unsigned int digit = s_digit;
+        // pass B: compact the candidates (newborns whose top 11 bits equal the threshold bin)
+        for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nb; i0 += stride) {
+            const unsigned int i = i0 + threadIdx.x;
+            const bool is_cand = i < nb && (p.nb_prio[i] >> 21) == digit;
+            const uint32_t slot = warp_append(&ctr->cand_n, is_cand);
+            if (is_cand) cand[slot] = i;
+        }
+        grid_sync(ctr->barrier, gridDim.x);
+        // CTA 0: krem-th largest key among the candidates, 8 bits per pass over the low 53 bits
+        if (blockIdx.x == 0) {
+            const unsigned int nc = __ldcg(&ctr->cand_n);
+            if (threadIdx.x == 0) s_prefix = (unsigned long long)digit;  // the 11 bits decided so far
+            int decided = 11;
+            while (decided < 64) {
+                const int bits = (64 - decided) >= 8 ? 8 : (64 - decided);
+                const int shift = 64 - decided - bits;
+                if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
+                __syncthreads();
+                const unsigned long long prefix = s_prefix;
+                for (unsigned int k = threadIdx.x; k < nc; k += blockDim.x) {
+                    const unsigned int i = __ldcg(&cand[k]);
+                    const unsigned long long key = cull_key(p, p.nb_cell[i], p.nb_prio[i]);
+                    if ((key >> (shift + bits)) == prefix)
+                        atomicAdd(&s_hist[(unsigned int)(key >> shift) & ((1u << bits) - 1u)], 1u);
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    unsigned long long krem = s_krem, cum = 0;
+                    int dg = 0;
+                    for (int b = (1 << bits) - 1; b >= 0; --b) {
+                        const unsigned long long h = s_hist[b];
+                        if (cum + h >= krem) { dg = b; break; }
+                        cum += h;
+                    }
+                    s_krem = krem - cum;
+                    s_prefix = (prefix << bits) | (unsigned long long)dg;
+                }
+                __syncthreads();
+                decided += bits;
+            }
+            if (threadIdx.x == 0) ctr->tau = s_prefix;
+        }
+        grid_sync(ctr->barrier, gridDim.x);
+        tau = __ldcg(&ctr->tau);
     }
     // ---- newborns: cull or admit (no living cost in the birth step, :1343)
     unsigned int n_culled = 0;
@@ -332,14 +391,7 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Param
         if (i < nb) {
             const uint32_t cell = p.nb_cell[i];
             bool survive = true;
-            if (cull) {
-                if (keep == 0) survive = false;
-                else {
-                    const uint64_t g = gcell_of(p, cell & (p.W - 1), cell >> p.log2W);
-                    const unsigned long long key = ((unsigned long long)p.nb_prio[i] << 32) | (uint32_t)g;
-                    survive = key >= tau;
-                }
-            }
+            if (cull) survive = keep != 0 && cull_key(p, cell, p.nb_prio[i]) >= tau;
             if (survive) {
                 const uint32_t t = __ldcg(p.tfA + cell);
                 p.tfA[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
@@ -357,7 +409,8 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Param
             else atomicExch(&ctr->overflow, 1u);
         }
     }
-    if (n_culled) atomicAdd(&ctr->culled, (unsigned long long)n_culled);
+    for (int o = 16; o > 0; o >>= 1) n_culled += __shfl_down_sync(0xFFFFFFFFu, n_culled, o);  // one atomic per warp
+    if ((threadIdx.x & 31) == 0 && n_culled) atomicAdd(&ctr->culled, (unsigned long long)n_culled);
     // ---- deferred living cost of the parents that lost round 1 (:1357-1368)
     unsigned int n_dead = 0;
     for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nrp; i0 += stride) {

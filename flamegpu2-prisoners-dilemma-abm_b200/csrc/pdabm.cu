@@ -232,7 +232,7 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     s->big_tiles = W >= 128;
     s->grid = s->big_tiles ? dim3(W / 128, cfg->rows / 16) : dim3(W / 16, cfg->rows / 16);
     if (cfg->sparse_ctas > 0) s->sparse_ctas = cfg->sparse_ctas;
-    else s->sparse_ctas = s->cells <= ((size_t)1 << 22) ? 1 : s->n_sms;
+    else s->sparse_ctas = s->cells <= ((size_t)1 << 22) ? 1 : 2 * s->n_sms;
     if (s->sparse_ctas > 1 && !prop.cooperativeLaunch) s->sparse_ctas = 1;
     s->sparse_threads = s->sparse_ctas == 1 ? 1024 : 512;
     if (s->sparse_ctas > s->n_sms * 2) s->sparse_ctas = s->n_sms * 2;
