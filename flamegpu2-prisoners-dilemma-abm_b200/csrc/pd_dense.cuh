@@ -108,21 +108,24 @@ __device__ __forceinline__ uint32_t game_outcome_rng(const Params& p, uint64_t m
 // (:373-440), the 8 iterations of play_challenge/play_response (:450-734) with exit_play_fn's
 // terminal rule, and the first move_request (:784-872).
 //
-// Per cell of tile + 1-ring a 32-bit word R is staged in shared memory: 0 for an empty cell,
-// 0x80000000 | roll >> 1 for an occupied one.  "Neighbour d is occupied AND challenges me" is then
-// the single comparison R[n] > R[me]; a (2^-31) tie of the truncated rolls falls back to the exact
-// (roll, cell) order.  The games found this way are queued warp-wide and evaluated 32 at a time;
-// those that need random words (RANDOM strategy or noise) are compacted once more so that the
-// Philox rounds always run with full lanes.
+// Per cell of tile + 1-ring ONE 32-bit word R is staged in shared memory:
+//     empty cell: 0        occupied: 1 | roll >> 12 (20 bits) | has-D-code | trait (2) | strategies (8)
+// so a single shared-memory load per neighbour answers "occupied?", "does it challenge me?"
+// (R[n] >> 11 > R[me] >> 11; a 2^-20 tie of the truncated rolls falls back to the exact
+// (roll, cell) order) and gives both strategies of the game.  Games that need random words
+// (RANDOM strategy or noise) are queued warp-wide so that the Philox rounds run with full lanes.
 // ------------------------------------------------------------------------------------------
 __constant__ int c_dir_dx[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
 __constant__ int c_dir_dy[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
 
-// exact "neighbour n (at direction d of local cell x,y) has the higher (roll, cell)" for the tie path
+constexpr uint32_t R_OCC = 0x80000000u;
+constexpr uint32_t R_DFLAG = 0x400u;
+
+// exact "neighbour d of local cell (x,y) has the higher (roll, cell)" for the tie path (:413)
 __device__ __noinline__ bool exact_higher(const Params& p, uint32_t x, uint32_t y, int d) {
     const uint64_t g = gcell_of(p, x, y), gn = nb_gcell(p, x, y, d);
     const uint32_t r = rng(p, g, S_ROLL).x, rn = rng(p, gn, S_ROLL).x;
-    return rn > r || (rn == r && gn > g);  // :413, tie -> cell index
+    return rn > r || (rn == r && gn > g);
 }
 
 // append the byte indices (b0 + k) of the bytes of `occ4` that have bit 7 set; all 32 lanes call
@@ -148,6 +151,12 @@ __device__ __forceinline__ void wappend4(unsigned int* cnt, uint16_t* list, uint
     }
 }
 
+// strategies of the game between me (word rme) and the neighbour (word rn) as I, the responder, see it
+__device__ __forceinline__ void game_strategies(uint32_t rme, uint32_t rn, uint32_t& mine, uint32_t& theirs) {
+    mine = (rme >> ((rn >> 7) & 6u)) & 3u;    // my strategy against the challenger's trait (:599)
+    theirs = (rn >> ((rme >> 7) & 6u)) & 3u;  // the challenger's strategy against my trait (:600)
+}
+
 template <int TW, int TH>
 __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Params p) {
     constexpr int SW = TW + 32, SH = TH + 2, NC = TW * TH, NWARP = NT / 32;
@@ -160,12 +169,12 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
     __shared__ __align__(16) uint8_t s_out[NC];
     __shared__ uint16_t s_cells[NC + 2 * (TW + 2) + 2 * TH];  // agents first (from 0), then ring cells
     __shared__ uint16_t s_mover[NC];
-    __shared__ uint16_t s_q[NWARP][256];   // per-warp queue of games: lane << 3 | sub-step
-    __shared__ uint8_t s_qo[NWARP][256];   // their results: outcome | alive << 2
-    __shared__ uint16_t s_q2[NWARP][256];  // second level: queue slots that need a Philox call
-    __shared__ unsigned int s_n[4];        // 0 agents, 1 ring cells, 2 movers
+    __shared__ uint16_t s_q[NWARP][256];  // per-warp queue of the games that need random words: lane << 3 | c
+    __shared__ uint8_t s_qo[NWARP][256];  // their outcomes
+    __shared__ unsigned int s_n[4];       // 0 agents, 1 ring cells, 2 movers
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const bool noisy = p.noise_thr != 0ull;
     if (tid < 4) s_n[tid] = 0;
     load_tile_vec<TW, TH, 1>(p, p.tfA, s_tf, x0, y0);
     load_tile_vec<TW, TH, 1>(p, p.strat, s_st, x0, y0);
@@ -187,7 +196,7 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
         }
     }
     __syncthreads();
-    // ... and the occupied cells of the 1-ring around it (they only need a roll)
+    // ... and the occupied cells of the 1-ring around it (they only need their word)
     const unsigned int n_agent = s_n[0];
     {
         constexpr int NRING = 2 * (TW + 2) + 2 * TH;
@@ -196,10 +205,10 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
             int si = 0;
             bool occ = false;
             if (i < NRING) {
-                if (i < TW + 2) si = 15 + i;                                   // top row
-                else if (i < 2 * (TW + 2)) si = (SH - 1) * SW + 15 + (i - (TW + 2));  // bottom row
+                if (i < TW + 2) si = 15 + i;                                           // top row
+                else if (i < 2 * (TW + 2)) si = (SH - 1) * SW + 15 + (i - (TW + 2));   // bottom row
                 else {
-                    const int k = i - 2 * (TW + 2);                            // left / right columns
+                    const int k = i - 2 * (TW + 2);                                    // left / right columns
                     si = (1 + (k >> 1)) * SW + ((k & 1) ? (16 + TW) : 15);
                 }
                 occ = (s_tf[si] & TF_OCC) != 0;
@@ -216,7 +225,9 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
         const int r = si / SW, c = si - r * SW;
         const uint32_t gx = (x0 + (uint32_t)(c - 16)) & (p.W - 1);
         const uint32_t gy = (p.row0 + y0 + (uint32_t)(r - 1)) & (p.W - 1);
-        s_R[si] = 0x80000000u | (rng(p, ((uint64_t)gy << p.log2W) | gx, S_ROLL).x >> 1);
+        const uint32_t roll = rng(p, ((uint64_t)gy << p.log2W) | gx, S_ROLL).x;
+        const uint32_t t = s_tf[si];
+        s_R[si] = R_OCC | ((roll >> 12) << 11) | ((t & TF_D) ? R_DFLAG : 0u) | ((t & TF_TRAIT) << 8) | (uint32_t)s_st[si];
     }
     __syncthreads();
     // ---- agents, 32 per warp iteration
@@ -228,18 +239,52 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
         const int ly = si / SW - 1, lx = si - (ly + 1) * SW - 16;
         const int cl = (ly << LOG_TW) | lx;
         const uint32_t rme = valid ? s_R[si] : 0xFFFFFFFFu;
-        uint32_t occ_mask = 0, gm = 0;
+        const uint32_t kme = rme >> 11;
+        uint32_t occ_mask = 0, gm = 0, rngm = 0, outc = 0, special = 0;
 #pragma unroll
         for (int d = 0; d < 8; ++d) {
+            const int c = 7 - d;  // neighbour d would challenge me in sub-step c (:477)
             const uint32_t rn = s_R[si + DY(d) * SW + DX(d)];
+            const uint32_t kn = rn >> 11;
             occ_mask |= (rn >> 31) << d;
-            bool hi = rn > rme;
-            if (rn == rme && valid) hi = exact_higher(p, x0 + lx, y0 + ly, d);  // 2^-31 per pair
-            gm |= (uint32_t)hi << (7 - d);  // bit c: neighbour 7-c challenges me in sub-step c (:477)
+            const uint32_t hi = kn > kme ? 1u : 0u;
+            special |= ((kn == kme ? 1u : 0u) | (hi & (rn >> 10))) << d;  // truncated-roll tie, or challenger with a D code
+            uint32_t mine, theirs;
+            game_strategies(rme, rn, mine, theirs);
+            const uint32_t need = (noisy || mine == 3u || theirs == 3u) ? hi : 0u;
+            gm |= hi << c;
+            rngm |= need << c;
+            outc |= (hi & (need ^ 1u)) * ((((mine != 1u) ? 2u : 0u) | ((theirs != 1u) ? 1u : 0u)) << (2 * c));
         }
-        if (!valid) { occ_mask = 0; gm = 0; }
-        // ---- queue my games (increasing sub-step order)
-        const int cnt = __popc(gm);
+        if (!valid) { occ_mask = 0; gm = 0; rngm = 0; special = 0; }
+        // act[7] / act[0] of the terminal rule come from the roll order alone (get_game_list, :413):
+        // a challenger that dies early still "would have challenged"
+        uint32_t roles = gm;
+        if (special) {  // rare: redo those directions exactly
+            uint32_t m = special;
+            while (m) {
+                const int d = __ffs(m) - 1, c = 7 - d;
+                m &= m - 1;
+                const int sn = si + c_dir_dy[d] * SW + c_dir_dx[d];
+                const uint32_t rn = s_R[sn];
+                bool hi = (rn >> 11) > kme;
+                if ((rn >> 11) == kme) hi = exact_higher(p, x0 + lx, y0 + ly, d);
+                roles = (roles & ~(1u << c)) | ((uint32_t)hi << c);
+                if (hi) {
+                    const uint32_t dn = ((uint32_t)s_tf[sn] & TF_D) >> TF_D_SHIFT;
+                    if (dn != 0u && (int)dn - 1 < c) hi = false;  // that challenger dies before sub-step c
+                }
+                uint32_t mine, theirs;
+                game_strategies(rme, rn, mine, theirs);
+                const bool need = hi && (noisy || mine == 3u || theirs == 3u);
+                gm = (gm & ~(1u << c)) | ((uint32_t)hi << c);
+                rngm = (rngm & ~(1u << c)) | ((uint32_t)need << c);
+                outc &= ~(3u << (2 * c));
+                if (hi && !need) outc |= (((mine != 1u) ? 2u : 0u) | ((theirs != 1u) ? 1u : 0u)) << (2 * c);
+            }
+        }
+        // ---- queue the games that need random words
+        const int cnt = __popc(rngm);
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -248,75 +293,57 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
         }
         const int off = incl - cnt;
         const int total = __shfl_sync(FULL, incl, 31);
-        {
-            uint32_t m = gm;
-            int k = off;
-            while (m) {
-                const int c = __ffs(m) - 1;
-                m &= m - 1;
-                s_q[warp][k++] = (uint16_t)((lane << 3) | c);
+        if (total) {
+            {
+                uint32_t m = rngm;
+                int k = off;
+                while (m) {
+                    const int c = __ffs(m) - 1;
+                    m &= m - 1;
+                    s_q[warp][k++] = (uint16_t)((lane << 3) | c);
+                }
             }
-        }
-        __syncwarp();
-        // ---- evaluate the games, 32 at a time; those that need random words go to the 2nd queue
-        const uint32_t pack = (uint32_t)si | ((uint32_t)cl << 16);
-        int n2 = 0;
-        for (int q0 = 0; q0 < total; q0 += 32) {
-            const int q = q0 + lane;
-            const bool active = q < total;
-            const uint32_t ent = active ? s_q[warp][q] : 0u;
-            const int c = (int)(ent & 7u), d = 7 - c;
-            const uint32_t pk = __shfl_sync(FULL, pack, (int)(ent >> 3));
-            bool need_rng = false;
-            if (active) {
-                const int si_l = (int)(pk & 0xFFFFu);
-                const int sn = si_l + c_dir_dy[d] * SW + c_dir_dx[d];
-                const uint32_t tl = s_tf[si_l], tn = s_tf[sn];
-                const uint32_t dn = (tn & TF_D) >> TF_D_SHIFT;
-                const uint32_t alive = (dn == 0u || (int)dn - 1 >= c) ? 4u : 0u;  // challenger still alive?
-                const uint32_t mine = ((uint32_t)s_st[si_l] >> (2 * (tn & TF_TRAIT))) & 3u;    // :599
-                const uint32_t theirs = ((uint32_t)s_st[sn] >> (2 * (tl & TF_TRAIT))) & 3u;    // :600
-                need_rng = alive && (p.noise_thr != 0ull || mine == 3u || theirs == 3u);
-                s_qo[warp][q] = (uint8_t)(alive | ((uint32_t)(mine != 1u) << 1) | (uint32_t)(theirs != 1u));
+            __syncwarp();
+            const uint32_t pack = (uint32_t)si | ((uint32_t)cl << 16);
+            for (int q0 = 0; q0 < total; q0 += 32) {
+                const int q = q0 + lane;
+                const bool active = q < total;
+                const uint32_t ent = active ? s_q[warp][q] : 0u;
+                const int c = (int)(ent & 7u), d = 7 - c;
+                const uint32_t pk = __shfl_sync(FULL, pack, (int)(ent >> 3));
+                if (active) {
+                    const int si_l = (int)(pk & 0xFFFFu), cl_l = (int)(pk >> 16);
+                    uint32_t mine, theirs;
+                    game_strategies(s_R[si_l], s_R[si_l + c_dir_dy[d] * SW + c_dir_dx[d]], mine, theirs);
+                    const uint64_t gl = gcell_of(p, x0 + (uint32_t)(cl_l & (TW - 1)), y0 + (uint32_t)(cl_l >> LOG_TW));
+                    s_qo[warp][q] = (uint8_t)game_outcome_rng(p, gl, c, mine, theirs);
+                }
             }
-            const unsigned int bal = __ballot_sync(FULL, need_rng);
-            if (need_rng) s_q2[warp][n2 + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)q;
-            n2 += __popc(bal);
-        }
-        __syncwarp();
-        for (int k0 = 0; k0 < n2; k0 += 32) {
-            const int k = k0 + lane;
-            const bool active = k < n2;
-            const int q = active ? s_q2[warp][k] : 0;
-            const uint32_t ent = s_q[warp][q];
-            const int c = (int)(ent & 7u), d = 7 - c;
-            const uint32_t pk = __shfl_sync(FULL, pack, (int)(ent >> 3));
-            if (active) {
-                const int si_l = (int)(pk & 0xFFFFu), cl_l = (int)(pk >> 16);
-                const int sn = si_l + c_dir_dy[d] * SW + c_dir_dx[d];
-                const uint32_t tl = s_tf[si_l], tn = s_tf[sn];
-                const uint32_t mine = ((uint32_t)s_st[si_l] >> (2 * (tn & TF_TRAIT))) & 3u;
-                const uint32_t theirs = ((uint32_t)s_st[sn] >> (2 * (tl & TF_TRAIT))) & 3u;
-                const uint64_t gl = gcell_of(p, x0 + (uint32_t)(cl_l & (TW - 1)), y0 + (uint32_t)(cl_l >> LOG_TW));
-                s_qo[warp][q] = (uint8_t)(4u | game_outcome_rng(p, gl, c, mine, theirs));
+            __syncwarp();
+            {
+                uint32_t m = rngm;
+                int k = off;
+                while (m) {
+                    const int c = __ffs(m) - 1;
+                    m &= m - 1;
+                    outc |= (uint32_t)s_qo[warp][k++] << (2 * c);
+                }
             }
+            __syncwarp();
         }
-        __syncwarp();
         // ---- my games in sub-step order (:677-710), terminal rule, travel decision
         bool mover = false;
         if (valid) {
             float e = s_e[cl];
             int games = 0;
             bool dead = false;
-            for (int k = 0; k < cnt; ++k) {
-                const uint32_t o = s_qo[warp][off + k];
-                if (!(o & 4u)) continue;                      // the challenger died earlier: no message
-                e = __fadd_rn(e, p.pay[o & 3u]);              // :679-688
-                if (e <= 0.0f) { dead = true; break; }        // :695-697
-                e = fminf(e, p.max_energy);                   // :698-701
-                ++games;                                      // :710
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (!((gm >> c) & 1u) || dead) continue;
+                e = __fadd_rn(e, p.pay[(outc >> (2 * c)) & 3u]);   // :679-688
+                if (e <= 0.0f) dead = true;                        // :695-697
+                else { e = fminf(e, p.max_energy); ++games; }      // :698-710
             }
-            const uint32_t trait = s_tf[si] & TF_TRAIT;
             if (dead) {
                 s_out[cl] = (uint8_t)TF_GHOST;
                 s_e[cl] = 0.0f;
@@ -325,16 +352,15 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
                 // terminal rule (:547-556, :719-730, :486-496) or no neighbours (:429-433):
                 // act[7]==1 <=> neighbour 7 exists and does not challenge me (sub-step 0);
                 // act[0]==0 <=> neighbour 0 challenges me (sub-step 7)
-                const bool act7_challenge = ((occ_mask >> 7) & 1u) && !(gm & 1u);
-                const bool act0_respond = (gm >> 7) & 1u;
+                const bool act7_challenge = ((occ_mask >> 7) & 1u) && !(roles & 1u);
+                const bool act0_respond = (roles >> 7) & 1u;
                 mover = occ_mask == 0u || (games == 0 && (act7_challenge || act0_respond));
-                s_out[cl] = (uint8_t)(TF_OCC | trait);
+                s_out[cl] = (uint8_t)(TF_OCC | ((rme >> 8) & TF_TRAIT));
                 s_e[cl] = e;
             }
         }
         const uint32_t slot = wappend(&s_n[2], mover);
         if (mover) { s_mover[slot] = (uint16_t)cl; ++n_movers; }
-        __syncwarp();
     }
     __syncthreads();
     // ---- movers: travel cost, death, random start, probe, claim (:794-868)
