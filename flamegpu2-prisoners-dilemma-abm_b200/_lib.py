@@ -11,6 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libpdabm.so")
 PD_OK = 0
 PD_TF_TRAIT_MASK = 0x03
 PD_TF_OCCUPIED = 0x80
+PD_PART_PRE, PD_PART_RETRY, PD_PART_HIST, PD_PART_CAND, PD_PART_APPLY = 0, 1, 2, 3, 4
+PD_GLB_WORDS, PD_HIST_WORDS = 20, 2048
 
 
 class pd_config(C.Structure):
@@ -44,7 +46,8 @@ class pd_config(C.Structure):
         ("collect_stats", C.c_uint8),
         ("device", C.c_int32),
         ("sparse_ctas", C.c_int32),
-        ("reserved", C.c_uint32 * 4),
+        ("ghost_rows", C.c_uint32),
+        ("reserved", C.c_uint32 * 3),
     ]
 
 
@@ -59,7 +62,7 @@ EXPORTS = (
     "pd_last_error", "pd_abi_version", "pd_default_config", "pd_create", "pd_destroy",
     "pd_bind_planes", "pd_init_population", "pd_sync_state", "pd_step", "pd_read_counts",
     "pd_read_stats", "pd_get_step", "pd_set_step", "pd_step_host", "pd_read_agent_steps",
-    "pd_set_profile", "pd_read_profile",
+    "pd_set_profile", "pd_read_profile", "pd_bind_comm", "pd_step_part",
 )
 
 _lib = None
@@ -110,6 +113,10 @@ def load() -> C.CDLL:
     lib.pd_set_profile.argtypes = [vp, i32]
     lib.pd_read_profile.restype = i32
     lib.pd_read_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u32), vp]
+    lib.pd_bind_comm.restype = i32
+    lib.pd_bind_comm.argtypes = [vp, vp, vp, vp, vp, u32, u32]
+    lib.pd_step_part.restype = i32
+    lib.pd_step_part.argtypes = [vp, i32, i32, vp, i32]
     lib.pd_debug_philox.restype = i32
     lib.pd_debug_philox.argtypes = [vp, vp, i32]
     _lib = lib

@@ -63,9 +63,16 @@ __device__ __forceinline__ void load_tile_vec(const Params& p, const uint8_t* __
     const uint32_t wch = p.W >> 4;  // 16-byte chunks per row
     for (int i = threadIdx.x; i < SH * NCH; i += NT) {
         const int r = i / NCH, j = i - r * NCH;
-        const uint32_t gy = (y0 + (uint32_t)(r - HALO)) & (p.H - 1);
         const uint32_t cx = ((x0 >> 4) + (uint32_t)(j - 1)) & (wch - 1);
-        const uint4 v = *reinterpret_cast<const uint4*>(plane + ((size_t)gy << p.log2W) + ((size_t)cx << 4));
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (p.wrap_y) {
+            const uint32_t gy = (y0 + (uint32_t)(r - HALO)) & (p.H - 1);
+            v = *reinterpret_cast<const uint4*>(plane + ((size_t)gy << p.log2W) + ((size_t)cx << 4));
+        } else {  // slab: rows beyond the local planes read as empty (they are outside the valid zone)
+            const int gy = (int)y0 + r - HALO;
+            if (gy >= 0 && gy < (int)p.H)
+                v = *reinterpret_cast<const uint4*>(plane + ((size_t)gy << p.log2W) + ((size_t)cx << 4));
+        }
         *reinterpret_cast<uint4*>(s + r * SW + j * 16) = v;
     }
 }
@@ -396,7 +403,7 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
         const int ly = (i * 4) >> LOG_TW, lx = (i * 4) & (TW - 1);
         *reinterpret_cast<float4*>(p.E1 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = reinterpret_cast<float4*>(s_e)[i];
     }
-    if (p.stats) {
+    if (p.stats && row_owned(p, y0)) {  // tiles are entirely owned or entirely ghost (16-row granularity)
         if (n_play_deaths) atomicAdd(&p.ctr->st_play_deaths, (unsigned long long)n_play_deaths);
         if (n_movers) atomicAdd(&p.ctr->st_movers, (unsigned long long)n_movers);
         if (n_travel_deaths) atomicAdd(&p.ctr->st_travel_deaths, (unsigned long long)n_travel_deaths);
@@ -450,7 +457,9 @@ __device__ __forceinline__ void resolve_claims(const Params& p, const uint8_t* s
         const int si = s_list[k];
         const int r = si / SW, c = si - r * SW;
         const uint32_t tx = (x0 + (uint32_t)(c - 16)) & (p.W - 1);
-        const uint32_t ty = (y0 + (uint32_t)(r - 2)) & (p.H - 1);
+        // local row of the contested cell (may be -1 or H in the ring): only used through nb_gcell,
+        // which maps it to the GLOBAL row modulo the world height
+        const uint32_t ty = p.wrap_y ? ((y0 + (uint32_t)(r - 2)) & (p.H - 1)) : (y0 + (uint32_t)(r - 2));
         uint32_t m = s_cl[si];
         int best = -1;
         Key bk;
@@ -584,7 +593,7 @@ __global__ void __launch_bounds__(NT) k_move_commit(const __grid_constant__ Para
         *reinterpret_cast<uint4*>(p.tfA + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = reinterpret_cast<uint4*>(s_out)[i];
     }
     flush_cells<TW>(p, s_lost, s_n[1], &p.ctr->mv_n, p.mv_cell, s_lost_state, p.mv_state, x0, y0, &s_n[2]);
-    if (p.stats && n_moved) atomicAdd(&p.ctr->st_moved, (unsigned long long)n_moved);
+    if (p.stats && n_moved && row_owned(p, y0)) atomicAdd(&p.ctr->st_moved, (unsigned long long)n_moved);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -767,24 +776,31 @@ __global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Par
     if (n_old) atomicAdd(&s_n[5], n_old);
     if (n_dead) atomicAdd(&s_n[7], n_dead);
     __syncthreads();
-    // one atomic per list per CTA, then plain copies
+    // one atomic per list per CTA, then plain copies.  A ghost tile of a slab only contributes its claim
+    // losers (the retry rounds need them); its newborns, deaths and counts belong to the owning slab.
+    const bool owned = row_owned(p, y0);
+    if (!owned) {
+        if (tid == 0) { s_n[3] = 0; s_n[4] = 0; s_n[5] = 0; s_n[7] = 0; }
+        __syncthreads();
+    }
+    const unsigned int n_birth_listed = owned ? n_birth : 0u;
     if (tid < 4) {
-        const unsigned int n = tid == 0 ? s_n[2] : tid == 1 ? n_birth : tid == 2 ? s_n[3] : s_n[4];
+        const unsigned int n = tid == 0 ? s_n[2] : tid == 1 ? n_birth_listed : tid == 2 ? s_n[3] : s_n[4];
         unsigned int* gc = tid == 0 ? &p.ctr->rp_n : tid == 1 ? &p.ctr->nb_n
                          : tid == 2 ? &p.ctr->risk_next_n : &p.ctr->dead_n;
         s_base[tid] = n ? atomicAdd(gc, n) : 0u;
     }
     __syncthreads();
     copy_cells<TW>(p, s_lost, s_n[2], s_base[0], p.rp_cell, s_lost_state, p.rp_state, x0, y0);
-    copy_cells<TW>(p, s_birth, n_birth, s_base[1], p.nb_cell, nullptr, nullptr, x0, y0);
+    copy_cells<TW>(p, s_birth, n_birth_listed, s_base[1], p.nb_cell, nullptr, nullptr, x0, y0);
     copy_cells<TW>(p, s_risk, s_n[3], s_base[2], p.risk_next, nullptr, nullptr, x0, y0);
     copy_cells<TW>(p, s_dead, s_n[4], s_base[3], p.dead_cell, nullptr, nullptr, x0, y0);
     if (tid == 0) {
         if (s_n[5]) atomicAdd(&p.ctr->n_old, (unsigned long long)s_n[5]);
-        if (n_birth) atomicAdd(&p.ctr->births, (unsigned long long)n_birth);
+        if (n_birth_listed) atomicAdd(&p.ctr->births, (unsigned long long)n_birth_listed);
         if (s_n[7]) atomicAdd(&p.ctr->living_deaths, (unsigned long long)s_n[7]);
     }
-    if (p.want_counts && tid < 16 && s_bins[tid]) atomicAdd(&p.ctr->bins[tid], (unsigned long long)s_bins[tid]);
+    if (p.want_counts && owned && tid < 16 && s_bins[tid]) atomicAdd(&p.ctr->bins[tid], (unsigned long long)s_bins[tid]);
 }
 
 }  // namespace pd

@@ -87,6 +87,18 @@ struct Params {
     unsigned long long max_agents;
     uint32_t pure, per_trait, max_children, want_counts, stats;
     uint32_t list_cap, sparse_ctas;
+    // row-slab decomposition (DESIGN.md "Multi-GPU"): the local planes hold `H` rows = owned rows plus
+    // a ghost zone above and below; rows wrap only when the handle owns the whole world
+    uint32_t wrap_y;          // 1: H == W, rows wrap (whole world); 0: slab with ghost rows, no wrap
+    uint32_t own_y0, own_y1;  // owned local rows [own_y0, own_y1); counters/cull only see these
+    uint32_t round0, round1;  // reproduction retry rounds to run in this launch (slab mode)
+    uint32_t world;           // number of slabs
+    uint32_t cand_cap;        // capacity (keys) of one rank's candidate block
+    unsigned long long* glb;        // [0] olds [1] births [2] active repro losers [3] agents [4..19] bins,
+                                    // summed over all slabs by the caller between the step's parts
+    unsigned int* ghist;            // 2048-bin cull histogram, summed over all slabs by the caller
+    unsigned long long* cand_out;   // this slab's cull candidates: [0] = count, then keys
+    const unsigned long long* cand_all;  // all slabs' candidate blocks, gathered by the caller
     // planes
     float* E0;       // caller-bound energy (state between steps)
     float* E1;       // scratch energy (state between play and the final sweep)
@@ -111,13 +123,22 @@ __device__ __forceinline__ Words rng_init(const Params& p, uint64_t gcell, uint3
 
 // global cell index (x + y*env_max, :339) of local cell (x, y) and of its neighbours
 __device__ __forceinline__ uint64_t gcell_of(const Params& p, uint32_t x, uint32_t y) {
-    return ((uint64_t)(p.row0 + y) << p.log2W) | x;
+    return ((uint64_t)((p.row0 + y) & (p.W - 1)) << p.log2W) | x;
 }
-// local plane index of the neighbour of local (x,y) in direction d, wrapping (:311-312)
+// local row of the neighbour row y + dy: wraps for a whole world (:311-312); a slab never wraps --
+// its outermost ghost rows are outside the zone whose results are used, so the index is just clamped
+__device__ __forceinline__ uint32_t nb_row(const Params& p, uint32_t y, int dy) {
+    if (p.wrap_y) return (y + (uint32_t)dy) & (p.H - 1);
+    const int r = (int)y + dy;
+    return (uint32_t)(r < 0 ? 0 : (r >= (int)p.H ? (int)p.H - 1 : r));
+}
+// local plane index of the neighbour of local (x,y) in direction d
 __device__ __forceinline__ uint32_t nb_local(const Params& p, uint32_t x, uint32_t y, int d) {
     const uint32_t nx = (x + (uint32_t)DX(d)) & (p.W - 1);
-    const uint32_t ny = (y + (uint32_t)DY(d)) & (p.H - 1);
-    return (ny << p.log2W) | nx;
+    return (nb_row(p, y, DY(d)) << p.log2W) | nx;
+}
+__device__ __forceinline__ bool row_owned(const Params& p, uint32_t y) {
+    return y >= p.own_y0 && y < p.own_y1;
 }
 __device__ __forceinline__ uint64_t nb_gcell(const Params& p, uint32_t x, uint32_t y, int d) {
     const uint32_t nx = (x + (uint32_t)DX(d)) & (p.W - 1);

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(1024) k_move_retry(const __grid_constant__ Par
                 p.tfA[tgt] = (uint8_t)(TF_OCC | (t & TF_TRAIT));
                 p.tfA[cell] = (uint8_t)TF_GHOST;
                 p.mv_state[i] = 0;
-                if (p.stats) atomicAdd(&ctr->st_moved, 1ull);
+                if (p.stats && row_owned(p, y)) atomicAdd(&ctr->st_moved, 1ull);
             } else {
                 p.tfA[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
                 ++still;
@@ -185,9 +185,12 @@ __global__ void __launch_bounds__(1024) k_repro_retry(const __grid_constant__ Pa
     if (n == 0) return;
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int round = 1; round < 8; ++round) {
-        // overpopulated gate, evaluated after every round (:1616, :1621-1625)
-        if (__ldcg(&ctr->n_old) + __ldcg(&ctr->births) > p.max_agents) break;
+    for (int round = (int)p.round0; round < (int)p.round1; ++round) {
+        // overpopulated gate, evaluated after every round (:1616, :1621-1625); in slab mode the caller
+        // has summed olds and births over all slabs into glb[] before this launch (one round per launch)
+        const unsigned long long pop = p.glb ? __ldcg(&p.glb[0]) + __ldcg(&p.glb[1])
+                                             : __ldcg(&ctr->n_old) + __ldcg(&ctr->births);
+        if (pop > p.max_agents) break;
         // ---- go forth
         for (unsigned int i = t0; i < n; i += stride) {
             const uint32_t st = p.rp_state[i];
@@ -254,11 +257,13 @@ __global__ void __launch_bounds__(1024) k_repro_retry(const __grid_constant__ Pa
                 p.E0[tgt] = ce;
                 p.strat[tgt] = (uint8_t)cs;
                 p.tfA[tgt] = (uint8_t)(TF_OCC | TF_NEWBORN | (t & TF_TRAIT));
-                const unsigned int slot = atomicAdd(&ctr->nb_n, 1u);
-                if (slot < p.list_cap) p.nb_cell[slot] = tgt;
-                else atomicExch(&ctr->overflow, 1u);
+                if (row_owned(p, tgt >> p.log2W)) {  // a child in the ghost zone belongs to the neighbour slab
+                    const unsigned int slot = atomicAdd(&ctr->nb_n, 1u);
+                    if (slot < p.list_cap) p.nb_cell[slot] = tgt;
+                    else atomicExch(&ctr->overflow, 1u);
+                    ++born;
+                }
                 p.rp_state[i] = 0x40u;  // REPRODUCTION_COMPLETE; living cost still due
-                ++born;
             } else {
                 ++still;
             }
@@ -271,118 +276,120 @@ __global__ void __launch_bounds__(1024) k_repro_retry(const __grid_constant__ Pa
 }
 
 // ------------------------------------------------------------------------------------------
-// k_finalize (sparse, persistent): the carrying-capacity cull, the deferred living cost of
+// Finalisation (sparse, persistent): the carrying-capacity cull, the deferred living cost of
 // the repro-loser list, the newborns' counts and the bookkeeping for the next step.
 // Cull (replaces the list-index rule :1343/:1354, SURVEY B-4): if olds + births exceed
 // max_agents, only the K = max_agents - olds newborns with the highest (Philox cull priority,
 // cell) keys survive.  The K-th largest 64-bit key is found exactly by a radix select: one
 // 2048-bin histogram of the top 11 bits over all newborns, compaction of the threshold bin's
 // few candidates, then 8-bit passes over the candidates only (CTA 0).
+// Whole world: one kernel (k_finalize).  Row slabs: three kernels (k_fin_hist, k_fin_cand,
+// k_fin_apply) with the caller summing the histogram and gathering the candidates in between.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long cull_key(const Params& p, uint32_t cell, uint32_t prio) {
     const uint64_t g = gcell_of(p, cell & (p.W - 1), cell >> p.log2W);
     return ((unsigned long long)prio << 32) | (uint32_t)g;
 }
 
-__global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Params p) {
-    Counters* ctr = p.ctr;
-    __shared__ unsigned int s_hist[2048];
-    __shared__ unsigned long long s_prefix;
-    __shared__ unsigned long long s_krem;
-    __shared__ unsigned int s_digit;
+struct CullPlan {
+    bool cull;                 // olds + births exceed the cap
+    unsigned long long keep;   // newborns allowed to survive (all slabs together)
+};
+__device__ __forceinline__ CullPlan cull_plan(const Params& p) {
+    const unsigned long long n_old = p.glb ? __ldcg(&p.glb[0]) : p.ctr->n_old;
+    const unsigned long long births = p.glb ? __ldcg(&p.glb[1]) : p.ctr->births;
+    CullPlan c;
+    c.cull = n_old + births > p.max_agents;
+    c.keep = 0;
+    if (c.cull) {
+        c.keep = p.max_agents > n_old ? p.max_agents - n_old : 0ull;
+        if (c.keep >= births) c.cull = false;
+    }
+    return c;
+}
+
+// pass A: priorities of this slab's newborns + histogram of their top 11 bits into `hist` (global memory)
+__device__ __forceinline__ void fin_hist(const Params& p, unsigned int nb, unsigned int* hist, unsigned int* s_hist) {
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned int nb = ctr->nb_n;
-    if (nb > p.list_cap) nb = p.list_cap;
-    unsigned int nrp = ctr->rp_n;
-    if (nrp > p.list_cap) nrp = p.list_cap;
-    const unsigned long long n_old = ctr->n_old;
-    const unsigned long long births = ctr->births;
-    unsigned int* g_hist = &ctr->hist[0][0];         // 2048 words
-    uint32_t* cand = p.risk_roll;                     // scratch: indices into the newborn list
-    // ---- cull threshold
-    bool cull = n_old + births > p.max_agents;
-    unsigned long long keep = 0;
-    unsigned long long tau = 0;  // survive iff key >= tau
-    if (cull) {
-        keep = p.max_agents > n_old ? p.max_agents - n_old : 0ull;
-        if (keep >= births) cull = false;
+    for (unsigned int i = threadIdx.x; i < 2048; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (unsigned int i = t0; i < nb; i += stride) {
+        const uint32_t cell = p.nb_cell[i];
+        const uint32_t prio = rng(p, gcell_of(p, cell & (p.W - 1), cell >> p.log2W), S_CULL).x;
+        p.nb_prio[i] = prio;
+        atomicAdd(&s_hist[prio >> 21], 1u);
     }
-    if (cull && keep > 0) {
-        // pass A: priorities + histogram of the top 11 bits
-        for (unsigned int i = threadIdx.x; i < 2048; i += blockDim.x) s_hist[i] = 0;
-        __syncthreads();
-        for (unsigned int i = t0; i < nb; i += stride) {
-            const uint32_t cell = p.nb_cell[i];
-            const uint32_t prio = rng(p, gcell_of(p, cell & (p.W - 1), cell >> p.log2W), S_CULL).x;
-            p.nb_prio[i] = prio;
-            atomicAdd(&s_hist[prio >> 21], 1u);
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i < 2048; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+}
+
+// threshold bin of the (summed) histogram; every CTA computes it identically.  Returns the bin;
+// *krem = how many of the bin's candidates survive.
+__device__ __forceinline__ unsigned int fin_digit(const unsigned int* hist, unsigned long long keep,
+                                                  unsigned int* s_hist, unsigned int* s_digit,
+                                                  unsigned long long* s_krem) {
+    for (unsigned int i = threadIdx.x; i < 2048; i += blockDim.x) s_hist[i] = __ldcg(&hist[i]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long cum = 0;
+        int digit = 0;
+        for (int b = 2047; b >= 0; --b) {
+            const unsigned long long h = s_hist[b];
+            if (cum + h >= keep) { digit = b; break; }
+            cum += h;
         }
+        *s_digit = (unsigned int)digit;
+        *s_krem = keep - cum;
+    }
+    __syncthreads();
+    return *s_digit;
+}
+
+// krem-th largest of `n` candidate keys (all with the same top 11 bits `digit`), by CTA 0 only:
+// 8 bits per pass over the low 53 bits.  key(k) fetches candidate k.
+template <typename KeyAt>
+__device__ __forceinline__ unsigned long long fin_select(unsigned int n, unsigned int digit, unsigned int* s_hist,
+                                                         unsigned long long* s_prefix, unsigned long long* s_krem,
+                                                         KeyAt key_at) {
+    if (threadIdx.x == 0) *s_prefix = (unsigned long long)digit;  // the 11 bits decided so far
+    int decided = 11;
+    while (decided < 64) {
+        const int bits = (64 - decided) >= 8 ? 8 : (64 - decided);
+        const int shift = 64 - decided - bits;
+        if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
         __syncthreads();
-        for (unsigned int i = threadIdx.x; i < 2048; i += blockDim.x)
-            if (s_hist[i]) atomicAdd(&g_hist[i], s_hist[i]);
-        grid_sync(ctr->barrier, gridDim.x);
-        // threshold bin: every CTA computes it identically from the global histogram
-        for (unsigned int i = threadIdx.x; i < 2048; i += blockDim.x) s_hist[i] = __ldcg(&g_hist[i]);
+        const unsigned long long prefix = *s_prefix;
+        for (unsigned int k = threadIdx.x; k < n; k += blockDim.x) {
+            const unsigned long long key = key_at(k);
+            if ((key >> (shift + bits)) == prefix)
+                atomicAdd(&s_hist[(unsigned int)(key >> shift) & ((1u << bits) - 1u)], 1u);
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
-            unsigned long long cum = 0;
-            int digit = 0;
-            for (int b = 2047; b >= 0; --b) {
+            unsigned long long krem = *s_krem, cum = 0;
+            int dg = 0;
+            for (int b = (1 << bits) - 1; b >= 0; --b) {
                 const unsigned long long h = s_hist[b];
-                if (cum + h >= keep) { digit = b; break; }
+                if (cum + h >= krem) { dg = b; break; }
                 cum += h;
             }
-            s_digit = (unsigned int)digit;
-            s_krem = keep - cum;  // how many of the threshold bin's candidates survive
+            *s_krem = krem - cum;
+            *s_prefix = (prefix << bits) | (unsigned long long)dg;
         }
         __syncthreads();
-        const unsigned int digit = s_digit;
-        // pass B: compact the candidates (newborns whose top 11 bits equal the threshold bin)
-        for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nb; i0 += stride) {
-            const unsigned int i = i0 + threadIdx.x;
-            const bool is_cand = i < nb && (p.nb_prio[i] >> 21) == digit;
-            const uint32_t slot = warp_append(&ctr->cand_n, is_cand);
-            if (is_cand) cand[slot] = i;
-        }
-        grid_sync(ctr->barrier, gridDim.x);
-        // CTA 0: krem-th largest key among the candidates, 8 bits per pass over the low 53 bits
-        if (blockIdx.x == 0) {
-            const unsigned int nc = __ldcg(&ctr->cand_n);
-            if (threadIdx.x == 0) s_prefix = (unsigned long long)digit;  // the 11 bits decided so far
-            int decided = 11;
-            while (decided < 64) {
-                const int bits = (64 - decided) >= 8 ? 8 : (64 - decided);
-                const int shift = 64 - decided - bits;
-                if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
-                __syncthreads();
-                const unsigned long long prefix = s_prefix;
-                for (unsigned int k = threadIdx.x; k < nc; k += blockDim.x) {
-                    const unsigned int i = __ldcg(&cand[k]);
-                    const unsigned long long key = cull_key(p, p.nb_cell[i], p.nb_prio[i]);
-                    if ((key >> (shift + bits)) == prefix)
-                        atomicAdd(&s_hist[(unsigned int)(key >> shift) & ((1u << bits) - 1u)], 1u);
-                }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    unsigned long long krem = s_krem, cum = 0;
-                    int dg = 0;
-                    for (int b = (1 << bits) - 1; b >= 0; --b) {
-                        const unsigned long long h = s_hist[b];
-                        if (cum + h >= krem) { dg = b; break; }
-                        cum += h;
-                    }
-                    s_krem = krem - cum;
-                    s_prefix = (prefix << bits) | (unsigned long long)dg;
-                }
-                __syncthreads();
-                decided += bits;
-            }
-            if (threadIdx.x == 0) ctr->tau = s_prefix;
-        }
-        grid_sync(ctr->barrier, gridDim.x);
-        tau = __ldcg(&ctr->tau);
+        decided += bits;
     }
+    return *s_prefix;
+}
+
+// newborns: cull or admit; deferred living cost of the repro losers; dying agents leave; all OWNED rows only
+__device__ __forceinline__ void fin_apply(const Params& p, unsigned int nb, unsigned int nrp, bool cull,
+                                          unsigned long long keep, unsigned long long tau) {
+    Counters* ctr = p.ctr;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     // ---- newborns: cull or admit (no living cost in the birth step, :1343)
     unsigned int n_culled = 0;
     for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nb; i0 += stride) {
@@ -418,17 +425,19 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Param
         bool at_risk = false;
         if (i < nrp) {
             const uint32_t cell = p.rp_cell[i];
-            const uint32_t t = __ldcg(p.tfA + cell);
-            float e = __ldcg(p.E0 + cell);
-            if (punish(p, e)) {
-                p.E0[cell] = e;
-                p.tfA[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
-                at_risk = e <= p.risk_thr;
-                if (p.want_counts) atomicAdd(&ctr->bins[count_bin(__ldcg(p.strat + cell), t & TF_TRAIT)], 1ull);
-            } else {
-                p.E0[cell] = 0.0f;
-                p.tfA[cell] = 0;
-                ++n_dead;
+            if (row_owned(p, cell >> p.log2W)) {
+                const uint32_t t = __ldcg(p.tfA + cell);
+                float e = __ldcg(p.E0 + cell);
+                if (punish(p, e)) {
+                    p.E0[cell] = e;
+                    p.tfA[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
+                    at_risk = e <= p.risk_thr;
+                    if (p.want_counts) atomicAdd(&ctr->bins[count_bin(__ldcg(p.strat + cell), t & TF_TRAIT)], 1ull);
+                } else {
+                    p.E0[cell] = 0.0f;
+                    p.tfA[cell] = 0;
+                    ++n_dead;
+                }
             }
         }
         const uint32_t slot = warp_append(&ctr->risk_next_n, at_risk);
@@ -442,23 +451,182 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Param
     unsigned int ndead = ctr->dead_n;
     if (ndead > p.list_cap) ndead = p.list_cap;
     for (unsigned int i = t0; i < ndead; i += stride) p.tfA[p.dead_cell[i]] = 0;
+}
+
+// bookkeeping by one thread after everything else of the step is done
+__device__ __forceinline__ void fin_bookkeeping(const Params& p) {
+    Counters* ctr = p.ctr;
+    const unsigned long long culled = __ldcg(&ctr->culled);
+    const unsigned long long ld = __ldcg(&ctr->living_deaths);
+    const unsigned long long b = __ldcg(&ctr->births);
+    ctr->n_agents = __ldcg(&ctr->n_old) + b - culled - ld;  // this slab's agents
+    unsigned int rn = __ldcg(&ctr->risk_next_n);
+    ctr->risk_n = rn > p.list_cap ? p.list_cap : rn;
+    if (p.want_counts)
+        for (int k = 0; k < 16; ++k) ctr->last_bins[k] = __ldcg(&ctr->bins[k]);
+    unsigned long long* s = ctr->last_stats;
+    s[0] = ctr->agents_start; s[1] = ctr->n_agents;
+    s[2] = __ldcg(&ctr->st_play_deaths); s[3] = __ldcg(&ctr->st_movers);
+    s[4] = __ldcg(&ctr->st_moved); s[5] = __ldcg(&ctr->st_travel_deaths);
+    s[6] = b; s[7] = culled; s[8] = ld;
+    s[9] = rn; s[10] = __ldcg(&ctr->mv_n); s[11] = __ldcg(&ctr->rp_n);
+    if (p.glb) {  // publish this slab's totals; the caller sums them over the slabs when it wants them
+        p.glb[3] = ctr->n_agents;
+        for (int k = 0; k < 16; ++k) p.glb[4 + k] = p.want_counts ? ctr->last_bins[k] : 0ull;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Params p) {
+    Counters* ctr = p.ctr;
+    __shared__ unsigned int s_hist[2048];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned long long s_krem;
+    __shared__ unsigned int s_digit;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    unsigned int nb = ctr->nb_n;
+    if (nb > p.list_cap) nb = p.list_cap;
+    unsigned int nrp = ctr->rp_n;
+    if (nrp > p.list_cap) nrp = p.list_cap;
+    unsigned int* g_hist = &ctr->hist[0][0];  // 2048 words
+    uint32_t* cand = p.risk_roll;              // scratch: indices into the newborn list
+    const CullPlan plan = cull_plan(p);
+    unsigned long long tau = 0;                // survive iff key >= tau
+    if (plan.cull && plan.keep > 0) {
+        fin_hist(p, nb, g_hist, s_hist);
+        grid_sync(ctr->barrier, gridDim.x);
+        const unsigned int digit = fin_digit(g_hist, plan.keep, s_hist, &s_digit, &s_krem);
+        for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nb; i0 += stride) {
+            const unsigned int i = i0 + threadIdx.x;
+            const bool is_cand = i < nb && (p.nb_prio[i] >> 21) == digit;
+            const uint32_t slot = warp_append(&ctr->cand_n, is_cand);
+            if (is_cand) cand[slot] = i;
+        }
+        grid_sync(ctr->barrier, gridDim.x);
+        if (blockIdx.x == 0) {
+            const unsigned int nc = __ldcg(&ctr->cand_n);
+            const unsigned long long t = fin_select(nc, digit, s_hist, &s_prefix, &s_krem, [&](unsigned int k) {
+                const unsigned int i = __ldcg(&cand[k]);
+                return cull_key(p, p.nb_cell[i], p.nb_prio[i]);
+            });
+            if (threadIdx.x == 0) ctr->tau = t;
+        }
+        grid_sync(ctr->barrier, gridDim.x);
+        tau = __ldcg(&ctr->tau);
+    }
+    fin_apply(p, nb, nrp, plan.cull, plan.keep, tau);
     grid_sync(ctr->barrier, gridDim.x);
-    // ---- bookkeeping (one thread)
+    if (blockIdx.x == 0 && threadIdx.x == 0) fin_bookkeeping(p);
+}
+
+// ---- row slabs, part 1: this slab's histogram into the bound exchange buffer (summed by the caller)
+__global__ void __launch_bounds__(1024) k_fin_hist(const __grid_constant__ Params p) {
+    __shared__ unsigned int s_hist[2048];
+    Counters* ctr = p.ctr;
+    const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned int i = t0; i < 2048; i += gridDim.x * blockDim.x) p.ghist[i] = 0;
+    grid_sync(ctr->barrier, gridDim.x);
+    const CullPlan plan = cull_plan(p);
+    if (!(plan.cull && plan.keep > 0)) return;
+    unsigned int nb = ctr->nb_n;
+    if (nb > p.list_cap) nb = p.list_cap;
+    fin_hist(p, nb, p.ghist, s_hist);
+}
+
+// ---- part 2 (after the histogram was summed): this slab's candidate keys into cand_out
+__global__ void __launch_bounds__(1024) k_fin_cand(const __grid_constant__ Params p) {
+    __shared__ unsigned int s_hist[2048];
+    __shared__ unsigned long long s_krem;
+    __shared__ unsigned int s_digit;
+    Counters* ctr = p.ctr;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    const CullPlan plan = cull_plan(p);
+    if (!(plan.cull && plan.keep > 0)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) p.cand_out[0] = 0ull;
+        return;
+    }
+    unsigned int nb = ctr->nb_n;
+    if (nb > p.list_cap) nb = p.list_cap;
+    const unsigned int digit = fin_digit(p.ghist, plan.keep, s_hist, &s_digit, &s_krem);
+    for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nb; i0 += stride) {
+        const unsigned int i = i0 + threadIdx.x;
+        const bool is_cand = i < nb && (p.nb_prio[i] >> 21) == digit;
+        const uint32_t slot = warp_append(&ctr->cand_n, is_cand);
+        if (is_cand) {
+            if (slot < p.cand_cap) p.cand_out[1 + slot] = cull_key(p, p.nb_cell[i], p.nb_prio[i]);
+            else atomicExch(&ctr->overflow, 1u);
+        }
+    }
+    grid_sync(ctr->barrier, gridDim.x);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const unsigned long long culled = __ldcg(&ctr->culled);
-        const unsigned long long ld = __ldcg(&ctr->living_deaths);
-        const unsigned long long b = __ldcg(&ctr->births);
-        ctr->n_agents = n_old + b - culled - ld;
-        unsigned int rn = __ldcg(&ctr->risk_next_n);
-        ctr->risk_n = rn > p.list_cap ? p.list_cap : rn;
-        if (p.want_counts)
-            for (int k = 0; k < 16; ++k) ctr->last_bins[k] = __ldcg(&ctr->bins[k]);
-        unsigned long long* s = ctr->last_stats;
-        s[0] = ctr->agents_start; s[1] = ctr->n_agents;
-        s[2] = __ldcg(&ctr->st_play_deaths); s[3] = __ldcg(&ctr->st_movers);
-        s[4] = __ldcg(&ctr->st_moved); s[5] = __ldcg(&ctr->st_travel_deaths);
-        s[6] = b; s[7] = culled; s[8] = ld;
-        s[9] = rn; s[10] = __ldcg(&ctr->mv_n); s[11] = __ldcg(&ctr->rp_n);
+        const unsigned int n = __ldcg(&ctr->cand_n);
+        p.cand_out[0] = n < p.cand_cap ? n : p.cand_cap;
+    }
+}
+
+// ---- part 3 (after all slabs' candidates were gathered): threshold, apply, bookkeeping
+__global__ void __launch_bounds__(1024) k_fin_apply(const __grid_constant__ Params p) {
+    __shared__ unsigned int s_hist[2048];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned long long s_krem;
+    __shared__ unsigned int s_digit;
+    Counters* ctr = p.ctr;
+    unsigned int nb = ctr->nb_n;
+    if (nb > p.list_cap) nb = p.list_cap;
+    unsigned int nrp = ctr->rp_n;
+    if (nrp > p.list_cap) nrp = p.list_cap;
+    const CullPlan plan = cull_plan(p);
+    unsigned long long tau = 0;
+    if (plan.cull && plan.keep > 0) {
+        const unsigned int digit = fin_digit(p.ghist, plan.keep, s_hist, &s_digit, &s_krem);
+        if (blockIdx.x == 0) {
+            // candidates of slab w live at cand_all[w * (1 + cap) + 1 ...]; flatten by a linear search
+            // over the (at most 8) block counts
+            const unsigned long long blk = 1ull + p.cand_cap;
+            unsigned int total = 0;
+            for (uint32_t w = 0; w < p.world; ++w) total += (unsigned int)__ldcg(&p.cand_all[w * blk]);
+            const unsigned long long t = fin_select(total, digit, s_hist, &s_prefix, &s_krem, [&](unsigned int k) {
+                uint32_t w = 0;
+                unsigned int cnt = (unsigned int)__ldcg(&p.cand_all[0]);
+                while (k >= cnt) { k -= cnt; ++w; cnt = (unsigned int)__ldcg(&p.cand_all[w * blk]); }
+                return __ldcg(&p.cand_all[w * blk + 1 + k]);
+            });
+            if (threadIdx.x == 0) ctr->tau = t;
+        }
+        grid_sync(ctr->barrier, gridDim.x);
+        tau = __ldcg(&ctr->tau);
+    }
+    fin_apply(p, nb, nrp, plan.cull, plan.keep, tau);
+    grid_sync(ctr->barrier, gridDim.x);
+    if (blockIdx.x == 0 && threadIdx.x == 0) fin_bookkeeping(p);
+}
+
+// ---- row slabs: publish this slab's olds / births / still-active repro losers for the caller to sum
+__global__ void k_publish_gate(const __grid_constant__ Params p, int round) {
+    if (threadIdx.x == 0) {
+        p.glb[0] = p.ctr->n_old;
+        p.glb[1] = p.ctr->births;
+        p.glb[2] = round == 0 ? p.ctr->rp_n : p.ctr->rp_active[round];
+    }
+}
+
+// ---- row slabs: the at-risk agents of the freshly received ghost rows join the current list
+__global__ void __launch_bounds__(256) k_ghost_risk_scan(const __grid_constant__ Params p) {
+    const size_t W = p.W;
+    const size_t n_top = (size_t)p.own_y0 * W, n_bot = (size_t)(p.H - p.own_y1) * W;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x; i0 < n_top + n_bot; i0 += stride) {
+        const size_t i = i0 + threadIdx.x;
+        bool at_risk = false;
+        size_t cell = 0;
+        if (i < n_top + n_bot) {
+            cell = i < n_top ? i : (size_t)p.own_y1 * W + (i - n_top);
+            at_risk = (p.tfA[cell] & TF_OCC) && p.E0[cell] <= p.risk_thr;
+        }
+        const uint32_t slot = warp_append(&p.ctr->risk_n, at_risk);
+        if (at_risk) {
+            if (slot < p.list_cap) p.risk_cur[slot] = (uint32_t)cell;
+            else atomicExch(&p.ctr->overflow, 1u);
+        }
     }
 }
 
@@ -477,7 +645,7 @@ __global__ void __launch_bounds__(NT) k_scan_state(const __grid_constant__ Param
     for (size_t i0 = (size_t)blockIdx.x * NT; i0 < cells; i0 += stride) {
         const size_t i = i0 + threadIdx.x;
         bool at_risk = false;
-        if (i < cells) {
+        if (i < cells && row_owned(p, (uint32_t)(i >> p.log2W))) {
             const uint32_t t = p.tfA[i];
             if (t & TF_OCC) {
                 ++n;
@@ -527,7 +695,7 @@ __global__ void __launch_bounds__(NT) k_init_hist(const __grid_constant__ Params
     const int shift = 56 - 8 * pass;
     const size_t stride = (size_t)gridDim.x * NT;
     for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < cells; i += stride) {
-        const uint64_t g = gcell_of(p, (uint32_t)(i & (p.W - 1)), (uint32_t)(i >> p.log2W));
+        const uint64_t g = (uint64_t)i;  // GLOBAL cell index: every slab scans the whole world and finds the same threshold
         const unsigned long long key = place_key(p, g);
         if (pass == 0 || (key >> (shift + 8)) == prefix)
             atomicAdd(&s_hist[(unsigned int)(key >> shift) & 255u], 1u);

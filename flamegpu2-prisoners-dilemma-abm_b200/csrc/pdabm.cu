@@ -72,6 +72,8 @@ struct pd_sim {
     int n_sms;
     int sparse_ctas, sparse_threads;
     bool big_tiles;
+    bool slab;        // row slab of a larger world (ghost rows, pd_step_part)
+    bool comm_bound;
     dim3 grid;
     HostOut* h;  // pinned
     bool lists_allocated;
@@ -183,8 +185,16 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     const uint32_t W = cfg->width;
     if (W < 16 || (W & (W - 1))) return fail(PD_ERR_INVALID, "width must be a power of two >= 16 (got %u)", W);
     if (W > 65536) return fail(PD_ERR_INVALID, "width > 65536 not supported");
-    if (cfg->row0 != 0 || cfg->rows != W)
-        return fail(PD_ERR_INVALID, "row-slab decomposition (row0=%u rows=%u) is not built yet: pass row0=0, rows=width", cfg->row0, cfg->rows);
+    const bool slab = cfg->rows != W;
+    if (!slab && (cfg->row0 != 0 || cfg->ghost_rows != 0))
+        return fail(PD_ERR_INVALID, "a whole world (rows == width) needs row0 = 0 and ghost_rows = 0");
+    if (slab) {
+        if (cfg->rows == 0 || cfg->rows % 16 || cfg->ghost_rows % 16 || cfg->ghost_rows < 64)
+            return fail(PD_ERR_INVALID, "slab: rows and ghost_rows must be multiples of 16 and ghost_rows >= 64 (got %u, %u)",
+                        cfg->rows, cfg->ghost_rows);
+        if (cfg->ghost_rows > cfg->rows || cfg->row0 + cfg->rows > W || W % cfg->rows)
+            return fail(PD_ERR_INVALID, "slab: need ghost_rows <= rows, rows | width and row0 + rows <= width");
+    }
     double wsum = 0;
     for (int i = 0; i < 4; ++i) {
         if (!(cfg->strategy_weights[i] >= 0.0f)) return fail(PD_ERR_INVALID, "strategy_weights must be >= 0");
@@ -197,9 +207,16 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     CK(cudaSetDevice(cfg->device));
     pd_sim* s = new pd_sim();
     s->cfg = *cfg;
-    s->cells = (size_t)cfg->rows * W;
+    const uint32_t Hl = cfg->rows + 2 * cfg->ghost_rows;  // local rows incl. the ghost zones
+    s->cells = (size_t)Hl * W;
+    s->slab = slab;
     Params& P = s->P;
-    P.W = W; P.H = cfg->rows; P.row0 = cfg->row0;
+    P.W = W; P.H = Hl;
+    P.row0 = (cfg->row0 + W - cfg->ghost_rows) & (W - 1);  // global row of local row 0
+    P.wrap_y = slab ? 0u : 1u;
+    P.own_y0 = cfg->ghost_rows; P.own_y1 = cfg->ghost_rows + cfg->rows;
+    P.round0 = 1; P.round1 = 8; P.world = 1; P.cand_cap = 0;
+    P.glb = nullptr; P.ghist = nullptr; P.cand_out = nullptr; P.cand_all = nullptr;
     P.log2W = 0;
     while ((1u << P.log2W) < W) ++P.log2W;
     P.k0 = (uint32_t)cfg->seed; P.k1 = (uint32_t)(cfg->seed >> 32);
@@ -230,7 +247,7 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     s->n_sms = prop.multiProcessorCount;
     s->big_tiles = W >= 128;
-    s->grid = s->big_tiles ? dim3(W / 128, cfg->rows / 16) : dim3(W / 16, cfg->rows / 16);
+    s->grid = s->big_tiles ? dim3(W / 128, Hl / 16) : dim3(W / 16, Hl / 16);
     if (cfg->sparse_ctas > 0) s->sparse_ctas = cfg->sparse_ctas;
     else s->sparse_ctas = s->cells <= ((size_t)1 << 22) ? 1 : 2 * s->n_sms;
     if (s->sparse_ctas > 1 && !prop.cooperativeLaunch) s->sparse_ctas = 1;
@@ -306,7 +323,8 @@ int pd_sync_state(pd_sim* s, void* stream) {
 
 int pd_init_population(pd_sim* s, uint64_t n_agents, void* stream) {
     if (!s || !s->bound) return fail(PD_ERR_STATE, "planes not bound");
-    if (n_agents > s->cells) return fail(PD_ERR_INVALID, "n_agents %llu > cells %zu", (unsigned long long)n_agents, s->cells);
+    const size_t world_cells = (size_t)s->cfg.width * s->cfg.width;
+    if (n_agents > world_cells) return fail(PD_ERR_INVALID, "n_agents %llu > cells %zu", (unsigned long long)n_agents, world_cells);
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(s->cfg.device));
     int rc = alloc_lists(s, n_agents);
@@ -315,12 +333,14 @@ int pd_init_population(pd_sim* s, uint64_t n_agents, void* stream) {
                                                                                   : (size_t)(s->n_sms * 16));
     unsigned long long tau = 0;
     const int none = n_agents == 0;
-    if (n_agents > 0 && n_agents < s->cells) {
+    const int gblocks = (int)((world_cells + NT - 1) / NT < (size_t)(s->n_sms * 16) ? (world_cells + NT - 1) / NT
+                                                                                      : (size_t)(s->n_sms * 16));
+    if (n_agents > 0 && n_agents < world_cells) {
         // n-th SMALLEST (priority, cell) key by an 8-pass radix select (model.py:1438-1450 restated)
         k_begin_step<<<1, 256, 0, st>>>(s->P.ctr, 0);
         unsigned long long prefix = 0, krem = n_agents;
         for (int pass = 0; pass < 8; ++pass) {
-            k_init_hist<<<blocks, NT, 0, st>>>(s->P, s->cells, pass, prefix);
+            k_init_hist<<<gblocks, NT, 0, st>>>(s->P, world_cells, pass, prefix);
             CK(cudaMemcpyAsync(s->h->hist, s->P.ctr->hist[pass], sizeof s->h->hist, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             unsigned long long cum = 0;
@@ -333,7 +353,7 @@ int pd_init_population(pd_sim* s, uint64_t n_agents, void* stream) {
             prefix = (prefix << 8) | (unsigned long long)digit;
         }
         tau = prefix;
-    } else if (n_agents == s->cells) {
+    } else if (n_agents == world_cells) {
         tau = ~0ull;
     }
     k_init_write<<<blocks, NT, 0, st>>>(s->P, s->cells, tau, none);
@@ -347,6 +367,7 @@ int pd_init_population(pd_sim* s, uint64_t n_agents, void* stream) {
 
 int pd_step(pd_sim* s, uint32_t n_steps, void* stream, int want_counts) {
     if (!s || !s->ready) return fail(PD_ERR_STATE, "pd_step before pd_init_population / pd_sync_state");
+    if (s->slab) return fail(PD_ERR_STATE, "a row slab is stepped with pd_step_part (the caller exchanges ghost rows and sums in between)");
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(s->cfg.device));
     for (uint32_t k = 0; k < n_steps; ++k) {
@@ -428,6 +449,82 @@ int pd_read_stats(pd_sim* s, pd_step_stats* o, void* stream) {
     o->agents_start = v[0]; o->agents_end = v[1]; o->play_deaths = v[2]; o->movers = v[3];
     o->moved = v[4]; o->travel_deaths = v[5]; o->births = v[6]; o->culled = v[7];
     o->living_deaths = v[8]; o->risk_list = v[9]; o->move_losers = v[10]; o->repro_losers = v[11];
+    return PD_OK;
+}
+
+int pd_bind_comm(pd_sim* s, uint64_t* glb, uint32_t* ghist, uint64_t* cand_out, const uint64_t* cand_all,
+                 uint32_t cand_cap, uint32_t world) {
+    if (!s || !glb || !ghist || !cand_out || !cand_all || !cand_cap || !world) return fail(PD_ERR_INVALID, "NULL argument");
+    if (!s->slab) return fail(PD_ERR_STATE, "pd_bind_comm is for row slabs (rows != width)");
+    s->P.glb = (unsigned long long*)glb;
+    s->P.ghist = ghist;
+    s->P.cand_out = (unsigned long long*)cand_out;
+    s->P.cand_all = (const unsigned long long*)cand_all;
+    s->P.cand_cap = cand_cap;
+    s->P.world = world;
+    s->comm_bound = true;
+    return PD_OK;
+}
+
+int pd_step_part(pd_sim* s, int part, int arg, void* stream, int want_counts) {
+    if (!s || !s->ready) return fail(PD_ERR_STATE, "pd_step_part before pd_init_population / pd_sync_state");
+    if (!s->slab || !s->comm_bound) return fail(PD_ERR_STATE, "pd_step_part needs a row slab with pd_bind_comm done");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(s->cfg.device));
+    Params& P = s->P;
+    P.step = s->step;
+    P.want_counts = want_counts ? 1u : 0u;
+    P.risk_cur = s->risk[s->risk_cur];
+    P.risk_next = s->risk[s->risk_cur ^ 1];
+    int rc = PD_OK;
+    switch (part) {
+    case PD_PART_PRE: {
+        // ghost rows were just refreshed by the caller: their at-risk agents join the list
+        const size_t ghost_cells = (size_t)2 * s->cfg.ghost_rows * P.W;
+        const int blocks = (int)((ghost_cells + 255) / 256 < (size_t)(s->n_sms * 8) ? (ghost_cells + 255) / 256 : (size_t)(s->n_sms * 8));
+        k_ghost_risk_scan<<<blocks, 256, 0, st>>>(P);
+        k_begin_step<<<1, 256, 0, st>>>(P.ctr, 1);
+        if ((rc = launch_sparse(s, k_risk_resolve, st))) return rc;
+        if (s->big_tiles) {
+            k_play_travel<128, 16><<<s->grid, NT, 0, st>>>(P);
+            k_move_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
+        } else {
+            k_play_travel<16, 16><<<s->grid, NT, 0, st>>>(P);
+            k_move_commit<16, 16><<<s->grid, NT, 0, st>>>(P);
+        }
+        if ((rc = launch_sparse(s, k_move_retry, st))) return rc;
+        if (s->big_tiles) {
+            k_repro_claim<128, 16><<<s->grid, NT, 0, st>>>(P);
+            k_repro_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
+        } else {
+            k_repro_claim<16, 16><<<s->grid, NT, 0, st>>>(P);
+            k_repro_commit<16, 16><<<s->grid, NT, 0, st>>>(P);
+        }
+        k_publish_gate<<<1, 32, 0, st>>>(P, 0);
+        break;
+    }
+    case PD_PART_RETRY:
+        if (arg < 1 || arg > 7) return fail(PD_ERR_INVALID, "retry round %d out of range 1..7", arg);
+        P.round0 = (uint32_t)arg; P.round1 = (uint32_t)arg + 1;
+        if ((rc = launch_sparse(s, k_repro_retry, st))) return rc;
+        k_publish_gate<<<1, 32, 0, st>>>(P, arg);
+        P.round0 = 1; P.round1 = 8;
+        break;
+    case PD_PART_HIST:
+        if ((rc = launch_sparse(s, k_fin_hist, st))) return rc;
+        break;
+    case PD_PART_CAND:
+        if ((rc = launch_sparse(s, k_fin_cand, st))) return rc;
+        break;
+    case PD_PART_APPLY:
+        if ((rc = launch_sparse(s, k_fin_apply, st))) return rc;
+        s->risk_cur ^= 1;
+        s->step += 1;
+        break;
+    default:
+        return fail(PD_ERR_INVALID, "unknown part %d", part);
+    }
+    CK(cudaGetLastError());
     return PD_OK;
 }
 

@@ -1,0 +1,198 @@
+"""One world row-decomposed over several GPUs (BASELINE config 5).
+
+The reference cannot do this at all (FLAMEGPU2 simulations are single-GPU and its bucket ids are
+32 bit, /root/reference/src/model.py:214, :338-339).  Here every rank owns a slab of rows plus a
+ghost zone of `ghost_rows` rows on each side.  Per step there is ONE halo exchange (the three state
+planes' boundary rows over NVLink) and a handful of tiny collectives for the two global decisions
+of the model -- the carrying-capacity gate of the reproduction rounds (exit_god_fn, :1607-1627) and
+the cull (:1339-1356):
+
+    exchange ghost rows -> PRE -> sum(glb) -> 7 x [RETRY r -> sum(glb)] -> HIST -> sum(ghist)
+        -> CAND -> gather(candidates) -> APPLY [-> sum(counts)]
+
+Everything else runs on the slab alone: the ghost zone (64 rows) is wider than the deepest
+dependency cone of one step (8 play sub-steps + 2 sweeps + 7 retry rounds of travel and of
+reproduction, <= 56 rows), so the owned rows come out bit-identical to a single-GPU run -- all
+random draws are keyed by the GLOBAL cell index.
+
+Two transports: `DistComm` (one slab per process/GPU, torch.distributed: NCCL on GPUs) and
+`LocalComm` (all slabs in one process on one GPU -- used by the tests to check decomposition
+invariance without a multi-GPU box).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import (PD_PART_PRE, PD_PART_RETRY, PD_PART_HIST, PD_PART_CAND, PD_PART_APPLY, PD_GLB_WORDS,
+                   PD_HIST_WORDS)
+from .sim import SimConfig, Simulation, PdabmError
+from .dist import slab_rows, ring_neighbours
+
+GHOST_ROWS = 64
+CAND_CAP = 1 << 16
+
+
+class _Slab:
+    """A Simulation handle for one slab plus its communication buffers."""
+
+    def __init__(self, cfg: SimConfig, rank: int, world: int, ghost_rows: int, cand_cap: int, stream=None):
+        import torch
+        row0, rows = slab_rows(cfg.width, rank, world)
+        if ghost_rows > rows:
+            raise PdabmError(f"ghost zone ({ghost_rows} rows) larger than the slab ({rows} rows): use fewer slabs")
+        self.rank, self.world = rank, world
+        self.sim = Simulation(cfg, stream=stream, slab=(row0, rows, ghost_rows))
+        dev = self.sim.device
+        self.glb = torch.zeros(PD_GLB_WORDS, dtype=torch.int64, device=dev)
+        self.ghist = torch.zeros(PD_HIST_WORDS, dtype=torch.int32, device=dev)
+        self.cand_out = torch.zeros(1 + cand_cap, dtype=torch.int64, device=dev)
+        self.cand_all = torch.zeros(world * (1 + cand_cap), dtype=torch.int64, device=dev)
+        self.sim._check(self.sim.lib.pd_bind_comm(self.sim._h, self.glb.data_ptr(), self.ghist.data_ptr(),
+                                                  self.cand_out.data_ptr(), self.cand_all.data_ptr(),
+                                                  cand_cap, world))
+
+    def part(self, part: int, arg: int = 0, want_counts: bool = False):
+        s = self.sim
+        s._check(s.lib.pd_step_part(s._h, part, arg, s.stream_ptr, int(want_counts)))
+
+    def planes3(self):
+        return (self.sim.energy, self.sim.strat, self.sim.tf)
+
+
+class LocalComm:
+    """All slabs in this process (one GPU): collectives are plain tensor ops."""
+
+    def __init__(self, world: int):
+        self.world = world
+        self.local_ranks = list(range(world))
+
+    def exchange(self, slabs: List[_Slab]):
+        g = slabs[0].sim.ghost_rows
+        r = slabs[0].sim.rows
+        for s in slabs:
+            up, down = ring_neighbours(s.rank, self.world)
+            for mine, theirs_up, theirs_down in zip(s.planes3(), slabs[up].planes3(), slabs[down].planes3()):
+                mine[0:g].copy_(theirs_up[r:r + g])              # upper neighbour's last owned rows
+                mine[g + r:g + r + g].copy_(theirs_down[g:2 * g])  # lower neighbour's first owned rows
+
+    def allreduce(self, tensors):
+        total = tensors[0].clone()
+        for t in tensors[1:]:
+            total += t
+        for t in tensors:
+            t.copy_(total)
+
+    def allgather(self, outs, ins):
+        import torch
+        cat = torch.cat(ins)
+        for o in outs:
+            o.copy_(cat)
+
+
+class DistComm:
+    """One slab per process: torch.distributed (NCCL over NVLink on GPUs, gloo on CPU in the tests)."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+        self.local_ranks = [self.rank]
+
+    def exchange(self, slabs: List[_Slab]):
+        dist = self.dist
+        s = slabs[0]
+        g, r = s.sim.ghost_rows, s.sim.rows
+        up, down = ring_neighbours(self.rank, self.world)
+        ops = []
+        for t in s.planes3():
+            ops.append(dist.P2POp(dist.isend, t[g:2 * g], up))              # my first owned rows -> upper slab's bottom ghosts
+            ops.append(dist.P2POp(dist.isend, t[r:r + g], down))            # my last owned rows  -> lower slab's top ghosts
+            ops.append(dist.P2POp(dist.irecv, t[0:g], up))
+            ops.append(dist.P2POp(dist.irecv, t[g + r:g + r + g], down))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def allreduce(self, tensors):
+        self.dist.all_reduce(tensors[0], op=self.dist.ReduceOp.SUM)
+
+    def allgather(self, outs, ins):
+        self.dist.all_gather_into_tensor(outs[0], ins[0])
+
+
+class DecomposedWorld:
+    """`world` row slabs of one width x width world.  Same surface as Simulation where it matters:
+    init_population(), step(), counts(), planes() (rank-local rows for DistComm, all rows for LocalComm)."""
+
+    def __init__(self, cfg: SimConfig, comm, ghost_rows: int = GHOST_ROWS, cand_cap: int = CAND_CAP,
+                 retry_rounds: int = 7, stream=None):
+        self.cfg, self.comm = cfg, comm
+        self.retry_rounds = retry_rounds
+        self.slabs = [_Slab(cfg, r, comm.world, ghost_rows, cand_cap, stream) for r in comm.local_ranks]
+        self._counts = None
+
+    def close(self):
+        for s in self.slabs:
+            s.sim.close()
+
+    def init_population(self, n_agents: Optional[int] = None):
+        for s in self.slabs:
+            s.sim.init_population(n_agents)
+        self._publish_local_counts()
+
+    def _publish_local_counts(self):
+        import torch
+        for s in self.slabs:
+            c, n = s.sim.counts()
+            s.glb[3:] = torch.tensor([n] + [int(v) for v in c], dtype=torch.int64, device=s.glb.device)
+        self.comm.allreduce([s.glb[3:] for s in self.slabs])
+
+    def set_state_from(self, planes: Dict[str, np.ndarray]):
+        """Upload a whole-world state (oracle-style planes) -- each slab takes its rows; test helper."""
+        for s in self.slabs:
+            sim = s.sim
+            g, r, r0 = sim.ghost_rows, sim.rows, sim.row0
+            W = self.cfg.width
+            rows = [(r0 - g + k) % W for k in range(r + 2 * g)]
+            sim.set_state(planes["occ"][rows], planes["energy"][rows], planes["trait"][rows], planes["strat"][rows])
+        self._publish_local_counts()
+
+    def step(self, n_steps: int = 1, want_counts: bool = True):
+        comm, slabs = self.comm, self.slabs
+        for k in range(n_steps):
+            wc = want_counts and k + 1 == n_steps
+            comm.exchange(slabs)
+            for s in slabs:
+                s.part(PD_PART_PRE, 0, wc)
+            comm.allreduce([s.glb for s in slabs])
+            for rnd in range(1, self.retry_rounds + 1):
+                for s in slabs:
+                    s.part(PD_PART_RETRY, rnd, wc)
+                comm.allreduce([s.glb for s in slabs])
+            for s in slabs:
+                s.part(PD_PART_HIST, 0, wc)
+            comm.allreduce([s.ghist for s in slabs])
+            for s in slabs:
+                s.part(PD_PART_CAND, 0, wc)
+            comm.allgather([s.cand_all for s in slabs], [s.cand_out for s in slabs])
+            for s in slabs:
+                s.part(PD_PART_APPLY, 0, wc)
+        comm.allreduce([s.glb[3:] for s in slabs])  # agents + 16 counts of the last step
+
+    def counts(self):
+        """Global (population_strat_count[16], agent count) after the last step()."""
+        v = self.slabs[0].glb.cpu().numpy()
+        for s in self.slabs:
+            s.sim.counts()  # raises on a list overflow in any slab
+        return v[4:20].astype(np.int64), int(v[3])
+
+    def planes(self) -> Dict[str, np.ndarray]:
+        """Owned rows of the local slabs, stacked in rank order."""
+        parts = [s.sim.planes() for s in self.slabs]
+        return {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
+
+    def agent_steps(self) -> int:
+        return sum(s.sim.agent_steps() for s in self.slabs)

@@ -58,12 +58,13 @@ class SimConfig:
         if self.max_agents < 0:
             self.max_agents = int(cells * 0.5)
 
-    def to_c(self) -> pd_config:
+    def to_c(self, row0: int = 0, rows: Optional[int] = None, ghost_rows: int = 0) -> pd_config:
         c = pd_config()
         c.struct_size = C.sizeof(pd_config)
         c.width = self.width
-        c.row0 = 0
-        c.rows = self.width
+        c.row0 = row0
+        c.rows = self.width if rows is None else rows
+        c.ghost_rows = ghost_rows
         c.seed = self.seed & 0xFFFFFFFFFFFFFFFF
         c.max_agents = self.max_agents
         for k in ("payoff_cc", "payoff_cd", "payoff_dc", "payoff_dd", "env_noise", "travel_cost",
@@ -97,7 +98,9 @@ class Simulation:
     """One world on one GPU.  ``energy``, ``strat`` and ``tf`` are torch CUDA tensors of
     shape [width, width] ([y, x]) that the library borrows (pd_bind_planes)."""
 
-    def __init__(self, config: SimConfig, stream=None):
+    def __init__(self, config: SimConfig, stream=None, slab=None):
+        """slab = (row0, rows, ghost_rows) makes this handle one row slab of the world (see decomp.py);
+        its planes then have rows + 2*ghost_rows rows."""
         import torch
         if not torch.cuda.is_available():
             raise PdabmError("CUDA device required: the agent pipeline has no CPU path")
@@ -106,14 +109,18 @@ class Simulation:
         self.torch = torch
         self.device = torch.device("cuda", config.device)
         W = config.width
+        self.slab = slab
+        row0, rows, ghost = (0, W, 0) if slab is None else slab
+        self.row0, self.rows, self.ghost_rows = row0, rows, ghost
+        H = rows + 2 * ghost
         with torch.cuda.device(self.device):
-            self.energy = torch.zeros((W, W), dtype=torch.float32, device=self.device)
-            self.strat = torch.zeros((W, W), dtype=torch.uint8, device=self.device)
-            self.tf = torch.zeros((W, W), dtype=torch.uint8, device=self.device)
+            self.energy = torch.zeros((H, W), dtype=torch.float32, device=self.device)
+            self.strat = torch.zeros((H, W), dtype=torch.uint8, device=self.device)
+            self.tf = torch.zeros((H, W), dtype=torch.uint8, device=self.device)
             torch.cuda.synchronize(self.device)
         self._stream = stream
         self._h = C.c_void_p()
-        ccfg = config.to_c()
+        ccfg = config.to_c(row0, rows, ghost)
         self._check(self.lib.pd_create(C.byref(ccfg), C.byref(self._h)))
         self._check(self.lib.pd_bind_planes(self._h, self.energy.data_ptr(), self.strat.data_ptr(),
                                             self.tf.data_ptr()))
@@ -199,13 +206,14 @@ class Simulation:
     def planes(self) -> Dict[str, np.ndarray]:
         """Download the world as NumPy planes (same keys as the oracle's ``planes()``)."""
         self.torch.cuda.synchronize(self.device)
-        tf = self.tf.cpu().numpy()
+        g, r = self.ghost_rows, self.rows
+        tf = self.tf[g:g + r].cpu().numpy()  # owned rows only
         occ = (tf & PD_TF_OCCUPIED) != 0
         return {
             "occ": occ.astype(np.uint8),
-            "energy": np.where(occ, self.energy.cpu().numpy(), np.float32(0)).astype(np.float32),
+            "energy": np.where(occ, self.energy[g:g + r].cpu().numpy(), np.float32(0)).astype(np.float32),
             "trait": np.where(occ, tf & PD_TF_TRAIT_MASK, 0).astype(np.uint8),
-            "strat": np.where(occ[..., None], unpack_strategies(self.strat.cpu().numpy()), 0).astype(np.uint8),
+            "strat": np.where(occ[..., None], unpack_strategies(self.strat[g:g + r].cpu().numpy()), 0).astype(np.uint8),
             "tf_raw": tf,
         }
 

@@ -74,7 +74,8 @@ typedef struct pd_config {
     uint8_t collect_stats;          /* 1: maintain the pd_step_stats counters        */
     int32_t device;                 /* CUDA device ordinal                           */
     int32_t sparse_ctas;            /* 0 = auto; CTAs of the persistent sparse kernels */
-    uint32_t reserved[4];
+    uint32_t ghost_rows;            /* row slab only: ghost rows above AND below (multiple of 16, >= 64) */
+    uint32_t reserved[3];
 } pd_config;
 
 /* Per-step event counters of the LAST executed step (debug / parity aid; the
@@ -121,6 +122,32 @@ int pd_step(pd_sim* sim, uint32_t n_steps, void* stream, int want_counts);
 int pd_read_counts(pd_sim* sim, uint64_t counts[16], uint64_t* n_agents, void* stream);
 
 int pd_read_stats(pd_sim* sim, pd_step_stats* out, void* stream);
+
+/* ---- One world in row slabs over several GPUs (one handle per slab) ---------------------------
+ * A slab owns rows [row0, row0 + rows) of the width x width world; its planes hold
+ * rows + 2*ghost_rows rows: ghost_rows rows of the upper neighbour slab, the owned rows, ghost_rows
+ * rows of the lower neighbour slab (periodic ring).  One model step is
+ *     caller: refresh the ghost rows of energy/strat/tf from the neighbour slabs (NVLink copy)
+ *     PD_PART_PRE            all dense sweeps + local retry rounds; publishes glb[0..2]
+ *     caller: sum glb over the slabs
+ *     PD_PART_RETRY r=1..7   one reproduction retry round, gated by the global population; caller sums glb
+ *     PD_PART_HIST           cull histogram into ghist;            caller sums ghist
+ *     PD_PART_CAND           this slab's cull candidates into cand_out;  caller gathers all blocks into cand_all
+ *     PD_PART_APPLY          cull, deferred living cost, bookkeeping; publishes glb[3..19] (agents, 16 counts)
+ * The ghost zone is wide enough that every other phase needs no communication (DESIGN.md "Multi-GPU");
+ * results are bit-identical to the whole-world run because all draws are keyed by the global cell. */
+#define PD_PART_PRE 0
+#define PD_PART_RETRY 1
+#define PD_PART_HIST 2
+#define PD_PART_CAND 3
+#define PD_PART_APPLY 4
+#define PD_GLB_WORDS 20
+#define PD_HIST_WORDS 2048
+/* glb: PD_GLB_WORDS u64; ghist: PD_HIST_WORDS u32; cand_out: 1 + cand_cap u64; cand_all: world * (1 + cand_cap) u64;
+ * all DEVICE buffers owned by the caller (torch tensors) so that it can run collectives on them. */
+int pd_bind_comm(pd_sim* sim, uint64_t* glb, uint32_t* ghist, uint64_t* cand_out, const uint64_t* cand_all,
+                 uint32_t cand_cap, uint32_t world);
+int pd_step_part(pd_sim* sim, int part, int arg, void* stream, int want_counts);
 
 /* Sum over all executed steps of the population at the START of the step (the numerator of
  * the agent-steps/s metric).  Synchronises `stream`. */
