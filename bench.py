@@ -8,8 +8,12 @@ A "step" is ONE model step (main layers 1-7, /root/reference/src/model.py:2140-2
 workload's world.  Default workload = BASELINE.json configs[2], the HBM-roofline config:
 16384 x 16384 cells (2^28), per-trait strategies, measured in the saturated steady state
 (P untimed pre-steps from init, then W warm-up steps, then K timed steps).  With --gpus N
-(torchrun) every rank advances its own world of that size (ensemble partitioning, no
-communication on the data path) -> weak scaling; value = all ranks' agent-steps / max time.
+(torchrun) the default is ONE world of 16384 x (16384*N) cells in N row slabs, one per GPU
+(2^28 cells per GPU -> weak scaling): one NVLink halo exchange of the state planes' boundary
+rows plus a handful of tiny collectives per step (decomp.py).  --partition ensemble instead
+gives every rank its own independent 2^28-cell world (no communication on the data path).
+value = all ranks' agent-steps / max time.  --workload config5 is BASELINE configs[4]
+(65536 x 65536 in 8 slabs of 8192 rows; needs --gpus 8).
 
 Keys of the JSON line beyond the base contract:
   roofline      dominant kernel (k_play_travel): algorithmic bytes per launch / mean device
@@ -33,6 +37,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+CONFIG5 = (65536, dict(strategy_per_trait=1),
+           "BASELINE configs[4]: 65536x65536 (2^32 cells) in row slabs, per-trait strategies, steady state")
 WORKLOADS = {
     # name: (width, SimConfig overrides, description)
     "config3": (16384, dict(strategy_per_trait=1),
@@ -175,16 +181,29 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from pdabm_b200 import Simulation, SimConfig
 
-    width, overrides, desc = WORKLOADS[args.workload]
+    from pdabm_b200 import DecomposedWorld, DistComm
+    width, overrides, desc = CONFIG5 if args.workload == "config5" else WORKLOADS[args.workload]
     if args.width:
         width = args.width
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    cfg = SimConfig(width=width, seed=12345 + rank, device=local_rank, **overrides)
-    sim = Simulation(cfg)
-    cells = width * width
-    want_counts = args.workload != "config3"  # config 3 logs first/last only
+    slabs = world > 1 and args.partition == "slabs"
+    if slabs:
+        # one world, one row slab per GPU; square for config5, else width x (width * N) so that every
+        # GPU owns the same 2^28 cells as the single-GPU run (weak scaling)
+        height = width if args.workload == "config5" else width * world
+        cfg = SimConfig(width=width, height=height, seed=12345, device=local_rank, **overrides)
+        sim = DecomposedWorld(cfg, DistComm())
+        one = sim.slabs[0].sim
+        cells = width * (height // world)              # owned cells per GPU
+        desc += f"; one {width}x{height} world in {world} row slabs"
+    else:
+        cfg = SimConfig(width=width, seed=12345 + rank, device=local_rank, **overrides)
+        sim = Simulation(cfg)
+        one = sim
+        cells = width * width
+    want_counts = args.workload not in ("config3", "config5")  # these log first/last only
 
     def barrier():
         torch.cuda.synchronize()
@@ -204,7 +223,7 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    sim.set_profile(True)
+    one.set_profile(True)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -214,32 +233,48 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
-    kernel_ms, prof_steps = sim.read_profile()
-    sim.set_profile(False)
+    kernel_ms, prof_steps = one.read_profile()   # rank 0's slab (all slabs do the same work)
+    one.set_profile(False)
     as1 = sim.agent_steps()
     counts, n_after = sim.counts()
     agent_steps = as1 - as0
 
     # ---- e2e: the host-buffer C-ABI call, state round trip through pinned host memory each step
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    h_e = torch.empty((width, width), dtype=torch.float32).pin_memory()
-    h_s = torch.empty((width, width), dtype=torch.uint8).pin_memory()
-    h_t = torch.empty((width, width), dtype=torch.uint8).pin_memory()
-    h_e.copy_(sim.energy)
-    h_s.copy_(sim.strat)
-    h_t.copy_(sim.tf)
+    rows_local = one.energy.shape[0]
+    h_e = torch.empty((rows_local, width), dtype=torch.float32).pin_memory()
+    h_s = torch.empty((rows_local, width), dtype=torch.uint8).pin_memory()
+    h_t = torch.empty((rows_local, width), dtype=torch.uint8).pin_memory()
+    h_e.copy_(one.energy)
+    h_s.copy_(one.strat)
+    h_t.copy_(one.tf)
     torch.cuda.synchronize()
-    sim.step_host(h_e, h_s, h_t, 1, h_e, h_s, h_t)  # warm-up of the host path
+
+    def host_step():
+        if slabs:  # same round trip, spelled out: upload the slab's planes, resync, step, download
+            one.energy.copy_(h_e, non_blocking=True)
+            one.strat.copy_(h_s, non_blocking=True)
+            one.tf.copy_(h_t, non_blocking=True)
+            one._check(one.lib.pd_sync_state(one._h, one.stream_ptr))
+            sim.step(1, want_counts=True)
+            h_e.copy_(one.energy, non_blocking=True)
+            h_s.copy_(one.strat, non_blocking=True)
+            h_t.copy_(one.tf, non_blocking=True)
+            sim.counts()
+        else:
+            sim.step_host(h_e, h_s, h_t, 1, h_e, h_s, h_t)
+
+    host_step()  # warm-up of the host path
     barrier()
     t0 = time.perf_counter()
     as_a = sim.agent_steps()
     for _ in range(e2e_steps):
-        sim.step_host(h_e, h_s, h_t, 1, h_e, h_s, h_t)
+        host_step()
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_agents = sim.agent_steps() - as_a
-    h2d = cells * 6
-    d2h = cells * 6 + 17 * 8
+    h2d = rows_local * width * 6
+    d2h = rows_local * width * 6 + 17 * 8
 
     # ---- reduce over ranks: total agent-steps, max time
     if world > 1:
@@ -252,6 +287,7 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         sim.close()
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
@@ -287,7 +323,9 @@ def run_ours(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": desc, "width": width, "cells": cells, "cells_per_gpu": cells,
-                   "partitioning": "one world per GPU (ensemble), no data-path collective" if world > 1 else "single world",
+                   "partitioning": ("row slabs of one world, one per GPU: NVLink halo exchange of 64 boundary rows x 3 planes "
+                                    "+ 11 small collectives per step" if slabs else
+                                    "one world per GPU (ensemble), no data-path collective" if world > 1 else "single world"),
                    "presteps": args.presteps, "agents_at_start": n_before, "agents_at_end": n_after,
                    "density": n_after / cells, "counts_every_step": want_counts,
                    "l2": "state (11 B/cell resident) larger than the 126 MB L2" if cells * 11 > 126e6
@@ -303,7 +341,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_agents / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                 "call": "pd_step_host (host planes in, host planes + counts out)"},
-        "gpu_launches": 9 * args.steps,
+        "gpu_launches": (28 if slabs else 9) * args.steps,
         "clocks": clocks,
         "init_and_presteps_s": init_s,
     }
@@ -317,6 +355,7 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     sim.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -326,7 +365,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS) + ["config5"])
+    ap.add_argument("--partition", default="slabs", choices=["slabs", "ensemble"],
+                    help="how N > 1 GPUs are used: row slabs of one world (default) or independent worlds")
     ap.add_argument("--width", type=int, default=0, help="override the workload's width (debug)")
     ap.add_argument("--presteps", type=int, default=80)
     ap.add_argument("--e2e-steps", type=int, default=10)

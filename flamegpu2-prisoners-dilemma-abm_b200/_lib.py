@@ -47,7 +47,8 @@ class pd_config(C.Structure):
         ("device", C.c_int32),
         ("sparse_ctas", C.c_int32),
         ("ghost_rows", C.c_uint32),
-        ("reserved", C.c_uint32 * 3),
+        ("world_height", C.c_uint32),
+        ("reserved", C.c_uint32 * 2),
     ]
 
 

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
         const int si = s_cells[k];
         const int r = si / SW, c = si - r * SW;
         const uint32_t gx = (x0 + (uint32_t)(c - 16)) & (p.W - 1);
-        const uint32_t gy = (p.row0 + y0 + (uint32_t)(r - 1)) & (p.W - 1);
+        const uint32_t gy = (p.row0 + y0 + (uint32_t)(r - 1)) & (p.HW - 1);
         const uint32_t roll = rng(p, ((uint64_t)gy << p.log2W) | gx, S_ROLL).x;
         const uint32_t t = s_tf[si];
         s_R[si] = R_OCC | ((roll >> 12) << 11) | ((t & TF_D) ? R_DFLAG : 0u) | ((t & TF_TRAIT) << 8) | (uint32_t)s_st[si];

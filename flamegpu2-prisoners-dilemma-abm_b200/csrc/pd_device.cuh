@@ -79,6 +79,7 @@ struct Counters {
 // ---- kernel parameter block (lives in the constant bank as a __grid_constant__ arg) ------
 struct Params {
     uint32_t W, H, row0, log2W;
+    uint32_t HW;  // height of the whole world (power of two; == W for the reference's square worlds)
     uint32_t k0, k1, step;
     float pay[4];  // index (i_coop << 1) | challenger_coop: {dd, dc, cd, cc} seen by the responder
     float max_energy, travel_cost, cost_of_living, reproduce_min_energy, reproduce_cost;
@@ -123,7 +124,7 @@ __device__ __forceinline__ Words rng_init(const Params& p, uint64_t gcell, uint3
 
 // global cell index (x + y*env_max, :339) of local cell (x, y) and of its neighbours
 __device__ __forceinline__ uint64_t gcell_of(const Params& p, uint32_t x, uint32_t y) {
-    return ((uint64_t)((p.row0 + y) & (p.W - 1)) << p.log2W) | x;
+    return ((uint64_t)((p.row0 + y) & (p.HW - 1)) << p.log2W) | x;
 }
 // local row of the neighbour row y + dy: wraps for a whole world (:311-312); a slab never wraps --
 // its outermost ghost rows are outside the zone whose results are used, so the index is just clamped
@@ -142,7 +143,7 @@ __device__ __forceinline__ bool row_owned(const Params& p, uint32_t y) {
 }
 __device__ __forceinline__ uint64_t nb_gcell(const Params& p, uint32_t x, uint32_t y, int d) {
     const uint32_t nx = (x + (uint32_t)DX(d)) & (p.W - 1);
-    const uint32_t gy = (p.row0 + y + (uint32_t)DY(d)) & (p.W - 1);
+    const uint32_t gy = (p.row0 + y + (uint32_t)DY(d)) & (p.HW - 1);
     return ((uint64_t)gy << p.log2W) | nx;
 }
 

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(1024) k_move_retry(const __grid_constant__ Par
             const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
             const int d = (int)(p.mv_aux[i] & 7u);
             const uint32_t tx = (x + (uint32_t)DX(d)) & (p.W - 1);
-            const uint32_t ty = (y + (uint32_t)DY(d)) & (p.H - 1);
+            const uint32_t ty = nb_row(p, y, DY(d));
             bool win = true, have_key = false;
             Key mine;
             for (int j = 0; j < 8; ++j) {
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(1024) k_repro_retry(const __grid_constant__ Pa
             const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
             const int d = (int)(p.rp_aux[i] & 7u);
             const uint32_t tx = (x + (uint32_t)DX(d)) & (p.W - 1);
-            const uint32_t ty = (y + (uint32_t)DY(d)) & (p.H - 1);
+            const uint32_t ty = nb_row(p, y, DY(d));
             bool win = true, have_key = false;
             Key mine;
             for (int j = 0; j < 8; ++j) {

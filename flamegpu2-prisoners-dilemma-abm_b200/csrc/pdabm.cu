@@ -79,8 +79,9 @@ struct pd_sim {
     bool lists_allocated;
     // optional per-kernel timing (pd_set_profile): events around every launch of a step
     bool profile;
-    std::vector<cudaEvent_t> ev;   // 10 events per profiled step, consumed by pd_read_profile
-    size_t ev_used;
+    std::vector<cudaEvent_t> ev;   // (start, end) event pairs, consumed by pd_read_profile
+    std::vector<int> ev_slot;      // kernel slot of pair k
+    size_t ev_used;                // events used (2 per pair)
     double kernel_ms[9];
     uint32_t prof_steps;
 };
@@ -97,7 +98,11 @@ int alloc_lists(pd_sim* s, uint64_t n_agents_hint) {
         cudaFree(s->P.nb_cell); cudaFree(s->P.nb_prio);
         s->lists_allocated = false;
     }
-    uint64_t cap = s->cfg.max_agents > n_agents_hint ? s->cfg.max_agents : n_agents_hint;
+    // this handle's share of the global cap (+25 % for density fluctuations between slabs; an overflow
+    // is detected and reported by pd_read_counts)
+    const double share = (double)s->cells / ((double)s->cfg.width * (double)s->P.HW);
+    uint64_t local_max = share >= 1.0 ? s->cfg.max_agents : (uint64_t)((double)s->cfg.max_agents * share * 1.25);
+    uint64_t cap = local_max > n_agents_hint ? local_max : n_agents_hint;
     cap += 1024;
     if (cap > s->cells) cap = s->cells;
     s->P.list_cap = (uint32_t)cap;
@@ -129,6 +134,32 @@ int launch_sparse(pd_sim* s, K kernel, cudaStream_t st) {
     }
     return PD_OK;
 }
+
+// per-kernel timing: a (start, end) CUDA event pair around one or more launches, tagged with a kernel slot
+int prof_begin(pd_sim* s, int slot, cudaStream_t st) {
+    if (!s->profile) return PD_OK;
+    while (s->ev_used + 2 > s->ev.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        s->ev.push_back(e);
+    }
+    if (s->ev_slot.size() < s->ev.size() / 2) s->ev_slot.resize(s->ev.size() / 2);
+    s->ev_slot[s->ev_used / 2] = slot;
+    CK(cudaEventRecord(s->ev[s->ev_used], st));
+    return PD_OK;
+}
+int prof_end(pd_sim* s, cudaStream_t st) {
+    if (!s->profile) return PD_OK;
+    CK(cudaEventRecord(s->ev[s->ev_used + 1], st));
+    s->ev_used += 2;
+    return PD_OK;
+}
+#define PROF(slot, ...)                                      \
+    do {                                                     \
+        if ((rc = prof_begin(s, slot, st))) return rc;       \
+        __VA_ARGS__;                                         \
+        if ((rc = prof_end(s, st))) return rc;               \
+    } while (0)
 
 int run_scan(pd_sim* s, cudaStream_t st) {
     s->P.risk_cur = s->risk[s->risk_cur];
@@ -185,15 +216,17 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     const uint32_t W = cfg->width;
     if (W < 16 || (W & (W - 1))) return fail(PD_ERR_INVALID, "width must be a power of two >= 16 (got %u)", W);
     if (W > 65536) return fail(PD_ERR_INVALID, "width > 65536 not supported");
-    const bool slab = cfg->rows != W;
+    const uint32_t HW = cfg->world_height ? cfg->world_height : W;  // non-square worlds: weak-scaling series
+    if (HW < 16 || (HW & (HW - 1)) || HW > (1u << 20)) return fail(PD_ERR_INVALID, "world_height must be a power of two in [16, 2^20]");
+    const bool slab = cfg->rows != HW;
     if (!slab && (cfg->row0 != 0 || cfg->ghost_rows != 0))
-        return fail(PD_ERR_INVALID, "a whole world (rows == width) needs row0 = 0 and ghost_rows = 0");
+        return fail(PD_ERR_INVALID, "a whole world (rows == world height) needs row0 = 0 and ghost_rows = 0");
     if (slab) {
         if (cfg->rows == 0 || cfg->rows % 16 || cfg->ghost_rows % 16 || cfg->ghost_rows < 64)
             return fail(PD_ERR_INVALID, "slab: rows and ghost_rows must be multiples of 16 and ghost_rows >= 64 (got %u, %u)",
                         cfg->rows, cfg->ghost_rows);
-        if (cfg->ghost_rows > cfg->rows || cfg->row0 + cfg->rows > W || W % cfg->rows)
-            return fail(PD_ERR_INVALID, "slab: need ghost_rows <= rows, rows | width and row0 + rows <= width");
+        if (cfg->ghost_rows > cfg->rows || cfg->row0 + cfg->rows > HW || HW % cfg->rows)
+            return fail(PD_ERR_INVALID, "slab: need ghost_rows <= rows, rows | world height and row0 + rows <= world height");
     }
     double wsum = 0;
     for (int i = 0; i < 4; ++i) {
@@ -211,8 +244,8 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     s->cells = (size_t)Hl * W;
     s->slab = slab;
     Params& P = s->P;
-    P.W = W; P.H = Hl;
-    P.row0 = (cfg->row0 + W - cfg->ghost_rows) & (W - 1);  // global row of local row 0
+    P.W = W; P.H = Hl; P.HW = HW;
+    P.row0 = (cfg->row0 + HW - cfg->ghost_rows) & (HW - 1);  // global row of local row 0
     P.wrap_y = slab ? 0u : 1u;
     P.own_y0 = cfg->ghost_rows; P.own_y1 = cfg->ghost_rows + cfg->rows;
     P.round0 = 1; P.round1 = 8; P.world = 1; P.cand_cap = 0;
@@ -323,7 +356,7 @@ int pd_sync_state(pd_sim* s, void* stream) {
 
 int pd_init_population(pd_sim* s, uint64_t n_agents, void* stream) {
     if (!s || !s->bound) return fail(PD_ERR_STATE, "planes not bound");
-    const size_t world_cells = (size_t)s->cfg.width * s->cfg.width;
+    const size_t world_cells = (size_t)s->cfg.width * s->P.HW;
     if (n_agents > world_cells) return fail(PD_ERR_INVALID, "n_agents %llu > cells %zu", (unsigned long long)n_agents, world_cells);
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(s->cfg.device));
@@ -377,41 +410,19 @@ int pd_step(pd_sim* s, uint32_t n_steps, void* stream, int want_counts) {
         P.risk_cur = s->risk[s->risk_cur];
         P.risk_next = s->risk[s->risk_cur ^ 1];
         int rc = PD_OK;
-        int mark = 0;
-        auto tick = [&]() -> int {  // event between two launches when profiling
-            if (!s->profile) return PD_OK;
-            if (s->ev_used >= s->ev.size()) {
-                cudaEvent_t e;
-                CK(cudaEventCreate(&e));
-                s->ev.push_back(e);
-            }
-            CK(cudaEventRecord(s->ev[s->ev_used++], st));
-            ++mark;
-            return PD_OK;
-        };
-        if ((rc = tick())) return rc;
-        k_begin_step<<<1, 256, 0, st>>>(P.ctr, 1);
-        if ((rc = tick())) return rc;
-        if ((rc = launch_sparse(s, k_risk_resolve, st))) return rc;
-        if ((rc = tick())) return rc;
-        if (s->big_tiles) k_play_travel<128, 16><<<s->grid, NT, 0, st>>>(P);
-        else k_play_travel<16, 16><<<s->grid, NT, 0, st>>>(P);
-        if ((rc = tick())) return rc;
-        if (s->big_tiles) k_move_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
-        else k_move_commit<16, 16><<<s->grid, NT, 0, st>>>(P);
-        if ((rc = tick())) return rc;
-        if ((rc = launch_sparse(s, k_move_retry, st))) return rc;
-        if ((rc = tick())) return rc;
-        if (s->big_tiles) k_repro_claim<128, 16><<<s->grid, NT, 0, st>>>(P);
-        else k_repro_claim<16, 16><<<s->grid, NT, 0, st>>>(P);
-        if ((rc = tick())) return rc;
-        if (s->big_tiles) k_repro_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
-        else k_repro_commit<16, 16><<<s->grid, NT, 0, st>>>(P);
-        if ((rc = tick())) return rc;
-        if ((rc = launch_sparse(s, k_repro_retry, st))) return rc;
-        if ((rc = tick())) return rc;
-        if ((rc = launch_sparse(s, k_finalize, st))) return rc;
-        if ((rc = tick())) return rc;
+        PROF(0, (k_begin_step<<<1, 256, 0, st>>>(P.ctr, 1)));
+        PROF(1, { if ((rc = launch_sparse(s, k_risk_resolve, st))) return rc; });
+        PROF(2, { if (s->big_tiles) k_play_travel<128, 16><<<s->grid, NT, 0, st>>>(P);
+                  else k_play_travel<16, 16><<<s->grid, NT, 0, st>>>(P); });
+        PROF(3, { if (s->big_tiles) k_move_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
+                  else k_move_commit<16, 16><<<s->grid, NT, 0, st>>>(P); });
+        PROF(4, { if ((rc = launch_sparse(s, k_move_retry, st))) return rc; });
+        PROF(5, { if (s->big_tiles) k_repro_claim<128, 16><<<s->grid, NT, 0, st>>>(P);
+                  else k_repro_claim<16, 16><<<s->grid, NT, 0, st>>>(P); });
+        PROF(6, { if (s->big_tiles) k_repro_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
+                  else k_repro_commit<16, 16><<<s->grid, NT, 0, st>>>(P); });
+        PROF(7, { if ((rc = launch_sparse(s, k_repro_retry, st))) return rc; });
+        PROF(8, { if ((rc = launch_sparse(s, k_finalize, st))) return rc; });
         s->risk_cur ^= 1;
         s->step += 1;
     }
@@ -482,42 +493,35 @@ int pd_step_part(pd_sim* s, int part, int arg, void* stream, int want_counts) {
         // ghost rows were just refreshed by the caller: their at-risk agents join the list
         const size_t ghost_cells = (size_t)2 * s->cfg.ghost_rows * P.W;
         const int blocks = (int)((ghost_cells + 255) / 256 < (size_t)(s->n_sms * 8) ? (ghost_cells + 255) / 256 : (size_t)(s->n_sms * 8));
-        k_ghost_risk_scan<<<blocks, 256, 0, st>>>(P);
-        k_begin_step<<<1, 256, 0, st>>>(P.ctr, 1);
-        if ((rc = launch_sparse(s, k_risk_resolve, st))) return rc;
-        if (s->big_tiles) {
-            k_play_travel<128, 16><<<s->grid, NT, 0, st>>>(P);
-            k_move_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
-        } else {
-            k_play_travel<16, 16><<<s->grid, NT, 0, st>>>(P);
-            k_move_commit<16, 16><<<s->grid, NT, 0, st>>>(P);
-        }
-        if ((rc = launch_sparse(s, k_move_retry, st))) return rc;
-        if (s->big_tiles) {
-            k_repro_claim<128, 16><<<s->grid, NT, 0, st>>>(P);
-            k_repro_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
-        } else {
-            k_repro_claim<16, 16><<<s->grid, NT, 0, st>>>(P);
-            k_repro_commit<16, 16><<<s->grid, NT, 0, st>>>(P);
-        }
+        PROF(0, { k_ghost_risk_scan<<<blocks, 256, 0, st>>>(P); k_begin_step<<<1, 256, 0, st>>>(P.ctr, 1); });
+        PROF(1, { if ((rc = launch_sparse(s, k_risk_resolve, st))) return rc; });
+        PROF(2, { if (s->big_tiles) k_play_travel<128, 16><<<s->grid, NT, 0, st>>>(P);
+                  else k_play_travel<16, 16><<<s->grid, NT, 0, st>>>(P); });
+        PROF(3, { if (s->big_tiles) k_move_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
+                  else k_move_commit<16, 16><<<s->grid, NT, 0, st>>>(P); });
+        PROF(4, { if ((rc = launch_sparse(s, k_move_retry, st))) return rc; });
+        PROF(5, { if (s->big_tiles) k_repro_claim<128, 16><<<s->grid, NT, 0, st>>>(P);
+                  else k_repro_claim<16, 16><<<s->grid, NT, 0, st>>>(P); });
+        PROF(6, { if (s->big_tiles) k_repro_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
+                  else k_repro_commit<16, 16><<<s->grid, NT, 0, st>>>(P); });
         k_publish_gate<<<1, 32, 0, st>>>(P, 0);
         break;
     }
     case PD_PART_RETRY:
         if (arg < 1 || arg > 7) return fail(PD_ERR_INVALID, "retry round %d out of range 1..7", arg);
         P.round0 = (uint32_t)arg; P.round1 = (uint32_t)arg + 1;
-        if ((rc = launch_sparse(s, k_repro_retry, st))) return rc;
+        PROF(7, { if ((rc = launch_sparse(s, k_repro_retry, st))) return rc; });
         k_publish_gate<<<1, 32, 0, st>>>(P, arg);
         P.round0 = 1; P.round1 = 8;
         break;
     case PD_PART_HIST:
-        if ((rc = launch_sparse(s, k_fin_hist, st))) return rc;
+        PROF(8, { if ((rc = launch_sparse(s, k_fin_hist, st))) return rc; });
         break;
     case PD_PART_CAND:
-        if ((rc = launch_sparse(s, k_fin_cand, st))) return rc;
+        PROF(8, { if ((rc = launch_sparse(s, k_fin_cand, st))) return rc; });
         break;
     case PD_PART_APPLY:
-        if ((rc = launch_sparse(s, k_fin_apply, st))) return rc;
+        PROF(8, { if ((rc = launch_sparse(s, k_fin_apply, st))) return rc; });
         s->risk_cur ^= 1;
         s->step += 1;
         break;
@@ -541,13 +545,11 @@ int pd_read_profile(pd_sim* s, double kernel_ms[9], uint32_t* steps, void* strea
     if (!s || !kernel_ms) return fail(PD_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
-    for (size_t b = 0; b + 10 <= s->ev_used; b += 10) {
-        for (int i = 0; i < 9; ++i) {
-            float ms = 0.f;
-            CK(cudaEventElapsedTime(&ms, s->ev[b + i], s->ev[b + i + 1]));
-            s->kernel_ms[i] += (double)ms;
-        }
-        s->prof_steps += 1;
+    for (size_t k = 0; 2 * k + 1 < s->ev_used; ++k) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s->ev[2 * k], s->ev[2 * k + 1]));
+        s->kernel_ms[s->ev_slot[k]] += (double)ms;
+        if (s->ev_slot[k] == 2) s->prof_steps += 1;  // one play sweep per step
     }
     s->ev_used = 0;
     for (int i = 0; i < 9; ++i) kernel_ms[i] = s->kernel_ms[i];

@@ -40,7 +40,7 @@ class _Slab:
 
     def __init__(self, cfg: SimConfig, rank: int, world: int, ghost_rows: int, cand_cap: int, stream=None):
         import torch
-        row0, rows = slab_rows(cfg.width, rank, world)
+        row0, rows = slab_rows(cfg.height, rank, world)
         if ghost_rows > rows:
             raise PdabmError(f"ghost zone ({ghost_rows} rows) larger than the slab ({rows} rows): use fewer slabs")
         self.rank, self.world = rank, world
@@ -109,10 +109,12 @@ class DistComm:
         up, down = ring_neighbours(self.rank, self.world)
         ops = []
         for t in s.planes3():
+            # Per peer the messages match in FIFO order, and with 2 slabs `up` and `down` are the same peer:
+            # it sends (its first rows, its last rows), so I must receive (bottom ghosts, top ghosts) in that order.
             ops.append(dist.P2POp(dist.isend, t[g:2 * g], up))              # my first owned rows -> upper slab's bottom ghosts
             ops.append(dist.P2POp(dist.isend, t[r:r + g], down))            # my last owned rows  -> lower slab's top ghosts
-            ops.append(dist.P2POp(dist.irecv, t[0:g], up))
-            ops.append(dist.P2POp(dist.irecv, t[g + r:g + r + g], down))
+            ops.append(dist.P2POp(dist.irecv, t[g + r:g + r + g], down))    # lower slab's first owned rows
+            ops.append(dist.P2POp(dist.irecv, t[0:g], up))                  # upper slab's last owned rows
         for req in dist.batch_isend_irecv(ops):
             req.wait()
 
@@ -155,8 +157,8 @@ class DecomposedWorld:
         for s in self.slabs:
             sim = s.sim
             g, r, r0 = sim.ghost_rows, sim.rows, sim.row0
-            W = self.cfg.width
-            rows = [(r0 - g + k) % W for k in range(r + 2 * g)]
+            HW = self.cfg.height
+            rows = [(r0 - g + k) % HW for k in range(r + 2 * g)]
             sim.set_state(planes["occ"][rows], planes["energy"][rows], planes["trait"][rows], planes["strat"][rows])
         self._publish_local_counts()
 

@@ -25,6 +25,7 @@ class SimConfig:
     """The reference's tunables under their environment-property names
     (model.py:1678-1743; module constants model.py:39-169)."""
     width: int = 512                       # ENV_MAX (:211)
+    height: int = -1                       # world height; -1 = width (the reference's worlds are square)
     seed: int = 12345                      # RANDOM_SEED (:39)
     init_agent_count: int = -1             # INIT_AGENT_COUNT (:45); -1 = int(cells * 0.16)
     max_agents: int = -1                   # AGENT_HARD_LIMIT (:49); -1 = int(cells * 0.5)
@@ -52,7 +53,9 @@ class SimConfig:
     sparse_ctas: int = 0
 
     def __post_init__(self):
-        cells = self.width * self.width
+        if self.height < 0:
+            self.height = self.width
+        cells = self.width * self.height
         if self.init_agent_count < 0:
             self.init_agent_count = int(cells * 0.16)
         if self.max_agents < 0:
@@ -63,8 +66,9 @@ class SimConfig:
         c.struct_size = C.sizeof(pd_config)
         c.width = self.width
         c.row0 = row0
-        c.rows = self.width if rows is None else rows
+        c.rows = self.height if rows is None else rows
         c.ghost_rows = ghost_rows
+        c.world_height = 0 if self.height == self.width else self.height
         c.seed = self.seed & 0xFFFFFFFFFFFFFFFF
         c.max_agents = self.max_agents
         for k in ("payoff_cc", "payoff_cd", "payoff_dc", "payoff_dd", "env_noise", "travel_cost",
@@ -110,7 +114,7 @@ class Simulation:
         self.device = torch.device("cuda", config.device)
         W = config.width
         self.slab = slab
-        row0, rows, ghost = (0, W, 0) if slab is None else slab
+        row0, rows, ghost = (0, config.height, 0) if slab is None else slab
         self.row0, self.rows, self.ghost_rows = row0, rows, ghost
         H = rows + 2 * ghost
         with torch.cuda.device(self.device):

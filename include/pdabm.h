@@ -75,7 +75,9 @@ typedef struct pd_config {
     int32_t device;                 /* CUDA device ordinal                           */
     int32_t sparse_ctas;            /* 0 = auto; CTAs of the persistent sparse kernels */
     uint32_t ghost_rows;            /* row slab only: ghost rows above AND below (multiple of 16, >= 64) */
-    uint32_t reserved[3];
+    uint32_t world_height;          /* 0 = width (square, like the reference); else a power of two: the world is
+                                       width x world_height cells (used for weak-scaling series of row slabs) */
+    uint32_t reserved[2];
 } pd_config;
 
 /* Per-step event counters of the LAST executed step (debug / parity aid; the

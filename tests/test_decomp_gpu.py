@@ -52,3 +52,28 @@ def test_slabs_equal_whole_world(name, world):
     finally:
         ref.close()
         dec.close()
+
+
+def test_non_square_world_slabs():
+    """width x (2*width) world (used by the weak-scaling bench): whole handle vs 2 and 4 slabs."""
+    from pdabm_b200 import Simulation, SimConfig, DecomposedWorld, LocalComm
+    kw = dict(width=128, height=512, seed=8, strategy_per_trait=1, env_noise=0.05, mutation_rate=0.01)
+    ref = Simulation(SimConfig(**kw))
+    decs = [DecomposedWorld(SimConfig(**kw), LocalComm(w)) for w in (2, 4)]
+    try:
+        ref.init_population()
+        for d in decs:
+            d.init_population()
+        for s in range(70):
+            ref.step(1)
+            a = ref.planes()
+            for d in decs:
+                d.step(1)
+                b = d.planes()
+                for k in ("occ", "trait", "strat", "energy"):
+                    assert np.array_equal(a[k], b[k]), f"step {s}: plane {k} differs ({d.comm.world} slabs)"
+                assert ref.counts()[1] == d.counts()[1]
+    finally:
+        ref.close()
+        for d in decs:
+            d.close()

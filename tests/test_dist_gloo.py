@@ -63,3 +63,65 @@ def test_shard_and_slab_single_process():
     with pytest.raises(ValueError):
         pdist.slab_rows(100, 0, 3)
     assert pdist.reduce_throughput(5.0, 2.0) == (5.0, 2.0)
+
+
+class _FakeSim:
+    def __init__(self, rank, rows, ghost, width):
+        self.rows, self.ghost_rows = rows, ghost
+        h = rows + 2 * ghost
+        base = torch.arange(h * width, dtype=torch.float32).reshape(h, width)
+        self.energy = base + 1000.0 * rank
+        self.strat = torch.full((h, width), 10 + rank, dtype=torch.uint8)
+        self.tf = torch.full((h, width), 20 + rank, dtype=torch.uint8)
+
+
+class _FakeSlab:
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+        self.sim = _FakeSim(rank, rows=8, ghost=4, width=16)
+
+    def planes3(self):
+        return (self.sim.energy, self.sim.strat, self.sim.tf)
+
+
+def _comm_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pdabm_b200.decomp import DistComm
+        comm = DistComm()
+        slab = _FakeSlab(rank, world)
+        own_before = slab.sim.energy[4:12].clone()
+        comm.exchange([slab])
+        up, down = (rank - 1) % world, (rank + 1) % world
+        h, w = 16, 16
+        base = torch.arange(h * w, dtype=torch.float32).reshape(h, w)
+        ok = torch.equal(slab.sim.energy[0:4], (base + 1000.0 * up)[8:12])       # upper slab's last owned rows
+        ok &= torch.equal(slab.sim.energy[12:16], (base + 1000.0 * down)[4:8])   # lower slab's first owned rows
+        ok &= torch.equal(slab.sim.energy[4:12], own_before)                      # owned rows untouched
+        ok &= bool((slab.sim.strat[0:4] == 10 + up).all() and (slab.sim.tf[12:16] == 20 + down).all())
+        g = torch.tensor([rank + 1, 10 * (rank + 1)], dtype=torch.int64)
+        comm.allreduce([g])
+        ok &= g.tolist() == [sum(range(1, world + 1)), 10 * sum(range(1, world + 1))]
+        out = torch.zeros(world * 3, dtype=torch.int64)
+        comm.allgather([out], [torch.tensor([rank, rank, rank], dtype=torch.int64)])
+        ok &= out.tolist() == [r for r in range(world) for _ in range(3)]
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distcomm_transport_gloo(world):
+    """Halo exchange, sum and gather of the decomposed world's transport on CPU tensors (gloo)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_comm_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res
