@@ -165,7 +165,7 @@ __device__ __forceinline__ void game_strategies(uint32_t rme, uint32_t rn, uint3
 }
 
 template <int TW, int TH>
-__global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ Params p) {
     constexpr int SW = TW + 32, SH = TH + 2, NC = TW * TH, NWARP = NT / 32;
     constexpr int LOG_TW = TW == 128 ? 7 : 4;
     static_assert(TW == 128 || TW == 16, "tile width");
@@ -247,23 +247,18 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
         const int cl = (ly << LOG_TW) | lx;
         const uint32_t rme = valid ? s_R[si] : 0xFFFFFFFFu;
         const uint32_t kme = rme >> 11;
-        uint32_t occ_mask = 0, gm = 0, rngm = 0, outc = 0, special = 0;
+        // ---- who is around me, and who challenges me (bit c of gm: my neighbour 7-c does, in sub-step c, :477)
+        uint32_t occ_mask = 0, gm = 0, special = 0;
 #pragma unroll
         for (int d = 0; d < 8; ++d) {
-            const int c = 7 - d;  // neighbour d would challenge me in sub-step c (:477)
             const uint32_t rn = s_R[si + DY(d) * SW + DX(d)];
             const uint32_t kn = rn >> 11;
             occ_mask |= (rn >> 31) << d;
             const uint32_t hi = kn > kme ? 1u : 0u;
+            gm |= hi << (7 - d);
             special |= ((kn == kme ? 1u : 0u) | (hi & (rn >> 10))) << d;  // truncated-roll tie, or challenger with a D code
-            uint32_t mine, theirs;
-            game_strategies(rme, rn, mine, theirs);
-            const uint32_t need = (noisy || mine == 3u || theirs == 3u) ? hi : 0u;
-            gm |= hi << c;
-            rngm |= need << c;
-            outc |= (hi & (need ^ 1u)) * ((((mine != 1u) ? 2u : 0u) | ((theirs != 1u) ? 1u : 0u)) << (2 * c));
         }
-        if (!valid) { occ_mask = 0; gm = 0; rngm = 0; special = 0; }
+        if (!valid) { occ_mask = 0; gm = 0; special = 0; }
         // act[7] / act[0] of the terminal rule come from the roll order alone (get_game_list, :413):
         // a challenger that dies early still "would have challenged"
         uint32_t roles = gm;
@@ -279,19 +274,13 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
                 roles = (roles & ~(1u << c)) | ((uint32_t)hi << c);
                 if (hi) {
                     const uint32_t dn = ((uint32_t)s_tf[sn] & TF_D) >> TF_D_SHIFT;
-                    if (dn != 0u && (int)dn - 1 < c) hi = false;  // that challenger dies before sub-step c
+                    if (dn != 0u && (int)dn - 1 < c) hi = false;  // that challenger dies before sub-step c: no message
                 }
-                uint32_t mine, theirs;
-                game_strategies(rme, rn, mine, theirs);
-                const bool need = hi && (noisy || mine == 3u || theirs == 3u);
                 gm = (gm & ~(1u << c)) | ((uint32_t)hi << c);
-                rngm = (rngm & ~(1u << c)) | ((uint32_t)need << c);
-                outc &= ~(3u << (2 * c));
-                if (hi && !need) outc |= (((mine != 1u) ? 2u : 0u) | ((theirs != 1u) ? 1u : 0u)) << (2 * c);
             }
         }
-        // ---- queue the games that need random words
-        const int cnt = __popc(rngm);
+        // ---- queue my games warp-wide, in sub-step order
+        const int cnt = __popc(gm);
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -300,44 +289,35 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
         }
         const int off = incl - cnt;
         const int total = __shfl_sync(FULL, incl, 31);
-        if (total) {
-            {
-                uint32_t m = rngm;
-                int k = off;
-                while (m) {
-                    const int c = __ffs(m) - 1;
-                    m &= m - 1;
-                    s_q[warp][k++] = (uint16_t)((lane << 3) | c);
-                }
-            }
-            __syncwarp();
-            const uint32_t pack = (uint32_t)si | ((uint32_t)cl << 16);
-            for (int q0 = 0; q0 < total; q0 += 32) {
-                const int q = q0 + lane;
-                const bool active = q < total;
-                const uint32_t ent = active ? s_q[warp][q] : 0u;
-                const int c = (int)(ent & 7u), d = 7 - c;
-                const uint32_t pk = __shfl_sync(FULL, pack, (int)(ent >> 3));
-                if (active) {
-                    const int si_l = (int)(pk & 0xFFFFu), cl_l = (int)(pk >> 16);
-                    uint32_t mine, theirs;
-                    game_strategies(s_R[si_l], s_R[si_l + c_dir_dy[d] * SW + c_dir_dx[d]], mine, theirs);
-                    const uint64_t gl = gcell_of(p, x0 + (uint32_t)(cl_l & (TW - 1)), y0 + (uint32_t)(cl_l >> LOG_TW));
-                    s_qo[warp][q] = (uint8_t)game_outcome_rng(p, gl, c, mine, theirs);
-                }
-            }
-            __syncwarp();
-            {
-                uint32_t m = rngm;
-                int k = off;
-                while (m) {
-                    const int c = __ffs(m) - 1;
-                    m &= m - 1;
-                    outc |= (uint32_t)s_qo[warp][k++] << (2 * c);
-                }
-            }
-            __syncwarp();
+        {
+            int k = off;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if ((gm >> c) & 1u) s_q[warp][k++] = (uint16_t)((lane << 3) | c);
         }
+        __syncwarp();
+        // ---- evaluate them 32 at a time (play_response, :599-689)
+        const uint32_t pack = (uint32_t)si | ((uint32_t)cl << 16);
+        for (int q0 = 0; q0 < total; q0 += 32) {
+            const int q = q0 + lane;
+            const bool active = q < total;
+            const uint32_t ent = active ? s_q[warp][q] : 0u;
+            const int c = (int)(ent & 7u), d = 7 - c;
+            const uint32_t pk = __shfl_sync(FULL, pack, (int)(ent >> 3));
+            if (active) {
+                const int si_l = (int)(pk & 0xFFFFu);
+                uint32_t mine, theirs;
+                game_strategies(s_R[si_l], s_R[si_l + c_dir_dy[d] * SW + c_dir_dx[d]], mine, theirs);
+                uint32_t o = ((mine != 1u) ? 2u : 0u) | ((theirs != 1u) ? 1u : 0u);
+                if (noisy || mine == 3u || theirs == 3u) {
+                    const int cl_l = (int)(pk >> 16);
+                    const uint64_t gl = gcell_of(p, x0 + (uint32_t)(cl_l & (TW - 1)), y0 + (uint32_t)(cl_l >> LOG_TW));
+                    o = game_outcome_rng(p, gl, c, mine, theirs);
+                }
+                s_qo[warp][q] = (uint8_t)o;
+            }
+        }
+        __syncwarp();
         // ---- my games in sub-step order (:677-710), terminal rule, travel decision
         bool mover = false;
         if (valid) {
@@ -347,7 +327,8 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 if (!((gm >> c) & 1u) || dead) continue;
-                e = __fadd_rn(e, p.pay[(outc >> (2 * c)) & 3u]);   // :679-688
+                const uint32_t o = s_qo[warp][off + __popc(gm & ((1u << c) - 1u))];
+                e = __fadd_rn(e, p.pay[o & 3u]);                   // :679-688
                 if (e <= 0.0f) dead = true;                        // :695-697
                 else { e = fminf(e, p.max_energy); ++games; }      // :698-710
             }
@@ -368,6 +349,7 @@ __global__ void __launch_bounds__(NT) k_play_travel(const __grid_constant__ Para
         }
         const uint32_t slot = wappend(&s_n[2], mover);
         if (mover) { s_mover[slot] = (uint16_t)cl; ++n_movers; }
+        __syncwarp();
     }
     __syncthreads();
     // ---- movers: travel cost, death, random start, probe, claim (:794-868)

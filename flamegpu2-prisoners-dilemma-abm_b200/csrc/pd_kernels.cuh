@@ -314,11 +314,17 @@ __device__ __forceinline__ void fin_hist(const Params& p, unsigned int nb, unsig
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     for (unsigned int i = threadIdx.x; i < 2048; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    for (unsigned int i = t0; i < nb; i += stride) {
-        const uint32_t cell = p.nb_cell[i];
-        const uint32_t prio = rng(p, gcell_of(p, cell & (p.W - 1), cell >> p.log2W), S_CULL).x;
-        p.nb_prio[i] = prio;
-        atomicAdd(&s_hist[prio >> 21], 1u);
+    for (unsigned int i = t0; i < nb; i += 4 * stride) {  // 4 independent loads in flight per thread
+        uint32_t cell[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cell[u] = (i + u * stride < nb) ? p.nb_cell[i + u * stride] : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i + u * stride >= nb) continue;
+            const uint32_t prio = rng(p, gcell_of(p, cell[u] & (p.W - 1), cell[u] >> p.log2W), S_CULL).x;
+            p.nb_prio[i + u * stride] = prio;
+            atomicAdd(&s_hist[prio >> 21], 1u);
+        }
     }
     __syncthreads();
     for (unsigned int i = threadIdx.x; i < 2048; i += blockDim.x)

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -71,6 +72,8 @@ struct pd_sim {
     uint32_t* risk[2];
     int n_sms;
     int sparse_ctas, sparse_threads;
+    bool sparse_auto;                       // CTA count per kernel from its occupancy
+    std::map<const void*, int> sparse_occ;  // kernel -> CTAs of its cooperative launch
     bool big_tiles;
     bool slab;        // row slab of a larger world (ghost rows, pd_step_part)
     bool comm_bound;
@@ -123,14 +126,28 @@ int alloc_lists(pd_sim* s, uint64_t n_agents_hint) {
     return PD_OK;
 }
 
+// Persistent sparse kernels: 1 CTA for small worlds; otherwise a cooperative launch that fills every SM
+// with as many 512-thread CTAs as the kernel's registers allow (these kernels are latency-bound list
+// walks, so more resident warps = more loads in flight).
 template <typename K>
 int launch_sparse(pd_sim* s, K kernel, cudaStream_t st) {
     void* args[] = {(void*)&s->P};
     if (s->sparse_ctas == 1) {
         CK(cudaLaunchKernel((const void*)kernel, dim3(1), dim3(s->sparse_threads), args, 0, st));
     } else {
-        CK(cudaLaunchCooperativeKernel((const void*)kernel, dim3(s->sparse_ctas), dim3(s->sparse_threads),
-                                       args, 0, st));
+        int ctas = s->sparse_ctas;
+        if (s->sparse_auto) {
+            auto it = s->sparse_occ.find((const void*)kernel);
+            if (it == s->sparse_occ.end()) {
+                int occ = 1;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, s->sparse_threads, 0));
+                if (occ < 1) occ = 1;
+                if (occ > 4) occ = 4;
+                it = s->sparse_occ.emplace((const void*)kernel, occ * s->n_sms).first;
+            }
+            ctas = it->second;
+        }
+        CK(cudaLaunchCooperativeKernel((const void*)kernel, dim3(ctas), dim3(s->sparse_threads), args, 0, st));
     }
     return PD_OK;
 }
@@ -281,11 +298,12 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     s->n_sms = prop.multiProcessorCount;
     s->big_tiles = W >= 128;
     s->grid = s->big_tiles ? dim3(W / 128, Hl / 16) : dim3(W / 16, Hl / 16);
+    s->sparse_auto = cfg->sparse_ctas <= 0;
     if (cfg->sparse_ctas > 0) s->sparse_ctas = cfg->sparse_ctas;
-    else s->sparse_ctas = s->cells <= ((size_t)1 << 22) ? 1 : 2 * s->n_sms;
+    else s->sparse_ctas = s->cells <= ((size_t)1 << 22) ? 1 : s->n_sms;
     if (s->sparse_ctas > 1 && !prop.cooperativeLaunch) s->sparse_ctas = 1;
     s->sparse_threads = s->sparse_ctas == 1 ? 1024 : 512;
-    if (s->sparse_ctas > s->n_sms * 2) s->sparse_ctas = s->n_sms * 2;
+    if (s->sparse_ctas > s->n_sms) s->sparse_ctas = s->n_sms;
     P.sparse_ctas = (uint32_t)s->sparse_ctas;
     CK(cudaMalloc(&P.E1, s->cells * sizeof(float)));
     CK(cudaMalloc(&P.tfB, s->cells));
