@@ -394,19 +394,17 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
 
 // ------------------------------------------------------------------------------------------
 // Claim resolution shared by k_move_commit and k_repro_commit.
-// s_tf: flags with a 2-cell halo; s_cl (same geometry, zeroed by the caller): on return every
-// cell of tile + 1-ring holds at most ONE bit: bit j set = "my neighbour j wins me".
-// A claimant with direction d therefore won iff bit (7-d) of its target's byte is set.
+// s_tf: flags with a 2-cell halo; s_cl (same geometry, zeroed by the caller) receives one bit per
+// claimant: bit j of a cell's byte = "my neighbour j claims me".  A cell with one bit has its
+// winner; only cells with >= 2 bits need the claimants' Philox priorities, which winner_of()
+// computes on demand (and caches by collapsing the byte to the winner's bit -- every thread that
+// races on it writes the same value).  A claimant with direction d won iff the winner is 7-d.
 // ------------------------------------------------------------------------------------------
-template <int TW, int TH, typename KeyFn>
-__device__ __forceinline__ void resolve_claims(const Params& p, const uint8_t* s_tf, uint8_t* s_cl,
-                                               uint16_t* s_list, unsigned int* s_cnt, uint32_t x0,
-                                               uint32_t y0, KeyFn keyfn) {
+template <int TW, int TH>
+__device__ __forceinline__ void scatter_claims(const uint8_t* s_tf, uint8_t* s_cl) {
     constexpr int SW = TW + 32, SH = TH + 4, NWORD = SH * SW / 4;
-    const int tid = threadIdx.x;
-    // scatter one bit per claimant; the tile is scanned 4 cells (one word) at a time and claimants
-    // are sparse (<= ~10 % of cells), so the common path is one load and one test per word
-    for (int w = tid; w < NWORD; w += NT) {
+    // the tile is scanned 4 cells (one word) at a time; claimants are sparse (<= ~10 % of cells)
+    for (int w = threadIdx.x; w < NWORD; w += NT) {
         const uint32_t t4 = reinterpret_cast<const uint32_t*>(s_tf)[w];
         uint32_t cm = t4 & 0x40404040u;
         while (cm) {
@@ -422,38 +420,29 @@ __device__ __forceinline__ void resolve_claims(const Params& p, const uint8_t* s
             atomicOr(reinterpret_cast<unsigned int*>(s_cl) + (st >> 2), (1u << (7 - d)) << (8 * (st & 3)));
         }
     }
-    __syncthreads();
-    // contested cells (>= 2 claimants) -> list
-    for (int w = tid; w < NWORD; w += NT) {
-        const uint32_t c4 = reinterpret_cast<const uint32_t*>(s_cl)[w];
-        if (c4 == 0u) continue;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const uint32_t m = (c4 >> (8 * b)) & 0xFFu;
-            if (m & (m - 1u)) s_list[atomicAdd(s_cnt, 1u)] = (uint16_t)(w * 4 + b);
-        }
+}
+
+// winning neighbour index of the claimed cell at shared index st (highest (priority, cell), :929, :1192)
+template <int TW, typename KeyFn>
+__device__ __forceinline__ int winner_of(const Params& p, uint8_t* s_cl, int st, uint32_t x0, uint32_t y0, KeyFn keyfn) {
+    constexpr int SW = TW + 32;
+    uint32_t m = s_cl[st];
+    if (!(m & (m - 1u))) return __ffs(m) - 1;  // a single claimant
+    const int r = st / SW, c = st - r * SW;
+    const uint32_t tx = (x0 + (uint32_t)(c - 16)) & (p.W - 1);
+    // local row of the claimed cell (may be -1 or H in the ring): only used through nb_gcell, which maps
+    // it to the GLOBAL row modulo the world height
+    const uint32_t ty = p.wrap_y ? ((y0 + (uint32_t)(r - 2)) & (p.H - 1)) : (y0 + (uint32_t)(r - 2));
+    int best = -1;
+    Key bk;
+    while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const Key k2 = keyfn(p, nb_gcell(p, tx, ty, j));
+        if (best < 0 || key_gt(k2, bk)) { bk = k2; best = j; }
     }
-    __syncthreads();
-    const unsigned int n = *s_cnt;
-    for (unsigned int k = tid; k < n; k += NT) {
-        const int si = s_list[k];
-        const int r = si / SW, c = si - r * SW;
-        const uint32_t tx = (x0 + (uint32_t)(c - 16)) & (p.W - 1);
-        // local row of the contested cell (may be -1 or H in the ring): only used through nb_gcell,
-        // which maps it to the GLOBAL row modulo the world height
-        const uint32_t ty = p.wrap_y ? ((y0 + (uint32_t)(r - 2)) & (p.H - 1)) : (y0 + (uint32_t)(r - 2));
-        uint32_t m = s_cl[si];
-        int best = -1;
-        Key bk;
-        while (m) {  // highest (priority, cell) wins (:929, :1192)
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            const Key k2 = keyfn(p, nb_gcell(p, tx, ty, j));
-            if (best < 0 || key_gt(k2, bk)) { bk = k2; best = j; }
-        }
-        s_cl[si] = (uint8_t)(1u << best);
-    }
-    __syncthreads();
+    s_cl[st] = (uint8_t)(1u << best);
+    return best;
 }
 
 // copy a CTA-local list of local cell indices into its reserved range of a global list
@@ -474,52 +463,32 @@ __device__ __forceinline__ void copy_cells(const Params& p, const uint16_t* s_li
     }
 }
 
-// copy a CTA-local list of local cell indices to a global list (one atomic per CTA)
-template <int TW>
-__device__ __forceinline__ void flush_cells(const Params& p, const uint16_t* s_list, unsigned int n,
-                                            unsigned int* gcounter, uint32_t* gcell_list,
-                                            const uint8_t* s_state, uint8_t* gstate, uint32_t x0,
-                                            uint32_t y0, unsigned int* s_slot) {
-    const unsigned int base = cta_reserve(gcounter, n, s_slot);
-    if (n == 0) return;
-    if (base + n > p.list_cap) {
-        if (threadIdx.x == 0) atomicExch(&p.ctr->overflow, 1u);
-        return;
-    }
-    for (unsigned int k = threadIdx.x; k < n; k += NT) {
-        const int cl = s_list[k];
-        const int ly = cl / TW, lx = cl - ly * TW;
-        gcell_list[base + k] = ((y0 + ly) << p.log2W) | (x0 + lx);
-        if (gstate) gstate[base + k] = s_state[k];
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // k_move_commit (dense sweep 2): move_response (:881-960), round 1.  tfB (2-halo) -> tfA.
 // An empty cell that received claims PULLS the winner's energy/strategies; a claimant looks up
-// its target's winner bit and either vacates (leaving a GHOST that keeps blocking movers this
+// its target's winner and either vacates (leaving a GHOST that keeps blocking movers this
 // step, quirk B-13) or joins the loser list.  Claimants and claimed cells are rare, so the dense
 // scan only classifies words and queues them; the queue is then processed with full lanes.
 // Loser state byte: 0x80 active | 0x40 fresh | claimed direction (k_move_retry derives the rest).
 // ------------------------------------------------------------------------------------------
 template <int TW, int TH>
-__global__ void __launch_bounds__(NT) k_move_commit(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(NT, 8) k_move_commit(const __grid_constant__ Params p) {
     constexpr int SW = TW + 32, SH = TH + 4, NC = TW * TH;
     __shared__ __align__(16) uint8_t s_tf[SH * SW];
     __shared__ __align__(16) uint8_t s_cl[SH * SW];
     __shared__ __align__(16) uint8_t s_out[NC];
-    __shared__ uint16_t s_list[(TH + 2) * (TW + 2)];
     __shared__ uint16_t s_work[NC];
     __shared__ uint16_t s_lost[NC];
     __shared__ uint8_t s_lost_state[NC];
-    __shared__ unsigned int s_n[4];  // 0 contested, 1 lost, 2 slot, 3 work
+    __shared__ unsigned int s_n[4];  // 0 work, 1 lost, 2 base
     const int tid = threadIdx.x;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     if (tid < 4) s_n[tid] = 0;
     load_tile_vec<TW, TH, 2>(p, p.tfB, s_tf, x0, y0);
     for (int i = tid; i < SH * SW / 16; i += NT) reinterpret_cast<uint4*>(s_cl)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    resolve_claims<TW, TH>(p, s_tf, s_cl, s_list, &s_n[0], x0, y0, TravelKey());
+    scatter_claims<TW, TH>(s_tf, s_cl);
+    __syncthreads();
     for (int i = tid; i < NC / 4; i += NT) {
         const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
         const int si = (ly + 2) * SW + lx + 16;
@@ -536,11 +505,11 @@ __global__ void __launch_bounds__(NT) k_move_commit(const __grid_constant__ Para
         while (sp) {
             const int b = (__ffs(sp) - 1) >> 3;
             sp &= sp - 1;
-            s_work[atomicAdd(&s_n[3], 1u)] = (uint16_t)(i * 4 + b);
+            s_work[atomicAdd(&s_n[0], 1u)] = (uint16_t)(i * 4 + b);
         }
     }
     __syncthreads();
-    const unsigned int n_work = s_n[3];
+    const unsigned int n_work = s_n[0];
     unsigned int n_moved = 0;
     for (unsigned int k = tid; k < n_work; k += NT) {
         const int cl = s_work[k];
@@ -550,7 +519,7 @@ __global__ void __launch_bounds__(NT) k_move_commit(const __grid_constant__ Para
         if (t & TF_CLAIM) {
             const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
             const int st = si + c_dir_dy[d] * SW + c_dir_dx[d];
-            if ((s_cl[st] >> (7 - d)) & 1u) {
+            if (winner_of<TW>(p, s_cl, st, x0, y0, TravelKey()) == 7 - d) {
                 s_out[cl] = (uint8_t)TF_GHOST;  // moved away; still blocks movers this step (B-13)
             } else {                            // :940-943 -> retry with the same roll
                 const unsigned int slot = atomicAdd(&s_n[1], 1u);
@@ -558,7 +527,7 @@ __global__ void __launch_bounds__(NT) k_move_commit(const __grid_constant__ Para
                 s_lost_state[slot] = (uint8_t)(0xC0u | (uint32_t)d);
             }
         } else {  // the winner relocates here (:946-956)
-            const int j = __ffs((uint32_t)s_cl[si]) - 1;
+            const int j = winner_of<TW>(p, s_cl, si, x0, y0, TravelKey());
             const uint32_t tn = s_tf[si + c_dir_dy[j] * SW + c_dir_dx[j]];
             const uint32_t x = x0 + lx, y = y0 + ly;
             const uint32_t src = nb_local(p, x, y, j);
@@ -574,7 +543,12 @@ __global__ void __launch_bounds__(NT) k_move_commit(const __grid_constant__ Para
         const int ly = (i * 16) / TW, lx = (i * 16) - ly * TW;
         *reinterpret_cast<uint4*>(p.tfA + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = reinterpret_cast<uint4*>(s_out)[i];
     }
-    flush_cells<TW>(p, s_lost, s_n[1], &p.ctr->mv_n, p.mv_cell, s_lost_state, p.mv_state, x0, y0, &s_n[2]);
+    const unsigned int n_lost = s_n[1];
+    if (n_lost) {  // uniform across the CTA
+        if (tid == 0) s_n[2] = atomicAdd(&p.ctr->mv_n, n_lost);
+        __syncthreads();
+        copy_cells<TW>(p, s_lost, n_lost, s_n[2], p.mv_cell, s_lost_state, p.mv_state, x0, y0);
+    }
     if (p.stats && n_moved && row_owned(p, y0)) atomicAdd(&p.ctr->st_moved, (unsigned long long)n_moved);
 }
 
@@ -634,26 +608,27 @@ __global__ void __launch_bounds__(NT) k_repro_claim(const __grid_constant__ Para
 
 // ------------------------------------------------------------------------------------------
 // k_repro_commit (dense sweep 4): god_multiply round 1 (:1144-1335) + environmental_punishment
-// (:1339-1371) + step_fn's counts (:1405-1419).  Claim losers go to the repro-loser list and
-// their living cost is deferred to k_finalize (a retry round may still charge them the
-// reproduction cost first).  An agent that dies of living cost keeps its cell (DYING) until the
-// retry rounds are over, exactly like in the reference where the punishment layer runs after
-// the god submodel.
+// (:1339-1371) + step_fn's counts (:1405-1419).  tfB (2-halo), E1, strat -> tfA, E0, strat.
+// The dense scan handles the common cells (empty, or occupied without a claim) inline and queues
+// the rare ones -- claimants and cells that receive a child -- which are then processed with full
+// lanes and patched into the output.  Claim losers go to the repro-loser list and their living cost
+// is deferred to k_finalize (a retry round may still charge them the reproduction cost first).
+// An agent that dies of living cost keeps its cell (DYING) until the retry rounds are over, exactly
+// like in the reference where the punishment layer runs after the god submodel.
 // ------------------------------------------------------------------------------------------
 template <int TW, int TH>
-__global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ Params p) {
     constexpr int SW = TW + 32, SH = TH + 4, NC = TW * TH;
     __shared__ __align__(16) uint8_t s_tf[SH * SW];
     __shared__ __align__(16) uint8_t s_cl[SH * SW];
-    __shared__ uint16_t s_list[(TH + 2) * (TW + 2)];
-    __shared__ uint16_t s_birth[NC];  // cells that receive a child
+    __shared__ uint16_t s_work[NC];   // claimants and birth cells of this tile
+    __shared__ uint16_t s_birth[NC];  // cells that received a child (for the newborn list)
     __shared__ uint16_t s_lost[NC];
     __shared__ uint8_t s_lost_state[NC];
     __shared__ uint16_t s_risk[NC];
     __shared__ uint16_t s_dead[NC];
-    __shared__ float s_ce[NC];        // child energy by cell (only written/read for birth cells)
     __shared__ unsigned int s_bins[16];
-    __shared__ unsigned int s_n[8];   // 0 contested, 1 births, 2 lost, 3 risk, 4 dead, 5 n_old, 6 -, 7 living deaths
+    __shared__ unsigned int s_n[8];   // 0 work, 1 births, 2 lost, 3 risk, 4 dead, 5 n_old, 6 -, 7 living deaths
     __shared__ unsigned int s_base[4];
     const int tid = threadIdx.x;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
@@ -662,36 +637,9 @@ __global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Par
     load_tile_vec<TW, TH, 2>(p, p.tfB, s_tf, x0, y0);
     for (int i = tid; i < SH * SW / 16; i += NT) reinterpret_cast<uint4*>(s_cl)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    resolve_claims<TW, TH>(p, s_tf, s_cl, s_list, &s_n[0], x0, y0, ReproKey());
-    // ---- cells of this tile that receive a child
-    for (int i = tid; i < NC / 4; i += NT) {
-        const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
-        const uint32_t c4 = *reinterpret_cast<const uint32_t*>(s_cl + (ly + 2) * SW + lx + 16);
-        if (c4 == 0u) continue;
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-            if ((c4 >> (8 * b)) & 0xFFu) s_birth[atomicAdd(&s_n[1], 1u)] = (uint16_t)(i * 4 + b);
-    }
+    scatter_claims<TW, TH>(s_tf, s_cl);
     __syncthreads();
-    const unsigned int n_birth = s_n[1];
-    // ---- the children (:1216-1328), all lanes busy
-    for (unsigned int k = tid; k < n_birth; k += NT) {
-        const int cl = s_birth[k];
-        const int ly = cl / TW, lx = cl - ly * TW;
-        const int si = (ly + 2) * SW + lx + 16;
-        const uint32_t x = x0 + lx, y = y0 + ly;
-        const int j = __ffs((uint32_t)s_cl[si]) - 1;  // the winning neighbour
-        const uint32_t tn = s_tf[si + c_dir_dy[j] * SW + c_dir_dx[j]];
-        const uint32_t src = nb_local(p, x, y, j);
-        const float pe = __fsub_rn(p.E1[src], p.reproduce_cost);
-        float ce;
-        uint32_t cs;
-        make_child(p, nb_gcell(p, x, y, j), p.strat[src], tn & TF_TRAIT, pe, ce, cs);
-        p.strat[((size_t)y << p.log2W) | x] = (uint8_t)cs;
-        s_ce[cl] = ce;
-    }
-    __syncthreads();
-    // ---- main loop, 4 cells per thread
+    // ---- dense scan, 4 cells per thread
     unsigned int n_old = 0, n_dead = 0;
     for (int i = tid; i < NC / 4; i += NT) {
         const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
@@ -710,27 +658,14 @@ __global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Par
         n_old += __popc(t4 & 0x80808080u);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t t = (t4 >> (8 * k)) & 0xFFu, cb = (c4 >> (8 * k)) & 0xFFu;
+            const uint32_t t = (t4 >> (8 * k)) & 0xFFu;
             const int cl = i * 4 + k;
-            if (t & TF_OCC) {
+            if (t & TF_CLAIM) {           // a parent with a claim: decided in the queue below
+                s_work[atomicAdd(&s_n[0], 1u)] = (uint16_t)cl;
+            } else if (t & TF_OCC) {      // everybody else pays the cost of living now (:1357-1368)
                 const uint32_t trait = t & TF_TRAIT;
                 float e = ev[k];
-                bool lost = false;
-                if (t & TF_CLAIM) {
-                    const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
-                    const int st = si + k + c_dir_dy[d] * SW + c_dir_dx[d];
-                    if ((s_cl[st] >> (7 - d)) & 1u) {
-                        e = __fsub_rn(e, p.reproduce_cost);  // :1211-1213
-                    } else {  // stays ATTEMPTING_REPRODUCTION (:1203-1205): retry list, living cost deferred
-                        lost = true;
-                        const unsigned int slot = atomicAdd(&s_n[2], 1u);
-                        s_lost[slot] = (uint16_t)cl;
-                        s_lost_state[slot] = (uint8_t)(0xC0u | (uint32_t)d);
-                    }
-                }
-                if (lost) {
-                    out4 |= (TF_OCC | trait) << (8 * k);
-                } else if (punish(p, e)) {
+                if (punish(p, e)) {
                     out4 |= (TF_OCC | trait) << (8 * k);
                     ev[k] = e;
                     if (e <= p.risk_thr) s_risk[atomicAdd(&s_n[3], 1u)] = (uint16_t)cl;
@@ -743,17 +678,61 @@ __global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Par
                     s_dead[atomicAdd(&s_n[4], 1u)] = (uint16_t)cl;
                     ++n_dead;
                 }
-            } else if (cb) {  // a child was born here: the winner's trait, energy from the birth pass
-                const int j = __ffs(cb) - 1;
-                const uint32_t tn = s_tf[si + k + c_dir_dy[j] * SW + c_dir_dx[j]];
-                out4 |= (TF_OCC | TF_NEWBORN | (tn & TF_TRAIT)) << (8 * k);
-                ev[k] = s_ce[cl];
             } else {
                 ev[k] = 0.0f;
+                if ((c4 >> (8 * k)) & 0xFFu) s_work[atomicAdd(&s_n[0], 1u)] = (uint16_t)cl;  // a child is born here
             }
         }
         *reinterpret_cast<uint32_t*>(p.tfA + cell0) = out4;
         *reinterpret_cast<float4*>(p.E0 + cell0) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+    }
+    __syncthreads();  // the queue is complete; the dense stores above are ordered before the patches below
+    const unsigned int n_work = s_n[0];
+    for (unsigned int k = tid; k < n_work; k += NT) {
+        const int cl = s_work[k];
+        const int ly = cl / TW, lx = cl - ly * TW;
+        const int si = (ly + 2) * SW + lx + 16;
+        const uint32_t x = x0 + lx, y = y0 + ly;
+        const size_t cell = ((size_t)y << p.log2W) | x;
+        const uint32_t t = s_tf[si];
+        if (t & TF_CLAIM) {
+            const uint32_t trait = t & TF_TRAIT;
+            const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
+            const int st = si + c_dir_dy[d] * SW + c_dir_dx[d];
+            float e = p.E1[cell];
+            if (winner_of<TW>(p, s_cl, st, x0, y0, ReproKey()) == 7 - d) {
+                e = __fsub_rn(e, p.reproduce_cost);  // :1211-1213
+                if (punish(p, e)) {
+                    p.tfA[cell] = (uint8_t)(TF_OCC | trait);
+                    p.E0[cell] = e;
+                    if (e <= p.risk_thr) s_risk[atomicAdd(&s_n[3], 1u)] = (uint16_t)cl;
+                    if (p.want_counts) atomicAdd(&s_bins[count_bin(p.strat[cell], trait)], 1u);
+                } else {
+                    p.tfA[cell] = (uint8_t)(TF_OCC | TF_DYING);
+                    p.E0[cell] = 0.0f;
+                    s_dead[atomicAdd(&s_n[4], 1u)] = (uint16_t)cl;
+                    atomicAdd(&s_n[7], 1u);
+                }
+            } else {  // stays ATTEMPTING_REPRODUCTION (:1203-1205): retry list, living cost deferred
+                p.tfA[cell] = (uint8_t)(TF_OCC | trait);
+                p.E0[cell] = e;
+                const unsigned int slot = atomicAdd(&s_n[2], 1u);
+                s_lost[slot] = (uint16_t)cl;
+                s_lost_state[slot] = (uint8_t)(0xC0u | (uint32_t)d);
+            }
+        } else {  // a child is born here (:1216-1328): the winner's trait, its own energy and strategies
+            const int j = winner_of<TW>(p, s_cl, si, x0, y0, ReproKey());
+            const uint32_t tn = s_tf[si + c_dir_dy[j] * SW + c_dir_dx[j]];
+            const uint32_t src = nb_local(p, x, y, j);
+            const float pe = __fsub_rn(p.E1[src], p.reproduce_cost);
+            float ce;
+            uint32_t cs;
+            make_child(p, nb_gcell(p, x, y, j), p.strat[src], tn & TF_TRAIT, pe, ce, cs);
+            p.strat[cell] = (uint8_t)cs;
+            p.E0[cell] = ce;
+            p.tfA[cell] = (uint8_t)(TF_OCC | TF_NEWBORN | (tn & TF_TRAIT));
+            s_birth[atomicAdd(&s_n[1], 1u)] = (uint16_t)cl;
+        }
     }
     if (n_old) atomicAdd(&s_n[5], n_old);
     if (n_dead) atomicAdd(&s_n[7], n_dead);
@@ -761,28 +740,27 @@ __global__ void __launch_bounds__(NT) k_repro_commit(const __grid_constant__ Par
     // one atomic per list per CTA, then plain copies.  A ghost tile of a slab only contributes its claim
     // losers (the retry rounds need them); its newborns, deaths and counts belong to the owning slab.
     const bool owned = row_owned(p, y0);
-    if (!owned) {
-        if (tid == 0) { s_n[3] = 0; s_n[4] = 0; s_n[5] = 0; s_n[7] = 0; }
-        __syncthreads();
-    }
-    const unsigned int n_birth_listed = owned ? n_birth : 0u;
+    const unsigned int n_lost = s_n[2];
+    const unsigned int n_birth = owned ? s_n[1] : 0u, n_risk = owned ? s_n[3] : 0u, n_dying = owned ? s_n[4] : 0u;
     if (tid < 4) {
-        const unsigned int n = tid == 0 ? s_n[2] : tid == 1 ? n_birth_listed : tid == 2 ? s_n[3] : s_n[4];
+        const unsigned int n = tid == 0 ? n_lost : tid == 1 ? n_birth : tid == 2 ? n_risk : n_dying;
         unsigned int* gc = tid == 0 ? &p.ctr->rp_n : tid == 1 ? &p.ctr->nb_n
                          : tid == 2 ? &p.ctr->risk_next_n : &p.ctr->dead_n;
         s_base[tid] = n ? atomicAdd(gc, n) : 0u;
     }
     __syncthreads();
-    copy_cells<TW>(p, s_lost, s_n[2], s_base[0], p.rp_cell, s_lost_state, p.rp_state, x0, y0);
-    copy_cells<TW>(p, s_birth, n_birth_listed, s_base[1], p.nb_cell, nullptr, nullptr, x0, y0);
-    copy_cells<TW>(p, s_risk, s_n[3], s_base[2], p.risk_next, nullptr, nullptr, x0, y0);
-    copy_cells<TW>(p, s_dead, s_n[4], s_base[3], p.dead_cell, nullptr, nullptr, x0, y0);
-    if (tid == 0) {
-        if (s_n[5]) atomicAdd(&p.ctr->n_old, (unsigned long long)s_n[5]);
-        if (n_birth_listed) atomicAdd(&p.ctr->births, (unsigned long long)n_birth_listed);
-        if (s_n[7]) atomicAdd(&p.ctr->living_deaths, (unsigned long long)s_n[7]);
+    copy_cells<TW>(p, s_lost, n_lost, s_base[0], p.rp_cell, s_lost_state, p.rp_state, x0, y0);
+    copy_cells<TW>(p, s_birth, n_birth, s_base[1], p.nb_cell, nullptr, nullptr, x0, y0);
+    copy_cells<TW>(p, s_risk, n_risk, s_base[2], p.risk_next, nullptr, nullptr, x0, y0);
+    copy_cells<TW>(p, s_dead, n_dying, s_base[3], p.dead_cell, nullptr, nullptr, x0, y0);
+    if (owned) {
+        if (tid == 0) {
+            if (s_n[5]) atomicAdd(&p.ctr->n_old, (unsigned long long)s_n[5]);
+            if (n_birth) atomicAdd(&p.ctr->births, (unsigned long long)n_birth);
+            if (s_n[7]) atomicAdd(&p.ctr->living_deaths, (unsigned long long)s_n[7]);
+        }
+        if (p.want_counts && tid < 16 && s_bins[tid]) atomicAdd(&p.ctr->bins[tid], (unsigned long long)s_bins[tid]);
     }
-    if (p.want_counts && owned && tid < 16 && s_bins[tid]) atomicAdd(&p.ctr->bins[tid], (unsigned long long)s_bins[tid]);
 }
 
 }  // namespace pd
