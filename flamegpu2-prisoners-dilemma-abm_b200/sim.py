@@ -221,6 +221,23 @@ class Simulation:
             "tf_raw": tf,
         }
 
+    def export_state(self, path: str):
+        """Dump the world for visual inspection (takes the place of the OpenGL visualiser,
+        configure_visualisation, model.py:1753-1777): a .npz with occ / trait / strat / energy planes, or,
+        for a .ppm path, an image coloured by trait like the reference (agent_color = trait, :1470)."""
+        pl = self.planes()
+        if path.endswith(".ppm"):
+            palette = np.array([[228, 26, 28], [55, 126, 184], [77, 175, 74], [152, 78, 163]], np.uint8)  # SET1
+            img = np.full(pl["occ"].shape + (3,), 26, np.uint8)  # VISUALISATION_BG_RGB 0.1
+            occ = pl["occ"].astype(bool)
+            img[occ] = palette[pl["trait"][occ]]
+            with open(path, "wb") as f:
+                f.write(b"P6\n%d %d\n255\n" % (img.shape[1], img.shape[0]))
+                f.write(img.tobytes())
+        else:
+            np.savez_compressed(path, occ=pl["occ"], trait=pl["trait"], strat=pl["strat"], energy=pl["energy"],
+                                step=self.step_index)
+
     def step_host(self, h_energy, h_strat, h_tf, n_steps=1, out_energy=None, out_strat=None, out_tf=None):
         """pd_step_host: host buffers in, host buffers out (the e2e path of bench.py)."""
         arr = (C.c_uint64 * 16)()

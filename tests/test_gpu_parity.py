@@ -182,3 +182,34 @@ def test_determinism_same_seed():
         sim.close()
     for a, b in zip(outs[0], outs[1]):
         assert np.array_equal(a, b)
+
+
+def test_ensemble_driver_and_json_logs(tmp_path):
+    """CUDAEnsemble-style driver (model.py:1801-1838): independent runs on concurrent streams, one JSON
+    step log per run; each log must equal a stand-alone run of the same seed."""
+    import json
+    from pdabm_b200 import model, SimConfig
+    base = SimConfig(width=64, seed=500)
+    runs = model.configure_runplan(base, multi_run_count=2, multi_run_steps=12)[:6]
+    paths = model.run_ensemble(runs, out_directory=str(tmp_path), devices=[0], streams_per_device=3)
+    assert len(paths) == 6
+    for run, path in zip(runs, paths):
+        doc = json.loads(open(path).read().splitlines()[0])
+        assert doc["config"]["random_seed"] == run["config"].seed
+        assert doc["config"]["environment"]["cost_of_living"] == run["config"].cost_of_living
+        assert [s["step_index"] for s in doc["steps"]] == list(range(13))
+        solo = model.simulate(run["config"], 12)
+        assert doc["steps"] == solo.doc["steps"]
+
+
+def test_state_export(tmp_path):
+    from pdabm_b200 import Simulation, SimConfig
+    sim = Simulation(SimConfig(width=64, seed=3))
+    sim.init_population()
+    sim.step(3)
+    sim.export_state(str(tmp_path / "w.npz"))
+    sim.export_state(str(tmp_path / "w.ppm"))
+    z = np.load(tmp_path / "w.npz")
+    assert z["occ"].sum() == sim.counts()[1] and z["strat"].shape == (64, 64, 4)
+    assert open(tmp_path / "w.ppm", "rb").read(2) == b"P6"
+    sim.close()
