@@ -622,7 +622,12 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
     __shared__ __align__(16) uint8_t s_tf[SH * SW];
     __shared__ __align__(16) uint8_t s_cl[SH * SW];
     __shared__ uint16_t s_work[NC];   // claimants and birth cells of this tile
-    __shared__ uint16_t s_birth[NC];  // cells that received a child (for the newborn list)
+    // cells that received a child (for the newborn list) with the child's payload.  A birth needs an empty
+    // cell of the tile AND a distinct parent in tile + 1-ring, hence at most (NC + ring) / 2 per tile.
+    constexpr int NBMAX = NC / 2 + TW + TH + 8;
+    __shared__ uint16_t s_birth[NBMAX];
+    __shared__ float s_birth_e[NBMAX];
+    __shared__ uint16_t s_birth_g[NBMAX];
     __shared__ uint16_t s_lost[NC];
     __shared__ uint8_t s_lost_state[NC];
     __shared__ uint16_t s_risk[NC];
@@ -687,6 +692,7 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
         *reinterpret_cast<float4*>(p.E0 + cell0) = make_float4(ev[0], ev[1], ev[2], ev[3]);
     }
     __syncthreads();  // the queue is complete; the dense stores above are ordered before the patches below
+    const bool owned_tile = row_owned(p, y0);
     const unsigned int n_work = s_n[0];
     for (unsigned int k = tid; k < n_work; k += NT) {
         const int cl = s_work[k];
@@ -728,10 +734,21 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
             float ce;
             uint32_t cs;
             make_child(p, nb_gcell(p, x, y, j), p.strat[src], tn & TF_TRAIT, pe, ce, cs);
-            p.strat[cell] = (uint8_t)cs;
-            p.E0[cell] = ce;
-            p.tfA[cell] = (uint8_t)(TF_OCC | TF_NEWBORN | (tn & TF_TRAIT));
-            s_birth[atomicAdd(&s_n[1], 1u)] = (uint16_t)cl;
+            if (owned_tile) {
+                // Not written into the planes yet: near the carrying capacity almost every newborn is culled
+                // in the same step (k_finalize), so it only goes on the newborn list with its payload.  If
+                // retry rounds run, k_repro_retry first marks the listed cells as occupied.
+                const unsigned int slot = atomicAdd(&s_n[1], 1u);
+                if (slot < (unsigned int)NBMAX) {
+                    s_birth[slot] = (uint16_t)cl;
+                    s_birth_e[slot] = ce;
+                    s_birth_g[slot] = (uint16_t)(cs | ((tn & TF_TRAIT) << 8));
+                } else atomicExch(&p.ctr->overflow, 1u);
+            } else {  // ghost tile of a slab: the owner lists it; here it only has to block its cell
+                p.strat[cell] = (uint8_t)cs;
+                p.E0[cell] = ce;
+                p.tfA[cell] = (uint8_t)(TF_OCC | TF_NEWBORN | (tn & TF_TRAIT));
+            }
         }
     }
     if (n_old) atomicAdd(&s_n[5], n_old);
@@ -741,7 +758,8 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
     // losers (the retry rounds need them); its newborns, deaths and counts belong to the owning slab.
     const bool owned = row_owned(p, y0);
     const unsigned int n_lost = s_n[2];
-    const unsigned int n_birth = owned ? s_n[1] : 0u, n_risk = owned ? s_n[3] : 0u, n_dying = owned ? s_n[4] : 0u;
+    const unsigned int n_birth = owned ? (s_n[1] < (unsigned int)NBMAX ? s_n[1] : (unsigned int)NBMAX) : 0u;
+    const unsigned int n_risk = owned ? s_n[3] : 0u, n_dying = owned ? s_n[4] : 0u;
     if (tid < 4) {
         const unsigned int n = tid == 0 ? n_lost : tid == 1 ? n_birth : tid == 2 ? n_risk : n_dying;
         unsigned int* gc = tid == 0 ? &p.ctr->rp_n : tid == 1 ? &p.ctr->nb_n
@@ -751,6 +769,11 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
     __syncthreads();
     copy_cells<TW>(p, s_lost, n_lost, s_base[0], p.rp_cell, s_lost_state, p.rp_state, x0, y0);
     copy_cells<TW>(p, s_birth, n_birth, s_base[1], p.nb_cell, nullptr, nullptr, x0, y0);
+    if (n_birth && s_base[1] + n_birth <= p.list_cap)
+        for (unsigned int k = tid; k < n_birth; k += NT) {
+            p.nb_e[s_base[1] + k] = s_birth_e[k];
+            p.nb_gene[s_base[1] + k] = s_birth_g[k];
+        }
     copy_cells<TW>(p, s_risk, n_risk, s_base[2], p.risk_next, nullptr, nullptr, x0, y0);
     copy_cells<TW>(p, s_dead, n_dying, s_base[3], p.dead_cell, nullptr, nullptr, x0, y0);
     if (owned) {

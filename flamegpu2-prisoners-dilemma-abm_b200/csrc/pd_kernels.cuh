@@ -185,6 +185,19 @@ __global__ void __launch_bounds__(1024) k_repro_retry(const __grid_constant__ Pa
     if (n == 0) return;
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    // The newborns of round 1 are only on the newborn list so far (k_repro_commit).  If retry rounds are
+    // going to run, they must block their cells: mark them occupied first.
+    if (p.round0 == 1) {
+        const unsigned long long pop0 = p.glb ? __ldcg(&p.glb[0]) + __ldcg(&p.glb[1])
+                                              : __ldcg(&ctr->n_old) + __ldcg(&ctr->births);
+        if (pop0 > p.max_agents) return;  // the gate is closed for good: no retry rounds this step
+        unsigned int nb1 = ctr->nb_n;
+        if (nb1 > p.list_cap) nb1 = p.list_cap;
+        for (unsigned int i = t0; i < nb1; i += stride)
+            p.tfA[p.nb_cell[i]] = (uint8_t)(TF_OCC | TF_NEWBORN | ((uint32_t)(p.nb_gene[i] >> 8) & TF_TRAIT));
+        if (t0 == 0) ctr->nb_flagged = 1u;
+        grid_sync(ctr->barrier, gridDim.x);
+    }
     for (int round = (int)p.round0; round < (int)p.round1; ++round) {
         // overpopulated gate, evaluated after every round (:1616, :1621-1625); in slab mode the caller
         // has summed olds and births over all slabs into glb[] before this launch (one round per launch)
@@ -254,13 +267,14 @@ __global__ void __launch_bounds__(1024) k_repro_retry(const __grid_constant__ Pa
                 float ce;
                 uint32_t cs;
                 make_child(p, gcell_of(p, x, y), __ldcg(p.strat + cell), t & TF_TRAIT, pe, ce, cs);
-                p.E0[tgt] = ce;
-                p.strat[tgt] = (uint8_t)cs;
-                p.tfA[tgt] = (uint8_t)(TF_OCC | TF_NEWBORN | (t & TF_TRAIT));
+                p.tfA[tgt] = (uint8_t)(TF_OCC | TF_NEWBORN | (t & TF_TRAIT));  // blocks its cell in later rounds
                 if (row_owned(p, tgt >> p.log2W)) {  // a child in the ghost zone belongs to the neighbour slab
                     const unsigned int slot = atomicAdd(&ctr->nb_n, 1u);
-                    if (slot < p.list_cap) p.nb_cell[slot] = tgt;
-                    else atomicExch(&ctr->overflow, 1u);
+                    if (slot < p.list_cap) {
+                        p.nb_cell[slot] = tgt;
+                        p.nb_e[slot] = ce;
+                        p.nb_gene[slot] = (uint16_t)(cs | ((t & TF_TRAIT) << 8));
+                    } else atomicExch(&ctr->overflow, 1u);
                     ++born;
                 }
                 p.rp_state[i] = 0x40u;  // REPRODUCTION_COMPLETE; living cost still due
@@ -398,6 +412,7 @@ __device__ __forceinline__ void fin_apply(const Params& p, unsigned int nb, unsi
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     // ---- newborns: cull or admit (no living cost in the birth step, :1343)
     unsigned int n_culled = 0;
+    const bool flagged = __ldcg(&ctr->nb_flagged) != 0u;
     for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nb; i0 += stride) {
         const unsigned int i = i0 + threadIdx.x;
         bool at_risk = false;
@@ -405,14 +420,16 @@ __device__ __forceinline__ void fin_apply(const Params& p, unsigned int nb, unsi
             const uint32_t cell = p.nb_cell[i];
             bool survive = true;
             if (cull) survive = keep != 0 && cull_key(p, cell, p.nb_prio[i]) >= tau;
-            if (survive) {
-                const uint32_t t = __ldcg(p.tfA + cell);
-                p.tfA[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
-                at_risk = __ldcg(p.E0 + cell) <= p.risk_thr;
-                if (p.want_counts) atomicAdd(&ctr->bins[count_bin(__ldcg(p.strat + cell), t & TF_TRAIT)], 1ull);
+            if (survive) {  // only now does the newborn enter the planes
+                const uint32_t gene = p.nb_gene[i];
+                const float ce = p.nb_e[i];
+                p.tfA[cell] = (uint8_t)(TF_OCC | ((gene >> 8) & TF_TRAIT));
+                p.E0[cell] = ce;
+                p.strat[cell] = (uint8_t)(gene & 0xFFu);
+                at_risk = ce <= p.risk_thr;
+                if (p.want_counts) atomicAdd(&ctr->bins[count_bin(gene & 0xFFu, (gene >> 8) & TF_TRAIT)], 1ull);
             } else {
-                p.tfA[cell] = 0;
-                p.E0[cell] = 0.0f;
+                if (flagged) p.tfA[cell] = 0;  // it was marked occupied for the retry rounds
                 ++n_culled;
             }
         }
