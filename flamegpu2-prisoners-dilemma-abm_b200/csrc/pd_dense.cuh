@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
     __shared__ uint16_t s_mover[NC];
     __shared__ uint16_t s_q[NWARP][256];  // per-warp queue of the games that need random words: lane << 3 | c
     __shared__ uint8_t s_qo[NWARP][256];  // their outcomes
+    __shared__ uint8_t s_q2[NWARP][256];  // second level: queue slots whose game needs random words
     __shared__ unsigned int s_n[4];       // 0 agents, 1 ring cells, 2 movers
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
@@ -298,23 +299,40 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
         __syncwarp();
         // ---- evaluate them 32 at a time (play_response, :599-689)
         const uint32_t pack = (uint32_t)si | ((uint32_t)cl << 16);
+        int n2 = 0;
         for (int q0 = 0; q0 < total; q0 += 32) {
             const int q = q0 + lane;
             const bool active = q < total;
             const uint32_t ent = active ? s_q[warp][q] : 0u;
-            const int c = (int)(ent & 7u), d = 7 - c;
+            const int d = 7 - (int)(ent & 7u);
             const uint32_t pk = __shfl_sync(FULL, pack, (int)(ent >> 3));
+            bool need = false;
             if (active) {
                 const int si_l = (int)(pk & 0xFFFFu);
                 uint32_t mine, theirs;
                 game_strategies(s_R[si_l], s_R[si_l + c_dir_dy[d] * SW + c_dir_dx[d]], mine, theirs);
-                uint32_t o = ((mine != 1u) ? 2u : 0u) | ((theirs != 1u) ? 1u : 0u);
-                if (noisy || mine == 3u || theirs == 3u) {
-                    const int cl_l = (int)(pk >> 16);
-                    const uint64_t gl = gcell_of(p, x0 + (uint32_t)(cl_l & (TW - 1)), y0 + (uint32_t)(cl_l >> LOG_TW));
-                    o = game_outcome_rng(p, gl, c, mine, theirs);
-                }
-                s_qo[warp][q] = (uint8_t)o;
+                need = noisy || mine == 3u || theirs == 3u;
+                s_qo[warp][q] = (uint8_t)(((mine != 1u) ? 2u : 0u) | ((theirs != 1u) ? 1u : 0u));
+            }
+            // the games that need random words are compacted once more: the Philox rounds then run with full lanes
+            const unsigned int bal = __ballot_sync(FULL, need);
+            if (need) s_q2[warp][n2 + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)q;
+            n2 += __popc(bal);
+        }
+        __syncwarp();
+        for (int k0 = 0; k0 < n2; k0 += 32) {
+            const int k = k0 + lane;
+            const bool active = k < n2;
+            const int q = active ? s_q2[warp][k] : 0;
+            const uint32_t ent = s_q[warp][q];
+            const int c = (int)(ent & 7u), d = 7 - c;
+            const uint32_t pk = __shfl_sync(FULL, pack, (int)(ent >> 3));
+            if (active) {
+                const int si_l = (int)(pk & 0xFFFFu), cl_l = (int)(pk >> 16);
+                uint32_t mine, theirs;
+                game_strategies(s_R[si_l], s_R[si_l + c_dir_dy[d] * SW + c_dir_dx[d]], mine, theirs);
+                const uint64_t gl = gcell_of(p, x0 + (uint32_t)(cl_l & (TW - 1)), y0 + (uint32_t)(cl_l >> LOG_TW));
+                s_qo[warp][q] = (uint8_t)game_outcome_rng(p, gl, c, mine, theirs);
             }
         }
         __syncwarp();
