@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
     constexpr int SW = TW + 32, SH = TH + 4, NC = TW * TH;
     __shared__ __align__(16) uint8_t s_tf[SH * SW];
     __shared__ __align__(16) uint8_t s_cl[SH * SW];
-    __shared__ uint16_t s_work[NC];   // claimants and birth cells of this tile
+    __shared__ uint16_t s_work[NC];   // claimants of this tile from the front, birth cells from the back
     // cells that received a child (for the newborn list) with the child's payload.  A birth needs an empty
     // cell of the tile AND a distinct parent in tile + 1-ring, hence at most (NC + ring) / 2 per tile.
     constexpr int NBMAX = NC / 2 + TW + TH + 8;
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
     __shared__ uint16_t s_risk[NC];
     __shared__ uint16_t s_dead[NC];
     __shared__ unsigned int s_bins[16];
-    __shared__ unsigned int s_n[8];   // 0 work, 1 births, 2 lost, 3 risk, 4 dead, 5 n_old, 6 -, 7 living deaths
+    __shared__ unsigned int s_n[8];   // 0 claimants, 1 births listed, 2 lost, 3 risk, 4 dead, 5 n_old, 6 birth cells, 7 living deaths
     __shared__ unsigned int s_base[4];
     const int tid = threadIdx.x;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
                 }
             } else {
                 ev[k] = 0.0f;
-                if ((c4 >> (8 * k)) & 0xFFu) s_work[atomicAdd(&s_n[0], 1u)] = (uint16_t)cl;  // a child is born here
+                if ((c4 >> (8 * k)) & 0xFFu) s_work[NC - 1 - atomicAdd(&s_n[6], 1u)] = (uint16_t)cl;  // a child is born here
             }
         }
         *reinterpret_cast<uint32_t*>(p.tfA + cell0) = out4;
@@ -711,15 +711,18 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
     }
     __syncthreads();  // the queue is complete; the dense stores above are ordered before the patches below
     const bool owned_tile = row_owned(p, y0);
-    const unsigned int n_work = s_n[0];
-    for (unsigned int k = tid; k < n_work; k += NT) {
-        const int cl = s_work[k];
+    // two homogeneous queues (no divergence between the two kinds of work inside a warp)
+    const unsigned int n_claim = s_n[0], n_born = s_n[6];
+    for (unsigned int k = tid; k < n_claim + n_born; k += NT) {
+        // claimants first, then birth cells; the boundary falls inside at most one warp
+        const bool is_claim = k < n_claim;
+        const int cl = is_claim ? s_work[k] : s_work[NC - 1 - (k - n_claim)];
         const int ly = cl / TW, lx = cl - ly * TW;
         const int si = (ly + 2) * SW + lx + 16;
         const uint32_t x = x0 + lx, y = y0 + ly;
         const size_t cell = ((size_t)y << p.log2W) | x;
         const uint32_t t = s_tf[si];
-        if (t & TF_CLAIM) {
+        if (is_claim) {
             const uint32_t trait = t & TF_TRAIT;
             const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
             const int st = si + c_dir_dy[d] * SW + c_dir_dx[d];
