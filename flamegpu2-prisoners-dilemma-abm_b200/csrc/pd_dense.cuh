@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(NT, 8) k_move_commit(const __grid_constant__ P
     __shared__ uint16_t s_work[NC];
     __shared__ uint16_t s_lost[NC];
     __shared__ uint8_t s_lost_state[NC];
-    __shared__ unsigned int s_n[4];  // 0 work, 1 lost, 2 base
+    __shared__ unsigned int s_n[4];  // 0 claimants, 1 lost, 2 base, 3 claimed cells
     const int tid = threadIdx.x;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     if (tid < 4) s_n[tid] = 0;
@@ -513,28 +513,29 @@ __global__ void __launch_bounds__(NT, 8) k_move_commit(const __grid_constant__ P
         const uint32_t t4 = *reinterpret_cast<const uint32_t*>(s_tf + si);
         const uint32_t c4 = *reinterpret_cast<const uint32_t*>(s_cl + si);
         reinterpret_cast<uint32_t*>(s_out)[i] = t4 & 0x87878787u;  // OCC | GHOST | trait
-        // sp: bit 7 of byte b set <=> cell b is a claimant or received a claim
-        uint32_t sp = (t4 & 0x40404040u) << 1;
-        if (c4) {
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-                if ((c4 >> (8 * b)) & 0xFFu) sp |= 0x80u << (8 * b);
-        }
+        // claimants are queued from the front, claimed cells from the back: two homogeneous queues
+        uint32_t sp = t4 & 0x40404040u;
         while (sp) {
             const int b = (__ffs(sp) - 1) >> 3;
             sp &= sp - 1;
             s_work[atomicAdd(&s_n[0], 1u)] = (uint16_t)(i * 4 + b);
         }
+        if (c4) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if ((c4 >> (8 * b)) & 0xFFu) s_work[NC - 1 - atomicAdd(&s_n[3], 1u)] = (uint16_t)(i * 4 + b);
+        }
     }
     __syncthreads();
-    const unsigned int n_work = s_n[0];
+    const unsigned int n_claim = s_n[0], n_tgt = s_n[3];
     unsigned int n_moved = 0;
-    for (unsigned int k = tid; k < n_work; k += NT) {
-        const int cl = s_work[k];
+    for (unsigned int k = tid; k < n_claim + n_tgt; k += NT) {
+        const bool is_claim = k < n_claim;
+        const int cl = is_claim ? s_work[k] : s_work[NC - 1 - (k - n_claim)];
         const int ly = cl / TW, lx = cl - ly * TW;
         const int si = (ly + 2) * SW + lx + 16;
         const uint32_t t = s_tf[si];
-        if (t & TF_CLAIM) {
+        if (is_claim) {
             const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
             const int st = si + c_dir_dy[d] * SW + c_dir_dx[d];
             if (winner_of<TW>(p, s_cl, st, x0, y0, TravelKey()) == 7 - d) {
