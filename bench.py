@@ -359,13 +359,89 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_config4(args, rank, world, local_rank):
+    """BASELINE configs[3]: an ensemble sweep of 1024x1024 worlds over a noise x mutation x payoff grid,
+    one run per CUDA stream, runs spread over the GPUs (CUDAEnsemble, model.py:1801-1838).  No
+    communication between runs; value = all runs' agent-steps / device time of the slowest GPU."""
+    import threading
+    import torch
+    import torch.distributed as dist
+    from pdabm_b200 import Simulation, SimConfig
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    grid = [(n, m, cc) for n in (0.0, 0.01, 0.05, 0.1) for m in (0.0, 0.001, 0.01, 0.05) for cc in (2.0, 3.0, 4.0, 6.0)]
+    per_gpu = args.runs
+    mine = [grid[(rank * per_gpu + i) % len(grid)] for i in range(per_gpu)]
+    sims, streams = [], []
+    for i, (noise, mut, cc) in enumerate(mine):
+        st = torch.cuda.Stream()
+        cfg = SimConfig(width=1024, seed=12345 + rank * per_gpu + i, env_noise=noise, mutation_rate=mut,
+                        payoff_cc=cc, device=local_rank)
+        sims.append(Simulation(cfg, stream=st))
+        streams.append(st)
+
+    def drive(sim, k):
+        sim.step(k, want_counts=True)
+
+    def all_streams(k):
+        th = [threading.Thread(target=drive, args=(s, k)) for s in sims]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    for s in sims:
+        s.init_population()
+    all_streams(args.presteps + args.warmup)
+    as0 = sum(s.agent_steps() for s in sims)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    start = torch.cuda.Event(enable_timing=True)
+    start.record()
+    for st in streams:
+        st.wait_event(start)
+    all_streams(args.steps)
+    ends = []
+    for st in streams:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(st)
+        ends.append(e)
+    torch.cuda.synchronize()
+    ms = max(start.elapsed_time(e) for e in ends)
+    agent_steps = sum(s.agent_steps() for s in sims) - as0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        a = torch.tensor([agent_steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(a, op=dist.ReduceOp.SUM)
+        ms, agent_steps = float(t[0]), float(a[0])
+    if rank == 0:
+        line = {"metric": "agent-steps/sec", "value": agent_steps / (ms / 1e3), "unit": "agent-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "BASELINE configs[3]: ensemble sweep of 1024x1024 worlds over noise x mutation x payoff_cc, "
+                                       f"{per_gpu} concurrent runs per GPU, one per CUDA stream, counts every step",
+                           "runs": per_gpu * world, "presteps": args.presteps,
+                           "l2": "each world's state fits in L2: no HBM roofline claim"},
+                "gpu_launches": 9 * args.steps * per_gpu * world}
+        print(json.dumps(line), flush=True)
+    for s in sims:
+        s.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS) + ["config5"])
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS) + ["config4", "config5"])
+    ap.add_argument("--runs", type=int, default=16, help="config4: concurrent runs per GPU")
     ap.add_argument("--partition", default="slabs", choices=["slabs", "ensemble"],
                     help="how N > 1 GPUs are used: row slabs of one world (default) or independent worlds")
     ap.add_argument("--width", type=int, default=0, help="override the workload's width (debug)")
@@ -379,7 +455,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        if args.workload in ("config4", "config5"):
+            args.workload = "config2" if args.workload == "config4" else "config3"
         run_reference(args, rank, world)
+    elif args.workload == "config4":
+        run_config4(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

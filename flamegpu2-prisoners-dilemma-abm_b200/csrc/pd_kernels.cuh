@@ -345,6 +345,40 @@ __device__ __forceinline__ void fin_hist(const Params& p, unsigned int nb, unsig
         if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
 }
 
+// Largest bin b such that the number of entries in bins >= b reaches `keep`, found by warp 0 in parallel
+// (each lane owns a contiguous chunk of bins, a warp scan finds the chunk, its lane finishes serially).
+// Writes the bin to *s_digit and keep - (entries in bins > b) to *s_krem.  Call with all threads; nbins % 32 == 0.
+__device__ __forceinline__ void find_threshold_bin(const unsigned int* s_hist, int nbins, unsigned long long keep,
+                                                   unsigned int* s_digit, unsigned long long* s_krem) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x, per = nbins / 32;
+        // lane 0 owns the TOP chunk so that a prefix scan over lanes is a suffix scan over bins
+        const int hi = nbins - 1 - lane * per;
+        unsigned long long mine = 0;
+        for (int j = 0; j < per; ++j) mine += s_hist[hi - j];
+        unsigned long long incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const unsigned int reach = __ballot_sync(0xFFFFFFFFu, incl >= keep);
+        const int owner = reach ? __ffs(reach) - 1 : 31;  // first chunk (from the top) where the count is reached
+        if (lane == owner) {
+            unsigned long long cum = incl - mine;
+            int digit = hi - per + 1;  // lowest bin of my chunk if never reached (cannot happen for keep <= total)
+            for (int j = 0; j < per; ++j) {
+                const unsigned long long h = s_hist[hi - j];
+                if (cum + h >= keep) { digit = hi - j; break; }
+                cum += h;
+            }
+            *s_digit = (unsigned int)digit;
+            *s_krem = keep - cum;
+        }
+    }
+    __syncthreads();
+}
+
 // threshold bin of the (summed) histogram; every CTA computes it identically.  Returns the bin;
 // *krem = how many of the bin's candidates survive.
 __device__ __forceinline__ unsigned int fin_digit(const unsigned int* hist, unsigned long long keep,
@@ -352,18 +386,7 @@ __device__ __forceinline__ unsigned int fin_digit(const unsigned int* hist, unsi
                                                   unsigned long long* s_krem) {
     for (unsigned int i = threadIdx.x; i < 2048; i += blockDim.x) s_hist[i] = __ldcg(&hist[i]);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long cum = 0;
-        int digit = 0;
-        for (int b = 2047; b >= 0; --b) {
-            const unsigned long long h = s_hist[b];
-            if (cum + h >= keep) { digit = b; break; }
-            cum += h;
-        }
-        *s_digit = (unsigned int)digit;
-        *s_krem = keep - cum;
-    }
-    __syncthreads();
+    find_threshold_bin(s_hist, 2048, keep, s_digit, s_krem);
     return *s_digit;
 }
 
@@ -373,6 +396,8 @@ template <typename KeyAt>
 __device__ __forceinline__ unsigned long long fin_select(unsigned int n, unsigned int digit, unsigned int* s_hist,
                                                          unsigned long long* s_prefix, unsigned long long* s_krem,
                                                          KeyAt key_at) {
+    __shared__ unsigned int s_dg_store;
+    unsigned int* s_dg = &s_dg_store;
     if (threadIdx.x == 0) *s_prefix = (unsigned long long)digit;  // the 11 bits decided so far
     int decided = 11;
     while (decided < 64) {
@@ -387,7 +412,10 @@ __device__ __forceinline__ unsigned long long fin_select(unsigned int n, unsigne
                 atomicAdd(&s_hist[(unsigned int)(key >> shift) & ((1u << bits) - 1u)], 1u);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (bits == 8) {
+            find_threshold_bin(s_hist, 256, *s_krem, s_dg, s_krem);
+            if (threadIdx.x == 0) *s_prefix = (prefix << 8) | (unsigned long long)*s_dg;
+        } else if (threadIdx.x == 0) {  // the last, narrower digit
             unsigned long long krem = *s_krem, cum = 0;
             int dg = 0;
             for (int b = (1 << bits) - 1; b >= 0; --b) {
