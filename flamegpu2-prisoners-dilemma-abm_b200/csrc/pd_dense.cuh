@@ -89,15 +89,6 @@ __device__ __forceinline__ uint32_t wappend(unsigned int* counter, bool pred) {
     return base + (unsigned int)__popc(m & ((1u << lane) - 1u));
 }
 
-// reserve `n` slots of a global list for this CTA (one atomic), broadcast through shared memory
-__device__ __forceinline__ unsigned int cta_reserve(unsigned int* gcounter, unsigned int n, unsigned int* s_slot) {
-    if (threadIdx.x == 0) *s_slot = n ? atomicAdd(gcounter, n) : 0u;
-    __syncthreads();
-    const unsigned int b = *s_slot;
-    __syncthreads();
-    return b;
-}
-
 // the game of sub-step c as the responder at my_g sees it -> index into Params::pay
 __device__ __forceinline__ uint32_t game_outcome_rng(const Params& p, uint64_t my_g, int c, uint32_t mine,
                                                      uint32_t theirs) {
