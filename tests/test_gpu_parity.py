@@ -213,3 +213,89 @@ def test_state_export(tmp_path):
     assert z["occ"].sum() == sim.counts()[1] and z["strat"].shape == (64, 64, 4)
     assert open(tmp_path / "w.ppm", "rb").read(2) == b"P6"
     sim.close()
+
+
+# ----------------------------------------------------------------------------- edge cases
+def test_empty_world():
+    _run(3, width=32, seed=1, init_agent_count=0)
+
+
+def test_single_agent_world():
+    _run(30, width=32, seed=2, init_agent_count=1)
+
+
+def test_full_world_no_free_cell():
+    """Every cell occupied: nobody can move or reproduce until deaths open cells."""
+    _run(25, width=32, seed=3, init_agent_count=32 * 32, max_agents=32 * 32, cost_of_living=4.0)
+
+
+def test_extinction():
+    """A cost of living that kills everybody: the population reaches 0 and stays there (exit condition, :1579-1588)."""
+    sim, orc = _pair(width=32, seed=4, cost_of_living=60.0)
+    try:
+        sim.init_population()
+        orc.init_population()
+        for s in range(4):
+            sim.step(1)
+            orc.step()
+            _compare(sim, orc, f"step {s}")
+        assert sim.counts()[1] == 0
+    finally:
+        sim.close()
+
+
+def test_no_children_allowed_and_non_negative_payoffs():
+    """max_children_per_step = 0 (:1054) and a payoff matrix without negative entries (nobody is ever at risk)."""
+    _run(40, width=64, seed=5, max_children_per_step=0, payoff_cd=0.0)
+    _run(70, width=64, seed=6, payoff_cd=0.5, payoff_dd=0.25)
+
+
+def test_cap_below_initial_population():
+    """max_agents below the initial population: every newborn is culled, olds are never culled."""
+    _run(40, width=64, seed=7, init_agent_count=1500, max_agents=1000, reproduce_min_energy=45.0, reproduce_cost=5.0)
+
+
+def test_skewed_strategy_weights_and_energy_parameters():
+    _run(50, width=64, seed=8, strategy_weights=[0.7, 0.1, 0.1, 0.1], init_energy_mu=80.0, init_energy_sigma=30.0,
+         init_energy_min=1.0, max_energy=120.0, reproduce_min_energy=90.0, strategy_per_trait=1, mutation_rate=0.5)
+
+
+def test_multi_step_call_equals_single_steps():
+    from pdabm_b200 import Simulation, SimConfig
+    a = Simulation(SimConfig(width=128, seed=9, env_noise=0.05))
+    b = Simulation(SimConfig(width=128, seed=9, env_noise=0.05))
+    try:
+        a.init_population()
+        b.init_population()
+        a.step(37)
+        for _ in range(37):
+            b.step(1, want_counts=False)
+        b.step(0)
+        pa, pb = a.planes(), b.planes()
+        for k in ("tf_raw", "energy", "strat"):
+            assert np.array_equal(pa[k], pb[k])
+        assert a.counts()[1] == b.counts()[1] and a.step_index == b.step_index == 37
+    finally:
+        a.close()
+        b.close()
+
+
+def test_host_buffer_step_roundtrip():
+    """pd_step_host (the e2e path): host planes in, host planes out == device-resident stepping."""
+    import torch
+    from pdabm_b200 import Simulation, SimConfig
+    a = Simulation(SimConfig(width=128, seed=10, mutation_rate=0.02))
+    b = Simulation(SimConfig(width=128, seed=10, mutation_rate=0.02))
+    try:
+        a.init_population()
+        b.init_population()
+        h_e, h_s, h_t = a.energy.cpu().pin_memory(), a.strat.cpu().pin_memory(), a.tf.cpu().pin_memory()
+        for s in range(8):
+            a.step(1)
+            counts_b, n_b = b.step_host(h_e, h_s, h_t, 1, h_e, h_s, h_t)
+            assert torch.equal(h_t, a.tf.cpu()) and torch.equal(h_e, a.energy.cpu())
+            ca, na = a.counts()
+            assert na == n_b and np.array_equal(ca, counts_b)
+    finally:
+        a.close()
+        b.close()
