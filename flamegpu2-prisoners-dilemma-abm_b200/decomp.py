@@ -171,6 +171,12 @@ class DecomposedWorld:
                 s.part(PD_PART_PRE, 0, wc)
             comm.allreduce([s.glb for s in slabs])
             for rnd in range(1, self.retry_rounds + 1):
+                # exit_god_fn (model.py:1614-1627) on the host, like the reference: another round only while the
+                # GLOBAL population is within the cap and somebody is still trying.  Reading three words back
+                # costs one stream synchronisation and saves 7 launches + 7 all-reduces in the saturated state.
+                olds, births, active = (int(v) for v in slabs[0].glb[:3].tolist())
+                if olds + births > self.cfg.max_agents or active == 0:
+                    break
                 for s in slabs:
                     s.part(PD_PART_RETRY, rnd, wc)
                 comm.allreduce([s.glb for s in slabs])
