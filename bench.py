@@ -199,7 +199,7 @@ def run_ours(args, rank, world, local_rank):
         cells = width * (height // world)              # owned cells per GPU
         desc += f"; one {width}x{height} world in {world} row slabs"
     else:
-        cfg = SimConfig(width=width, seed=12345 + rank, device=local_rank, **overrides)
+        cfg = SimConfig(width=width, seed=12345 + rank, device=local_rank, sparse_ctas=args.sparse_ctas, **overrides)
         sim = Simulation(cfg)
         one = sim
         cells = width * width
@@ -446,6 +446,7 @@ def main():
                     help="how N > 1 GPUs are used: row slabs of one world (default) or independent worlds")
     ap.add_argument("--width", type=int, default=0, help="override the workload's width (debug)")
     ap.add_argument("--presteps", type=int, default=80)
+    ap.add_argument("--sparse-ctas", type=int, default=0, help="CTAs of the sparse list kernels (0 = library default)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

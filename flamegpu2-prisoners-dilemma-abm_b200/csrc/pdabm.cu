@@ -300,9 +300,12 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     s->n_sms = prop.multiProcessorCount;
     s->big_tiles = W >= 128;
     s->grid = s->big_tiles ? dim3(W / 128, Hl / 16) : dim3(W / 16, Hl / 16);
-    s->sparse_auto = cfg->sparse_ctas <= 0;
+    // measured on B200 (profiles/README.md): one 1024-thread CTA wins up to 2^19 cells (no grid barriers),
+    // 16 CTAs up to 2^22 (0.283 -> 0.235 ms/step at 1024^2 and still co-schedulable with other runs'
+    // kernels in an ensemble), every SM beyond that
+    s->sparse_auto = cfg->sparse_ctas <= 0 && s->cells > ((size_t)1 << 22);
     if (cfg->sparse_ctas > 0) s->sparse_ctas = cfg->sparse_ctas;
-    else s->sparse_ctas = s->cells <= ((size_t)1 << 22) ? 1 : s->n_sms;
+    else s->sparse_ctas = s->cells <= ((size_t)1 << 19) ? 1 : s->cells <= ((size_t)1 << 22) ? 16 : s->n_sms;
     if (s->sparse_ctas > 1 && !prop.cooperativeLaunch) s->sparse_ctas = 1;
     s->sparse_threads = s->sparse_ctas == 1 ? 1024 : 512;
     if (s->sparse_ctas > s->n_sms) s->sparse_ctas = s->n_sms;
