@@ -113,8 +113,6 @@ __device__ __forceinline__ uint32_t game_outcome_rng(const Params& p, uint64_t m
 // (roll, cell) order) and gives both strategies of the game.  Games that need random words
 // (RANDOM strategy or noise) are queued warp-wide so that the Philox rounds run with full lanes.
 // ------------------------------------------------------------------------------------------
-__constant__ int c_dir_dx[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
-__constant__ int c_dir_dy[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
 
 constexpr uint32_t R_OCC = 0x80000000u;
 constexpr uint32_t R_DFLAG = 0x400u;
@@ -203,10 +201,15 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
     __shared__ uint8_t s_qo[NWARP][256];  // their outcomes
     __shared__ uint8_t s_q2[NWARP][256];  // second level: queue slots whose game needs random words
     __shared__ unsigned int s_n[4];       // 0 agents, 1 ring cells, 2 movers
+    // look-up tables in shared memory: an indexed constant load (LDC) goes through the address-divergence
+    // unit, which ncu shows 61 % busy in this kernel; LDS has headroom
+    __shared__ int s_off[8];              // shared-memory offset of neighbour d
+    __shared__ float s_pay[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const bool noisy = p.noise_thr != 0ull;
-    if (tid < 4) s_n[tid] = 0;
+    if (tid < 4) { s_n[tid] = 0; s_pay[tid] = p.pay[tid]; }
+    if (tid < 8) s_off[tid] = DY(tid) * SW + DX(tid);
     load_tile_vec<TW, TH, 1>(p, p.tfA, s_tf, x0, y0);
     load_tile_vec<TW, TH, 1>(p, p.strat, s_st, x0, y0);
     for (int i = tid; i < NC / 4; i += NT) {
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
             while (m) {
                 const int d = __ffs(m) - 1, c = 7 - d;
                 m &= m - 1;
-                const int sn = si + c_dir_dy[d] * SW + c_dir_dx[d];
+                const int sn = si + s_off[d];
                 const uint32_t rn = s_R[sn];
                 bool hi = (rn >> 11) > kme;
                 if ((rn >> 11) == kme) hi = exact_higher(p, x0 + lx, y0 + ly, d);
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
             if (active) {
                 const int si_l = (int)(pk & 0xFFFFu);
                 uint32_t mine, theirs;
-                game_strategies(s_R[si_l], s_R[si_l + c_dir_dy[d] * SW + c_dir_dx[d]], mine, theirs);
+                game_strategies(s_R[si_l], s_R[si_l + s_off[d]], mine, theirs);
                 need = noisy || mine == 3u || theirs == 3u;
                 s_qo[warp][q] = (uint8_t)(((mine != 1u) ? 2u : 0u) | ((theirs != 1u) ? 1u : 0u));
             }
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
             if (active) {
                 const int si_l = (int)(pk & 0xFFFFu), cl_l = (int)(pk >> 16);
                 uint32_t mine, theirs;
-                game_strategies(s_R[si_l], s_R[si_l + c_dir_dy[d] * SW + c_dir_dx[d]], mine, theirs);
+                game_strategies(s_R[si_l], s_R[si_l + s_off[d]], mine, theirs);
                 const uint64_t gl = gcell_of(p, x0 + (uint32_t)(cl_l & (TW - 1)), y0 + (uint32_t)(cl_l >> LOG_TW));
                 s_qo[warp][q] = (uint8_t)game_outcome_rng(p, gl, c, mine, theirs);
             }
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
             for (int c = 0; c < 8; ++c) {
                 if (!((gm >> c) & 1u) || dead) continue;
                 const uint32_t o = s_qo[warp][off + __popc(gm & ((1u << c) - 1u))];
-                e = __fadd_rn(e, p.pay[o & 3u]);                   // :679-688
+                e = __fadd_rn(e, s_pay[o & 3u]);                   // :679-688
                 if (e <= 0.0f) dead = true;                        // :695-697
                 else { e = fminf(e, p.max_energy); ++games; }      // :698-710
             }
@@ -442,7 +445,7 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
 // races on it writes the same value).  A claimant with direction d won iff the winner is 7-d.
 // ------------------------------------------------------------------------------------------
 template <int TW, int TH>
-__device__ __forceinline__ void scatter_claims(const uint8_t* s_tf, uint8_t* s_cl) {
+__device__ __forceinline__ void scatter_claims(const uint8_t* s_tf, uint8_t* s_cl, const int* s_dxy) {
     constexpr int SW = TW + 32, SH = TH + 4, NWORD = SH * SW / 4;
     // the tile is scanned 4 cells (one word) at a time; claimants are sparse (<= ~10 % of cells)
     for (int w = threadIdx.x; w < NWORD; w += NT) {
@@ -454,7 +457,7 @@ __device__ __forceinline__ void scatter_claims(const uint8_t* s_tf, uint8_t* s_c
             const int si = w * 4 + b;
             const int d = (int)(((t4 >> (8 * b)) & TF_DIR) >> TF_DIR_SHIFT);
             const int r = si / SW, c = si - r * SW;
-            const int rr = r + c_dir_dy[d], cc = c + c_dir_dx[d];
+            const int rr = r + s_dxy[8 + d], cc = c + s_dxy[d];  // (shared-memory LUT: LDC would go through the ADU)
             // only targets inside tile + 1-ring matter (rows 1..TH+2, columns 15..TW+16)
             if (rr < 1 || rr > TH + 2 || cc < 15 || cc > TW + 16) continue;
             const int st = rr * SW + cc;
@@ -522,14 +525,16 @@ __global__ void __launch_bounds__(NT, 8) k_move_commit(const __grid_constant__ P
     __shared__ uint16_t s_lost[NC];
     __shared__ uint8_t s_lost_state[NC];
     __shared__ unsigned int s_q[4];  // queue lengths: 0 claimants, 1 claimed cells
+    __shared__ int s_dxy[16], s_off[8];  // dx[8] dy[8]; shared-memory offset of neighbour d
     __shared__ unsigned int s_n[4];  // 1 lost, 2 base
     const int tid = threadIdx.x;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     if (tid < 4) s_n[tid] = s_q[tid] = 0;
+    if (tid < 8) { s_dxy[tid] = DX(tid); s_dxy[8 + tid] = DY(tid); s_off[tid] = DY(tid) * SW + DX(tid); }
     load_tile_vec<TW, TH, 2>(p, p.tfB, s_tf, x0, y0);
     for (int i = tid; i < SH * SW / 16; i += NT) reinterpret_cast<uint4*>(s_cl)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    scatter_claims<TW, TH>(s_tf, s_cl);
+    scatter_claims<TW, TH>(s_tf, s_cl, s_dxy);
     __syncthreads();
     for (int i = tid; i < NC / 4; i += NT) {
         const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
@@ -556,7 +561,7 @@ __global__ void __launch_bounds__(NT, 8) k_move_commit(const __grid_constant__ P
         const uint32_t t = s_tf[si];
         if (is_claim) {
             const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
-            const int st = si + c_dir_dy[d] * SW + c_dir_dx[d];
+            const int st = si + s_off[d];
             if (winner_of<TW>(p, s_cl, st, x0, y0, TravelKey()) == 7 - d) {
                 s_out[cl] = (uint8_t)TF_GHOST;  // moved away; still blocks movers this step (B-13)
             } else {                            // :940-943 -> retry with the same roll
@@ -566,7 +571,7 @@ __global__ void __launch_bounds__(NT, 8) k_move_commit(const __grid_constant__ P
             }
         } else {  // the winner relocates here (:946-956)
             const int j = winner_of<TW>(p, s_cl, si, x0, y0, TravelKey());
-            const uint32_t tn = s_tf[si + c_dir_dy[j] * SW + c_dir_dx[j]];
+            const uint32_t tn = s_tf[si + s_off[j]];
             const uint32_t x = x0 + lx, y = y0 + ly;
             const uint32_t src = nb_local(p, x, y, j);
             const size_t cell = ((size_t)y << p.log2W) | x;
@@ -673,14 +678,16 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
     __shared__ unsigned int s_bins[16];
     __shared__ unsigned int s_n[8];   // 0 claimants, 1 births listed, 2 lost, 3 risk, 4 dead, 5 n_old, 6 birth cells, 7 living deaths
     __shared__ unsigned int s_base[4];
+    __shared__ int s_dxy[16], s_off[8];  // dx[8] dy[8]; shared-memory offset of neighbour d
     const int tid = threadIdx.x;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     if (tid < 8) s_n[tid] = 0;
     if (tid < 16) s_bins[tid] = 0;
+    if (tid < 8) { s_dxy[tid] = DX(tid); s_dxy[8 + tid] = DY(tid); s_off[tid] = DY(tid) * SW + DX(tid); }
     load_tile_vec<TW, TH, 2>(p, p.tfB, s_tf, x0, y0);
     for (int i = tid; i < SH * SW / 16; i += NT) reinterpret_cast<uint4*>(s_cl)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    scatter_claims<TW, TH>(s_tf, s_cl);
+    scatter_claims<TW, TH>(s_tf, s_cl, s_dxy);
     __syncthreads();
     // ---- dense scan, 4 cells per thread
     unsigned int n_old = 0, n_dead = 0;
@@ -745,7 +752,7 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
         if (is_claim) {
             const uint32_t trait = t & TF_TRAIT;
             const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
-            const int st = si + c_dir_dy[d] * SW + c_dir_dx[d];
+            const int st = si + s_off[d];
             float e = p.E1[cell];
             if (winner_of<TW>(p, s_cl, st, x0, y0, ReproKey()) == 7 - d) {
                 e = __fsub_rn(e, p.reproduce_cost);  // :1211-1213
@@ -769,7 +776,7 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
             }
         } else {  // a child is born here (:1216-1328): the winner's trait, its own energy and strategies
             const int j = winner_of<TW>(p, s_cl, si, x0, y0, ReproKey());
-            const uint32_t tn = s_tf[si + c_dir_dy[j] * SW + c_dir_dx[j]];
+            const uint32_t tn = s_tf[si + s_off[j]];
             const uint32_t src = nb_local(p, x, y, j);
             const float pe = __fsub_rn(p.E1[src], p.reproduce_cost);
             float ce;
