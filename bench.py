@@ -192,17 +192,21 @@ def run_ours(args, rank, world, local_rank):
     if slabs:
         # one world, one row slab per GPU; square for config5, else width x (width * N) so that every
         # GPU owns the same 2^28 cells as the single-GPU run (weak scaling)
-        height = width if args.workload == "config5" else width * world
+        height = args.height or (width if args.workload == "config5" else width * world)
         cfg = SimConfig(width=width, height=height, seed=12345, device=local_rank, **overrides)
         sim = DecomposedWorld(cfg, DistComm())
         one = sim.slabs[0].sim
         cells = width * (height // world)              # owned cells per GPU
         desc += f"; one {width}x{height} world in {world} row slabs"
     else:
-        cfg = SimConfig(width=width, seed=12345 + rank, device=local_rank, sparse_ctas=args.sparse_ctas, **overrides)
+        height = args.height or width
+        cfg = SimConfig(width=width, height=height, seed=12345 + rank, device=local_rank, sparse_ctas=args.sparse_ctas,
+                        **overrides)
         sim = Simulation(cfg)
         one = sim
-        cells = width * width
+        cells = width * height
+        if height != width:
+            desc += f"; one {width}x{height} world"
     want_counts = args.workload not in ("config3", "config5")  # these log first/last only
 
     def barrier():
@@ -320,11 +324,13 @@ def run_ours(args, rank, world, local_rank):
     line = {
         "metric": "agent-steps/sec", "value": agent_steps / secs, "unit": "agent-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True,
+        "scaling": "strong" if (args.height or (slabs and args.workload == "config5")) else "weak",
+        "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": desc, "width": width, "cells": cells, "cells_per_gpu": cells,
                    "partitioning": ("row slabs of one world, one per GPU: NVLink halo exchange of 64 boundary rows x 3 planes "
-                                    "+ 11 small collectives per step" if slabs else
+                                    "+ 4 (gate closed) to 11 small collectives per step" if slabs else
                                     "one world per GPU (ensemble), no data-path collective" if world > 1 else "single world"),
                    "presteps": args.presteps, "agents_at_start": n_before, "agents_at_end": n_after,
                    "density": n_after / cells, "counts_every_step": want_counts,
@@ -445,6 +451,8 @@ def main():
     ap.add_argument("--partition", default="slabs", choices=["slabs", "ensemble"],
                     help="how N > 1 GPUs are used: row slabs of one world (default) or independent worlds")
     ap.add_argument("--width", type=int, default=0, help="override the workload's width (debug)")
+    ap.add_argument("--height", type=int, default=0,
+                    help="slabs: fixed world height in rows (strong scaling); default width * N (weak scaling)")
     ap.add_argument("--presteps", type=int, default=80)
     ap.add_argument("--sparse-ctas", type=int, default=0, help="CTAs of the sparse list kernels (0 = library default)")
     ap.add_argument("--e2e-steps", type=int, default=10)

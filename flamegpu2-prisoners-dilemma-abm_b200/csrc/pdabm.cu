@@ -490,6 +490,7 @@ int pd_bind_comm(pd_sim* s, uint64_t* glb, uint32_t* ghist, uint64_t* cand_out, 
                  uint32_t cand_cap, uint32_t world) {
     if (!s || !glb || !ghist || !cand_out || !cand_all || !cand_cap || !world) return fail(PD_ERR_INVALID, "NULL argument");
     if (!s->slab) return fail(PD_ERR_STATE, "pd_bind_comm is for row slabs (rows != width)");
+    if (world > PD_MAX_WORLD) return fail(PD_ERR_INVALID, "world %u exceeds PD_MAX_WORLD %d", world, PD_MAX_WORLD);
     s->P.glb = (unsigned long long*)glb;
     s->P.ghist = ghist;
     s->P.cand_out = (unsigned long long*)cand_out;

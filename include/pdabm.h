@@ -145,6 +145,7 @@ int pd_read_stats(pd_sim* sim, pd_step_stats* out, void* stream);
 #define PD_PART_APPLY 4
 #define PD_GLB_WORDS 20
 #define PD_HIST_WORDS 2048
+#define PD_MAX_WORLD 256   /* most slabs one world can be cut into */
 /* glb: PD_GLB_WORDS u64; ghist: PD_HIST_WORDS u32; cand_out: 1 + cand_cap u64; cand_all: world * (1 + cand_cap) u64;
  * all DEVICE buffers owned by the caller (torch tensors) so that it can run collectives on them. */
 int pd_bind_comm(pd_sim* sim, uint64_t* glb, uint32_t* ghist, uint64_t* cand_out, const uint64_t* cand_all,
