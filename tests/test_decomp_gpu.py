@@ -77,3 +77,42 @@ def test_non_square_world_slabs():
         ref.close()
         for d in decs:
             d.close()
+
+
+def test_full_size_2p28_slabs_equal_whole_world():
+    """BASELINE configs[2] at its full size (16384^2 = 2^28 cells, per-trait strategies), far beyond what
+    the oracle can follow: the size-independent properties are (a) the decomposed world (4 slabs, halo
+    exchange, global gate and cull) stays bit-identical to the whole world through growth, saturation and
+    the first culls, (b) the population bookkeeping closes every step, (c) one agent per cell, energies in
+    (0, max_energy], counts sum to the population, cap respected."""
+    from pdabm_b200 import Simulation, SimConfig, DecomposedWorld, LocalComm
+    kw = dict(width=16384, seed=12345, strategy_per_trait=1, collect_stats=True)
+    ref = Simulation(SimConfig(**kw))
+    dec = DecomposedWorld(SimConfig(**kw), LocalComm(4))
+    try:
+        ref.init_population()
+        dec.init_population()
+        culled = 0
+        for s in range(66):
+            ref.step(1)
+            dec.step(1)
+            st = ref.stats()
+            ca, na = ref.counts()
+            cb, nb = dec.counts()
+            assert na == nb and np.array_equal(ca, cb), f"step {s}: counts differ"
+            assert st["agents_end"] == na == ca.sum()
+            assert st["agents_end"] == (st["agents_start"] - st["play_deaths"] - st["travel_deaths"]
+                                        + st["births"] - st["culled"] - st["living_deaths"])
+            assert na <= ref.cfg.max_agents
+            culled += st["culled"]
+        assert culled > 0, "the run must reach the carrying capacity"
+        a, b = ref.planes(), dec.planes()
+        for k in ("occ", "trait", "strat", "energy"):
+            assert np.array_equal(a[k], b[k]), f"plane {k} differs"
+        occ = a["occ"].astype(bool)
+        assert int(occ.sum()) == na
+        e = a["energy"][occ]
+        assert e.min() > 0 and e.max() <= ref.cfg.max_energy
+    finally:
+        ref.close()
+        dec.close()
