@@ -202,7 +202,10 @@ def run_ours(args, rank, world, local_rank):
         height = args.height or width
         cfg = SimConfig(width=width, height=height, seed=12345 + rank, device=local_rank, sparse_ctas=args.sparse_ctas,
                         **overrides)
-        sim = Simulation(cfg)
+        # an explicit stream: worlds of <= 2^22 cells then replay one CUDA graph per step (pd_config.use_graphs)
+        run_stream = torch.cuda.Stream()
+        torch.cuda.set_stream(run_stream)
+        sim = Simulation(cfg, stream=run_stream)
         one = sim
         cells = width * height
         if height != width:
@@ -227,19 +230,30 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    one.set_profile(True)
+    # Large worlds: the per-kernel events sit inside the timed region (18 event records against ~10 ms of
+    # kernels).  Small worlds (graph replay) are timed without them and profiled in a second pass of K steps.
+    graphed = (not slabs) and cells <= (1 << 22)
+    one.set_profile(not graphed)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    rr0 = sim.retry_rounds_run if slabs else 0
+    gr0 = 0 if slabs else one.graph_replays()
     for _ in range(args.steps):
         sim.step(1, want_counts=want_counts)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    retry_rounds = (sim.retry_rounds_run - rr0) if slabs else 0
+    replays = 0 if slabs else one.graph_replays() - gr0
     clocks = sampler.stop() if rank == 0 else None
+    as1 = sim.agent_steps()
+    if graphed:
+        one.set_profile(True)
+        for _ in range(args.steps):
+            sim.step(1, want_counts=want_counts)
     kernel_ms, prof_steps = one.read_profile()   # rank 0's slab (all slabs do the same work)
     one.set_profile(False)
-    as1 = sim.agent_steps()
     counts, n_after = sim.counts()
     agent_steps = as1 - as0
 
@@ -347,7 +361,10 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_agents / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                 "call": "pd_step_host (host planes in, host planes + counts out)"},
-        "gpu_launches": (28 if slabs else 9) * args.steps,
+        # per step: 9 kernels (whole world; replayed as one CUDA graph on small worlds), or 12 + 2 per
+        # reproduction retry round that actually ran (row slab, this rank)
+        "gpu_launches": (12 * args.steps + 2 * retry_rounds) if slabs else 9 * args.steps,
+        "graph_replays": replays,
         "clocks": clocks,
         "init_and_presteps_s": init_s,
     }

@@ -48,7 +48,8 @@ class pd_config(C.Structure):
         ("sparse_ctas", C.c_int32),
         ("ghost_rows", C.c_uint32),
         ("world_height", C.c_uint32),
-        ("reserved", C.c_uint32 * 2),
+        ("use_graphs", C.c_int32),
+        ("reserved", C.c_uint32),
     ]
 
 
@@ -63,7 +64,7 @@ EXPORTS = (
     "pd_last_error", "pd_abi_version", "pd_default_config", "pd_create", "pd_destroy",
     "pd_bind_planes", "pd_init_population", "pd_sync_state", "pd_step", "pd_read_counts",
     "pd_read_stats", "pd_get_step", "pd_set_step", "pd_step_host", "pd_read_agent_steps",
-    "pd_set_profile", "pd_read_profile", "pd_bind_comm", "pd_step_part",
+    "pd_set_profile", "pd_read_profile", "pd_bind_comm", "pd_step_part", "pd_graph_replays",
 )
 
 _lib = None
@@ -118,6 +119,8 @@ def load() -> C.CDLL:
     lib.pd_bind_comm.argtypes = [vp, vp, vp, vp, vp, u32, u32]
     lib.pd_step_part.restype = i32
     lib.pd_step_part.argtypes = [vp, i32, i32, vp, i32]
+    lib.pd_graph_replays.restype = i32
+    lib.pd_graph_replays.argtypes = [vp, C.POINTER(u64)]
     lib.pd_debug_philox.restype = i32
     lib.pd_debug_philox.argtypes = [vp, vp, i32]
     _lib = lib

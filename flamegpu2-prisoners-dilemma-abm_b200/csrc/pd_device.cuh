@@ -69,6 +69,8 @@ struct Counters {
     unsigned int risk_n;
     unsigned int overflow;
     unsigned int barrier[2];
+    unsigned int step_no;  // model step being computed: the Philox key of every draw.  Device-resident so that
+    unsigned int pad2_;    // a captured CUDA graph of one step can be replayed (k_set_step / fin_bookkeeping)
     unsigned long long n_agents;
     unsigned long long agents_start;
     unsigned long long agent_steps;  // running sum of the population at the start of every step
@@ -80,7 +82,7 @@ struct Counters {
 struct Params {
     uint32_t W, H, row0, log2W;
     uint32_t HW;  // height of the whole world (power of two; == W for the reference's square worlds)
-    uint32_t k0, k1, step;
+    uint32_t k0, k1;
     float pay[4];  // index (i_coop << 1) | challenger_coop: {dd, dc, cd, cc} seen by the responder
     float max_energy, travel_cost, cost_of_living, reproduce_min_energy, reproduce_cost;
     float inherit, e_mu, e_sigma, e_min, risk_thr, mutation_rate;
@@ -118,7 +120,8 @@ struct Params {
 };
 
 __device__ __forceinline__ Words rng(const Params& p, uint64_t gcell, uint32_t stream) {
-    return philox4x32_10((uint32_t)gcell, (uint32_t)(gcell >> 32), p.step, stream, p.k0, p.k1);
+    // the step number only changes between kernels (end of k_finalize / k_fin_apply): read-only here
+    return philox4x32_10((uint32_t)gcell, (uint32_t)(gcell >> 32), __ldg(&p.ctr->step_no), stream, p.k0, p.k1);
 }
 __device__ __forceinline__ Words rng_init(const Params& p, uint64_t gcell, uint32_t stream) {
     return philox4x32_10((uint32_t)gcell, (uint32_t)(gcell >> 32), INIT_STEP, stream, p.k0, p.k1);

@@ -21,6 +21,8 @@
 namespace pd {
 
 // ------------------------------------------------------------------------------------------
+__global__ void k_set_step(Counters* ctr, unsigned int step) { ctr->step_no = step; }
+
 __global__ void k_begin_step(Counters* ctr, int count_step) {
     // zero everything up to (not including) risk_n
     unsigned int* w = reinterpret_cast<unsigned int*>(ctr);
@@ -525,6 +527,7 @@ __device__ __forceinline__ void fin_bookkeeping(const Params& p) {
     s[4] = __ldcg(&ctr->st_moved); s[5] = __ldcg(&ctr->st_travel_deaths);
     s[6] = b; s[7] = culled; s[8] = ld;
     s[9] = rn; s[10] = __ldcg(&ctr->mv_n); s[11] = __ldcg(&ctr->rp_n);
+    ctr->step_no += 1u;  // the step is complete
     if (p.glb) {  // publish this slab's totals; the caller sums them over the slabs when it wants them
         p.glb[3] = ctr->n_agents;
         for (int k = 0; k < 16; ++k) p.glb[4 + k] = p.want_counts ? ctr->last_bins[k] : 0ull;

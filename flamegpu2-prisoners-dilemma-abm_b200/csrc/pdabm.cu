@@ -87,14 +87,26 @@ struct pd_sim {
     size_t ev_used;                // events used (2 per pair)
     double kernel_ms[9];
     uint32_t prof_steps;
+    bool step_dirty;               // host step number not yet written to Counters::step_no
+    // CUDA graphs of one whole step (9 launches), one per (at-risk list parity, want_counts); used for worlds
+    // small enough that launch latency matters, on explicit (capturable) streams, when profiling is off
+    bool graphs;
+    cudaGraphExec_t gexec[4];
+    uint64_t graph_replays;
 };
 
 namespace {
+
+void drop_graphs(pd_sim* s) {  // the captured launches hold plane / list pointers by value
+    for (cudaGraphExec_t& g : s->gexec)
+        if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+}
 
 int alloc_lists(pd_sim* s, uint64_t n_agents_hint) {
     if (s->lists_allocated) {
         if (n_agents_hint + 1024 <= s->P.list_cap || s->P.list_cap == s->cells) return PD_OK;
         // grow: free and reallocate
+        drop_graphs(s);
         cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.risk_roll);
         cudaFree(s->P.mv_cell); cudaFree(s->P.mv_state); cudaFree(s->P.mv_aux);
         cudaFree(s->P.rp_cell); cudaFree(s->P.rp_state); cudaFree(s->P.rp_aux);
@@ -180,6 +192,63 @@ int prof_end(pd_sim* s, cudaStream_t st) {
         if ((rc = prof_end(s, st))) return rc;               \
     } while (0)
 
+int push_step(pd_sim* s, cudaStream_t st) {
+    if (!s->step_dirty) return PD_OK;
+    k_set_step<<<1, 1, 0, st>>>(s->P.ctr, s->step);
+    CK(cudaGetLastError());
+    s->step_dirty = false;
+    return PD_OK;
+}
+
+// the 9 launches of one model step, in the order of the reference's main layers (model.py:2140-2163)
+int launch_step(pd_sim* s, cudaStream_t st) {
+    Params& P = s->P;
+    int rc = PD_OK;
+    PROF(0, (k_begin_step<<<1, 256, 0, st>>>(P.ctr, 1)));
+    PROF(1, { if ((rc = launch_sparse(s, k_risk_resolve, st))) return rc; });
+    PROF(2, { if (s->big_tiles) k_play_travel<128, 16><<<s->grid, NT, 0, st>>>(P);
+              else k_play_travel<16, 16><<<s->grid, NT, 0, st>>>(P); });
+    PROF(3, { if (s->big_tiles) k_move_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
+              else k_move_commit<16, 16><<<s->grid, NT, 0, st>>>(P); });
+    PROF(4, { if ((rc = launch_sparse(s, k_move_retry, st))) return rc; });
+    PROF(5, { if (s->big_tiles) k_repro_claim<128, 16><<<s->grid, NT, 0, st>>>(P);
+              else k_repro_claim<16, 16><<<s->grid, NT, 0, st>>>(P); });
+    PROF(6, { if (s->big_tiles) k_repro_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
+              else k_repro_commit<16, 16><<<s->grid, NT, 0, st>>>(P); });
+    PROF(7, { if ((rc = launch_sparse(s, k_repro_retry, st))) return rc; });
+    PROF(8, { if ((rc = launch_sparse(s, k_finalize, st))) return rc; });
+    return PD_OK;
+}
+
+// Replay (capturing on first use) the graph of one step for the current Params.  Returns PD_OK with
+// *done = false when graphs cannot be used on this stream -- the caller then launches directly.
+int graph_step(pd_sim* s, cudaStream_t st, bool* done) {
+    *done = false;
+    if (!s->graphs || s->profile || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return PD_OK;
+    const int idx = s->risk_cur * 2 + (s->P.want_counts ? 1 : 0);
+    if (!s->gexec[idx]) {
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+        int rc = PD_OK;
+        if (e == cudaSuccess) {
+            rc = launch_step(s, st);
+            e = cudaStreamEndCapture(st, &g);
+        }
+        if (e == cudaSuccess && rc == PD_OK) e = cudaGraphInstantiate(&s->gexec[idx], g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (e != cudaSuccess || rc != PD_OK) {  // not capturable here: fall back to plain launches for good
+            cudaGetLastError();
+            s->gexec[idx] = nullptr;
+            s->graphs = false;
+            return PD_OK;
+        }
+    }
+    CK(cudaGraphLaunch(s->gexec[idx], st));
+    s->graph_replays += 1;
+    *done = true;
+    return PD_OK;
+}
+
 int run_scan(pd_sim* s, cudaStream_t st) {
     s->P.risk_cur = s->risk[s->risk_cur];
     s->P.risk_next = s->risk[s->risk_cur ^ 1];
@@ -225,6 +294,7 @@ int pd_default_config(pd_config* c, uint32_t width) {
     c->collect_stats = 0;
     c->device = 0;
     c->sparse_ctas = 0;
+    c->use_graphs = 0;
     return PD_OK;
 }
 
@@ -310,6 +380,8 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     s->sparse_threads = s->sparse_ctas == 1 ? 1024 : 512;
     if (s->sparse_ctas > s->n_sms) s->sparse_ctas = s->n_sms;
     P.sparse_ctas = (uint32_t)s->sparse_ctas;
+    s->graphs = cfg->use_graphs > 0 || (cfg->use_graphs == 0 && !slab && s->cells <= ((size_t)1 << 22));
+    if (slab) s->graphs = false;  // a slab is stepped in parts with host decisions in between
     CK(cudaMalloc(&P.E1, s->cells * sizeof(float)));
     CK(cudaMalloc(&P.tfB, s->cells));
     CK(cudaMalloc(&P.ctr, sizeof(Counters)));
@@ -324,6 +396,7 @@ int pd_destroy(pd_sim* s) {
     if (!s) return PD_OK;
     cudaSetDevice(s->cfg.device);
     cudaDeviceSynchronize();
+    drop_graphs(s);
     cudaFree(s->P.E1); cudaFree(s->P.tfB); cudaFree(s->P.ctr);
     if (s->lists_allocated) {
         cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.risk_roll);
@@ -349,6 +422,7 @@ int pd_bind_planes(pd_sim* s, float* energy, uint8_t* strat, uint8_t* tf) {
     for (int i = 0; i < 3; ++i)
         if (((uintptr_t)ptrs[i]) & 15u) return fail(PD_ERR_INVALID, "plane %d is not 16-byte aligned", i);
     s->P.E0 = energy; s->P.strat = strat; s->P.tfA = tf;
+    drop_graphs(s);
     s->bound = true;
     s->ready = false;
     return PD_OK;
@@ -415,6 +489,7 @@ int pd_init_population(pd_sim* s, uint64_t n_agents, void* stream) {
     k_init_write<<<blocks, NT, 0, st>>>(s->P, s->cells, tau, none);
     CK(cudaGetLastError());
     s->step = 0;
+    s->step_dirty = true;
     rc = run_scan(s, st);
     if (rc) return rc;
     s->ready = true;
@@ -426,26 +501,16 @@ int pd_step(pd_sim* s, uint32_t n_steps, void* stream, int want_counts) {
     if (s->slab) return fail(PD_ERR_STATE, "a row slab is stepped with pd_step_part (the caller exchanges ghost rows and sums in between)");
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(s->cfg.device));
+    int rc = push_step(s, st);
+    if (rc) return rc;
     for (uint32_t k = 0; k < n_steps; ++k) {
         Params& P = s->P;
-        P.step = s->step;
         P.want_counts = (want_counts && k + 1 == n_steps) ? 1u : 0u;
         P.risk_cur = s->risk[s->risk_cur];
         P.risk_next = s->risk[s->risk_cur ^ 1];
-        int rc = PD_OK;
-        PROF(0, (k_begin_step<<<1, 256, 0, st>>>(P.ctr, 1)));
-        PROF(1, { if ((rc = launch_sparse(s, k_risk_resolve, st))) return rc; });
-        PROF(2, { if (s->big_tiles) k_play_travel<128, 16><<<s->grid, NT, 0, st>>>(P);
-                  else k_play_travel<16, 16><<<s->grid, NT, 0, st>>>(P); });
-        PROF(3, { if (s->big_tiles) k_move_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
-                  else k_move_commit<16, 16><<<s->grid, NT, 0, st>>>(P); });
-        PROF(4, { if ((rc = launch_sparse(s, k_move_retry, st))) return rc; });
-        PROF(5, { if (s->big_tiles) k_repro_claim<128, 16><<<s->grid, NT, 0, st>>>(P);
-                  else k_repro_claim<16, 16><<<s->grid, NT, 0, st>>>(P); });
-        PROF(6, { if (s->big_tiles) k_repro_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
-                  else k_repro_commit<16, 16><<<s->grid, NT, 0, st>>>(P); });
-        PROF(7, { if ((rc = launch_sparse(s, k_repro_retry, st))) return rc; });
-        PROF(8, { if ((rc = launch_sparse(s, k_finalize, st))) return rc; });
+        bool replayed = false;
+        if ((rc = graph_step(s, st, &replayed))) return rc;
+        if (!replayed && (rc = launch_step(s, st))) return rc;
         s->risk_cur ^= 1;
         s->step += 1;
     }
@@ -507,11 +572,11 @@ int pd_step_part(pd_sim* s, int part, int arg, void* stream, int want_counts) {
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(s->cfg.device));
     Params& P = s->P;
-    P.step = s->step;
+    int rc = push_step(s, st);
+    if (rc) return rc;
     P.want_counts = want_counts ? 1u : 0u;
     P.risk_cur = s->risk[s->risk_cur];
     P.risk_next = s->risk[s->risk_cur ^ 1];
-    int rc = PD_OK;
     switch (part) {
     case PD_PART_PRE: {
         // ghost rows were just refreshed by the caller: their at-risk agents join the list
@@ -591,6 +656,12 @@ int pd_read_agent_steps(pd_sim* s, uint64_t* agent_steps, void* stream) {
     return PD_OK;
 }
 
+int pd_graph_replays(pd_sim* s, uint64_t* steps) {
+    if (!s || !steps) return fail(PD_ERR_INVALID, "NULL argument");
+    *steps = s->graph_replays;
+    return PD_OK;
+}
+
 int pd_get_step(pd_sim* s, uint32_t* step) {
     if (!s || !step) return fail(PD_ERR_INVALID, "NULL argument");
     *step = s->step;
@@ -599,6 +670,7 @@ int pd_get_step(pd_sim* s, uint32_t* step) {
 int pd_set_step(pd_sim* s, uint32_t step) {
     if (!s) return fail(PD_ERR_INVALID, "NULL argument");
     s->step = step;
+    s->step_dirty = true;  // written to the device at the start of the next step call, on its stream
     return PD_OK;
 }
 

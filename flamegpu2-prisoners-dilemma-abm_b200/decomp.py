@@ -134,6 +134,7 @@ class DecomposedWorld:
         self.cfg, self.comm = cfg, comm
         self.retry_rounds = retry_rounds
         self.slabs = [_Slab(cfg, r, comm.world, ghost_rows, cand_cap, stream) for r in comm.local_ranks]
+        self.retry_rounds_run = 0  # reproduction retry rounds executed so far (2 launches + 1 all-reduce each)
         self._counts = None
 
     def close(self):
@@ -180,6 +181,7 @@ class DecomposedWorld:
                 for s in slabs:
                     s.part(PD_PART_RETRY, rnd, wc)
                 comm.allreduce([s.glb for s in slabs])
+                self.retry_rounds_run += 1
             for s in slabs:
                 s.part(PD_PART_HIST, 0, wc)
             comm.allreduce([s.ghist for s in slabs])

@@ -146,6 +146,9 @@ def simulate(cfg: SimConfig, steps: int, log_file: Optional[str] = None,
              output_every_n_steps: int = 1, stream=None, verbose: bool = False) -> StepLog:
     """The step loop of ``simulation.simulate()`` (model.py:2176): init_fn, then per step the
     pipeline + step_fn + exit_condition_fn (model.py:1579-1588), logging every N steps."""
+    if stream is None:  # an explicit stream lets small worlds replay one CUDA graph per step
+        import torch
+        stream = torch.cuda.Stream(device=cfg.device)
     sim = Simulation(cfg, stream=stream)
     try:
         sim.init_population()

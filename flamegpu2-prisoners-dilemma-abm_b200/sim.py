@@ -51,6 +51,7 @@ class SimConfig:
     device: int = 0
     collect_stats: bool = False
     sparse_ctas: int = 0
+    use_graphs: int = 0                    # 0 auto, 1 always, -1 never (one CUDA graph per step; needs a stream)
 
     def __post_init__(self):
         if self.height < 0:
@@ -84,6 +85,7 @@ class SimConfig:
         c.collect_stats = int(bool(self.collect_stats))
         c.device = int(self.device)
         c.sparse_ctas = int(self.sparse_ctas)
+        c.use_graphs = int(self.use_graphs)
         return c
 
 
@@ -189,6 +191,12 @@ class Simulation:
         """Sum over executed steps of the population at the start of the step."""
         v = C.c_uint64()
         self._check(self.lib.pd_read_agent_steps(self._h, C.byref(v), self.stream_ptr))
+        return int(v.value)
+
+    def graph_replays(self) -> int:
+        """Steps run by replaying a captured CUDA graph (small worlds on an explicit stream)."""
+        v = C.c_uint64()
+        self._check(self.lib.pd_graph_replays(self._h, C.byref(v)))
         return int(v.value)
 
     def set_profile(self, on: bool):

@@ -77,7 +77,10 @@ typedef struct pd_config {
     uint32_t ghost_rows;            /* row slab only: ghost rows above AND below (multiple of 16, >= 64) */
     uint32_t world_height;          /* 0 = width (square, like the reference); else a power of two: the world is
                                        width x world_height cells (used for weak-scaling series of row slabs) */
-    uint32_t reserved[2];
+    int32_t use_graphs;             /* 0 = auto (whole worlds <= 2^22 cells), 1 = always, -1 = never: replay one
+                                       captured CUDA graph per step instead of 9 launches.  Only on explicit
+                                       (capturable) streams and while per-kernel profiling is off. */
+    uint32_t reserved;
 } pd_config;
 
 /* Per-step event counters of the LAST executed step (debug / parity aid; the
@@ -167,6 +170,10 @@ int pd_read_profile(pd_sim* sim, double kernel_ms[PDABM_NUM_KERNELS], uint32_t* 
 /* Step index of the next step to run (0-based; Philox counter word 2). */
 int pd_get_step(pd_sim* sim, uint32_t* step);
 int pd_set_step(pd_sim* sim, uint32_t step);
+
+/* Number of model steps this handle ran by replaying a captured CUDA graph (pd_config.use_graphs)
+ * rather than by launching the 9 kernels one by one. */
+int pd_graph_replays(pd_sim* sim, uint64_t* steps);
 
 /* HOST-buffer entry point (what a host-side caller without device buffers binds):
  * uploads the three planes from host memory, runs n_steps, downloads the planes back
