@@ -112,7 +112,7 @@ struct Params {
     uint32_t* risk_cur; uint32_t* risk_next; float* risk_e; uint32_t* risk_roll;
     uint32_t* mv_cell; uint8_t* mv_state; uint8_t* mv_aux;
     uint32_t* rp_cell; uint8_t* rp_state; uint8_t* rp_aux;
-    uint32_t* nb_cell; uint32_t* nb_prio;
+    uint32_t* nb_cell;
     float* nb_e; uint16_t* nb_gene;  // the newborn's energy and strategies | trait << 8 (it is written into the
                                      // planes only if it survives the cull, or when retry rounds must see it)
     uint32_t* dead_cell;  // aliases mv_cell (the travel rounds are over when it is filled)

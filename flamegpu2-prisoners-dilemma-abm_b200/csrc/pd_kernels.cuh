@@ -302,9 +302,11 @@ __global__ void __launch_bounds__(1024) k_repro_retry(const __grid_constant__ Pa
 // Whole world: one kernel (k_finalize).  Row slabs: three kernels (k_fin_hist, k_fin_cand,
 // k_fin_apply) with the caller summing the histogram and gathering the candidates in between.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long cull_key(const Params& p, uint32_t cell, uint32_t prio) {
+// The priority is recomputed wherever it is needed instead of being stored per newborn: the sparse
+// kernels wait on memory (issue slots ~11 % busy), a Philox call is cheaper than a list round trip.
+__device__ __forceinline__ unsigned long long cull_key(const Params& p, uint32_t cell) {
     const uint64_t g = gcell_of(p, cell & (p.W - 1), cell >> p.log2W);
-    return ((unsigned long long)prio << 32) | (uint32_t)g;
+    return ((unsigned long long)rng(p, g, S_CULL).x << 32) | (uint32_t)g;
 }
 
 struct CullPlan {
@@ -324,7 +326,7 @@ __device__ __forceinline__ CullPlan cull_plan(const Params& p) {
     return c;
 }
 
-// pass A: priorities of this slab's newborns + histogram of their top 11 bits into `hist` (global memory)
+// pass A: histogram of the top 11 key bits of this slab's newborns into `hist` (global memory)
 __device__ __forceinline__ void fin_hist(const Params& p, unsigned int nb, unsigned int* hist, unsigned int* s_hist) {
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -337,9 +339,7 @@ __device__ __forceinline__ void fin_hist(const Params& p, unsigned int nb, unsig
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (i + u * stride >= nb) continue;
-            const uint32_t prio = rng(p, gcell_of(p, cell[u] & (p.W - 1), cell[u] >> p.log2W), S_CULL).x;
-            p.nb_prio[i + u * stride] = prio;
-            atomicAdd(&s_hist[prio >> 21], 1u);
+            atomicAdd(&s_hist[(unsigned int)(cull_key(p, cell[u]) >> 53)], 1u);
         }
     }
     __syncthreads();
@@ -453,7 +453,7 @@ __device__ __forceinline__ void fin_apply(const Params& p, unsigned int nb, unsi
         if (i < nb) {
             const uint32_t cell = p.nb_cell[i];
             bool survive = true;
-            if (cull) survive = keep != 0 && cull_key(p, cell, p.nb_prio[i]) >= tau;
+            if (cull) survive = keep != 0 && cull_key(p, cell) >= tau;
             if (survive) {  // only now does the newborn enter the planes
                 const uint32_t gene = p.nb_gene[i];
                 const float ce = p.nb_e[i];
@@ -483,11 +483,15 @@ __device__ __forceinline__ void fin_apply(const Params& p, unsigned int nb, unsi
         if (i < nrp) {
             const uint32_t cell = p.rp_cell[i];
             if (row_owned(p, cell >> p.log2W)) {
-                const uint32_t t = __ldcg(p.tfA + cell);
+                // No retry round ran (gate closed, the saturated state): the flag byte is still canonical and
+                // is neither read nor rewritten (listing the energy too was tried: it costs k_repro_commit
+                // more than it saves here).
                 float e = __ldcg(p.E0 + cell);
+                const bool need_t = flagged || p.want_counts;
+                const uint32_t t = need_t ? __ldcg(p.tfA + cell) : 0u;
                 if (punish(p, e)) {
                     p.E0[cell] = e;
-                    p.tfA[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
+                    if (flagged) p.tfA[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
                     at_risk = e <= p.risk_thr;
                     if (p.want_counts) atomicAdd(&ctr->bins[count_bin(__ldcg(p.strat + cell), t & TF_TRAIT)], 1ull);
                 } else {
@@ -555,7 +559,7 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Param
         const unsigned int digit = fin_digit(g_hist, plan.keep, s_hist, &s_digit, &s_krem);
         for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nb; i0 += stride) {
             const unsigned int i = i0 + threadIdx.x;
-            const bool is_cand = i < nb && (p.nb_prio[i] >> 21) == digit;
+            const bool is_cand = i < nb && (unsigned int)(cull_key(p, p.nb_cell[i]) >> 53) == digit;
             const uint32_t slot = warp_append(&ctr->cand_n, is_cand);
             if (is_cand) cand[slot] = i;
         }
@@ -564,7 +568,7 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Param
             const unsigned int nc = __ldcg(&ctr->cand_n);
             const unsigned long long t = fin_select(nc, digit, s_hist, &s_prefix, &s_krem, [&](unsigned int k) {
                 const unsigned int i = __ldcg(&cand[k]);
-                return cull_key(p, p.nb_cell[i], p.nb_prio[i]);
+                return cull_key(p, p.nb_cell[i]);
             });
             if (threadIdx.x == 0) ctr->tau = t;
         }
@@ -607,10 +611,11 @@ __global__ void __launch_bounds__(1024) k_fin_cand(const __grid_constant__ Param
     const unsigned int digit = fin_digit(p.ghist, plan.keep, s_hist, &s_digit, &s_krem);
     for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nb; i0 += stride) {
         const unsigned int i = i0 + threadIdx.x;
-        const bool is_cand = i < nb && (p.nb_prio[i] >> 21) == digit;
+        const unsigned long long key = i < nb ? cull_key(p, p.nb_cell[i]) : 0ull;
+        const bool is_cand = i < nb && (unsigned int)(key >> 53) == digit;
         const uint32_t slot = warp_append(&ctr->cand_n, is_cand);
         if (is_cand) {
-            if (slot < p.cand_cap) p.cand_out[1 + slot] = cull_key(p, p.nb_cell[i], p.nb_prio[i]);
+            if (slot < p.cand_cap) p.cand_out[1 + slot] = key;
             else atomicExch(&ctr->overflow, 1u);
         }
     }

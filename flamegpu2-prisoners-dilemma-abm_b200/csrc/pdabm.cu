@@ -110,7 +110,7 @@ int alloc_lists(pd_sim* s, uint64_t n_agents_hint) {
         cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.risk_roll);
         cudaFree(s->P.mv_cell); cudaFree(s->P.mv_state); cudaFree(s->P.mv_aux);
         cudaFree(s->P.rp_cell); cudaFree(s->P.rp_state); cudaFree(s->P.rp_aux);
-        cudaFree(s->P.nb_cell); cudaFree(s->P.nb_prio); cudaFree(s->P.nb_e); cudaFree(s->P.nb_gene);
+        cudaFree(s->P.nb_cell); cudaFree(s->P.nb_e); cudaFree(s->P.nb_gene);
         s->lists_allocated = false;
     }
     // this handle's share of the global cap (+25 % for density fluctuations between slabs; an overflow
@@ -133,7 +133,6 @@ int alloc_lists(pd_sim* s, uint64_t n_agents_hint) {
     CK(cudaMalloc(&s->P.rp_state, cap));
     CK(cudaMalloc(&s->P.rp_aux, cap));
     CK(cudaMalloc(&s->P.nb_cell, cap * 4));
-    CK(cudaMalloc(&s->P.nb_prio, cap * 4));
     CK(cudaMalloc(&s->P.nb_e, cap * 4));
     CK(cudaMalloc(&s->P.nb_gene, cap * 2));
     s->lists_allocated = true;
@@ -402,7 +401,7 @@ int pd_destroy(pd_sim* s) {
         cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.risk_roll);
         cudaFree(s->P.mv_cell); cudaFree(s->P.mv_state); cudaFree(s->P.mv_aux);
         cudaFree(s->P.rp_cell); cudaFree(s->P.rp_state); cudaFree(s->P.rp_aux);
-        cudaFree(s->P.nb_cell); cudaFree(s->P.nb_prio); cudaFree(s->P.nb_e); cudaFree(s->P.nb_gene);
+        cudaFree(s->P.nb_cell); cudaFree(s->P.nb_e); cudaFree(s->P.nb_gene);
     }
     cudaFreeHost(s->h);
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
