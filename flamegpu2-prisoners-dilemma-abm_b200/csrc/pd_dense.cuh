@@ -152,14 +152,17 @@ __device__ __forceinline__ uint32_t nonzero_bytes(uint32_t v) {
     return (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
 }
 
-// Reserve slots in up to four shared-memory lists with ONE warp scan: byte k of `n` is the number of
-// entries (<= 4) this lane appends to list k, cnt[k] is that list's counter.  The start offsets come
-// back in off[k].  All 32 lanes must call.  Measured: 5 % faster than per-cell shared atomics in
-// k_move_commit; no gain in k_repro_claim / k_repro_commit, which keep the atomics (profiles/README.md).
-template <int NL>
+// Reserve slots in up to 32/BITS shared-memory lists with ONE warp scan: field k (BITS wide) of `n` is the
+// number of entries this lane appends to list k, cnt[k] is that list's counter; the warp's sum per field
+// must fit in BITS bits.  The start offsets come back in off[k].  All 32 lanes must call.
+// Measured: faster than per-cell shared atomics in k_move_commit; no gain in k_repro_claim /
+// k_repro_commit, which keep the atomics (profiles/README.md).
+template <int NL, int BITS>
 __device__ __forceinline__ void wreserve(unsigned int* cnt, uint32_t n, uint32_t (&off)[NL]) {
+    static_assert(NL * BITS <= 32, "packed counters");
+    constexpr uint32_t FM = BITS == 32 ? 0xFFFFFFFFu : ((1u << BITS) - 1u);
     const int lane = threadIdx.x & 31;
-    uint32_t incl = n;  // a warp adds at most 128 per byte: no carry between the packed counters
+    uint32_t incl = n;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t v = __shfl_up_sync(FULL, incl, o);
@@ -172,11 +175,11 @@ __device__ __forceinline__ void wreserve(unsigned int* cnt, uint32_t n, uint32_t
     const uint32_t excl = incl - n;
     uint32_t base = 0;
     if (lane < NL) {
-        const uint32_t t = (total >> (8 * lane)) & 0xFFu;
+        const uint32_t t = (total >> (BITS * lane)) & FM;
         if (t) base = atomicAdd(&cnt[lane], t);
     }
 #pragma unroll
-    for (int k = 0; k < NL; ++k) off[k] = __shfl_sync(FULL, base, k) + ((excl >> (8 * k)) & 0xFFu);
+    for (int k = 0; k < NL; ++k) off[k] = __shfl_sync(FULL, base, k) + ((excl >> (BITS * k)) & FM);
 }
 
 // strategies of the game between me (word rme) and the neighbour (word rn) as I, the responder, see it
@@ -444,24 +447,36 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
 // computes on demand (and caches by collapsing the byte to the winner's bit -- every thread that
 // races on it writes the same value).  A claimant with direction d won iff the winner is 7-d.
 // ------------------------------------------------------------------------------------------
-template <int TW, int TH>
+template <int TW, int TH, int CELLS>
 __device__ __forceinline__ void scatter_claims(const uint8_t* s_tf, uint8_t* s_cl, const int* s_dxy) {
-    constexpr int SW = TW + 32, SH = TH + 4, NWORD = SH * SW / 4;
-    // the tile is scanned 4 cells (one word) at a time; claimants are sparse (<= ~10 % of cells)
-    for (int w = threadIdx.x; w < NWORD; w += NT) {
-        const uint32_t t4 = reinterpret_cast<const uint32_t*>(s_tf)[w];
-        uint32_t cm = t4 & 0x40404040u;
-        while (cm) {
-            const int b = (__ffs(cm) - 1) >> 3;
-            cm &= cm - 1;
-            const int si = w * 4 + b;
-            const int d = (int)(((t4 >> (8 * b)) & TF_DIR) >> TF_DIR_SHIFT);
-            const int r = si / SW, c = si - r * SW;
-            const int rr = r + s_dxy[8 + d], cc = c + s_dxy[d];  // (shared-memory LUT: LDC would go through the ADU)
-            // only targets inside tile + 1-ring matter (rows 1..TH+2, columns 15..TW+16)
-            if (rr < 1 || rr > TH + 2 || cc < 15 || cc > TW + 16) continue;
-            const int st = rr * SW + cc;
-            atomicOr(reinterpret_cast<unsigned int*>(s_cl) + (st >> 2), (1u << (7 - d)) << (8 * (st & 3)));
+    // the tile is scanned CELLS (4 or 16) cells per thread at a time; claimants are sparse (<= ~10 % of cells).
+    // Measured: 16 is faster in k_move_commit (4 % claimants), 4 in k_repro_commit (5 %, longer work per claim).
+    constexpr int SW = TW + 32, SH = TH + 4, NW = CELLS / 4, NCHUNK = SH * SW / CELLS;
+    static_assert(SW % CELLS == 0 && (CELLS == 4 || CELLS == 16), "a chunk stays inside one row");
+    for (int w = threadIdx.x; w < NCHUNK; w += NT) {
+        uint32_t tw[NW];
+        if (CELLS == 16) {
+            const uint4 t16 = reinterpret_cast<const uint4*>(s_tf)[w];
+            tw[0] = t16.x; tw[NW > 1 ? 1 : 0] = t16.y; tw[NW > 2 ? 2 : 0] = t16.z; tw[NW > 3 ? 3 : 0] = t16.w;
+            if (!((t16.x | t16.y | t16.z | t16.w) & 0x40404040u)) continue;
+        } else {
+            tw[0] = reinterpret_cast<const uint32_t*>(s_tf)[w];
+        }
+        const int r = (w * CELLS) / SW, c0 = w * CELLS - r * SW;
+#pragma unroll
+        for (int h = 0; h < NW; ++h) {
+            uint32_t cm = tw[h] & 0x40404040u;
+            while (cm) {
+                const int b = (__ffs(cm) - 1) >> 3;
+                cm &= cm - 1;
+                const int d = (int)(((tw[h] >> (8 * b)) & TF_DIR) >> TF_DIR_SHIFT);
+                const int c = c0 + h * 4 + b;
+                const int rr = r + s_dxy[8 + d], cc = c + s_dxy[d];  // (shared-memory LUT: LDC would go through the ADU)
+                // only targets inside tile + 1-ring matter (rows 1..TH+2, columns 15..TW+16)
+                if (rr < 1 || rr > TH + 2 || cc < 15 || cc > TW + 16) continue;
+                const int st = rr * SW + cc;
+                atomicOr(reinterpret_cast<unsigned int*>(s_cl) + (st >> 2), (1u << (7 - d)) << (8 * (st & 3)));
+            }
         }
     }
 }
@@ -534,21 +549,26 @@ __global__ void __launch_bounds__(NT, 8) k_move_commit(const __grid_constant__ P
     load_tile_vec<TW, TH, 2>(p, p.tfB, s_tf, x0, y0);
     for (int i = tid; i < SH * SW / 16; i += NT) reinterpret_cast<uint4*>(s_cl)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    scatter_claims<TW, TH>(s_tf, s_cl, s_dxy);
+    scatter_claims<TW, TH, 16>(s_tf, s_cl, s_dxy);
     __syncthreads();
-    for (int i = tid; i < NC / 4; i += NT) {
-        const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
+    // 8 cells per thread: one pass over the tile.  Claimants are queued from the front of s_work, claimed
+    // cells from the back -- two homogeneous queues -- with slots from one packed warp scan.
+    for (int i = tid; i < NC / 8; i += NT) {
+        const int ly = (i * 8) / TW, lx = (i * 8) - ly * TW;
         const int si = (ly + 2) * SW + lx + 16;
-        const uint32_t t4 = *reinterpret_cast<const uint32_t*>(s_tf + si);
-        const uint32_t c4 = *reinterpret_cast<const uint32_t*>(s_cl + si);
-        reinterpret_cast<uint32_t*>(s_out)[i] = t4 & 0x87878787u;  // OCC | GHOST | trait
-        // claimants are queued from the front, claimed cells from the back: two homogeneous queues, slots
-        // from one packed warp scan per word
-        const uint32_t claim4 = (t4 << 1) & 0x80808080u, tgt4 = nonzero_bytes(c4);
+        const uint2 t8 = *reinterpret_cast<const uint2*>(s_tf + si);
+        const uint2 c8 = *reinterpret_cast<const uint2*>(s_cl + si);
+        reinterpret_cast<uint2*>(s_out)[i] = make_uint2(t8.x & 0x87878787u, t8.y & 0x87878787u);  // OCC | GHOST | trait
+        const uint32_t claim[2] = {(t8.x << 1) & 0x80808080u, (t8.y << 1) & 0x80808080u};
+        const uint32_t tgt[2] = {nonzero_bytes(c8.x), nonzero_bytes(c8.y)};
         uint32_t off[2];
-        wreserve<2>(s_q, (uint32_t)__popc(claim4) | ((uint32_t)__popc(tgt4) << 8), off);
-        for (uint32_t m = claim4; m; m &= m - 1) s_work[off[0]++] = (uint16_t)(i * 4 + ((__ffs(m) - 1) >> 3));
-        for (uint32_t m = tgt4; m; m &= m - 1) s_work[NC - 1 - off[1]++] = (uint16_t)(i * 4 + ((__ffs(m) - 1) >> 3));
+        wreserve<2, 16>(s_q, (uint32_t)(__popc(claim[0]) + __popc(claim[1]))
+                                 | ((uint32_t)(__popc(tgt[0]) + __popc(tgt[1])) << 16), off);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            for (uint32_t m = claim[h]; m; m &= m - 1) s_work[off[0]++] = (uint16_t)(i * 8 + h * 4 + ((__ffs(m) - 1) >> 3));
+            for (uint32_t m = tgt[h]; m; m &= m - 1) s_work[NC - 1 - off[1]++] = (uint16_t)(i * 8 + h * 4 + ((__ffs(m) - 1) >> 3));
+        }
     }
     __syncthreads();
     const unsigned int n_claim = s_q[0], n_tgt = s_q[1];
@@ -687,7 +707,7 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
     load_tile_vec<TW, TH, 2>(p, p.tfB, s_tf, x0, y0);
     for (int i = tid; i < SH * SW / 16; i += NT) reinterpret_cast<uint4*>(s_cl)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    scatter_claims<TW, TH>(s_tf, s_cl, s_dxy);
+    scatter_claims<TW, TH, 4>(s_tf, s_cl, s_dxy);
     __syncthreads();
     // ---- dense scan, 4 cells per thread
     unsigned int n_old = 0, n_dead = 0;
