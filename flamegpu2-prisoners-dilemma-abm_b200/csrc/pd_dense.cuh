@@ -629,16 +629,32 @@ __global__ void __launch_bounds__(NT) k_repro_claim(const __grid_constant__ Para
     const int tid = threadIdx.x;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     if (tid < 2) s_n[tid] = 0;
+    // the energies are requested before the flag tile arrives, so that the two latencies overlap (empty cells
+    // hold 0 in E1: loading them is only wasted bandwidth, and only in sparse worlds)
+    constexpr int NIT = (NC / 4 + NT - 1) / NT;
+    float4 e_pre[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int i = tid + it * NT;
+        e_pre[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < NC / 4 && p.max_children > 0u) {
+            const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
+            e_pre[it] = *reinterpret_cast<const float4*>(p.E1 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx);
+        }
+    }
     load_tile_vec<TW, TH, 1>(p, p.tfA, s_tf, x0, y0);
     __syncthreads();
-    for (int i = tid; i < NC / 4; i += NT) {
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int i = tid + it * NT;
+        if (i >= NC / 4) break;
         const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
         const int si = (ly + 1) * SW + lx + 16;
         const uint32_t t4 = *reinterpret_cast<const uint32_t*>(s_tf + si);
         const uint32_t occ4 = t4 & 0x80808080u;
         reinterpret_cast<uint32_t*>(s_out)[i] = t4 & (occ4 | (occ4 >> 6) | (occ4 >> 7));  // OCC | trait of occupied cells
         if (occ4 && p.max_children > 0u) {  // :1054
-            const float4 e4 = *reinterpret_cast<const float4*>(p.E1 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx);
+            const float4 e4 = e_pre[it];
             const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k)

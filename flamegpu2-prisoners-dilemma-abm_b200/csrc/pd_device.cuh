@@ -58,7 +58,7 @@ static_assert(DY(0) == -1 && DY(1) == 0 && DY(2) == 1 && DY(3) == -1 && DY(4) ==
 // ---- device-resident counters -----------------------------------------------------------
 struct Counters {
     // zeroed at the start of every step (k_begin_step)
-    unsigned int mv_n, rp_n, nb_n, risk_next_n, dead_n, cand_n, nb_flagged, pad1_;
+    unsigned int mv_n, rp_n, nb_n, risk_next_n, dead_n, cand_n, nb_flagged, dep_n;
     unsigned int mv_active[8], rp_active[8];
     unsigned long long n_old, births, culled, living_deaths;
     unsigned long long st_play_deaths, st_movers, st_moved, st_travel_deaths;

@@ -38,9 +38,13 @@ __global__ void k_begin_step(Counters* ctr, int count_step) {
 // k_risk_resolve: the agents whose energy is so low that a run of negative payoffs could kill
 // them during play (list built by the previous step).  A responder that dies in sub-step c
 // (:695-697) neither challenges nor responds afterwards, so its neighbours' games depend on
-// WHEN it dies.  Eight lock-stepped rounds over the sparse list reproduce exit_play_fn's
-// iterations (:1527-1556) exactly; the result (D code) is written into the agent's tf byte so
+// WHEN it dies.  The result (D code = sub-step of death + 1) is written into the agent's tf byte so
 // the dense play sweep knows for every neighbour whether it is still alive in sub-step c.
+//   Phase 1, no barriers: an at-risk agent none of whose challengers is itself at risk meets all
+//   its challengers for sure, so it plays its sub-steps by itself, all loads of one agent in flight
+//   together.
+//   Phase 2, the rest (an at-risk challenger may die before it challenges): eight lock-stepped rounds
+//   over those few reproduce exit_play_fn's iterations (:1527-1556) exactly.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_risk_resolve(const __grid_constant__ Params p) {
     Counters* ctr = p.ctr;
@@ -48,40 +52,79 @@ __global__ void __launch_bounds__(1024) k_risk_resolve(const __grid_constant__ P
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (n == 0) return;
-    for (int c = 0; c < 8; ++c) {
-        const int d = 7 - c;  // my direction towards whoever challenges me in sub-step c (:477)
-        for (unsigned int i = t0; i < n; i += stride) {
+    uint32_t* dep = p.risk_next;  // scratch: the next step's list is only filled after this kernel
+    for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
+        const unsigned int i = i0 + threadIdx.x;
+        bool dependent = false;
+        if (i < n) {
             const uint32_t cell = p.risk_cur[i];
             const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
             const uint32_t t = __ldcg(p.tfA + cell);
-            const uint64_t g = gcell_of(p, x, y);
-            float e;
-            uint32_t roll;
-            if (c == 0) {
-                e = p.E0[cell];
-                roll = rng(p, g, S_ROLL).x;
-                p.risk_e[i] = e;
-                p.risk_roll[i] = roll;
-            } else {
-                e = p.risk_e[i];
-                roll = p.risk_roll[i];
+            if (t & TF_OCC) {  // else: a stale entry
+                uint32_t nc[8], tn[8];
+#pragma unroll
+                for (int d = 0; d < 8; ++d) {
+                    nc[d] = nb_local(p, x, y, d);
+                    tn[d] = __ldcg(p.tfA + nc[d]);
+                }
+                float e = __ldcg(p.E0 + cell);
+                const uint32_t my_strat = __ldcg(p.strat + cell);
+                const uint64_t g = gcell_of(p, x, y);
+                const uint32_t roll = rng(p, g, S_ROLL).x;
+                uint32_t chal = 0;  // bit d: my neighbour d challenges me (:413), in sub-step 7-d
+#pragma unroll
+                for (int d = 0; d < 8; ++d) {
+                    if (!(tn[d] & TF_OCC)) continue;
+                    const uint64_t gn = nb_gcell(p, x, y, d);
+                    const uint32_t rn = rng(p, gn, S_ROLL).x;
+                    if (rn > roll || (rn == roll && gn > g)) chal |= 1u << d;
+                }
+#pragma unroll
+                for (int d = 0; d < 8; ++d)
+                    if (((chal >> d) & 1u) && __ldcg(p.E0 + nc[d]) <= p.risk_thr) dependent = true;
+                if (dependent) {
+                    p.risk_e[i] = e;
+                    p.risk_roll[i] = roll;
+                } else {
+                    for (int c = 0; c < 8; ++c) {
+                        const int d = 7 - c;
+                        if (!((chal >> d) & 1u)) continue;
+                        e = __fadd_rn(e, game_payoff(p, g, c, my_strat, t & TF_TRAIT, __ldcg(p.strat + nc[d]), tn[d] & TF_TRAIT));
+                        if (e <= 0.0f) {
+                            p.tfA[cell] = (uint8_t)(t | ((uint32_t)(c + 1) << TF_D_SHIFT));
+                            break;
+                        }
+                        e = fminf(e, p.max_energy);
+                    }
+                }
             }
-            if (!(t & TF_OCC) || (t & TF_D)) continue;  // empty (stale entry) or already dead
+        }
+        const uint32_t slot = warp_append(&ctr->dep_n, dependent);
+        if (dependent) dep[slot] = i;  // dep_n <= n <= list_cap
+    }
+    grid_sync(ctr->barrier, gridDim.x);
+    const unsigned int ndep = __ldcg(&ctr->dep_n);
+    if (ndep == 0) return;
+    for (int c = 0; c < 8; ++c) {
+        const int d = 7 - c;  // my direction towards whoever challenges me in sub-step c (:477)
+        for (unsigned int k = t0; k < ndep; k += stride) {
+            const unsigned int i = __ldcg(&dep[k]);
+            const uint32_t cell = p.risk_cur[i];
+            const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
+            const uint32_t t = __ldcg(p.tfA + cell);
+            if (t & TF_D) continue;  // already dead
             const uint32_t nc = nb_local(p, x, y, d);
             const uint32_t tn = __ldcg(p.tfA + nc);
             if (!(tn & TF_OCC)) continue;
-            const uint64_t gn = nb_gcell(p, x, y, d);
+            const uint64_t g = gcell_of(p, x, y), gn = nb_gcell(p, x, y, d);
+            const uint32_t roll = p.risk_roll[i];
             const uint32_t rn = rng(p, gn, S_ROLL).x;
             if (!(rn > roll || (rn == roll && gn > g))) continue;  // I am the challenger (:413)
             const uint32_t dn = (tn & TF_D) >> TF_D_SHIFT;
             if (dn != 0u && (int)dn - 1 < c) continue;  // challenger died in an earlier sub-step
-            const float pay = game_payoff(p, g, c, p.strat[cell], t & TF_TRAIT, p.strat[nc], tn & TF_TRAIT);
-            e = __fadd_rn(e, pay);
-            if (e <= 0.0f) {
-                p.tfA[cell] = (uint8_t)(t | ((uint32_t)(c + 1) << TF_D_SHIFT));
-            } else {
-                p.risk_e[i] = fminf(e, p.max_energy);
-            }
+            const float e = __fadd_rn(p.risk_e[i], game_payoff(p, g, c, p.strat[cell], t & TF_TRAIT, p.strat[nc], tn & TF_TRAIT));
+            if (e <= 0.0f) p.tfA[cell] = (uint8_t)(t | ((uint32_t)(c + 1) << TF_D_SHIFT));
+            else p.risk_e[i] = fminf(e, p.max_energy);
         }
         grid_sync(ctr->barrier, gridDim.x);
     }
