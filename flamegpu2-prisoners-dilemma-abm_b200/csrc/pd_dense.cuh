@@ -720,6 +720,12 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
     if (tid < 8) s_n[tid] = 0;
     if (tid < 16) s_bins[tid] = 0;
     if (tid < 8) { s_dxy[tid] = DX(tid); s_dxy[8 + tid] = DY(tid); s_off[tid] = DY(tid) * SW + DX(tid); }
+    // pull the tile's energies into L2 now: they are read two barriers later, and the kernel has no registers
+    // to spare for holding them (6 CTAs/SM)
+    for (int i = tid; i < NC / 32; i += NT) {
+        const int ly = (i * 32) / TW, lx = (i * 32) - ly * TW;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.E1 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx));
+    }
     load_tile_vec<TW, TH, 2>(p, p.tfB, s_tf, x0, y0);
     for (int i = tid; i < SH * SW / 16; i += NT) reinterpret_cast<uint4*>(s_cl)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();

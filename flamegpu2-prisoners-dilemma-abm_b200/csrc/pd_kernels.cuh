@@ -518,36 +518,47 @@ __device__ __forceinline__ void fin_apply(const Params& p, unsigned int nb, unsi
     }
     for (int o = 16; o > 0; o >>= 1) n_culled += __shfl_down_sync(0xFFFFFFFFu, n_culled, o);  // one atomic per warp
     if ((threadIdx.x & 31) == 0 && n_culled) atomicAdd(&ctr->culled, (unsigned long long)n_culled);
-    // ---- deferred living cost of the parents that lost round 1 (:1357-1368)
+    // ---- deferred living cost of the parents that lost round 1 (:1357-1368); 4 independent scattered
+    // read-modify-writes in flight per thread (the loop waits on DRAM, not on issue slots)
     unsigned int n_dead = 0;
-    for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nrp; i0 += stride) {
-        const unsigned int i = i0 + threadIdx.x;
-        bool at_risk = false;
-        if (i < nrp) {
-            const uint32_t cell = p.rp_cell[i];
-            if (row_owned(p, cell >> p.log2W)) {
+    for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nrp; i0 += 4 * stride) {
+        uint32_t cell[4];
+        float ev[4];
+        bool mine[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned int i = i0 + u * stride + threadIdx.x;
+            cell[u] = i < nrp ? p.rp_cell[i] : 0u;
+            mine[u] = i < nrp && row_owned(p, cell[u] >> p.log2W);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ev[u] = mine[u] ? __ldcg(p.E0 + cell[u]) : 1.0f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            bool at_risk = false;
+            if (mine[u]) {
                 // No retry round ran (gate closed, the saturated state): the flag byte is still canonical and
                 // is neither read nor rewritten (listing the energy too was tried: it costs k_repro_commit
                 // more than it saves here).
-                float e = __ldcg(p.E0 + cell);
+                float e = ev[u];
                 const bool need_t = flagged || p.want_counts;
-                const uint32_t t = need_t ? __ldcg(p.tfA + cell) : 0u;
+                const uint32_t t = need_t ? __ldcg(p.tfA + cell[u]) : 0u;
                 if (punish(p, e)) {
-                    p.E0[cell] = e;
-                    if (flagged) p.tfA[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
+                    p.E0[cell[u]] = e;
+                    if (flagged) p.tfA[cell[u]] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
                     at_risk = e <= p.risk_thr;
-                    if (p.want_counts) atomicAdd(&ctr->bins[count_bin(__ldcg(p.strat + cell), t & TF_TRAIT)], 1ull);
+                    if (p.want_counts) atomicAdd(&ctr->bins[count_bin(__ldcg(p.strat + cell[u]), t & TF_TRAIT)], 1ull);
                 } else {
-                    p.E0[cell] = 0.0f;
-                    p.tfA[cell] = 0;
+                    p.E0[cell[u]] = 0.0f;
+                    p.tfA[cell[u]] = 0;
                     ++n_dead;
                 }
             }
-        }
-        const uint32_t slot = warp_append(&ctr->risk_next_n, at_risk);
-        if (at_risk) {
-            if (slot < p.list_cap) p.risk_next[slot] = p.rp_cell[i];
-            else atomicExch(&ctr->overflow, 1u);
+            const uint32_t slot = warp_append(&ctr->risk_next_n, at_risk);
+            if (at_risk) {
+                if (slot < p.list_cap) p.risk_next[slot] = cell[u];
+                else atomicExch(&ctr->overflow, 1u);
+            }
         }
     }
     if (n_dead) atomicAdd(&ctr->living_deaths, (unsigned long long)n_dead);
