@@ -604,7 +604,8 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Param
     unsigned int nrp = ctr->rp_n;
     if (nrp > p.list_cap) nrp = p.list_cap;
     unsigned int* g_hist = &ctr->hist[0][0];  // 2048 words
-    uint32_t* cand = p.risk_roll;              // scratch: indices into the newborn list
+    unsigned long long* cand = reinterpret_cast<unsigned long long*>(p.risk_roll);  // scratch: candidate keys
+    const unsigned int cand_cap = p.list_cap / 2u;
     const CullPlan plan = cull_plan(p);
     unsigned long long tau = 0;                // survive iff key >= tau
     if (plan.cull && plan.keep > 0) {
@@ -613,17 +614,20 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Param
         const unsigned int digit = fin_digit(g_hist, plan.keep, s_hist, &s_digit, &s_krem);
         for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nb; i0 += stride) {
             const unsigned int i = i0 + threadIdx.x;
-            const bool is_cand = i < nb && (unsigned int)(cull_key(p, p.nb_cell[i]) >> 53) == digit;
+            const unsigned long long key = i < nb ? cull_key(p, p.nb_cell[i]) : 0ull;
+            const bool is_cand = i < nb && (unsigned int)(key >> 53) == digit;
             const uint32_t slot = warp_append(&ctr->cand_n, is_cand);
-            if (is_cand) cand[slot] = i;
+            if (is_cand) {
+                if (slot < cand_cap) cand[slot] = key;
+                else atomicExch(&ctr->overflow, 1u);  // > cap/2 newborns in one of 2048 bins: not a real world
+            }
         }
         grid_sync(ctr->barrier, gridDim.x);
         if (blockIdx.x == 0) {
-            const unsigned int nc = __ldcg(&ctr->cand_n);
-            const unsigned long long t = fin_select(nc, digit, s_hist, &s_prefix, &s_krem, [&](unsigned int k) {
-                const unsigned int i = __ldcg(&cand[k]);
-                return cull_key(p, p.nb_cell[i]);
-            });
+            unsigned int nc = __ldcg(&ctr->cand_n);
+            if (nc > cand_cap) nc = cand_cap;
+            const unsigned long long t = fin_select(nc, digit, s_hist, &s_prefix, &s_krem,
+                                                    [&](unsigned int k) { return __ldcg(&cand[k]); });
             if (threadIdx.x == 0) ctr->tau = t;
         }
         grid_sync(ctr->barrier, gridDim.x);
