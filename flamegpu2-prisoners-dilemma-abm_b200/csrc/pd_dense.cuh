@@ -690,8 +690,8 @@ __global__ void __launch_bounds__(NT) k_repro_claim(const __grid_constant__ Para
 // (:1339-1371) + step_fn's counts (:1405-1419).  tfB (2-halo), E1, strat -> tfA, E0, strat.
 // The dense scan handles the common cells (empty, or occupied without a claim) inline and queues
 // the rare ones -- claimants and cells that receive a child -- which are then processed with full
-// lanes and patched into the output.  Claim losers go to the repro-loser list and their living cost
-// is deferred to k_finalize (a retry round may still charge them the reproduction cost first).
+// lanes and patched into the output.  Claim losers go to the repro-loser list; they pay the living cost
+// here too unless it would kill them (then it is deferred to k_finalize, see below).
 // An agent that dies of living cost keeps its cell (DYING) until the retry rounds are over, exactly
 // like in the reference where the punishment layer runs after the god submodel.
 // ------------------------------------------------------------------------------------------
@@ -795,23 +795,36 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
             const uint32_t trait = t & TF_TRAIT;
             const int d = (int)((t & TF_DIR) >> TF_DIR_SHIFT);
             const int st = si + s_off[d];
-            float e = p.E1[cell];
-            if (winner_of<TW>(p, s_cl, st, x0, y0, ReproKey()) == 7 - d) {
-                e = __fsub_rn(e, p.reproduce_cost);  // :1211-1213
-                if (punish(p, e)) {
-                    p.tfA[cell] = (uint8_t)(TF_OCC | trait);
-                    p.E0[cell] = e;
-                    if (e <= p.risk_thr) s_risk[atomicAdd(&s_n[3], 1u)] = (uint16_t)cl;
-                    if (p.want_counts) atomicAdd(&s_bins[count_bin(p.strat[cell], trait)], 1u);
-                } else {
-                    p.tfA[cell] = (uint8_t)(TF_OCC | TF_DYING);
-                    p.E0[cell] = 0.0f;
-                    s_dead[atomicAdd(&s_n[4], 1u)] = (uint16_t)cl;
-                    atomicAdd(&s_n[7], 1u);
-                }
-            } else {  // stays ATTEMPTING_REPRODUCTION (:1203-1205): retry list, living cost deferred
+            const float e_in = p.E1[cell];
+            const bool won = winner_of<TW>(p, s_cl, st, x0, y0, ReproKey()) == 7 - d;
+            // Winner: reproduction cost (:1211-1213), then the cost of living.  Loser (stays
+            // ATTEMPTING_REPRODUCTION, :1203-1205, on the retry list): it is charged the cost of living right
+            // away, as if it never reproduces -- true for all losers in the saturated state, where no retry round
+            // runs; if it wins a later round, k_repro_retry recomputes its energy from E1 in the reference's layer
+            // order.  Only a loser the living cost would KILL is deferred to k_finalize: it must stay a live
+            // parent for the retry rounds.  One code path for both keeps the warp converged.
+            float e = won ? __fsub_rn(e_in, p.reproduce_cost) : e_in;
+            const bool alive = punish(p, e);
+            if (alive) {
                 p.tfA[cell] = (uint8_t)(TF_OCC | trait);
                 p.E0[cell] = e;
+                if (e <= p.risk_thr) s_risk[atomicAdd(&s_n[3], 1u)] = (uint16_t)cl;
+                if (p.want_counts) atomicAdd(&s_bins[count_bin(p.strat[cell], trait)], 1u);
+            } else if (won) {
+                p.tfA[cell] = (uint8_t)(TF_OCC | TF_DYING);
+                p.E0[cell] = 0.0f;
+                s_dead[atomicAdd(&s_n[4], 1u)] = (uint16_t)cl;
+                atomicAdd(&s_n[7], 1u);
+            } else {
+                p.tfA[cell] = (uint8_t)(TF_OCC | trait);
+                p.E0[cell] = e_in;
+                if (owned_tile) {
+                    const unsigned int dslot = atomicAdd(&p.ctr->dl_n, 1u);
+                    if (dslot < p.list_cap) p.dl_cell[dslot] = (uint32_t)cell;
+                    else atomicExch(&p.ctr->overflow, 1u);
+                }
+            }
+            if (!won) {
                 const unsigned int slot = atomicAdd(&s_n[2], 1u);
                 s_lost[slot] = (uint16_t)cl;
                 s_lost_state[slot] = (uint8_t)(0xC0u | (uint32_t)d);

@@ -59,6 +59,7 @@ static_assert(DY(0) == -1 && DY(1) == 0 && DY(2) == 1 && DY(3) == -1 && DY(4) ==
 struct Counters {
     // zeroed at the start of every step (k_begin_step)
     unsigned int mv_n, rp_n, nb_n, risk_next_n, dead_n, cand_n, nb_flagged, dep_n;
+    unsigned int dl_n, pad1_;
     unsigned int mv_active[8], rp_active[8];
     unsigned long long n_old, births, culled, living_deaths;
     unsigned long long st_play_deaths, st_movers, st_moved, st_travel_deaths;
@@ -116,6 +117,8 @@ struct Params {
     float* nb_e; uint16_t* nb_gene;  // the newborn's energy and strategies | trait << 8 (it is written into the
                                      // planes only if it survives the cull, or when retry rounds must see it)
     uint32_t* dead_cell;  // aliases mv_cell (the travel rounds are over when it is filled)
+    uint32_t* dl_cell;    // claim losers whose living cost is deferred to k_finalize; aliases risk_e (only used
+                          // inside k_risk_resolve)
     Counters* ctr;
 };
 

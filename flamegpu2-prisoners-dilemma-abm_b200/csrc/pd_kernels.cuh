@@ -307,8 +307,8 @@ __global__ void __launch_bounds__(1024) k_repro_retry(const __grid_constant__ Pa
             p.tfA[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
             if (aux & 0x80u) {
                 const uint32_t tgt = nb_local(p, x, y, (int)(aux & 7u));
-                const float pe = __fsub_rn(__ldcg(p.E0 + cell), p.reproduce_cost);
-                p.E0[cell] = pe;
+                const float e1 = __ldcg(p.E1 + cell);  // the energy it entered reproduction with
+                const float pe = __fsub_rn(e1, p.reproduce_cost);
                 float ce;
                 uint32_t cs;
                 make_child(p, gcell_of(p, x, y), __ldcg(p.strat + cell), t & TF_TRAIT, pe, ce, cs);
@@ -322,7 +322,35 @@ __global__ void __launch_bounds__(1024) k_repro_retry(const __grid_constant__ Pa
                     } else atomicExch(&ctr->overflow, 1u);
                     ++born;
                 }
-                p.rp_state[i] = 0x40u;  // REPRODUCTION_COMPLETE; living cost still due
+                // The parent.  k_repro_commit already charged it the living cost if it survives that without
+                // reproducing ("eager"); now the reproduction cost comes first (:1211-1213, then :1357-1368).
+                float chk = e1;
+                if (!punish(p, chk)) {
+                    p.E0[cell] = pe;  // deferred loser: k_finalize charges the living cost (dl list)
+                } else {
+                    float e = pe;
+                    const bool own = row_owned(p, y);
+                    if (punish(p, e)) {
+                        p.E0[cell] = e;
+                        if (own && e <= p.risk_thr && !(chk <= p.risk_thr)) {  // not yet on the next at-risk list
+                            const unsigned int rs = atomicAdd(&ctr->risk_next_n, 1u);
+                            if (rs < p.list_cap) p.risk_next[rs] = cell;
+                            else atomicExch(&ctr->overflow, 1u);
+                        }
+                    } else {  // it dies after all: same bookkeeping as a death in k_repro_commit
+                        p.E0[cell] = 0.0f;
+                        p.tfA[cell] = (uint8_t)(TF_OCC | TF_DYING);
+                        if (own) {
+                            const unsigned int ds = atomicAdd(&ctr->dead_n, 1u);
+                            if (ds < p.list_cap) p.dead_cell[ds] = cell;
+                            else atomicExch(&ctr->overflow, 1u);
+                            atomicAdd(&ctr->living_deaths, 1ull);
+                            if (p.want_counts)  // it was counted alive
+                                atomicAdd(&ctr->bins[count_bin(__ldcg(p.strat + cell), t & TF_TRAIT)], ~0ull);
+                        }
+                    }
+                }
+                p.rp_state[i] = 0x40u;  // REPRODUCTION_COMPLETE
             } else {
                 ++still;
             }
@@ -482,7 +510,7 @@ __device__ __forceinline__ unsigned long long fin_select(unsigned int n, unsigne
 }
 
 // newborns: cull or admit; deferred living cost of the repro losers; dying agents leave; all OWNED rows only
-__device__ __forceinline__ void fin_apply(const Params& p, unsigned int nb, unsigned int nrp, bool cull,
+__device__ __forceinline__ void fin_apply(const Params& p, unsigned int nb, bool cull,
                                           unsigned long long keep, unsigned long long tau) {
     Counters* ctr = p.ctr;
     const unsigned int stride = gridDim.x * blockDim.x;
@@ -518,18 +546,20 @@ __device__ __forceinline__ void fin_apply(const Params& p, unsigned int nb, unsi
     }
     for (int o = 16; o > 0; o >>= 1) n_culled += __shfl_down_sync(0xFFFFFFFFu, n_culled, o);  // one atomic per warp
     if ((threadIdx.x & 31) == 0 && n_culled) atomicAdd(&ctr->culled, (unsigned long long)n_culled);
-    // ---- deferred living cost of the parents that lost round 1 (:1357-1368); 4 independent scattered
-    // read-modify-writes in flight per thread (the loop waits on DRAM, not on issue slots)
+    // ---- deferred living cost (:1357-1368) of the few round-1 losers it would kill (k_repro_commit lists them;
+    // every other loser has paid already)
     unsigned int n_dead = 0;
-    for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nrp; i0 += 4 * stride) {
+    unsigned int ndl = __ldcg(&ctr->dl_n);
+    if (ndl > p.list_cap) ndl = p.list_cap;
+    for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < ndl; i0 += 4 * stride) {
         uint32_t cell[4];
         float ev[4];
         bool mine[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const unsigned int i = i0 + u * stride + threadIdx.x;
-            cell[u] = i < nrp ? p.rp_cell[i] : 0u;
-            mine[u] = i < nrp && row_owned(p, cell[u] >> p.log2W);
+            cell[u] = i < ndl ? p.dl_cell[i] : 0u;
+            mine[u] = i < ndl && row_owned(p, cell[u] >> p.log2W);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) ev[u] = mine[u] ? __ldcg(p.E0 + cell[u]) : 1.0f;
@@ -537,9 +567,7 @@ __device__ __forceinline__ void fin_apply(const Params& p, unsigned int nb, unsi
         for (int u = 0; u < 4; ++u) {
             bool at_risk = false;
             if (mine[u]) {
-                // No retry round ran (gate closed, the saturated state): the flag byte is still canonical and
-                // is neither read nor rewritten (listing the energy too was tried: it costs k_repro_commit
-                // more than it saves here).
+                // no retry round ran (gate closed): the flag byte is still canonical
                 float e = ev[u];
                 const bool need_t = flagged || p.want_counts;
                 const uint32_t t = need_t ? __ldcg(p.tfA + cell[u]) : 0u;
@@ -601,8 +629,6 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Param
     const unsigned int stride = gridDim.x * blockDim.x;
     unsigned int nb = ctr->nb_n;
     if (nb > p.list_cap) nb = p.list_cap;
-    unsigned int nrp = ctr->rp_n;
-    if (nrp > p.list_cap) nrp = p.list_cap;
     unsigned int* g_hist = &ctr->hist[0][0];  // 2048 words
     unsigned long long* cand = reinterpret_cast<unsigned long long*>(p.risk_roll);  // scratch: candidate keys
     const unsigned int cand_cap = p.list_cap / 2u;
@@ -633,7 +659,7 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Param
         grid_sync(ctr->barrier, gridDim.x);
         tau = __ldcg(&ctr->tau);
     }
-    fin_apply(p, nb, nrp, plan.cull, plan.keep, tau);
+    fin_apply(p, nb, plan.cull, plan.keep, tau);
     grid_sync(ctr->barrier, gridDim.x);
     if (blockIdx.x == 0 && threadIdx.x == 0) fin_bookkeeping(p);
 }
@@ -694,8 +720,6 @@ __global__ void __launch_bounds__(1024) k_fin_apply(const __grid_constant__ Para
     Counters* ctr = p.ctr;
     unsigned int nb = ctr->nb_n;
     if (nb > p.list_cap) nb = p.list_cap;
-    unsigned int nrp = ctr->rp_n;
-    if (nrp > p.list_cap) nrp = p.list_cap;
     const CullPlan plan = cull_plan(p);
     unsigned long long tau = 0;
     if (plan.cull && plan.keep > 0) {
@@ -726,7 +750,7 @@ __global__ void __launch_bounds__(1024) k_fin_apply(const __grid_constant__ Para
         grid_sync(ctr->barrier, gridDim.x);
         tau = __ldcg(&ctr->tau);
     }
-    fin_apply(p, nb, nrp, plan.cull, plan.keep, tau);
+    fin_apply(p, nb, plan.cull, plan.keep, tau);
     grid_sync(ctr->barrier, gridDim.x);
     if (blockIdx.x == 0 && threadIdx.x == 0) fin_bookkeeping(p);
 }

@@ -124,6 +124,7 @@ int alloc_lists(pd_sim* s, uint64_t n_agents_hint) {
     CK(cudaMalloc(&s->risk[0], cap * 4));
     CK(cudaMalloc(&s->risk[1], cap * 4));
     CK(cudaMalloc(&s->P.risk_e, cap * 4));
+    s->P.dl_cell = reinterpret_cast<uint32_t*>(s->P.risk_e);
     CK(cudaMalloc(&s->P.risk_roll, cap * 4));
     CK(cudaMalloc(&s->P.mv_cell, cap * 4));
     s->P.dead_cell = s->P.mv_cell;

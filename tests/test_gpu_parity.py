@@ -123,6 +123,17 @@ def test_harsh_world_many_deaths():
          init_agent_count=2500)
 
 
+def test_parents_that_die_of_the_living_cost():
+    """Reproduction threshold below the cost of living: claim losers that the living cost would kill must stay
+    live parents through the retry rounds (deferred list), winners pay reproduction cost first, then die."""
+    _run(40, width=64, seed=77, reproduce_min_energy=1.5, reproduce_cost=0.5, cost_of_living=2.0,
+         init_energy_mu=4.0, init_energy_sigma=2.0, init_energy_min=1.0, payoff_cc=3.0, payoff_dd=0.0,
+         init_agent_count=1500, max_agents=3000)
+    _run(25, width=64, seed=78, reproduce_min_energy=2.0, reproduce_cost=1.0, cost_of_living=2.5,
+         init_energy_mu=5.0, init_energy_sigma=3.0, init_energy_min=1.0, env_noise=0.1, mutation_rate=0.05,
+         strategy_per_trait=1, init_agent_count=1200, max_agents=4096)
+
+
 def test_dense_world_conflicts():
     """Dense start: many travel/reproduction conflicts, retry rounds, full neighbourhoods."""
     _run(30, width=64, seed=3, init_agent_count=3000, max_agents=3600, reproduce_min_energy=40.0,
