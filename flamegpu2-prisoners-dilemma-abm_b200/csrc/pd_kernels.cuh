@@ -53,6 +53,10 @@ __global__ void __launch_bounds__(1024) k_risk_resolve(const __grid_constant__ P
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (n == 0) return;
     uint32_t* dep = p.risk_next;  // scratch: the next step's list is only filled after this kernel
+    // Phase 1 pays off when a lock-stepped round would need several entries per thread; with fewer entries than
+    // threads (small worlds) the rounds are pure barrier latency and the extra pass only adds to it, so every
+    // entry goes straight to phase 2.
+    const bool split = n > stride;
     for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
         const unsigned int i = i0 + threadIdx.x;
         bool dependent = false;
@@ -60,7 +64,11 @@ __global__ void __launch_bounds__(1024) k_risk_resolve(const __grid_constant__ P
             const uint32_t cell = p.risk_cur[i];
             const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
             const uint32_t t = __ldcg(p.tfA + cell);
-            if (t & TF_OCC) {  // else: a stale entry
+            if ((t & TF_OCC) && !split) {
+                dependent = true;
+                p.risk_e[i] = __ldcg(p.E0 + cell);
+                p.risk_roll[i] = rng(p, gcell_of(p, x, y), S_ROLL).x;
+            } else if (t & TF_OCC) {  // else: a stale entry
                 uint32_t nc[8], tn[8];
 #pragma unroll
                 for (int d = 0; d < 8; ++d) {
