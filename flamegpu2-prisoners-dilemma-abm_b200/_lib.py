@@ -49,7 +49,7 @@ class pd_config(C.Structure):
         ("ghost_rows", C.c_uint32),
         ("world_height", C.c_uint32),
         ("use_graphs", C.c_int32),
-        ("reserved", C.c_uint32),
+        ("debug_select_cap", C.c_uint32),
     ]
 
 

@@ -98,6 +98,7 @@ struct Params {
     uint32_t round0, round1;  // reproduction retry rounds to run in this launch (slab mode)
     uint32_t world;           // number of slabs
     uint32_t cand_cap;        // capacity (keys) of one rank's candidate block
+    uint32_t select_cap;      // cull select: most keys resolved in shared memory (tests lower it to reach the fallback)
     unsigned long long* glb;        // [0] olds [1] births [2] active repro losers [3] agents [4..19] bins,
                                     // summed over all slabs by the caller between the step's parts
     unsigned int* ghist;            // 2048-bin cull histogram, summed over all slabs by the caller

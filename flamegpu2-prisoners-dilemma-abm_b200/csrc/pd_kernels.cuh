@@ -471,16 +471,59 @@ __device__ __forceinline__ unsigned int fin_digit(const unsigned int* hist, unsi
     return *s_digit;
 }
 
-// krem-th largest of `n` candidate keys (all with the same top 11 bits `digit`), by CTA 0 only:
-// 8 bits per pass over the low 53 bits.  key(k) fetches candidate k.
+// krem-th largest of `n` candidate keys (all with the same top 11 bits `digit`), by CTA 0 only.  One pass
+// histograms the next 11 bits (s_hist has 2048 words); the threshold bin then holds n/2048 keys on average:
+// they are compacted into shared memory and the answer is the key with exactly krem-1 larger ones (keys are
+// unique: the cell index is in the low bits).  Only if that bin is improbably full do 8-bit passes over all
+// candidates finish the job.  key_at(k) fetches candidate k.
 template <typename KeyAt>
 __device__ __forceinline__ unsigned long long fin_select(unsigned int n, unsigned int digit, unsigned int* s_hist,
                                                          unsigned long long* s_prefix, unsigned long long* s_krem,
-                                                         KeyAt key_at) {
+                                                         unsigned int smem_cap, KeyAt key_at) {
+    constexpr unsigned int SK = 1024;
+    __shared__ unsigned long long s_keys[SK];
+    __shared__ unsigned int s_m;
     __shared__ unsigned int s_dg_store;
     unsigned int* s_dg = &s_dg_store;
-    if (threadIdx.x == 0) *s_prefix = (unsigned long long)digit;  // the 11 bits decided so far
-    int decided = 11;
+    for (unsigned int i = threadIdx.x; i < 2048; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_m = 0;
+    __syncthreads();
+    for (unsigned int k = threadIdx.x; k < n; k += 4 * blockDim.x) {  // 4 independent loads in flight
+        unsigned long long key[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) key[u] = (k + u * blockDim.x < n) ? key_at(k + u * blockDim.x) : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (k + u * blockDim.x < n && (unsigned int)(key[u] >> 53) == digit)
+                atomicAdd(&s_hist[(unsigned int)(key[u] >> 42) & 2047u], 1u);
+    }
+    __syncthreads();
+    find_threshold_bin(s_hist, 2048, *s_krem, s_dg, s_krem);
+    const unsigned long long prefix22 = ((unsigned long long)digit << 11) | (unsigned long long)*s_dg;
+    const unsigned int m = s_hist[*s_dg];
+    if (m <= (smem_cap < SK ? smem_cap : SK)) {  // smem_cap < SK only in tests of the fallback below
+        for (unsigned int k = threadIdx.x; k < n; k += 4 * blockDim.x) {
+            unsigned long long key[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) key[u] = (k + u * blockDim.x < n) ? key_at(k + u * blockDim.x) : 0ull;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (k + u * blockDim.x < n && (key[u] >> 42) == prefix22) s_keys[atomicAdd(&s_m, 1u)] = key[u];
+        }
+        __syncthreads();
+        const unsigned long long krem = *s_krem;
+        for (unsigned int i = threadIdx.x; i < m; i += blockDim.x) {
+            const unsigned long long mine = s_keys[i];
+            unsigned long long larger = 0;
+            for (unsigned int j = 0; j < m; ++j) larger += s_keys[j] > mine ? 1ull : 0ull;
+            if (larger + 1ull == krem) *s_prefix = mine;
+        }
+        __syncthreads();
+        return *s_prefix;
+    }
+    if (threadIdx.x == 0) *s_prefix = prefix22;  // the 22 bits decided so far
+    __syncthreads();
+    int decided = 22;
     while (decided < 64) {
         const int bits = (64 - decided) >= 8 ? 8 : (64 - decided);
         const int shift = 64 - decided - bits;
@@ -660,7 +703,7 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Param
         if (blockIdx.x == 0) {
             unsigned int nc = __ldcg(&ctr->cand_n);
             if (nc > cand_cap) nc = cand_cap;
-            const unsigned long long t = fin_select(nc, digit, s_hist, &s_prefix, &s_krem,
+            const unsigned long long t = fin_select(nc, digit, s_hist, &s_prefix, &s_krem, p.select_cap,
                                                     [&](unsigned int k) { return __ldcg(&cand[k]); });
             if (threadIdx.x == 0) ctr->tau = t;
         }
@@ -748,7 +791,7 @@ __global__ void __launch_bounds__(1024) k_fin_apply(const __grid_constant__ Para
             }
             __syncthreads();
             const unsigned int total = s_cum[p.world];
-            const unsigned long long t = fin_select(total, digit, s_hist, &s_prefix, &s_krem, [&](unsigned int k) {
+            const unsigned long long t = fin_select(total, digit, s_hist, &s_prefix, &s_krem, p.select_cap, [&](unsigned int k) {
                 uint32_t w = 0;
                 while (k >= s_cum[w + 1]) ++w;
                 return __ldcg(&p.cand_all[w * blk + 1 + (k - s_cum[w])]);

@@ -338,6 +338,7 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     P.wrap_y = slab ? 0u : 1u;
     P.own_y0 = cfg->ghost_rows; P.own_y1 = cfg->ghost_rows + cfg->rows;
     P.round0 = 1; P.round1 = 8; P.world = 1; P.cand_cap = 0;
+    P.select_cap = cfg->debug_select_cap ? cfg->debug_select_cap : 0xFFFFFFFFu;
     P.glb = nullptr; P.ghist = nullptr; P.cand_out = nullptr; P.cand_all = nullptr;
     P.log2W = 0;
     while ((1u << P.log2W) < W) ++P.log2W;

@@ -52,6 +52,7 @@ class SimConfig:
     collect_stats: bool = False
     sparse_ctas: int = 0
     use_graphs: int = 0                    # 0 auto, 1 always, -1 never (one CUDA graph per step; needs a stream)
+    debug_select_cap: int = 0              # tests only: force the cull select's global-memory fallback
 
     def __post_init__(self):
         if self.height < 0:
@@ -86,6 +87,7 @@ class SimConfig:
         c.device = int(self.device)
         c.sparse_ctas = int(self.sparse_ctas)
         c.use_graphs = int(self.use_graphs)
+        c.debug_select_cap = int(self.debug_select_cap)
         return c
 
 

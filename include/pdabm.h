@@ -80,7 +80,8 @@ typedef struct pd_config {
     int32_t use_graphs;             /* 0 = auto (whole worlds <= 2^22 cells), 1 = always, -1 = never: replay one
                                        captured CUDA graph per step instead of 9 launches.  Only on explicit
                                        (capturable) streams and while per-kernel profiling is off. */
-    uint32_t reserved;
+    uint32_t debug_select_cap;      /* 0 = default; tests: cap of the cull select's shared-memory stage, to force its
+                                       global-memory fallback */
 } pd_config;
 
 /* Per-step event counters of the LAST executed step (debug / parity aid; the

@@ -24,6 +24,8 @@ CASES = {
                              reproduce_cost=10.0, payoff_cc=10.0), 25),
     "dying_parents": (dict(width=256, seed=36, reproduce_min_energy=1.5, reproduce_cost=0.5, cost_of_living=2.0,
                            init_energy_mu=4.0, init_energy_sigma=2.0, init_energy_min=1.0, init_agent_count=24000), 30),
+    "select_fallback": (dict(width=256, seed=37, debug_select_cap=1, init_agent_count=30000, max_agents=31000,
+                             reproduce_min_energy=40.0, reproduce_cost=10.0), 30),
     "inherit": (dict(width=256, seed=35, reproduction_inheritence=0.5, env_noise=0.2, mutation_rate=0.2), 70),
 }
 

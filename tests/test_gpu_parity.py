@@ -30,7 +30,7 @@ def _pair(**kw):
     from pdabm_b200 import Simulation, SimConfig
     from oracle.pd_oracle import Oracle, Params
     sim = Simulation(SimConfig(collect_stats=True, **kw))
-    okw = {k: v for k, v in kw.items() if k != "sparse_ctas"}
+    okw = {k: v for k, v in kw.items() if k not in ("sparse_ctas", "debug_select_cap")}
     orc = Oracle(Params(**okw))
     return sim, orc
 
@@ -132,6 +132,14 @@ def test_parents_that_die_of_the_living_cost():
     _run(25, width=64, seed=78, reproduce_min_energy=2.0, reproduce_cost=1.0, cost_of_living=2.5,
          init_energy_mu=5.0, init_energy_sigma=3.0, init_energy_min=1.0, env_noise=0.1, mutation_rate=0.05,
          strategy_per_trait=1, init_agent_count=1200, max_agents=4096)
+
+
+def test_cull_select_fallback_path():
+    """The cull's k-th-key select normally finishes in shared memory; with the stage capped at 1 key it must
+    take the 8-bit passes over global memory whenever the threshold bin holds more -- same survivors."""
+    _run(75, width=128, seed=41, debug_select_cap=1)
+    _run(40, width=128, seed=42, debug_select_cap=1, sparse_ctas=8, init_agent_count=7000, max_agents=7200,
+         reproduce_min_energy=40.0, reproduce_cost=10.0)
 
 
 def test_dense_world_conflicts():
