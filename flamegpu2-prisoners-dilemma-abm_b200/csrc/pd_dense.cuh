@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
     __shared__ __align__(16) uint8_t s_tf[SH * SW];
     __shared__ __align__(16) uint8_t s_st[SH * SW];
     __shared__ __align__(16) uint32_t s_R[SH * SW];
+    __shared__ __align__(16) float s_e[NC];
     __shared__ __align__(16) uint8_t s_out[NC];
     __shared__ uint16_t s_cells[NC + 2 * (TW + 2) + 2 * TH];  // agents first (from 0), then ring cells
     __shared__ uint16_t s_mover[NC];
@@ -214,10 +215,11 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
     if (tid < 8) s_off[tid] = DY(tid) * SW + DX(tid);
     load_tile_vec<TW, TH, 1>(p, p.tfA, s_tf, x0, y0);
     load_tile_vec<TW, TH, 1>(p, p.strat, s_st, x0, y0);
-    // Energies are NOT staged in shared memory: an agent loads its own from E0 at the top of its iteration and
-    // stores the result to E1 itself (fewer instructions than a dense float4 tile in and out: 5.33 -> 5.29 ms).
-    // E1 of cells that are empty throughout the step is therefore stale; every reader masks it with the flags.
-    // (The 36 KB of shared memory left would allow 6 CTAs per SM at 40 registers; measured slower, 5.38 ms.)
+    for (int i = tid; i < NC / 4; i += NT) {
+        const int ly = (i * 4) >> LOG_TW, lx = (i * 4) & (TW - 1);
+        reinterpret_cast<float4*>(s_e)[i] =
+            *reinterpret_cast<const float4*>(p.E0 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx);
+    }
     for (int i = tid; i < NC / 16; i += NT) reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < SH * SW / 4; i += NT) reinterpret_cast<uint4*>(s_R)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
@@ -274,8 +276,6 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
         const int ly = si / SW - 1, lx = si - (ly + 1) * SW - 16;
         const int cl = (ly << LOG_TW) | lx;
         const uint32_t rme = valid ? s_R[si] : 0xFFFFFFFFu;
-        const size_t gidx = ((size_t)(y0 + (uint32_t)ly) << p.log2W) + x0 + (uint32_t)lx;
-        const float e_in = valid ? p.E0[gidx] : 0.0f;  // used ~400 instructions further down
         const uint32_t kme = rme >> 11;
         // ---- who is around me, and who challenges me (bit c of gm: my neighbour 7-c does, in sub-step c, :477)
         uint32_t occ_mask = 0, gm = 0, special = 0;
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
         // ---- my games in sub-step order (:677-710), terminal rule, travel decision
         bool mover = false;
         if (valid) {
-            float e = e_in;
+            float e = s_e[cl];
             int games = 0;
             bool dead = false;
 #pragma unroll
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
             }
             if (dead) {
                 s_out[cl] = (uint8_t)TF_GHOST;
-                p.E1[gidx] = 0.0f;
+                s_e[cl] = 0.0f;
                 ++n_play_deaths;
             } else {
                 // terminal rule (:547-556, :719-730, :486-496) or no neighbours (:429-433):
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
                 const bool act0_respond = (roles >> 7) & 1u;
                 mover = occ_mask == 0u || (games == 0 && (act7_challenge || act0_respond));
                 s_out[cl] = (uint8_t)(TF_OCC | ((rme >> 8) & TF_TRAIT));
-                p.E1[gidx] = e;
+                s_e[cl] = e;
             }
         }
         const uint32_t slot = wappend(&s_n[2], mover);
@@ -406,15 +406,14 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
         const int cl = s_mover[k];
         const int ly = cl >> LOG_TW, lx = cl & (TW - 1);
         const int si = (ly + 1) * SW + lx + 16;
-        float* e1 = p.E1 + ((size_t)(y0 + (uint32_t)ly) << p.log2W) + x0 + (uint32_t)lx;  // written above, same CTA
-        const float e = __fsub_rn(*e1, p.travel_cost);      // :800
+        const float e = __fsub_rn(s_e[cl], p.travel_cost);  // :800
         if (e <= 0.0f) {                                    // :801-804
             s_out[cl] = (uint8_t)TF_GHOST;
-            *e1 = 0.0f;
+            s_e[cl] = 0.0f;
             ++n_travel_deaths;
             continue;
         }
-        *e1 = e;
+        s_e[cl] = e;
         uint32_t occ_mask = 0;
 #pragma unroll
         for (int d = 0; d < 8; ++d) occ_mask |= (s_R[si + DY(d) * SW + DX(d)] >> 31) << d;
@@ -428,6 +427,10 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
     for (int i = tid; i < NC / 16; i += NT) {
         const int ly = (i * 16) >> LOG_TW, lx = (i * 16) & (TW - 1);
         *reinterpret_cast<uint4*>(p.tfB + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = reinterpret_cast<uint4*>(s_out)[i];
+    }
+    for (int i = tid; i < NC / 4; i += NT) {
+        const int ly = (i * 4) >> LOG_TW, lx = (i * 4) & (TW - 1);
+        *reinterpret_cast<float4*>(p.E1 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = reinterpret_cast<float4*>(s_e)[i];
     }
     if (p.stats && row_owned(p, y0)) {  // tiles are entirely owned or entirely ghost (16-row granularity)
         if (n_play_deaths) atomicAdd(&p.ctr->st_play_deaths, (unsigned long long)n_play_deaths);
