@@ -330,10 +330,11 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         sw = min(width, 256)
-        cval, ctotal, csecs, _ = cpu_oracle_throughput(overrides, sw, 70, 12, 1)
+        csteps = 250  # ~10 s of CPU work at 256^2 (the contract asks for a 10-30 s sample)
+        cval, ctotal, csecs, _ = cpu_oracle_throughput(overrides, sw, 70, csteps, 1)
         cpu = {"value": cval, "unit": "agent-steps/s", "cores": 1, "kind": "port",
                "sample": f"NumPy oracle (oracle/pd_oracle.py), one {sw}x{sw} world with the workload's parameters, "
-                         f"70 untimed pre-steps then 12 timed steps ({csecs:.1f} s), single process"}
+                         f"70 untimed pre-steps then {csteps} timed steps ({csecs:.1f} s), single process"}
 
     line = {
         "metric": "agent-steps/sec", "value": agent_steps / secs, "unit": "agent-steps/s",
