@@ -371,13 +371,13 @@ __global__ void __launch_bounds__(1024) k_repro_retry(const __grid_constant__ Pa
 }
 
 // ------------------------------------------------------------------------------------------
-// Finalisation (sparse, persistent): the carrying-capacity cull, the deferred living cost of
-// the repro-loser list, the newborns' counts and the bookkeeping for the next step.
+// Finalisation (sparse, persistent): the carrying-capacity cull, the living cost of the few claim
+// losers it kills (deferred by k_repro_commit), the newborns' counts and the bookkeeping for the next step.
 // Cull (replaces the list-index rule :1343/:1354, SURVEY B-4): if olds + births exceed
 // max_agents, only the K = max_agents - olds newborns with the highest (Philox cull priority,
 // cell) keys survive.  The K-th largest 64-bit key is found exactly by a radix select: one
 // 2048-bin histogram of the top 11 bits over all newborns, compaction of the threshold bin's
-// few candidates, then 8-bit passes over the candidates only (CTA 0).
+// few candidates, then (CTA 0) one 11-bit pass over the candidates and a rank count of what is left.
 // Whole world: one kernel (k_finalize).  Row slabs: three kernels (k_fin_hist, k_fin_cand,
 // k_fin_apply) with the caller summing the histogram and gathering the candidates in between.
 // ------------------------------------------------------------------------------------------
@@ -560,7 +560,7 @@ __device__ __forceinline__ unsigned long long fin_select(unsigned int n, unsigne
     return *s_prefix;
 }
 
-// newborns: cull or admit; deferred living cost of the repro losers; dying agents leave; all OWNED rows only
+// newborns: cull or admit; deferred living cost of the listed claim losers; dying agents leave; all OWNED rows only
 __device__ __forceinline__ void fin_apply(const Params& p, unsigned int nb, bool cull,
                                           unsigned long long keep, unsigned long long tau) {
     Counters* ctr = p.ctr;
