@@ -65,6 +65,7 @@ EXPORTS = (
     "pd_bind_planes", "pd_init_population", "pd_sync_state", "pd_step", "pd_read_counts",
     "pd_read_stats", "pd_get_step", "pd_set_step", "pd_step_host", "pd_read_agent_steps",
     "pd_set_profile", "pd_read_profile", "pd_bind_comm", "pd_step_part", "pd_graph_replays",
+    "pd_set_step_log", "pd_read_step_log",
 )
 
 _lib = None
@@ -119,6 +120,10 @@ def load() -> C.CDLL:
     lib.pd_bind_comm.argtypes = [vp, vp, vp, vp, vp, u32, u32]
     lib.pd_step_part.restype = i32
     lib.pd_step_part.argtypes = [vp, i32, i32, vp, i32]
+    lib.pd_set_step_log.restype = i32
+    lib.pd_set_step_log.argtypes = [vp, u32, vp]
+    lib.pd_read_step_log.restype = i32
+    lib.pd_read_step_log.argtypes = [vp, C.POINTER(u64), u32, C.POINTER(u32), vp]
     lib.pd_graph_replays.restype = i32
     lib.pd_graph_replays.argtypes = [vp, C.POINTER(u64)]
     lib.pd_debug_philox.restype = i32

@@ -70,6 +70,7 @@ struct Counters {
     unsigned int risk_n;
     unsigned int overflow;
     unsigned int barrier[2];
+    unsigned int log_n, log_dropped;  // rows in the step log / rows that did not fit
     unsigned int step_no;  // model step being computed: the Philox key of every draw.  Device-resident so that
     unsigned int pad2_;    // a captured CUDA graph of one step can be replayed (k_set_step / fin_bookkeeping)
     unsigned long long n_agents;
@@ -98,6 +99,8 @@ struct Params {
     uint32_t round0, round1;  // reproduction retry rounds to run in this launch (slab mode)
     uint32_t world;           // number of slabs
     uint32_t cand_cap;        // capacity (keys) of one rank's candidate block
+    unsigned long long* step_log;  // [log_cap][18] rows: step, agents, 16 counts; nullptr = off
+    uint32_t log_cap;
     uint32_t select_cap;      // cull select: most keys resolved in shared memory (tests lower it to reach the fallback)
     unsigned long long* glb;        // [0] olds [1] births [2] active repro losers [3] agents [4..19] bins,
                                     // summed over all slabs by the caller between the step's parts

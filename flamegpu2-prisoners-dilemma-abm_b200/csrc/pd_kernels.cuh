@@ -665,6 +665,18 @@ __device__ __forceinline__ void fin_bookkeeping(const Params& p) {
     s[6] = b; s[7] = culled; s[8] = ld;
     s[9] = rn; s[10] = __ldcg(&ctr->mv_n); s[11] = __ldcg(&ctr->rp_n);
     ctr->step_no += 1u;  // the step is complete
+    if (p.want_counts && p.step_log) {  // one row per counted step, read back whenever the host wants
+        const unsigned int row = ctr->log_n;
+        if (row < p.log_cap) {
+            unsigned long long* r = p.step_log + (size_t)row * 18u;
+            r[0] = ctr->step_no;
+            r[1] = ctr->n_agents;
+            for (int k = 0; k < 16; ++k) r[2 + k] = ctr->last_bins[k];
+            ctr->log_n = row + 1u;
+        } else {
+            ctr->log_dropped += 1u;
+        }
+    }
     if (p.glb) {  // publish this slab's totals; the caller sums them over the slabs when it wants them
         p.glb[3] = ctr->n_agents;
         for (int k = 0; k < 16; ++k) p.glb[4 + k] = p.want_counts ? ctr->last_bins[k] : 0ull;

@@ -339,6 +339,7 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     P.own_y0 = cfg->ghost_rows; P.own_y1 = cfg->ghost_rows + cfg->rows;
     P.round0 = 1; P.round1 = 8; P.world = 1; P.cand_cap = 0;
     P.select_cap = cfg->debug_select_cap ? cfg->debug_select_cap : 0xFFFFFFFFu;
+    P.step_log = nullptr; P.log_cap = 0;
     P.glb = nullptr; P.ghist = nullptr; P.cand_out = nullptr; P.cand_all = nullptr;
     P.log2W = 0;
     while ((1u << P.log2W) < W) ++P.log2W;
@@ -396,8 +397,9 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
 int pd_destroy(pd_sim* s) {
     if (!s) return PD_OK;
     cudaSetDevice(s->cfg.device);
-    cudaDeviceSynchronize();
+    // (no cudaDeviceSynchronize: it is an error while another thread captures a graph; cudaFree below waits)
     drop_graphs(s);
+    if (s->P.step_log) cudaFree(s->P.step_log);
     cudaFree(s->P.E1); cudaFree(s->P.tfB); cudaFree(s->P.ctr);
     if (s->lists_allocated) {
         cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.risk_roll);
@@ -506,7 +508,7 @@ int pd_step(pd_sim* s, uint32_t n_steps, void* stream, int want_counts) {
     if (rc) return rc;
     for (uint32_t k = 0; k < n_steps; ++k) {
         Params& P = s->P;
-        P.want_counts = (want_counts && k + 1 == n_steps) ? 1u : 0u;
+        P.want_counts = (want_counts == 2 || (want_counts && k + 1 == n_steps)) ? 1u : 0u;
         P.risk_cur = s->risk[s->risk_cur];
         P.risk_next = s->risk[s->risk_cur ^ 1];
         bool replayed = false;
@@ -654,6 +656,42 @@ int pd_read_agent_steps(pd_sim* s, uint64_t* agent_steps, void* stream) {
     CK(cudaMemcpyAsync(&s->h->n_agents, &s->P.ctr->agent_steps, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     *agent_steps = s->h->n_agents;
+    return PD_OK;
+}
+
+int pd_set_step_log(pd_sim* s, uint32_t capacity_rows, void* stream) {
+    if (!s) return fail(PD_ERR_INVALID, "NULL argument");
+    if (s->slab) return fail(PD_ERR_STATE, "the step log holds whole-world counts; a slab's caller sums them itself");
+    CK(cudaSetDevice(s->cfg.device));
+    // No device-wide synchronisation here: another handle's thread may be capturing a graph (an ensemble),
+    // during which cudaDeviceSynchronize is an error.  cudaFree waits for the device by itself; the caller
+    // must not have steps of THIS handle in flight (enable the log before stepping, resize after a read).
+    drop_graphs(s);  // the captured launches hold the log pointer by value
+    if (s->P.step_log) { cudaFree(s->P.step_log); s->P.step_log = nullptr; }
+    s->P.log_cap = 0;
+    if (capacity_rows) {
+        CK(cudaMalloc(&s->P.step_log, (size_t)capacity_rows * PD_LOG_ROW_WORDS * sizeof(unsigned long long)));
+        s->P.log_cap = capacity_rows;
+    }
+    CK(cudaMemsetAsync(&s->P.ctr->log_n, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream));
+    return PD_OK;
+}
+
+int pd_read_step_log(pd_sim* s, uint64_t* rows, uint32_t max_rows, uint32_t* n_rows, void* stream) {
+    if (!s || !rows || !n_rows) return fail(PD_ERR_INVALID, "NULL argument");
+    if (!s->P.step_log) return fail(PD_ERR_STATE, "step log not enabled (pd_set_step_log)");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(s->cfg.device));
+    unsigned int head[2] = {0, 0};  // log_n, log_dropped
+    CK(cudaMemcpyAsync(head, &s->P.ctr->log_n, sizeof head, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint32_t n = head[0] < max_rows ? head[0] : max_rows;
+    if (n) CK(cudaMemcpyAsync(rows, s->P.step_log, (size_t)n * PD_LOG_ROW_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemsetAsync(&s->P.ctr->log_n, 0, 2 * sizeof(unsigned int), st));
+    CK(cudaStreamSynchronize(st));
+    *n_rows = n;
+    if (head[1] || head[0] > max_rows)
+        return fail(PD_ERR_OVERFLOW, "step log: %u rows did not fit (capacity %u, read %u of %u)", head[1], s->P.log_cap, n, head[0]);
     return PD_OK;
 }
 

@@ -155,18 +155,32 @@ def simulate(cfg: SimConfig, steps: int, log_file: Optional[str] = None,
         log = StepLog(cfg, steps, output_every_n_steps)
         counts, n = sim.counts()
         log.frame(0, counts, n)  # frame 0: counts pre-filled by init_fn (model.py:1517-1522)
-        done = 0
-        while done < steps:
-            chunk = min(output_every_n_steps, steps - done)
-            sim.step(chunk, want_counts=True)
-            done += chunk
-            counts, n = sim.counts()
-            if done % output_every_n_steps == 0 or done == steps:
-                log.frame(done, counts, n)
-            if verbose:
-                print(f"step {done}: agents {n}")
-            if n <= 0:  # exit_condition_fn (model.py:1583-1588)
-                break
+        # The logged counts stay on the device (pd_set_step_log): up to `cap` frames are queued without a host
+        # synchronisation in between, then read back together.
+        every = max(1, int(output_every_n_steps))
+        cap = max(1, min(1024, -(-steps // every)))
+        sim.enable_step_log(cap)
+        done, extinct = 0, False
+        while done < steps and not extinct:
+            queued = 0
+            while done < steps and queued < cap:
+                if every == 1:
+                    chunk = min(cap - queued, steps - done)
+                    sim.step(chunk, want_counts="every")
+                    queued += chunk
+                else:
+                    chunk = min(every, steps - done)
+                    sim.step(chunk, want_counts=True)
+                    queued += 1
+                done += chunk
+            for row in sim.read_step_log():
+                log.frame(int(row[0]), row[2:], int(row[1]))
+                if verbose:
+                    print(f"step {int(row[0])}: agents {int(row[1])}")
+                if row[1] <= 0:  # exit_condition_fn (model.py:1583-1588)
+                    extinct = True
+                    break
+        sim.counts()  # raises if a sparse list overflowed during the run
         if log_file:
             log.write(log_file)
         return log

@@ -127,6 +127,7 @@ class Simulation:
             self.tf = torch.zeros((H, W), dtype=torch.uint8, device=self.device)
             torch.cuda.synchronize(self.device)
         self._stream = stream
+        self._log_cap = 0
         self._h = C.c_void_p()
         ccfg = config.to_c(row0, rows, ghost)
         self._check(self.lib.pd_create(C.byref(ccfg), C.byref(self._h)))
@@ -170,9 +171,11 @@ class Simulation:
         torch.cuda.synchronize(self.device)
         self._check(self.lib.pd_sync_state(self._h, self.stream_ptr))
 
-    def step(self, n_steps: int = 1, want_counts: bool = True):
-        """Main layers 1-7 (model.py:2140-2163) n_steps times; asynchronous."""
-        self._check(self.lib.pd_step(self._h, int(n_steps), self.stream_ptr, int(bool(want_counts))))
+    def step(self, n_steps: int = 1, want_counts=True):
+        """Main layers 1-7 (model.py:2140-2163) n_steps times; asynchronous.  want_counts: False, True (the
+        strategy counts of the last step) or "every" (of every step, for the device-resident step log)."""
+        wc = 2 if want_counts == "every" else int(bool(want_counts))
+        self._check(self.lib.pd_step(self._h, int(n_steps), self.stream_ptr, wc))
 
     def counts(self):
         """(population_strat_count[16], agent count) -- step_fn (model.py:1405-1419) and logCount (:185)."""
@@ -194,6 +197,18 @@ class Simulation:
         v = C.c_uint64()
         self._check(self.lib.pd_read_agent_steps(self._h, C.byref(v), self.stream_ptr))
         return int(v.value)
+
+    def enable_step_log(self, capacity_rows: int):
+        """Keep (step, agent count, 16 counts) of every counted step on the device (0 = off)."""
+        self._check(self.lib.pd_set_step_log(self._h, int(capacity_rows), self.stream_ptr))
+        self._log_cap = int(capacity_rows)
+
+    def read_step_log(self) -> np.ndarray:
+        """Rows logged since the last call, oldest first: int64 [n, 18] = step, agents, counts[16]."""
+        buf = (C.c_uint64 * (18 * max(1, self._log_cap)))()
+        n = C.c_uint32()
+        self._check(self.lib.pd_read_step_log(self._h, buf, self._log_cap, C.byref(n), self.stream_ptr))
+        return np.frombuffer(buf, dtype=np.uint64, count=18 * n.value).reshape(n.value, 18).astype(np.int64)
 
     def graph_replays(self) -> int:
         """Steps run by replaying a captured CUDA graph (small worlds on an explicit stream)."""

@@ -119,8 +119,8 @@ int pd_init_population(pd_sim* sim, uint64_t n_agents, void* stream);
 int pd_sync_state(pd_sim* sim, void* stream);
 
 /* Run n_steps model steps (main layers 1-7, model.py:2140-2163) asynchronously on `stream`.
- * want_counts != 0 also produces the 16 strategy counts of step_fn (:1405-1419) for the
- * LAST of the n_steps (the population total is always maintained). */
+ * want_counts = 1 also produces the 16 strategy counts of step_fn (:1405-1419) for the LAST of
+ * the n_steps, want_counts = 2 for every step (the population total is always maintained). */
 int pd_step(pd_sim* sim, uint32_t n_steps, void* stream, int want_counts);
 
 /* population_strat_count[16] (bin = 4*my + other, model.py:1413-1419) and the agent count
@@ -159,6 +159,18 @@ int pd_step_part(pd_sim* sim, int part, int arg, void* stream, int want_counts);
 /* Sum over all executed steps of the population at the START of the step (the numerator of
  * the agent-steps/s metric).  Synchronises `stream`. */
 int pd_read_agent_steps(pd_sim* sim, uint64_t* agent_steps, void* stream);
+
+/* Device-resident step log (the reference logs population_strat_count and the agent count every
+ * OUTPUT_EVERY_N_STEPS steps, model.py:180-187, reading them back on the host each time).  With the log
+ * enabled, every step that computes counts (pd_step's want_counts: 1 = the call's last step, 2 = every
+ * step) appends one row of PD_LOG_ROW_WORDS u64 -- step index after the step, agent count, 16 counts --
+ * to a device buffer, so a whole run can be queued without a host synchronisation per logged step.
+ * pd_read_step_log synchronises `stream`, copies up to max_rows rows (oldest first) and empties the log;
+ * rows beyond the capacity are dropped and make the call return PD_ERR_OVERFLOW.  Whole worlds only.
+ * Call pd_set_step_log while no step of this handle is in flight (before stepping, or after a read). */
+#define PD_LOG_ROW_WORDS 18
+int pd_set_step_log(pd_sim* sim, uint32_t capacity_rows, void* stream);
+int pd_read_step_log(pd_sim* sim, uint64_t* rows, uint32_t max_rows, uint32_t* n_rows, void* stream);
 
 /* Per-kernel device timing: with profiling on, pd_step records a CUDA event between every
  * two kernel launches; pd_read_profile synchronises `stream` and returns the accumulated

@@ -361,3 +361,38 @@ def test_graph_replay_equals_direct_launches_and_oracle(width):
     finally:
         g.close()
         d.close()
+
+
+def test_device_step_log_equals_per_step_readback():
+    """pd_set_step_log: counts of every counted step stay on the device and are read back together; they must
+    equal what pd_read_counts returns step by step, in order, with the step index and the agent count."""
+    import torch
+    from pdabm_b200 import Simulation, SimConfig, PdabmError
+    kw = dict(width=128, seed=5, env_noise=0.05, mutation_rate=0.02)
+    a = Simulation(SimConfig(**kw), stream=torch.cuda.Stream())
+    b = Simulation(SimConfig(**kw))
+    try:
+        a.init_population()
+        b.init_population()
+        a.enable_step_log(64)
+        a.step(10, want_counts="every")
+        a.step(5, want_counts=True)
+        a.step(3, want_counts=False)
+        a.step(1, want_counts=True)
+        rows = a.read_step_log()
+        assert [int(r[0]) for r in rows] == list(range(1, 11)) + [15, 19]
+        expect = {}
+        for s in range(1, 20):
+            b.step(1)
+            expect[s] = b.counts()
+        for r in rows:
+            counts, n = expect[int(r[0])]
+            assert int(r[1]) == n and np.array_equal(r[2:], counts), f"step {int(r[0])}"
+        assert a.read_step_log().shape == (0, 18)  # emptied by the read
+        a.enable_step_log(4)
+        a.step(6, want_counts="every")
+        with pytest.raises(PdabmError):
+            a.read_step_log()
+    finally:
+        a.close()
+        b.close()
