@@ -198,6 +198,30 @@ class Simulation:
         self._check(self.lib.pd_read_agent_steps(self._h, C.byref(v), self.stream_ptr))
         return int(v.value)
 
+    @property
+    def step_index(self) -> int:
+        """Index of the next step to run (a Philox key word: a run is resumed by restoring it with the planes)."""
+        v = C.c_uint32()
+        self._check(self.lib.pd_get_step(self._h, C.byref(v)))
+        return int(v.value)
+
+    @step_index.setter
+    def step_index(self, step: int):
+        self._check(self.lib.pd_set_step(self._h, int(step)))
+
+    def save_checkpoint(self, path: str):
+        """World + step index as one .npz: everything a run needs to continue bit-identically."""
+        pl = self.planes()
+        np.savez_compressed(path, occ=pl["occ"], energy=pl["energy"], trait=pl["trait"], strat=pl["strat"],
+                            step=np.int64(self.step_index), seed=np.uint64(self.cfg.seed & 0xFFFFFFFFFFFFFFFF))
+
+    def load_checkpoint(self, path: str):
+        with np.load(path) as z:
+            if int(z["seed"]) != (self.cfg.seed & 0xFFFFFFFFFFFFFFFF):
+                raise PdabmError("checkpoint was written with a different seed: the run would not continue identically")
+            self.set_state(z["occ"], z["energy"], z["trait"], z["strat"])
+            self.step_index = int(z["step"])
+
     def enable_step_log(self, capacity_rows: int):
         """Keep (step, agent count, 16 counts) of every counted step on the device (0 = off)."""
         self._check(self.lib.pd_set_step_log(self._h, int(capacity_rows), self.stream_ptr))
@@ -225,12 +249,6 @@ class Simulation:
         n = C.c_uint32()
         self._check(self.lib.pd_read_profile(self._h, ms, C.byref(n), self.stream_ptr))
         return {k: float(ms[i]) for i, k in enumerate(self.KERNELS)}, int(n.value)
-
-    @property
-    def step_index(self) -> int:
-        v = C.c_uint32()
-        self._check(self.lib.pd_get_step(self._h, C.byref(v)))
-        return int(v.value)
 
     def planes(self) -> Dict[str, np.ndarray]:
         """Download the world as NumPy planes (same keys as the oracle's ``planes()``)."""

@@ -396,3 +396,37 @@ def test_device_step_log_equals_per_step_readback():
     finally:
         a.close()
         b.close()
+
+
+def test_checkpoint_resume_is_bit_identical(tmp_path):
+    """Planes + step index are the whole state of a run: a fresh handle that loads them continues exactly like
+    the uninterrupted run (the step index is a Philox key word and lives on the device)."""
+    import torch
+    from pdabm_b200 import Simulation, SimConfig, PdabmError
+    kw = dict(width=128, seed=2024, env_noise=0.05, mutation_rate=0.02, strategy_per_trait=1)
+    a = Simulation(SimConfig(**kw))
+    b = Simulation(SimConfig(**kw))
+    c = Simulation(SimConfig(**kw), stream=torch.cuda.Stream())  # resumes through the graph-replay path
+    d = Simulation(SimConfig(**{**kw, "seed": 1}))
+    try:
+        a.init_population()
+        a.step(70)
+        b.init_population()
+        b.step(41)
+        assert b.step_index == 41
+        path = str(tmp_path / "ckpt.npz")
+        b.save_checkpoint(path)
+        c.load_checkpoint(path)
+        assert c.step_index == 41
+        c.step(29)
+        pa, pc = a.planes(), c.planes()
+        for k in ("occ", "trait", "strat", "energy"):
+            assert np.array_equal(pa[k], pc[k]), f"plane {k} differs after resume"
+        ca, na = a.counts()
+        cc, nc = c.counts()
+        assert na == nc and np.array_equal(ca, cc)
+        with pytest.raises(PdabmError):
+            d.load_checkpoint(path)
+    finally:
+        for s in (a, b, c, d):
+            s.close()
