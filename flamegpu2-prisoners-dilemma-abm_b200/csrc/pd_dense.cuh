@@ -152,6 +152,14 @@ __device__ __forceinline__ uint32_t nonzero_bytes(uint32_t v) {
     return (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
 }
 
+// bit 7 of every byte of v that has two or more bits set
+__device__ __forceinline__ uint32_t multi_bit_bytes(uint32_t v) {
+    uint32_t c = v - ((v >> 1) & 0x55555555u);
+    c = (c & 0x33333333u) + ((c >> 2) & 0x33333333u);
+    c = (c + (c >> 4)) & 0x0F0F0F0Fu;        // bits set per byte, 0..8
+    return (c + 0x7E7E7E7Eu) & 0x80808080u;  // >= 2
+}
+
 // Reserve slots in up to 32/BITS shared-memory lists with ONE warp scan: field k (BITS wide) of `n` is the
 // number of entries this lane appends to list k, cnt[k] is that list's counter; the warp's sum per field
 // must fit in BITS bits.  The start offsets come back in off[k].  All 32 lanes must call.
@@ -504,6 +512,31 @@ __device__ __forceinline__ int winner_of(const Params& p, uint8_t* s_cl, int st,
     return best;
 }
 
+// Contested cells (two or more claim bits) of tile + 1-ring are listed and resolved in a phase of their own,
+// one lane per cell: the Philox rounds of a contest then run once per cell on a few full-ish warps, instead of
+// once per claimant AND per claimed cell inside the divergent work loops (17 % of k_repro_commit's instructions).
+// append_contested: the cells of one 4-byte word of s_cl starting at shared index si0.
+__device__ __forceinline__ void append_contested(uint32_t c4, int si0, uint16_t* s_ct, unsigned int* s_nct) {
+    if (!(c4 & (c4 - 1u))) return;  // at most one bit in the whole word
+    for (uint32_t m = multi_bit_bytes(c4); m; m &= m - 1) s_ct[atomicAdd(s_nct, 1u)] = (uint16_t)(si0 + ((__ffs(m) - 1) >> 3));
+}
+// the ring around the tile (rows 1 and TH+2, columns 15 and TW+16 of the 2-halo layout)
+template <int TW, int TH>
+__device__ __forceinline__ void append_contested_ring(const uint8_t* s_cl, uint16_t* s_ct, unsigned int* s_nct) {
+    constexpr int SW = TW + 32, NRING = 2 * (TW + 2) + 2 * TH;
+    for (int i = threadIdx.x; i < NRING; i += NT) {
+        int st;
+        if (i < TW + 2) st = 1 * SW + 15 + i;
+        else if (i < 2 * (TW + 2)) st = (TH + 2) * SW + 15 + (i - (TW + 2));
+        else {
+            const int k = i - 2 * (TW + 2);
+            st = (2 + (k >> 1)) * SW + ((k & 1) ? (16 + TW) : 15);
+        }
+        const uint32_t m = s_cl[st];
+        if (m & (m - 1u)) s_ct[atomicAdd(s_nct, 1u)] = (uint16_t)st;
+    }
+}
+
 // copy a CTA-local list of local cell indices into its reserved range of a global list
 template <int TW>
 __device__ __forceinline__ void copy_cells(const Params& p, const uint16_t* s_list, unsigned int n,
@@ -541,7 +574,8 @@ __global__ void __launch_bounds__(NT, 8) k_move_commit(const __grid_constant__ P
     __shared__ uint8_t s_lost_state[NC];
     __shared__ unsigned int s_q[4];  // queue lengths: 0 claimants, 1 claimed cells
     __shared__ int s_dxy[16], s_off[8];  // dx[8] dy[8]; shared-memory offset of neighbour d
-    __shared__ unsigned int s_n[4];  // 1 lost, 2 base
+    __shared__ unsigned int s_n[4];  // 1 lost, 2 base, 3 contested cells
+    uint16_t* s_ct = s_lost;         // contested cells; consumed before the first loser is listed
     const int tid = threadIdx.x;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     if (tid < 4) s_n[tid] = s_q[tid] = 0;
@@ -561,6 +595,8 @@ __global__ void __launch_bounds__(NT, 8) k_move_commit(const __grid_constant__ P
         reinterpret_cast<uint2*>(s_out)[i] = make_uint2(t8.x & 0x87878787u, t8.y & 0x87878787u);  // OCC | GHOST | trait
         const uint32_t claim[2] = {(t8.x << 1) & 0x80808080u, (t8.y << 1) & 0x80808080u};
         const uint32_t tgt[2] = {nonzero_bytes(c8.x), nonzero_bytes(c8.y)};
+        append_contested(c8.x, si, s_ct, &s_n[3]);
+        append_contested(c8.y, si + 4, s_ct, &s_n[3]);
         uint32_t off[2];
         wreserve<2, 16>(s_q, (uint32_t)(__popc(claim[0]) + __popc(claim[1]))
                                  | ((uint32_t)(__popc(tgt[0]) + __popc(tgt[1])) << 16), off);
@@ -570,6 +606,9 @@ __global__ void __launch_bounds__(NT, 8) k_move_commit(const __grid_constant__ P
             for (uint32_t m = tgt[h]; m; m &= m - 1) s_work[NC - 1 - off[1]++] = (uint16_t)(i * 8 + h * 4 + ((__ffs(m) - 1) >> 3));
         }
     }
+    append_contested_ring<TW, TH>(s_cl, s_ct, &s_n[3]);
+    __syncthreads();
+    for (unsigned int k = tid; k < s_n[3]; k += NT) winner_of<TW>(p, s_cl, s_ct[k], x0, y0, TravelKey());  // caches the winner
     __syncthreads();
     const unsigned int n_claim = s_q[0], n_tgt = s_q[1];
     unsigned int n_moved = 0;
@@ -714,10 +753,13 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
     __shared__ unsigned int s_bins[16];
     __shared__ unsigned int s_n[8];   // 0 claimants, 1 births listed, 2 lost, 3 risk, 4 dead, 5 n_old, 6 birth cells, 7 living deaths
     __shared__ unsigned int s_base[4];
+    __shared__ unsigned int s_nct;   // contested cells
+    uint16_t* s_ct = s_lost;         // their list; consumed before the first loser is listed
     __shared__ int s_dxy[16], s_off[8];  // dx[8] dy[8]; shared-memory offset of neighbour d
     const int tid = threadIdx.x;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     if (tid < 8) s_n[tid] = 0;
+    if (tid == 0) s_nct = 0;
     if (tid < 16) s_bins[tid] = 0;
     if (tid < 8) { s_dxy[tid] = DX(tid); s_dxy[8 + tid] = DY(tid); s_off[tid] = DY(tid) * SW + DX(tid); }
     // pull the tile's energies into L2 now: they are read two barriers later, and the kernel has no registers
@@ -775,10 +817,14 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
                 if ((c4 >> (8 * k)) & 0xFFu) s_work[NC - 1 - atomicAdd(&s_n[6], 1u)] = (uint16_t)cl;  // a child is born here
             }
         }
+        append_contested(c4, si, s_ct, &s_nct);
         *reinterpret_cast<uint32_t*>(p.tfA + cell0) = out4;
         *reinterpret_cast<float4*>(p.E0 + cell0) = make_float4(ev[0], ev[1], ev[2], ev[3]);
     }
-    __syncthreads();  // the queue is complete; the dense stores above are ordered before the patches below
+    append_contested_ring<TW, TH>(s_cl, s_ct, &s_nct);
+    __syncthreads();  // the queues are complete; the dense stores above are ordered before the patches below
+    for (unsigned int k = tid; k < s_nct; k += NT) winner_of<TW>(p, s_cl, s_ct[k], x0, y0, ReproKey());  // caches the winner
+    __syncthreads();
     const bool owned_tile = row_owned(p, y0);
     // two homogeneous queues (no divergence between the two kinds of work inside a warp)
     const unsigned int n_claim = s_n[0], n_born = s_n[6];
