@@ -147,6 +147,19 @@ __device__ __forceinline__ void wappend4(unsigned int* cnt, uint16_t* list, uint
     }
 }
 
+// Shared-memory atomic add that the compiler leaves alone.  For `atomicAdd(&counter, 1)` in divergent code nvcc
+// emits a warp-aggregation sequence (vote, popc, leader election, shuffle: ~20 issue slots per site); with the
+// handful of lanes that append to a queue at any one site here, letting the hardware serialise the lanes of one
+// ATOMS is cheaper (profiles/README.md).
+__device__ __forceinline__ unsigned int satom_add(unsigned int* counter, unsigned int v) {
+    unsigned int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;"
+                 : "=r"(old)
+                 : "r"((unsigned int)__cvta_generic_to_shared(counter)), "r"(v)
+                 : "memory");
+    return old;
+}
+
 // bit 7 of every non-zero byte of v
 __device__ __forceinline__ uint32_t nonzero_bytes(uint32_t v) {
     return (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
@@ -518,7 +531,7 @@ __device__ __forceinline__ int winner_of(const Params& p, uint8_t* s_cl, int st,
 // append_contested: the cells of one 4-byte word of s_cl starting at shared index si0.
 __device__ __forceinline__ void append_contested(uint32_t c4, int si0, uint16_t* s_ct, unsigned int* s_nct) {
     if (!(c4 & (c4 - 1u))) return;  // at most one bit in the whole word
-    for (uint32_t m = multi_bit_bytes(c4); m; m &= m - 1) s_ct[atomicAdd(s_nct, 1u)] = (uint16_t)(si0 + ((__ffs(m) - 1) >> 3));
+    for (uint32_t m = multi_bit_bytes(c4); m; m &= m - 1) s_ct[satom_add(s_nct, 1u)] = (uint16_t)(si0 + ((__ffs(m) - 1) >> 3));
 }
 // the ring around the tile (rows 1 and TH+2, columns 15 and TW+16 of the 2-halo layout)
 template <int TW, int TH>
@@ -533,7 +546,7 @@ __device__ __forceinline__ void append_contested_ring(const uint8_t* s_cl, uint1
             st = (2 + (k >> 1)) * SW + ((k & 1) ? (16 + TW) : 15);
         }
         const uint32_t m = s_cl[st];
-        if (m & (m - 1u)) s_ct[atomicAdd(s_nct, 1u)] = (uint16_t)st;
+        if (m & (m - 1u)) s_ct[satom_add(s_nct, 1u)] = (uint16_t)st;
     }
 }
 
@@ -698,7 +711,7 @@ __global__ void __launch_bounds__(NT) k_repro_claim(const __grid_constant__ Para
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (((occ4 >> (8 * k)) & 0x80u) && ev[k] >= p.reproduce_min_energy)  // :978-979
-                    s_par[atomicAdd(&s_n[0], 1u)] = (uint16_t)(i * 4 + k);
+                    s_par[satom_add(&s_n[0], 1u)] = (uint16_t)(i * 4 + k);
         }
     }
     __syncthreads();
@@ -795,26 +808,26 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
             const uint32_t t = (t4 >> (8 * k)) & 0xFFu;
             const int cl = i * 4 + k;
             if (t & TF_CLAIM) {           // a parent with a claim: decided in the queue below
-                s_work[atomicAdd(&s_n[0], 1u)] = (uint16_t)cl;
+                s_work[satom_add(&s_n[0], 1u)] = (uint16_t)cl;
             } else if (t & TF_OCC) {      // everybody else pays the cost of living now (:1357-1368)
                 const uint32_t trait = t & TF_TRAIT;
                 float e = ev[k];
                 if (punish(p, e)) {
                     out4 |= (TF_OCC | trait) << (8 * k);
                     ev[k] = e;
-                    if (e <= p.risk_thr) s_risk[atomicAdd(&s_n[3], 1u)] = (uint16_t)cl;
+                    if (e <= p.risk_thr) s_risk[satom_add(&s_n[3], 1u)] = (uint16_t)cl;
                     if (p.want_counts) atomicAdd(&s_bins[count_bin((st4 >> (8 * k)) & 0xFFu, trait)], 1u);
                 } else {
                     // dies (:1364-1366) -- but the punishment layer runs AFTER the god submodel, so the
                     // cell stays occupied for the reproduction retry rounds; k_finalize clears it
                     out4 |= (TF_OCC | TF_DYING) << (8 * k);
                     ev[k] = 0.0f;
-                    s_dead[atomicAdd(&s_n[4], 1u)] = (uint16_t)cl;
+                    s_dead[satom_add(&s_n[4], 1u)] = (uint16_t)cl;
                     ++n_dead;
                 }
             } else {
                 ev[k] = 0.0f;
-                if ((c4 >> (8 * k)) & 0xFFu) s_work[NC - 1 - atomicAdd(&s_n[6], 1u)] = (uint16_t)cl;  // a child is born here
+                if ((c4 >> (8 * k)) & 0xFFu) s_work[NC - 1 - satom_add(&s_n[6], 1u)] = (uint16_t)cl;  // a child is born here
             }
         }
         append_contested(c4, si, s_ct, &s_nct);
@@ -854,13 +867,13 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
             if (alive) {
                 p.tfA[cell] = (uint8_t)(TF_OCC | trait);
                 p.E0[cell] = e;
-                if (e <= p.risk_thr) s_risk[atomicAdd(&s_n[3], 1u)] = (uint16_t)cl;
+                if (e <= p.risk_thr) s_risk[satom_add(&s_n[3], 1u)] = (uint16_t)cl;
                 if (p.want_counts) atomicAdd(&s_bins[count_bin(p.strat[cell], trait)], 1u);
             } else if (won) {
                 p.tfA[cell] = (uint8_t)(TF_OCC | TF_DYING);
                 p.E0[cell] = 0.0f;
-                s_dead[atomicAdd(&s_n[4], 1u)] = (uint16_t)cl;
-                atomicAdd(&s_n[7], 1u);
+                s_dead[satom_add(&s_n[4], 1u)] = (uint16_t)cl;
+                satom_add(&s_n[7], 1u);
             } else {
                 p.tfA[cell] = (uint8_t)(TF_OCC | trait);
                 p.E0[cell] = e_in;
@@ -871,7 +884,7 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
                 }
             }
             if (!won) {
-                const unsigned int slot = atomicAdd(&s_n[2], 1u);
+                const unsigned int slot = satom_add(&s_n[2], 1u);
                 s_lost[slot] = (uint16_t)cl;
                 s_lost_state[slot] = (uint8_t)(0xC0u | (uint32_t)d);
             }
@@ -887,7 +900,7 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
                 // Not written into the planes yet: near the carrying capacity almost every newborn is culled
                 // in the same step (k_finalize), so it only goes on the newborn list with its payload.  If
                 // retry rounds run, k_repro_retry first marks the listed cells as occupied.
-                const unsigned int slot = atomicAdd(&s_n[1], 1u);
+                const unsigned int slot = satom_add(&s_n[1], 1u);
                 if (slot < (unsigned int)NBMAX) {
                     s_birth[slot] = (uint16_t)cl;
                     s_birth_e[slot] = ce;
@@ -900,8 +913,8 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
             }
         }
     }
-    if (n_old) atomicAdd(&s_n[5], n_old);
-    if (n_dead) atomicAdd(&s_n[7], n_dead);
+    if (n_old) satom_add(&s_n[5], n_old);
+    if (n_dead) satom_add(&s_n[7], n_dead);
     __syncthreads();
     // one atomic per list per CTA, then plain copies.  A ghost tile of a slab only contributes its claim
     // losers (the retry rounds need them); its newborns, deaths and counts belong to the owning slab.
