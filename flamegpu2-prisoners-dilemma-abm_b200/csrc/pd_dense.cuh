@@ -77,14 +77,27 @@ __device__ __forceinline__ void load_tile_vec(const Params& p, const uint8_t* __
     }
 }
 
-// warp-aggregated append to a shared- or global-memory counter; all 32 lanes must call
+// Shared-memory atomic add that the compiler leaves alone.  For `atomicAdd(&counter, 1)` in divergent code nvcc
+// emits a warp-aggregation sequence (vote, popc, leader election, shuffle: ~20 issue slots per site); with the
+// handful of lanes that append to a queue at any one site here, letting the hardware serialise the lanes of one
+// ATOMS is cheaper (profiles/README.md).
+__device__ __forceinline__ unsigned int satom_add(unsigned int* counter, unsigned int v) {
+    unsigned int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;"
+                 : "=r"(old)
+                 : "r"((unsigned int)__cvta_generic_to_shared(counter)), "r"(v)
+                 : "memory");
+    return old;
+}
+
+// warp-aggregated append to a shared-memory counter; all 32 lanes must call
 __device__ __forceinline__ uint32_t wappend(unsigned int* counter, bool pred) {
     const unsigned int m = __ballot_sync(FULL, pred);
     if (m == 0u) return 0u;
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(m) - 1;
     unsigned int base = 0;
-    if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(m));
+    if (lane == leader) base = satom_add(counter, (unsigned int)__popc(m));
     base = __shfl_sync(FULL, base, leader);
     return base + (unsigned int)__popc(m & ((1u << lane) - 1u));
 }
@@ -137,7 +150,7 @@ __device__ __forceinline__ void wappend4(unsigned int* cnt, uint16_t* list, uint
     const int total = __shfl_sync(FULL, incl, 31);
     if (total == 0) return;
     unsigned int base = 0;
-    if (lane == 31) base = atomicAdd(cnt, (unsigned int)total);
+    if (lane == 31) base = satom_add(cnt, (unsigned int)total);
     base = __shfl_sync(FULL, base, 31);
     unsigned int k = base + (unsigned int)(incl - n);
     while (occ4) {
@@ -145,19 +158,6 @@ __device__ __forceinline__ void wappend4(unsigned int* cnt, uint16_t* list, uint
         occ4 &= occ4 - 1;
         list[k++] = (uint16_t)(b0 + b);
     }
-}
-
-// Shared-memory atomic add that the compiler leaves alone.  For `atomicAdd(&counter, 1)` in divergent code nvcc
-// emits a warp-aggregation sequence (vote, popc, leader election, shuffle: ~20 issue slots per site); with the
-// handful of lanes that append to a queue at any one site here, letting the hardware serialise the lanes of one
-// ATOMS is cheaper (profiles/README.md).
-__device__ __forceinline__ unsigned int satom_add(unsigned int* counter, unsigned int v) {
-    unsigned int old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;"
-                 : "=r"(old)
-                 : "r"((unsigned int)__cvta_generic_to_shared(counter)), "r"(v)
-                 : "memory");
-    return old;
 }
 
 // bit 7 of every non-zero byte of v
@@ -197,7 +197,7 @@ __device__ __forceinline__ void wreserve(unsigned int* cnt, uint32_t n, uint32_t
     uint32_t base = 0;
     if (lane < NL) {
         const uint32_t t = (total >> (BITS * lane)) & FM;
-        if (t) base = atomicAdd(&cnt[lane], t);
+        if (t) base = satom_add(&cnt[lane], t);
     }
 #pragma unroll
     for (int k = 0; k < NL; ++k) off[k] = __shfl_sync(FULL, base, k) + ((excl >> (BITS * k)) & FM);
@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(NT, 8) k_move_commit(const __grid_constant__ P
             if (winner_of<TW>(p, s_cl, st, x0, y0, TravelKey()) == 7 - d) {
                 s_out[cl] = (uint8_t)TF_GHOST;  // moved away; still blocks movers this step (B-13)
             } else {                            // :940-943 -> retry with the same roll
-                const unsigned int slot = atomicAdd(&s_n[1], 1u);
+                const unsigned int slot = satom_add(&s_n[1], 1u);
                 s_lost[slot] = (uint16_t)cl;
                 s_lost_state[slot] = (uint8_t)(0xC0u | (uint32_t)d);
             }
