@@ -786,7 +786,8 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
     __syncthreads();
     scatter_claims<TW, TH, 4>(s_tf, s_cl, s_dxy);
     __syncthreads();
-    // ---- dense scan, 4 cells per thread
+    // ---- dense scan, 4 cells per thread, branch-free per cell; the rare cells (claimants, birth cells, at-risk,
+    // dying) are appended to their queues from bit masks
     unsigned int n_old = 0, n_dead = 0;
     for (int i = tid; i < NC / 4; i += NT) {
         const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
@@ -794,42 +795,48 @@ __global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ 
         const size_t cell0 = ((size_t)(y0 + ly) << p.log2W) + x0 + lx;
         const uint32_t t4 = *reinterpret_cast<const uint32_t*>(s_tf + si);
         const uint32_t c4 = *reinterpret_cast<const uint32_t*>(s_cl + si);
+        const uint32_t occ4 = t4 & 0x80808080u;
+        const uint32_t claim4 = (t4 << 1) & 0x80808080u;  // parents with a claim: decided in the queue below
         float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t st4 = 0;
-        if (t4 & 0x80808080u) {
+        if (occ4) {
             e4 = *reinterpret_cast<const float4*>(p.E1 + cell0);
             if (p.want_counts) st4 = *reinterpret_cast<const uint32_t*>(p.strat + cell0);
         }
         float ev[4] = {e4.x, e4.y, e4.z, e4.w};
-        uint32_t out4 = 0;
-        n_old += __popc(t4 & 0x80808080u);
+        const uint32_t pay4 = occ4 & ~claim4;               // everybody else pays the cost of living now (:1357-1368)
+        const uint32_t born4 = nonzero_bytes(c4) & ~occ4;   // a child is born in an empty cell that received a claim
+        uint32_t dead4 = 0, risk4 = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t t = (t4 >> (8 * k)) & 0xFFu;
-            const int cl = i * 4 + k;
-            if (t & TF_CLAIM) {           // a parent with a claim: decided in the queue below
-                s_work[satom_add(&s_n[0], 1u)] = (uint16_t)cl;
-            } else if (t & TF_OCC) {      // everybody else pays the cost of living now (:1357-1368)
-                const uint32_t trait = t & TF_TRAIT;
-                float e = ev[k];
-                if (punish(p, e)) {
-                    out4 |= (TF_OCC | trait) << (8 * k);
-                    ev[k] = e;
-                    if (e <= p.risk_thr) s_risk[satom_add(&s_n[3], 1u)] = (uint16_t)cl;
-                    if (p.want_counts) atomicAdd(&s_bins[count_bin((st4 >> (8 * k)) & 0xFFu, trait)], 1u);
-                } else {
-                    // dies (:1364-1366) -- but the punishment layer runs AFTER the god submodel, so the
-                    // cell stays occupied for the reproduction retry rounds; k_finalize clears it
-                    out4 |= (TF_OCC | TF_DYING) << (8 * k);
-                    ev[k] = 0.0f;
-                    s_dead[satom_add(&s_n[4], 1u)] = (uint16_t)cl;
-                    ++n_dead;
-                }
-            } else {
+            const uint32_t bit = 0x80u << (8 * k);
+            float e = ev[k];
+            const bool alive = punish(p, e);
+            if (pay4 & bit) {
+                // a death (:1364-1366) keeps its cell for the reproduction retry rounds (the punishment layer runs
+                // AFTER the god submodel); k_finalize clears it
+                if (!alive) dead4 |= bit;
+                else if (e <= p.risk_thr) risk4 |= bit;
+                ev[k] = alive ? e : 0.0f;
+            } else if (!(claim4 & bit)) {
                 ev[k] = 0.0f;
-                if ((c4 >> (8 * k)) & 0xFFu) s_work[NC - 1 - satom_add(&s_n[6], 1u)] = (uint16_t)cl;  // a child is born here
             }
         }
+        // OCC | trait for the survivors, OCC | DYING for the dying, 0 for claimants (patched below) and empty cells
+        static_assert(TF_OCC == 0x80u && TF_DYING == 0x08u && TF_TRAIT == 0x03u && TF_CLAIM == 0x40u, "flag layout");
+        const uint32_t live4 = pay4 & ~dead4;
+        const uint32_t out4 = (t4 & (live4 | (live4 >> 6) | (live4 >> 7))) | dead4 | (dead4 >> 4);
+        n_old += __popc(occ4);
+        n_dead += __popc(dead4);
+        if (p.want_counts)
+            for (uint32_t m = live4; m; m &= m - 1) {
+                const int b = (__ffs(m) - 1) >> 3;
+                atomicAdd(&s_bins[count_bin((st4 >> (8 * b)) & 0xFFu, (t4 >> (8 * b)) & TF_TRAIT)], 1u);
+            }
+        for (uint32_t m = claim4; m; m &= m - 1) s_work[satom_add(&s_n[0], 1u)] = (uint16_t)(i * 4 + ((__ffs(m) - 1) >> 3));
+        for (uint32_t m = born4; m; m &= m - 1) s_work[NC - 1 - satom_add(&s_n[6], 1u)] = (uint16_t)(i * 4 + ((__ffs(m) - 1) >> 3));
+        for (uint32_t m = risk4; m; m &= m - 1) s_risk[satom_add(&s_n[3], 1u)] = (uint16_t)(i * 4 + ((__ffs(m) - 1) >> 3));
+        for (uint32_t m = dead4; m; m &= m - 1) s_dead[satom_add(&s_n[4], 1u)] = (uint16_t)(i * 4 + ((__ffs(m) - 1) >> 3));
         append_contested(c4, si, s_ct, &s_nct);
         *reinterpret_cast<uint32_t*>(p.tfA + cell0) = out4;
         *reinterpret_cast<float4*>(p.E0 + cell0) = make_float4(ev[0], ev[1], ev[2], ev[3]);
