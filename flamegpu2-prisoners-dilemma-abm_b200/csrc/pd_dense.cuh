@@ -707,11 +707,11 @@ __global__ void __launch_bounds__(NT) k_repro_claim(const __grid_constant__ Para
         reinterpret_cast<uint32_t*>(s_out)[i] = t4 & (occ4 | (occ4 >> 6) | (occ4 >> 7));  // OCC | trait of occupied cells
         if (occ4 && p.max_children > 0u) {  // :1054
             const float4 e4 = e_pre[it];
-            const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (((occ4 >> (8 * k)) & 0x80u) && ev[k] >= p.reproduce_min_energy)  // :978-979
-                    s_par[satom_add(&s_n[0], 1u)] = (uint16_t)(i * 4 + k);
+            // :978-979
+            const uint32_t par4 = occ4 & ((e4.x >= p.reproduce_min_energy ? 0x80u : 0u) | (e4.y >= p.reproduce_min_energy ? 0x8000u : 0u)
+                                          | (e4.z >= p.reproduce_min_energy ? 0x800000u : 0u)
+                                          | (e4.w >= p.reproduce_min_energy ? 0x80000000u : 0u));
+            for (uint32_t m = par4; m; m &= m - 1) s_par[satom_add(&s_n[0], 1u)] = (uint16_t)(i * 4 + ((__ffs(m) - 1) >> 3));
         }
     }
     __syncthreads();
