@@ -299,16 +299,19 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
         const uint32_t rme = valid ? s_R[si] : 0xFFFFFFFFu;
         const uint32_t kme = rme >> 11;
         // ---- who is around me, and who challenges me (bit c of gm: my neighbour 7-c does, in sub-step c, :477)
-        uint32_t occ_mask = 0, gm = 0, special = 0;
+        uint32_t occ_mask = 0, gm = 0, dflag = 0;
+        bool tie = false;
 #pragma unroll
         for (int d = 0; d < 8; ++d) {
             const uint32_t rn = s_R[si + DY(d) * SW + DX(d)];
             const uint32_t kn = rn >> 11;
             occ_mask |= (rn >> 31) << d;
-            const uint32_t hi = kn > kme ? 1u : 0u;
-            gm |= hi << (7 - d);
-            special |= ((kn == kme ? 1u : 0u) | (hi & (rn >> 10))) << d;  // truncated-roll tie, or challenger with a D code
+            gm |= (kn > kme ? 1u : 0u) << (7 - d);
+            dflag |= (rn & R_DFLAG) >> (10 - d);  // bit d: neighbour d carries a D code
+            tie |= kn == kme;
         }
+        // directions to redo exactly: challengers with a D code; on a truncated-roll tie (2^-20 per pair) all of them
+        uint32_t special = tie ? 0xFFu : (__brev(gm) >> 24) & dflag;
         if (!valid) { occ_mask = 0; gm = 0; special = 0; }
         // act[7] / act[0] of the terminal rule come from the roll order alone (get_game_list, :413):
         // a challenger that dies early still "would have challenged"
