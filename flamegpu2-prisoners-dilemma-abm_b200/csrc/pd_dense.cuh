@@ -393,16 +393,16 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
         bool mover = false;
         if (valid) {
             float e = s_e[cl];
-            int games = 0;
             bool dead = false;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 if (!((gm >> c) & 1u) || dead) continue;
-                const uint32_t o = s_qo[warp][off + __popc(gm & ((1u << c) - 1u))];
-                e = __fadd_rn(e, s_pay[o & 3u]);                   // :679-688
+                const uint32_t o = s_qo[warp][off + __popc(gm & ((1u << c) - 1u))];  // 0..3 by construction
+                e = __fadd_rn(e, s_pay[o]);                        // :679-688
                 if (e <= 0.0f) dead = true;                        // :695-697
-                else { e = fminf(e, p.max_energy); ++games; }      // :698-710
+                else e = fminf(e, p.max_energy);                   // :698-702
             }
+            const int games = cnt;  // games_played (:710) of an agent that is still alive: all of them
             if (dead) {
                 s_out[cl] = (uint8_t)TF_GHOST;
                 s_e[cl] = 0.0f;
