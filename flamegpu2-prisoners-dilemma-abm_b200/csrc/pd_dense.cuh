@@ -394,10 +394,12 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
         if (valid) {
             float e = s_e[cl];
             bool dead = false;
+            const uint8_t* my_o = &s_qo[warp][off];  // my outcomes, in sub-step order
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                if (!((gm >> c) & 1u) || dead) continue;
-                const uint32_t o = s_qo[warp][off + __popc(gm & ((1u << c) - 1u))];  // 0..3 by construction
+                if (!((gm >> c) & 1u)) continue;
+                const uint32_t o = *my_o++;                        // 0..3 by construction
+                if (dead) continue;
                 e = __fadd_rn(e, s_pay[o]);                        // :679-688
                 if (e <= 0.0f) dead = true;                        // :695-697
                 else e = fminf(e, p.max_energy);                   // :698-702
