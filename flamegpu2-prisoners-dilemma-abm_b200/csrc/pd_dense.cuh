@@ -344,10 +344,10 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
         const int off = incl - cnt;
         const int total = __shfl_sync(FULL, incl, 31);
         {
-            int k = off;
+            uint16_t* qp = &s_q[warp][off];
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-                if ((gm >> c) & 1u) s_q[warp][k++] = (uint16_t)((lane << 3) | c);
+                if ((gm >> c) & 1u) *qp++ = (uint16_t)((lane << 3) | c);
         }
         __syncwarp();
         // ---- evaluate them 32 at a time (play_response, :599-689)
@@ -398,11 +398,9 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 if (!((gm >> c) & 1u)) continue;
-                const uint32_t o = *my_o++;                        // 0..3 by construction
-                if (dead) continue;
-                e = __fadd_rn(e, s_pay[o]);                        // :679-688
-                if (e <= 0.0f) dead = true;                        // :695-697
-                else e = fminf(e, p.max_energy);                   // :698-702
+                e = __fadd_rn(e, s_pay[*my_o++]);                  // :679-688; outcomes are 0..3 by construction
+                dead |= e <= 0.0f;                                 // :695-697 -- latched: what a dead agent's energy
+                e = fminf(e, p.max_energy);                        // :698-702    does afterwards is never used
             }
             const int games = cnt;  // games_played (:710) of an agent that is still alive: all of them
             if (dead) {
