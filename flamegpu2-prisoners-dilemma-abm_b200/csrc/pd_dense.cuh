@@ -365,7 +365,9 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
                 uint32_t mine, theirs;
                 game_strategies(s_R[si_l], s_R[si_l + s_off[d]], mine, theirs);
                 need = noisy || mine == 3u || theirs == 3u;
-                s_qo[warp][q] = (uint8_t)(((mine != 1u) ? 2u : 0u) | ((theirs != 1u) ? 1u : 0u));
+                // the outcome, or -- for the games that go to the random-word pass -- the two strategies
+                s_qo[warp][q] = need ? (uint8_t)((mine << 2) | theirs)
+                                     : (uint8_t)(((mine != 1u) ? 2u : 0u) | ((theirs != 1u) ? 1u : 0u));
             }
             // the games that need random words are compacted once more: the Philox rounds then run with full lanes
             const unsigned int bal = __ballot_sync(FULL, need);
@@ -378,12 +380,11 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
             const bool active = k < n2;
             const int q = active ? s_q2[warp][k] : 0;
             const uint32_t ent = s_q[warp][q];
-            const int c = (int)(ent & 7u), d = 7 - c;
+            const int c = (int)(ent & 7u);
             const uint32_t pk = __shfl_sync(FULL, pack, (int)(ent >> 3));
             if (active) {
-                const int si_l = (int)(pk & 0xFFFFu), cl_l = (int)(pk >> 16);
-                uint32_t mine, theirs;
-                game_strategies(s_R[si_l], s_R[si_l + s_off[d]], mine, theirs);
+                const int cl_l = (int)(pk >> 16);
+                const uint32_t ms = s_qo[warp][q], mine = ms >> 2, theirs = ms & 3u;
                 const uint64_t gl = gcell_of(p, x0 + (uint32_t)(cl_l & (TW - 1)), y0 + (uint32_t)(cl_l >> LOG_TW));
                 s_qo[warp][q] = (uint8_t)game_outcome_rng(p, gl, c, mine, theirs);
             }
