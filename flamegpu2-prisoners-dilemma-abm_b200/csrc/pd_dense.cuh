@@ -419,8 +419,7 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
                 s_e[cl] = e;
             }
         }
-        const uint32_t slot = wappend(&s_n[2], mover);
-        if (mover) { s_mover[slot] = (uint16_t)cl; ++n_movers; }
+        if (mover) { s_mover[satom_add(&s_n[2], 1u)] = (uint16_t)cl; ++n_movers; }  // ~2 lanes of 32
         __syncwarp();
     }
     __syncthreads();
