@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
     __shared__ __align__(16) uint8_t s_out[NC];
     __shared__ uint16_t s_cells[NC + 2 * (TW + 2) + 2 * TH];  // agents first (from 0), then ring cells
     __shared__ uint16_t s_mover[NC];
-    __shared__ uint16_t s_q[NWARP][256];  // per-warp queue of the games that need random words: lane << 3 | c
+    __shared__ uint16_t s_q[NWARP][256];  // per-warp queue of the games: responder's shared-memory cell index << 3 | c
     __shared__ uint8_t s_qo[NWARP][256];  // their outcomes
     __shared__ uint8_t s_q2[NWARP][256];  // second level: queue slots whose game needs random words
     __shared__ unsigned int s_n[4];       // 0 agents, 1 ring cells, 2 movers
@@ -347,21 +347,19 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
             uint16_t* qp = &s_q[warp][off];
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-                if ((gm >> c) & 1u) *qp++ = (uint16_t)((lane << 3) | c);
+                if ((gm >> c) & 1u) *qp++ = (uint16_t)((si << 3) | c);
         }
         __syncwarp();
         // ---- evaluate them 32 at a time (play_response, :599-689)
-        const uint32_t pack = (uint32_t)si | ((uint32_t)cl << 16);
         int n2 = 0;
         for (int q0 = 0; q0 < total; q0 += 32) {
             const int q = q0 + lane;
             const bool active = q < total;
-            const uint32_t ent = active ? s_q[warp][q] : 0u;
+            const uint32_t ent = active ? s_q[warp][q] : 0u;  // responder's cell << 3 | sub-step
             const int d = 7 - (int)(ent & 7u);
-            const uint32_t pk = __shfl_sync(FULL, pack, (int)(ent >> 3));
             bool need = false;
             if (active) {
-                const int si_l = (int)(pk & 0xFFFFu);
+                const int si_l = (int)(ent >> 3);
                 uint32_t mine, theirs;
                 game_strategies(s_R[si_l], s_R[si_l + s_off[d]], mine, theirs);
                 need = noisy || mine == 3u || theirs == 3u;
@@ -381,11 +379,10 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
             const int q = active ? s_q2[warp][k] : 0;
             const uint32_t ent = s_q[warp][q];
             const int c = (int)(ent & 7u);
-            const uint32_t pk = __shfl_sync(FULL, pack, (int)(ent >> 3));
             if (active) {
-                const int cl_l = (int)(pk >> 16);
+                const int si_l = (int)(ent >> 3), r_l = si_l / SW;
                 const uint32_t ms = s_qo[warp][q], mine = ms >> 2, theirs = ms & 3u;
-                const uint64_t gl = gcell_of(p, x0 + (uint32_t)(cl_l & (TW - 1)), y0 + (uint32_t)(cl_l >> LOG_TW));
+                const uint64_t gl = gcell_of(p, x0 + (uint32_t)(si_l - r_l * SW - 16), y0 + (uint32_t)(r_l - 1));
                 s_qo[warp][q] = (uint8_t)game_outcome_rng(p, gl, c, mine, theirs);
             }
         }
