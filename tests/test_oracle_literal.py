@@ -17,6 +17,13 @@ CASES = {
                   init_agent_count=150),
     "dense": dict(width=16, seed=8, init_agent_count=180, max_agents=220, reproduce_min_energy=40.0,
                   reproduce_cost=10.0, payoff_cc=10.0),
+    # reproduction threshold below the cost of living: parents die of the living cost, also right after
+    # reproducing in a retry round (the regime of k_repro_commit's deferred-loser list)
+    "dying_parents": dict(width=16, seed=10, reproduce_min_energy=1.5, reproduce_cost=0.5, cost_of_living=2.0,
+                          init_energy_mu=4.0, init_energy_sigma=2.0, init_energy_min=1.0, init_agent_count=100),
+    "dying_parents_noise": dict(width=16, seed=11, reproduce_min_energy=2.0, reproduce_cost=1.0, cost_of_living=2.5,
+                                init_energy_mu=5.0, init_energy_sigma=3.0, init_energy_min=1.0, env_noise=0.1,
+                                mutation_rate=0.05, strategy_per_trait=1, init_agent_count=80, max_agents=256),
     "tiny_cap": dict(width=16, seed=9, max_agents=60, reproduce_min_energy=52.0, reproduce_cost=5.0),
 }
 
