@@ -1,4 +1,4 @@
-// The four dense sweeps of a step (v2: compacted work lists, shared-memory claim scatter).
+// The four dense sweeps of a step (compacted work lists, shared-memory claim scatter).
 //
 //   k_play_travel   tfA, strat (1-halo), E0 -> tfB, E1     search/game list/8 play sub-steps/first move_request
 //   k_move_commit   tfB (2-halo)            -> tfA          move_response round 1 (winners are pulled)
@@ -14,7 +14,10 @@
 //     32 lanes busy;
 //   * claims are resolved by scattering one bit per claimant into a shared-memory byte per target
 //     (bit j = "my neighbour j claims me"); only cells with >= 2 bits need priorities;
-//   * global list appends are aggregated per CTA (one atomicAdd per list per CTA).
+//   * global list appends are aggregated per CTA (one atomicAdd per list per CTA);
+//   * measured since (profiles/README.md): ballots / shuffles in a hot loop, nvcc's warp-aggregated
+//     atomicAdd(&shared_counter, 1) in divergent code (use satom_add) and extra __syncthreads() phases with
+//     little work in them all cost more than their instruction count suggests.
 // Every sweep is still a pure gather in global memory: a cell is written by its own tile only.
 #pragma once
 #include <cuda_runtime.h>
