@@ -6,8 +6,9 @@ src/simulation_analysis.R reads) -- the fraction of reference points that fall i
 
 The reference cannot be run in this environment (pyflamegpu is not installable), so by default the
 script only produces the band of THIS implementation; pass --reference-logs DIR to compare.
+Test infrastructure (it lives under tests/ because its `--engine oracle` mode imports oracle/).
 
-    python tools/stat_compare.py --width 512 --steps 100 --seeds 32 [--engine cuda|oracle]
+    python tests/stat_compare.py --width 512 --steps 100 --seeds 32 [--engine cuda|oracle]
                                  [--reference-logs data/] [--out bands.json]
 """
 from __future__ import annotations

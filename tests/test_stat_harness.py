@@ -1,4 +1,4 @@
-"""The statistical-comparison harness (tools/stat_compare.py) on CPU with the oracle as the engine."""
+"""The statistical-comparison harness (tests/stat_compare.py) on CPU with the oracle as the engine."""
 import importlib.util
 import json
 import os
@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-spec = importlib.util.spec_from_file_location("stat_compare", os.path.join(ROOT, "tools", "stat_compare.py"))
+spec = importlib.util.spec_from_file_location("stat_compare", os.path.join(ROOT, "tests", "stat_compare.py"))
 sc = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(sc)
 
