@@ -105,43 +105,28 @@ __device__ __forceinline__ uint32_t wappend(unsigned int* counter, bool pred) {
     return base + (unsigned int)__popc(m & ((1u << lane) - 1u));
 }
 
-// the game of sub-step c as the responder at my_g sees it -> index into Params::pay
-__device__ __forceinline__ uint32_t game_outcome_rng(const Params& p, uint64_t my_g, int c, uint32_t mine,
-                                                     uint32_t theirs) {
-    bool i_coop = mine != 1u, ch_coop = theirs != 1u;
-    const Words w = rng(p, my_g, S_GAME0 + (uint32_t)c);            // :611-612
-    if (theirs == 3u) ch_coop = (w.z >> 31) != 0u;                   // :630-635
-    if (mine == 3u) i_coop = (w.w >> 31) != 0u;                      // :663-668
-    if ((unsigned long long)w.y < p.noise_thr) ch_coop = !ch_coop;   // :638-640
-    if ((unsigned long long)w.x < p.noise_thr) i_coop = !i_coop;     // :672-674
-    return ((uint32_t)i_coop << 1) | (uint32_t)ch_coop;
-}
-
 // ------------------------------------------------------------------------------------------
 // k_play_travel (dense sweep 1).  Fuses search_for_neighbours (:352-372), get_game_list
 // (:373-440), the 8 iterations of play_challenge/play_response (:450-734) with exit_play_fn's
 // terminal rule, and the first move_request (:784-872).
 //
 // Per cell of tile + 1-ring ONE 32-bit word R is staged in shared memory:
-//     empty cell: 0        occupied: 1 | roll >> 12 (20 bits) | has-D-code | trait (2) | strategies (8)
-// so a single shared-memory load per neighbour answers "occupied?", "does it challenge me?"
-// (R[n] >> 11 > R[me] >> 11; a 2^-20 tie of the truncated rolls falls back to the exact
-// (roll, cell) order) and gives both strategies of the game.  Games that need random words
-// (RANDOM strategy or noise) are queued warp-wide so that the Philox rounds run with full lanes.
+//     empty cell: 0
+//     occupied:   bit 31 | roll (19 bits) << 12 | has-D-code << 11 | strategies (8) << 3 | trait (2) << 1
+// so one shared-memory load per neighbour answers "occupied?", "does it challenge me?" (an unsigned
+// compare of the whole word against one of two thresholds: a tie of the rolls goes to the neighbour in a
+// direction >= 4) and yields both strategies of the game.  An agent then plays its (up to) 8 games as the
+// responder in sub-step order straight from those words: the strategies, the two RANDOM coins (bits of the
+// agent's own roll call, kept next to its list entry) and -- with noise -- the two flips form the index
+// of a 256-entry payoff table in shared memory, so a game costs one table look-up and no random call.
 // ------------------------------------------------------------------------------------------
 
 constexpr uint32_t R_OCC = 0x80000000u;
-constexpr uint32_t R_DFLAG = 0x400u;
-
-// exact "neighbour d of local cell (x,y) has the higher (roll, cell)" for the tie path (:413)
-__device__ __noinline__ bool exact_higher(const Params& p, uint32_t x, uint32_t y, int d) {
-    const uint64_t g = gcell_of(p, x, y), gn = nb_gcell(p, x, y, d);
-    const uint32_t r = rng(p, g, S_ROLL).x, rn = rng(p, gn, S_ROLL).x;
-    return rn > r || (rn == r && gn > g);
-}
+constexpr uint32_t R_DFLAG = 0x800u;
+constexpr uint32_t R_LOW = 0xFFFu;  // everything below the roll
 
 // append the byte indices (b0 + k) of the bytes of `occ4` that have bit 7 set; all 32 lanes call
-__device__ __forceinline__ void wappend4(unsigned int* cnt, uint16_t* list, uint32_t occ4, int b0) {
+__device__ __forceinline__ void wappend4(unsigned int* cnt, uint32_t* list, uint32_t occ4, int b0) {
     const int lane = threadIdx.x & 31;
     const int n = __popc(occ4);
     int incl = n;
@@ -159,7 +144,7 @@ __device__ __forceinline__ void wappend4(unsigned int* cnt, uint16_t* list, uint
     while (occ4) {
         const int b = (__ffs(occ4) - 1) >> 3;
         occ4 &= occ4 - 1;
-        list[k++] = (uint16_t)(b0 + b);
+        list[k++] = (uint32_t)(b0 + b);
     }
 }
 
@@ -206,37 +191,81 @@ __device__ __forceinline__ void wreserve(unsigned int* cnt, uint32_t n, uint32_t
     for (int k = 0; k < NL; ++k) off[k] = __shfl_sync(FULL, base, k) + ((excl >> (BITS * k)) & FM);
 }
 
-// strategies of the game between me (word rme) and the neighbour (word rn) as I, the responder, see it
-__device__ __forceinline__ void game_strategies(uint32_t rme, uint32_t rn, uint32_t& mine, uint32_t& theirs) {
-    mine = (rme >> ((rn >> 7) & 6u)) & 3u;    // my strategy against the challenger's trait (:599)
-    theirs = (rn >> ((rme >> 7) & 6u)) & 3u;  // the challenger's strategy against my trait (:600)
+// entry i of the payoff table: bits 0-1 the challenger's strategy against my trait, 2-3 my strategy against
+// its trait (:599-600), 4 the challenger's RANDOM coin, 5 mine (:631, :664), 6 the challenger's noise flip,
+// 7 mine (:638-640, :672-674) -> my payoff (:677-689)
+__device__ __forceinline__ float lut_entry(const Params& p, uint32_t i) {
+    const uint32_t theirs = i & 3u, mine = (i >> 2) & 3u;
+    bool ch_coop = theirs == 3u ? ((i >> 4) & 1u) != 0u : theirs != 1u;
+    bool i_coop = mine == 3u ? ((i >> 5) & 1u) != 0u : mine != 1u;
+    if ((i >> 6) & 1u) ch_coop = !ch_coop;
+    if ((i >> 7) & 1u) i_coop = !i_coop;
+    return p.pay[((uint32_t)i_coop << 1) | (uint32_t)ch_coop];
+}
+
+// The (up to) 8 games of one agent as the responder, in sub-step order (:677-710).  rn[d] = word of neighbour d
+// (0 if it does not play against me), tA / tB = the thresholds a challenger's word exceeds.  Returns the energy
+// after the last game; `dead` latches a death (:695-697: what a dead agent's energy does afterwards is never
+// used), `any` = at least one game.
+template <bool NOISY>
+__device__ __forceinline__ float play_games(const Params& p, const float* s_lut, const uint32_t (&rn)[8], uint32_t rme,
+                                            uint32_t tA, uint32_t tB, uint32_t coins, uint64_t my_g, float e,
+                                            bool& dead, bool& any) {
+    // my strategy byte replicated through 64 bits and moved up by 4: a funnel shift by the neighbour's word --
+    // whose low 5 bits are 2 * its trait plus a multiple of 8 -- drops my strategy against that trait at bits 4-5
+    const uint32_t rep = ((rme >> 3) & 0xFFu) * 0x01010101u;
+    const uint32_t xlo = rep << 4, xhi = rep >> 4;  // (rep:rep << 4) = xhi:xlo
+    const uint32_t my_sh = (rme & 6u) | 1u;         // the neighbour's strategy against my trait -> bits 2-3
+    const char* lut = reinterpret_cast<const char*>(s_lut);
+    Words nw = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int d = 7 - c;  // my direction towards whoever challenges me in sub-step c (:477)
+        const uint32_t r = rn[d];
+        const bool hi = r > (d < 4 ? tA : tB);  // it challenges me (:413)
+        const uint32_t m = __funnelshift_r(xlo, xhi, r);
+        const uint32_t t = r >> my_sh;
+        uint32_t idx = (m & 0x30u) | (t & ~0x30u);
+        const uint32_t cs = c < 3 ? coins << (6 - 2 * c) : coins >> (2 * c - 6);
+        idx = (cs & 0xC0u) | (idx & ~0xC0u);
+        idx &= 0xFCu;
+        if (NOISY) {
+            if ((c & 1) == 0) nw = rng(p, my_g, S_NOISE0 + (uint32_t)(c >> 1));  // :611-612
+            const uint32_t my_roll = (c & 1) ? nw.z : nw.x, ch_roll = (c & 1) ? nw.w : nw.y;
+            if ((unsigned long long)ch_roll < p.noise_thr) idx |= 0x100u;  // :638-640
+            if ((unsigned long long)my_roll < p.noise_thr) idx |= 0x200u;  // :672-674
+        }
+        const float en = fminf(__fadd_rn(e, *reinterpret_cast<const float*>(lut + idx)), p.max_energy);  // :679-702
+        e = hi ? en : e;
+        dead |= e <= 0.0f;  // :695-697 (an agent enters the step with energy > 0)
+        any |= hi;
+    }
+    return e;
 }
 
 template <int TW, int TH>
 __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ Params p) {
-    constexpr int SW = TW + 32, SH = TH + 2, NC = TW * TH, NWARP = NT / 32;
+    constexpr int SW = TW + 32, SH = TH + 2, NC = TW * TH, NRING = 2 * (TW + 2) + 2 * TH;
     constexpr int LOG_TW = TW == 128 ? 7 : 4;
     static_assert(TW == 128 || TW == 16, "tile width");
+    static_assert(SH * SW < 65536, "a shared-memory cell index fits 16 bits");
     __shared__ __align__(16) uint8_t s_tf[SH * SW];
     __shared__ __align__(16) uint8_t s_st[SH * SW];
     __shared__ __align__(16) uint32_t s_R[SH * SW];
     __shared__ __align__(16) float s_e[NC];
     __shared__ __align__(16) uint8_t s_out[NC];
-    __shared__ uint16_t s_cells[NC + 2 * (TW + 2) + 2 * TH];  // agents first (from 0), then ring cells
+    // the occupied cells: agents of the tile first (from 0), then ring cells.  Entry = shared-memory cell
+    // index | the agent's 16 coin bits << 16 (written by whoever computes its roll)
+    __shared__ uint32_t s_cells[NC + NRING];
     __shared__ uint16_t s_mover[NC];
-    __shared__ uint16_t s_q[NWARP][256];  // per-warp queue of the games: responder's shared-memory cell index << 3 | c
-    __shared__ uint8_t s_qo[NWARP][256];  // their outcomes
-    __shared__ uint8_t s_q2[NWARP][256];  // second level: queue slots whose game needs random words
-    __shared__ unsigned int s_n[4];       // 0 agents, 1 ring cells, 2 movers
-    // look-up tables in shared memory: an indexed constant load (LDC) goes through the address-divergence
-    // unit, which ncu shows 61 % busy in this kernel; LDS has headroom
-    __shared__ int s_off[8];              // shared-memory offset of neighbour d
-    __shared__ float s_pay[4];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ float s_lut[256];
+    __shared__ unsigned int s_n[4];  // 0 agents, 1 ring cells, 2 movers
+    const int tid = threadIdx.x;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const bool noisy = p.noise_thr != 0ull;
-    if (tid < 4) { s_n[tid] = 0; s_pay[tid] = p.pay[tid]; }
-    if (tid < 8) s_off[tid] = DY(tid) * SW + DX(tid);
+    if (tid < 4) s_n[tid] = 0;
+    static_assert(NT == 256, "one table entry per thread");
+    s_lut[tid] = lut_entry(p, (uint32_t)tid);
     load_tile_vec<TW, TH, 1>(p, p.tfA, s_tf, x0, y0);
     load_tile_vec<TW, TH, 1>(p, p.strat, s_st, x0, y0);
     for (int i = tid; i < NC / 4; i += NT) {
@@ -259,168 +288,81 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
     __syncthreads();
     // ... and the occupied cells of the 1-ring around it (they only need their word)
     const unsigned int n_agent = s_n[0];
-    {
-        constexpr int NRING = 2 * (TW + 2) + 2 * TH;
-        for (int base = 0; base < NRING; base += NT) {
-            const int i = base + tid;
-            int si = 0;
-            bool occ = false;
-            if (i < NRING) {
-                if (i < TW + 2) si = 15 + i;                                           // top row
-                else if (i < 2 * (TW + 2)) si = (SH - 1) * SW + 15 + (i - (TW + 2));   // bottom row
-                else {
-                    const int k = i - 2 * (TW + 2);                                    // left / right columns
-                    si = (1 + (k >> 1)) * SW + ((k & 1) ? (16 + TW) : 15);
-                }
-                occ = (s_tf[si] & TF_OCC) != 0;
+    for (int base = 0; base < NRING; base += NT) {
+        const int i = base + tid;
+        int si = 0;
+        bool occ = false;
+        if (i < NRING) {
+            if (i < TW + 2) si = 15 + i;                                           // top row
+            else if (i < 2 * (TW + 2)) si = (SH - 1) * SW + 15 + (i - (TW + 2));   // bottom row
+            else {
+                const int k = i - 2 * (TW + 2);                                    // left / right columns
+                si = (1 + (k >> 1)) * SW + ((k & 1) ? (16 + TW) : 15);
             }
-            const uint32_t slot = wappend(&s_n[1], occ);
-            if (occ) s_cells[n_agent + slot] = (uint16_t)si;
+            occ = (s_tf[si] & TF_OCC) != 0;
         }
+        const uint32_t slot = wappend(&s_n[1], occ);
+        if (occ) s_cells[n_agent + slot] = (uint32_t)si;
     }
     __syncthreads();
     // ---- per-step die roll (:364) of every occupied cell in reach -- recomputed, not communicated
     const unsigned int n_roll = n_agent + s_n[1];
     for (unsigned int k = tid; k < n_roll; k += NT) {
-        const int si = s_cells[k];
+        const int si = (int)s_cells[k];
         const int r = si / SW, c = si - r * SW;
         const uint32_t gx = (x0 + (uint32_t)(c - 16)) & (p.W - 1);
         const uint32_t gy = (p.row0 + y0 + (uint32_t)(r - 1)) & (p.HW - 1);
-        const uint32_t roll = rng(p, ((uint64_t)gy << p.log2W) | gx, S_ROLL).x;
+        const Words w = rng(p, ((uint64_t)gy << p.log2W) | gx, S_ROLL);
         const uint32_t t = s_tf[si];
-        s_R[si] = R_OCC | ((roll >> 12) << 11) | ((t & TF_D) ? R_DFLAG : 0u) | ((t & TF_TRAIT) << 8) | (uint32_t)s_st[si];
+        s_R[si] = R_OCC | ((w.x >> ROLL_SHIFT) << 12) | ((t & TF_D) ? R_DFLAG : 0u) | ((uint32_t)s_st[si] << 3) |
+                  ((t & TF_TRAIT) << 1);
+        s_cells[k] = (uint32_t)si | (w.w << 16);
     }
     __syncthreads();
-    // ---- agents, 32 per warp iteration
+    // ---- agents: roles, games, terminal rule, travel decision -- one lane per agent, no warp-wide operations
     unsigned int n_play_deaths = 0, n_movers = 0;
-    for (unsigned int base = warp * 32; base < n_agent; base += NT) {
-        const unsigned int a = base + lane;
-        const bool valid = a < n_agent;
-        const int si = valid ? s_cells[a] : (SW + 16);
+    for (unsigned int a = tid; a < n_agent; a += NT) {
+        const uint32_t ent = s_cells[a];
+        const int si = (int)(ent & 0xFFFFu);
+        const uint32_t coins = ent >> 16;
         const int ly = si / SW - 1, lx = si - (ly + 1) * SW - 16;
         const int cl = (ly << LOG_TW) | lx;
-        const uint32_t rme = valid ? s_R[si] : 0xFFFFFFFFu;
-        const uint32_t kme = rme >> 11;
-        // ---- who is around me, and who challenges me (bit c of gm: my neighbour 7-c does, in sub-step c, :477)
-        uint32_t occ_mask = 0, gm = 0, dflag = 0;
-        bool tie = false;
+        const uint32_t rme = s_R[si];
+        uint32_t rn[8];
 #pragma unroll
-        for (int d = 0; d < 8; ++d) {
-            const uint32_t rn = s_R[si + DY(d) * SW + DX(d)];
-            const uint32_t kn = rn >> 11;
-            occ_mask |= (rn >> 31) << d;
-            gm |= (kn > kme ? 1u : 0u) << (7 - d);
-            dflag |= (rn & R_DFLAG) >> (10 - d);  // bit d: neighbour d carries a D code
-            tie |= kn == kme;
-        }
-        // directions to redo exactly: challengers with a D code; on a truncated-roll tie (2^-20 per pair) all of them
-        uint32_t special = tie ? 0xFFu : (__brev(gm) >> 24) & dflag;
-        if (!valid) { occ_mask = 0; gm = 0; special = 0; }
-        // act[7] / act[0] of the terminal rule come from the roll order alone (get_game_list, :413):
-        // a challenger that dies early still "would have challenged"
-        uint32_t roles = gm;
-        if (special) {  // rare: redo those directions exactly
-            uint32_t m = special;
-            while (m) {
-                const int d = __ffs(m) - 1, c = 7 - d;
-                m &= m - 1;
-                const int sn = si + s_off[d];
-                const uint32_t rn = s_R[sn];
-                bool hi = (rn >> 11) > kme;
-                if ((rn >> 11) == kme) hi = exact_higher(p, x0 + lx, y0 + ly, d);
-                roles = (roles & ~(1u << c)) | ((uint32_t)hi << c);
-                if (hi) {
-                    const uint32_t dn = ((uint32_t)s_tf[sn] & TF_D) >> TF_D_SHIFT;
-                    if (dn != 0u && (int)dn - 1 < c) hi = false;  // that challenger dies before sub-step c: no message
+        for (int d = 0; d < 8; ++d) rn[d] = s_R[si + DY(d) * SW + DX(d)];
+        const uint32_t tA = rme | R_LOW, tB = (rme & ~R_LOW) - 1u;  // neighbour d challenges me iff rn[d] > (d < 4 ? tA : tB)
+        const uint32_t any_nb = (rn[0] | rn[1] | rn[2]) | (rn[3] | rn[4] | rn[5]) | (rn[6] | rn[7]);
+        // act[7] / act[0] of the terminal rule come from the roll order alone (get_game_list, :413): a
+        // challenger that dies early still "would have challenged".
+        // act[7]==1 <=> neighbour 7 exists and does not challenge me; act[0]==0 <=> neighbour 0 challenges me
+        const bool act7_challenge = rn[7] != 0u && !(rn[7] > tB);
+        const bool act0_respond = rn[0] > tA;
+        if (any_nb & R_DFLAG) {  // rare: a neighbour dies during play (D code = sub-step of death + 1)
+#pragma unroll
+            for (int d = 0; d < 8; ++d)
+                if (rn[d] & R_DFLAG) {
+                    const uint32_t dn = ((uint32_t)s_tf[si + DY(d) * SW + DX(d)] & TF_D) >> TF_D_SHIFT;
+                    if ((int)dn - 1 < 7 - d) rn[d] = 0u;  // dead before sub-step 7-d: it sends no challenge
                 }
-                gm = (gm & ~(1u << c)) | ((uint32_t)hi << c);
-            }
         }
-        // ---- queue my games warp-wide, in sub-step order
-        const int cnt = __popc(gm);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += v;
+        bool dead = false, any = false;
+        const float e0 = s_e[cl];
+        float e;
+        if (noisy) e = play_games<true>(p, s_lut, rn, rme, tA, tB, coins, gcell_of(p, x0 + (uint32_t)lx, y0 + (uint32_t)ly), e0, dead, any);
+        else e = play_games<false>(p, s_lut, rn, rme, tA, tB, coins, 0ull, e0, dead, any);
+        if (dead) {
+            s_out[cl] = (uint8_t)TF_GHOST;
+            s_e[cl] = 0.0f;
+            ++n_play_deaths;
+        } else {
+            // terminal rule (:547-556, :719-730, :486-496) or no neighbours (:429-433); games_played (:710) of an
+            // agent that is still alive counts all its games as the responder
+            const bool mover = any_nb == 0u || (!any && (act7_challenge || act0_respond));
+            s_out[cl] = (uint8_t)(TF_OCC | ((rme >> 1) & TF_TRAIT));
+            s_e[cl] = e;
+            if (mover) { s_mover[satom_add(&s_n[2], 1u)] = (uint16_t)cl; ++n_movers; }
         }
-        const int off = incl - cnt;
-        const int total = __shfl_sync(FULL, incl, 31);
-        {
-            uint16_t* qp = &s_q[warp][off];
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                if ((gm >> c) & 1u) *qp++ = (uint16_t)((si << 3) | c);
-        }
-        __syncwarp();
-        // ---- evaluate them 32 at a time (play_response, :599-689)
-        int n2 = 0;
-        for (int q0 = 0; q0 < total; q0 += 32) {
-            const int q = q0 + lane;
-            const bool active = q < total;
-            const uint32_t ent = active ? s_q[warp][q] : 0u;  // responder's cell << 3 | sub-step
-            const int d = 7 - (int)(ent & 7u);
-            bool need = false;
-            if (active) {
-                const int si_l = (int)(ent >> 3);
-                uint32_t mine, theirs;
-                game_strategies(s_R[si_l], s_R[si_l + s_off[d]], mine, theirs);
-                need = noisy || mine == 3u || theirs == 3u;
-                // the outcome, or -- for the games that go to the random-word pass -- the two strategies
-                s_qo[warp][q] = need ? (uint8_t)((mine << 2) | theirs)
-                                     : (uint8_t)(((mine != 1u) ? 2u : 0u) | ((theirs != 1u) ? 1u : 0u));
-            }
-            // the games that need random words are compacted once more: the Philox rounds then run with full lanes
-            const unsigned int bal = __ballot_sync(FULL, need);
-            if (need) s_q2[warp][n2 + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)q;
-            n2 += __popc(bal);
-        }
-        __syncwarp();
-        for (int k0 = 0; k0 < n2; k0 += 32) {
-            const int k = k0 + lane;
-            const bool active = k < n2;
-            const int q = active ? s_q2[warp][k] : 0;
-            const uint32_t ent = s_q[warp][q];
-            const int c = (int)(ent & 7u);
-            if (active) {
-                const int si_l = (int)(ent >> 3), r_l = si_l / SW;
-                const uint32_t ms = s_qo[warp][q], mine = ms >> 2, theirs = ms & 3u;
-                const uint64_t gl = gcell_of(p, x0 + (uint32_t)(si_l - r_l * SW - 16), y0 + (uint32_t)(r_l - 1));
-                s_qo[warp][q] = (uint8_t)game_outcome_rng(p, gl, c, mine, theirs);
-            }
-        }
-        __syncwarp();
-        // ---- my games in sub-step order (:677-710), terminal rule, travel decision
-        bool mover = false;
-        if (valid) {
-            float e = s_e[cl];
-            bool dead = false;
-            const uint8_t* my_o = &s_qo[warp][off];  // my outcomes, in sub-step order
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (!((gm >> c) & 1u)) continue;
-                e = __fadd_rn(e, s_pay[*my_o++]);                  // :679-688; outcomes are 0..3 by construction
-                dead |= e <= 0.0f;                                 // :695-697 -- latched: what a dead agent's energy
-                e = fminf(e, p.max_energy);                        // :698-702    does afterwards is never used
-            }
-            const int games = cnt;  // games_played (:710) of an agent that is still alive: all of them
-            if (dead) {
-                s_out[cl] = (uint8_t)TF_GHOST;
-                s_e[cl] = 0.0f;
-                ++n_play_deaths;
-            } else {
-                // terminal rule (:547-556, :719-730, :486-496) or no neighbours (:429-433):
-                // act[7]==1 <=> neighbour 7 exists and does not challenge me (sub-step 0);
-                // act[0]==0 <=> neighbour 0 challenges me (sub-step 7)
-                const bool act7_challenge = ((occ_mask >> 7) & 1u) && !(roles & 1u);
-                const bool act0_respond = (roles >> 7) & 1u;
-                mover = occ_mask == 0u || (games == 0 && (act7_challenge || act0_respond));
-                s_out[cl] = (uint8_t)(TF_OCC | ((rme >> 8) & TF_TRAIT));
-                s_e[cl] = e;
-            }
-        }
-        if (mover) { s_mover[satom_add(&s_n[2], 1u)] = (uint16_t)cl; ++n_movers; }  // ~2 lanes of 32
-        __syncwarp();
     }
     __syncthreads();
     // ---- movers: travel cost, death, random start, probe, claim (:794-868)

@@ -30,9 +30,13 @@ constexpr uint32_t TF_D_SHIFT = 3u;
 constexpr uint32_t TF_D = 0x78u;
 
 // ---- Philox stream ids (counter word 3); must equal oracle/pd_oracle.py -----------------
-constexpr uint32_t S_ROLL = 0;    // x: pair-ordering roll (:364)  y: travel priority (:806)  z>>29: travel start dir (:810)
-constexpr uint32_t S_GAME0 = 1;   // +c; keyed by the RESPONDER's cell: x my noise (:611) y challenger noise (:612)
-                                  //     z>>31 challenger RANDOM coin (:631)  w>>31 my RANDOM coin (:664)
+constexpr uint32_t S_ROLL = 0;    // x>>13: pair-ordering roll (:364)  y: travel priority (:806)  z>>29: travel start dir (:810)
+                                  // w bits 2c / 2c+1: the challenger's / my RANDOM coin (:631 / :664) of the game I
+                                  // respond to in sub-step c -- a game without noise needs no random call of its own
+constexpr uint32_t S_NOISE0 = 1;  // +(c>>1); keyed by the RESPONDER's cell: even c: x my noise roll (:611) y the
+                                  //     challenger's (:612); odd c: z mine, w the challenger's
+constexpr uint32_t ROLL_SHIFT = 13;  // the pair-ordering roll keeps the top 19 bits of its word; a tie is won by the
+                                     // neighbour in a direction >= 4 (replaces the id tie-break of :413)
 constexpr uint32_t S_REPRO = 9;   // x: reproduction claim priority (:1076)  y>>29: start dir (:1079)
 constexpr uint32_t S_MUT = 10;    // mutation rolls (:1263, :1278, :1291-1292), keyed by the parent's cell
 constexpr uint32_t S_PICK = 11;   // replacement picks (:1265, :1281, :1303, :1314)
@@ -161,22 +165,27 @@ __device__ __forceinline__ uint64_t nb_gcell(const Params& p, uint32_t x, uint32
 
 // ---- the game as the RESPONDER sees it (play_response, :599-689) --------------------------
 // strategies: 0 COOP, 1 DEFECT, 2 TFT (== COOP: its memory is submodel-local and every pair
-// plays once per step, :621-629/:646-661), 3 RANDOM.
-__device__ __forceinline__ float game_payoff(const Params& p, uint64_t my_gcell, int c,
+// plays once per step, :621-629/:646-661), 3 RANDOM.  `coins` = the w word of the responder's
+// S_ROLL call.  (The dense play sweep has its own table-driven form of this, pd_dense.cuh.)
+__device__ __forceinline__ float game_payoff(const Params& p, uint64_t my_gcell, int c, uint32_t coins,
                                              uint32_t my_strat, uint32_t my_trait,
                                              uint32_t ch_strat, uint32_t ch_trait) {
     const uint32_t mine = (my_strat >> (2 * ch_trait)) & 3u;    // :599
     const uint32_t theirs = (ch_strat >> (2 * my_trait)) & 3u;  // :600
-    bool i_coop = mine != 1u;
-    bool ch_coop = theirs != 1u;
-    if (p.noise_thr != 0ull || mine == 3u || theirs == 3u) {
-        const Words w = rng(p, my_gcell, S_GAME0 + (uint32_t)c);  // :611-612
-        if (theirs == 3u) ch_coop = (w.z >> 31) != 0u;             // :630-635
-        if (mine == 3u) i_coop = (w.w >> 31) != 0u;                // :663-668
-        if ((unsigned long long)w.y < p.noise_thr) ch_coop = !ch_coop;  // :638-640
-        if ((unsigned long long)w.x < p.noise_thr) i_coop = !i_coop;    // :672-674
+    bool i_coop = mine == 3u ? ((coins >> (2 * c + 1)) & 1u) != 0u : mine != 1u;      // :663-668
+    bool ch_coop = theirs == 3u ? ((coins >> (2 * c)) & 1u) != 0u : theirs != 1u;     // :630-635
+    if (p.noise_thr != 0ull) {
+        const Words w = rng(p, my_gcell, S_NOISE0 + ((uint32_t)c >> 1));  // :611-612
+        const uint32_t my_roll = (c & 1) ? w.z : w.x, ch_roll = (c & 1) ? w.w : w.y;
+        if ((unsigned long long)ch_roll < p.noise_thr) ch_coop = !ch_coop;  // :638-640
+        if ((unsigned long long)my_roll < p.noise_thr) i_coop = !i_coop;    // :672-674
     }
     return p.pay[((uint32_t)i_coop << 1) | (uint32_t)ch_coop];  // :677-689 (my side only)
+}
+// "the neighbour in direction d (roll word rn) is higher than me (roll word r)": it challenges me (:413)
+__device__ __forceinline__ bool roll_higher(uint32_t rn, uint32_t r, int d) {
+    const uint32_t kn = rn >> ROLL_SHIFT, k = r >> ROLL_SHIFT;
+    return kn > k || (kn == k && d >= 4);
 }
 
 // ---- triangular probe (:826-839, :1088-1101) ---------------------------------------------

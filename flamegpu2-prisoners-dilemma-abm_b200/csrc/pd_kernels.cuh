@@ -67,7 +67,6 @@ __global__ void __launch_bounds__(1024) k_risk_resolve(const __grid_constant__ P
             if ((t & TF_OCC) && !split) {
                 dependent = true;
                 p.risk_e[i] = __ldcg(p.E0 + cell);
-                p.risk_roll[i] = rng(p, gcell_of(p, x, y), S_ROLL).x;
             } else if (t & TF_OCC) {  // else: a stale entry
                 uint32_t nc[8], tn[8];
 #pragma unroll
@@ -78,26 +77,24 @@ __global__ void __launch_bounds__(1024) k_risk_resolve(const __grid_constant__ P
                 float e = __ldcg(p.E0 + cell);
                 const uint32_t my_strat = __ldcg(p.strat + cell);
                 const uint64_t g = gcell_of(p, x, y);
-                const uint32_t roll = rng(p, g, S_ROLL).x;
+                const Words wr = rng(p, g, S_ROLL);
+                const uint32_t roll = wr.x, coins = wr.w;
                 uint32_t chal = 0;  // bit d: my neighbour d challenges me (:413), in sub-step 7-d
 #pragma unroll
                 for (int d = 0; d < 8; ++d) {
                     if (!(tn[d] & TF_OCC)) continue;
-                    const uint64_t gn = nb_gcell(p, x, y, d);
-                    const uint32_t rn = rng(p, gn, S_ROLL).x;
-                    if (rn > roll || (rn == roll && gn > g)) chal |= 1u << d;
+                    if (roll_higher(rng(p, nb_gcell(p, x, y, d), S_ROLL).x, roll, d)) chal |= 1u << d;
                 }
 #pragma unroll
                 for (int d = 0; d < 8; ++d)
                     if (((chal >> d) & 1u) && __ldcg(p.E0 + nc[d]) <= p.risk_thr) dependent = true;
                 if (dependent) {
                     p.risk_e[i] = e;
-                    p.risk_roll[i] = roll;
                 } else {
                     for (int c = 0; c < 8; ++c) {
                         const int d = 7 - c;
                         if (!((chal >> d) & 1u)) continue;
-                        e = __fadd_rn(e, game_payoff(p, g, c, my_strat, t & TF_TRAIT, __ldcg(p.strat + nc[d]), tn[d] & TF_TRAIT));
+                        e = __fadd_rn(e, game_payoff(p, g, c, coins, my_strat, t & TF_TRAIT, __ldcg(p.strat + nc[d]), tn[d] & TF_TRAIT));
                         if (e <= 0.0f) {
                             p.tfA[cell] = (uint8_t)(t | ((uint32_t)(c + 1) << TF_D_SHIFT));
                             break;
@@ -124,13 +121,12 @@ __global__ void __launch_bounds__(1024) k_risk_resolve(const __grid_constant__ P
             const uint32_t nc = nb_local(p, x, y, d);
             const uint32_t tn = __ldcg(p.tfA + nc);
             if (!(tn & TF_OCC)) continue;
-            const uint64_t g = gcell_of(p, x, y), gn = nb_gcell(p, x, y, d);
-            const uint32_t roll = p.risk_roll[i];
-            const uint32_t rn = rng(p, gn, S_ROLL).x;
-            if (!(rn > roll || (rn == roll && gn > g))) continue;  // I am the challenger (:413)
+            const uint64_t g = gcell_of(p, x, y);
+            const Words wr = rng(p, g, S_ROLL);  // (recomputed: cheaper than a list round trip for these few)
+            if (!roll_higher(rng(p, nb_gcell(p, x, y, d), S_ROLL).x, wr.x, d)) continue;  // I am the challenger (:413)
             const uint32_t dn = (tn & TF_D) >> TF_D_SHIFT;
             if (dn != 0u && (int)dn - 1 < c) continue;  // challenger died in an earlier sub-step
-            const float e = __fadd_rn(p.risk_e[i], game_payoff(p, g, c, p.strat[cell], t & TF_TRAIT, p.strat[nc], tn & TF_TRAIT));
+            const float e = __fadd_rn(p.risk_e[i], game_payoff(p, g, c, wr.w, p.strat[cell], t & TF_TRAIT, p.strat[nc], tn & TF_TRAIT));
             if (e <= 0.0f) p.tfA[cell] = (uint8_t)(t | ((uint32_t)(c + 1) << TF_D_SHIFT));
             else p.risk_e[i] = fminf(e, p.max_energy);
         }

@@ -15,7 +15,7 @@ from collections import defaultdict
 import numpy as np
 
 from .philox import philox_scalar
-from .pd_oracle import (Params, prob_threshold, NORMAL_SCALE, S_ROLL, S_GAME0, S_REPRO, S_MUT, S_PICK,
+from .pd_oracle import (Params, prob_threshold, NORMAL_SCALE, S_ROLL, S_NOISE0, ROLL_SHIFT, S_REPRO, S_MUT, S_PICK,
                         S_CULL, S_ENERGY, READY, READY_TO_CHALLENGE, READY_TO_RESPOND,
                         MOVEMENT_UNRESOLVED, MOVING, ATTEMPTING_REPRODUCTION, REPRODUCTION_IMPOSSIBLE,
                         REPRODUCTION_COMPLETE, NEW_AGENT)
@@ -68,7 +68,9 @@ class LiteralModel:
         msgs = {}
         for a in self.agents:                                       # search_for_neighbours :352-372
             a["bucket"] = self.pos_to_bucket_id(a["x"], a["y"])
-            a["roll"] = self.rng(a["bucket"], S_ROLL)[0]            # :364
+            w = self.rng(a["bucket"], S_ROLL)
+            a["roll"] = w[0] >> ROLL_SHIFT                          # :364 (top 19 bits)
+            a["coins"] = w[3] & 0xFFFF                              # the coins of :631 / :664
             a["roll_cell"] = a["bucket"]
             msgs[a["bucket"]] = (a["id"], a["roll"])
         for a in self.agents:                                       # get_game_list :373-440
@@ -80,7 +82,7 @@ class LiteralModel:
                 if nb in msgs:
                     nid, nroll = msgs[nb]
                     n += 1
-                    if a["roll"] > nroll or (nroll == a["roll"] and a["roll_cell"] > nb):   # :413 (cell tag)
+                    if a["roll"] > nroll or (nroll == a["roll"] and i < 4):   # :413 (tie: direction class)
                         action = 1
                     else:
                         action = 0
@@ -136,8 +138,13 @@ class LiteralModel:
                         continue
                     my_strategy = a["strat"][m["trait"]]            # :599
                     ch_strategy = m["strat"][a["trait"]]            # :600
-                    w = self.rng(a["bucket"], S_GAME0 + (a["cs"] - 1))
-                    my_roll, ch_roll = w[0], w[1]                   # :611-612
+                    c = a["cs"] - 1                                 # the sub-step being played
+                    coin_ch = (a["coins"] >> (2 * c)) & 1
+                    coin_me = (a["coins"] >> (2 * c + 1)) & 1
+                    my_roll = ch_roll = 0xFFFFFFFF
+                    if self.noise_thr:                              # :611-612
+                        w = self.rng(a["bucket"], S_NOISE0 + (c >> 1))
+                        my_roll, ch_roll = (w[2], w[3]) if c & 1 else (w[0], w[1])
                     if ch_strategy == 0:
                         ch_coop = True
                     elif ch_strategy == 1:
@@ -145,7 +152,7 @@ class LiteralModel:
                     elif ch_strategy == 2:
                         ch_coop = True                              # :621-629 memory never matches
                     else:
-                        ch_coop = (w[2] >> 31) == 1                 # :631
+                        ch_coop = coin_ch == 1                      # :631
                     if ch_roll < self.noise_thr:                    # :638-640
                         ch_coop = not ch_coop
                     if my_strategy == 0:
@@ -155,7 +162,7 @@ class LiteralModel:
                     elif my_strategy == 2:
                         i_coop = True                               # :646-661
                     else:
-                        i_coop = (w[3] >> 31) == 1                  # :664
+                        i_coop = coin_me == 1                       # :664
                     if my_roll < self.noise_thr:                    # :672-674
                         i_coop = not i_coop
                     e = a["energy"]

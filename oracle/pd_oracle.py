@@ -14,8 +14,15 @@ it follows.  Three deliberate restatements (DESIGN.md "Semantics"):
 * all random draws are Philox4x32-10 words keyed (seed; cell, step, stream)
   instead of per-thread cuRAND (model.py:364, :611-612, :631, :664, :806-810,
   :1076-1079, :1236, :1263-1314);
-* ties between equal rolls are broken by the *cell index* the agent stood on
-  when it drew (the reference uses the agent id, model.py:413, :929, :1192);
+* the pair-ordering roll of play is the top 19 bits of a Philox word and a tie is
+  won by the neighbour in a direction >= 4 (the reference: a float and the agent
+  id, model.py:413); travel / reproduction claims are ordered by a 32-bit word and
+  ties are broken by the *cell index* the agent stood on when it drew (the
+  reference uses the agent id, model.py:929, :1192);
+* the RANDOM-strategy coins of a game (model.py:631, :664) are two bits of the
+  RESPONDER's roll call (bits 2c, 2c+1 of its 4th word for sub-step c), so a game
+  without noise needs no random call of its own; the noise rolls (:611-612) come
+  from four calls per responder (streams 1..4, two sub-steps per call);
 * the list-index cull (model.py:1343, :1354) is replaced by "the surplus
   newborns with the lowest Philox cull priority die" (SURVEY Appendix B-4).
 """
@@ -48,9 +55,12 @@ DY = np.array([-1, 0, 1, -1, 1, -1, 0, 1], dtype=np.int64)
 NDIR = 8  # SPACES_WITHIN_RADIUS, model.py:255
 
 # --- Philox stream ids (4th counter word); step index is the 3rd --------------
-S_ROLL = 0      # w0 pair-ordering roll (:364) w1 travel priority (:806) w2>>29 travel start dir (:810)
-S_GAME0 = 1     # +c, c=0..7, keyed by the RESPONDER's cell: w0 my noise (:611) w1 challenger
-                # noise (:612) w2>>31 challenger RANDOM coin (:631) w3>>31 my RANDOM coin (:664)
+S_ROLL = 0      # w0>>13 pair-ordering roll (:364) w1 travel priority (:806) w2>>29 travel start dir (:810)
+                # w3 bits 2c / 2c+1: the challenger's / my RANDOM coin (:631 / :664) of the game I
+                # respond to in sub-step c
+S_NOISE0 = 1    # +(c>>1), keyed by the RESPONDER's cell: even c: w0 my noise roll (:611) w1 the
+                # challenger's (:612); odd c: w2 mine, w3 the challenger's
+ROLL_SHIFT = 13  # the pair-ordering roll keeps the top 19 bits of its word
 S_REPRO = 9     # w0 reproduction claim priority (:1076) w1>>29 start dir (:1079)
 S_MUT = 10      # w0..w3 mutation rolls (:1263, :1278, :1291-1292), keyed by the PARENT's cell
 S_PICK = 11     # w0..w3 replacement-strategy picks (:1265, :1281, :1303, :1314)
@@ -127,6 +137,10 @@ class Params:
     strategy_pure: int = 0                 # model.py:158
     strategy_per_trait: int = 0            # model.py:161
     strategy_weights: List[float] = field(default_factory=lambda: [0.25, 0.25, 0.25, 0.25])  # :127-149
+    # ORACLE-ONLY switch: "priority" = the cull the product implements (SURVEY B-4); "list_index" = the
+    # reference's own rule (model.py:1343, :1354) under the FLAMEGPU2 list semantics of SURVEY Appendix D-2
+    # [FG2-ext]; tests/test_cull_variants.py compares the two statistically
+    cull: str = "priority"
 
     def __post_init__(self):
         w = self.width
@@ -182,6 +196,7 @@ class Oracle:
         self.act = np.full((0, NDIR), -1, np.int8)          # my_actions
         self.roll = np.zeros(0, np.uint32)                  # die_roll
         self.roll_cell = np.zeros(0, np.int64)              # tie-break tag: cell at draw time
+        self.coins = np.zeros(0, np.uint32)                 # RANDOM coins of the games I respond to
         self.bucket = np.zeros(0, np.int64)                 # my_bucket
         self.stats: Dict[str, int] = {}
         self.population_strat_count = np.zeros(16, np.int64)
@@ -194,7 +209,7 @@ class Oracle:
                              self.k0, self.k1)
 
     _ARRS = ("id", "x", "y", "energy", "status", "trait", "strat", "nb_list", "act", "roll",
-             "roll_cell", "bucket")
+             "roll_cell", "bucket", "coins")
 
     def _compact(self, alive: np.ndarray, extra: Dict[str, np.ndarray] | None = None):
         """Remove dead agents from every per-agent array (FLAMEGPU2 death compaction)."""
@@ -203,6 +218,25 @@ class Oracle:
         if extra:
             for k in list(extra):
                 extra[k] = extra[k][alive]
+
+    def _partition(self, passing: np.ndarray, sub: Dict[str, np.ndarray] | None = None, remap_chal: bool = False):
+        """cull == "list_index" only.  [FG2-ext, SURVEY Appendix D-2]: a function condition stably
+        partitions the agent list -- failing agents first, passing agents after them -- and the order is
+        not restored; deaths compact stably (_compact) and newborns append at the end.  Nothing but the
+        list-index cull (model.py:1343, :1354) ever looks at the order."""
+        if self.p.cull != "list_index":
+            return
+        order = np.concatenate([np.flatnonzero(~passing), np.flatnonzero(passing)])
+        for n in self._ARRS:
+            setattr(self, n, getattr(self, n)[order])
+        if sub:
+            for k in list(sub):
+                sub[k] = sub[k][order]
+        if remap_chal:   # this layer's challenge messages hold list indices (challenger of a bucket)
+            cb = self.chal_bucket
+            inv = np.empty_like(order)
+            inv[order] = np.arange(order.size)
+            self.chal_bucket = np.where(cb >= 0, inv[np.maximum(cb, 0)], -1)
 
     def _nb_bucket(self, idx: np.ndarray, d) -> np.ndarray:
         """pos_from_moore_seq + pos_to_bucket_id, model.py:294-342."""
@@ -258,6 +292,7 @@ class Oracle:
         self.act = np.full((n, NDIR), -1, np.int8)
         self.roll = np.zeros(n, np.uint32)
         self.roll_cell = np.zeros(n, np.int64)
+        self.coins = np.zeros(n, np.uint32)
         self.bucket = self.x + self.y * W
         self.step_index = 0
         self.population_strat_count = self.strategy_counts()                   # :1517-1522
@@ -278,6 +313,7 @@ class Oracle:
         self.act = np.full((n, NDIR), -1, np.int8)
         self.roll = np.zeros(n, np.uint32)
         self.roll_cell = np.zeros(n, np.int64)
+        self.coins = np.zeros(n, np.uint32)
         self.bucket = self.x + self.y * W
         self.population_strat_count = self.strategy_counts()
 
@@ -285,9 +321,10 @@ class Oracle:
     def search_for_neighbours(self):
         """model.py:352-372: bucket id, per-step die roll, post (id, roll) at my bucket."""
         self.bucket = self.x + self.y * self.W                                  # :361
-        w0, _, _, _ = self._rng(self.bucket, S_ROLL)
-        self.roll = w0                                                          # :364
+        w0, _, _, w3 = self._rng(self.bucket, S_ROLL)
+        self.roll = w0 >> np.uint32(ROLL_SHIFT)                                 # :364
         self.roll_cell = self.bucket.copy()
+        self.coins = w3 & np.uint32(0xFFFF)
         self.msg_id = np.zeros(self.cells, np.int64)                           # player_search_msg
         self.msg_roll = np.zeros(self.cells, np.uint32)
         self.msg_id[self.bucket] = self.id
@@ -304,8 +341,9 @@ class Oracle:
             nroll = self.msg_roll[nb]                                           # :408
             present = nid != 0
             num_neighbours += present
-            # I challenge iff my (roll, tag) is higher -- :413 (tag = cell, see module doc)
-            higher = (self.roll > nroll) | ((self.roll == nroll) & (self.roll_cell > nb))
+            # I challenge iff my roll is higher -- :413; a tie goes to whoever sees the other in a
+            # direction < 4 (see module doc)
+            higher = (self.roll > nroll) | ((self.roll == nroll) & (i < 4))
             self.act[:, i] = np.where(present, np.where(higher, 1, 0), -1)      # :415-418, :399
             self.nb_list[:, i] = np.where(present, nid, 0)                      # :423
         self.status = np.where(num_neighbours == 0, MOVEMENT_UNRESOLVED, READY_TO_CHALLENGE)  # :429-436
@@ -337,6 +375,7 @@ class Oracle:
 
     def _play_challenge(self, sub):
         """play_challenge, model.py:450-566 (condition :442-448)."""
+        self._partition(self.status == READY_TO_CHALLENGE, sub)
         sel = np.flatnonzero(self.status == READY_TO_CHALLENGE)
         # message list of this layer: target bucket -> challenger agent index
         self.chal_bucket = np.full(self.cells, -1, np.int64)
@@ -368,6 +407,7 @@ class Oracle:
     def _play_response(self, sub):
         """play_response, model.py:575-734 (condition :569-574)."""
         p = self.p
+        self._partition(self.status == READY_TO_RESPOND, sub, remap_chal=True)
         sel = np.flatnonzero(self.status == READY_TO_RESPOND)
         if sel.size == 0:
             return 0, 0
@@ -388,13 +428,17 @@ class Oracle:
             c_g = c_sub[has]
             my_strategy = self.strat[me, self.trait[ch]]                        # :599
             ch_strategy = self.strat[ch, self.trait[me]]                        # :600
-            w0, w1, w2, w3 = self._rng(self.bucket[me], S_GAME0 + c_g)          # :611-612, :631, :664
+            coins = self.coins[me] >> (2 * c_g).astype(np.uint32)               # :631, :664
             # COOP -> C, DEFECT -> D, TFT -> C (memory never matches: it is submodel-local and
             # each pair plays once per step, :621-629, :646-661), RANDOM -> coin (:630-635)
-            ch_coop = np.where(ch_strategy == RANDOM, (w2 >> np.uint32(31)) == 1, ch_strategy != DEFECT)
-            ch_coop = ch_coop ^ (w1.astype(np.uint64) < np.uint64(self.noise_thr))   # :638-640
-            i_coop = np.where(my_strategy == RANDOM, (w3 >> np.uint32(31)) == 1, my_strategy != DEFECT)
-            i_coop = i_coop ^ (w0.astype(np.uint64) < np.uint64(self.noise_thr))     # :672-674
+            ch_coop = np.where(ch_strategy == RANDOM, (coins & np.uint32(1)) == 1, ch_strategy != DEFECT)
+            i_coop = np.where(my_strategy == RANDOM, (coins & np.uint32(2)) == 2, my_strategy != DEFECT)
+            if self.noise_thr:
+                n0, n1, n2, n3 = self._rng(self.bucket[me], S_NOISE0 + (c_g >> 1))   # :611-612
+                odd = (c_g & 1) == 1
+                my_roll, ch_roll = np.where(odd, n2, n0), np.where(odd, n3, n1)
+                ch_coop = ch_coop ^ (ch_roll.astype(np.uint64) < np.uint64(self.noise_thr))   # :638-640
+                i_coop = i_coop ^ (my_roll.astype(np.uint64) < np.uint64(self.noise_thr))     # :672-674
             pay = np.where(i_coop & ch_coop, self.payoff_cc,
                            np.where(~i_coop & ~ch_coop, self.payoff_dd,
                                     np.where(i_coop & ~ch_coop, self.payoff_cd, self.payoff_dc)))  # :677-689
@@ -455,6 +499,7 @@ class Oracle:
     def _move_request(self, sub, first):
         """move_request, model.py:784-872 (condition :777-782)."""
         p = self.p
+        self._partition(self.status == MOVEMENT_UNRESOLVED, sub)
         sel = np.flatnonzero(self.status == MOVEMENT_UNRESOLVED)
         self.claim_key = np.zeros(self.cells, np.uint64)                        # agent_move_request_msg
         if sel.size == 0:
@@ -498,6 +543,7 @@ class Oracle:
 
     def _move_response(self, sub):
         """move_response, model.py:881-960 (condition :874-879)."""
+        self._partition(self.status == MOVING, sub)
         sel = np.flatnonzero(self.status == MOVING)
         if sel.size == 0:
             return
@@ -522,6 +568,7 @@ class Oracle:
         """neighbourhood_broadcast :963-972, neighbourhood_update :975-1031; one iteration (:1591-1596)."""
         occ = np.zeros(self.cells, np.int64)
         occ[self.bucket] = self.id                                              # :968-969
+        self._partition(self.energy >= np.float32(self.p.reproduce_min_energy))
         sel = np.flatnonzero(self.energy >= np.float32(self.p.reproduce_min_energy))   # :978-979
         if sel.size == 0:
             return
@@ -561,6 +608,7 @@ class Oracle:
         self.repro_key = np.zeros(self.cells, np.uint64)                        # god_go_forth_msg
         if overpopulated >= 1:
             return
+        self._partition(self.status == ATTEMPTING_REPRODUCTION, sub)
         sel = np.flatnonzero(self.status == ATTEMPTING_REPRODUCTION)
         if sel.size == 0:
             return
@@ -603,6 +651,7 @@ class Oracle:
         p = self.p
         if overpopulated >= 1:
             return
+        self._partition(self.status == ATTEMPTING_REPRODUCTION, sub)
         sel = np.flatnonzero(self.status == ATTEMPTING_REPRODUCTION)
         if sel.size == 0:
             return
@@ -672,6 +721,7 @@ class Oracle:
         self.act = np.concatenate([self.act, np.full((nb, NDIR), -1, np.int8)])
         self.roll = np.concatenate([self.roll, np.zeros(nb, np.uint32)])
         self.roll_cell = np.concatenate([self.roll_cell, np.zeros(nb, np.int64)])
+        self.coins = np.concatenate([self.coins, np.zeros(nb, np.uint32)])
         self.bucket = np.concatenate([self.bucket, tgt])                        # :1252
         for k, dflt in (("request_bucket", 0), ("last_reproduction_attempt", NDIR + 1),
                         ("reproduce_sequence", 0), ("agents_spawned", 0)):
@@ -682,6 +732,8 @@ class Oracle:
     def environmental_punishment(self):
         """environmental_punishment, model.py:1339-1371, with the priority cull (B-4)."""
         p = self.p
+        if p.cull == "list_index":
+            return self._environmental_punishment_list_index()
         newborn = self.status == NEW_AGENT
         n_old = int((~newborn).sum())
         n_new = int(newborn.sum())
@@ -703,6 +755,29 @@ class Oracle:
         self.status[old] = READY                                                # :1368
         alive[old[dies]] = False
         self.stats["culled"] = culled
+        self.stats["living_deaths"] = int(dies.sum())
+        self._compact(alive)
+
+    def _environmental_punishment_list_index(self):
+        """environmental_punishment with the reference's OWN cull (model.py:1339-1371) under the list
+        semantics of SURVEY Appendix D-2 [FG2-ext]: the condition (:1343) sees the index in the whole
+        list, the function (:1354) the index within its working set (the agents that passed)."""
+        p = self.p
+        idx = np.arange(self.n)
+        passing = (self.status != NEW_AGENT) | (idx >= p.max_agents)            # :1343
+        self._partition(passing)
+        ws = np.arange(self.n - int(passing.sum()), self.n)                     # the working set, in list order
+        ws_index = np.arange(ws.size)
+        cull = ws_index >= p.max_agents                                         # :1354-1356
+        e = np.minimum(self.energy[ws], np.float32(p.max_energy))              # :1360-1362
+        e = (e - np.float32(p.cost_of_living)).astype(np.float32)               # :1363
+        dies = ~cull & (e <= np.float32(0))                                     # :1364-1366
+        keep = ~cull & ~dies
+        self.energy[ws[keep]] = e[keep]                                         # :1367
+        self.status[ws[keep]] = READY                                           # :1368
+        alive = np.ones(self.n, bool)
+        alive[ws[cull | dies]] = False
+        self.stats["culled"] = int(cull.sum())
         self.stats["living_deaths"] = int(dies.sum())
         self._compact(alive)
 

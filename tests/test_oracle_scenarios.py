@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle.philox import philox_scalar, philox4x32_10
-from oracle.pd_oracle import (Oracle, Params, DX, DY, S_ROLL, S_GAME0, S_REPRO, S_CULL, S_ENERGY,
+from oracle.pd_oracle import (Oracle, Params, DX, DY, S_ROLL, S_NOISE0, ROLL_SHIFT, S_REPRO, S_CULL, S_ENERGY,
                               normal_from_words, prob_threshold, NORMAL_SCALE)
 
 
@@ -106,7 +106,7 @@ def test_two_agent_play_table(sa, sb):
     o = world(16, [(4, 4, 50.0, 0, [sa] * 4), (5, 4, 60.0, 1, [sb] * 4)])
     o.search_for_neighbours()
     o.get_game_list()
-    roll_a, roll_b = words(o, 4 + 4 * 16, S_ROLL)[0], words(o, 5 + 4 * 16, S_ROLL)[0]
+    roll_a, roll_b = words(o, 4 + 4 * 16, S_ROLL)[0] >> ROLL_SHIFT, words(o, 5 + 4 * 16, S_ROLL)[0] >> ROLL_SHIFT
     assert roll_a != roll_b
     o.pdgame_model()
     a_is_responder = roll_a < roll_b
@@ -121,25 +121,43 @@ def test_two_agent_play_table(sa, sb):
 
 
 def test_random_strategy_and_noise_use_the_responders_words():
-    """RANDOM cooperates iff the coin's top bit is set (model.py:631, :664); noise flips a choice
-    iff its word < noise * 2^32 (:638-640, :672-674); words keyed by the responder's cell and
-    the sub-step c = direction from challenger to responder."""
-    noise = 0.3
-    o = world(16, [(4, 4, 50.0, 2, [3] * 4), (5, 5, 60.0, 1, [3] * 4)], env_noise=noise)
-    o.search_for_neighbours()
-    o.get_game_list()
-    ca, cb = 4 + 4 * 16, 5 + 5 * 16
-    a_resp = words(o, ca, S_ROLL)[0] < words(o, cb, S_ROLL)[0]
-    resp_cell = ca if a_resp else cb
-    c = 0 if a_resp else 7      # challenger b at (5,5) reaches a at (4,4) in direction 0; a reaches b in 7
-    w = words(o, resp_cell, S_GAME0 + c)
-    thr = prob_threshold(noise)
-    i_coop = ((w[3] >> 31) == 1) ^ (w[0] < thr)
-    ch_coop = ((w[2] >> 31) == 1) ^ (w[1] < thr)
-    pay = 3.0 if (i_coop and ch_coop) else 0.0 if (not i_coop and not ch_coop) else -1.0 if i_coop else 5.0
-    o.pdgame_model()
-    e = float(o.energy[0 if a_resp else 1])
-    assert e == (50.0 if a_resp else 60.0) + pay
+    """RANDOM cooperates iff its coin bit is set (model.py:631, :664): bits 2c (challenger) and 2c+1 (responder)
+    of the 4th word of the RESPONDER's roll call; noise flips a choice iff its word < noise * 2^32 (:638-640,
+    :672-674): words of the responder's call S_NOISE0 + c//2, (x, y) for even c and (z, w) for odd c, where
+    c = direction from challenger to responder."""
+    for noise in (0.3, 0.0):
+        o = world(16, [(4, 4, 50.0, 2, [3] * 4), (5, 5, 60.0, 1, [3] * 4)], env_noise=noise)
+        o.search_for_neighbours()
+        o.get_game_list()
+        ca, cb = 4 + 4 * 16, 5 + 5 * 16
+        a_resp = (words(o, ca, S_ROLL)[0] >> ROLL_SHIFT) < (words(o, cb, S_ROLL)[0] >> ROLL_SHIFT)
+        resp_cell = ca if a_resp else cb
+        c = 0 if a_resp else 7      # challenger b at (5,5) reaches a at (4,4) in direction 0; a reaches b in 7
+        coins = words(o, resp_cell, S_ROLL)[3]
+        w = words(o, resp_cell, S_NOISE0 + c // 2)
+        my_roll, ch_roll = (w[2], w[3]) if c & 1 else (w[0], w[1])
+        thr = prob_threshold(noise)
+        i_coop = (((coins >> (2 * c + 1)) & 1) == 1) ^ (my_roll < thr)
+        ch_coop = (((coins >> (2 * c)) & 1) == 1) ^ (ch_roll < thr)
+        pay = 3.0 if (i_coop and ch_coop) else 0.0 if (not i_coop and not ch_coop) else -1.0 if i_coop else 5.0
+        o.pdgame_model()
+        e = float(o.energy[0 if a_resp else 1])
+        assert e == (50.0 if a_resp else 60.0) + pay
+
+
+def test_roll_tie_goes_to_the_neighbour_in_a_direction_ge_4():
+    """The pair-ordering roll keeps 19 bits; on a tie the agent that sees the other in a direction < 4
+    challenges (replaces the id tie-break of model.py:413): exactly one challenger per pair, from both sides."""
+    for dirn in range(8):
+        o = world(16, [(8, 8, 50.0, 0, [0] * 4), (8 + int(DX[dirn]), 8 + int(DY[dirn]), 50.0, 0, [0] * 4)])
+        o.search_for_neighbours()
+        o.roll[:] = 7            # force the tie
+        o.msg_roll[o.bucket] = o.roll
+        o.get_game_list()
+        ia = int(np.flatnonzero((o.x == 8) & (o.y == 8))[0])
+        ib = 1 - ia
+        assert int(o.act[ia, dirn]) == (1 if dirn < 4 else 0)
+        assert int(o.act[ib, 7 - dirn]) == (0 if dirn < 4 else 1)
 
 
 def test_play_death_and_energy_clamp():
@@ -147,7 +165,7 @@ def test_play_death_and_energy_clamp():
     o = world(16, [(4, 4, 0.5, 0, [0] * 4), (5, 4, 149.0, 0, [1] * 4)])
     o.search_for_neighbours()
     o.get_game_list()
-    coop_responds = words(o, 4 + 64, S_ROLL)[0] < words(o, 5 + 64, S_ROLL)[0]
+    coop_responds = (words(o, 4 + 64, S_ROLL)[0] >> ROLL_SHIFT) < (words(o, 5 + 64, S_ROLL)[0] >> ROLL_SHIFT)
     o.pdgame_model()
     if coop_responds:
         assert o.n == 1 and o.stats["play_deaths"] == 1 and float(o.energy[0]) == 149.0
