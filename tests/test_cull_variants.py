@@ -1,0 +1,68 @@
+"""Statistical validation of the ONE semantic the build replaced: the reference culls
+by FLAMEGPU2 list index (model.py:1343, :1354), the product culls the surplus newborns with the lowest Philox
+priority.  The oracle can run both (Params.cull); a grid layout can only run the second.  32 seeds each at
+128 x 128 over 100 steps (the cap is reached near step 60): the 95 % bands of the two rules must overlap at
+every checked step for the population and for all 16 strategy bins, and the means of one rule must lie
+inside the band of the other.  CPU only."""
+import importlib.util
+import multiprocessing as mp
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+spec = importlib.util.spec_from_file_location("stat_compare", os.path.join(ROOT, "tests", "stat_compare.py"))
+sc = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(sc)
+
+WIDTH, STEPS, SEEDS = 128, 100, 32
+CHECK = (25, 50, 60, 75, 100)
+
+
+def _run(job):
+    cull, seed = job
+    from oracle.pd_oracle import Oracle, Params
+    o = Oracle(Params(width=WIDTH, seed=seed, cull=cull))
+    o.init_population()
+    out = np.zeros((STEPS + 1, 16), np.int64)
+    out[0] = o.population_strat_count
+    peak = o.n
+    for t in range(1, STEPS + 1):
+        o.step()
+        out[t] = o.population_strat_count
+        peak = max(peak, o.n)
+    return out, peak
+
+
+def test_priority_cull_and_list_index_cull_agree_statistically():
+    jobs = [(cull, 12345 + i) for cull in ("priority", "list_index") for i in range(SEEDS)]
+    procs = max(1, min(8, os.cpu_count() or 1))
+    with mp.get_context("fork").Pool(procs) as pool:
+        res = pool.map(_run, jobs)
+    a = np.stack([r[0] for r in res[:SEEDS]])       # priority   [seed, step, bin]
+    b = np.stack([r[0] for r in res[SEEDS:]])       # list index
+    cap = WIDTH * WIDTH // 2
+    # the priority cull is a hard cap; the list-index cull overshoots a little (<= 0.5 % + )
+    assert max(r[1] for r in res[:SEEDS]) <= cap
+    peak_b = max(r[1] for r in res[SEEDS:])
+    assert cap < peak_b <= int(cap * 1.02), peak_b
+    mean_a, lo_a, hi_a = sc.bands(a)
+    mean_b, lo_b, hi_b = sc.bands(b)
+    inside = total = 0
+    for t in CHECK:
+        # 16 strategy bins: the bands overlap, and each rule's mean lies in the other's band
+        assert np.all(np.maximum(lo_a[t], lo_b[t]) <= np.minimum(hi_a[t], hi_b[t])), f"bands disjoint at step {t}"
+        inside += int(((mean_b[t] >= lo_a[t]) & (mean_b[t] <= hi_a[t])).sum())
+        inside += int(((mean_a[t] >= lo_b[t]) & (mean_a[t] <= hi_b[t])).sum())
+        total += 32
+    assert inside == total, f"{inside}/{total} means inside the other rule's 95 % band"
+    # the population: identical during growth (no cull yet), within the overshoot afterwards
+    pa, pb = a.sum(axis=2).mean(axis=0), b.sum(axis=2).mean(axis=0)
+    assert abs(pa[25] - pb[25]) / pa[25] < 0.02
+    assert abs(pa[STEPS] - pb[STEPS]) / pa[STEPS] < 0.01
+    # difference of the two rules' means in units of the seed-to-seed standard deviation (reported in DESIGN.md)
+    sd = 0.5 * (a.std(axis=0, ddof=1) + b.std(axis=0, ddof=1))
+    z = np.abs(mean_a - mean_b)[list(CHECK)] / np.maximum(sd[list(CHECK)], 1.0)
+    print(f"cull variants: peak list-index population {peak_b} (cap {cap}); max |mean difference| = {z.max():.2f} sd; "
+          f"final population {pa[STEPS]:.0f} vs {pb[STEPS]:.0f}")
+    assert z.max() < 1.0

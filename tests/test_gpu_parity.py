@@ -154,10 +154,49 @@ def test_multi_cta_sparse_path():
          payoff_cd=-10.0, reproduce_min_energy=60.0)
 
 
-def test_config1_512_defaults():
-    """BASELINE config 1: 512x512, defaults, first 12 steps bit-exact (the full 100 steps run in
-    the bench's cpu_baseline leg)."""
-    _run(12, width=512, seed=12345)
+@pytest.mark.parametrize("mode", ["kin_other", "pure"])
+def test_config1_512_full_run(mode):
+    """BASELINE config 1 at its own size and length: 512x512, model.py defaults, all 100 steps -- through the
+    growth phase, the cap (near step 60) and 40 steps of cull -- in the literal default mode (kin/other,
+    model.py:158-161) and in the "global strategy" (pure) variant BASELINE.json names."""
+    _run(100, width=512, seed=12345, **({"strategy_pure": 1} if mode == "pure" else {}))
+
+
+def test_config2_1024_own_size_past_the_cull():
+    """BASELINE config 2 at its own size: 1024x1024, noise 0.05, mutation 0.01, kin/other; 72 steps so that the
+    carrying capacity is reached and the cull (model.py:1339-1371) runs for several steps."""
+    _run(72, width=1024, seed=12345, env_noise=0.05, mutation_rate=0.01)
+
+
+def test_saturated_4096_per_trait_spot_check():
+    """A size the 128x16-tile kernels had only been checked at through invariants: 4096x4096 (32 x 256 CTAs per
+    sweep), per-trait mode, saturated.  The CUDA path runs 80 steps from init, its state is loaded into the
+    oracle, and both then take 3 steps: every plane, the counts and the event counters bit-exact."""
+    from pdabm_b200 import Simulation, SimConfig
+    from oracle.pd_oracle import Oracle, Params
+    kw = dict(width=4096, seed=2025, strategy_per_trait=1)
+    sim = Simulation(SimConfig(collect_stats=True, **kw))
+    try:
+        sim.init_population()
+        sim.step(80)
+        pl = sim.planes()
+        _, n = sim.counts()
+        assert n > 0.95 * sim.cfg.max_agents
+        orc = Oracle(Params(**kw))
+        orc.load_planes(pl["occ"], pl["energy"], pl["trait"], pl["strat"].reshape(-1, 4))
+        orc.step_index = sim.step_index
+        exact = _compare(sim, orc, "loaded")
+        for s in range(3):
+            sim.step(1)
+            st = orc.step()
+            exact &= _compare(sim, orc, f"step {s}")
+            gs = sim.stats()
+            for k in ("play_deaths", "movers", "moved", "travel_deaths", "births", "culled", "living_deaths"):
+                assert gs[k] == st[k], f"step {s}: stat {k} gpu {gs[k]} != oracle {st[k]}"
+            assert st["culled"] > 0
+        assert exact
+    finally:
+        sim.close()
 
 
 def test_size_independent_invariants_large():
