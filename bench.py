@@ -50,10 +50,11 @@ WORKLOADS = {
 }
 # algorithmic bytes per cell per launch of each dense sweep (DESIGN.md "Kernels"):
 #   play_travel : read tfA 1 + strat 1 + E0 4, write tfB 1 + E1 4
-#   move_commit : read tfB 1, write tfA 1
-#   repro_claim : read tfA 1 + E1 4, write tfB 1
-#   repro_commit: read tfB 1 + E1 4, write tfA 1 + E0 4   (+1 strat when counts are wanted)
-ALG_BYTES = {"play_travel": 11, "move_commit": 2, "repro_claim": 6, "repro_commit": 10}
+#   repro_claim : read tfB 1 + E1 4, write tfA 1
+#   punish      : read tfA 1 + E1 4, write tfA 1 + E0 4   (+1 strat when counts are wanted)
+# (the sparse kernels -- travel / reproduction rounds, at-risk agents, cull -- move list entries and the sectors
+#  around ~5 % of the cells; their traffic is reported from ncu, not from a per-cell figure)
+ALG_BYTES = {"play_travel": 11, "repro_claim": 6, "punish": 10}
 
 
 def measured_peaks():
@@ -294,13 +295,58 @@ def run_ours(args, rank, world, local_rank):
     h2d = rows_local * width * 6
     d2h = rows_local * width * 6 + 17 * 8
 
+    # ---- where the end-to-end time goes: the same round trip spelled out, CUDA events between its three legs
+    cur = torch.cuda.current_stream()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    legs = [0.0, 0.0, 0.0]
+    nbd = 3
+    for _ in range(nbd):
+        evs[0].record(cur)
+        one.energy.copy_(h_e, non_blocking=True)
+        one.strat.copy_(h_s, non_blocking=True)
+        one.tf.copy_(h_t, non_blocking=True)
+        evs[1].record(cur)
+        one._check(one.lib.pd_sync_state(one._h, one.stream_ptr))
+        sim.step(1, want_counts=True)
+        evs[2].record(cur)
+        h_e.copy_(one.energy, non_blocking=True)
+        h_s.copy_(one.strat, non_blocking=True)
+        h_t.copy_(one.tf, non_blocking=True)
+        evs[3].record(cur)
+        torch.cuda.synchronize()
+        for k in range(3):
+            legs[k] += evs[k].elapsed_time(evs[k + 1]) / nbd
+    barrier()
+
+    # ---- also (N = 1, default workload): the other BASELINE configurations and the from-init phase, in short
+    also = None
+    if world == 1 and args.workload == "config3" and not args.no_also:
+        also = {}
+        # config 3 from init: the growth phase (16 % -> 50 % density in ~60 steps), counts off
+        sim.init_population()
+        torch.cuda.synchronize()
+        as_i = sim.agent_steps()
+        ei0, ei1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ei0.record()
+        sim.step(60, want_counts=False)
+        ei1.record()
+        torch.cuda.synchronize()
+        msi = ei0.elapsed_time(ei1)
+        also["config3_from_init"] = {"workload": desc + " -- the first 60 steps from init (growth phase)", "steps": 60,
+                                     "ms_per_step": msi / 60, "value": (sim.agent_steps() - as_i) / (msi / 1e3),
+                                     "unit": "agent-steps/s", "agents_at_end": sim.counts()[1]}
+        also["config1"] = _small_config_line("config1", 100)
+        also["config2"] = _small_config_line("config2", 500)
+        also["config4_16runs"] = _ensemble_line(16, 100)
+
     # ---- reduce over ranks: total agent-steps, max time
     if world > 1:
-        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e_s] + legs, dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         a = torch.tensor([agent_steps, e2e_agents], dtype=torch.float64, device="cuda")
         dist.all_reduce(a, op=dist.ReduceOp.SUM)
         ms, e2e_s = float(t[0]), float(t[1])
+        legs = [float(t[2]), float(t[3]), float(t[4])]
         agent_steps, e2e_agents = float(a[0]), float(a[1])
     if rank != 0:
         sim.close()
@@ -317,7 +363,7 @@ def run_ours(args, rank, world, local_rank):
         per = v / max(1, prof_steps)
         ent = {"ms_per_step": per, "share": per / step_ms_sum if step_ms_sum else None}
         if k in ALG_BYTES:
-            b = ALG_BYTES[k] + (1 if (k == "repro_commit" and want_counts) else 0)
+            b = ALG_BYTES[k] + (1 if (k == "punish" and want_counts) else 0)
             ent["alg_bytes_per_cell"] = b
             ent["gbs"] = b * cells / (per * 1e-3) / 1e9 if per > 0 else None
             ent["frac_of_hbm_peak"] = ent["gbs"] / peak if per > 0 else None
@@ -343,28 +389,38 @@ def run_ours(args, rank, world, local_rank):
         "scaling": "strong" if (args.height or (slabs and args.workload == "config5")) else "weak",
         "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": desc, "width": width, "cells": cells, "cells_per_gpu": cells,
+        "config": {"workload": desc, "width": width, "cells": cells * world if slabs else cells, "cells_per_gpu": cells,
                    "partitioning": ("row slabs of one world, one per GPU: NVLink halo exchange of 64 boundary rows x 3 planes "
                                     "+ 4 (gate closed) to 11 small collectives per step" if slabs else
                                     "one world per GPU (ensemble), no data-path collective" if world > 1 else "single world"),
                    "presteps": args.presteps, "agents_at_start": n_before, "agents_at_end": n_after,
-                   "density": n_after / cells, "counts_every_step": want_counts,
+                   "density": n_after / (cells * world if slabs else cells), "counts_every_step": want_counts,
                    "l2": "state (11 B/cell resident) larger than the 126 MB L2" if cells * 11 > 126e6
                          else "state fits in L2: HBM roofline figures are not meaningful at this size"},
         "cell_steps_per_s": cells * world * args.steps / secs,
         "step_alg_bytes_per_cell": total_alg, "step_alg_gbs": step_gbs, "step_frac_of_hbm_peak": step_gbs / peak,
         "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": kern[dom]["gbs"], "peak": peak,
                      "unit": "GB/s", "frac": kern[dom]["frac_of_hbm_peak"], "traffic": None,
+                     "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch, STORED in "
+                                       "profiles/traffic.json (not measured by this run)",
                      "peak_source": peak_src, "alg_bytes_per_launch": ALG_BYTES[dom] * cells,
-                     "launch_ms": kern[dom]["ms_per_step"]},
+                     "launch_ms": kern[dom]["ms_per_step"],
+                     # HBM is the roofline this path is held against; what limits the kernel TODAY is named here
+                     "limited_by": "instruction issue (ncu: issue slots ~70 % busy, DRAM ~15 %)"
+                                   if (kern[dom]["frac_of_hbm_peak"] or 0) < 0.5 else "HBM bandwidth"},
         "kernels": kern,
+        "also": also,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_agents / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                "call": "pd_step_host (host planes in, host planes + counts out)"},
-        # per step: 9 kernels (whole world; replayed as one CUDA graph on small worlds), or 12 + 2 per
+                "call": "pd_step_host (host planes in, host planes + counts out)",
+                # the legs of one round trip (max over ranks, CUDA events): the PCIe copies are the floor
+                "h2d_ms": legs[0], "step_ms": legs[1], "d2h_ms": legs[2],
+                "h2d_gbs_per_gpu": h2d / (legs[0] * 1e-3) / 1e9 if legs[0] > 0 else None,
+                "d2h_gbs_per_gpu": d2h / (legs[2] * 1e-3) / 1e9 if legs[2] > 0 else None},
+        # per step: 8 kernels (whole world; replayed as one CUDA graph on small worlds), or 12 + 2 per
         # reproduction retry round that actually ran (row slab, this rank)
-        "gpu_launches": (12 * args.steps + 2 * retry_rounds) if slabs else 9 * args.steps,
+        "gpu_launches": (12 * args.steps + 2 * retry_rounds) if slabs else 8 * args.steps,
         "graph_replays": replays,
         "clocks": clocks,
         "init_and_presteps_s": init_s,
@@ -374,6 +430,12 @@ def run_ours(args, rank, world, local_rank):
         try:
             tr = json.load(open(traffic_file))
             line["roofline"]["traffic"] = tr.get("k_" + dom, {}).get(args.workload)
+            for k, ent in kern.items():  # stored ncu bytes per launch of every kernel, and their ratio to the
+                t_k = tr.get("k_" + k, {}).get(args.workload)  # algorithmic bytes where a per-cell figure exists
+                if t_k is not None:
+                    ent["traffic_bytes_per_launch_ncu_stored"] = t_k
+                    if "alg_bytes_per_cell" in ent:
+                        ent["traffic_ratio"] = t_k / (ent["alg_bytes_per_cell"] * cells)
         except Exception:
             pass
     print(json.dumps(line), flush=True)
@@ -381,6 +443,82 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _small_config_line(name, steps, from_init=True):
+    """One of BASELINE's small configurations (configs[0] / configs[1]) from init, counts every step, on an
+    explicit stream (one CUDA graph replay per step): ms per step and agent-steps/s over `steps` steps."""
+    import torch
+    from pdabm_b200 import Simulation, SimConfig
+    width, overrides, desc = WORKLOADS[name]
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        sim = Simulation(SimConfig(width=width, seed=12345, **overrides), stream=st)
+        sim.init_population()
+        sim.step(3, want_counts=True)            # graph capture + warm-up, then start again from init
+        sim.init_population()
+        st.synchronize()
+        as0, gr0 = sim.agent_steps(), sim.graph_replays()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        sim.step(steps, want_counts="every")
+        e1.record(st)
+        st.synchronize()
+        ms = e0.elapsed_time(e1)
+        out = {"workload": desc, "steps": steps, "from": "init (16 % density)", "ms_per_step": ms / steps,
+               "value": (sim.agent_steps() - as0) / (ms / 1e3), "unit": "agent-steps/s",
+               "graph_replays": sim.graph_replays() - gr0, "agents_at_end": sim.counts()[1]}
+        sim.close()
+    return out
+
+
+def _ensemble_line(runs, steps):
+    """BASELINE configs[3] in small: `runs` concurrent 1024x1024 worlds of the noise x mutation x payoff grid on
+    one GPU, one per CUDA stream, from init."""
+    import threading
+    import torch
+    from pdabm_b200 import Simulation, SimConfig
+    grid = [(n, m, cc) for n in (0.0, 0.01, 0.05, 0.1) for m in (0.0, 0.001, 0.01, 0.05) for cc in (2.0, 3.0, 4.0, 6.0)]
+    sims, streams = [], []
+    for i in range(runs):
+        noise, mut, cc = grid[(i * 5) % len(grid)]
+        stt = torch.cuda.Stream()
+        sims.append(Simulation(SimConfig(width=1024, seed=12345 + i, env_noise=noise, mutation_rate=mut, payoff_cc=cc),
+                               stream=stt))
+        streams.append(stt)
+
+    def all_streams(k):
+        th = [threading.Thread(target=lambda s=s: s.step(k, want_counts="every")) for s in sims]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    for s in sims:
+        s.init_population()
+    all_streams(3)
+    for s in sims:
+        s.init_population()
+    torch.cuda.synchronize()
+    as0 = sum(s.agent_steps() for s in sims)
+    start = torch.cuda.Event(enable_timing=True)
+    start.record()
+    for stt in streams:
+        stt.wait_event(start)
+    all_streams(steps)
+    ends = []
+    for stt in streams:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stt)
+        ends.append(e)
+    torch.cuda.synchronize()
+    ms = max(start.elapsed_time(e) for e in ends)
+    val = (sum(s.agent_steps() for s in sims) - as0) / (ms / 1e3)
+    for s in sims:
+        s.close()
+    return {"workload": f"BASELINE configs[3] in small: {runs} concurrent 1024x1024 runs (noise x mutation x payoff_cc), "
+                        "one per CUDA stream, from init, counts every step",
+            "runs": runs, "steps": steps, "ms_per_step_all_runs": ms / steps, "value": val, "unit": "agent-steps/s"}
 
 
 def run_config4(args, rank, world, local_rank):
@@ -449,7 +587,7 @@ def run_config4(args, rank, world, local_rank):
                                        f"{per_gpu} concurrent runs per GPU, one per CUDA stream, counts every step",
                            "runs": per_gpu * world, "presteps": args.presteps,
                            "l2": "each world's state fits in L2: no HBM roofline claim"},
-                "gpu_launches": 9 * args.steps * per_gpu * world}
+                "gpu_launches": 8 * args.steps * per_gpu * world}
         print(json.dumps(line), flush=True)
     for s in sims:
         s.close()
@@ -461,7 +599,7 @@ def run_config4(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)  # ~1 s of timed region at the default workload
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS) + ["config4", "config5"])
@@ -475,6 +613,7 @@ def main():
     ap.add_argument("--sparse-ctas", type=int, default=0, help="CTAs of the sparse list kernels (0 = library default)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the short runs of the other BASELINE configs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

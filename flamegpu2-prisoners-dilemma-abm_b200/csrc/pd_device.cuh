@@ -13,15 +13,13 @@ namespace pd {
 // ---- tf plane bits ---------------------------------------------------------------------
 // Canonical (between steps): OCC | trait.  Transient meanings per phase:
 //   tfA during play      : bits 3-6 = D code of an at-risk agent (0 none, c+1 = dies in sub-step c)
-//   tfB/tfA during travel: GHOST = cell was occupied at step start but is empty now (still
+//   tfB during travel    : GHOST = cell was occupied at step start but is empty now (still
 //                          blocks movers, quirk B-13), CLAIM|DIR = mover claiming direction DIR
-//   tfB during reproduce : CLAIM|DIR = parent claiming direction DIR
-//   tfA after reproduce  : NEWBORN (same bit as GHOST) until the cull has run
+//   tfA during reproduce : CLAIM|DIR = parent claiming direction DIR; NEWBORN (same bit as GHOST) = child of
+//                          this step (only written when retry rounds must see its cell), until the cull has run
 constexpr uint32_t TF_TRAIT = 0x03u;
 constexpr uint32_t TF_GHOST = 0x04u;
 constexpr uint32_t TF_NEWBORN = 0x04u;
-constexpr uint32_t TF_DYING = 0x08u;  // tfA after the final sweep: died of living cost, but still
-                                      // occupies its cell until the reproduction rounds are over
 constexpr uint32_t TF_DIR_SHIFT = 3u;
 constexpr uint32_t TF_DIR = 0x38u;
 constexpr uint32_t TF_CLAIM = 0x40u;
@@ -62,10 +60,10 @@ static_assert(DY(0) == -1 && DY(1) == 0 && DY(2) == 1 && DY(3) == -1 && DY(4) ==
 // ---- device-resident counters -----------------------------------------------------------
 struct Counters {
     // zeroed at the start of every step (k_begin_step)
-    unsigned int mv_n, rp_n, nb_n, risk_next_n, dead_n, cand_n, nb_flagged, dep_n;
-    unsigned int dl_n, pad1_;
+    unsigned int mv_n, rp_n, nb_n, risk_next_n, cand_n, nb_flagged, dep_n, pad1_;
+    unsigned int rt_n[2], dw_n[2];  // retry list / deferred winners: [0] travel, [1] reproduction
     unsigned int mv_active[8], rp_active[8];
-    unsigned long long n_old, births, culled, living_deaths;
+    unsigned long long n_old, culled, living_deaths, pad2_;
     unsigned long long st_play_deaths, st_movers, st_moved, st_travel_deaths;
     unsigned long long bins[16];
     unsigned int hist[8][256];
@@ -76,7 +74,7 @@ struct Counters {
     unsigned int barrier[2];
     unsigned int log_n, log_dropped;  // rows in the step log / rows that did not fit
     unsigned int step_no;  // model step being computed: the Philox key of every draw.  Device-resident so that
-    unsigned int pad2_;    // a captured CUDA graph of one step can be replayed (k_set_step / fin_bookkeeping)
+    unsigned int pad3_;    // a captured CUDA graph of one step can be replayed (k_set_step / fin_bookkeeping)
     unsigned long long n_agents;
     unsigned long long agents_start;
     unsigned long long agent_steps;  // running sum of the population at the start of every step
@@ -111,6 +109,7 @@ struct Params {
     unsigned int* ghist;            // 2048-bin cull histogram, summed over all slabs by the caller
     unsigned long long* cand_out;   // this slab's cull candidates: [0] = count, then keys
     const unsigned long long* cand_all;  // all slabs' candidate blocks, gathered by the caller
+    const float* lut;  // 256-entry payoff table of the play sweep (lut_entry, pd_dense.cuh)
     // planes
     float* E0;       // caller-bound energy (state between steps)
     float* E1;       // scratch energy (state between play and the final sweep)
@@ -118,15 +117,15 @@ struct Params {
     uint8_t* tfA;    // caller-bound
     uint8_t* tfB;    // scratch
     // sparse lists
-    uint32_t* risk_cur; uint32_t* risk_next; float* risk_e; uint32_t* risk_roll;
-    uint32_t* mv_cell; uint8_t* mv_state; uint8_t* mv_aux;
-    uint32_t* rp_cell; uint8_t* rp_state; uint8_t* rp_aux;
+    uint32_t* risk_cur; uint32_t* risk_next; float* risk_e;
+    unsigned long long* cand;  // cull select: the threshold bin's candidate keys (list_cap / 2 of them)
+    uint32_t* mv_cell; uint8_t* mv_state;  // travel claimants of the dense sweep (round 1)
+    uint32_t* rp_cell; uint8_t* rp_state;  // reproduction claimants of the dense sweep (round 1)
+    uint32_t* rt_cell; uint8_t* rt_state; uint8_t* rt_aux;  // the losers of round 1: rounds 2..8 (travel, then reproduction)
+    uint32_t* dw_idx;  // round 1's contested winners, committed after a barrier; aliases risk_e (free after k_risk_resolve)
     uint32_t* nb_cell;
     float* nb_e; uint16_t* nb_gene;  // the newborn's energy and strategies | trait << 8 (it is written into the
                                      // planes only if it survives the cull, or when retry rounds must see it)
-    uint32_t* dead_cell;  // aliases mv_cell (the travel rounds are over when it is filled)
-    uint32_t* dl_cell;    // claim losers whose living cost is deferred to k_finalize; aliases risk_e (only used
-                          // inside k_risk_resolve)
     Counters* ctr;
 };
 

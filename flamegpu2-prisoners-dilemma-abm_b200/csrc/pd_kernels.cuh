@@ -4,14 +4,16 @@
 //   k_begin_step    zero the per-step counters
 //   k_risk_resolve  sparse: exact death sub-step of the few agents that CAN die in play
 //   k_play_travel   dense sweep 1: roll + roles + 8 play sub-steps + mover decision + travel claim
-//   k_move_commit   dense sweep 2: resolve travel claims (round 1), pull movers into targets
-//   k_move_retry    sparse: travel rounds 2..8 for the claim losers
-//   k_repro_claim   dense sweep 3: eligibility + reproduction claim
-//   k_repro_commit  dense sweep 4: resolve claims (round 1), births, cost of living, death, counts
-//   k_repro_retry   sparse: reproduction rounds 2..8 (gated by the carrying capacity)
-//   k_finalize      sparse: newborn cull (exact k-th selection), deferred living cost, counts
-// Every dense sweep is a pure GATHER: a cell reads its neighbourhood and writes only itself,
-// so there are no claim planes, no atomics on cells and no clears (DESIGN.md "Kernels").
+//   k_move_rounds   sparse: the (up to) 8 rounds of move_response / move_request over the travel list
+//   k_repro_claim   dense sweep 2: eligibility + reproduction claim
+//   k_repro_rounds  sparse: the (up to) 8 rounds of god_multiply / god_go_forth (gated by the carrying capacity)
+//   k_punish        dense sweep 3: cost of living, death, counts, next step's at-risk list
+//   k_finalize      sparse: newborn cull (exact k-th selection), the surviving newborns enter the planes
+// The dense sweeps are pure GATHERS (a cell reads its neighbourhood and writes only itself); the sparse
+// kernels work in place on the flag plane, phases separated by grid barriers: there are no claim planes,
+// no atomics on cells and no clears (DESIGN.md "Kernels").
+// The persistent sparse kernels are templated on their block size: one 1024-thread CTA on small worlds,
+// 512-thread CTAs (128 registers available) in the cooperative multi-CTA launch.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -46,7 +48,8 @@ __global__ void k_begin_step(Counters* ctr, int count_step) {
 //   Phase 2, the rest (an at-risk challenger may die before it challenges): eight lock-stepped rounds
 //   over those few reproduce exit_play_fn's iterations (:1527-1556) exactly.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_risk_resolve(const __grid_constant__ Params p) {
+template <int BS>
+__global__ void __launch_bounds__(BS) k_risk_resolve(const __grid_constant__ Params p) {
     Counters* ctr = p.ctr;
     const unsigned int n = ctr->risk_n;
     const unsigned int stride = gridDim.x * blockDim.x;
@@ -135,31 +138,152 @@ __global__ void __launch_bounds__(1024) k_risk_resolve(const __grid_constant__ P
 }
 
 // ------------------------------------------------------------------------------------------
-// k_move_retry (sparse, persistent): travel rounds 2..8 (exit_move_fn, :1559-1576) for the
-// losers of round 1.  Three phases per round separated by grid barriers:
-//   request  (:784-872)  probe from the saved direction over blocked = OCC|GHOST, post the claim
-//   response (:881-960)  every claimant evaluates the contest at its target
-//   apply                winners relocate, losers drop their claim
+// Claim resolution over a list (move_response :881-960, god_multiply :1170-1205), in place on a flag plane.
+// A claimant reads the claim flags of the 8 cells around its target; `rivals` = neighbours of the target
+// (other than me) that claim it too.  Highest (priority, cell) wins; only contested targets need priorities.
+//
+// Round 1 visits every claimant of the dense sweep ONCE: an uncontested claimant (most of them) commits on
+// the spot -- nobody else looks at its flag or at its target -- and a loser drops its claim and joins the
+// retry list at once; only a contested WINNER must wait until its rivals have seen its flag, so it goes on a
+// short deferred list that is committed after a grid barrier.  (A loser that has already dropped its flag
+// may be missed by a rival, which changes nothing: the winner's flag stays, and the winner wins whoever it sees.)
+// Rounds 2..8 run over the compact retry list in three barrier-separated phases (request / response / apply).
+// List entry state: 0x80 active | 0x40 fresh (claimed by the dense sweep) | (probes used - 1) << 3 | start direction.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_move_retry(const __grid_constant__ Params p) {
+// CTA-aggregated append to N global lists at once: ONE atomicAdd per list per call for the whole CTA (a
+// warp-aggregated append costs one same-address atomic per warp: ~1.3 M of them per step on the round-1 lists
+// of a 2^28-cell world, which serialise in L2 -- profiles/README.md).  Every thread of the CTA must call;
+// slot[k] is only meaningful where pred[k] is set.  Two barriers per call.
+template <int N>
+__device__ __forceinline__ void block_append(unsigned int* const (&counter)[N], const bool (&pred)[N], uint32_t (&slot)[N]) {
+    __shared__ unsigned int s_cnt[N][32];
+    __shared__ unsigned int s_base[N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    unsigned int m[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        m[k] = __ballot_sync(0xFFFFFFFFu, pred[k]);
+        if (lane == 0) s_cnt[k][warp] = (unsigned int)__popc(m[k]);
+    }
+    __syncthreads();
+    if (threadIdx.x < N) {
+        const int k = threadIdx.x;
+        unsigned int total = 0;
+        for (int w = 0; w < nwarp; ++w) {
+            const unsigned int c = s_cnt[k][w];
+            s_cnt[k][w] = total;
+            total += c;
+        }
+        s_base[k] = total ? atomicAdd(counter[k], total) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) slot[k] = s_base[k] + s_cnt[k][warp] + (unsigned int)__popc(m[k] & ((1u << lane) - 1u));
+}
+
+template <typename KeyFn>
+__device__ __forceinline__ bool contest(const Params& p, const uint8_t* tf, uint32_t x, uint32_t y, int d, KeyFn keyfn,
+                                        bool& contested) {
+    const uint32_t tx = (x + (uint32_t)DX(d)) & (p.W - 1);
+    const uint32_t ty = nb_row(p, y, DY(d));
+    uint32_t rivals = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t tn = __ldcg(tf + nb_local(p, tx, ty, j));
+        if (claims_dir(tn, 7 - j)) rivals |= 1u << j;
+    }
+    rivals &= ~(1u << (7 - d));  // that one is me
+    contested = rivals != 0u;
+    if (!contested) return true;
+    const Key mine = keyfn(p, gcell_of(p, x, y));
+    bool win = true;
+    for (uint32_t m = rivals; m; m &= m - 1)
+        if (key_gt(keyfn(p, nb_gcell(p, tx, ty, __ffs(m) - 1)), mine)) win = false;
+    return win;
+}
+
+// a mover relocates (:946-956); its old cell stays a GHOST: it blocks movers all step (B-13)
+__device__ __forceinline__ void commit_move(const Params& p, uint8_t* tf, uint32_t cell, uint32_t t, int d) {
+    const uint32_t tgt = nb_local(p, cell & (p.W - 1), cell >> p.log2W, d);
+    p.E1[tgt] = __ldcg(p.E1 + cell);
+    p.strat[tgt] = __ldcg(p.strat + cell);
+    tf[tgt] = (uint8_t)(TF_OCC | (t & TF_TRAIT));
+    tf[cell] = (uint8_t)TF_GHOST;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_move_rounds (sparse, persistent): the movement submodel's rounds (exit_move_fn, :1559-1576).  Round 1's
+// move_request is fused into k_play_travel, which lists its claimants; in place on tfB / E1 / strat.
+// ------------------------------------------------------------------------------------------
+template <int BS>
+__global__ void __launch_bounds__(BS) k_move_rounds(const __grid_constant__ Params p) {
     Counters* ctr = p.ctr;
-    unsigned int n = ctr->mv_n;
-    if (n > p.list_cap) n = p.list_cap;
-    if (n == 0) return;
+    unsigned int n0 = ctr->mv_n;
+    if (n0 > p.list_cap) n0 = p.list_cap;
+    if (n0 == 0) return;
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    uint8_t* tf = p.tfB;
+    unsigned int moved = 0;
+    // ---- round 1: one visit per claimant
+    for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < n0; i0 += stride) {
+        const unsigned int i = i0 + threadIdx.x;
+        bool defer = false, lost = false;
+        uint32_t cell = 0, st = 0;
+        if (i < n0) {
+            cell = p.mv_cell[i];
+            st = p.mv_state[i];
+            const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
+            const int d = (int)(st & 7u);
+            bool contested;
+            const bool win = contest(p, tf, x, y, d, TravelKey(), contested);
+            if (!contested) {
+                commit_move(p, tf, cell, __ldcg(tf + cell), d);
+                if (row_owned(p, y)) ++moved;
+            } else if (win) {
+                defer = true;
+            } else {
+                tf[cell] = (uint8_t)(__ldcg(tf + cell) & (TF_OCC | TF_TRAIT));  // :940-943 -> retry with the same roll
+                lost = true;
+            }
+        }
+        unsigned int* const cnt[2] = {&ctr->dw_n[0], &ctr->rt_n[0]};
+        const bool pred[2] = {defer, lost};
+        uint32_t slot[2];
+        block_append<2>(cnt, pred, slot);
+        if (defer) p.dw_idx[slot[0]] = i;  // dw_n <= n0 <= list_cap
+        if (lost) {
+            p.rt_cell[slot[1]] = cell;
+            p.rt_state[slot[1]] = (uint8_t)st;
+        }
+    }
+    grid_sync(ctr->barrier, gridDim.x);
+    const unsigned int ndw = __ldcg(&ctr->dw_n[0]);
+    for (unsigned int k = t0; k < ndw; k += stride) {
+        const unsigned int i = __ldcg(&p.dw_idx[k]);
+        const uint32_t cell = p.mv_cell[i];
+        commit_move(p, tf, cell, __ldcg(tf + cell), (int)(p.mv_state[i] & 7u));
+        if (row_owned(p, cell >> p.log2W)) ++moved;
+    }
+    const unsigned int n = __ldcg(&ctr->rt_n[0]);
+    if (n == 0) {
+        if (p.stats && moved) atomicAdd(&ctr->st_moved, (unsigned long long)moved);
+        return;
+    }
+    grid_sync(ctr->barrier, gridDim.x);
+    // ---- rounds 2..8 over the retry list
     for (int round = 1; round < 8; ++round) {
-        // ---- request
+        // request (:784-872): probe from the saved direction over blocked = OCC|GHOST, post the claim
         for (unsigned int i = t0; i < n; i += stride) {
-            const uint32_t st = p.mv_state[i];
+            const uint32_t st = p.rt_state[i];
             if (!(st & 0x80u)) continue;
-            const uint32_t cell = p.mv_cell[i];
+            const uint32_t cell = p.rt_cell[i];
             const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
             uint32_t blocked = 0;
 #pragma unroll
             for (int d = 0; d < 8; ++d)
-                if (__ldcg(p.tfA + nb_local(p, x, y, d)) & (TF_OCC | TF_GHOST)) blocked |= 1u << d;
-            int l = (int)(st & 7u), seq = (int)((st >> 3) & 7u) + 1;  // state: 0x80 active | 0x40 fresh | (seq-1) << 3 | start
+                if (__ldcg(tf + nb_local(p, x, y, d)) & (TF_OCC | TF_GHOST)) blocked |= 1u << d;
+            int l = (int)(st & 7u), seq = (int)((st >> 3) & 7u) + 1;
             if (st & 0x40u) {  // fresh from round 1: it claimed direction l after probe_pos probes (:848-849)
                 const int s0 = (int)(rng(p, gcell_of(p, x, y), S_ROLL).z >> 29);
                 seq = probe_pos(s0, l);
@@ -167,53 +291,38 @@ __global__ void __launch_bounds__(1024) k_move_retry(const __grid_constant__ Par
             }
             const int dir = probe(blocked, l, seq);
             if (dir < 0) {
-                p.mv_state[i] = 0;  // no free space: stays put (:842-846)
+                p.rt_state[i] = 0;  // no free space: stays put (:842-846)
             } else {
-                const uint32_t t = __ldcg(p.tfA + cell);
-                p.tfA[cell] = (uint8_t)((t & (TF_OCC | TF_TRAIT)) | TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT));
-                p.mv_state[i] = (uint8_t)(0x80u | (uint32_t)((dir + 1) & 7) | ((uint32_t)(seq - 1) << 3));
-                p.mv_aux[i] = (uint8_t)dir;
+                const uint32_t t = __ldcg(tf + cell);
+                tf[cell] = (uint8_t)((t & (TF_OCC | TF_TRAIT)) | TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT));
+                p.rt_state[i] = (uint8_t)(0x80u | (uint32_t)((dir + 1) & 7) | ((uint32_t)(seq - 1) << 3));
+                p.rt_aux[i] = (uint8_t)dir;
             }
         }
         grid_sync(ctr->barrier, gridDim.x);
-        // ---- response
+        // response (:881-960)
         for (unsigned int i = t0; i < n; i += stride) {
-            if (!(p.mv_state[i] & 0x80u)) continue;
-            const uint32_t cell = p.mv_cell[i];
-            const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
-            const int d = (int)(p.mv_aux[i] & 7u);
-            const uint32_t tx = (x + (uint32_t)DX(d)) & (p.W - 1);
-            const uint32_t ty = nb_row(p, y, DY(d));
-            bool win = true, have_key = false;
-            Key mine;
-            for (int j = 0; j < 8; ++j) {
-                if (j == 7 - d) continue;
-                const uint32_t tn = __ldcg(p.tfA + nb_local(p, tx, ty, j));
-                if (!claims_dir(tn, 7 - j)) continue;
-                if (!have_key) { mine = TravelKey()(p, gcell_of(p, x, y)); have_key = true; }
-                if (key_gt(TravelKey()(p, nb_gcell(p, tx, ty, j)), mine)) win = false;
-            }
-            p.mv_aux[i] = (uint8_t)((uint32_t)d | (win ? 0x80u : 0u));
+            if (!(p.rt_state[i] & 0x80u)) continue;
+            const uint32_t cell = p.rt_cell[i];
+            const int d = (int)(p.rt_aux[i] & 7u);
+            bool contested;
+            const bool win = contest(p, tf, cell & (p.W - 1), cell >> p.log2W, d, TravelKey(), contested);
+            p.rt_aux[i] = (uint8_t)((uint32_t)d | (win ? 0x80u : 0u));
         }
         grid_sync(ctr->barrier, gridDim.x);
-        // ---- apply
+        // apply
         unsigned int still = 0;
         for (unsigned int i = t0; i < n; i += stride) {
-            if (!(p.mv_state[i] & 0x80u)) continue;
-            const uint32_t cell = p.mv_cell[i];
-            const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
-            const uint32_t aux = p.mv_aux[i];
-            const uint32_t t = __ldcg(p.tfA + cell);
+            if (!(p.rt_state[i] & 0x80u)) continue;
+            const uint32_t cell = p.rt_cell[i];
+            const uint32_t aux = p.rt_aux[i];
+            const uint32_t t = __ldcg(tf + cell);
             if (aux & 0x80u) {
-                const uint32_t tgt = nb_local(p, x, y, (int)(aux & 7u));
-                p.E1[tgt] = __ldcg(p.E1 + cell);
-                p.strat[tgt] = __ldcg(p.strat + cell);
-                p.tfA[tgt] = (uint8_t)(TF_OCC | (t & TF_TRAIT));
-                p.tfA[cell] = (uint8_t)TF_GHOST;
-                p.mv_state[i] = 0;
-                if (p.stats && row_owned(p, y)) atomicAdd(&ctr->st_moved, 1ull);
+                commit_move(p, tf, cell, t, (int)(aux & 7u));
+                p.rt_state[i] = 0;
+                if (row_owned(p, cell >> p.log2W)) ++moved;
             } else {
-                p.tfA[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
+                tf[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
                 ++still;
             }
         }
@@ -221,49 +330,149 @@ __global__ void __launch_bounds__(1024) k_move_retry(const __grid_constant__ Par
         grid_sync(ctr->barrier, gridDim.x);
         if (__ldcg(&ctr->mv_active[round]) == 0u) break;
     }
+    if (p.stats && moved) atomicAdd(&ctr->st_moved, (unsigned long long)moved);
 }
 
 // ------------------------------------------------------------------------------------------
-// k_repro_retry (sparse, persistent): reproduction rounds 2..8 (exit_god_fn, :1607-1627).
-// Runs only while the population (olds + births so far) does not exceed max_agents.
+// k_repro_rounds (sparse, persistent): the god submodel's rounds (exit_god_fn, :1607-1627).  Round 1's
+// god_go_forth is fused into k_repro_claim, which lists its claimants; in place on tfA / E1.  Round 1 always
+// runs; further rounds only while the population (olds + births so far) does not exceed max_agents (:1616,
+// :1621-1625).  A winner pays the reproduction cost in E1 (the cost of living follows in k_punish, like layer 7
+// after the god submodel) and its child goes on the newborn list with its energy and strategies; the child
+// enters the flag plane only when further rounds must see its cell blocked -- near the carrying capacity
+// almost every newborn is culled in the same step.
+// Rounds [round0, round1) run in this launch (a row slab runs one round per launch: the caller sums the
+// population over the slabs in between).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_repro_retry(const __grid_constant__ Params p) {
+struct Birth {
+    bool born;
+    uint32_t tgt, gene;
+    float ce;
+};
+// the parent at `cell` (flag byte t) reproduces into direction d (:1208-1328); mark = the child blocks its cell
+__device__ __forceinline__ Birth commit_birth(const Params& p, uint8_t* tf, uint32_t cell, uint32_t t, int d, bool mark) {
+    const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
+    Birth b;
+    b.tgt = nb_local(p, x, y, d);
+    const float pe = __fsub_rn(__ldcg(p.E1 + cell), p.reproduce_cost);  // :1211-1213
+    p.E1[cell] = pe;
+    uint32_t cs;
+    make_child(p, gcell_of(p, x, y), __ldcg(p.strat + cell), t & TF_TRAIT, pe, b.ce, cs);
+    b.gene = cs | ((t & TF_TRAIT) << 8);
+    b.born = row_owned(p, b.tgt >> p.log2W);  // a child in the ghost zone belongs to the neighbour slab: it is not
+    // listed here, so it cannot be flagged later -- it has to block its cell from now on
+    if (mark || !b.born) tf[b.tgt] = (uint8_t)(TF_OCC | TF_NEWBORN | (t & TF_TRAIT));
+    return b;
+}
+// every thread of the CTA calls: the newborn list takes the child with its payload; `births` is counted by
+// the callers from the list length
+__device__ __forceinline__ void store_birth(const Params& p, const Birth& b, uint32_t slot) {
+    if (b.born) {
+        if (slot < p.list_cap) {
+            p.nb_cell[slot] = b.tgt;
+            p.nb_e[slot] = b.ce;
+            p.nb_gene[slot] = (uint16_t)b.gene;
+        } else atomicExch(&p.ctr->overflow, 1u);
+    }
+}
+__device__ __forceinline__ void list_birth(const Params& p, const Birth& b) {
+    unsigned int* const cnt[1] = {&p.ctr->nb_n};
+    const bool pred[1] = {b.born};
+    uint32_t slot[1];
+    block_append<1>(cnt, pred, slot);
+    store_birth(p, b, slot[0]);
+}
+
+template <int BS>
+__global__ void __launch_bounds__(BS) k_repro_rounds(const __grid_constant__ Params p) {
     Counters* ctr = p.ctr;
-    unsigned int n = ctr->rp_n;
-    if (n > p.list_cap) n = p.list_cap;
-    if (n == 0) return;
+    unsigned int n0 = ctr->rp_n;
+    if (n0 > p.list_cap) n0 = p.list_cap;
+    if (n0 == 0) return;  // nobody claims: no births either
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    // The newborns of round 1 are only on the newborn list so far (k_repro_commit).  If retry rounds are
-    // going to run, they must block their cells: mark them occupied first.
-    if (p.round0 == 1) {
-        const unsigned long long pop0 = p.glb ? __ldcg(&p.glb[0]) + __ldcg(&p.glb[1])
-                                              : __ldcg(&ctr->n_old) + __ldcg(&ctr->births);
-        if (pop0 > p.max_agents) return;  // the gate is closed for good: no retry rounds this step
-        unsigned int nb1 = ctr->nb_n;
-        if (nb1 > p.list_cap) nb1 = p.list_cap;
-        for (unsigned int i = t0; i < nb1; i += stride)
-            p.tfA[p.nb_cell[i]] = (uint8_t)(TF_OCC | TF_NEWBORN | ((uint32_t)(p.nb_gene[i] >> 8) & TF_TRAIT));
-        if (t0 == 0) ctr->nb_flagged = 1u;
+    uint8_t* tf = p.tfA;
+    if (p.round0 == 0) {
+        // ---- round 1: one visit per claimant
+        for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < n0; i0 += stride) {
+            const unsigned int i = i0 + threadIdx.x;
+            bool defer = false, lost = false;
+            uint32_t cell = 0, st = 0;
+            Birth b;
+            b.born = false; b.tgt = 0; b.gene = 0; b.ce = 0.0f;
+            if (i < n0) {
+                cell = p.rp_cell[i];
+                st = p.rp_state[i];
+                const int d = (int)(st & 7u);
+                bool contested;
+                const bool win = contest(p, tf, cell & (p.W - 1), cell >> p.log2W, d, ReproKey(), contested);
+                const uint32_t t = __ldcg(tf + cell);
+                if (!contested) {
+                    tf[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
+                    b = commit_birth(p, tf, cell, t, d, false);
+                } else if (win) {
+                    defer = true;
+                } else {
+                    tf[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));  // stays ATTEMPTING_REPRODUCTION (:1203-1205)
+                    lost = true;
+                }
+            }
+            unsigned int* const cnt[3] = {&ctr->nb_n, &ctr->dw_n[1], &ctr->rt_n[1]};
+            const bool pred[3] = {b.born, defer, lost};
+            uint32_t slot[3];
+            block_append<3>(cnt, pred, slot);
+            store_birth(p, b, slot[0]);
+            if (defer) p.dw_idx[slot[1]] = i;
+            if (lost) {
+                p.rt_cell[slot[2]] = cell;
+                p.rt_state[slot[2]] = (uint8_t)st;
+            }
+        }
         grid_sync(ctr->barrier, gridDim.x);
+        const unsigned int ndw = __ldcg(&ctr->dw_n[1]);
+        for (unsigned int k0 = blockIdx.x * blockDim.x; k0 < ndw; k0 += stride) {
+            const unsigned int k = k0 + threadIdx.x;
+            Birth b;
+            b.born = false; b.tgt = 0; b.gene = 0; b.ce = 0.0f;
+            if (k < ndw) {
+                const unsigned int i = __ldcg(&p.dw_idx[k]);
+                const uint32_t cell = p.rp_cell[i];
+                const uint32_t t = __ldcg(tf + cell);
+                tf[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
+                b = commit_birth(p, tf, cell, t, (int)(p.rp_state[i] & 7u), false);
+            }
+            list_birth(p, b);
+        }
+        grid_sync(ctr->barrier, gridDim.x);
+        if (t0 == 0) ctr->rp_active[0] = __ldcg(&ctr->rt_n[1]);
     }
-    for (int round = (int)p.round0; round < (int)p.round1; ++round) {
+    const unsigned int n = __ldcg(&ctr->rt_n[1]);
+    for (int round = p.round0 > 1u ? (int)p.round0 : 1; round < (int)p.round1; ++round) {
         // overpopulated gate, evaluated after every round (:1616, :1621-1625); in slab mode the caller
-        // has summed olds and births over all slabs into glb[] before this launch (one round per launch)
+        // has summed olds and births over all slabs into glb[] before this launch
         const unsigned long long pop = p.glb ? __ldcg(&p.glb[0]) + __ldcg(&p.glb[1])
-                                             : __ldcg(&ctr->n_old) + __ldcg(&ctr->births);
-        if (pop > p.max_agents) break;
-        // ---- go forth
+                                             : __ldcg(&ctr->n_old) + (unsigned long long)__ldcg(&ctr->nb_n);
+        if (pop > p.max_agents || n == 0) break;
+        if (round == 1) {
+            // the newborns of round 1 are only on the newborn list so far: they must block their cells now
+            unsigned int nb1 = __ldcg(&ctr->nb_n);
+            if (nb1 > p.list_cap) nb1 = p.list_cap;
+            for (unsigned int i = t0; i < nb1; i += stride)
+                tf[p.nb_cell[i]] = (uint8_t)(TF_OCC | TF_NEWBORN | ((uint32_t)(p.nb_gene[i] >> 8) & TF_TRAIT));
+            if (t0 == 0) ctr->nb_flagged = 1u;
+            grid_sync(ctr->barrier, gridDim.x);
+        }
+        // ---- go forth (:1042-1134)
         for (unsigned int i = t0; i < n; i += stride) {
-            const uint32_t st = p.rp_state[i];
+            const uint32_t st = p.rt_state[i];
             if (!(st & 0x80u)) continue;
-            const uint32_t cell = p.rp_cell[i];
+            const uint32_t cell = p.rt_cell[i];
             const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
             uint32_t blocked = 0;
 #pragma unroll
             for (int d = 0; d < 8; ++d)
-                if (__ldcg(p.tfA + nb_local(p, x, y, d)) & TF_OCC) blocked |= 1u << d;
-            int l = (int)(st & 7u), seq = (int)((st >> 3) & 7u) + 1;  // state: 0x80 active | 0x40 fresh | (seq-1) << 3 | start
+                if (__ldcg(tf + nb_local(p, x, y, d)) & TF_OCC) blocked |= 1u << d;
+            int l = (int)(st & 7u), seq = (int)((st >> 3) & 7u) + 1;
             if (st & 0x40u) {  // fresh from round 1: it claimed direction l after probe_pos probes (:1110-1111)
                 const int s0 = (int)(rng(p, gcell_of(p, x, y), S_REPRO).y >> 29);
                 seq = probe_pos(s0, l);
@@ -271,95 +480,45 @@ __global__ void __launch_bounds__(1024) k_repro_retry(const __grid_constant__ Pa
             }
             const int dir = probe(blocked, l, seq);  // also covers reproduce_sequence >= 8 (:1067)
             if (dir < 0) {
-                p.rp_state[i] = 0x40u;  // REPRODUCTION_IMPOSSIBLE (:1104-1108); living cost still due
+                p.rt_state[i] = 0x40u;  // REPRODUCTION_IMPOSSIBLE (:1104-1108)
             } else {
-                const uint32_t t = __ldcg(p.tfA + cell);
-                p.tfA[cell] = (uint8_t)((t & (TF_OCC | TF_TRAIT)) | TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT));
-                p.rp_state[i] = (uint8_t)(0x80u | (uint32_t)((dir + 1) & 7) | ((uint32_t)(seq - 1) << 3));
-                p.rp_aux[i] = (uint8_t)dir;
+                const uint32_t t = __ldcg(tf + cell);
+                tf[cell] = (uint8_t)((t & (TF_OCC | TF_TRAIT)) | TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT));
+                p.rt_state[i] = (uint8_t)(0x80u | (uint32_t)((dir + 1) & 7) | ((uint32_t)(seq - 1) << 3));
+                p.rt_aux[i] = (uint8_t)dir;
             }
         }
         grid_sync(ctr->barrier, gridDim.x);
         // ---- multiply: contest
         for (unsigned int i = t0; i < n; i += stride) {
-            if (!(p.rp_state[i] & 0x80u)) continue;
-            const uint32_t cell = p.rp_cell[i];
-            const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
-            const int d = (int)(p.rp_aux[i] & 7u);
-            const uint32_t tx = (x + (uint32_t)DX(d)) & (p.W - 1);
-            const uint32_t ty = nb_row(p, y, DY(d));
-            bool win = true, have_key = false;
-            Key mine;
-            for (int j = 0; j < 8; ++j) {
-                if (j == 7 - d) continue;
-                const uint32_t tn = __ldcg(p.tfA + nb_local(p, tx, ty, j));
-                if (!claims_dir(tn, 7 - j)) continue;
-                if (!have_key) { mine = ReproKey()(p, gcell_of(p, x, y)); have_key = true; }
-                if (key_gt(ReproKey()(p, nb_gcell(p, tx, ty, j)), mine)) win = false;
-            }
-            p.rp_aux[i] = (uint8_t)((uint32_t)d | (win ? 0x80u : 0u));
+            if (!(p.rt_state[i] & 0x80u)) continue;
+            const uint32_t cell = p.rt_cell[i];
+            const int d = (int)(p.rt_aux[i] & 7u);
+            bool contested;
+            const bool win = contest(p, tf, cell & (p.W - 1), cell >> p.log2W, d, ReproKey(), contested);
+            p.rt_aux[i] = (uint8_t)((uint32_t)d | (win ? 0x80u : 0u));
         }
         grid_sync(ctr->barrier, gridDim.x);
         // ---- multiply: apply
-        unsigned int still = 0, born = 0;
-        for (unsigned int i = t0; i < n; i += stride) {
-            if (!(p.rp_state[i] & 0x80u)) continue;
-            const uint32_t cell = p.rp_cell[i];
-            const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
-            const uint32_t aux = p.rp_aux[i];
-            const uint32_t t = __ldcg(p.tfA + cell);
-            p.tfA[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
-            if (aux & 0x80u) {
-                const uint32_t tgt = nb_local(p, x, y, (int)(aux & 7u));
-                const float e1 = __ldcg(p.E1 + cell);  // the energy it entered reproduction with
-                const float pe = __fsub_rn(e1, p.reproduce_cost);
-                float ce;
-                uint32_t cs;
-                make_child(p, gcell_of(p, x, y), __ldcg(p.strat + cell), t & TF_TRAIT, pe, ce, cs);
-                p.tfA[tgt] = (uint8_t)(TF_OCC | TF_NEWBORN | (t & TF_TRAIT));  // blocks its cell in later rounds
-                if (row_owned(p, tgt >> p.log2W)) {  // a child in the ghost zone belongs to the neighbour slab
-                    const unsigned int slot = atomicAdd(&ctr->nb_n, 1u);
-                    if (slot < p.list_cap) {
-                        p.nb_cell[slot] = tgt;
-                        p.nb_e[slot] = ce;
-                        p.nb_gene[slot] = (uint16_t)(cs | ((t & TF_TRAIT) << 8));
-                    } else atomicExch(&ctr->overflow, 1u);
-                    ++born;
-                }
-                // The parent.  k_repro_commit already charged it the living cost if it survives that without
-                // reproducing ("eager"); now the reproduction cost comes first (:1211-1213, then :1357-1368).
-                float chk = e1;
-                if (!punish(p, chk)) {
-                    p.E0[cell] = pe;  // deferred loser: k_finalize charges the living cost (dl list)
+        unsigned int still = 0;
+        for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
+            const unsigned int i = i0 + threadIdx.x;
+            Birth b;
+            b.born = false; b.tgt = 0; b.gene = 0; b.ce = 0.0f;
+            if (i < n && (p.rt_state[i] & 0x80u)) {
+                const uint32_t cell = p.rt_cell[i];
+                const uint32_t aux = p.rt_aux[i];
+                const uint32_t t = __ldcg(tf + cell);
+                tf[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
+                if (aux & 0x80u) {
+                    b = commit_birth(p, tf, cell, t, (int)(aux & 7u), true);  // blocks its cell in later rounds
+                    p.rt_state[i] = 0x40u;  // REPRODUCTION_COMPLETE: one child per step (B-6)
                 } else {
-                    float e = pe;
-                    const bool own = row_owned(p, y);
-                    if (punish(p, e)) {
-                        p.E0[cell] = e;
-                        if (own && e <= p.risk_thr && !(chk <= p.risk_thr)) {  // not yet on the next at-risk list
-                            const unsigned int rs = atomicAdd(&ctr->risk_next_n, 1u);
-                            if (rs < p.list_cap) p.risk_next[rs] = cell;
-                            else atomicExch(&ctr->overflow, 1u);
-                        }
-                    } else {  // it dies after all: same bookkeeping as a death in k_repro_commit
-                        p.E0[cell] = 0.0f;
-                        p.tfA[cell] = (uint8_t)(TF_OCC | TF_DYING);
-                        if (own) {
-                            const unsigned int ds = atomicAdd(&ctr->dead_n, 1u);
-                            if (ds < p.list_cap) p.dead_cell[ds] = cell;
-                            else atomicExch(&ctr->overflow, 1u);
-                            atomicAdd(&ctr->living_deaths, 1ull);
-                            if (p.want_counts)  // it was counted alive
-                                atomicAdd(&ctr->bins[count_bin(__ldcg(p.strat + cell), t & TF_TRAIT)], ~0ull);
-                        }
-                    }
+                    ++still;
                 }
-                p.rp_state[i] = 0x40u;  // REPRODUCTION_COMPLETE
-            } else {
-                ++still;
             }
+            list_birth(p, b);
         }
-        if (born) atomicAdd(&ctr->births, (unsigned long long)born);
         if (still) atomicAdd(&ctr->rp_active[round], still);
         grid_sync(ctr->barrier, gridDim.x);
         if (__ldcg(&ctr->rp_active[round]) == 0u) break;
@@ -390,7 +549,7 @@ struct CullPlan {
 };
 __device__ __forceinline__ CullPlan cull_plan(const Params& p) {
     const unsigned long long n_old = p.glb ? __ldcg(&p.glb[0]) : p.ctr->n_old;
-    const unsigned long long births = p.glb ? __ldcg(&p.glb[1]) : p.ctr->births;
+    const unsigned long long births = p.glb ? __ldcg(&p.glb[1]) : (unsigned long long)p.ctr->nb_n;
     CullPlan c;
     c.cull = n_old + births > p.max_agents;
     c.keep = 0;
@@ -556,7 +715,7 @@ __device__ __forceinline__ unsigned long long fin_select(unsigned int n, unsigne
     return *s_prefix;
 }
 
-// newborns: cull or admit; deferred living cost of the listed claim losers; dying agents leave; all OWNED rows only
+// newborns: cull or admit (OWNED rows only)
 __device__ __forceinline__ void fin_apply(const Params& p, unsigned int nb, bool cull,
                                           unsigned long long keep, unsigned long long tau) {
     Counters* ctr = p.ctr;
@@ -593,54 +752,6 @@ __device__ __forceinline__ void fin_apply(const Params& p, unsigned int nb, bool
     }
     for (int o = 16; o > 0; o >>= 1) n_culled += __shfl_down_sync(0xFFFFFFFFu, n_culled, o);  // one atomic per warp
     if ((threadIdx.x & 31) == 0 && n_culled) atomicAdd(&ctr->culled, (unsigned long long)n_culled);
-    // ---- deferred living cost (:1357-1368) of the few round-1 losers it would kill (k_repro_commit lists them;
-    // every other loser has paid already)
-    unsigned int n_dead = 0;
-    unsigned int ndl = __ldcg(&ctr->dl_n);
-    if (ndl > p.list_cap) ndl = p.list_cap;
-    for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < ndl; i0 += 4 * stride) {
-        uint32_t cell[4];
-        float ev[4];
-        bool mine[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const unsigned int i = i0 + u * stride + threadIdx.x;
-            cell[u] = i < ndl ? p.dl_cell[i] : 0u;
-            mine[u] = i < ndl && row_owned(p, cell[u] >> p.log2W);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) ev[u] = mine[u] ? __ldcg(p.E0 + cell[u]) : 1.0f;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            bool at_risk = false;
-            if (mine[u]) {
-                // no retry round ran (gate closed): the flag byte is still canonical
-                float e = ev[u];
-                const bool need_t = flagged || p.want_counts;
-                const uint32_t t = need_t ? __ldcg(p.tfA + cell[u]) : 0u;
-                if (punish(p, e)) {
-                    p.E0[cell[u]] = e;
-                    if (flagged) p.tfA[cell[u]] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
-                    at_risk = e <= p.risk_thr;
-                    if (p.want_counts) atomicAdd(&ctr->bins[count_bin(__ldcg(p.strat + cell[u]), t & TF_TRAIT)], 1ull);
-                } else {
-                    p.E0[cell[u]] = 0.0f;
-                    p.tfA[cell[u]] = 0;
-                    ++n_dead;
-                }
-            }
-            const uint32_t slot = warp_append(&ctr->risk_next_n, at_risk);
-            if (at_risk) {
-                if (slot < p.list_cap) p.risk_next[slot] = cell[u];
-                else atomicExch(&ctr->overflow, 1u);
-            }
-        }
-    }
-    if (n_dead) atomicAdd(&ctr->living_deaths, (unsigned long long)n_dead);
-    // ---- the agents the final sweep killed finally leave their cells
-    unsigned int ndead = ctr->dead_n;
-    if (ndead > p.list_cap) ndead = p.list_cap;
-    for (unsigned int i = t0; i < ndead; i += stride) p.tfA[p.dead_cell[i]] = 0;
 }
 
 // bookkeeping by one thread after everything else of the step is done
@@ -648,7 +759,7 @@ __device__ __forceinline__ void fin_bookkeeping(const Params& p) {
     Counters* ctr = p.ctr;
     const unsigned long long culled = __ldcg(&ctr->culled);
     const unsigned long long ld = __ldcg(&ctr->living_deaths);
-    const unsigned long long b = __ldcg(&ctr->births);
+    const unsigned long long b = __ldcg(&ctr->nb_n);  // births = the newborn list
     ctr->n_agents = __ldcg(&ctr->n_old) + b - culled - ld;  // this slab's agents
     unsigned int rn = __ldcg(&ctr->risk_next_n);
     ctr->risk_n = rn > p.list_cap ? p.list_cap : rn;
@@ -679,7 +790,8 @@ __device__ __forceinline__ void fin_bookkeeping(const Params& p) {
     }
 }
 
-__global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Params p) {
+template <int BS>
+__global__ void __launch_bounds__(BS) k_finalize(const __grid_constant__ Params p) {
     Counters* ctr = p.ctr;
     __shared__ unsigned int s_hist[2048];
     __shared__ unsigned long long s_prefix;
@@ -689,7 +801,7 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Param
     unsigned int nb = ctr->nb_n;
     if (nb > p.list_cap) nb = p.list_cap;
     unsigned int* g_hist = &ctr->hist[0][0];  // 2048 words
-    unsigned long long* cand = reinterpret_cast<unsigned long long*>(p.risk_roll);  // scratch: candidate keys
+    unsigned long long* cand = p.cand;
     const unsigned int cand_cap = p.list_cap / 2u;
     const CullPlan plan = cull_plan(p);
     unsigned long long tau = 0;                // survive iff key >= tau
@@ -724,7 +836,8 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Param
 }
 
 // ---- row slabs, part 1: this slab's histogram into the bound exchange buffer (summed by the caller)
-__global__ void __launch_bounds__(1024) k_fin_hist(const __grid_constant__ Params p) {
+template <int BS>
+__global__ void __launch_bounds__(BS) k_fin_hist(const __grid_constant__ Params p) {
     __shared__ unsigned int s_hist[2048];
     Counters* ctr = p.ctr;
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -738,7 +851,8 @@ __global__ void __launch_bounds__(1024) k_fin_hist(const __grid_constant__ Param
 }
 
 // ---- part 2 (after the histogram was summed): this slab's candidate keys into cand_out
-__global__ void __launch_bounds__(1024) k_fin_cand(const __grid_constant__ Params p) {
+template <int BS>
+__global__ void __launch_bounds__(BS) k_fin_cand(const __grid_constant__ Params p) {
     __shared__ unsigned int s_hist[2048];
     __shared__ unsigned long long s_krem;
     __shared__ unsigned int s_digit;
@@ -770,7 +884,8 @@ __global__ void __launch_bounds__(1024) k_fin_cand(const __grid_constant__ Param
 }
 
 // ---- part 3 (after all slabs' candidates were gathered): threshold, apply, bookkeeping
-__global__ void __launch_bounds__(1024) k_fin_apply(const __grid_constant__ Params p) {
+template <int BS>
+__global__ void __launch_bounds__(BS) k_fin_apply(const __grid_constant__ Params p) {
     __shared__ unsigned int s_hist[2048];
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned long long s_krem;
@@ -818,8 +933,8 @@ __global__ void __launch_bounds__(1024) k_fin_apply(const __grid_constant__ Para
 __global__ void k_publish_gate(const __grid_constant__ Params p, int round) {
     if (threadIdx.x == 0) {
         p.glb[0] = p.ctr->n_old;
-        p.glb[1] = p.ctr->births;
-        p.glb[2] = round == 0 ? p.ctr->rp_n : p.ctr->rp_active[round];
+        p.glb[1] = p.ctr->nb_n;  // births
+        p.glb[2] = p.ctr->rp_active[round];
     }
 }
 

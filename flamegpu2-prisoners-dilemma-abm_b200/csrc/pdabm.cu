@@ -107,9 +107,10 @@ int alloc_lists(pd_sim* s, uint64_t n_agents_hint) {
         if (n_agents_hint + 1024 <= s->P.list_cap || s->P.list_cap == s->cells) return PD_OK;
         // grow: free and reallocate
         drop_graphs(s);
-        cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.risk_roll);
-        cudaFree(s->P.mv_cell); cudaFree(s->P.mv_state); cudaFree(s->P.mv_aux);
-        cudaFree(s->P.rp_cell); cudaFree(s->P.rp_state); cudaFree(s->P.rp_aux);
+        cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.cand);
+        cudaFree(s->P.mv_cell); cudaFree(s->P.mv_state);
+        cudaFree(s->P.rp_cell); cudaFree(s->P.rp_state);
+        cudaFree(s->P.rt_cell); cudaFree(s->P.rt_state); cudaFree(s->P.rt_aux);
         cudaFree(s->P.nb_cell); cudaFree(s->P.nb_e); cudaFree(s->P.nb_gene);
         s->lists_allocated = false;
     }
@@ -124,15 +125,15 @@ int alloc_lists(pd_sim* s, uint64_t n_agents_hint) {
     CK(cudaMalloc(&s->risk[0], cap * 4));
     CK(cudaMalloc(&s->risk[1], cap * 4));
     CK(cudaMalloc(&s->P.risk_e, cap * 4));
-    s->P.dl_cell = reinterpret_cast<uint32_t*>(s->P.risk_e);
-    CK(cudaMalloc(&s->P.risk_roll, cap * 4));
+    CK(cudaMalloc(&s->P.cand, (cap / 2 + 1) * 8));
     CK(cudaMalloc(&s->P.mv_cell, cap * 4));
-    s->P.dead_cell = s->P.mv_cell;
+    s->P.dw_idx = reinterpret_cast<uint32_t*>(s->P.risk_e);
     CK(cudaMalloc(&s->P.mv_state, cap));
-    CK(cudaMalloc(&s->P.mv_aux, cap));
     CK(cudaMalloc(&s->P.rp_cell, cap * 4));
     CK(cudaMalloc(&s->P.rp_state, cap));
-    CK(cudaMalloc(&s->P.rp_aux, cap));
+    CK(cudaMalloc(&s->P.rt_cell, cap * 4));
+    CK(cudaMalloc(&s->P.rt_state, cap));
+    CK(cudaMalloc(&s->P.rt_aux, cap));
     CK(cudaMalloc(&s->P.nb_cell, cap * 4));
     CK(cudaMalloc(&s->P.nb_e, cap * 4));
     CK(cudaMalloc(&s->P.nb_gene, cap * 2));
@@ -144,7 +145,7 @@ int alloc_lists(pd_sim* s, uint64_t n_agents_hint) {
 // with as many 512-thread CTAs as the kernel's registers allow (these kernels are latency-bound list
 // walks, so more resident warps = more loads in flight).
 template <typename K>
-int launch_sparse(pd_sim* s, K kernel, cudaStream_t st) {
+int launch_sparse_k(pd_sim* s, K kernel, cudaStream_t st) {
     void* args[] = {(void*)&s->P};
     if (s->sparse_ctas == 1) {
         CK(cudaLaunchKernel((const void*)kernel, dim3(1), dim3(s->sparse_threads), args, 0, st));
@@ -165,6 +166,10 @@ int launch_sparse(pd_sim* s, K kernel, cudaStream_t st) {
     }
     return PD_OK;
 }
+
+// one 1024-thread CTA, or a cooperative launch of 512-thread CTAs (a second instantiation: 128 registers each)
+#define launch_sparse(s, kernel, st) \
+    ((s)->sparse_threads == 1024 ? launch_sparse_k(s, kernel<1024>, st) : launch_sparse_k(s, kernel<512>, st))
 
 // per-kernel timing: a (start, end) CUDA event pair around one or more launches, tagged with a kernel slot
 int prof_begin(pd_sim* s, int slot, cudaStream_t st) {
@@ -200,7 +205,14 @@ int push_step(pd_sim* s, cudaStream_t st) {
     return PD_OK;
 }
 
-// the 9 launches of one model step, in the order of the reference's main layers (model.py:2140-2163)
+int launch_punish(pd_sim* s, cudaStream_t st) {
+    const size_t owned = (size_t)(s->P.own_y1 - s->P.own_y0) * s->P.W;
+    k_punish<<<(unsigned int)((owned + PUNISH_CELLS - 1) / PUNISH_CELLS), NT, 0, st>>>(s->P);
+    CK(cudaGetLastError());
+    return PD_OK;
+}
+
+// the 8 launches of one model step, in the order of the reference's main layers (model.py:2140-2163)
 int launch_step(pd_sim* s, cudaStream_t st) {
     Params& P = s->P;
     int rc = PD_OK;
@@ -208,15 +220,12 @@ int launch_step(pd_sim* s, cudaStream_t st) {
     PROF(1, { if ((rc = launch_sparse(s, k_risk_resolve, st))) return rc; });
     PROF(2, { if (s->big_tiles) k_play_travel<128, 16><<<s->grid, NT, 0, st>>>(P);
               else k_play_travel<16, 16><<<s->grid, NT, 0, st>>>(P); });
-    PROF(3, { if (s->big_tiles) k_move_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
-              else k_move_commit<16, 16><<<s->grid, NT, 0, st>>>(P); });
-    PROF(4, { if ((rc = launch_sparse(s, k_move_retry, st))) return rc; });
-    PROF(5, { if (s->big_tiles) k_repro_claim<128, 16><<<s->grid, NT, 0, st>>>(P);
+    PROF(3, { if ((rc = launch_sparse(s, k_move_rounds, st))) return rc; });
+    PROF(4, { if (s->big_tiles) k_repro_claim<128, 16><<<s->grid, NT, 0, st>>>(P);
               else k_repro_claim<16, 16><<<s->grid, NT, 0, st>>>(P); });
-    PROF(6, { if (s->big_tiles) k_repro_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
-              else k_repro_commit<16, 16><<<s->grid, NT, 0, st>>>(P); });
-    PROF(7, { if ((rc = launch_sparse(s, k_repro_retry, st))) return rc; });
-    PROF(8, { if ((rc = launch_sparse(s, k_finalize, st))) return rc; });
+    PROF(5, { if ((rc = launch_sparse(s, k_repro_rounds, st))) return rc; });
+    PROF(6, { if ((rc = launch_punish(s, st))) return rc; });
+    PROF(7, { if ((rc = launch_sparse(s, k_finalize, st))) return rc; });
     return PD_OK;
 }
 
@@ -337,7 +346,7 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     P.row0 = (cfg->row0 + HW - cfg->ghost_rows) & (HW - 1);  // global row of local row 0
     P.wrap_y = slab ? 0u : 1u;
     P.own_y0 = cfg->ghost_rows; P.own_y1 = cfg->ghost_rows + cfg->rows;
-    P.round0 = 1; P.round1 = 8; P.world = 1; P.cand_cap = 0;
+    P.round0 = 0; P.round1 = 8; P.world = 1; P.cand_cap = 0;
     P.select_cap = cfg->debug_select_cap ? cfg->debug_select_cap : 0xFFFFFFFFu;
     P.step_log = nullptr; P.log_cap = 0;
     P.glb = nullptr; P.ghist = nullptr; P.cand_out = nullptr; P.cand_all = nullptr;
@@ -384,6 +393,13 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     P.sparse_ctas = (uint32_t)s->sparse_ctas;
     s->graphs = cfg->use_graphs > 0 || (cfg->use_graphs == 0 && !slab && s->cells <= ((size_t)1 << 22));
     if (slab) s->graphs = false;  // a slab is stepped in parts with host decisions in between
+    {
+        float h_lut[256], *d_lut = nullptr;
+        for (uint32_t i = 0; i < 256; ++i) h_lut[i] = lut_entry(P.pay, i);
+        CK(cudaMalloc(&d_lut, sizeof h_lut));
+        CK(cudaMemcpy(d_lut, h_lut, sizeof h_lut, cudaMemcpyHostToDevice));
+        P.lut = d_lut;
+    }
     CK(cudaMalloc(&P.E1, s->cells * sizeof(float)));
     CK(cudaMalloc(&P.tfB, s->cells));
     CK(cudaMalloc(&P.ctr, sizeof(Counters)));
@@ -400,11 +416,12 @@ int pd_destroy(pd_sim* s) {
     // (no cudaDeviceSynchronize: it is an error while another thread captures a graph; cudaFree below waits)
     drop_graphs(s);
     if (s->P.step_log) cudaFree(s->P.step_log);
-    cudaFree(s->P.E1); cudaFree(s->P.tfB); cudaFree(s->P.ctr);
+    cudaFree(s->P.E1); cudaFree(s->P.tfB); cudaFree(s->P.ctr); cudaFree(const_cast<float*>(s->P.lut));
     if (s->lists_allocated) {
-        cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.risk_roll);
-        cudaFree(s->P.mv_cell); cudaFree(s->P.mv_state); cudaFree(s->P.mv_aux);
-        cudaFree(s->P.rp_cell); cudaFree(s->P.rp_state); cudaFree(s->P.rp_aux);
+        cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.cand);
+        cudaFree(s->P.mv_cell); cudaFree(s->P.mv_state);
+        cudaFree(s->P.rp_cell); cudaFree(s->P.rp_state);
+        cudaFree(s->P.rt_cell); cudaFree(s->P.rt_state); cudaFree(s->P.rt_aux);
         cudaFree(s->P.nb_cell); cudaFree(s->P.nb_e); cudaFree(s->P.nb_gene);
     }
     cudaFreeHost(s->h);
@@ -589,31 +606,31 @@ int pd_step_part(pd_sim* s, int part, int arg, void* stream, int want_counts) {
         PROF(1, { if ((rc = launch_sparse(s, k_risk_resolve, st))) return rc; });
         PROF(2, { if (s->big_tiles) k_play_travel<128, 16><<<s->grid, NT, 0, st>>>(P);
                   else k_play_travel<16, 16><<<s->grid, NT, 0, st>>>(P); });
-        PROF(3, { if (s->big_tiles) k_move_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
-                  else k_move_commit<16, 16><<<s->grid, NT, 0, st>>>(P); });
-        PROF(4, { if ((rc = launch_sparse(s, k_move_retry, st))) return rc; });
-        PROF(5, { if (s->big_tiles) k_repro_claim<128, 16><<<s->grid, NT, 0, st>>>(P);
+        PROF(3, { if ((rc = launch_sparse(s, k_move_rounds, st))) return rc; });
+        PROF(4, { if (s->big_tiles) k_repro_claim<128, 16><<<s->grid, NT, 0, st>>>(P);
                   else k_repro_claim<16, 16><<<s->grid, NT, 0, st>>>(P); });
-        PROF(6, { if (s->big_tiles) k_repro_commit<128, 16><<<s->grid, NT, 0, st>>>(P);
-                  else k_repro_commit<16, 16><<<s->grid, NT, 0, st>>>(P); });
+        P.round0 = 0; P.round1 = 1;  // round 1 needs no gate (:1682); the caller sums the population before any other
+        PROF(5, { if ((rc = launch_sparse(s, k_repro_rounds, st))) return rc; });
+        P.round0 = 0; P.round1 = 8;
         k_publish_gate<<<1, 32, 0, st>>>(P, 0);
         break;
     }
     case PD_PART_RETRY:
         if (arg < 1 || arg > 7) return fail(PD_ERR_INVALID, "retry round %d out of range 1..7", arg);
         P.round0 = (uint32_t)arg; P.round1 = (uint32_t)arg + 1;
-        PROF(7, { if ((rc = launch_sparse(s, k_repro_retry, st))) return rc; });
+        PROF(5, { if ((rc = launch_sparse(s, k_repro_rounds, st))) return rc; });
         k_publish_gate<<<1, 32, 0, st>>>(P, arg);
-        P.round0 = 1; P.round1 = 8;
+        P.round0 = 0; P.round1 = 8;
         break;
-    case PD_PART_HIST:
-        PROF(8, { if ((rc = launch_sparse(s, k_fin_hist, st))) return rc; });
+    case PD_PART_HIST:  // the reproduction rounds are over: cost of living, then this slab's cull histogram
+        PROF(6, { if ((rc = launch_punish(s, st))) return rc; });
+        PROF(7, { if ((rc = launch_sparse(s, k_fin_hist, st))) return rc; });
         break;
     case PD_PART_CAND:
-        PROF(8, { if ((rc = launch_sparse(s, k_fin_cand, st))) return rc; });
+        PROF(7, { if ((rc = launch_sparse(s, k_fin_cand, st))) return rc; });
         break;
     case PD_PART_APPLY:
-        PROF(8, { if ((rc = launch_sparse(s, k_fin_apply, st))) return rc; });
+        PROF(7, { if ((rc = launch_sparse(s, k_fin_apply, st))) return rc; });
         s->risk_cur ^= 1;
         s->step += 1;
         break;

@@ -78,7 +78,7 @@ typedef struct pd_config {
     uint32_t world_height;          /* 0 = width (square, like the reference); else a power of two: the world is
                                        width x world_height cells (used for weak-scaling series of row slabs) */
     int32_t use_graphs;             /* 0 = auto (whole worlds <= 2^22 cells), 1 = always, -1 = never: replay one
-                                       captured CUDA graph per step instead of 9 launches.  Only on explicit
+                                       captured CUDA graph per step instead of 8 launches.  Only on explicit
                                        (capturable) streams and while per-kernel profiling is off. */
     uint32_t debug_select_cap;      /* 0 = default; tests: cap of the cull select's shared-memory stage, to force its
                                        global-memory fallback */
@@ -134,12 +134,12 @@ int pd_read_stats(pd_sim* sim, pd_step_stats* out, void* stream);
  * rows + 2*ghost_rows rows: ghost_rows rows of the upper neighbour slab, the owned rows, ghost_rows
  * rows of the lower neighbour slab (periodic ring).  One model step is
  *     caller: refresh the ghost rows of energy/strat/tf from the neighbour slabs (NVLink copy)
- *     PD_PART_PRE            all dense sweeps + local retry rounds; publishes glb[0..2]
+ *     PD_PART_PRE            play, all travel rounds, reproduction claims and round 1; publishes glb[0..2]
  *     caller: sum glb over the slabs
- *     PD_PART_RETRY r=1..7   one reproduction retry round, gated by the global population; caller sums glb
- *     PD_PART_HIST           cull histogram into ghist;            caller sums ghist
+ *     PD_PART_RETRY r=1..7   one further reproduction round, gated by the global population; caller sums glb
+ *     PD_PART_HIST           cost of living (k_punish), then the cull histogram into ghist;  caller sums ghist
  *     PD_PART_CAND           this slab's cull candidates into cand_out;  caller gathers all blocks into cand_all
- *     PD_PART_APPLY          cull, deferred living cost, bookkeeping; publishes glb[3..19] (agents, 16 counts)
+ *     PD_PART_APPLY          cull, bookkeeping; publishes glb[3..19] (agents, 16 counts)
  * The ghost zone is wide enough that every other phase needs no communication (DESIGN.md "Multi-GPU");
  * results are bit-identical to the whole-world run because all draws are keyed by the global cell. */
 #define PD_PART_PRE 0
@@ -175,7 +175,7 @@ int pd_read_step_log(pd_sim* sim, uint64_t* rows, uint32_t max_rows, uint32_t* n
 /* Per-kernel device timing: with profiling on, pd_step records a CUDA event between every
  * two kernel launches; pd_read_profile synchronises `stream` and returns the accumulated
  * milliseconds per kernel, in launch order: begin_step, risk_resolve, play_travel,
- * move_commit, move_retry, repro_claim, repro_commit, repro_retry, finalize. */
+ * move_rounds, repro_claim, repro_rounds, punish, finalize (slot 8 is unused). */
 #define PDABM_NUM_KERNELS 9
 int pd_set_profile(pd_sim* sim, int on);
 int pd_read_profile(pd_sim* sim, double kernel_ms[PDABM_NUM_KERNELS], uint32_t* steps, void* stream);
@@ -185,7 +185,7 @@ int pd_get_step(pd_sim* sim, uint32_t* step);
 int pd_set_step(pd_sim* sim, uint32_t step);
 
 /* Number of model steps this handle ran by replaying a captured CUDA graph (pd_config.use_graphs)
- * rather than by launching the 9 kernels one by one. */
+ * rather than by launching the 8 kernels one by one. */
 int pd_graph_replays(pd_sim* sim, uint64_t* steps);
 
 /* HOST-buffer entry point (what a host-side caller without device buffers binds):
