@@ -50,11 +50,12 @@ WORKLOADS = {
 }
 # algorithmic bytes per cell per launch of each dense sweep (DESIGN.md "Kernels"):
 #   play_travel : read tfA 1 + strat 1 + E0 4, write tfB 1 + E1 4
-#   repro_claim : read tfB 1 + E1 4, write tfA 1
+#   move_commit : read tfB 1, write tfA 1; plus the movers' payload (~4 % of the cells move: 5 B gathered + 5 B
+#                 scattered each, sector-granular -- ncu's traffic is the honest figure for this kernel)
+#   repro_claim : read tfA 1 + E1 4, write tfB 1
+#   repro_commit: read tfB 1, write tfA 1; plus parents' energy / strategies gathered for ~3.5 % of the cells
 #   punish      : read tfA 1 + E1 4, write tfA 1 + E0 4   (+1 strat when counts are wanted)
-# (the sparse kernels -- travel / reproduction rounds, at-risk agents, cull -- move list entries and the sectors
-#  around ~5 % of the cells; their traffic is reported from ncu, not from a per-cell figure)
-ALG_BYTES = {"play_travel": 11, "repro_claim": 6, "punish": 10}
+ALG_BYTES = {"play_travel": 11, "move_commit": 2, "repro_claim": 6, "repro_commit": 2, "punish": 10}
 
 
 def measured_peaks():
@@ -418,9 +419,9 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_ms": legs[0], "step_ms": legs[1], "d2h_ms": legs[2],
                 "h2d_gbs_per_gpu": h2d / (legs[0] * 1e-3) / 1e9 if legs[0] > 0 else None,
                 "d2h_gbs_per_gpu": d2h / (legs[2] * 1e-3) / 1e9 if legs[2] > 0 else None},
-        # per step: 8 kernels (whole world; replayed as one CUDA graph on small worlds), or 12 + 2 per
+        # per step: 10 kernels (whole world; replayed as one CUDA graph on small worlds), or 14 + 2 per
         # reproduction retry round that actually ran (row slab, this rank)
-        "gpu_launches": (12 * args.steps + 2 * retry_rounds) if slabs else 8 * args.steps,
+        "gpu_launches": (14 * args.steps + 2 * retry_rounds) if slabs else 10 * args.steps,
         "graph_replays": replays,
         "clocks": clocks,
         "init_and_presteps_s": init_s,
@@ -587,7 +588,7 @@ def run_config4(args, rank, world, local_rank):
                                        f"{per_gpu} concurrent runs per GPU, one per CUDA stream, counts every step",
                            "runs": per_gpu * world, "presteps": args.presteps,
                            "l2": "each world's state fits in L2: no HBM roofline claim"},
-                "gpu_launches": 8 * args.steps * per_gpu * world}
+                "gpu_launches": 10 * args.steps * per_gpu * world}
         print(json.dumps(line), flush=True)
     for s in sims:
         s.close()

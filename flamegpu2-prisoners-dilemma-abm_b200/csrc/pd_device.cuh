@@ -13,13 +13,16 @@ namespace pd {
 // ---- tf plane bits ---------------------------------------------------------------------
 // Canonical (between steps): OCC | trait.  Transient meanings per phase:
 //   tfA during play      : bits 3-6 = D code of an at-risk agent (0 none, c+1 = dies in sub-step c)
-//   tfB during travel    : GHOST = cell was occupied at step start but is empty now (still
+//   tfB/tfA during travel: GHOST = cell was occupied at step start but is empty now (still
 //                          blocks movers, quirk B-13), CLAIM|DIR = mover claiming direction DIR
-//   tfA during reproduce : CLAIM|DIR = parent claiming direction DIR; NEWBORN (same bit as GHOST) = child of
-//                          this step (only written when retry rounds must see its cell), until the cull has run
+//   tfB/tfA during reproduce: CLAIM|DIR = parent claiming direction DIR; PARENT = reproduced; NEWBORN (same bit as
+//                          GHOST) = child of this step (only written when retry rounds must see its cell), until
+//                          the cull has run
 constexpr uint32_t TF_TRAIT = 0x03u;
 constexpr uint32_t TF_GHOST = 0x04u;
 constexpr uint32_t TF_NEWBORN = 0x04u;
+constexpr uint32_t TF_PARENT = 0x08u;  // tfA after a claim was won: reproduced this step (k_punish charges the cost);
+                                       // shares a bit with DIR, so it only means PARENT when CLAIM is clear
 constexpr uint32_t TF_DIR_SHIFT = 3u;
 constexpr uint32_t TF_DIR = 0x38u;
 constexpr uint32_t TF_CLAIM = 0x40u;
@@ -61,7 +64,7 @@ static_assert(DY(0) == -1 && DY(1) == 0 && DY(2) == 1 && DY(3) == -1 && DY(4) ==
 struct Counters {
     // zeroed at the start of every step (k_begin_step)
     unsigned int mv_n, rp_n, nb_n, risk_next_n, cand_n, nb_flagged, dep_n, pad1_;
-    unsigned int rt_n[2], dw_n[2];  // retry list / deferred winners: [0] travel, [1] reproduction
+    unsigned int rt_n[2], pad4_[2];  // retry list: [0] travel, [1] reproduction
     unsigned int mv_active[8], rp_active[8];
     unsigned long long n_old, culled, living_deaths, pad2_;
     unsigned long long st_play_deaths, st_movers, st_moved, st_travel_deaths;
@@ -119,10 +122,11 @@ struct Params {
     // sparse lists
     uint32_t* risk_cur; uint32_t* risk_next; float* risk_e;
     unsigned long long* cand;  // cull select: the threshold bin's candidate keys (list_cap / 2 of them)
-    uint32_t* mv_cell; uint8_t* mv_state;  // travel claimants of the dense sweep (round 1)
-    uint32_t* rp_cell; uint8_t* rp_state;  // reproduction claimants of the dense sweep (round 1)
+    // round 1 claims, one contiguous segment per tile (entry = tile-local cell | direction << 16) and the
+    // (first entry, count) of every tile's segment
+    uint32_t* mv_claim; uint32_t* rp_claim;
+    uint2* seg_mv; uint2* seg_rp;
     uint32_t* rt_cell; uint8_t* rt_state; uint8_t* rt_aux;  // the losers of round 1: rounds 2..8 (travel, then reproduction)
-    uint32_t* dw_idx;  // round 1's contested winners, committed after a barrier; aliases risk_e (free after k_risk_resolve)
     uint32_t* nb_cell;
     float* nb_e; uint16_t* nb_gene;  // the newborn's energy and strategies | trait << 8 (it is written into the
                                      // planes only if it survives the cull, or when retry rounds must see it)

@@ -4,14 +4,16 @@
 //   k_begin_step    zero the per-step counters
 //   k_risk_resolve  sparse: exact death sub-step of the few agents that CAN die in play
 //   k_play_travel   dense sweep 1: roll + roles + 8 play sub-steps + mover decision + travel claim
-//   k_move_rounds   sparse: the (up to) 8 rounds of move_response / move_request over the travel list
-//   k_repro_claim   dense sweep 2: eligibility + reproduction claim
-//   k_repro_rounds  sparse: the (up to) 8 rounds of god_multiply / god_go_forth (gated by the carrying capacity)
-//   k_punish        dense sweep 3: cost of living, death, counts, next step's at-risk list
+//   k_move_commit   dense sweep 2: resolve travel claims (round 1) from the tile's claim list, pull movers in
+//   k_move_retry    sparse: travel rounds 2..8 for the claim losers
+//   k_repro_claim   dense sweep 3: eligibility + reproduction claim
+//   k_repro_commit  dense sweep 4: resolve claims (round 1) from the tile's claim list, births
+//   k_repro_retry   sparse: reproduction rounds 2..8 (gated by the carrying capacity)
+//   k_punish        dense sweep 5: reproduction cost, cost of living, death, counts, next step's at-risk list
+//                   (cell-local, streaming, in place)
 //   k_finalize      sparse: newborn cull (exact k-th selection), the surviving newborns enter the planes
-// The dense sweeps are pure GATHERS (a cell reads its neighbourhood and writes only itself); the sparse
-// kernels work in place on the flag plane, phases separated by grid barriers: there are no claim planes,
-// no atomics on cells and no clears (DESIGN.md "Kernels").
+// Every dense sweep is a pure GATHER: a cell reads its neighbourhood and writes only itself, so there are no
+// claim planes, no atomics on cells and no clears (DESIGN.md "Kernels").
 // The persistent sparse kernels are templated on their block size: one 1024-thread CTA on small worlds,
 // 512-thread CTAs (128 registers available) in the cooperative multi-CTA launch.
 #pragma once
@@ -138,52 +140,18 @@ __global__ void __launch_bounds__(BS) k_risk_resolve(const __grid_constant__ Par
 }
 
 // ------------------------------------------------------------------------------------------
-// Claim resolution over a list (move_response :881-960, god_multiply :1170-1205), in place on a flag plane.
-// A claimant reads the claim flags of the 8 cells around its target; `rivals` = neighbours of the target
-// (other than me) that claim it too.  Highest (priority, cell) wins; only contested targets need priorities.
-//
-// Round 1 visits every claimant of the dense sweep ONCE: an uncontested claimant (most of them) commits on
-// the spot -- nobody else looks at its flag or at its target -- and a loser drops its claim and joins the
-// retry list at once; only a contested WINNER must wait until its rivals have seen its flag, so it goes on a
-// short deferred list that is committed after a grid barrier.  (A loser that has already dropped its flag
-// may be missed by a rival, which changes nothing: the winner's flag stays, and the winner wins whoever it sees.)
-// Rounds 2..8 run over the compact retry list in three barrier-separated phases (request / response / apply).
+// Retry rounds (sparse, persistent).  Round 1 of both claim phases is resolved per tile by the dense commit
+// sweeps (pd_dense.cuh), which list their losers; rounds 2..8 only touch those (~5 % of the movers, ~1/3 of the
+// attempting parents -- and at saturation the population gate stops reproduction after round 1), in place on
+// the flag plane, three phases per round separated by grid barriers:
+//   request  (:784-872, :1042-1134)  probe from the saved direction, post the claim as flags in my own byte
+//   response (:881-960, :1170-1205)  every claimant reads the claim flags around its target; only a contested
+//                                    target needs the rivals' Philox priorities (recomputed, never communicated)
+//   apply                            winners commit, losers drop their claim and stay on the list
 // List entry state: 0x80 active | 0x40 fresh (claimed by the dense sweep) | (probes used - 1) << 3 | start direction.
 // ------------------------------------------------------------------------------------------
-// CTA-aggregated append to N global lists at once: ONE atomicAdd per list per call for the whole CTA (a
-// warp-aggregated append costs one same-address atomic per warp: ~1.3 M of them per step on the round-1 lists
-// of a 2^28-cell world, which serialise in L2 -- profiles/README.md).  Every thread of the CTA must call;
-// slot[k] is only meaningful where pred[k] is set.  Two barriers per call.
-template <int N>
-__device__ __forceinline__ void block_append(unsigned int* const (&counter)[N], const bool (&pred)[N], uint32_t (&slot)[N]) {
-    __shared__ unsigned int s_cnt[N][32];
-    __shared__ unsigned int s_base[N];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-    unsigned int m[N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        m[k] = __ballot_sync(0xFFFFFFFFu, pred[k]);
-        if (lane == 0) s_cnt[k][warp] = (unsigned int)__popc(m[k]);
-    }
-    __syncthreads();
-    if (threadIdx.x < N) {
-        const int k = threadIdx.x;
-        unsigned int total = 0;
-        for (int w = 0; w < nwarp; ++w) {
-            const unsigned int c = s_cnt[k][w];
-            s_cnt[k][w] = total;
-            total += c;
-        }
-        s_base[k] = total ? atomicAdd(counter[k], total) : 0u;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < N; ++k) slot[k] = s_base[k] + s_cnt[k][warp] + (unsigned int)__popc(m[k] & ((1u << lane) - 1u));
-}
-
 template <typename KeyFn>
-__device__ __forceinline__ bool contest(const Params& p, const uint8_t* tf, uint32_t x, uint32_t y, int d, KeyFn keyfn,
-                                        bool& contested) {
+__device__ __forceinline__ bool contest(const Params& p, const uint8_t* tf, uint32_t x, uint32_t y, int d, KeyFn keyfn) {
     const uint32_t tx = (x + (uint32_t)DX(d)) & (p.W - 1);
     const uint32_t ty = nb_row(p, y, DY(d));
     uint32_t rivals = 0;
@@ -193,8 +161,7 @@ __device__ __forceinline__ bool contest(const Params& p, const uint8_t* tf, uint
         if (claims_dir(tn, 7 - j)) rivals |= 1u << j;
     }
     rivals &= ~(1u << (7 - d));  // that one is me
-    contested = rivals != 0u;
-    if (!contested) return true;
+    if (!rivals) return true;
     const Key mine = keyfn(p, gcell_of(p, x, y));
     bool win = true;
     for (uint32_t m = rivals; m; m &= m - 1)
@@ -202,78 +169,21 @@ __device__ __forceinline__ bool contest(const Params& p, const uint8_t* tf, uint
     return win;
 }
 
-// a mover relocates (:946-956); its old cell stays a GHOST: it blocks movers all step (B-13)
-__device__ __forceinline__ void commit_move(const Params& p, uint8_t* tf, uint32_t cell, uint32_t t, int d) {
-    const uint32_t tgt = nb_local(p, cell & (p.W - 1), cell >> p.log2W, d);
-    p.E1[tgt] = __ldcg(p.E1 + cell);
-    p.strat[tgt] = __ldcg(p.strat + cell);
-    tf[tgt] = (uint8_t)(TF_OCC | (t & TF_TRAIT));
-    tf[cell] = (uint8_t)TF_GHOST;
-}
-
 // ------------------------------------------------------------------------------------------
-// k_move_rounds (sparse, persistent): the movement submodel's rounds (exit_move_fn, :1559-1576).  Round 1's
-// move_request is fused into k_play_travel, which lists its claimants; in place on tfB / E1 / strat.
+// k_move_retry: travel rounds 2..8 (exit_move_fn, :1559-1576) for the losers of round 1, on tfA / E1 / strat.
 // ------------------------------------------------------------------------------------------
 template <int BS>
-__global__ void __launch_bounds__(BS) k_move_rounds(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(BS) k_move_retry(const __grid_constant__ Params p) {
     Counters* ctr = p.ctr;
-    unsigned int n0 = ctr->mv_n;
-    if (n0 > p.list_cap) n0 = p.list_cap;
-    if (n0 == 0) return;
+    unsigned int n = ctr->rt_n[0];
+    if (n > p.list_cap) n = p.list_cap;
+    if (n == 0) return;
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    uint8_t* tf = p.tfB;
+    uint8_t* tf = p.tfA;
     unsigned int moved = 0;
-    // ---- round 1: one visit per claimant
-    for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < n0; i0 += stride) {
-        const unsigned int i = i0 + threadIdx.x;
-        bool defer = false, lost = false;
-        uint32_t cell = 0, st = 0;
-        if (i < n0) {
-            cell = p.mv_cell[i];
-            st = p.mv_state[i];
-            const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
-            const int d = (int)(st & 7u);
-            bool contested;
-            const bool win = contest(p, tf, x, y, d, TravelKey(), contested);
-            if (!contested) {
-                commit_move(p, tf, cell, __ldcg(tf + cell), d);
-                if (row_owned(p, y)) ++moved;
-            } else if (win) {
-                defer = true;
-            } else {
-                tf[cell] = (uint8_t)(__ldcg(tf + cell) & (TF_OCC | TF_TRAIT));  // :940-943 -> retry with the same roll
-                lost = true;
-            }
-        }
-        unsigned int* const cnt[2] = {&ctr->dw_n[0], &ctr->rt_n[0]};
-        const bool pred[2] = {defer, lost};
-        uint32_t slot[2];
-        block_append<2>(cnt, pred, slot);
-        if (defer) p.dw_idx[slot[0]] = i;  // dw_n <= n0 <= list_cap
-        if (lost) {
-            p.rt_cell[slot[1]] = cell;
-            p.rt_state[slot[1]] = (uint8_t)st;
-        }
-    }
-    grid_sync(ctr->barrier, gridDim.x);
-    const unsigned int ndw = __ldcg(&ctr->dw_n[0]);
-    for (unsigned int k = t0; k < ndw; k += stride) {
-        const unsigned int i = __ldcg(&p.dw_idx[k]);
-        const uint32_t cell = p.mv_cell[i];
-        commit_move(p, tf, cell, __ldcg(tf + cell), (int)(p.mv_state[i] & 7u));
-        if (row_owned(p, cell >> p.log2W)) ++moved;
-    }
-    const unsigned int n = __ldcg(&ctr->rt_n[0]);
-    if (n == 0) {
-        if (p.stats && moved) atomicAdd(&ctr->st_moved, (unsigned long long)moved);
-        return;
-    }
-    grid_sync(ctr->barrier, gridDim.x);
-    // ---- rounds 2..8 over the retry list
     for (int round = 1; round < 8; ++round) {
-        // request (:784-872): probe from the saved direction over blocked = OCC|GHOST, post the claim
+        // ---- request: blocked = OCC|GHOST (a cell vacated this step keeps blocking movers, B-13)
         for (unsigned int i = t0; i < n; i += stride) {
             const uint32_t st = p.rt_state[i];
             if (!(st & 0x80u)) continue;
@@ -300,27 +210,31 @@ __global__ void __launch_bounds__(BS) k_move_rounds(const __grid_constant__ Para
             }
         }
         grid_sync(ctr->barrier, gridDim.x);
-        // response (:881-960)
+        // ---- response
         for (unsigned int i = t0; i < n; i += stride) {
             if (!(p.rt_state[i] & 0x80u)) continue;
             const uint32_t cell = p.rt_cell[i];
             const int d = (int)(p.rt_aux[i] & 7u);
-            bool contested;
-            const bool win = contest(p, tf, cell & (p.W - 1), cell >> p.log2W, d, TravelKey(), contested);
+            const bool win = contest(p, tf, cell & (p.W - 1), cell >> p.log2W, d, TravelKey());
             p.rt_aux[i] = (uint8_t)((uint32_t)d | (win ? 0x80u : 0u));
         }
         grid_sync(ctr->barrier, gridDim.x);
-        // apply
+        // ---- apply
         unsigned int still = 0;
         for (unsigned int i = t0; i < n; i += stride) {
             if (!(p.rt_state[i] & 0x80u)) continue;
             const uint32_t cell = p.rt_cell[i];
+            const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
             const uint32_t aux = p.rt_aux[i];
             const uint32_t t = __ldcg(tf + cell);
-            if (aux & 0x80u) {
-                commit_move(p, tf, cell, t, (int)(aux & 7u));
+            if (aux & 0x80u) {  // the winner relocates (:946-956)
+                const uint32_t tgt = nb_local(p, x, y, (int)(aux & 7u));
+                p.E1[tgt] = __ldcg(p.E1 + cell);
+                p.strat[tgt] = __ldcg(p.strat + cell);
+                tf[tgt] = (uint8_t)(TF_OCC | (t & TF_TRAIT));
+                tf[cell] = (uint8_t)TF_GHOST;
                 p.rt_state[i] = 0;
-                if (row_owned(p, cell >> p.log2W)) ++moved;
+                if (row_owned(p, y)) ++moved;
             } else {
                 tf[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
                 ++still;
@@ -334,125 +248,26 @@ __global__ void __launch_bounds__(BS) k_move_rounds(const __grid_constant__ Para
 }
 
 // ------------------------------------------------------------------------------------------
-// k_repro_rounds (sparse, persistent): the god submodel's rounds (exit_god_fn, :1607-1627).  Round 1's
-// god_go_forth is fused into k_repro_claim, which lists its claimants; in place on tfA / E1.  Round 1 always
-// runs; further rounds only while the population (olds + births so far) does not exceed max_agents (:1616,
-// :1621-1625).  A winner pays the reproduction cost in E1 (the cost of living follows in k_punish, like layer 7
-// after the god submodel) and its child goes on the newborn list with its energy and strategies; the child
-// enters the flag plane only when further rounds must see its cell blocked -- near the carrying capacity
-// almost every newborn is culled in the same step.
-// Rounds [round0, round1) run in this launch (a row slab runs one round per launch: the caller sums the
-// population over the slabs in between).
+// k_repro_retry: reproduction rounds 2..8 (exit_god_fn, :1607-1627), only while the population (olds + births
+// so far) does not exceed max_agents (:1616, :1621-1625).  On tfA; E1 is read-only (a winner is flagged PARENT,
+// k_punish charges the reproduction cost).  Rounds [round0, round1) run in this launch (a row slab runs one
+// round per launch: the caller sums the population over the slabs in between).
 // ------------------------------------------------------------------------------------------
-struct Birth {
-    bool born;
-    uint32_t tgt, gene;
-    float ce;
-};
-// the parent at `cell` (flag byte t) reproduces into direction d (:1208-1328); mark = the child blocks its cell
-__device__ __forceinline__ Birth commit_birth(const Params& p, uint8_t* tf, uint32_t cell, uint32_t t, int d, bool mark) {
-    const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
-    Birth b;
-    b.tgt = nb_local(p, x, y, d);
-    const float pe = __fsub_rn(__ldcg(p.E1 + cell), p.reproduce_cost);  // :1211-1213
-    p.E1[cell] = pe;
-    uint32_t cs;
-    make_child(p, gcell_of(p, x, y), __ldcg(p.strat + cell), t & TF_TRAIT, pe, b.ce, cs);
-    b.gene = cs | ((t & TF_TRAIT) << 8);
-    b.born = row_owned(p, b.tgt >> p.log2W);  // a child in the ghost zone belongs to the neighbour slab: it is not
-    // listed here, so it cannot be flagged later -- it has to block its cell from now on
-    if (mark || !b.born) tf[b.tgt] = (uint8_t)(TF_OCC | TF_NEWBORN | (t & TF_TRAIT));
-    return b;
-}
-// every thread of the CTA calls: the newborn list takes the child with its payload; `births` is counted by
-// the callers from the list length
-__device__ __forceinline__ void store_birth(const Params& p, const Birth& b, uint32_t slot) {
-    if (b.born) {
-        if (slot < p.list_cap) {
-            p.nb_cell[slot] = b.tgt;
-            p.nb_e[slot] = b.ce;
-            p.nb_gene[slot] = (uint16_t)b.gene;
-        } else atomicExch(&p.ctr->overflow, 1u);
-    }
-}
-__device__ __forceinline__ void list_birth(const Params& p, const Birth& b) {
-    unsigned int* const cnt[1] = {&p.ctr->nb_n};
-    const bool pred[1] = {b.born};
-    uint32_t slot[1];
-    block_append<1>(cnt, pred, slot);
-    store_birth(p, b, slot[0]);
-}
-
 template <int BS>
-__global__ void __launch_bounds__(BS) k_repro_rounds(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(BS) k_repro_retry(const __grid_constant__ Params p) {
     Counters* ctr = p.ctr;
-    unsigned int n0 = ctr->rp_n;
-    if (n0 > p.list_cap) n0 = p.list_cap;
-    if (n0 == 0) return;  // nobody claims: no births either
+    unsigned int n = ctr->rt_n[1];
+    if (n > p.list_cap) n = p.list_cap;
+    if (n == 0) return;
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     uint8_t* tf = p.tfA;
-    if (p.round0 == 0) {
-        // ---- round 1: one visit per claimant
-        for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < n0; i0 += stride) {
-            const unsigned int i = i0 + threadIdx.x;
-            bool defer = false, lost = false;
-            uint32_t cell = 0, st = 0;
-            Birth b;
-            b.born = false; b.tgt = 0; b.gene = 0; b.ce = 0.0f;
-            if (i < n0) {
-                cell = p.rp_cell[i];
-                st = p.rp_state[i];
-                const int d = (int)(st & 7u);
-                bool contested;
-                const bool win = contest(p, tf, cell & (p.W - 1), cell >> p.log2W, d, ReproKey(), contested);
-                const uint32_t t = __ldcg(tf + cell);
-                if (!contested) {
-                    tf[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
-                    b = commit_birth(p, tf, cell, t, d, false);
-                } else if (win) {
-                    defer = true;
-                } else {
-                    tf[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));  // stays ATTEMPTING_REPRODUCTION (:1203-1205)
-                    lost = true;
-                }
-            }
-            unsigned int* const cnt[3] = {&ctr->nb_n, &ctr->dw_n[1], &ctr->rt_n[1]};
-            const bool pred[3] = {b.born, defer, lost};
-            uint32_t slot[3];
-            block_append<3>(cnt, pred, slot);
-            store_birth(p, b, slot[0]);
-            if (defer) p.dw_idx[slot[1]] = i;
-            if (lost) {
-                p.rt_cell[slot[2]] = cell;
-                p.rt_state[slot[2]] = (uint8_t)st;
-            }
-        }
-        grid_sync(ctr->barrier, gridDim.x);
-        const unsigned int ndw = __ldcg(&ctr->dw_n[1]);
-        for (unsigned int k0 = blockIdx.x * blockDim.x; k0 < ndw; k0 += stride) {
-            const unsigned int k = k0 + threadIdx.x;
-            Birth b;
-            b.born = false; b.tgt = 0; b.gene = 0; b.ce = 0.0f;
-            if (k < ndw) {
-                const unsigned int i = __ldcg(&p.dw_idx[k]);
-                const uint32_t cell = p.rp_cell[i];
-                const uint32_t t = __ldcg(tf + cell);
-                tf[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
-                b = commit_birth(p, tf, cell, t, (int)(p.rp_state[i] & 7u), false);
-            }
-            list_birth(p, b);
-        }
-        grid_sync(ctr->barrier, gridDim.x);
-        if (t0 == 0) ctr->rp_active[0] = __ldcg(&ctr->rt_n[1]);
-    }
-    const unsigned int n = __ldcg(&ctr->rt_n[1]);
-    for (int round = p.round0 > 1u ? (int)p.round0 : 1; round < (int)p.round1; ++round) {
+    for (int round = (int)p.round0; round < (int)p.round1; ++round) {
         // overpopulated gate, evaluated after every round (:1616, :1621-1625); in slab mode the caller
         // has summed olds and births over all slabs into glb[] before this launch
         const unsigned long long pop = p.glb ? __ldcg(&p.glb[0]) + __ldcg(&p.glb[1])
                                              : __ldcg(&ctr->n_old) + (unsigned long long)__ldcg(&ctr->nb_n);
-        if (pop > p.max_agents || n == 0) break;
+        if (pop > p.max_agents) break;
         if (round == 1) {
             // the newborns of round 1 are only on the newborn list so far: they must block their cells now
             unsigned int nb1 = __ldcg(&ctr->nb_n);
@@ -494,8 +309,7 @@ __global__ void __launch_bounds__(BS) k_repro_rounds(const __grid_constant__ Par
             if (!(p.rt_state[i] & 0x80u)) continue;
             const uint32_t cell = p.rt_cell[i];
             const int d = (int)(p.rt_aux[i] & 7u);
-            bool contested;
-            const bool win = contest(p, tf, cell & (p.W - 1), cell >> p.log2W, d, ReproKey(), contested);
+            const bool win = contest(p, tf, cell & (p.W - 1), cell >> p.log2W, d, ReproKey());
             p.rt_aux[i] = (uint8_t)((uint32_t)d | (win ? 0x80u : 0u));
         }
         grid_sync(ctr->barrier, gridDim.x);
@@ -503,21 +317,37 @@ __global__ void __launch_bounds__(BS) k_repro_rounds(const __grid_constant__ Par
         unsigned int still = 0;
         for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
             const unsigned int i = i0 + threadIdx.x;
-            Birth b;
-            b.born = false; b.tgt = 0; b.gene = 0; b.ce = 0.0f;
+            bool born = false;
+            uint32_t tgt = 0, gene = 0;
+            float ce = 0.0f;
             if (i < n && (p.rt_state[i] & 0x80u)) {
                 const uint32_t cell = p.rt_cell[i];
+                const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
                 const uint32_t aux = p.rt_aux[i];
                 const uint32_t t = __ldcg(tf + cell);
-                tf[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
                 if (aux & 0x80u) {
-                    b = commit_birth(p, tf, cell, t, (int)(aux & 7u), true);  // blocks its cell in later rounds
-                    p.rt_state[i] = 0x40u;  // REPRODUCTION_COMPLETE: one child per step (B-6)
+                    tgt = nb_local(p, x, y, (int)(aux & 7u));
+                    const float pe = __fsub_rn(__ldcg(p.E1 + cell), p.reproduce_cost);  // :1211-1213
+                    uint32_t cs;
+                    make_child(p, gcell_of(p, x, y), __ldcg(p.strat + cell), t & TF_TRAIT, pe, ce, cs);
+                    tf[tgt] = (uint8_t)(TF_OCC | TF_NEWBORN | (t & TF_TRAIT));  // blocks its cell in later rounds
+                    tf[cell] = (uint8_t)(TF_OCC | TF_PARENT | (t & TF_TRAIT));  // REPRODUCTION_COMPLETE: one child per step (B-6)
+                    gene = cs | ((t & TF_TRAIT) << 8);
+                    born = row_owned(p, tgt >> p.log2W);  // a child in the ghost zone belongs to the neighbour slab
+                    p.rt_state[i] = 0x40u;
                 } else {
+                    tf[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
                     ++still;
                 }
             }
-            list_birth(p, b);
+            const uint32_t slot = warp_append(&ctr->nb_n, born);
+            if (born) {
+                if (slot < p.list_cap) {
+                    p.nb_cell[slot] = tgt;
+                    p.nb_e[slot] = ce;
+                    p.nb_gene[slot] = (uint16_t)gene;
+                } else atomicExch(&ctr->overflow, 1u);
+            }
         }
         if (still) atomicAdd(&ctr->rp_active[round], still);
         grid_sync(ctr->barrier, gridDim.x);
@@ -934,7 +764,7 @@ __global__ void k_publish_gate(const __grid_constant__ Params p, int round) {
     if (threadIdx.x == 0) {
         p.glb[0] = p.ctr->n_old;
         p.glb[1] = p.ctr->nb_n;  // births
-        p.glb[2] = p.ctr->rp_active[round];
+        p.glb[2] = round == 0 ? p.ctr->rt_n[1] : p.ctr->rp_active[round];  // parents still trying
     }
 }
 

@@ -85,7 +85,7 @@ struct pd_sim {
     std::vector<cudaEvent_t> ev;   // (start, end) event pairs, consumed by pd_read_profile
     std::vector<int> ev_slot;      // kernel slot of pair k
     size_t ev_used;                // events used (2 per pair)
-    double kernel_ms[9];
+    double kernel_ms[PDABM_NUM_KERNELS];
     uint32_t prof_steps;
     bool step_dirty;               // host step number not yet written to Counters::step_no
     // CUDA graphs of one whole step (9 launches), one per (at-risk list parity, want_counts); used for worlds
@@ -108,8 +108,7 @@ int alloc_lists(pd_sim* s, uint64_t n_agents_hint) {
         // grow: free and reallocate
         drop_graphs(s);
         cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.cand);
-        cudaFree(s->P.mv_cell); cudaFree(s->P.mv_state);
-        cudaFree(s->P.rp_cell); cudaFree(s->P.rp_state);
+        cudaFree(s->P.mv_claim); cudaFree(s->P.rp_claim);
         cudaFree(s->P.rt_cell); cudaFree(s->P.rt_state); cudaFree(s->P.rt_aux);
         cudaFree(s->P.nb_cell); cudaFree(s->P.nb_e); cudaFree(s->P.nb_gene);
         s->lists_allocated = false;
@@ -126,11 +125,8 @@ int alloc_lists(pd_sim* s, uint64_t n_agents_hint) {
     CK(cudaMalloc(&s->risk[1], cap * 4));
     CK(cudaMalloc(&s->P.risk_e, cap * 4));
     CK(cudaMalloc(&s->P.cand, (cap / 2 + 1) * 8));
-    CK(cudaMalloc(&s->P.mv_cell, cap * 4));
-    s->P.dw_idx = reinterpret_cast<uint32_t*>(s->P.risk_e);
-    CK(cudaMalloc(&s->P.mv_state, cap));
-    CK(cudaMalloc(&s->P.rp_cell, cap * 4));
-    CK(cudaMalloc(&s->P.rp_state, cap));
+    CK(cudaMalloc(&s->P.mv_claim, cap * 4));
+    CK(cudaMalloc(&s->P.rp_claim, cap * 4));
     CK(cudaMalloc(&s->P.rt_cell, cap * 4));
     CK(cudaMalloc(&s->P.rt_state, cap));
     CK(cudaMalloc(&s->P.rt_aux, cap));
@@ -212,20 +208,24 @@ int launch_punish(pd_sim* s, cudaStream_t st) {
     return PD_OK;
 }
 
-// the 8 launches of one model step, in the order of the reference's main layers (model.py:2140-2163)
+// one dense sweep over the tiles
+#define DENSE(kernel) do { if (s->big_tiles) kernel<128, 16><<<s->grid, NT, 0, st>>>(P); \
+                           else kernel<16, 16><<<s->grid, NT, 0, st>>>(P); } while (0)
+
+// the 10 launches of one model step, in the order of the reference's main layers (model.py:2140-2163)
 int launch_step(pd_sim* s, cudaStream_t st) {
     Params& P = s->P;
     int rc = PD_OK;
     PROF(0, (k_begin_step<<<1, 256, 0, st>>>(P.ctr, 1)));
     PROF(1, { if ((rc = launch_sparse(s, k_risk_resolve, st))) return rc; });
-    PROF(2, { if (s->big_tiles) k_play_travel<128, 16><<<s->grid, NT, 0, st>>>(P);
-              else k_play_travel<16, 16><<<s->grid, NT, 0, st>>>(P); });
-    PROF(3, { if ((rc = launch_sparse(s, k_move_rounds, st))) return rc; });
-    PROF(4, { if (s->big_tiles) k_repro_claim<128, 16><<<s->grid, NT, 0, st>>>(P);
-              else k_repro_claim<16, 16><<<s->grid, NT, 0, st>>>(P); });
-    PROF(5, { if ((rc = launch_sparse(s, k_repro_rounds, st))) return rc; });
-    PROF(6, { if ((rc = launch_punish(s, st))) return rc; });
-    PROF(7, { if ((rc = launch_sparse(s, k_finalize, st))) return rc; });
+    PROF(2, DENSE(k_play_travel));
+    PROF(3, DENSE(k_move_commit));
+    PROF(4, { if ((rc = launch_sparse(s, k_move_retry, st))) return rc; });
+    PROF(5, DENSE(k_repro_claim));
+    PROF(6, DENSE(k_repro_commit));
+    PROF(7, { if ((rc = launch_sparse(s, k_repro_retry, st))) return rc; });
+    PROF(8, { if ((rc = launch_punish(s, st))) return rc; });
+    PROF(9, { if ((rc = launch_sparse(s, k_finalize, st))) return rc; });
     return PD_OK;
 }
 
@@ -346,7 +346,7 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     P.row0 = (cfg->row0 + HW - cfg->ghost_rows) & (HW - 1);  // global row of local row 0
     P.wrap_y = slab ? 0u : 1u;
     P.own_y0 = cfg->ghost_rows; P.own_y1 = cfg->ghost_rows + cfg->rows;
-    P.round0 = 0; P.round1 = 8; P.world = 1; P.cand_cap = 0;
+    P.round0 = 1; P.round1 = 8; P.world = 1; P.cand_cap = 0;
     P.select_cap = cfg->debug_select_cap ? cfg->debug_select_cap : 0xFFFFFFFFu;
     P.step_log = nullptr; P.log_cap = 0;
     P.glb = nullptr; P.ghist = nullptr; P.cand_out = nullptr; P.cand_all = nullptr;
@@ -394,6 +394,13 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     s->graphs = cfg->use_graphs > 0 || (cfg->use_graphs == 0 && !slab && s->cells <= ((size_t)1 << 22));
     if (slab) s->graphs = false;  // a slab is stepped in parts with host decisions in between
     {
+        const size_t tiles = (size_t)s->grid.x * s->grid.y;
+        CK(cudaMalloc(&P.seg_mv, tiles * sizeof(uint2)));
+        CK(cudaMalloc(&P.seg_rp, tiles * sizeof(uint2)));
+        CK(cudaMemset(P.seg_mv, 0, tiles * sizeof(uint2)));
+        CK(cudaMemset(P.seg_rp, 0, tiles * sizeof(uint2)));
+    }
+    {
         float h_lut[256], *d_lut = nullptr;
         for (uint32_t i = 0; i < 256; ++i) h_lut[i] = lut_entry(P.pay, i);
         CK(cudaMalloc(&d_lut, sizeof h_lut));
@@ -417,10 +424,10 @@ int pd_destroy(pd_sim* s) {
     drop_graphs(s);
     if (s->P.step_log) cudaFree(s->P.step_log);
     cudaFree(s->P.E1); cudaFree(s->P.tfB); cudaFree(s->P.ctr); cudaFree(const_cast<float*>(s->P.lut));
+    cudaFree(s->P.seg_mv); cudaFree(s->P.seg_rp);
     if (s->lists_allocated) {
         cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.cand);
-        cudaFree(s->P.mv_cell); cudaFree(s->P.mv_state);
-        cudaFree(s->P.rp_cell); cudaFree(s->P.rp_state);
+        cudaFree(s->P.mv_claim); cudaFree(s->P.rp_claim);
         cudaFree(s->P.rt_cell); cudaFree(s->P.rt_state); cudaFree(s->P.rt_aux);
         cudaFree(s->P.nb_cell); cudaFree(s->P.nb_e); cudaFree(s->P.nb_gene);
     }
@@ -604,33 +611,30 @@ int pd_step_part(pd_sim* s, int part, int arg, void* stream, int want_counts) {
         const int blocks = (int)((ghost_cells + 255) / 256 < (size_t)(s->n_sms * 8) ? (ghost_cells + 255) / 256 : (size_t)(s->n_sms * 8));
         PROF(0, { k_ghost_risk_scan<<<blocks, 256, 0, st>>>(P); k_begin_step<<<1, 256, 0, st>>>(P.ctr, 1); });
         PROF(1, { if ((rc = launch_sparse(s, k_risk_resolve, st))) return rc; });
-        PROF(2, { if (s->big_tiles) k_play_travel<128, 16><<<s->grid, NT, 0, st>>>(P);
-                  else k_play_travel<16, 16><<<s->grid, NT, 0, st>>>(P); });
-        PROF(3, { if ((rc = launch_sparse(s, k_move_rounds, st))) return rc; });
-        PROF(4, { if (s->big_tiles) k_repro_claim<128, 16><<<s->grid, NT, 0, st>>>(P);
-                  else k_repro_claim<16, 16><<<s->grid, NT, 0, st>>>(P); });
-        P.round0 = 0; P.round1 = 1;  // round 1 needs no gate (:1682); the caller sums the population before any other
-        PROF(5, { if ((rc = launch_sparse(s, k_repro_rounds, st))) return rc; });
-        P.round0 = 0; P.round1 = 8;
+        PROF(2, DENSE(k_play_travel));
+        PROF(3, DENSE(k_move_commit));
+        PROF(4, { if ((rc = launch_sparse(s, k_move_retry, st))) return rc; });
+        PROF(5, DENSE(k_repro_claim));
+        PROF(6, DENSE(k_repro_commit));
         k_publish_gate<<<1, 32, 0, st>>>(P, 0);
         break;
     }
     case PD_PART_RETRY:
         if (arg < 1 || arg > 7) return fail(PD_ERR_INVALID, "retry round %d out of range 1..7", arg);
         P.round0 = (uint32_t)arg; P.round1 = (uint32_t)arg + 1;
-        PROF(5, { if ((rc = launch_sparse(s, k_repro_rounds, st))) return rc; });
+        PROF(7, { if ((rc = launch_sparse(s, k_repro_retry, st))) return rc; });
         k_publish_gate<<<1, 32, 0, st>>>(P, arg);
-        P.round0 = 0; P.round1 = 8;
+        P.round0 = 1; P.round1 = 8;
         break;
     case PD_PART_HIST:  // the reproduction rounds are over: cost of living, then this slab's cull histogram
-        PROF(6, { if ((rc = launch_punish(s, st))) return rc; });
-        PROF(7, { if ((rc = launch_sparse(s, k_fin_hist, st))) return rc; });
+        PROF(8, { if ((rc = launch_punish(s, st))) return rc; });
+        PROF(9, { if ((rc = launch_sparse(s, k_fin_hist, st))) return rc; });
         break;
     case PD_PART_CAND:
-        PROF(7, { if ((rc = launch_sparse(s, k_fin_cand, st))) return rc; });
+        PROF(9, { if ((rc = launch_sparse(s, k_fin_cand, st))) return rc; });
         break;
     case PD_PART_APPLY:
-        PROF(7, { if ((rc = launch_sparse(s, k_fin_apply, st))) return rc; });
+        PROF(9, { if ((rc = launch_sparse(s, k_fin_apply, st))) return rc; });
         s->risk_cur ^= 1;
         s->step += 1;
         break;
@@ -646,11 +650,11 @@ int pd_set_profile(pd_sim* s, int on) {
     s->profile = on != 0;
     s->ev_used = 0;
     s->prof_steps = 0;
-    for (int i = 0; i < 9; ++i) s->kernel_ms[i] = 0.0;
+    for (int i = 0; i < PDABM_NUM_KERNELS; ++i) s->kernel_ms[i] = 0.0;
     return PD_OK;
 }
 
-int pd_read_profile(pd_sim* s, double kernel_ms[9], uint32_t* steps, void* stream) {
+int pd_read_profile(pd_sim* s, double kernel_ms[PDABM_NUM_KERNELS], uint32_t* steps, void* stream) {
     if (!s || !kernel_ms) return fail(PD_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
@@ -661,7 +665,7 @@ int pd_read_profile(pd_sim* s, double kernel_ms[9], uint32_t* steps, void* strea
         if (s->ev_slot[k] == 2) s->prof_steps += 1;  // one play sweep per step
     }
     s->ev_used = 0;
-    for (int i = 0; i < 9; ++i) kernel_ms[i] = s->kernel_ms[i];
+    for (int i = 0; i < PDABM_NUM_KERNELS; ++i) kernel_ms[i] = s->kernel_ms[i];
     if (steps) *steps = s->prof_steps;
     return PD_OK;
 }

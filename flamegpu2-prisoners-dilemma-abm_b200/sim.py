@@ -189,8 +189,8 @@ class Simulation:
         self._check(self.lib.pd_read_stats(self._h, C.byref(st), self.stream_ptr))
         return {n: int(getattr(st, n)) for n, _ in pd_step_stats._fields_}
 
-    KERNELS = ("begin_step", "risk_resolve", "play_travel", "move_rounds", "repro_claim",
-               "repro_rounds", "punish", "finalize", "other")
+    KERNELS = ("begin_step", "risk_resolve", "play_travel", "move_commit", "move_retry", "repro_claim",
+               "repro_commit", "repro_retry", "punish", "finalize")
 
     def agent_steps(self) -> int:
         """Sum over executed steps of the population at the start of the step."""
@@ -245,7 +245,7 @@ class Simulation:
 
     def read_profile(self):
         """({kernel: total ms}, profiled steps)."""
-        ms = (C.c_double * 9)()
+        ms = (C.c_double * len(self.KERNELS))()
         n = C.c_uint32()
         self._check(self.lib.pd_read_profile(self._h, ms, C.byref(n), self.stream_ptr))
         return {k: float(ms[i]) for i, k in enumerate(self.KERNELS)}, int(n.value)

@@ -78,7 +78,7 @@ typedef struct pd_config {
     uint32_t world_height;          /* 0 = width (square, like the reference); else a power of two: the world is
                                        width x world_height cells (used for weak-scaling series of row slabs) */
     int32_t use_graphs;             /* 0 = auto (whole worlds <= 2^22 cells), 1 = always, -1 = never: replay one
-                                       captured CUDA graph per step instead of 8 launches.  Only on explicit
+                                       captured CUDA graph per step instead of 10 launches.  Only on explicit
                                        (capturable) streams and while per-kernel profiling is off. */
     uint32_t debug_select_cap;      /* 0 = default; tests: cap of the cull select's shared-memory stage, to force its
                                        global-memory fallback */
@@ -174,9 +174,9 @@ int pd_read_step_log(pd_sim* sim, uint64_t* rows, uint32_t max_rows, uint32_t* n
 
 /* Per-kernel device timing: with profiling on, pd_step records a CUDA event between every
  * two kernel launches; pd_read_profile synchronises `stream` and returns the accumulated
- * milliseconds per kernel, in launch order: begin_step, risk_resolve, play_travel,
- * move_rounds, repro_claim, repro_rounds, punish, finalize (slot 8 is unused). */
-#define PDABM_NUM_KERNELS 9
+ * milliseconds per kernel, in launch order: begin_step, risk_resolve, play_travel, move_commit,
+ * move_retry, repro_claim, repro_commit, repro_retry, punish, finalize. */
+#define PDABM_NUM_KERNELS 10
 int pd_set_profile(pd_sim* sim, int on);
 int pd_read_profile(pd_sim* sim, double kernel_ms[PDABM_NUM_KERNELS], uint32_t* steps, void* stream);
 
@@ -185,7 +185,7 @@ int pd_get_step(pd_sim* sim, uint32_t* step);
 int pd_set_step(pd_sim* sim, uint32_t step);
 
 /* Number of model steps this handle ran by replaying a captured CUDA graph (pd_config.use_graphs)
- * rather than by launching the 8 kernels one by one. */
+ * rather than by launching the 10 kernels one by one. */
 int pd_graph_replays(pd_sim* sim, uint64_t* steps);
 
 /* HOST-buffer entry point (what a host-side caller without device buffers binds):
