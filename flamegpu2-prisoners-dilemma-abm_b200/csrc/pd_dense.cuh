@@ -42,7 +42,7 @@ __device__ __forceinline__ bool key_gt(const Key& a, const Key& b) {
 }
 struct TravelKey {
     __device__ __forceinline__ Key operator()(const Params& p, uint64_t g) const {
-        Key k; k.prio = rng(p, g, S_ROLL).y; k.gcell = g; return k;  // :806
+        Key k; k.prio = rng(p, g, S_TRAVEL).x; k.gcell = g; return k;  // :806
     }
 };
 struct ReproKey {
@@ -115,22 +115,25 @@ __device__ __forceinline__ uint32_t wappend(unsigned int* counter, bool pred) {
 //
 // Per cell of tile + 1-ring ONE 32-bit word R is staged in shared memory:
 //     empty cell: 0
-//     occupied:   bit 31 | roll (19 bits) << 12 | has-D-code << 11 | strategies (8) << 3 | trait (2) << 1
+//     occupied:   bit 31 | roll (16 bits) << 15 | has-D-code << 11 | strategies (8) << 3 | trait (2) << 1
 // so one shared-memory load per neighbour answers "occupied?", "does it challenge me?" (an unsigned
 // compare of the whole word against one of two thresholds: a tie of the rolls goes to the neighbour in a
-// direction >= 4) and yields both strategies of the game.  An agent then plays its (up to) 8 games as the
-// responder in sub-step order straight from those words: the strategies, the two RANDOM coins (bits of the
-// agent's own roll call, kept next to its list entry) and -- with noise -- the two flips form the index
-// of a 256-entry payoff table in shared memory, so a game costs one table look-up and no random call.
+// direction >= 4) and yields both strategies of the game.  The words are built straight from global memory,
+// four cells (one flag word, one strategy word, ONE Philox call) per thread -- no flag / strategy tiles in
+// shared memory and a single barrier before the agents run; the same pass compacts the tile's agents into a
+// work list.  An agent then plays its (up to) 8 games as the responder in sub-step order straight from the
+// words: the strategies, the two RANDOM coins (the low half of the agent's play word, kept next to its list
+// entry) and -- with noise -- the two flips form the index of a 256-entry payoff table in shared memory, so a
+// game costs one table look-up and no random call.
 // ------------------------------------------------------------------------------------------
 
 constexpr uint32_t R_OCC = 0x80000000u;
 constexpr uint32_t R_DFLAG = 0x800u;
-constexpr uint32_t R_LOW = 0xFFFu;  // everything below the roll
+constexpr uint32_t R_LOW = 0x7FFFu;  // everything below the roll
 
-// append v0 + k for every byte k of `occ4` that has bit 7 set; all 32 lanes call.  Four ballots give every lane its
+// append v[k] for every byte k of `occ4` that has bit 7 set; all 32 lanes call.  Four ballots give every lane its
 // slots without a scan (the order inside the warp's chunk is byte-major, which nobody cares about).
-__device__ __forceinline__ void wappend4(unsigned int* cnt, uint32_t* list, uint32_t occ4, uint32_t v0) {
+__device__ __forceinline__ void wappend4(unsigned int* cnt, uint32_t* list, uint32_t occ4, const uint32_t (&v)[4]) {
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t m0 = __ballot_sync(FULL, occ4 & 0x80u), m1 = __ballot_sync(FULL, occ4 & 0x8000u);
@@ -140,10 +143,10 @@ __device__ __forceinline__ void wappend4(unsigned int* cnt, uint32_t* list, uint
     unsigned int base = 0;
     if (lane == 0) base = satom_add(cnt, (unsigned int)total);
     base = __shfl_sync(FULL, base, 0);
-    if (occ4 & 0x80u) list[base + __popc(m0 & lt)] = v0;
-    if (occ4 & 0x8000u) list[base + n0 + __popc(m1 & lt)] = v0 + 1u;
-    if (occ4 & 0x800000u) list[base + n0 + n1 + __popc(m2 & lt)] = v0 + 2u;
-    if (occ4 & 0x80000000u) list[base + n0 + n1 + n2 + __popc(m3 & lt)] = v0 + 3u;
+    if (occ4 & 0x80u) list[base + __popc(m0 & lt)] = v[0];
+    if (occ4 & 0x8000u) list[base + n0 + __popc(m1 & lt)] = v[1];
+    if (occ4 & 0x800000u) list[base + n0 + n1 + __popc(m2 & lt)] = v[2];
+    if (occ4 & 0x80000000u) list[base + n0 + n1 + n2 + __popc(m3 & lt)] = v[3];
 }
 
 // entry i of the payoff table: bits 0-1 the challenger's strategy against my trait, 2-3 my strategy against
@@ -200,100 +203,106 @@ __device__ __forceinline__ float play_games(const Params& p, const float* s_lut,
 
 template <int TW, int TH>
 __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ Params p) {
-    constexpr int SW = TW + 32, SH = TH + 2, NC = TW * TH, NRING = 2 * (TW + 2) + 2 * TH;
+    // R words: TH + 2 rows of GROW groups of 4 cells -- the groups left and right of the tile hold the ring columns
+    constexpr int GROW = TW / 4 + 2, SWR = 4 * GROW, NC = TW * TH;
+    constexpr int NI = NC / 4, NITEM = NI + 2 * GROW + 2 * TH;  // interior groups, then the ring's: top, bottom, sides
     constexpr int LOG_TW = TW == 128 ? 7 : 4;
     static_assert(TW == 128 || TW == 16, "tile width");
-    static_assert(SH * SW < 65536 && SW == TW + 32, "a shared-memory cell index fits 16 bits");
-    __shared__ __align__(16) uint8_t s_tf[SH * SW];
-    __shared__ __align__(16) uint8_t s_st[SH * SW];
-    __shared__ __align__(16) uint32_t s_R[SH * SW];
+    static_assert(NI % 32 == 0, "whole warps of interior groups");
+    __shared__ __align__(16) uint32_t s_R[(TH + 2) * SWR];
     __shared__ __align__(16) float s_e[NC];
     __shared__ __align__(16) uint8_t s_out[NC];
-    // the agents of the tile: tile-local cell index | the agent's 16 coin bits << 16 (written by whoever computes
-    // its roll); and the occupied cells of the 1-ring around the tile (shared-memory cell index)
+    // the agents of the tile: tile-local cell index | the agent's 16 coin bits << 16.  Later: the tile's claimants.
     __shared__ uint32_t s_cells[NC];
-    __shared__ uint16_t s_ring[NRING];
     __shared__ uint16_t s_mover[NC];
     __shared__ float s_lut[256];
-    __shared__ unsigned int s_n[4];  // 0 agents, 1 ring cells (later: base of this tile's travel-list entries), 2 movers, 3 claimants
+    __shared__ unsigned int s_n[4];  // 0 agents, 1 base of this tile's travel-list entries, 2 movers, 3 claimants
     const int tid = threadIdx.x;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const bool noisy = p.noise_thr != 0ull;
     if (tid < 4) s_n[tid] = 0;
-    static_assert(NT == 256, "one table entry per thread");
-    s_lut[tid] = __ldg(p.lut + tid);  // lut_entry() of every index, filled by pd_create
-    load_tile_vec<TW, TH, 1>(p, p.tfA, s_tf, x0, y0);
-    load_tile_vec<TW, TH, 1>(p, p.strat, s_st, x0, y0);
+    // the energies go straight to shared memory (cp.async); they are first needed after the barrier below
     for (int i = tid; i < NC / 4; i += NT) {
         const int ly = (i * 4) >> LOG_TW, lx = (i * 4) & (TW - 1);
-        reinterpret_cast<float4*>(s_e)[i] =
-            *reinterpret_cast<const float4*>(p.E0 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx);
+        const float* src = p.E0 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(s_e + i * 4)), "l"(src));
     }
+    asm volatile("cp.async.commit_group;");
+    static_assert(NT == 256, "one table entry per thread");
+    s_lut[tid] = __ldg(p.lut + tid);  // lut_entry() of every index, filled by pd_create
     for (int i = tid; i < NC / 16; i += NT) reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < SH * SW / 4; i += NT) reinterpret_cast<uint4*>(s_R)[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    // ---- compaction, 4 cells per lane: the agents of this tile, and the occupied cells of the 1-ring around it
-    // (they only need their word)
-    for (int base = 0; base < NC / 4; base += NT) {
-        const int i = base + tid;  // NC/4 is a multiple of 32, so whole warps are in or out
-        if (i < NC / 4) {
-            const int ly = (i * 4) >> LOG_TW, lx = (i * 4) & (TW - 1);
-            wappend4(&s_n[0], s_cells, *reinterpret_cast<const uint32_t*>(s_tf + (ly + 1) * SW + lx + 16) & 0x80808080u,
-                     (uint32_t)(i * 4));
+    // ---- the word of every cell in reach: per-step die roll (:364) recomputed, not communicated.  One group of 4
+    // cells per thread and iteration: flag word + strategy word from global memory, one Philox call, 4 words out.
+    constexpr int NIT = (NITEM + NT - 1) / NT;
+    uint32_t tf4[NIT], st4[NIT];
+    int sw[NIT];          // shared-memory word index of the group, -1 = no item
+    uint32_t gq[NIT];     // global column of the group's first cell
+    uint32_t gyv[NIT];    // global row
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int j = tid + it * NT;
+        int ly, lx4;
+        if (j < NI) { ly = j / (TW / 4); lx4 = 4 * (j - ly * (TW / 4)); }
+        else {
+            const int r = j - NI;
+            if (r < GROW) { ly = -1; lx4 = 4 * r - 4; }
+            else if (r < 2 * GROW) { ly = TH; lx4 = 4 * (r - GROW) - 4; }
+            else { const int k = r - 2 * GROW; ly = k >> 1; lx4 = (k & 1) ? TW : -4; }
+        }
+        sw[it] = j < NITEM ? (ly + 1) * SWR + 4 + lx4 : -1;
+        gq[it] = (x0 + (uint32_t)lx4) & (p.W - 1);
+        gyv[it] = (p.row0 + y0 + (uint32_t)ly) & (p.HW - 1);
+        tf4[it] = 0; st4[it] = 0;
+        const int yl = (int)y0 + ly;  // local row: wraps for a whole world; a slab reads rows beyond its planes as empty
+        const bool in = j < NITEM && (p.wrap_y || (yl >= 0 && yl < (int)p.H));
+        if (in) {
+            const size_t off = ((size_t)(p.wrap_y ? ((uint32_t)yl & (p.H - 1)) : (uint32_t)yl) << p.log2W) + gq[it];
+            tf4[it] = *reinterpret_cast<const uint32_t*>(p.tfA + off);
+            st4[it] = *reinterpret_cast<const uint32_t*>(p.strat + off);
         }
     }
-    for (int base = 0; base < NRING; base += NT) {
-        const int i = base + tid;
-        int si = 0;
-        bool occ = false;
-        if (i < NRING) {
-            if (i < TW + 2) si = 15 + i;                                           // top row
-            else if (i < 2 * (TW + 2)) si = (SH - 1) * SW + 15 + (i - (TW + 2));   // bottom row
-            else {
-                const int k = i - 2 * (TW + 2);                                    // left / right columns
-                si = (1 + (k >> 1)) * SW + ((k & 1) ? (16 + TW) : 15);
+    __syncthreads();  // the list counters are zero (the loads above are in flight meanwhile)
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int j = tid + it * NT;
+        if (it * NT >= NITEM) break;
+        if (it * NT < NI || j < NITEM) {  // (the interior iterations are warp-uniform: wappend4 needs whole warps)
+            const uint32_t occ4 = tf4[it] & 0x80808080u;
+            uint4 r4 = make_uint4(0, 0, 0, 0);
+            uint32_t v[4] = {0, 0, 0, 0};
+            if (occ4) {
+                const uint64_t g4 = (((uint64_t)gyv[it] << p.log2W) | gq[it]) >> 2;
+                const Words w = rng(p, g4, S_ROLL);
+                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+                uint32_t rr[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t t = (tf4[it] >> (8 * k)) & 0xFFu, sb = (st4[it] >> (8 * k)) & 0xFFu;
+                    rr[k] = (t & TF_OCC) ? (R_OCC | ((ww[k] >> ROLL_SHIFT) << 15) | ((t & TF_D) ? R_DFLAG : 0u) | (sb << 3) |
+                                            ((t & TF_TRAIT) << 1)) : 0u;
+                    v[k] = ((uint32_t)(j * 4 + k)) | (ww[k] << 16);  // (interior: j * 4 + k is the tile-local cell)
+                }
+                r4 = make_uint4(rr[0], rr[1], rr[2], rr[3]);
             }
-            occ = (s_tf[si] & TF_OCC) != 0;
+            if (j < NITEM) *reinterpret_cast<uint4*>(s_R + sw[it]) = r4;
+            if (it * NT < NI) wappend4(&s_n[0], s_cells, j < NI ? occ4 : 0u, v);
         }
-        const uint32_t slot = wappend(&s_n[1], occ);
-        if (occ) s_ring[slot] = (uint16_t)si;
     }
-    __syncthreads();
-    // ---- per-step die roll (:364) of every occupied cell in reach -- recomputed, not communicated
-    const unsigned int n_agent = s_n[0];
-    const unsigned int n_roll = n_agent + s_n[1];
-    for (unsigned int k = tid; k < n_roll; k += NT) {
-        int si, lx, ly;  // shared-memory index and tile coordinates (the ring is at -1 / TW / TH)
-        if (k < n_agent) {
-            const int cl = (int)s_cells[k];
-            ly = cl >> LOG_TW; lx = cl & (TW - 1);
-            si = cl + (ly << 5) + SW + 16;  // (ly + 1) * SW + lx + 16 with SW = TW + 32
-        } else {
-            si = s_ring[k - n_agent];
-            const int r = si / SW;
-            ly = r - 1; lx = si - r * SW - 16;
-        }
-        const uint32_t gx = (x0 + (uint32_t)lx) & (p.W - 1);
-        const uint32_t gy = (p.row0 + y0 + (uint32_t)ly) & (p.HW - 1);
-        const Words w = rng(p, ((uint64_t)gy << p.log2W) | gx, S_ROLL);
-        const uint32_t t = s_tf[si];
-        s_R[si] = R_OCC | ((w.x >> ROLL_SHIFT) << 12) | ((t & TF_D) ? R_DFLAG : 0u) | ((uint32_t)s_st[si] << 3) |
-                  ((t & TF_TRAIT) << 1);
-        if (k < n_agent) s_cells[k] |= w.w << 16;
-    }
+    asm volatile("cp.async.wait_all;");
     __syncthreads();
     // ---- agents: roles, games, terminal rule, travel decision -- one lane per agent, no warp-wide operations
+    const unsigned int n_agent = s_n[0];
     unsigned int n_play_deaths = 0, n_movers = 0;
     for (unsigned int a = tid; a < n_agent; a += NT) {
         const uint32_t ent = s_cells[a];
         const int cl = (int)(ent & 0xFFFFu);
         const uint32_t coins = ent >> 16;
         const int ly = cl >> LOG_TW, lx = cl & (TW - 1);
-        const int si = cl + (ly << 5) + SW + 16;
+        const int si = (ly + 1) * SWR + 4 + lx;
         const uint32_t rme = s_R[si];
         uint32_t rn[8];
 #pragma unroll
-        for (int d = 0; d < 8; ++d) rn[d] = s_R[si + DY(d) * SW + DX(d)];
+        for (int d = 0; d < 8; ++d) rn[d] = s_R[si + DY(d) * SWR + DX(d)];
         const uint32_t tA = rme | R_LOW, tB = (rme & ~R_LOW) - 1u;  // neighbour d challenges me iff rn[d] > (d < 4 ? tA : tB)
         const uint32_t any_nb = (rn[0] | rn[1] | rn[2]) | (rn[3] | rn[4] | rn[5]) | (rn[6] | rn[7]);
         // act[7] / act[0] of the terminal rule come from the roll order alone (get_game_list, :413): a
@@ -305,7 +314,7 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
 #pragma unroll
             for (int d = 0; d < 8; ++d)
                 if (rn[d] & R_DFLAG) {
-                    const uint32_t dn = ((uint32_t)s_tf[si + DY(d) * SW + DX(d)] & TF_D) >> TF_D_SHIFT;
+                    const uint32_t dn = ((uint32_t)p.tfA[nb_local(p, x0 + lx, y0 + ly, d)] & TF_D) >> TF_D_SHIFT;
                     if ((int)dn - 1 < 7 - d) rn[d] = 0u;  // dead before sub-step 7-d: it sends no challenge
                 }
         }
@@ -334,7 +343,7 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
     for (unsigned int k = tid; k < n_mover; k += NT) {
         const int cl = s_mover[k];
         const int ly = cl >> LOG_TW, lx = cl & (TW - 1);
-        const int si = (ly + 1) * SW + lx + 16;
+        const int si = (ly + 1) * SWR + 4 + lx;
         const float e = __fsub_rn(s_e[cl], p.travel_cost);  // :800
         if (e <= 0.0f) {                                    // :801-804
             s_out[cl] = (uint8_t)TF_GHOST;
@@ -345,9 +354,9 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
         s_e[cl] = e;
         uint32_t occ_mask = 0;
 #pragma unroll
-        for (int d = 0; d < 8; ++d) occ_mask |= (s_R[si + DY(d) * SW + DX(d)] >> 31) << d;
-        const Words w = rng(p, gcell_of(p, x0 + lx, y0 + ly), S_ROLL);
-        int l = (int)(w.z >> 29), seq = 0;  // :810
+        for (int d = 0; d < 8; ++d) occ_mask |= (s_R[si + DY(d) * SWR + DX(d)] >> 31) << d;
+        const Words w = rng(p, gcell_of(p, x0 + lx, y0 + ly), S_TRAVEL);
+        int l = (int)(w.y >> 29), seq = 0;  // :810
         const int dir = probe(occ_mask, l, seq);
         if (dir >= 0) {
             s_out[cl] = (uint8_t)(s_out[cl] | TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT));

@@ -31,13 +31,15 @@ constexpr uint32_t TF_D_SHIFT = 3u;
 constexpr uint32_t TF_D = 0x78u;
 
 // ---- Philox stream ids (counter word 3); must equal oracle/pd_oracle.py -----------------
-constexpr uint32_t S_ROLL = 0;    // x>>13: pair-ordering roll (:364)  y: travel priority (:806)  z>>29: travel start dir (:810)
-                                  // w bits 2c / 2c+1: the challenger's / my RANDOM coin (:631 / :664) of the game I
-                                  // respond to in sub-step c -- a game without noise needs no random call of its own
+constexpr uint32_t S_ROLL = 0;    // ONE call per four cells in a row: counter = cell >> 2, the cell's word = word cell & 3.
+                                  // Top 16 bits: pair-ordering roll (:364; a tie is won by the neighbour in a direction
+                                  // >= 4, which replaces the id tie-break of :413).  Bits 2c / 2c+1: the challenger's /
+                                  // my RANDOM coin (:631 / :664) of the game I respond to in sub-step c -- a game
+                                  // without noise needs no random call of its own
 constexpr uint32_t S_NOISE0 = 1;  // +(c>>1); keyed by the RESPONDER's cell: even c: x my noise roll (:611) y the
                                   //     challenger's (:612); odd c: z mine, w the challenger's
-constexpr uint32_t ROLL_SHIFT = 13;  // the pair-ordering roll keeps the top 19 bits of its word; a tie is won by the
-                                     // neighbour in a direction >= 4 (replaces the id tie-break of :413)
+constexpr uint32_t S_TRAVEL = 14; // x: travel priority (:806)  y>>29: travel start dir (:810)
+constexpr uint32_t ROLL_SHIFT = 16;
 constexpr uint32_t S_REPRO = 9;   // x: reproduction claim priority (:1076)  y>>29: start dir (:1079)
 constexpr uint32_t S_MUT = 10;    // mutation rolls (:1263, :1278, :1291-1292), keyed by the parent's cell
 constexpr uint32_t S_PICK = 11;   // replacement picks (:1265, :1281, :1303, :1314)
@@ -169,7 +171,7 @@ __device__ __forceinline__ uint64_t nb_gcell(const Params& p, uint32_t x, uint32
 // ---- the game as the RESPONDER sees it (play_response, :599-689) --------------------------
 // strategies: 0 COOP, 1 DEFECT, 2 TFT (== COOP: its memory is submodel-local and every pair
 // plays once per step, :621-629/:646-661), 3 RANDOM.  `coins` = the w word of the responder's
-// S_ROLL call.  (The dense play sweep has its own table-driven form of this, pd_dense.cuh.)
+// play word.  (The dense play sweep has its own table-driven form of this, pd_dense.cuh.)
 __device__ __forceinline__ float game_payoff(const Params& p, uint64_t my_gcell, int c, uint32_t coins,
                                              uint32_t my_strat, uint32_t my_trait,
                                              uint32_t ch_strat, uint32_t ch_trait) {
@@ -185,7 +187,13 @@ __device__ __forceinline__ float game_payoff(const Params& p, uint64_t my_gcell,
     }
     return p.pay[((uint32_t)i_coop << 1) | (uint32_t)ch_coop];  // :677-689 (my side only)
 }
-// "the neighbour in direction d (roll word rn) is higher than me (roll word r)": it challenges me (:413)
+// the play word of a cell (S_ROLL)
+__device__ __forceinline__ uint32_t play_word(const Params& p, uint64_t gcell) {
+    const Words w = rng(p, gcell >> 2, S_ROLL);
+    const uint32_t k = (uint32_t)gcell & 3u;
+    return k == 0u ? w.x : k == 1u ? w.y : k == 2u ? w.z : w.w;
+}
+// "the neighbour in direction d (play word rn) is higher than me (play word r)": it challenges me (:413)
 __device__ __forceinline__ bool roll_higher(uint32_t rn, uint32_t r, int d) {
     const uint32_t kn = rn >> ROLL_SHIFT, k = r >> ROLL_SHIFT;
     return kn > k || (kn == k && d >= 4);

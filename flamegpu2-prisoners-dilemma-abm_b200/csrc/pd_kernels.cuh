@@ -82,13 +82,12 @@ __global__ void __launch_bounds__(BS) k_risk_resolve(const __grid_constant__ Par
                 float e = __ldcg(p.E0 + cell);
                 const uint32_t my_strat = __ldcg(p.strat + cell);
                 const uint64_t g = gcell_of(p, x, y);
-                const Words wr = rng(p, g, S_ROLL);
-                const uint32_t roll = wr.x, coins = wr.w;
+                const uint32_t roll = play_word(p, g), coins = roll;
                 uint32_t chal = 0;  // bit d: my neighbour d challenges me (:413), in sub-step 7-d
 #pragma unroll
                 for (int d = 0; d < 8; ++d) {
                     if (!(tn[d] & TF_OCC)) continue;
-                    if (roll_higher(rng(p, nb_gcell(p, x, y, d), S_ROLL).x, roll, d)) chal |= 1u << d;
+                    if (roll_higher(play_word(p, nb_gcell(p, x, y, d)), roll, d)) chal |= 1u << d;
                 }
 #pragma unroll
                 for (int d = 0; d < 8; ++d)
@@ -127,11 +126,11 @@ __global__ void __launch_bounds__(BS) k_risk_resolve(const __grid_constant__ Par
             const uint32_t tn = __ldcg(p.tfA + nc);
             if (!(tn & TF_OCC)) continue;
             const uint64_t g = gcell_of(p, x, y);
-            const Words wr = rng(p, g, S_ROLL);  // (recomputed: cheaper than a list round trip for these few)
-            if (!roll_higher(rng(p, nb_gcell(p, x, y, d), S_ROLL).x, wr.x, d)) continue;  // I am the challenger (:413)
+            const uint32_t wr = play_word(p, g);  // (recomputed: cheaper than a list round trip for these few)
+            if (!roll_higher(play_word(p, nb_gcell(p, x, y, d)), wr, d)) continue;  // I am the challenger (:413)
             const uint32_t dn = (tn & TF_D) >> TF_D_SHIFT;
             if (dn != 0u && (int)dn - 1 < c) continue;  // challenger died in an earlier sub-step
-            const float e = __fadd_rn(p.risk_e[i], game_payoff(p, g, c, wr.w, p.strat[cell], t & TF_TRAIT, p.strat[nc], tn & TF_TRAIT));
+            const float e = __fadd_rn(p.risk_e[i], game_payoff(p, g, c, wr, p.strat[cell], t & TF_TRAIT, p.strat[nc], tn & TF_TRAIT));
             if (e <= 0.0f) p.tfA[cell] = (uint8_t)(t | ((uint32_t)(c + 1) << TF_D_SHIFT));
             else p.risk_e[i] = fminf(e, p.max_energy);
         }
@@ -195,7 +194,7 @@ __global__ void __launch_bounds__(BS) k_move_retry(const __grid_constant__ Param
                 if (__ldcg(tf + nb_local(p, x, y, d)) & (TF_OCC | TF_GHOST)) blocked |= 1u << d;
             int l = (int)(st & 7u), seq = (int)((st >> 3) & 7u) + 1;
             if (st & 0x40u) {  // fresh from round 1: it claimed direction l after probe_pos probes (:848-849)
-                const int s0 = (int)(rng(p, gcell_of(p, x, y), S_ROLL).z >> 29);
+                const int s0 = (int)(rng(p, gcell_of(p, x, y), S_TRAVEL).y >> 29);
                 seq = probe_pos(s0, l);
                 l = (l + 1) & 7;
             }

@@ -186,11 +186,20 @@ int prof_end(pd_sim* s, cudaStream_t st) {
     s->ev_used += 2;
     return PD_OK;
 }
-#define PROF(slot, ...)                                      \
-    do {                                                     \
-        if ((rc = prof_begin(s, slot, st))) return rc;       \
-        __VA_ARGS__;                                         \
-        if ((rc = prof_end(s, st))) return rc;               \
+// PDABM_DEBUG_SYNC=1 in the environment: synchronise after every kernel and name the one that failed
+static const bool g_debug_sync = getenv("PDABM_DEBUG_SYNC") != nullptr;
+#define PROF(slot, ...)                                                                              \
+    do {                                                                                             \
+        if ((rc = prof_begin(s, slot, st))) return rc;                                               \
+        __VA_ARGS__;                                                                                 \
+        if ((rc = prof_end(s, st))) return rc;                                                       \
+        if (g_debug_sync) {                                                                          \
+            cudaError_t e_ = cudaStreamSynchronize(st);                                              \
+            if (e_ == cudaSuccess) e_ = cudaGetLastError();                                          \
+            if (e_ != cudaSuccess)                                                                   \
+                return fail(PD_ERR_CUDA, "kernel slot %d of step %u failed: %s", slot, s->step,       \
+                            cudaGetErrorString(e_));                                                 \
+        }                                                                                            \
     } while (0)
 
 int push_step(pd_sim* s, cudaStream_t st) {

@@ -15,7 +15,7 @@ from collections import defaultdict
 import numpy as np
 
 from .philox import philox_scalar
-from .pd_oracle import (Params, prob_threshold, NORMAL_SCALE, S_ROLL, S_NOISE0, ROLL_SHIFT, S_REPRO, S_MUT, S_PICK,
+from .pd_oracle import (Params, prob_threshold, NORMAL_SCALE, S_ROLL, S_NOISE0, S_TRAVEL, ROLL_SHIFT, S_REPRO, S_MUT, S_PICK,
                         S_CULL, S_ENERGY, READY, READY_TO_CHALLENGE, READY_TO_RESPOND,
                         MOVEMENT_UNRESOLVED, MOVING, ATTEMPTING_REPRODUCTION, REPRODUCTION_IMPOSSIBLE,
                         REPRODUCTION_COMPLETE, NEW_AGENT)
@@ -68,9 +68,9 @@ class LiteralModel:
         msgs = {}
         for a in self.agents:                                       # search_for_neighbours :352-372
             a["bucket"] = self.pos_to_bucket_id(a["x"], a["y"])
-            w = self.rng(a["bucket"], S_ROLL)
-            a["roll"] = w[0] >> ROLL_SHIFT                          # :364 (top 19 bits)
-            a["coins"] = w[3] & 0xFFFF                              # the coins of :631 / :664
+            w = self.rng(a["bucket"] >> 2, S_ROLL)[a["bucket"] & 3]   # one call per four cells in a row
+            a["roll"] = w >> ROLL_SHIFT                             # :364 (top 16 bits)
+            a["coins"] = w & 0xFFFF                                 # the coins of :631 / :664
             a["roll_cell"] = a["bucket"]
             msgs[a["bucket"]] = (a["id"], a["roll"])
         for a in self.agents:                                       # get_game_list :373-440
@@ -230,10 +230,10 @@ class LiteralModel:
                     if e <= 0.0:                                    # :801-804
                         continue
                     a["energy"] = e
-                    w = self.rng(a["bucket"], S_ROLL)
-                    a["roll"] = w[1]                                # :806
+                    w = self.rng(a["bucket"], S_TRAVEL)
+                    a["roll"] = w[0]                                # :806
                     a["roll_cell"] = a["bucket"]
-                    a["lma"] = w[2] >> 29                           # :810
+                    a["lma"] = w[1] >> 29                           # :810
                 found, lma, mseq = self._probe(a["nb"], a["lma"], a["mseq"])
                 survivors.append(a)
                 if found is None:                                   # :842-846

@@ -14,15 +14,16 @@ it follows.  Three deliberate restatements (DESIGN.md "Semantics"):
 * all random draws are Philox4x32-10 words keyed (seed; cell, step, stream)
   instead of per-thread cuRAND (model.py:364, :611-612, :631, :664, :806-810,
   :1076-1079, :1236, :1263-1314);
-* the pair-ordering roll of play is the top 19 bits of a Philox word and a tie is
-  won by the neighbour in a direction >= 4 (the reference: a float and the agent
-  id, model.py:413); travel / reproduction claims are ordered by a 32-bit word and
+* ONE Philox call serves the play phase of four cells in a row (counter = cell >> 2,
+  the cell's word is word cell & 3): its top 16 bits are the pair-ordering roll
+  (model.py:364; a tie is won by the neighbour in a direction >= 4 -- the reference:
+  a float and the agent id, :413), its low 16 bits the RANDOM-strategy coins of the
+  games the agent RESPONDS to (:631, :664; bits 2c and 2c+1 for sub-step c), so a
+  game without noise needs no random call of its own; the noise rolls (:611-612)
+  come from four calls per responder (streams 1..4, two sub-steps per call);
+* travel / reproduction claims are ordered by a 32-bit word of a per-cell call and
   ties are broken by the *cell index* the agent stood on when it drew (the
   reference uses the agent id, model.py:929, :1192);
-* the RANDOM-strategy coins of a game (model.py:631, :664) are two bits of the
-  RESPONDER's roll call (bits 2c, 2c+1 of its 4th word for sub-step c), so a game
-  without noise needs no random call of its own; the noise rolls (:611-612) come
-  from four calls per responder (streams 1..4, two sub-steps per call);
 * the list-index cull (model.py:1343, :1354) is replaced by "the surplus
   newborns with the lowest Philox cull priority die" (SURVEY Appendix B-4).
 """
@@ -55,12 +56,13 @@ DY = np.array([-1, 0, 1, -1, 1, -1, 0, 1], dtype=np.int64)
 NDIR = 8  # SPACES_WITHIN_RADIUS, model.py:255
 
 # --- Philox stream ids (4th counter word); step index is the 3rd --------------
-S_ROLL = 0      # w0>>13 pair-ordering roll (:364) w1 travel priority (:806) w2>>29 travel start dir (:810)
-                # w3 bits 2c / 2c+1: the challenger's / my RANDOM coin (:631 / :664) of the game I
-                # respond to in sub-step c
+S_ROLL = 0      # counter = cell >> 2, word = cell & 3: top 16 bits pair-ordering roll (:364), bits 2c /
+                # 2c+1: the challenger's / my RANDOM coin (:631 / :664) of the game I respond to in
+                # sub-step c
 S_NOISE0 = 1    # +(c>>1), keyed by the RESPONDER's cell: even c: w0 my noise roll (:611) w1 the
                 # challenger's (:612); odd c: w2 mine, w3 the challenger's
-ROLL_SHIFT = 13  # the pair-ordering roll keeps the top 19 bits of its word
+ROLL_SHIFT = 16  # the pair-ordering roll is the top half of the cell's word, the coins the low half
+S_TRAVEL = 14   # w0 travel priority (:806) w1>>29 travel start direction (:810)
 S_REPRO = 9     # w0 reproduction claim priority (:1076) w1>>29 start dir (:1079)
 S_MUT = 10      # w0..w3 mutation rolls (:1263, :1278, :1291-1292), keyed by the PARENT's cell
 S_PICK = 11     # w0..w3 replacement-strategy picks (:1265, :1281, :1303, :1314)
@@ -250,6 +252,13 @@ class Oracle:
         return int(self.id.shape[0])
 
     # ------------------------------------------------------------------ init_fn
+    def play_word(self, cell) -> np.ndarray:
+        """The play-phase word of a cell: one S_ROLL call per group of four cells (counter = cell >> 2)."""
+        cell = np.asarray(cell, dtype=np.uint64)
+        w = np.stack(self._rng(cell >> np.uint64(2), S_ROLL), axis=-1)
+        k = (cell & np.uint64(3)).astype(np.int64)
+        return np.take_along_axis(w, k[..., None], axis=-1)[..., 0] if w.ndim > 1 else w[int(k)]
+
     def init_population(self):
         """init_fn.run, model.py:1423-1524 -- Philox-keyed, exact count (B-10)."""
         p, W, cells = self.p, self.W, self.cells
@@ -321,10 +330,10 @@ class Oracle:
     def search_for_neighbours(self):
         """model.py:352-372: bucket id, per-step die roll, post (id, roll) at my bucket."""
         self.bucket = self.x + self.y * self.W                                  # :361
-        w0, _, _, w3 = self._rng(self.bucket, S_ROLL)
-        self.roll = w0 >> np.uint32(ROLL_SHIFT)                                 # :364
+        word = self.play_word(self.bucket)
+        self.roll = word >> np.uint32(ROLL_SHIFT)                               # :364
         self.roll_cell = self.bucket.copy()
-        self.coins = w3 & np.uint32(0xFFFF)
+        self.coins = word & np.uint32(0xFFFF)
         self.msg_id = np.zeros(self.cells, np.int64)                           # player_search_msg
         self.msg_roll = np.zeros(self.cells, np.uint32)
         self.msg_id[self.bucket] = self.id
@@ -515,11 +524,11 @@ class Oracle:
             dies = e <= np.float32(0)                                           # :801-804
             dead[f[dies]] = True
             self.energy[f] = np.where(dies, self.energy[f], e)                  # :805
-            _, w1, w2, _ = self._rng(self.bucket[f], S_ROLL)
-            self.roll[f] = w1                                                   # :806-807
+            w0, w1, _, _ = self._rng(self.bucket[f], S_TRAVEL)
+            self.roll[f] = w0                                                   # :806-807
             self.roll_cell[f] = self.bucket[f]
             lma = lma.copy()
-            lma[fresh] = (w2 >> np.uint32(29)).astype(np.int64)                 # :810
+            lma[fresh] = (w1 >> np.uint32(29)).astype(np.int64)                 # :810
         live = ~dead[sel]
         found, l, seq = self._probe(sel, lma, sub["move_sequence"][sel])
         found &= live

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle.philox import philox_scalar, philox4x32_10
-from oracle.pd_oracle import (Oracle, Params, DX, DY, S_ROLL, S_NOISE0, ROLL_SHIFT, S_REPRO, S_CULL, S_ENERGY,
+from oracle.pd_oracle import (Oracle, Params, DX, DY, S_ROLL, S_NOISE0, S_TRAVEL, ROLL_SHIFT, S_REPRO, S_CULL, S_ENERGY,
                               normal_from_words, prob_threshold, NORMAL_SCALE)
 
 
@@ -27,6 +27,12 @@ def world(W, agents, **kw):
 def words(o, cell, stream, step=None):
     step = o.step_index if step is None else step
     return philox_scalar((cell & 0xFFFFFFFF, cell >> 32, step, stream), (o.k0, o.k1))
+
+
+def play_word(o, cell):
+    """The play-phase word of a cell: one S_ROLL call per four cells in a row (counter = cell >> 2, word cell & 3):
+    top 16 bits = pair-ordering roll, low 16 bits = the RANDOM coins."""
+    return words(o, cell >> 2, S_ROLL)[cell & 3]
 
 
 # ----------------------------------------------------------------------------- RNG pins
@@ -106,7 +112,7 @@ def test_two_agent_play_table(sa, sb):
     o = world(16, [(4, 4, 50.0, 0, [sa] * 4), (5, 4, 60.0, 1, [sb] * 4)])
     o.search_for_neighbours()
     o.get_game_list()
-    roll_a, roll_b = words(o, 4 + 4 * 16, S_ROLL)[0] >> ROLL_SHIFT, words(o, 5 + 4 * 16, S_ROLL)[0] >> ROLL_SHIFT
+    roll_a, roll_b = play_word(o, 4 + 4 * 16) >> ROLL_SHIFT, play_word(o, 5 + 4 * 16) >> ROLL_SHIFT
     assert roll_a != roll_b
     o.pdgame_model()
     a_is_responder = roll_a < roll_b
@@ -122,7 +128,7 @@ def test_two_agent_play_table(sa, sb):
 
 def test_random_strategy_and_noise_use_the_responders_words():
     """RANDOM cooperates iff its coin bit is set (model.py:631, :664): bits 2c (challenger) and 2c+1 (responder)
-    of the 4th word of the RESPONDER's roll call; noise flips a choice iff its word < noise * 2^32 (:638-640,
+    of the RESPONDER's play word; noise flips a choice iff its word < noise * 2^32 (:638-640,
     :672-674): words of the responder's call S_NOISE0 + c//2, (x, y) for even c and (z, w) for odd c, where
     c = direction from challenger to responder."""
     for noise in (0.3, 0.0):
@@ -130,10 +136,10 @@ def test_random_strategy_and_noise_use_the_responders_words():
         o.search_for_neighbours()
         o.get_game_list()
         ca, cb = 4 + 4 * 16, 5 + 5 * 16
-        a_resp = (words(o, ca, S_ROLL)[0] >> ROLL_SHIFT) < (words(o, cb, S_ROLL)[0] >> ROLL_SHIFT)
+        a_resp = (play_word(o, ca) >> ROLL_SHIFT) < (play_word(o, cb) >> ROLL_SHIFT)
         resp_cell = ca if a_resp else cb
         c = 0 if a_resp else 7      # challenger b at (5,5) reaches a at (4,4) in direction 0; a reaches b in 7
-        coins = words(o, resp_cell, S_ROLL)[3]
+        coins = play_word(o, resp_cell) & 0xFFFF
         w = words(o, resp_cell, S_NOISE0 + c // 2)
         my_roll, ch_roll = (w[2], w[3]) if c & 1 else (w[0], w[1])
         thr = prob_threshold(noise)
@@ -146,7 +152,7 @@ def test_random_strategy_and_noise_use_the_responders_words():
 
 
 def test_roll_tie_goes_to_the_neighbour_in_a_direction_ge_4():
-    """The pair-ordering roll keeps 19 bits; on a tie the agent that sees the other in a direction < 4
+    """The pair-ordering roll has 16 bits; on a tie the agent that sees the other in a direction < 4
     challenges (replaces the id tie-break of model.py:413): exactly one challenger per pair, from both sides."""
     for dirn in range(8):
         o = world(16, [(8, 8, 50.0, 0, [0] * 4), (8 + int(DX[dirn]), 8 + int(DY[dirn]), 50.0, 0, [0] * 4)])
@@ -165,7 +171,7 @@ def test_play_death_and_energy_clamp():
     o = world(16, [(4, 4, 0.5, 0, [0] * 4), (5, 4, 149.0, 0, [1] * 4)])
     o.search_for_neighbours()
     o.get_game_list()
-    coop_responds = (words(o, 4 + 64, S_ROLL)[0] >> ROLL_SHIFT) < (words(o, 5 + 64, S_ROLL)[0] >> ROLL_SHIFT)
+    coop_responds = (play_word(o, 4 + 64) >> ROLL_SHIFT) < (play_word(o, 5 + 64) >> ROLL_SHIFT)
     o.pdgame_model()
     if coop_responds:
         assert o.n == 1 and o.stats["play_deaths"] == 1 and float(o.energy[0]) == 149.0
@@ -204,7 +210,7 @@ def test_isolated_agent_moves_one_cell_and_pays():
     from the draw (:810), first free slot = the start; then cost of living (:1357-1368)."""
     o = world(16, [(8, 8, 50.0, 3, [1, 2, 3, 0])])
     cell = 8 + 8 * 16
-    s = words(o, cell, S_ROLL)[2] >> 29
+    s = words(o, cell, S_TRAVEL)[1] >> 29
     st = o.step()
     assert st["movers"] == 1 and st["moved"] == 1
     assert (int(o.x[0]), int(o.y[0])) == (8 + int(DX[s]), 8 + int(DY[s]))
@@ -227,14 +233,14 @@ def test_two_movers_one_target_highest_roll_wins():
     for seed in range(400):
         o = world(16, [(4, 4, 50.0, 0, [0] * 4), (6, 4, 50.0, 0, [0] * 4)], seed=seed)
         ca, cb = 4 + 64, 6 + 64
-        wa, wb = words(o, ca, S_ROLL), words(o, cb, S_ROLL)
-        ta = (4 + int(DX[wa[2] >> 29]), 4 + int(DY[wa[2] >> 29]))
-        tb = (6 + int(DX[wb[2] >> 29]), 4 + int(DY[wb[2] >> 29]))
+        wa, wb = words(o, ca, S_TRAVEL), words(o, cb, S_TRAVEL)
+        ta = (4 + int(DX[wa[1] >> 29]), 4 + int(DY[wa[1] >> 29]))
+        tb = (6 + int(DX[wb[1] >> 29]), 4 + int(DY[wb[1] >> 29]))
         if ta != tb:
             continue
         found = True
         st = o.step()
-        a_wins = (wa[1], ca) > (wb[1], cb)
+        a_wins = (wa[0], ca) > (wb[0], cb)
         pos = {(int(x), int(y)) for x, y in zip(o.x, o.y)}
         assert ta in pos
         winner_start = (4, 4) if a_wins else (6, 4)
