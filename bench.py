@@ -178,6 +178,48 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------- GPU side
+def decomp_parity(world, rank, local_rank, steps=70):
+    """Before a slab run is timed: the same decomposition over the SAME transport (torch.distributed / NCCL) on a
+    small world, checked bit for bit against one handle that steps the whole world (every rank runs its own).
+    70 steps of a 256 x (256 N) world: growth with reproduction retry rounds (global gate), then the cap and the
+    cull (global histogram + candidate gather).  Returns the line's `decomp_parity` string; a mismatch is fatal."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pdabm_b200 import Simulation, SimConfig, DecomposedWorld, DistComm
+    kw = dict(width=256, height=256 * world, seed=77, strategy_per_trait=1, env_noise=0.05, mutation_rate=0.01,
+              device=local_rank)
+    ref = Simulation(SimConfig(**kw))
+    dec = DecomposedWorld(SimConfig(**kw), DistComm())
+    ref.init_population()
+    dec.init_population()
+    ok = True
+    for s in range(steps):
+        ref.step(1)
+        dec.step(1)
+        if s % 10 == 9 or s == steps - 1:
+            a, b = ref.planes(), dec.planes()
+            rows = slice(rank * 256, (rank + 1) * 256)
+            ok &= all(np.array_equal(a[k][rows], b[k]) for k in ("occ", "trait", "strat", "energy", "tf_raw"))
+            ca, na = ref.counts()
+            cb, nb = dec.counts()
+            ok &= na == nb and bool(np.array_equal(ca, cb))
+    retries = dec.retry_rounds_run
+    n_end = ref.counts()[1]
+    ref.close()
+    dec.close()
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if int(t[0]) != 1:
+        if rank == 0:
+            print(json.dumps({"error": f"decomp_parity FAILED: {world} ranks over NCCL differ from the single-handle run"}),
+                  flush=True)
+        sys.exit(3)
+    return (f"bit-identical to the single-handle run: {world} ranks over NCCL, {steps} steps of a 256x{256 * world} "
+            f"per-trait world with noise and mutation ({retries} reproduction retry rounds, cap reached: "
+            f"{n_end} agents), planes and counts compared every 10 steps")
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -191,6 +233,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     slabs = world > 1 and args.partition == "slabs"
+    parity = decomp_parity(world, rank, local_rank) if slabs else None
     if slabs:
         # one world, one row slab per GPU; square for config5, else width x (width * N) so that every
         # GPU owns the same 2^28 cells as the single-GPU run (weak scaling)
@@ -340,6 +383,32 @@ def run_ours(args, rank, world, local_rank):
         also["config2"] = _small_config_line("config2", 500)
         also["config4_16runs"] = _ensemble_line(16, 100)
 
+    # ---- also (N = 8, default workload): BASELINE configs[4] itself -- 65536 x 65536 (2^32 cells) in 8 slabs of 8192 rows
+    if slabs and world == 8 and args.workload == "config3" and not args.no_also:
+        sim.close()
+        w5, ov5, d5 = CONFIG5
+        big = DecomposedWorld(SimConfig(width=w5, height=w5, seed=12345, device=local_rank, **ov5), DistComm())
+        big.init_population()
+        big.step(args.presteps, want_counts=False)
+        big.step(3, want_counts=False)
+        barrier()
+        a5 = big.agent_steps()
+        e50, e51 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e50.record()
+        for _ in range(20):
+            big.step(1, want_counts=False)
+        e51.record()
+        barrier()
+        t5 = torch.tensor([e50.elapsed_time(e51)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        g5 = torch.tensor([big.agent_steps() - a5], dtype=torch.float64, device="cuda")
+        dist.all_reduce(g5, op=dist.ReduceOp.SUM)
+        also = {"config5": {"workload": d5 + f"; one {w5}x{w5} world in 8 row slabs (2^29 cells per GPU)", "steps": 20,
+                            "ms_per_step": float(t5[0]) / 20, "value": float(g5[0]) / (float(t5[0]) / 1e3),
+                            "unit": "agent-steps/s", "cell_steps_per_s": w5 * w5 * 20 / (float(t5[0]) / 1e3),
+                            "agents_at_end": big.counts()[1]}}
+        sim = big
+
     # ---- reduce over ranks: total agent-steps, max time
     if world > 1:
         t = torch.tensor([ms, e2e_s] + legs, dtype=torch.float64, device="cuda")
@@ -411,6 +480,7 @@ def run_ours(args, rank, world, local_rank):
                                    if (kern[dom]["frac_of_hbm_peak"] or 0) < 0.5 else "HBM bandwidth"},
         "kernels": kern,
         "also": also,
+        "decomp_parity": parity,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_agents / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,

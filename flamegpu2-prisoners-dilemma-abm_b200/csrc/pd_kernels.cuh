@@ -672,8 +672,12 @@ __global__ void __launch_bounds__(BS) k_fin_hist(const __grid_constant__ Params 
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     for (unsigned int i = t0; i < 2048; i += gridDim.x * blockDim.x) p.ghist[i] = 0;
     grid_sync(ctr->barrier, gridDim.x);
-    const CullPlan plan = cull_plan(p);
-    if (!(plan.cull && plan.keep > 0)) return;
+    // inside PD_PART_PRE the global population is not known yet: the histogram is computed in any case, so that it
+    // can ride on the same all-reduce as the population (it is final unless further reproduction rounds run)
+    if (!p.hist_force) {
+        const CullPlan plan = cull_plan(p);
+        if (!(plan.cull && plan.keep > 0)) return;
+    }
     unsigned int nb = ctr->nb_n;
     if (nb > p.list_cap) nb = p.list_cap;
     fin_hist(p, nb, p.ghist, s_hist);

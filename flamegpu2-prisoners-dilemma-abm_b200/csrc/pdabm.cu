@@ -355,7 +355,7 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     P.row0 = (cfg->row0 + HW - cfg->ghost_rows) & (HW - 1);  // global row of local row 0
     P.wrap_y = slab ? 0u : 1u;
     P.own_y0 = cfg->ghost_rows; P.own_y1 = cfg->ghost_rows + cfg->rows;
-    P.round0 = 1; P.round1 = 8; P.world = 1; P.cand_cap = 0;
+    P.round0 = 1; P.round1 = 8; P.world = 1; P.cand_cap = 0; P.hist_force = 0;
     P.select_cap = cfg->debug_select_cap ? cfg->debug_select_cap : 0xFFFFFFFFu;
     P.step_log = nullptr; P.log_cap = 0;
     P.glb = nullptr; P.ghist = nullptr; P.cand_out = nullptr; P.cand_all = nullptr;
@@ -626,6 +626,10 @@ int pd_step_part(pd_sim* s, int part, int arg, void* stream, int want_counts) {
         PROF(5, DENSE(k_repro_claim));
         PROF(6, DENSE(k_repro_commit));
         k_publish_gate<<<1, 32, 0, st>>>(P, 0);
+        // the cull histogram of round 1's newborns rides on the same all-reduce as the gate words
+        P.hist_force = 1;
+        PROF(9, { if ((rc = launch_sparse(s, k_fin_hist, st))) return rc; });
+        P.hist_force = 0;
         break;
     }
     case PD_PART_RETRY:
@@ -635,11 +639,11 @@ int pd_step_part(pd_sim* s, int part, int arg, void* stream, int want_counts) {
         k_publish_gate<<<1, 32, 0, st>>>(P, arg);
         P.round0 = 1; P.round1 = 8;
         break;
-    case PD_PART_HIST:  // the reproduction rounds are over: cost of living, then this slab's cull histogram
-        PROF(8, { if ((rc = launch_punish(s, st))) return rc; });
+    case PD_PART_HIST:  // retry rounds added newborns: this slab's cull histogram again
         PROF(9, { if ((rc = launch_sparse(s, k_fin_hist, st))) return rc; });
         break;
-    case PD_PART_CAND:
+    case PD_PART_CAND:  // the reproduction rounds are over: cost of living, then this slab's cull candidates
+        PROF(8, { if ((rc = launch_punish(s, st))) return rc; });
         PROF(9, { if ((rc = launch_sparse(s, k_fin_cand, st))) return rc; });
         break;
     case PD_PART_APPLY:

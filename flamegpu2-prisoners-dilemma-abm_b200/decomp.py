@@ -7,8 +7,11 @@ planes' boundary rows over NVLink) and a handful of tiny collectives for the two
 of the model -- the carrying-capacity gate of the reproduction rounds (exit_god_fn, :1607-1627) and
 the cull (:1339-1356):
 
-    exchange ghost rows -> PRE -> sum(glb) -> 7 x [RETRY r -> sum(glb)] -> HIST -> sum(ghist)
+    exchange ghost rows -> PRE -> sum(glb + ghist, one all-reduce) -> [7 x [RETRY r -> sum(glb)] -> HIST -> sum(ghist)]
         -> CAND -> gather(candidates) -> APPLY [-> sum(counts)]
+
+(the bracketed retry branch only runs while the global population is within the cap, i.e. never in the
+saturated state: a step then costs one halo exchange, one 8 KB all-reduce and one all-gather)
 
 Everything else runs on the slab alone: the ghost zone (64 rows) is wider than the deepest
 dependency cone of one step (8 play sub-steps + 2 sweeps + 7 retry rounds of travel and of
@@ -32,7 +35,7 @@ from .sim import SimConfig, Simulation, PdabmError
 from .dist import slab_rows, ring_neighbours
 
 GHOST_ROWS = 64
-CAND_CAP = 1 << 16
+CAND_CAP = 1 << 14   # keys per slab in the cull's threshold bin: newborns / 2048 (+ Poisson), 9 k at 2^29 cells per slab
 
 
 class _Slab:
@@ -46,8 +49,12 @@ class _Slab:
         self.rank, self.world = rank, world
         self.sim = Simulation(cfg, stream=stream, slab=(row0, rows, ghost_rows))
         dev = self.sim.device
-        self.glb = torch.zeros(PD_GLB_WORDS, dtype=torch.int64, device=dev)
-        self.ghist = torch.zeros(PD_HIST_WORDS, dtype=torch.int32, device=dev)
+        # the gate words and the cull histogram are views of ONE buffer, so that one all-reduce sums both: the
+        # 2048 u32 bins travel as 1024 i64 words (a bin's sum over the slabs is < 2^32, so no carry crosses a word)
+        self.wire = torch.zeros(PD_GLB_WORDS + PD_HIST_WORDS // 2, dtype=torch.int64, device=dev)
+        self.glb = self.wire[:PD_GLB_WORDS]
+        self.ghist = self.wire[PD_GLB_WORDS:].view(torch.int32)
+        self.gate_host = torch.zeros(3, dtype=torch.int64).pin_memory()
         self.cand_out = torch.zeros(1 + cand_cap, dtype=torch.int64, device=dev)
         self.cand_all = torch.zeros(world * (1 + cand_cap), dtype=torch.int64, device=dev)
         self.sim._check(self.sim.lib.pd_bind_comm(self.sim._h, self.glb.data_ptr(), self.ghist.data_ptr(),
@@ -131,7 +138,10 @@ class DecomposedWorld:
 
     def __init__(self, cfg: SimConfig, comm, ghost_rows: int = GHOST_ROWS, cand_cap: int = CAND_CAP,
                  retry_rounds: int = 7, stream=None):
+        import torch
+        self.torch = torch
         self.cfg, self.comm = cfg, comm
+        self.stream = stream
         self.retry_rounds = retry_rounds
         self.slabs = [_Slab(cfg, r, comm.world, ghost_rows, cand_cap, stream) for r in comm.local_ranks]
         self.retry_rounds_run = 0  # reproduction retry rounds executed so far (2 launches + 1 all-reduce each)
@@ -163,34 +173,48 @@ class DecomposedWorld:
             sim.set_state(planes["occ"][rows], planes["energy"][rows], planes["trait"][rows], planes["strat"][rows])
         self._publish_local_counts()
 
+    def _gate(self):
+        """exit_god_fn (model.py:1614-1627) on the host, like the reference: (olds, births, parents still trying),
+        summed over the slabs.  One small pinned copy and one stream synchronisation."""
+        s = self.slabs[0]
+        s.gate_host.copy_(s.glb[:3], non_blocking=True)
+        self.torch.cuda.current_stream(s.sim.device).synchronize()
+        return (int(v) for v in s.gate_host.tolist())
+
     def step(self, n_steps: int = 1, want_counts: bool = True):
+        import contextlib
         comm, slabs = self.comm, self.slabs
-        for k in range(n_steps):
-            wc = want_counts and k + 1 == n_steps
-            comm.exchange(slabs)
-            for s in slabs:
-                s.part(PD_PART_PRE, 0, wc)
-            comm.allreduce([s.glb for s in slabs])
-            for rnd in range(1, self.retry_rounds + 1):
-                # exit_god_fn (model.py:1614-1627) on the host, like the reference: another round only while the
-                # GLOBAL population is within the cap and somebody is still trying.  Reading three words back
-                # costs one stream synchronisation and saves 7 launches + 7 all-reduces in the saturated state.
-                olds, births, active = (int(v) for v in slabs[0].glb[:3].tolist())
-                if olds + births > self.cfg.max_agents or active == 0:
-                    break
+        # everything -- kernels, halo copies, collectives -- is ordered on ONE stream: the handle's, if it has one
+        ctx = self.torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
+        with ctx:
+            for k in range(n_steps):
+                wc = want_counts and k + 1 == n_steps
+                comm.exchange(slabs)
                 for s in slabs:
-                    s.part(PD_PART_RETRY, rnd, wc)
-                comm.allreduce([s.glb for s in slabs])
-                self.retry_rounds_run += 1
-            for s in slabs:
-                s.part(PD_PART_HIST, 0, wc)
-            comm.allreduce([s.ghist for s in slabs])
-            for s in slabs:
-                s.part(PD_PART_CAND, 0, wc)
-            comm.allgather([s.cand_all for s in slabs], [s.cand_out for s in slabs])
-            for s in slabs:
-                s.part(PD_PART_APPLY, 0, wc)
-        comm.allreduce([s.glb[3:] for s in slabs])  # agents + 16 counts of the last step
+                    s.part(PD_PART_PRE, 0, wc)
+                comm.allreduce([s.wire for s in slabs])   # gate words + cull histogram of round 1's newborns
+                retried = False
+                for rnd in range(1, self.retry_rounds + 1):
+                    # another round only while the GLOBAL population is within the cap and somebody is still trying:
+                    # never in the saturated state, where this read is the step's only host synchronisation
+                    olds, births, active = self._gate()
+                    if olds + births > self.cfg.max_agents or active == 0:
+                        break
+                    for s in slabs:
+                        s.part(PD_PART_RETRY, rnd, wc)
+                    comm.allreduce([s.glb for s in slabs])
+                    self.retry_rounds_run += 1
+                    retried = True
+                if retried:   # more newborns than the histogram saw
+                    for s in slabs:
+                        s.part(PD_PART_HIST, 0, wc)
+                    comm.allreduce([s.ghist for s in slabs])
+                for s in slabs:
+                    s.part(PD_PART_CAND, 0, wc)
+                comm.allgather([s.cand_all for s in slabs], [s.cand_out for s in slabs])
+                for s in slabs:
+                    s.part(PD_PART_APPLY, 0, wc)
+            comm.allreduce([s.glb[3:] for s in slabs])  # agents + 16 counts of the last step
 
     def counts(self):
         """Global (population_strat_count[16], agent count) after the last step()."""

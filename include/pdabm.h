@@ -134,11 +134,14 @@ int pd_read_stats(pd_sim* sim, pd_step_stats* out, void* stream);
  * rows + 2*ghost_rows rows: ghost_rows rows of the upper neighbour slab, the owned rows, ghost_rows
  * rows of the lower neighbour slab (periodic ring).  One model step is
  *     caller: refresh the ghost rows of energy/strat/tf from the neighbour slabs (NVLink copy)
- *     PD_PART_PRE            play, all travel rounds, reproduction claims and round 1; publishes glb[0..2]
- *     caller: sum glb over the slabs
- *     PD_PART_RETRY r=1..7   one further reproduction round, gated by the global population; caller sums glb
- *     PD_PART_HIST           cost of living (k_punish), then the cull histogram into ghist;  caller sums ghist
- *     PD_PART_CAND           this slab's cull candidates into cand_out;  caller gathers all blocks into cand_all
+ *     PD_PART_PRE            play, all travel rounds, reproduction claims and round 1; publishes glb[0..2] and
+ *                            the cull histogram of round 1's newborns in ghist
+ *     caller: sum glb and ghist over the slabs (ONE all-reduce if the two are views of one buffer)
+ *     PD_PART_RETRY r=1..7   one further reproduction round, gated by the global population; caller sums glb.
+ *                            Only needed while glb[0] + glb[1] <= max_agents and glb[2] > 0 (exit_god_fn).
+ *     PD_PART_HIST           only if retry rounds ran: the histogram again;  caller sums ghist
+ *     PD_PART_CAND           cost of living (k_punish), then this slab's cull candidates into cand_out;
+ *                            caller gathers all blocks into cand_all
  *     PD_PART_APPLY          cull, bookkeeping; publishes glb[3..19] (agents, 16 counts)
  * The ghost zone is wide enough that every other phase needs no communication (DESIGN.md "Multi-GPU");
  * results are bit-identical to the whole-world run because all draws are keyed by the global cell. */
