@@ -102,25 +102,19 @@ void drop_graphs(pd_sim* s) {  // the captured launches hold plane / list pointe
         if (g) { cudaGraphExecDestroy(g); g = nullptr; }
 }
 
-int alloc_lists(pd_sim* s, uint64_t n_agents_hint) {
-    if (s->lists_allocated) {
-        if (n_agents_hint + 1024 <= s->P.list_cap || s->P.list_cap == s->cells) return PD_OK;
-        // grow: free and reallocate
-        drop_graphs(s);
-        cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.cand);
-        cudaFree(s->P.mv_claim); cudaFree(s->P.rp_claim);
-        cudaFree(s->P.rt_cell); cudaFree(s->P.rt_state); cudaFree(s->P.rt_aux);
-        cudaFree(s->P.nb_cell); cudaFree(s->P.nb_e); cudaFree(s->P.nb_gene);
-        s->lists_allocated = false;
-    }
-    // this handle's share of the global cap (+25 % for density fluctuations between slabs; an overflow
-    // is detected and reported by pd_read_counts)
-    const double share = (double)s->cells / ((double)s->cfg.width * (double)s->P.HW);
-    uint64_t local_max = share >= 1.0 ? s->cfg.max_agents : (uint64_t)((double)s->cfg.max_agents * share * 1.25);
-    uint64_t cap = local_max > n_agents_hint ? local_max : n_agents_hint;
-    cap += 1024;
-    if (cap > s->cells) cap = s->cells;
-    s->P.list_cap = (uint32_t)cap;
+void free_lists(pd_sim* s) {  // cudaFree(nullptr) is a no-op: safe on a partially allocated set
+    cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.cand);
+    cudaFree(s->P.mv_claim); cudaFree(s->P.rp_claim);
+    cudaFree(s->P.rt_cell); cudaFree(s->P.rt_state); cudaFree(s->P.rt_aux);
+    cudaFree(s->P.nb_cell); cudaFree(s->P.nb_e); cudaFree(s->P.nb_gene);
+    s->risk[0] = s->risk[1] = nullptr; s->P.risk_e = nullptr; s->P.cand = nullptr;
+    s->P.mv_claim = s->P.rp_claim = nullptr;
+    s->P.rt_cell = nullptr; s->P.rt_state = s->P.rt_aux = nullptr;
+    s->P.nb_cell = nullptr; s->P.nb_e = nullptr; s->P.nb_gene = nullptr;
+    s->lists_allocated = false;
+}
+
+int alloc_lists_raw(pd_sim* s, uint64_t cap) {
     CK(cudaMalloc(&s->risk[0], cap * 4));
     CK(cudaMalloc(&s->risk[1], cap * 4));
     CK(cudaMalloc(&s->P.risk_e, cap * 4));
@@ -133,6 +127,26 @@ int alloc_lists(pd_sim* s, uint64_t n_agents_hint) {
     CK(cudaMalloc(&s->P.nb_cell, cap * 4));
     CK(cudaMalloc(&s->P.nb_e, cap * 4));
     CK(cudaMalloc(&s->P.nb_gene, cap * 2));
+    return PD_OK;
+}
+
+int alloc_lists(pd_sim* s, uint64_t n_agents_hint) {
+    if (s->lists_allocated) {
+        if (n_agents_hint + 1024 <= s->P.list_cap || s->P.list_cap == s->cells) return PD_OK;
+        drop_graphs(s);  // grow: free and reallocate
+        free_lists(s);
+    }
+    // this handle's share of the global cap (+25 % for density fluctuations between slabs; an overflow
+    // is detected and reported by pd_read_counts)
+    const double share = (double)s->cells / ((double)s->cfg.width * (double)s->P.HW);
+    uint64_t local_max = share >= 1.0 ? s->cfg.max_agents : (uint64_t)((double)s->cfg.max_agents * share * 1.25);
+    uint64_t cap = local_max > n_agents_hint ? local_max : n_agents_hint;
+    cap += 1024;
+    if (cap > s->cells) cap = s->cells;
+    if (cap > 0xFFFFFFFFull) cap = 0xFFFFFFFFull;  // list indices are 32 bit
+    s->P.list_cap = (uint32_t)cap;
+    const int rc = alloc_lists_raw(s, cap);
+    if (rc) { free_lists(s); return rc; }  // nothing of a partial set is kept
     s->lists_allocated = true;
     return PD_OK;
 }
@@ -271,6 +285,9 @@ int run_scan(pd_sim* s, cudaStream_t st) {
     s->P.risk_cur = s->risk[s->risk_cur];
     s->P.risk_next = s->risk[s->risk_cur ^ 1];
     k_begin_step<<<1, 256, 0, st>>>(s->P.ctr, 0);
+    // the overflow flag is sticky within a run only: a (re)initialised state starts clean (the first scan of
+    // pd_sync_state may overflow the initial lists before they are grown and the scan is repeated)
+    CK(cudaMemsetAsync(&s->P.ctr->overflow, 0, sizeof(unsigned int), st));
     const int blocks = (int)((s->cells + NT - 1) / NT < (size_t)(s->n_sms * 16) ? (s->cells + NT - 1) / NT
                                                                                   : (size_t)(s->n_sms * 16));
     k_scan_state<<<blocks, NT, 0, st>>>(s->P, s->cells);
@@ -335,6 +352,11 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
         if (cfg->ghost_rows > cfg->rows || cfg->row0 + cfg->rows > HW || HW % cfg->rows)
             return fail(PD_ERR_INVALID, "slab: need ghost_rows <= rows, rows | world height and row0 + rows <= world height");
     }
+    // cell indices in the lists, the claim entries and the low word of the cull / placement keys are 32 bit
+    if ((uint64_t)W * HW > (1ull << 32))
+        return fail(PD_ERR_INVALID, "world of %u x %u cells exceeds 2^32 cells", W, HW);
+    if ((uint64_t)W * ((uint64_t)cfg->rows + 2ull * cfg->ghost_rows) > 0xFFFFFFFFull && slab)
+        return fail(PD_ERR_INVALID, "slab of %u x %u local cells exceeds 2^32 - 1", W, cfg->rows + 2 * cfg->ghost_rows);
     double wsum = 0;
     for (int i = 0; i < 4; ++i) {
         if (!(cfg->strategy_weights[i] >= 0.0f)) return fail(PD_ERR_INVALID, "strategy_weights must be >= 0");
@@ -345,7 +367,11 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     CK(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(PD_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
     CK(cudaSetDevice(cfg->device));
-    pd_sim* s = new pd_sim();
+    pd_sim* s = new pd_sim();  // value-initialised: every pointer below starts as nullptr
+    struct Guard {             // a failure part-way releases what was allocated so far
+        pd_sim* s;
+        ~Guard() { if (s) pd_destroy(s); }
+    } guard{s};
     s->cfg = *cfg;
     const uint32_t Hl = cfg->rows + 2 * cfg->ghost_rows;  // local rows incl. the ghost zones
     s->cells = (size_t)Hl * W;
@@ -413,8 +439,8 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
         float h_lut[256], *d_lut = nullptr;
         for (uint32_t i = 0; i < 256; ++i) h_lut[i] = lut_entry(P.pay, i);
         CK(cudaMalloc(&d_lut, sizeof h_lut));
-        CK(cudaMemcpy(d_lut, h_lut, sizeof h_lut, cudaMemcpyHostToDevice));
         P.lut = d_lut;
+        CK(cudaMemcpy(d_lut, h_lut, sizeof h_lut, cudaMemcpyHostToDevice));
     }
     CK(cudaMalloc(&P.E1, s->cells * sizeof(float)));
     CK(cudaMalloc(&P.tfB, s->cells));
@@ -422,6 +448,7 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     CK(cudaMemset(P.ctr, 0, sizeof(Counters)));
     CK(cudaMallocHost(&s->h, sizeof(HostOut)));
     memset(s->h, 0, sizeof(HostOut));
+    guard.s = nullptr;
     *out = s;
     return PD_OK;
 }
@@ -434,13 +461,8 @@ int pd_destroy(pd_sim* s) {
     if (s->P.step_log) cudaFree(s->P.step_log);
     cudaFree(s->P.E1); cudaFree(s->P.tfB); cudaFree(s->P.ctr); cudaFree(const_cast<float*>(s->P.lut));
     cudaFree(s->P.seg_mv); cudaFree(s->P.seg_rp);
-    if (s->lists_allocated) {
-        cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.cand);
-        cudaFree(s->P.mv_claim); cudaFree(s->P.rp_claim);
-        cudaFree(s->P.rt_cell); cudaFree(s->P.rt_state); cudaFree(s->P.rt_aux);
-        cudaFree(s->P.nb_cell); cudaFree(s->P.nb_e); cudaFree(s->P.nb_gene);
-    }
-    cudaFreeHost(s->h);
+    free_lists(s);
+    if (s->h) cudaFreeHost(s->h);
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
     delete s;
     return PD_OK;
@@ -772,12 +794,15 @@ int pd_step_host(pd_sim* s, const float* h_e, const uint8_t* h_s, const uint8_t*
 // test hook: Philox known-answer vectors through the device implementation
 int pd_debug_philox(const uint32_t* ctr_key6, uint32_t* out4, int n) {
     uint32_t *d_in = nullptr, *d_out = nullptr;
+    struct Guard {
+        uint32_t *&a, *&b;
+        ~Guard() { cudaFree(a); cudaFree(b); }
+    } guard{d_in, d_out};
     CK(cudaMalloc(&d_in, (size_t)n * 6 * 4));
     CK(cudaMalloc(&d_out, (size_t)n * 4 * 4));
     CK(cudaMemcpy(d_in, ctr_key6, (size_t)n * 6 * 4, cudaMemcpyHostToDevice));
     k_philox_kat<<<(n + 127) / 128, 128>>>(d_in, d_out, n);
     CK(cudaMemcpy(out4, d_out, (size_t)n * 4 * 4, cudaMemcpyDeviceToHost));
-    cudaFree(d_in); cudaFree(d_out);
     return PD_OK;
 }
 

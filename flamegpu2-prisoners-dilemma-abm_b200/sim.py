@@ -165,6 +165,8 @@ class Simulation:
         torch = self.torch
         tf = (np.asarray(occ, np.uint8) * np.uint8(PD_TF_OCCUPIED)) | (np.asarray(trait, np.uint8) & 3)
         tf = np.where(np.asarray(occ) != 0, tf, 0).astype(np.uint8)
+        if self._stream is not None:  # the copies below run on torch's current stream: no step may still be in flight
+            self._stream.synchronize()
         self.tf.copy_(torch.from_numpy(tf))
         self.energy.copy_(torch.from_numpy(np.asarray(energy, np.float32)))
         self.strat.copy_(torch.from_numpy(pack_strategies(strat4)))
@@ -209,14 +211,23 @@ class Simulation:
     def step_index(self, step: int):
         self._check(self.lib.pd_set_step(self._h, int(step)))
 
+    @staticmethod
+    def _ckpt_path(path: str) -> str:
+        return path if path.endswith(".npz") else path + ".npz"  # (np.savez appends the suffix by itself)
+
     def save_checkpoint(self, path: str):
-        """World + step index as one .npz: everything a run needs to continue bit-identically."""
+        """World + step index as one .npz: everything a run needs to continue bit-identically.  (A row slab is
+        checkpointed through its DecomposedWorld: a slab alone does not hold a world.)"""
+        if self.slab is not None:
+            raise PdabmError("save_checkpoint on a row slab: checkpoint the DecomposedWorld instead")
         pl = self.planes()
-        np.savez_compressed(path, occ=pl["occ"], energy=pl["energy"], trait=pl["trait"], strat=pl["strat"],
+        np.savez_compressed(self._ckpt_path(path), occ=pl["occ"], energy=pl["energy"], trait=pl["trait"], strat=pl["strat"],
                             step=np.int64(self.step_index), seed=np.uint64(self.cfg.seed & 0xFFFFFFFFFFFFFFFF))
 
     def load_checkpoint(self, path: str):
-        with np.load(path) as z:
+        if self.slab is not None:
+            raise PdabmError("load_checkpoint on a row slab: restore the DecomposedWorld instead")
+        with np.load(self._ckpt_path(path)) as z:
             if int(z["seed"]) != (self.cfg.seed & 0xFFFFFFFFFFFFFFFF):
                 raise PdabmError("checkpoint was written with a different seed: the run would not continue identically")
             self.set_state(z["occ"], z["energy"], z["trait"], z["strat"])
