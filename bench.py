@@ -50,12 +50,11 @@ WORKLOADS = {
 }
 # algorithmic bytes per cell per launch of each dense sweep (DESIGN.md "Kernels"):
 #   play_travel : read tfA 1 + strat 1 + E0 4, write tfB 1 + E1 4
-#   move_commit : read tfB 1, write tfA 1; plus the movers' payload (~4 % of the cells move: 5 B gathered + 5 B
-#                 scattered each, sector-granular -- ncu's traffic is the honest figure for this kernel)
-#   repro_claim : read tfA 1 + E1 4, write tfB 1
-#   repro_commit: read tfB 1, write tfA 1; plus parents' energy / strategies gathered for ~3.5 % of the cells
-#   punish      : read tfA 1 + E1 4, write tfA 1 + E0 4   (+1 strat when counts are wanted)
-ALG_BYTES = {"play_travel": 11, "move_commit": 2, "repro_claim": 6, "repro_commit": 2, "punish": 10}
+#   claim_punish: read tfB 1 + E1 4, write tfA 1 + E0 4   (+1 strat when counts are wanted)
+# The claim commits (move_commit, repro_commit) are sparse: one thread per claimant (~4 % / ~6 % of the cells),
+# a handful of random 32-byte sectors each -- their cost is DRAM transactions, not bytes per cell, so they carry
+# ncu's measured traffic (profiles/traffic.json) instead of an algorithmic figure.
+ALG_BYTES = {"play_travel": 11, "claim_punish": 10}
 
 
 def measured_peaks():
@@ -433,7 +432,7 @@ def run_ours(args, rank, world, local_rank):
         per = v / max(1, prof_steps)
         ent = {"ms_per_step": per, "share": per / step_ms_sum if step_ms_sum else None}
         if k in ALG_BYTES:
-            b = ALG_BYTES[k] + (1 if (k == "punish" and want_counts) else 0)
+            b = ALG_BYTES[k] + (1 if (k == "claim_punish" and want_counts) else 0)
             ent["alg_bytes_per_cell"] = b
             ent["gbs"] = b * cells / (per * 1e-3) / 1e9 if per > 0 else None
             ent["frac_of_hbm_peak"] = ent["gbs"] / peak if per > 0 else None
@@ -465,7 +464,7 @@ def run_ours(args, rank, world, local_rank):
                                     "one world per GPU (ensemble), no data-path collective" if world > 1 else "single world"),
                    "presteps": args.presteps, "agents_at_start": n_before, "agents_at_end": n_after,
                    "density": n_after / (cells * world if slabs else cells), "counts_every_step": want_counts,
-                   "l2": "state (11 B/cell resident) larger than the 126 MB L2" if cells * 11 > 126e6
+                   "l2": "state (11 B/cell of planes + 8 B/cell claim words resident) larger than the 126 MB L2" if cells * 11 > 126e6
                          else "state fits in L2: HBM roofline figures are not meaningful at this size"},
         "cell_steps_per_s": cells * world * args.steps / secs,
         "step_alg_bytes_per_cell": total_alg, "step_alg_gbs": step_gbs, "step_frac_of_hbm_peak": step_gbs / peak,
@@ -489,9 +488,9 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_ms": legs[0], "step_ms": legs[1], "d2h_ms": legs[2],
                 "h2d_gbs_per_gpu": h2d / (legs[0] * 1e-3) / 1e9 if legs[0] > 0 else None,
                 "d2h_gbs_per_gpu": d2h / (legs[2] * 1e-3) / 1e9 if legs[2] > 0 else None},
-        # per step: 10 kernels (whole world; replayed as one CUDA graph on small worlds), or 14 + 2 per
+        # per step: 9 kernels (whole world; replayed as one CUDA graph on small worlds), or 12 + 2 per
         # reproduction retry round that actually ran (row slab, this rank)
-        "gpu_launches": (14 * args.steps + 2 * retry_rounds) if slabs else 10 * args.steps,
+        "gpu_launches": (12 * args.steps + 2 * retry_rounds) if slabs else 9 * args.steps,
         "graph_replays": replays,
         "clocks": clocks,
         "init_and_presteps_s": init_s,
@@ -658,7 +657,7 @@ def run_config4(args, rank, world, local_rank):
                                        f"{per_gpu} concurrent runs per GPU, one per CUDA stream, counts every step",
                            "runs": per_gpu * world, "presteps": args.presteps,
                            "l2": "each world's state fits in L2: no HBM roofline claim"},
-                "gpu_launches": 10 * args.steps * per_gpu * world}
+                "gpu_launches": 9 * args.steps * per_gpu * world}
         print(json.dumps(line), flush=True)
     for s in sims:
         s.close()

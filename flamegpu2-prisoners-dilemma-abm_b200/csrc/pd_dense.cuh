@@ -1,16 +1,17 @@
-// The three dense sweeps of a step.
+// The two dense sweeps of a step.
 //
-//   k_play_travel   tfA, strat (1-halo), E0 -> tfB, E1     search/game list/8 play sub-steps/first move_request;
-//                                                          the movers that claim a cell go on the travel list
-//   k_repro_claim   tfB (1-halo), E1        -> tfA          neighbourhood_update + first god_go_forth; the parents
-//                                                          that claim a cell go on the reproduction list
-//   k_punish        tfA, E1                 -> tfA, E0      environmental_punishment + counts (cell-local, in place)
+//   k_play_travel   tfA, strat (1-halo), E0 -> tfB, E1     search/game list/8 play sub-steps/first move_request:
+//                                                          a mover posts its claim on the target's word of the claim
+//                                                          plane and goes on the claim list
+//   k_claim_punish  tfB (1-halo), E1        -> tfA, E0     neighbourhood_update + first god_go_forth: a parent posts
+//                                                          its claim and goes on the claim list; fused with
+//                                                          environmental_punishment + counts (cell-local)
 //
-// The claims themselves -- move_response / god_multiply, all 8 rounds of each -- are resolved by the persistent
-// SPARSE kernels of pd_kernels.cuh over those two lists, in place on the flag plane: a claimant reads the claim
-// flags around its target, and only contested targets need the rivals' Philox priorities (recomputed, never
-// communicated).  (Round 1 of both used to be two more dense sweeps that scanned every cell for a 4-5 % claimant
-// rate: 2.6 ms of an 8.2 ms step, issue-bound at 18 of 32 lanes -- profiles/README.md.)
+// The claims themselves -- move_response / god_multiply, all 8 rounds of each -- are resolved by SPARSE kernels
+// (pd_kernels.cuh) over those lists, in place on tfB: a claimant has won iff its target's claim word is still its
+// own (atomic max, pd_device.cuh claim_word), one independent thread per claimant, no barriers.
+// (Round 1 of both used to be two more dense sweeps that staged every tile to resolve a 4-5 % claimant rate:
+// 1.8 ms of a 5.3 ms step, latency-bound on the per-tile barrier phases -- profiles/README.md.)
 //
 // Design rules learned from the profiles:
 //   * u8 planes enter shared memory as 16-byte chunks (interior at column 16 of a TW+32 wide row);
@@ -21,7 +22,7 @@
 //   * ballots / shuffles in a hot loop, nvcc's warp-aggregated atomicAdd(&shared_counter, 1) in divergent code
 //     (use satom_add) and extra __syncthreads() phases with little work in them all cost more than their
 //     instruction count suggests.
-// Every sweep is a pure gather in global memory: a cell is written by its own tile only.
+// Every sweep is a pure gather on the planes: a cell is written by its own tile only.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,27 +33,6 @@ namespace pd {
 constexpr int NT = 256;  // threads per CTA of the dense sweeps
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
-// contest key of a claimant: (priority word, global cell) -- higher wins (:929, :1192)
-struct Key {
-    uint32_t prio;
-    uint64_t gcell;
-};
-__device__ __forceinline__ bool key_gt(const Key& a, const Key& b) {
-    return a.prio > b.prio || (a.prio == b.prio && a.gcell > b.gcell);
-}
-struct TravelKey {
-    __device__ __forceinline__ Key operator()(const Params& p, uint64_t g) const {
-        Key k; k.prio = rng(p, g, S_TRAVEL).x; k.gcell = g; return k;  // :806
-    }
-};
-struct ReproKey {
-    __device__ __forceinline__ Key operator()(const Params& p, uint64_t g) const {
-        Key k; k.prio = rng(p, g, S_REPRO).x; k.gcell = g; return k;  // :1076
-    }
-};
-__device__ __forceinline__ bool claims_dir(uint32_t t, int dir) {
-    return (t & TF_CLAIM) && (int)((t & TF_DIR) >> TF_DIR_SHIFT) == dir;
-}
 // living cost for one agent (environmental_punishment, :1357-1368); returns false if it dies
 __device__ __forceinline__ bool punish(const Params& p, float& e) {
     e = __fsub_rn(fminf(e, p.max_energy), p.cost_of_living);
@@ -339,6 +319,7 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
     __syncthreads();
     // ---- movers: travel cost, death, random start, probe, claim (:794-868)
     const unsigned int n_mover = s_n[2];
+    const uint32_t step = __ldg(&p.ctr->step_no);
     unsigned int n_travel_deaths = 0;
     for (unsigned int k = tid; k < n_mover; k += NT) {
         const int cl = s_mover[k];
@@ -359,7 +340,7 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
         int l = (int)(w.y >> 29), seq = 0;  // :810
         const int dir = probe(occ_mask, l, seq);
         if (dir >= 0) {
-            s_out[cl] = (uint8_t)(s_out[cl] | TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT));
+            prefetch_claim(p.claim + nb_local(p, x0 + lx, y0 + ly, dir));
             s_cells[satom_add(&s_n[3], 1u)] = (uint32_t)cl | ((uint32_t)dir << 16);  // (the agent list is spent)
         }
     }
@@ -375,20 +356,24 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
         const int ly = (i * 4) >> LOG_TW, lx = (i * 4) & (TW - 1);
         *reinterpret_cast<float4*>(p.E1 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = reinterpret_cast<float4*>(s_e)[i];
     }
-    // ---- the claimants of this tile form one contiguous segment of the travel claim list (k_move_commit reads
-    // it back per tile); entry = tile-local cell | direction << 16
-    const unsigned int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    // ---- the claimants of this tile go on the claim list (k_move_commit): cell, claimed direction
     if (n_claim) {  // uniform across the CTA
         __syncthreads();
         const unsigned int base = s_n[1];
         if (base + n_claim > p.list_cap) {
-            if (tid == 0) { atomicExch(&p.ctr->overflow, 1u); p.seg_mv[tile] = make_uint2(0u, 0u); }
+            if (tid == 0) atomicExch(&p.ctr->overflow, 1u);
         } else {
-            for (unsigned int k = tid; k < n_claim; k += NT) p.mv_claim[base + k] = s_cells[k];
-            if (tid == 0) p.seg_mv[tile] = make_uint2(base, n_claim);
+            for (unsigned int k = tid; k < n_claim; k += NT) {
+                const uint32_t ent = s_cells[k], cl = ent & 0xFFFFu;
+                const uint32_t x = x0 + (cl & (TW - 1)), y = y0 + (cl >> LOG_TW);
+                const int dir = (int)(ent >> 16);
+                // :861-868: the request goes to the target cell.  Posted here, after the CTA's last barrier (a barrier
+                // waits for the CTA's outstanding reductions), with the priority drawn again rather than kept
+                post_claim(p.claim + nb_local(p, x, y, dir), claim_word(step, CLAIM_TRAVEL, rng(p, gcell_of(p, x, y), S_TRAVEL).x, dir));
+                p.cl_cell[base + k] = (y << p.log2W) | x;
+                p.cl_dir[base + k] = (uint8_t)dir;
+            }
         }
-    } else if (tid == 0) {
-        p.seg_mv[tile] = make_uint2(0u, 0u);
     }
     if (p.stats && row_owned(p, y0)) {  // tiles are entirely owned or entirely ghost (16-row granularity)
         if (n_play_deaths) atomicAdd(&p.ctr->st_play_deaths, (unsigned long long)n_play_deaths);
@@ -398,38 +383,70 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
 }
 
 // ------------------------------------------------------------------------------------------
-// k_repro_claim (dense sweep 2): neighbourhood_update (:975-1031) + first god_go_forth
-// (:1042-1134).  tfB (1-halo; the travel rounds are over, GHOSTs are free cells again), E1 -> tfA.
-// The parents that claim a cell go on the reproduction list (god_multiply is resolved by
-// k_repro_rounds); the agents of the owned rows are counted (the carrying-capacity gate needs them).
+// k_claim_punish (dense sweep 2): neighbourhood_update (:975-1031) + first god_go_forth (:1042-1134), fused
+// with environmental_punishment (:1339-1371), step_fn's counts (:1405-1419) and the next step's at-risk list.
+// Reads tfB (1-halo; the travel rounds are over, GHOSTs are free cells again) and E1; writes tfA and E0, the
+// canonical state of the next step.
+//   * A parent that finds a free cell posts its claim on it and goes on the claim list (god_multiply is resolved
+//     by k_repro_commit / k_repro_retry); the agents of the owned rows are counted (the carrying-capacity gate).
+//   * The reference charges the cost of living in layer 7, after the god submodel (:2157-2163).  The only thing
+//     the reproduction rounds change about it is the reproduction cost of the parents that win a claim, so
+//     everybody is charged HERE as a non-parent (cell-local: min(e, max) - cost, death at <= 0) and a winner
+//     re-derives its own outcome from E1, which stays read-only (parent_outcome below).  The rounds themselves
+//     run on tfB, where an agent that has just died of the living cost still occupies its cell, as in the
+//     reference; the newborns are exempt (they enter tfA / E0 in k_finalize, if they survive the cull).
+// A slab leaves the state of its ghost rows alone: the next halo exchange overwrites them.
 // ------------------------------------------------------------------------------------------
+struct Outcome {
+    float e;      // energy after the cost of living (0 if dead)
+    bool alive, risk;
+};
+// environmental_punishment for one agent that entered layer 6 with energy e1 (:1357-1368); a parent paid the
+// reproduction cost first (:1211-1213)
+__device__ __forceinline__ Outcome outcome_of(const Params& p, float e1, bool parent) {
+    float e = parent ? __fsub_rn(e1, p.reproduce_cost) : e1;
+    Outcome o;
+    o.alive = punish(p, e);
+    o.e = o.alive ? e : 0.0f;
+    o.risk = o.alive && e <= p.risk_thr;
+    return o;
+}
+
 template <int TW, int TH>
-__global__ void __launch_bounds__(NT) k_repro_claim(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(NT) k_claim_punish(const __grid_constant__ Params p) {
     constexpr int SW = TW + 32, SH = TH + 2, NC = TW * TH;
     __shared__ __align__(16) uint8_t s_tf[SH * SW];
-    __shared__ __align__(16) uint8_t s_out[NC];
     __shared__ uint16_t s_par[NC];
-    __shared__ uint32_t s_claim[NC];
-    __shared__ unsigned int s_n[4];  // 0 parents, 1 claimants, 2 base of this tile's list entries, 3 agents
+    __shared__ uint32_t s_claim[NC];   // claimants: tile-local cell | direction << 16
+    __shared__ uint32_t s_prio[NC];
+    __shared__ uint16_t s_risk[NC];
+    __shared__ unsigned int s_bins[16];
+    __shared__ unsigned int s_n[8];  // 0 parents, 1 claimants, 2 base of the claim entries, 3 agents, 4 at-risk, 5 their base, 6 deaths
     const int tid = threadIdx.x;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    if (tid < 4) s_n[tid] = 0;
+    const bool owned = row_owned(p, y0);  // tiles are entirely owned or entirely ghost (16-row granularity)
+    if (tid < 8) s_n[tid] = 0;
+    if (tid < 16) s_bins[tid] = 0;
     // the energies are requested before the flag tile arrives, so that the two latencies overlap (empty cells
     // hold 0 in E1: loading them is only wasted bandwidth, and only in sparse worlds)
     constexpr int NIT = (NC / 4 + NT - 1) / NT;
     float4 e_pre[NIT];
+    uint32_t st_pre[NIT];
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
         const int i = tid + it * NT;
         e_pre[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < NC / 4 && p.max_children > 0u) {
+        st_pre[it] = 0;
+        if (i < NC / 4) {
             const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
-            e_pre[it] = *reinterpret_cast<const float4*>(p.E1 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx);
+            const size_t off = ((size_t)(y0 + ly) << p.log2W) + x0 + lx;
+            e_pre[it] = *reinterpret_cast<const float4*>(p.E1 + off);
+            if (p.want_counts && owned) st_pre[it] = *reinterpret_cast<const uint32_t*>(p.strat + off);
         }
     }
-    load_tile_vec<TW, TH, 1>(p, p.tfA, s_tf, x0, y0);
+    load_tile_vec<TW, TH, 1>(p, p.tfB, s_tf, x0, y0);
     __syncthreads();
-    unsigned int n_occ = 0;
+    unsigned int n_occ = 0, n_dead = 0;
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
         const int i = tid + it * NT;
@@ -439,19 +456,50 @@ __global__ void __launch_bounds__(NT) k_repro_claim(const __grid_constant__ Para
         const uint32_t t4 = *reinterpret_cast<const uint32_t*>(s_tf + si);
         const uint32_t occ4 = t4 & 0x80808080u;
         n_occ += __popc(occ4);
-        reinterpret_cast<uint32_t*>(s_out)[i] = t4 & (occ4 | (occ4 >> 6) | (occ4 >> 7));  // OCC | trait of occupied cells
+        const float4 e4 = e_pre[it];
         if (occ4 && p.max_children > 0u) {  // :1054
-            const float4 e4 = e_pre[it];
             // :978-979
             const uint32_t par4 = occ4 & ((e4.x >= p.reproduce_min_energy ? 0x80u : 0u) | (e4.y >= p.reproduce_min_energy ? 0x8000u : 0u)
                                           | (e4.z >= p.reproduce_min_energy ? 0x800000u : 0u)
                                           | (e4.w >= p.reproduce_min_energy ? 0x80000000u : 0u));
             for (uint32_t m = par4; m; m &= m - 1) s_par[satom_add(&s_n[0], 1u)] = (uint16_t)(i * 4 + ((__ffs(m) - 1) >> 3));
         }
+        if (owned) {  // ---- cost of living, as non-parents (:1357-1368)
+            float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+            uint32_t dead4 = 0, risk4 = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t bit = 0x80u << (8 * k);
+                float e = ev[k];
+                const bool alive = punish(p, e);
+                if (occ4 & bit) {
+                    if (!alive) dead4 |= bit;
+                    else if (e <= p.risk_thr) risk4 |= bit;
+                    ev[k] = alive ? e : 0.0f;
+                } else {
+                    ev[k] = 0.0f;
+                }
+            }
+            static_assert(TF_OCC == 0x80u && TF_TRAIT == 0x03u, "flag layout");
+            const uint32_t live4 = occ4 & ~dead4;
+            n_dead += __popc(dead4);
+            if (p.want_counts)
+                for (uint32_t m = live4; m; m &= m - 1) {
+                    const int b = (__ffs(m) - 1) >> 3;
+                    atomicAdd(&s_bins[count_bin((st_pre[it] >> (8 * b)) & 0xFFu, (t4 >> (8 * b)) & TF_TRAIT)], 1u);
+                }
+            for (uint32_t m = risk4; m; m &= m - 1) s_risk[satom_add(&s_n[4], 1u)] = (uint16_t)(i * 4 + ((__ffs(m) - 1) >> 3));
+            const size_t off = ((size_t)(y0 + ly) << p.log2W) + x0 + lx;
+            // OCC | trait for the survivors, 0 for the dead, the empty and the vacated
+            *reinterpret_cast<uint32_t*>(p.tfA + off) = t4 & (live4 | (live4 >> 6) | (live4 >> 7));
+            *reinterpret_cast<float4*>(p.E0 + off) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+        }
     }
     if (n_occ) satom_add(&s_n[3], n_occ);
+    if (n_dead) satom_add(&s_n[6], n_dead);
     __syncthreads();
     const unsigned int n_par = s_n[0];
+    const uint32_t step = __ldg(&p.ctr->step_no);
     for (unsigned int k = tid; k < n_par; k += NT) {
         const int cl = s_par[k];
         const int ly = cl / TW, lx = cl - ly * TW;
@@ -465,410 +513,68 @@ __global__ void __launch_bounds__(NT) k_repro_claim(const __grid_constant__ Para
         int l = (int)(w.y >> 29), seq = 0;  // :1079
         const int dir = probe(occ_mask, l, seq);
         if (dir >= 0) {
-            s_out[cl] = (uint8_t)(s_out[cl] | TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT));
-            s_claim[satom_add(&s_n[1], 1u)] = (uint32_t)cl | ((uint32_t)dir << 16);
+            prefetch_claim(p.claim + nb_local(p, x0 + lx, y0 + ly, dir));
+            const unsigned int slot = satom_add(&s_n[1], 1u);
+            s_claim[slot] = (uint32_t)cl | ((uint32_t)dir << 16);
+            s_prio[slot] = w.x;
         }
     }
     __syncthreads();
-    const unsigned int n_claim = s_n[1];
+    const unsigned int n_claim = s_n[1], n_risk = s_n[4];
     if (tid == 0) {
         if (n_claim) s_n[2] = atomicAdd(&p.ctr->rp_n, n_claim);
-        if (s_n[3] && row_owned(p, y0)) atomicAdd(&p.ctr->n_old, (unsigned long long)s_n[3]);
-    }
-    for (int i = tid; i < NC / 16; i += NT) {
-        const int ly = (i * 16) / TW, lx = (i * 16) - ly * TW;
-        *reinterpret_cast<uint4*>(p.tfB + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = reinterpret_cast<uint4*>(s_out)[i];
-    }
-    const unsigned int tile = blockIdx.y * gridDim.x + blockIdx.x;
-    if (n_claim) {  // uniform across the CTA; entry = tile-local cell | direction << 16
-        __syncthreads();
-        const unsigned int base = s_n[2];
-        if (base + n_claim > p.list_cap) {
-            if (tid == 0) { atomicExch(&p.ctr->overflow, 1u); p.seg_rp[tile] = make_uint2(0u, 0u); }
-        } else {
-            for (unsigned int k = tid; k < n_claim; k += NT) p.rp_claim[base + k] = s_claim[k];
-            if (tid == 0) p.seg_rp[tile] = make_uint2(base, n_claim);
-        }
-    } else if (tid == 0) {
-        p.seg_rp[tile] = make_uint2(0u, 0u);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Round 1 of a claim phase, resolved per tile (move_response :881-960, god_multiply :1170-1205).
-// The flag tile with a 2-cell halo is staged in shared memory; every claimant in reach ORs one bit into a
-// shared-memory byte per target (bit j = "my neighbour j claims me"): the tile's own claimants come from the
-// tile's segment of the claim list (full lanes, no scan of the tile), the few in the 2-ring from a scan of the
-// ring's words.  A target with one bit has its winner; only targets with >= 2 bits need the claimants' Philox
-// priorities (recomputed; winner_of caches the result by collapsing the byte to the winner's bit -- every thread
-// that races on it writes the same value).  A claimant with direction d won iff its target's winner is 7-d.
-// The first claimant to hit a target inside the tile also lists it, so the claimed cells need no scan either.
-// ------------------------------------------------------------------------------------------
-template <int TW, int TH>
-struct ClaimTile {
-    static constexpr int SW = TW + 32, SH = TH + 4, NC = TW * TH;
-    // one claim of the claimant at shared-memory cell (r, c) towards direction d
-    static __device__ __forceinline__ void scatter(uint8_t* s_cl, uint16_t* s_tgt, unsigned int* n_tgt, int r, int c, int d) {
-        const int rr = r + DY(d), cc = c + DX(d);
-        // only targets inside tile + 1-ring matter (rows 1..TH+2, columns 15..TW+16)
-        if (rr < 1 || rr > TH + 2 || cc < 15 || cc > TW + 16) return;
-        const int st = rr * SW + cc;
-        const unsigned int sh = 8u * (unsigned int)(st & 3);
-        const unsigned int old = atomicOr(reinterpret_cast<unsigned int*>(s_cl) + (st >> 2), (1u << (7 - d)) << sh);
-        if (((old >> sh) & 0xFFu) == 0u && rr >= 2 && rr <= TH + 1 && cc >= 16 && cc <= TW + 15)
-            s_tgt[satom_add(n_tgt, 1u)] = (uint16_t)((rr - 2) * TW + (cc - 16));
-    }
-    // the claimants of the 2-ring around the tile: scan its words for CLAIM flags
-    static __device__ __forceinline__ void scatter_ring(const uint8_t* s_tf, uint8_t* s_cl, uint16_t* s_tgt, unsigned int* n_tgt) {
-        constexpr int WROW = (TW + 8) / 4;          // words 12..TW+19 of a ring row
-        constexpr int NW = 4 * WROW + 2 * TH;       // 4 full rows + 2 words per tile row
-        for (int i = threadIdx.x; i < NW; i += NT) {
-            int r, c0;
-            if (i < 4 * WROW) {
-                const int q = i / WROW;
-                r = q < 2 ? q : TH + q;             // rows 0, 1, TH+2, TH+3
-                c0 = 12 + 4 * (i - q * WROW);
-            } else {
-                const int k = i - 4 * WROW;
-                r = 2 + (k >> 1);
-                c0 = (k & 1) ? TW + 16 : 12;
-            }
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(s_tf + r * SW + c0);
-            for (uint32_t cm = w & 0x40404040u; cm; cm &= cm - 1) {
-                const int b = (__ffs(cm) - 1) >> 3;
-                scatter(s_cl, s_tgt, n_tgt, r, c0 + b, (int)(((w >> (8 * b)) & TF_DIR) >> TF_DIR_SHIFT));
-            }
-        }
-    }
-    // winning neighbour index of the claimed cell at shared index st (highest (priority, cell), :929, :1192)
-    template <typename KeyFn>
-    static __device__ __forceinline__ int winner_of(const Params& p, uint8_t* s_cl, int st, uint32_t x0, uint32_t y0, KeyFn keyfn) {
-        uint32_t m = s_cl[st];
-        if (!(m & (m - 1u))) return __ffs(m) - 1;  // a single claimant
-        const int r = st / SW, c = st - r * SW;
-        const uint32_t tx = (x0 + (uint32_t)(c - 16)) & (p.W - 1);
-        // local row of the claimed cell (may be -1 or H in the ring): only used through nb_gcell, which maps
-        // it to the GLOBAL row modulo the world height
-        const uint32_t ty = p.wrap_y ? ((y0 + (uint32_t)(r - 2)) & (p.H - 1)) : (y0 + (uint32_t)(r - 2));
-        int best = -1;
-        Key bk;
-        while (m) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            const Key k2 = keyfn(p, nb_gcell(p, tx, ty, j));
-            if (best < 0 || key_gt(k2, bk)) { bk = k2; best = j; }
-        }
-        s_cl[st] = (uint8_t)(1u << best);
-        return best;
-    }
-};
-
-// the tile's losers join the retry list of the sparse rounds; state byte: 0x80 active | 0x40 fresh | claimed direction
-template <int TW>
-__device__ __forceinline__ void append_losers(const Params& p, unsigned int* rt_n, const uint16_t* s_lost, const uint8_t* s_lost_dir,
-                                              unsigned int n_lost, unsigned int* s_base, uint32_t x0, uint32_t y0) {
-    if (n_lost == 0) return;  // uniform across the CTA
-    if (threadIdx.x == 0) *s_base = atomicAdd(rt_n, n_lost);
-    __syncthreads();
-    const unsigned int base = *s_base;
-    if (base + n_lost > p.list_cap) {
-        if (threadIdx.x == 0) atomicExch(&p.ctr->overflow, 1u);
-        return;
-    }
-    for (unsigned int k = threadIdx.x; k < n_lost; k += NT) {
-        const uint32_t cl = s_lost[k];
-        const uint32_t ly = cl / TW, lx = cl - ly * TW;
-        p.rt_cell[base + k] = ((y0 + ly) << p.log2W) | (x0 + lx);
-        p.rt_state[base + k] = (uint8_t)(0xC0u | (uint32_t)s_lost_dir[k]);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_move_commit (dense sweep 2): move_response (:881-960), round 1.  tfB (2-halo) -> tfA.
-// A claimant looks up its target's winner and either relocates -- it PUSHES its energy / strategies into the
-// target cell (requested before the flag tile arrives, so no load sits between two barriers) and leaves a GHOST
-// that keeps blocking movers this step (quirk B-13) -- or joins the retry list (k_move_retry).  The tile that
-// owns the target writes the target's flag byte.
-// ------------------------------------------------------------------------------------------
-template <int TW, int TH>
-__global__ void __launch_bounds__(NT, 8) k_move_commit(const __grid_constant__ Params p) {
-    using CT = ClaimTile<TW, TH>;
-    constexpr int SW = CT::SW, SH = CT::SH, NC = CT::NC;
-    __shared__ __align__(16) uint8_t s_tf[SH * SW];
-    __shared__ __align__(16) uint8_t s_cl[SH * SW];
-    __shared__ __align__(16) uint8_t s_out[NC];
-    __shared__ uint16_t s_tgt[NC];
-    __shared__ uint16_t s_lost[NC];
-    __shared__ uint8_t s_lost_dir[NC];
-    __shared__ unsigned int s_n[4];  // 0 claimed cells, 1 lost, 2 base
-    const int tid = threadIdx.x;
-    const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    const uint2 seg = p.seg_mv[blockIdx.y * gridDim.x + blockIdx.x];
-    if (tid < 4) s_n[tid] = 0;
-    // my claimant (the tile's first NT; more are rare and take the loop below) and its payload
-    uint32_t ent0 = 0, st0 = 0;
-    float e0 = 0.0f;
-    if ((unsigned int)tid < seg.y) {
-        ent0 = p.mv_claim[seg.x + tid];
-        const uint32_t cl = ent0 & 0xFFFFu;
-        const size_t cell = ((size_t)(y0 + cl / TW) << p.log2W) + x0 + cl % TW;
-        e0 = p.E1[cell];
-        st0 = p.strat[cell];
-    }
-    load_tile_vec<TW, TH, 2>(p, p.tfB, s_tf, x0, y0);
-    for (int i = tid; i < SH * SW / 16; i += NT) reinterpret_cast<uint4*>(s_cl)[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    for (int i = tid; i < NC / 16; i += NT) {  // OCC | GHOST | trait
-        const int ly = (i * 16) / TW, lx = (i * 16) - ly * TW;
-        uint4 v = *reinterpret_cast<const uint4*>(s_tf + (ly + 2) * SW + lx + 16);
-        v.x &= 0x87878787u; v.y &= 0x87878787u; v.z &= 0x87878787u; v.w &= 0x87878787u;
-        reinterpret_cast<uint4*>(s_out)[i] = v;
-    }
-    for (unsigned int k = tid; k < seg.y; k += NT) {
-        const uint32_t ent = k == (unsigned int)tid ? ent0 : p.mv_claim[seg.x + k];
-        const int cl = (int)(ent & 0xFFFFu);
-        CT::scatter(s_cl, s_tgt, &s_n[0], cl / TW + 2, cl % TW + 16, (int)(ent >> 16));
-    }
-    CT::scatter_ring(s_tf, s_cl, s_tgt, &s_n[0]);
-    __syncthreads();
-    for (unsigned int k = tid; k < seg.y; k += NT) {  // the claimants of this tile
-        const bool first = k == (unsigned int)tid;
-        const uint32_t ent = first ? ent0 : p.mv_claim[seg.x + k];
-        const int cl = (int)(ent & 0xFFFFu), d = (int)(ent >> 16);
-        const int ly = cl / TW, lx = cl - ly * TW;
-        const int st = (ly + 2 + DY(d)) * SW + lx + 16 + DX(d);
-        if (CT::winner_of(p, s_cl, st, x0, y0, TravelKey()) == 7 - d) {  // relocates (:946-956)
-            const size_t cell = ((size_t)(y0 + ly) << p.log2W) + x0 + lx;
-            const uint32_t tgt = nb_local(p, x0 + lx, y0 + ly, d);
-            p.E1[tgt] = first ? e0 : p.E1[cell];
-            p.strat[tgt] = (uint8_t)(first ? st0 : (uint32_t)p.strat[cell]);
-            s_out[cl] = (uint8_t)TF_GHOST;  // still blocks movers this step (B-13)
-        } else {                            // :940-943 -> retry with the same roll
-            const unsigned int slot = satom_add(&s_n[1], 1u);
-            s_lost[slot] = (uint16_t)cl;
-            s_lost_dir[slot] = (uint8_t)d;
-        }
-    }
-    const unsigned int n_tgt = s_n[0];
-    for (unsigned int k = tid; k < n_tgt; k += NT) {  // the claimed cells of this tile: the winner's flag byte
-        const int cl = s_tgt[k];
-        const int ly = cl / TW, lx = cl - ly * TW;
-        const int si = (ly + 2) * SW + lx + 16;
-        const int j = CT::winner_of(p, s_cl, si, x0, y0, TravelKey());
-        s_out[cl] = (uint8_t)(TF_OCC | ((uint32_t)s_tf[si + DY(j) * SW + DX(j)] & TF_TRAIT));
-    }
-    __syncthreads();
-    for (int i = tid; i < NC / 16; i += NT) {
-        const int ly = (i * 16) / TW, lx = (i * 16) - ly * TW;
-        *reinterpret_cast<uint4*>(p.tfA + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = reinterpret_cast<uint4*>(s_out)[i];
-    }
-    append_losers<TW>(p, &p.ctr->rt_n[0], s_lost, s_lost_dir, s_n[1], &s_n[2], x0, y0);
-    if (p.stats && tid == 0 && n_tgt && row_owned(p, y0)) atomicAdd(&p.ctr->st_moved, (unsigned long long)n_tgt);
-}
-
-// ------------------------------------------------------------------------------------------
-// k_repro_commit (dense sweep 4): god_multiply (:1144-1335), round 1.  tfB (2-halo) -> tfA.
-// A winner is flagged PARENT (k_punish charges the reproduction cost before the cost of living: E1 stays
-// read-only) and makes its child from its own energy / strategies (requested before the flag tile arrives);
-// a loser joins the retry list (k_repro_retry).  The child only goes on the newborn list, with its energy and
-// strategies: near the carrying capacity almost every newborn is culled in the same step, so it enters the
-// planes in k_finalize if it survives, or when retry rounds must see its cell blocked.
-// ------------------------------------------------------------------------------------------
-template <int TW, int TH>
-__global__ void __launch_bounds__(NT, 6) k_repro_commit(const __grid_constant__ Params p) {
-    using CT = ClaimTile<TW, TH>;
-    constexpr int SW = CT::SW, SH = CT::SH, NC = CT::NC;
-    __shared__ __align__(16) uint8_t s_tf[SH * SW];
-    __shared__ __align__(16) uint8_t s_cl[SH * SW];
-    __shared__ __align__(16) uint8_t s_out[NC];
-    __shared__ uint16_t s_tgt[NC];
-    __shared__ uint16_t s_lost[NC];
-    __shared__ uint8_t s_lost_dir[NC];
-    // a birth needs a parent in the tile AND a distinct empty cell in tile + 1-ring
-    constexpr int NBMAX = NC / 2 + TW + TH + 8;
-    __shared__ uint32_t s_birth[NBMAX];   // local plane index of the child's cell (it may lie in a neighbouring tile)
-    __shared__ float s_birth_e[NBMAX];
-    __shared__ uint16_t s_birth_g[NBMAX];
-    __shared__ unsigned int s_n[4];  // 0 claimed cells, 1 lost, 2 base, 3 births listed
-    __shared__ unsigned int s_nb_base;
-    const int tid = threadIdx.x;
-    const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    const uint2 seg = p.seg_rp[blockIdx.y * gridDim.x + blockIdx.x];
-    if (tid < 4) s_n[tid] = 0;
-    uint32_t ent0 = 0, st0 = 0;
-    float e0 = 0.0f;
-    if ((unsigned int)tid < seg.y) {
-        ent0 = p.rp_claim[seg.x + tid];
-        const uint32_t cl = ent0 & 0xFFFFu;
-        const size_t cell = ((size_t)(y0 + cl / TW) << p.log2W) + x0 + cl % TW;
-        e0 = p.E1[cell];
-        st0 = p.strat[cell];
-    }
-    load_tile_vec<TW, TH, 2>(p, p.tfB, s_tf, x0, y0);
-    for (int i = tid; i < SH * SW / 16; i += NT) reinterpret_cast<uint4*>(s_cl)[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    for (int i = tid; i < NC / 16; i += NT) {  // OCC | trait
-        const int ly = (i * 16) / TW, lx = (i * 16) - ly * TW;
-        uint4 v = *reinterpret_cast<const uint4*>(s_tf + (ly + 2) * SW + lx + 16);
-        v.x &= 0x83838383u; v.y &= 0x83838383u; v.z &= 0x83838383u; v.w &= 0x83838383u;
-        reinterpret_cast<uint4*>(s_out)[i] = v;
-    }
-    for (unsigned int k = tid; k < seg.y; k += NT) {
-        const uint32_t ent = k == (unsigned int)tid ? ent0 : p.rp_claim[seg.x + k];
-        const int cl = (int)(ent & 0xFFFFu);
-        CT::scatter(s_cl, s_tgt, &s_n[0], cl / TW + 2, cl % TW + 16, (int)(ent >> 16));
-    }
-    CT::scatter_ring(s_tf, s_cl, s_tgt, &s_n[0]);
-    __syncthreads();
-    for (unsigned int k = tid; k < seg.y; k += NT) {  // the parents of this tile
-        const bool first = k == (unsigned int)tid;
-        const uint32_t ent = first ? ent0 : p.rp_claim[seg.x + k];
-        const int cl = (int)(ent & 0xFFFFu), d = (int)(ent >> 16);
-        const int ly = cl / TW, lx = cl - ly * TW;
-        const int si = (ly + 2) * SW + lx + 16;
-        if (CT::winner_of(p, s_cl, si + DY(d) * SW + DX(d), x0, y0, ReproKey()) == 7 - d) {
-            // REPRODUCTION_COMPLETE (:1211-1213, :1331); the child (:1216-1328): my trait, its own energy and strategies
-            const uint32_t x = x0 + lx, y = y0 + ly;
-            const size_t cell = ((size_t)y << p.log2W) | x;
-            const uint32_t trait = (uint32_t)s_tf[si] & TF_TRAIT;
-            const float pe = __fsub_rn(first ? e0 : p.E1[cell], p.reproduce_cost);
-            float ce;
-            uint32_t cs;
-            make_child(p, gcell_of(p, x, y), first ? st0 : (uint32_t)p.strat[cell], trait, pe, ce, cs);
-            s_out[cl] = (uint8_t)(s_out[cl] | TF_PARENT);
-            const uint32_t tgt = nb_local(p, x, y, d);
-            if (row_owned(p, tgt >> p.log2W)) {  // a child in the ghost zone belongs to the neighbour slab
-                const unsigned int slot = satom_add(&s_n[3], 1u);
-                s_birth[slot] = tgt;
-                s_birth_e[slot] = ce;
-                s_birth_g[slot] = (uint16_t)(cs | (trait << 8));
-            }
-        } else {  // stays ATTEMPTING_REPRODUCTION (:1203-1205)
-            const unsigned int slot = satom_add(&s_n[1], 1u);
-            s_lost[slot] = (uint16_t)cl;
-            s_lost_dir[slot] = (uint8_t)d;
-        }
-    }
-    if (!row_owned(p, y0)) {
-        // ghost tile of a slab (tiles are entirely owned or entirely ghost, 16-row granularity): the children
-        // born here are listed by the slab that owns these rows; here they only have to block their cells
-        const unsigned int n_tgt = s_n[0];
-        for (unsigned int k = tid; k < n_tgt; k += NT) {
-            const int cl = s_tgt[k];
-            const int ly = cl / TW, lx = cl - ly * TW;
-            const int si = (ly + 2) * SW + lx + 16;
-            const int j = CT::winner_of(p, s_cl, si, x0, y0, ReproKey());
-            s_out[cl] = (uint8_t)(TF_OCC | TF_NEWBORN | ((uint32_t)s_tf[si + DY(j) * SW + DX(j)] & TF_TRAIT));
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < NC / 16; i += NT) {
-        const int ly = (i * 16) / TW, lx = (i * 16) - ly * TW;
-        *reinterpret_cast<uint4*>(p.tfA + ((size_t)(y0 + ly) << p.log2W) + x0 + lx) = reinterpret_cast<uint4*>(s_out)[i];
-    }
-    const unsigned int n_birth = s_n[3];
-    if (tid == 0 && n_birth) s_nb_base = atomicAdd(&p.ctr->nb_n, n_birth);
-    append_losers<TW>(p, &p.ctr->rt_n[1], s_lost, s_lost_dir, s_n[1], &s_n[2], x0, y0);
-    if (n_birth) {  // uniform across the CTA
-        __syncthreads();
-        const unsigned int base = s_nb_base;
-        if (base + n_birth > p.list_cap) {
-            if (tid == 0) atomicExch(&p.ctr->overflow, 1u);
-        } else {
-            for (unsigned int k = tid; k < n_birth; k += NT) {
-                p.nb_cell[base + k] = s_birth[k];
-                p.nb_e[base + k] = s_birth_e[k];
-                p.nb_gene[base + k] = s_birth_g[k];
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_punish (dense sweep 3): environmental_punishment (:1339-1371) + step_fn's counts (:1405-1419) + the next
-// step's at-risk list.  Cell-local and in place: tfA, E1 -> tfA, E0.  Runs after ALL reproduction rounds, like
-// the reference's layer 7 after the god submodel (:2157-2163); the newborns are exempt -- they are either not in
-// the planes yet (k_finalize admits the ones that survive the cull) or flagged NEWBORN (when retry rounds ran).
-// A slab skips its ghost rows: the next halo exchange overwrites them.
-// ------------------------------------------------------------------------------------------
-constexpr int PUNISH_CELLS = NT * 16;  // per CTA
-
-__global__ void __launch_bounds__(NT) k_punish(const __grid_constant__ Params p) {
-    __shared__ uint32_t s_risk[PUNISH_CELLS];
-    __shared__ unsigned int s_bins[16];
-    __shared__ unsigned int s_n[4];  // 0 at-risk, 1 base, 2 deaths
-    const int tid = threadIdx.x;
-    if (tid < 16) s_bins[tid] = 0;
-    if (tid < 4) s_n[tid] = 0;
-    __syncthreads();
-    const size_t cell0 = ((size_t)p.own_y0 << p.log2W) + (size_t)blockIdx.x * PUNISH_CELLS + (size_t)tid * 16;
-    const size_t cell_end = (size_t)p.own_y1 << p.log2W;
-    unsigned int n_dead = 0;
-    if (cell0 < cell_end) {
-        const uint4 t16 = *reinterpret_cast<const uint4*>(p.tfA + cell0);
-        const uint32_t tw[4] = {t16.x, t16.y, t16.z, t16.w};
-        uint32_t ow[4];
-        uint4 s16 = make_uint4(0, 0, 0, 0);
-        if (p.want_counts) s16 = *reinterpret_cast<const uint4*>(p.strat + cell0);
-        const uint32_t sw[4] = {s16.x, s16.y, s16.z, s16.w};
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const uint32_t t4 = tw[h];
-            const uint32_t occ4 = t4 & 0x80808080u;
-            const uint32_t newborn4 = (t4 << 5) & occ4;  // TF_NEWBORN (bit 2) of occupied cells
-            const uint32_t pay4 = occ4 & ~newborn4;
-            const uint32_t parent4 = (t4 << 4) & pay4;   // TF_PARENT (bit 3): reproduced this step
-            float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (occ4) e4 = *reinterpret_cast<const float4*>(p.E1 + cell0 + h * 4);
-            float ev[4] = {e4.x, e4.y, e4.z, e4.w};
-            uint32_t dead4 = 0, risk4 = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t bit = 0x80u << (8 * k);
-                float e = ev[k];
-                if (parent4 & bit) e = __fsub_rn(e, p.reproduce_cost);  // :1211-1213 (layer 6 before layer 7)
-                const bool alive = punish(p, e);                        // :1357-1366
-                if (pay4 & bit) {
-                    if (!alive) dead4 |= bit;
-                    else if (e <= p.risk_thr) risk4 |= bit;
-                    ev[k] = alive ? e : 0.0f;
-                } else {
-                    ev[k] = 0.0f;  // empty, or a flagged newborn (its energy is on the newborn list)
-                }
-            }
-            static_assert(TF_OCC == 0x80u && TF_NEWBORN == 0x04u && TF_PARENT == 0x08u && TF_TRAIT == 0x03u, "flag layout");
-            const uint32_t live4 = pay4 & ~dead4;
-            const uint32_t keep4 = live4 | newborn4;
-            // OCC | trait for the survivors, OCC | NEWBORN | trait for flagged newborns, 0 for the dead and the empty
-            ow[h] = t4 & (keep4 | (keep4 >> 6) | (keep4 >> 7) | (newborn4 >> 5));
-            n_dead += __popc(dead4);
-            if (p.want_counts)
-                for (uint32_t m = live4; m; m &= m - 1) {
-                    const int b = (__ffs(m) - 1) >> 3;
-                    atomicAdd(&s_bins[count_bin((sw[h] >> (8 * b)) & 0xFFu, (t4 >> (8 * b)) & TF_TRAIT)], 1u);
-                }
-            for (uint32_t m = risk4; m; m &= m - 1)
-                s_risk[satom_add(&s_n[0], 1u)] = (uint32_t)(cell0 + h * 4 + ((__ffs(m) - 1) >> 3));
-            *reinterpret_cast<float4*>(p.E0 + cell0 + h * 4) = make_float4(ev[0], ev[1], ev[2], ev[3]);
-        }
-        *reinterpret_cast<uint4*>(p.tfA + cell0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-    }
-    if (n_dead) satom_add(&s_n[2], n_dead);
-    __syncthreads();
-    const unsigned int n_risk = s_n[0];
-    if (tid == 0) {
-        if (n_risk) s_n[1] = atomicAdd(&p.ctr->risk_next_n, n_risk);
-        if (s_n[2]) atomicAdd(&p.ctr->living_deaths, (unsigned long long)s_n[2]);
+        if (n_risk) s_n[5] = atomicAdd(&p.ctr->risk_next_n, n_risk);
+        if (s_n[3] && owned) atomicAdd(&p.ctr->n_old, (unsigned long long)s_n[3]);
+        if (s_n[6]) atomicAdd(&p.ctr->living_deaths, (unsigned long long)s_n[6]);
     }
     if (p.want_counts && tid < 16 && s_bins[tid]) atomicAdd(&p.ctr->bins[tid], (unsigned long long)s_bins[tid]);
-    if (n_risk) {  // uniform across the CTA
-        __syncthreads();
-        const unsigned int base = s_n[1];
+    if (n_claim == 0 && n_risk == 0) return;  // uniform across the CTA
+    __syncthreads();
+    if (n_claim) {
+        const unsigned int base = s_n[2];
+        if (base + n_claim > p.list_cap) {
+            if (tid == 0) atomicExch(&p.ctr->overflow, 1u);
+        } else {
+            for (unsigned int k = tid; k < n_claim; k += NT) {
+                const uint32_t ent = s_claim[k], cl = ent & 0xFFFFu;
+                const uint32_t x = x0 + cl % TW, y = y0 + cl / TW;
+                const int dir = (int)(ent >> 16);
+                // :1123-1130: the request goes to the target cell (posted after the CTA's last barrier: a barrier
+                // waits for the CTA's outstanding reductions)
+                post_claim(p.claim + nb_local(p, x, y, dir), claim_word(step, CLAIM_REPRO, s_prio[k], dir));
+                p.cl_cell[base + k] = (y << p.log2W) | x;
+                p.cl_dir[base + k] = (uint8_t)dir;
+            }
+        }
+    }
+    if (n_risk) {
+        const unsigned int base = s_n[5];
         if (base + n_risk > p.list_cap) {
             if (tid == 0) atomicExch(&p.ctr->overflow, 1u);
         } else {
-            for (unsigned int k = tid; k < n_risk; k += NT) p.risk_next[base + k] = s_risk[k];
+            for (unsigned int k = tid; k < n_risk; k += NT) {
+                const uint32_t cl = s_risk[k];
+                p.risk_next[base + k] = ((y0 + cl / TW) << p.log2W) | (x0 + cl % TW);
+            }
         }
+    }
+}
+
+// A parent that has won its claim (god_multiply, :1211-1213) re-derives its layer-7 outcome: k_claim_punish
+// charged it as a non-parent.  e1 = its energy when it entered layer 6 (E1 is read-only), `cell` its cell, owned
+// rows only.  Almost always only the energy changes; deaths, counts and the at-risk list are corrected if not.
+__device__ __forceinline__ void parent_outcome(const Params& p, uint32_t cell, float e1, uint32_t strat, uint32_t trait) {
+    const Outcome a = outcome_of(p, e1, false), b = outcome_of(p, e1, true);
+    p.E0[cell] = b.e;
+    if (a.alive != b.alive) {
+        p.tfA[cell] = (uint8_t)(b.alive ? (TF_OCC | trait) : 0u);
+        atomicAdd(&p.ctr->living_deaths, b.alive ? ~0ull : 1ull);  // (+1, or -1 if a negative cost revives it)
+        if (p.want_counts) atomicAdd(&p.ctr->bins[count_bin(strat, trait)], b.alive ? 1ull : ~0ull);
+    }
+    if (b.risk && !a.risk) {  // (an entry that is no longer at risk is harmless: k_risk_resolve replays it exactly)
+        const unsigned int slot = atomicAdd(&p.ctr->risk_next_n, 1u);
+        if (slot < p.list_cap) p.risk_next[slot] = cell;
+        else atomicExch(&p.ctr->overflow, 1u);
     }
 }
 

@@ -13,19 +13,14 @@ namespace pd {
 // ---- tf plane bits ---------------------------------------------------------------------
 // Canonical (between steps): OCC | trait.  Transient meanings per phase:
 //   tfA during play      : bits 3-6 = D code of an at-risk agent (0 none, c+1 = dies in sub-step c)
-//   tfB/tfA during travel: GHOST = cell was occupied at step start but is empty now (still
-//                          blocks movers, quirk B-13), CLAIM|DIR = mover claiming direction DIR
-//   tfB/tfA during reproduce: CLAIM|DIR = parent claiming direction DIR; PARENT = reproduced; NEWBORN (same bit as
-//                          GHOST) = child of this step (only written when retry rounds must see its cell), until
-//                          the cull has run
+//   tfB during travel     : GHOST = cell was occupied at step start but is empty now (still blocks movers,
+//                          quirk B-13)
+//   tfB during reproduce  : NEWBORN (same bit as GHOST, but with OCC) = child of this step (only written when
+//                          retry rounds must see its cell)
+// Claims are not flags: a claimant posts its key with an atomic max into the claim plane (claim_word below).
 constexpr uint32_t TF_TRAIT = 0x03u;
 constexpr uint32_t TF_GHOST = 0x04u;
 constexpr uint32_t TF_NEWBORN = 0x04u;
-constexpr uint32_t TF_PARENT = 0x08u;  // tfA after a claim was won: reproduced this step (k_punish charges the cost);
-                                       // shares a bit with DIR, so it only means PARENT when CLAIM is clear
-constexpr uint32_t TF_DIR_SHIFT = 3u;
-constexpr uint32_t TF_DIR = 0x38u;
-constexpr uint32_t TF_CLAIM = 0x40u;
 constexpr uint32_t TF_OCC = 0x80u;
 constexpr uint32_t TF_D_SHIFT = 3u;
 constexpr uint32_t TF_D = 0x78u;
@@ -125,10 +120,12 @@ struct Params {
     // sparse lists
     uint32_t* risk_cur; uint32_t* risk_next; float* risk_e;
     unsigned long long* cand;  // cull select: the threshold bin's candidate keys (list_cap / 2 of them)
-    // round 1 claims, one contiguous segment per tile (entry = tile-local cell | direction << 16) and the
-    // (first entry, count) of every tile's segment
-    uint32_t* mv_claim; uint32_t* rp_claim;
-    uint2* seg_mv; uint2* seg_rp;
+    // One 64-bit word per cell: the highest claim posted on it (claim_word; atomic max, never cleared -- newer
+    // rounds carry a higher tag).  Replaces the move / reproduction request messages keyed by the target's bucket
+    // (:864-868, :1126-1130) and the "highest roll wins" scan of their readers (:929, :1192).
+    unsigned long long* claim;
+    // round 1 claimants (the travel phase's, then the reproduction phase's): cell and claimed direction
+    uint32_t* cl_cell; uint8_t* cl_dir;
     uint32_t* rt_cell; uint8_t* rt_state; uint8_t* rt_aux;  // the losers of round 1: rounds 2..8 (travel, then reproduction)
     uint32_t* nb_cell;
     float* nb_e; uint16_t* nb_gene;  // the newborn's energy and strategies | trait << 8 (it is written into the
@@ -167,6 +164,30 @@ __device__ __forceinline__ uint64_t nb_gcell(const Params& p, uint32_t x, uint32
     const uint32_t nx = (x + (uint32_t)DX(d)) & (p.W - 1);
     const uint32_t gy = (p.row0 + y + (uint32_t)DY(d)) & (p.HW - 1);
     return ((uint64_t)gy << p.log2W) | nx;
+}
+
+// ---- claims (move_request :864-868 / move_response :929-935; god_go_forth :1126-1130 / god_multiply :1192-1198) --
+// A claimant posts ONE word on its target cell with an atomic max and has won iff the cell still holds exactly
+// its word when the round is resolved.  Layout, most significant first:
+//     tag  (29 bits)  (step & 0x1FFFFFF) << 4 | phase << 3 | round   -- phase 0 travel, 1 reproduction; round 0..7
+//     prio (32 bits)  the claimant's Philox priority (:806, :1076): the highest roll wins
+//     j    (3 bits)   7 - claimed direction = where the claimant stands as seen from the cell.  Unique among the
+//                     rivals of one cell; decides a tie of the priorities (it takes the place of the id comparison
+//                     of :929 / :1192, like the direction class does for the play rolls)
+// The tag grows with every round, so a word left over from an earlier round, phase or step always loses: the plane
+// is never cleared (the host zeroes it when the step counter's 25 bits wrap, and whenever the step is set).
+constexpr uint32_t CLAIM_TRAVEL = 0u, CLAIM_REPRO = 8u;
+__device__ __forceinline__ unsigned long long claim_word(uint32_t step, uint32_t phase_round, uint32_t prio, int dir) {
+    const unsigned long long tag = ((unsigned long long)(step & 0x1FFFFFFu) << 4) | phase_round;
+    return (tag << 35) | ((unsigned long long)prio << 3) | (unsigned long long)(7 - dir);
+}
+// A reduction on a word that misses in the L2 is served far more slowly than a load (measured: 16 M reductions
+// per ms against > 100 M random sector loads): the claimant asks for the word's line ahead of posting
+__device__ __forceinline__ void prefetch_claim(const unsigned long long* word) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(word));
+}
+__device__ __forceinline__ void post_claim(unsigned long long* word, unsigned long long v) {
+    asm volatile("red.global.max.u64 [%0], %1;" ::"l"(word), "l"(v) : "memory");
 }
 
 // ---- the game as the RESPONDER sees it (play_response, :599-689) --------------------------

@@ -4,16 +4,16 @@
 //   k_begin_step    zero the per-step counters
 //   k_risk_resolve  sparse: exact death sub-step of the few agents that CAN die in play
 //   k_play_travel   dense sweep 1: roll + roles + 8 play sub-steps + mover decision + travel claim
-//   k_move_commit   dense sweep 2: resolve travel claims (round 1) from the tile's claim list, pull movers in
+//   k_move_commit   sparse: resolve the travel claims of round 1 (one thread per claimant), winners relocate
 //   k_move_retry    sparse: travel rounds 2..8 for the claim losers
-//   k_repro_claim   dense sweep 3: eligibility + reproduction claim
-//   k_repro_commit  dense sweep 4: resolve claims (round 1) from the tile's claim list, births
+//   k_claim_punish  dense sweep 2: eligibility + reproduction claim, fused with cost of living, death, counts
+//                   and the next step's at-risk list (a winning parent corrects its own outcome afterwards)
+//   k_repro_commit  sparse: resolve the reproduction claims of round 1, births
 //   k_repro_retry   sparse: reproduction rounds 2..8 (gated by the carrying capacity)
-//   k_punish        dense sweep 5: reproduction cost, cost of living, death, counts, next step's at-risk list
-//                   (cell-local, streaming, in place)
 //   k_finalize      sparse: newborn cull (exact k-th selection), the surviving newborns enter the planes
-// Every dense sweep is a pure GATHER: a cell reads its neighbourhood and writes only itself, so there are no
-// claim planes, no atomics on cells and no clears (DESIGN.md "Kernels").
+// Every dense sweep is a pure GATHER on the state planes: a cell reads its neighbourhood and writes only itself.
+// Claims go through ONE extra plane of 64-bit words with atomic max (the north star's "atomicMin on packed
+// (priority, id) per target cell"), tagged by step / phase / round so that it never needs clearing.
 // The persistent sparse kernels are templated on their block size: one 1024-thread CTA on small worlds,
 // 512-thread CTAs (128 registers available) in the cooperative multi-CTA launch.
 #pragma once
@@ -139,37 +139,207 @@ __global__ void __launch_bounds__(BS) k_risk_resolve(const __grid_constant__ Par
 }
 
 // ------------------------------------------------------------------------------------------
-// Retry rounds (sparse, persistent).  Round 1 of both claim phases is resolved per tile by the dense commit
-// sweeps (pd_dense.cuh), which list their losers; rounds 2..8 only touch those (~5 % of the movers, ~1/3 of the
-// attempting parents -- and at saturation the population gate stops reproduction after round 1), in place on
-// the flag plane, three phases per round separated by grid barriers:
-//   request  (:784-872, :1042-1134)  probe from the saved direction, post the claim as flags in my own byte
-//   response (:881-960, :1170-1205)  every claimant reads the claim flags around its target; only a contested
-//                                    target needs the rivals' Philox priorities (recomputed, never communicated)
-//   apply                            winners commit, losers drop their claim and stay on the list
-// List entry state: 0x80 active | 0x40 fresh (claimed by the dense sweep) | (probes used - 1) << 3 | start direction.
+// Claim resolution (sparse).  The dense sweeps post round 1's claims on the claim plane and list the claimants;
+// a claimant has won iff its target's word is still its own (pd_device.cuh claim_word).
+//   k_move_commit / k_repro_commit   round 1: independent threads over the listed claimants
+//   k_move_retry / k_repro_retry     rounds 2..8 for the losers (~5 % of the movers, ~1/3 of the attempting
+//                                    parents -- and at saturation the population gate stops reproduction after
+//                                    round 1), persistent, two phases per round separated by grid barriers:
+//       request  (:784-872, :1042-1134)  probe from the saved direction, post the claim
+//       response (:881-960, :1170-1205)  winners commit, losers stay on the list
+// Everything happens in place on tfB / E1 / strat: a winner only writes its own cell and its (empty) target,
+// nobody reads either in the same phase.
+// Retry-list entry state: 0x80 active | 0x40 fresh (claimed in round 1) | (probes used - 1) << 3 | start direction.
 // ------------------------------------------------------------------------------------------
-template <typename KeyFn>
-__device__ __forceinline__ bool contest(const Params& p, const uint8_t* tf, uint32_t x, uint32_t y, int d, KeyFn keyfn) {
-    const uint32_t tx = (x + (uint32_t)DX(d)) & (p.W - 1);
-    const uint32_t ty = nb_row(p, y, DY(d));
-    uint32_t rivals = 0;
+// A CTA takes chunks of COMMIT_CHUNK consecutive list entries, COMMIT_K per thread with all their loads in flight
+// together, stages what it appends to the global lists (losers, newborns) in shared memory and reserves the
+// space with ONE atomic per chunk and list: a warp-level append per entry makes ~10^6 atomics per step on one
+// address, which the L2 serialises (that alone was 2/3 of k_repro_commit's time, profiles/README.md).
+constexpr int COMMIT_NT = 256, COMMIT_K = 4, COMMIT_CHUNK = COMMIT_NT * COMMIT_K;
+
+// k_move_commit: move_response (:881-960), round 1.  A winner relocates -- energy, strategies and trait go to
+// the target cell -- and leaves a GHOST that keeps blocking movers this step (quirk B-13); a loser joins the
+// retry list with the direction it claimed.
+__global__ void __launch_bounds__(COMMIT_NT) k_move_commit(const __grid_constant__ Params p) {
+    __shared__ uint32_t s_lost_cell[COMMIT_CHUNK];
+    __shared__ uint8_t s_lost_state[COMMIT_CHUNK];
+    __shared__ unsigned int s_n[2];  // 0 losers of this chunk, 1 their base in the retry list
+    Counters* ctr = p.ctr;
+    unsigned int n = ctr->mv_n;
+    if (n > p.list_cap) n = p.list_cap;
+    const uint32_t step = __ldg(&ctr->step_no);
+    const int tid = threadIdx.x;
+    unsigned int moved = 0;
+    for (unsigned int c0 = blockIdx.x * COMMIT_CHUNK; c0 < n; c0 += gridDim.x * COMMIT_CHUNK) {
+        if (tid == 0) s_n[0] = 0;
+        __syncthreads();
+        uint32_t cell[COMMIT_K], tgt[COMMIT_K], st[COMMIT_K], t[COMMIT_K];
+        int d[COMMIT_K];
+        unsigned long long top[COMMIT_K];
+        float e[COMMIT_K];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t tn = __ldcg(tf + nb_local(p, tx, ty, j));
-        if (claims_dir(tn, 7 - j)) rivals |= 1u << j;
+        for (int k = 0; k < COMMIT_K; ++k) {
+            const unsigned int i = c0 + k * COMMIT_NT + tid;
+            cell[k] = i < n ? p.cl_cell[i] : 0u;
+            d[k] = i < n ? (int)p.cl_dir[i] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < COMMIT_K; ++k) {  // the payload is requested together with the verdict: one round trip
+            tgt[k] = nb_local(p, cell[k] & (p.W - 1), cell[k] >> p.log2W, d[k]);
+            top[k] = __ldcg(p.claim + tgt[k]);
+            e[k] = __ldcg(p.E1 + cell[k]);
+            st[k] = __ldcg(p.strat + cell[k]);
+            t[k] = __ldcg(p.tfB + cell[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < COMMIT_K; ++k) {
+            const bool valid = c0 + k * COMMIT_NT + tid < n;
+            const uint32_t x = cell[k] & (p.W - 1), y = cell[k] >> p.log2W;
+            const unsigned long long mine = claim_word(step, CLAIM_TRAVEL, rng(p, gcell_of(p, x, y), S_TRAVEL).x, d[k]);
+            const bool won = valid && top[k] == mine;
+            if (won) {  // :946-956
+                p.E1[tgt[k]] = e[k];
+                p.strat[tgt[k]] = (uint8_t)st[k];
+                p.tfB[tgt[k]] = (uint8_t)(TF_OCC | (t[k] & TF_TRAIT));
+                p.tfB[cell[k]] = (uint8_t)TF_GHOST;
+                if (row_owned(p, tgt[k] >> p.log2W)) ++moved;
+            }
+            const bool lost = valid && !won;  // :940-943 -> retry with the same roll
+            const uint32_t slot = wappend(&s_n[0], lost);
+            if (lost) {
+                s_lost_cell[slot] = cell[k];
+                s_lost_state[slot] = (uint8_t)(0xC0u | (uint32_t)d[k]);
+            }
+        }
+        __syncthreads();
+        const unsigned int n_lost = s_n[0];
+        if (n_lost) {  // uniform across the CTA
+            if (tid == 0) s_n[1] = atomicAdd(&ctr->rt_n[0], n_lost);
+            __syncthreads();
+            const unsigned int base = s_n[1];
+            if (base + n_lost > p.list_cap) {
+                if (tid == 0) atomicExch(&ctr->overflow, 1u);
+            } else {
+                for (unsigned int k = tid; k < n_lost; k += COMMIT_NT) {
+                    p.rt_cell[base + k] = s_lost_cell[k];
+                    p.rt_state[base + k] = s_lost_state[k];
+                }
+            }
+        }
     }
-    rivals &= ~(1u << (7 - d));  // that one is me
-    if (!rivals) return true;
-    const Key mine = keyfn(p, gcell_of(p, x, y));
-    bool win = true;
-    for (uint32_t m = rivals; m; m &= m - 1)
-        if (key_gt(keyfn(p, nb_gcell(p, tx, ty, __ffs(m) - 1)), mine)) win = false;
-    return win;
+    if (p.stats) {
+        for (int o = 16; o > 0; o >>= 1) moved += __shfl_down_sync(0xFFFFFFFFu, moved, o);
+        if ((tid & 31) == 0 && moved) atomicAdd(&ctr->st_moved, (unsigned long long)moved);
+    }
+}
+
+// k_repro_commit: god_multiply (:1144-1335), round 1.  A winner pays the reproduction cost (parent_outcome: its
+// layer-7 result is re-derived from E1, which stays read-only) and makes its child from its own energy /
+// strategies.  The child only goes on the newborn list, with its energy and strategies: near the carrying
+// capacity almost every newborn is culled in the same step, so it enters the planes in k_finalize if it survives,
+// or when retry rounds must see its cell blocked.  A child born into a ghost row belongs to the neighbour slab:
+// here it only blocks its cell.
+__global__ void __launch_bounds__(COMMIT_NT) k_repro_commit(const __grid_constant__ Params p) {
+    __shared__ uint32_t s_lost_cell[COMMIT_CHUNK];
+    __shared__ uint8_t s_lost_state[COMMIT_CHUNK];
+    __shared__ uint32_t s_nb_cell[COMMIT_CHUNK];
+    __shared__ float s_nb_e[COMMIT_CHUNK];
+    __shared__ uint16_t s_nb_gene[COMMIT_CHUNK];
+    __shared__ unsigned int s_n[4];  // 0 losers of this chunk, 1 newborns, 2 / 3 their bases in the global lists
+    Counters* ctr = p.ctr;
+    unsigned int n = ctr->rp_n;
+    if (n > p.list_cap) n = p.list_cap;
+    const uint32_t step = __ldg(&ctr->step_no);
+    const int tid = threadIdx.x;
+    for (unsigned int c0 = blockIdx.x * COMMIT_CHUNK; c0 < n; c0 += gridDim.x * COMMIT_CHUNK) {
+        if (tid < 2) s_n[tid] = 0;
+        __syncthreads();
+        uint32_t cell[COMMIT_K], tgt[COMMIT_K], st[COMMIT_K], t[COMMIT_K];
+        int d[COMMIT_K];
+        unsigned long long top[COMMIT_K];
+        float e[COMMIT_K];
+#pragma unroll
+        for (int k = 0; k < COMMIT_K; ++k) {
+            const unsigned int i = c0 + k * COMMIT_NT + tid;
+            cell[k] = i < n ? p.cl_cell[i] : 0u;
+            d[k] = i < n ? (int)p.cl_dir[i] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < COMMIT_K; ++k) {
+            tgt[k] = nb_local(p, cell[k] & (p.W - 1), cell[k] >> p.log2W, d[k]);
+            top[k] = __ldcg(p.claim + tgt[k]);
+            e[k] = __ldcg(p.E1 + cell[k]);
+            st[k] = __ldcg(p.strat + cell[k]);
+            t[k] = __ldcg(p.tfB + cell[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < COMMIT_K; ++k) {
+            const bool valid = c0 + k * COMMIT_NT + tid < n;
+            const uint32_t x = cell[k] & (p.W - 1), y = cell[k] >> p.log2W;
+            const uint64_t g = gcell_of(p, x, y);
+            const unsigned long long mine = claim_word(step, CLAIM_REPRO, rng(p, g, S_REPRO).x, d[k]);
+            const bool won = valid && top[k] == mine;
+            bool born = false;
+            float ce = 0.0f;
+            uint32_t gene = 0;
+            if (won) {
+                // REPRODUCTION_COMPLETE (:1211-1213, :1331); the child (:1216-1328): my trait, its own energy and strategies
+                const uint32_t trait = t[k] & TF_TRAIT;
+                uint32_t cs;
+                make_child(p, g, st[k], trait, __fsub_rn(e[k], p.reproduce_cost), ce, cs);
+                if (row_owned(p, y)) parent_outcome(p, cell[k], e[k], st[k], trait);
+                gene = cs | (trait << 8);
+                born = row_owned(p, tgt[k] >> p.log2W);
+                if (!born) p.tfB[tgt[k]] = (uint8_t)(TF_OCC | TF_NEWBORN | trait);
+            }
+            const uint32_t bslot = wappend(&s_n[1], born);
+            if (born) {
+                s_nb_cell[bslot] = tgt[k];
+                s_nb_e[bslot] = ce;
+                s_nb_gene[bslot] = (uint16_t)gene;
+            }
+            const bool lost = valid && !won;  // stays ATTEMPTING_REPRODUCTION (:1203-1205)
+            const uint32_t lslot = wappend(&s_n[0], lost);
+            if (lost) {
+                s_lost_cell[lslot] = cell[k];
+                s_lost_state[lslot] = (uint8_t)(0xC0u | (uint32_t)d[k]);
+            }
+        }
+        __syncthreads();
+        const unsigned int n_lost = s_n[0], n_born = s_n[1];
+        if (tid == 0) {
+            if (n_lost) s_n[2] = atomicAdd(&ctr->rt_n[1], n_lost);
+            if (n_born) s_n[3] = atomicAdd(&ctr->nb_n, n_born);
+        }
+        __syncthreads();
+        if (n_lost) {  // uniform across the CTA
+            const unsigned int base = s_n[2];
+            if (base + n_lost > p.list_cap) {
+                if (tid == 0) atomicExch(&ctr->overflow, 1u);
+            } else {
+                for (unsigned int k = tid; k < n_lost; k += COMMIT_NT) {
+                    p.rt_cell[base + k] = s_lost_cell[k];
+                    p.rt_state[base + k] = s_lost_state[k];
+                }
+            }
+        }
+        if (n_born) {
+            const unsigned int base = s_n[3];
+            if (base + n_born > p.list_cap) {
+                if (tid == 0) atomicExch(&ctr->overflow, 1u);
+            } else {
+                for (unsigned int k = tid; k < n_born; k += COMMIT_NT) {
+                    p.nb_cell[base + k] = s_nb_cell[k];
+                    p.nb_e[base + k] = s_nb_e[k];
+                    p.nb_gene[base + k] = s_nb_gene[k];
+                }
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
-// k_move_retry: travel rounds 2..8 (exit_move_fn, :1559-1576) for the losers of round 1, on tfA / E1 / strat.
+// k_move_retry: travel rounds 2..8 (exit_move_fn, :1559-1576) for the losers of round 1, on tfB / E1 / strat.
 // ------------------------------------------------------------------------------------------
 template <int BS>
 __global__ void __launch_bounds__(BS) k_move_retry(const __grid_constant__ Params p) {
@@ -179,7 +349,8 @@ __global__ void __launch_bounds__(BS) k_move_retry(const __grid_constant__ Param
     if (n == 0) return;
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    uint8_t* tf = p.tfA;
+    const uint32_t step = __ldg(&ctr->step_no);
+    uint8_t* tf = p.tfB;
     unsigned int moved = 0;
     for (int round = 1; round < 8; ++round) {
         // ---- request: blocked = OCC|GHOST (a cell vacated this step keeps blocking movers, B-13)
@@ -193,49 +364,40 @@ __global__ void __launch_bounds__(BS) k_move_retry(const __grid_constant__ Param
             for (int d = 0; d < 8; ++d)
                 if (__ldcg(tf + nb_local(p, x, y, d)) & (TF_OCC | TF_GHOST)) blocked |= 1u << d;
             int l = (int)(st & 7u), seq = (int)((st >> 3) & 7u) + 1;
+            const Words w = rng(p, gcell_of(p, x, y), S_TRAVEL);  // the roll of the first attempt is kept (:794-807)
             if (st & 0x40u) {  // fresh from round 1: it claimed direction l after probe_pos probes (:848-849)
-                const int s0 = (int)(rng(p, gcell_of(p, x, y), S_TRAVEL).y >> 29);
-                seq = probe_pos(s0, l);
+                seq = probe_pos((int)(w.y >> 29), l);
                 l = (l + 1) & 7;
             }
             const int dir = probe(blocked, l, seq);
             if (dir < 0) {
                 p.rt_state[i] = 0;  // no free space: stays put (:842-846)
             } else {
-                const uint32_t t = __ldcg(tf + cell);
-                tf[cell] = (uint8_t)((t & (TF_OCC | TF_TRAIT)) | TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT));
+                post_claim(p.claim + nb_local(p, x, y, dir), claim_word(step, CLAIM_TRAVEL + (uint32_t)round, w.x, dir));
                 p.rt_state[i] = (uint8_t)(0x80u | (uint32_t)((dir + 1) & 7) | ((uint32_t)(seq - 1) << 3));
                 p.rt_aux[i] = (uint8_t)dir;
             }
         }
         grid_sync(ctr->barrier, gridDim.x);
         // ---- response
-        for (unsigned int i = t0; i < n; i += stride) {
-            if (!(p.rt_state[i] & 0x80u)) continue;
-            const uint32_t cell = p.rt_cell[i];
-            const int d = (int)(p.rt_aux[i] & 7u);
-            const bool win = contest(p, tf, cell & (p.W - 1), cell >> p.log2W, d, TravelKey());
-            p.rt_aux[i] = (uint8_t)((uint32_t)d | (win ? 0x80u : 0u));
-        }
-        grid_sync(ctr->barrier, gridDim.x);
-        // ---- apply
         unsigned int still = 0;
         for (unsigned int i = t0; i < n; i += stride) {
             if (!(p.rt_state[i] & 0x80u)) continue;
             const uint32_t cell = p.rt_cell[i];
             const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
-            const uint32_t aux = p.rt_aux[i];
-            const uint32_t t = __ldcg(tf + cell);
-            if (aux & 0x80u) {  // the winner relocates (:946-956)
-                const uint32_t tgt = nb_local(p, x, y, (int)(aux & 7u));
+            const int d = (int)(p.rt_aux[i] & 7u);
+            const uint32_t tgt = nb_local(p, x, y, d);
+            const unsigned long long top = __ldcg(p.claim + tgt);
+            const unsigned long long mine = claim_word(step, CLAIM_TRAVEL + (uint32_t)round, rng(p, gcell_of(p, x, y), S_TRAVEL).x, d);
+            if (top == mine) {  // the winner relocates (:946-956)
+                const uint32_t t = __ldcg(tf + cell);
                 p.E1[tgt] = __ldcg(p.E1 + cell);
                 p.strat[tgt] = __ldcg(p.strat + cell);
                 tf[tgt] = (uint8_t)(TF_OCC | (t & TF_TRAIT));
                 tf[cell] = (uint8_t)TF_GHOST;
                 p.rt_state[i] = 0;
-                if (row_owned(p, y)) ++moved;
+                if (row_owned(p, tgt >> p.log2W)) ++moved;
             } else {
-                tf[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
                 ++still;
             }
         }
@@ -248,8 +410,8 @@ __global__ void __launch_bounds__(BS) k_move_retry(const __grid_constant__ Param
 
 // ------------------------------------------------------------------------------------------
 // k_repro_retry: reproduction rounds 2..8 (exit_god_fn, :1607-1627), only while the population (olds + births
-// so far) does not exceed max_agents (:1616, :1621-1625).  On tfA; E1 is read-only (a winner is flagged PARENT,
-// k_punish charges the reproduction cost).  Rounds [round0, round1) run in this launch (a row slab runs one
+// so far) does not exceed max_agents (:1616, :1621-1625).  On tfB; E1 is read-only (a winner's layer-7 outcome
+// is re-derived by parent_outcome).  Rounds [round0, round1) run in this launch (a row slab runs one
 // round per launch: the caller sums the population over the slabs in between).
 // ------------------------------------------------------------------------------------------
 template <int BS>
@@ -260,7 +422,8 @@ __global__ void __launch_bounds__(BS) k_repro_retry(const __grid_constant__ Para
     if (n == 0) return;
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    uint8_t* tf = p.tfA;
+    const uint32_t step = __ldg(&ctr->step_no);
+    uint8_t* tf = p.tfB;
     for (int round = (int)p.round0; round < (int)p.round1; ++round) {
         // overpopulated gate, evaluated after every round (:1616, :1621-1625); in slab mode the caller
         // has summed olds and births over all slabs into glb[] before this launch
@@ -287,32 +450,22 @@ __global__ void __launch_bounds__(BS) k_repro_retry(const __grid_constant__ Para
             for (int d = 0; d < 8; ++d)
                 if (__ldcg(tf + nb_local(p, x, y, d)) & TF_OCC) blocked |= 1u << d;
             int l = (int)(st & 7u), seq = (int)((st >> 3) & 7u) + 1;
+            const Words w = rng(p, gcell_of(p, x, y), S_REPRO);  // the roll of the first attempt is kept (:1074-1076)
             if (st & 0x40u) {  // fresh from round 1: it claimed direction l after probe_pos probes (:1110-1111)
-                const int s0 = (int)(rng(p, gcell_of(p, x, y), S_REPRO).y >> 29);
-                seq = probe_pos(s0, l);
+                seq = probe_pos((int)(w.y >> 29), l);
                 l = (l + 1) & 7;
             }
             const int dir = probe(blocked, l, seq);  // also covers reproduce_sequence >= 8 (:1067)
             if (dir < 0) {
                 p.rt_state[i] = 0x40u;  // REPRODUCTION_IMPOSSIBLE (:1104-1108)
             } else {
-                const uint32_t t = __ldcg(tf + cell);
-                tf[cell] = (uint8_t)((t & (TF_OCC | TF_TRAIT)) | TF_CLAIM | ((uint32_t)dir << TF_DIR_SHIFT));
+                post_claim(p.claim + nb_local(p, x, y, dir), claim_word(step, CLAIM_REPRO + (uint32_t)round, w.x, dir));
                 p.rt_state[i] = (uint8_t)(0x80u | (uint32_t)((dir + 1) & 7) | ((uint32_t)(seq - 1) << 3));
                 p.rt_aux[i] = (uint8_t)dir;
             }
         }
         grid_sync(ctr->barrier, gridDim.x);
-        // ---- multiply: contest
-        for (unsigned int i = t0; i < n; i += stride) {
-            if (!(p.rt_state[i] & 0x80u)) continue;
-            const uint32_t cell = p.rt_cell[i];
-            const int d = (int)(p.rt_aux[i] & 7u);
-            const bool win = contest(p, tf, cell & (p.W - 1), cell >> p.log2W, d, ReproKey());
-            p.rt_aux[i] = (uint8_t)((uint32_t)d | (win ? 0x80u : 0u));
-        }
-        grid_sync(ctr->barrier, gridDim.x);
-        // ---- multiply: apply
+        // ---- multiply (:1170-1335)
         unsigned int still = 0;
         for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
             const unsigned int i = i0 + threadIdx.x;
@@ -322,20 +475,23 @@ __global__ void __launch_bounds__(BS) k_repro_retry(const __grid_constant__ Para
             if (i < n && (p.rt_state[i] & 0x80u)) {
                 const uint32_t cell = p.rt_cell[i];
                 const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
-                const uint32_t aux = p.rt_aux[i];
-                const uint32_t t = __ldcg(tf + cell);
-                if (aux & 0x80u) {
-                    tgt = nb_local(p, x, y, (int)(aux & 7u));
-                    const float pe = __fsub_rn(__ldcg(p.E1 + cell), p.reproduce_cost);  // :1211-1213
+                const int d = (int)(p.rt_aux[i] & 7u);
+                tgt = nb_local(p, x, y, d);
+                const uint64_t g = gcell_of(p, x, y);
+                const unsigned long long top = __ldcg(p.claim + tgt);
+                const unsigned long long mine = claim_word(step, CLAIM_REPRO + (uint32_t)round, rng(p, g, S_REPRO).x, d);
+                if (top == mine) {
+                    const uint32_t t = __ldcg(tf + cell);
+                    const float e1 = __ldcg(p.E1 + cell);
+                    const uint32_t st = __ldcg(p.strat + cell);
                     uint32_t cs;
-                    make_child(p, gcell_of(p, x, y), __ldcg(p.strat + cell), t & TF_TRAIT, pe, ce, cs);
+                    make_child(p, g, st, t & TF_TRAIT, __fsub_rn(e1, p.reproduce_cost), ce, cs);  // :1211-1213
+                    if (row_owned(p, y)) parent_outcome(p, cell, e1, st, t & TF_TRAIT);
                     tf[tgt] = (uint8_t)(TF_OCC | TF_NEWBORN | (t & TF_TRAIT));  // blocks its cell in later rounds
-                    tf[cell] = (uint8_t)(TF_OCC | TF_PARENT | (t & TF_TRAIT));  // REPRODUCTION_COMPLETE: one child per step (B-6)
-                    gene = cs | ((t & TF_TRAIT) << 8);
+                    gene = cs | ((t & TF_TRAIT) << 8);  // (REPRODUCTION_COMPLETE: it leaves the list -- one child per step, B-6)
                     born = row_owned(p, tgt >> p.log2W);  // a child in the ghost zone belongs to the neighbour slab
                     p.rt_state[i] = 0x40u;
                 } else {
-                    tf[cell] = (uint8_t)(t & (TF_OCC | TF_TRAIT));
                     ++still;
                 }
             }

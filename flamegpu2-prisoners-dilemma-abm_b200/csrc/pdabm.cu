@@ -88,6 +88,7 @@ struct pd_sim {
     double kernel_ms[PDABM_NUM_KERNELS];
     uint32_t prof_steps;
     bool step_dirty;               // host step number not yet written to Counters::step_no
+    bool claim_dirty;              // the claim plane may hold words with tags that are not in the past: zero it
     // CUDA graphs of one whole step (9 launches), one per (at-risk list parity, want_counts); used for worlds
     // small enough that launch latency matters, on explicit (capturable) streams, when profiling is off
     bool graphs;
@@ -104,11 +105,11 @@ void drop_graphs(pd_sim* s) {  // the captured launches hold plane / list pointe
 
 void free_lists(pd_sim* s) {  // cudaFree(nullptr) is a no-op: safe on a partially allocated set
     cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.cand);
-    cudaFree(s->P.mv_claim); cudaFree(s->P.rp_claim);
+    cudaFree(s->P.cl_cell); cudaFree(s->P.cl_dir);
     cudaFree(s->P.rt_cell); cudaFree(s->P.rt_state); cudaFree(s->P.rt_aux);
     cudaFree(s->P.nb_cell); cudaFree(s->P.nb_e); cudaFree(s->P.nb_gene);
     s->risk[0] = s->risk[1] = nullptr; s->P.risk_e = nullptr; s->P.cand = nullptr;
-    s->P.mv_claim = s->P.rp_claim = nullptr;
+    s->P.cl_cell = nullptr; s->P.cl_dir = nullptr;
     s->P.rt_cell = nullptr; s->P.rt_state = s->P.rt_aux = nullptr;
     s->P.nb_cell = nullptr; s->P.nb_e = nullptr; s->P.nb_gene = nullptr;
     s->lists_allocated = false;
@@ -119,8 +120,8 @@ int alloc_lists_raw(pd_sim* s, uint64_t cap) {
     CK(cudaMalloc(&s->risk[1], cap * 4));
     CK(cudaMalloc(&s->P.risk_e, cap * 4));
     CK(cudaMalloc(&s->P.cand, (cap / 2 + 1) * 8));
-    CK(cudaMalloc(&s->P.mv_claim, cap * 4));
-    CK(cudaMalloc(&s->P.rp_claim, cap * 4));
+    CK(cudaMalloc(&s->P.cl_cell, cap * 4));
+    CK(cudaMalloc(&s->P.cl_dir, cap));
     CK(cudaMalloc(&s->P.rt_cell, cap * 4));
     CK(cudaMalloc(&s->P.rt_state, cap));
     CK(cudaMalloc(&s->P.rt_aux, cap));
@@ -216,6 +217,17 @@ static const bool g_debug_sync = getenv("PDABM_DEBUG_SYNC") != nullptr;
         }                                                                                            \
     } while (0)
 
+// Claim words carry (step mod 2^25) in their tag and are never cleared, because a later round always has a higher
+// tag.  That stops being true when the step is set from outside (pd_set_step, pd_init_population) or its 25 bits
+// wrap: the step then starts from a clean plane.
+int begin_claims(pd_sim* s, cudaStream_t st) {
+    if (s->claim_dirty || (s->step & 0x1FFFFFFu) == 0u) {
+        CK(cudaMemsetAsync(s->P.claim, 0, s->cells * sizeof(unsigned long long), st));
+        s->claim_dirty = false;
+    }
+    return PD_OK;
+}
+
 int push_step(pd_sim* s, cudaStream_t st) {
     if (!s->step_dirty) return PD_OK;
     k_set_step<<<1, 1, 0, st>>>(s->P.ctr, s->step);
@@ -224,9 +236,11 @@ int push_step(pd_sim* s, cudaStream_t st) {
     return PD_OK;
 }
 
-int launch_punish(pd_sim* s, cudaStream_t st) {
-    const size_t owned = (size_t)(s->P.own_y1 - s->P.own_y0) * s->P.W;
-    k_punish<<<(unsigned int)((owned + PUNISH_CELLS - 1) / PUNISH_CELLS), NT, 0, st>>>(s->P);
+// the sparse round-1 commits: independent threads over a device-side list length, grid-stride
+int launch_commit(pd_sim* s, void (*kernel)(const Params), cudaStream_t st) {
+    const size_t want = (s->cells / 16 + COMMIT_CHUNK - 1) / COMMIT_CHUNK;  // ~5 % of the cells claim
+    const size_t cap = (size_t)s->n_sms * 8;
+    kernel<<<(unsigned int)(want < cap ? want : cap), COMMIT_NT, 0, st>>>(s->P);
     CK(cudaGetLastError());
     return PD_OK;
 }
@@ -235,20 +249,19 @@ int launch_punish(pd_sim* s, cudaStream_t st) {
 #define DENSE(kernel) do { if (s->big_tiles) kernel<128, 16><<<s->grid, NT, 0, st>>>(P); \
                            else kernel<16, 16><<<s->grid, NT, 0, st>>>(P); } while (0)
 
-// the 10 launches of one model step, in the order of the reference's main layers (model.py:2140-2163)
+// the 9 launches of one model step, in the order of the reference's main layers (model.py:2140-2163)
 int launch_step(pd_sim* s, cudaStream_t st) {
     Params& P = s->P;
     int rc = PD_OK;
     PROF(0, (k_begin_step<<<1, 256, 0, st>>>(P.ctr, 1)));
     PROF(1, { if ((rc = launch_sparse(s, k_risk_resolve, st))) return rc; });
     PROF(2, DENSE(k_play_travel));
-    PROF(3, DENSE(k_move_commit));
+    PROF(3, { if ((rc = launch_commit(s, k_move_commit, st))) return rc; });
     PROF(4, { if ((rc = launch_sparse(s, k_move_retry, st))) return rc; });
-    PROF(5, DENSE(k_repro_claim));
-    PROF(6, DENSE(k_repro_commit));
+    PROF(5, DENSE(k_claim_punish));
+    PROF(6, { if ((rc = launch_commit(s, k_repro_commit, st))) return rc; });
     PROF(7, { if ((rc = launch_sparse(s, k_repro_retry, st))) return rc; });
-    PROF(8, { if ((rc = launch_punish(s, st))) return rc; });
-    PROF(9, { if ((rc = launch_sparse(s, k_finalize, st))) return rc; });
+    PROF(8, { if ((rc = launch_sparse(s, k_finalize, st))) return rc; });
     return PD_OK;
 }
 
@@ -367,6 +380,10 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     CK(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(PD_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
     CK(cudaSetDevice(cfg->device));
+    if (const char* g = getenv("PDABM_L2_FETCH")) {  // experiment: DRAM fetch granularity of the L2 (32 / 64 / 128 bytes)
+        const int v = atoi(g);
+        if (v == 32 || v == 64 || v == 128) CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v));
+    }
     pd_sim* s = new pd_sim();  // value-initialised: every pointer below starts as nullptr
     struct Guard {             // a failure part-way releases what was allocated so far
         pd_sim* s;
@@ -428,13 +445,8 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     P.sparse_ctas = (uint32_t)s->sparse_ctas;
     s->graphs = cfg->use_graphs > 0 || (cfg->use_graphs == 0 && !slab && s->cells <= ((size_t)1 << 22));
     if (slab) s->graphs = false;  // a slab is stepped in parts with host decisions in between
-    {
-        const size_t tiles = (size_t)s->grid.x * s->grid.y;
-        CK(cudaMalloc(&P.seg_mv, tiles * sizeof(uint2)));
-        CK(cudaMalloc(&P.seg_rp, tiles * sizeof(uint2)));
-        CK(cudaMemset(P.seg_mv, 0, tiles * sizeof(uint2)));
-        CK(cudaMemset(P.seg_rp, 0, tiles * sizeof(uint2)));
-    }
+    CK(cudaMalloc(&P.claim, s->cells * sizeof(unsigned long long)));
+    s->claim_dirty = true;  // zeroed on the stream of the first step
     {
         float h_lut[256], *d_lut = nullptr;
         for (uint32_t i = 0; i < 256; ++i) h_lut[i] = lut_entry(P.pay, i);
@@ -460,7 +472,7 @@ int pd_destroy(pd_sim* s) {
     drop_graphs(s);
     if (s->P.step_log) cudaFree(s->P.step_log);
     cudaFree(s->P.E1); cudaFree(s->P.tfB); cudaFree(s->P.ctr); cudaFree(const_cast<float*>(s->P.lut));
-    cudaFree(s->P.seg_mv); cudaFree(s->P.seg_rp);
+    cudaFree(s->P.claim);
     free_lists(s);
     if (s->h) cudaFreeHost(s->h);
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
@@ -548,6 +560,7 @@ int pd_init_population(pd_sim* s, uint64_t n_agents, void* stream) {
     CK(cudaGetLastError());
     s->step = 0;
     s->step_dirty = true;
+    s->claim_dirty = true;
     rc = run_scan(s, st);
     if (rc) return rc;
     s->ready = true;
@@ -566,6 +579,7 @@ int pd_step(pd_sim* s, uint32_t n_steps, void* stream, int want_counts) {
         P.want_counts = (want_counts == 2 || (want_counts && k + 1 == n_steps)) ? 1u : 0u;
         P.risk_cur = s->risk[s->risk_cur];
         P.risk_next = s->risk[s->risk_cur ^ 1];
+        if ((rc = begin_claims(s, st))) return rc;
         bool replayed = false;
         if ((rc = graph_step(s, st, &replayed))) return rc;
         if (!replayed && (rc = launch_step(s, st))) return rc;
@@ -637,20 +651,21 @@ int pd_step_part(pd_sim* s, int part, int arg, void* stream, int want_counts) {
     P.risk_next = s->risk[s->risk_cur ^ 1];
     switch (part) {
     case PD_PART_PRE: {
+        if ((rc = begin_claims(s, st))) return rc;
         // ghost rows were just refreshed by the caller: their at-risk agents join the list
         const size_t ghost_cells = (size_t)2 * s->cfg.ghost_rows * P.W;
         const int blocks = (int)((ghost_cells + 255) / 256 < (size_t)(s->n_sms * 8) ? (ghost_cells + 255) / 256 : (size_t)(s->n_sms * 8));
         PROF(0, { k_ghost_risk_scan<<<blocks, 256, 0, st>>>(P); k_begin_step<<<1, 256, 0, st>>>(P.ctr, 1); });
         PROF(1, { if ((rc = launch_sparse(s, k_risk_resolve, st))) return rc; });
         PROF(2, DENSE(k_play_travel));
-        PROF(3, DENSE(k_move_commit));
+        PROF(3, { if ((rc = launch_commit(s, k_move_commit, st))) return rc; });
         PROF(4, { if ((rc = launch_sparse(s, k_move_retry, st))) return rc; });
-        PROF(5, DENSE(k_repro_claim));
-        PROF(6, DENSE(k_repro_commit));
+        PROF(5, DENSE(k_claim_punish));
+        PROF(6, { if ((rc = launch_commit(s, k_repro_commit, st))) return rc; });
         k_publish_gate<<<1, 32, 0, st>>>(P, 0);
         // the cull histogram of round 1's newborns rides on the same all-reduce as the gate words
         P.hist_force = 1;
-        PROF(9, { if ((rc = launch_sparse(s, k_fin_hist, st))) return rc; });
+        PROF(8, { if ((rc = launch_sparse(s, k_fin_hist, st))) return rc; });
         P.hist_force = 0;
         break;
     }
@@ -662,14 +677,13 @@ int pd_step_part(pd_sim* s, int part, int arg, void* stream, int want_counts) {
         P.round0 = 1; P.round1 = 8;
         break;
     case PD_PART_HIST:  // retry rounds added newborns: this slab's cull histogram again
-        PROF(9, { if ((rc = launch_sparse(s, k_fin_hist, st))) return rc; });
+        PROF(8, { if ((rc = launch_sparse(s, k_fin_hist, st))) return rc; });
         break;
-    case PD_PART_CAND:  // the reproduction rounds are over: cost of living, then this slab's cull candidates
-        PROF(8, { if ((rc = launch_punish(s, st))) return rc; });
-        PROF(9, { if ((rc = launch_sparse(s, k_fin_cand, st))) return rc; });
+    case PD_PART_CAND:  // the reproduction rounds are over: this slab's cull candidates
+        PROF(8, { if ((rc = launch_sparse(s, k_fin_cand, st))) return rc; });
         break;
     case PD_PART_APPLY:
-        PROF(9, { if ((rc = launch_sparse(s, k_fin_apply, st))) return rc; });
+        PROF(8, { if ((rc = launch_sparse(s, k_fin_apply, st))) return rc; });
         s->risk_cur ^= 1;
         s->step += 1;
         break;
@@ -766,6 +780,7 @@ int pd_set_step(pd_sim* s, uint32_t step) {
     if (!s) return fail(PD_ERR_INVALID, "NULL argument");
     s->step = step;
     s->step_dirty = true;  // written to the device at the start of the next step call, on its stream
+    s->claim_dirty = true;
     return PD_OK;
 }
 

@@ -191,8 +191,8 @@ class Simulation:
         self._check(self.lib.pd_read_stats(self._h, C.byref(st), self.stream_ptr))
         return {n: int(getattr(st, n)) for n, _ in pd_step_stats._fields_}
 
-    KERNELS = ("begin_step", "risk_resolve", "play_travel", "move_commit", "move_retry", "repro_claim",
-               "repro_commit", "repro_retry", "punish", "finalize")
+    KERNELS = ("begin_step", "risk_resolve", "play_travel", "move_commit", "move_retry", "claim_punish",
+               "repro_commit", "repro_retry", "finalize")
 
     def agent_steps(self) -> int:
         """Sum over executed steps of the population at the start of the step."""

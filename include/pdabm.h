@@ -78,7 +78,7 @@ typedef struct pd_config {
     uint32_t world_height;          /* 0 = width (square, like the reference); else a power of two: the world is
                                        width x world_height cells (used for weak-scaling series of row slabs) */
     int32_t use_graphs;             /* 0 = auto (whole worlds <= 2^22 cells), 1 = always, -1 = never: replay one
-                                       captured CUDA graph per step instead of 10 launches.  Only on explicit
+                                       captured CUDA graph per step instead of 9 launches.  Only on explicit
                                        (capturable) streams and while per-kernel profiling is off. */
     uint32_t debug_select_cap;      /* 0 = default; tests: cap of the cull select's shared-memory stage, to force its
                                        global-memory fallback */
@@ -134,14 +134,13 @@ int pd_read_stats(pd_sim* sim, pd_step_stats* out, void* stream);
  * rows + 2*ghost_rows rows: ghost_rows rows of the upper neighbour slab, the owned rows, ghost_rows
  * rows of the lower neighbour slab (periodic ring).  One model step is
  *     caller: refresh the ghost rows of energy/strat/tf from the neighbour slabs (NVLink copy)
- *     PD_PART_PRE            play, all travel rounds, reproduction claims and round 1; publishes glb[0..2] and
- *                            the cull histogram of round 1's newborns in ghist
+ *     PD_PART_PRE            play, all travel rounds, reproduction claims (with the cost of living) and round 1;
+ *                            publishes glb[0..2] and the cull histogram of round 1's newborns in ghist
  *     caller: sum glb and ghist over the slabs (ONE all-reduce if the two are views of one buffer)
  *     PD_PART_RETRY r=1..7   one further reproduction round, gated by the global population; caller sums glb.
  *                            Only needed while glb[0] + glb[1] <= max_agents and glb[2] > 0 (exit_god_fn).
  *     PD_PART_HIST           only if retry rounds ran: the histogram again;  caller sums ghist
- *     PD_PART_CAND           cost of living (k_punish), then this slab's cull candidates into cand_out;
- *                            caller gathers all blocks into cand_all
+ *     PD_PART_CAND           this slab's cull candidates into cand_out;  caller gathers all blocks into cand_all
  *     PD_PART_APPLY          cull, bookkeeping; publishes glb[3..19] (agents, 16 counts)
  * The ghost zone is wide enough that every other phase needs no communication (DESIGN.md "Multi-GPU");
  * results are bit-identical to the whole-world run because all draws are keyed by the global cell. */
@@ -178,8 +177,8 @@ int pd_read_step_log(pd_sim* sim, uint64_t* rows, uint32_t max_rows, uint32_t* n
 /* Per-kernel device timing: with profiling on, pd_step records a CUDA event between every
  * two kernel launches; pd_read_profile synchronises `stream` and returns the accumulated
  * milliseconds per kernel, in launch order: begin_step, risk_resolve, play_travel, move_commit,
- * move_retry, repro_claim, repro_commit, repro_retry, punish, finalize. */
-#define PDABM_NUM_KERNELS 10
+ * move_retry, claim_punish, repro_commit, repro_retry, finalize. */
+#define PDABM_NUM_KERNELS 9
 int pd_set_profile(pd_sim* sim, int on);
 int pd_read_profile(pd_sim* sim, double kernel_ms[PDABM_NUM_KERNELS], uint32_t* steps, void* stream);
 
@@ -188,7 +187,7 @@ int pd_get_step(pd_sim* sim, uint32_t* step);
 int pd_set_step(pd_sim* sim, uint32_t step);
 
 /* Number of model steps this handle ran by replaying a captured CUDA graph (pd_config.use_graphs)
- * rather than by launching the 10 kernels one by one. */
+ * rather than by launching the 9 kernels one by one. */
 int pd_graph_replays(pd_sim* sim, uint64_t* steps);
 
 /* HOST-buffer entry point (what a host-side caller without device buffers binds):

@@ -244,7 +244,7 @@ class LiteralModel:
                 a["status"] = MOVING                                # :857
                 nx, ny = self.pos_from_moore_seq(a["x"], a["y"], found)
                 a["req"] = self.pos_to_bucket_id(nx, ny)            # :861-862
-                msgs[a["req"]].append(dict(id=a["id"], roll=a["roll"], tag=a["roll_cell"], x=nx, y=ny))
+                msgs[a["req"]].append(dict(id=a["id"], roll=a["roll"], tag=7 - found, x=nx, y=ny))
             self.agents = survivors
             for a in self.agents:                                   # move_response :881-960
                 if a["status"] != MOVING:
@@ -322,7 +322,7 @@ class LiteralModel:
                 a["rseq"] = rseq                                    # :1111
                 nx, ny = self.pos_from_moore_seq(a["x"], a["y"], found)
                 a["req"] = self.pos_to_bucket_id(nx, ny)
-                msgs[a["req"]].append(dict(id=a["id"], roll=a["roll"], tag=a["roll_cell"], x=nx, y=ny))
+                msgs[a["req"]].append(dict(id=a["id"], roll=a["roll"], tag=7 - found, x=nx, y=ny))
             newborn = []
             for a in self.agents:                                   # god_multiply :1144-1335
                 if not (overpopulated < 1 and a["status"] == ATTEMPTING_REPRODUCTION):

@@ -22,8 +22,9 @@ it follows.  Three deliberate restatements (DESIGN.md "Semantics"):
   game without noise needs no random call of its own; the noise rolls (:611-612)
   come from four calls per responder (streams 1..4, two sub-steps per call);
 * travel / reproduction claims are ordered by a 32-bit word of a per-cell call and
-  ties are broken by the *cell index* the agent stood on when it drew (the
-  reference uses the agent id, model.py:929, :1192);
+  ties are broken by where the claimant stands as seen from the contested cell
+  (7 - claimed direction, unique among the rivals of one cell; the reference
+  uses the agent id, model.py:929, :1192);
 * the list-index cull (model.py:1343, :1354) is replaced by "the surplus
   newborns with the lowest Philox cull priority die" (SURVEY Appendix B-4).
 """
@@ -487,6 +488,15 @@ class Oracle:
                 continue
             break
 
+    @staticmethod
+    def _claim_key(roll, direction) -> np.ndarray:
+        """Contest key of a claim (:929, :1192): the highest roll wins; equal rolls (2^-32 per pair of rivals) are
+        decided by where the claimant stands as seen from the contested cell, j = 7 - claimed direction, which is
+        unique among the rivals of one cell and takes the place of the reference's id comparison.  +1 keeps 0 for
+        'no claim'."""
+        j = (7 - np.asarray(direction)).astype(np.uint64)
+        return ((np.asarray(roll).astype(np.uint64) << np.uint64(3)) | j) + np.uint64(1)
+
     def _probe(self, sel, start, seq):
         """Triangular probe over neighbour_list, model.py:826-839 / :1088-1101.
 
@@ -543,7 +553,7 @@ class Oracle:
         sub["request_bucket"][g] = rb                                           # :862
         # one message per requester keyed by the requested bucket (:864-868); the reader keeps
         # the maximum (roll, tag) so we fold the bucket's messages into that maximum here
-        key = ((self.roll[g].astype(np.uint64) << np.uint64(32)) | self.roll_cell[g].astype(np.uint64)) + np.uint64(1)
+        key = self._claim_key(self.roll[g], lg)
         np.maximum.at(self.claim_key, rb, key)
         nd = int(dead.sum())
         self.stats["travel_deaths"] += nd
@@ -562,7 +572,7 @@ class Oracle:
             claimed = self.claim_key[nb] != 0
             # any claim on a neighbouring cell marks that slot occupied -- :922-925, :934
             self.nb_list[sel, i] = np.where(claimed, -1, self.nb_list[sel, i])
-        mine = ((self.roll[sel].astype(np.uint64) << np.uint64(32)) | self.roll_cell[sel].astype(np.uint64)) + np.uint64(1)
+        mine = self._claim_key(self.roll[sel], (sub["last_move_attempt"][sel] - 1) % NDIR)
         won = self.claim_key[rb] == mine                                        # :929-935, :940
         self.status[sel[~won]] = MOVEMENT_UNRESOLVED                            # :941
         w = sel[won]
@@ -646,7 +656,7 @@ class Oracle:
         self.status[g] = ATTEMPTING_REPRODUCTION                                # :1119
         rb = self._nb_bucket(g, lg)                                             # :1123
         sub["request_bucket"][g] = rb                                           # :1124
-        key = ((self.roll[g].astype(np.uint64) << np.uint64(32)) | self.roll_cell[g].astype(np.uint64)) + np.uint64(1)
+        key = self._claim_key(self.roll[g], lg)
         np.maximum.at(self.repro_key, rb, key)                                  # :1126-1130
         self.stats["repro_claims"] += int(g.size)
 
@@ -669,7 +679,7 @@ class Oracle:
             nb = self._nb_bucket(sel, i)
             claimed = self.repro_key[nb] != 0
             self.nb_list[sel, i] = np.where(claimed, -1, self.nb_list[sel, i])  # :1184-1187, :1197
-        mine = ((self.roll[sel].astype(np.uint64) << np.uint64(32)) | self.roll_cell[sel].astype(np.uint64)) + np.uint64(1)
+        mine = self._claim_key(self.roll[sel], (sub["last_reproduction_attempt"][sel] - 1) % NDIR)
         won = self.repro_key[rb] == mine                                        # :1192-1198, :1203
         w = sel[won]
         if w.size == 0:
