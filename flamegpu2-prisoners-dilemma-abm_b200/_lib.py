@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpdabm.so")
+# PDABM_LIB: developer hook for A/B timing of two builds of the library in one GPU session
+LIB_PATH = os.environ.get("PDABM_LIB") or os.path.join(_HERE, "libpdabm.so")
 
 PD_OK = 0
 PD_TF_TRAIT_MASK = 0x03

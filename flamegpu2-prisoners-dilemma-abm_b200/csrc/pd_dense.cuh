@@ -129,6 +129,35 @@ __device__ __forceinline__ void wappend4(unsigned int* cnt, uint32_t* list, uint
     if (occ4 & 0x80000000u) list[base + n0 + n1 + n2 + __popc(m3 & lt)] = v[3];
 }
 
+// Thread-level append of up to four values (byte k of `occ4` has bit 7 set = v[k] goes on the list): ONE shared
+// atomic per thread with its count, then plain stores.  No ballots, and with a per-lane count ptxas leaves the
+// atomic alone (for a uniform increment it wraps it in a vote / elect / shuffle sequence of ~15 issue slots).
+__device__ __forceinline__ void tappend4(unsigned int* cnt, uint32_t* list, uint32_t occ4, const uint32_t (&v)[4]) {
+    if (!occ4) return;
+    unsigned int slot = satom_add(cnt, (unsigned int)__popc(occ4));
+    if (occ4 & 0x80u) list[slot++] = v[0];
+    if (occ4 & 0x8000u) list[slot++] = v[1];
+    if (occ4 & 0x800000u) list[slot++] = v[2];
+    if (occ4 & 0x80000000u) list[slot] = v[3];
+}
+
+// the same for a list of tile-local cell indices: appends idx0 + k for every byte k of `occ4` that has bit 7 set
+__device__ __forceinline__ void wappend4_idx(unsigned int* cnt, uint16_t* list, uint32_t occ4, uint32_t idx0) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t m0 = __ballot_sync(FULL, occ4 & 0x80u), m1 = __ballot_sync(FULL, occ4 & 0x8000u);
+    const uint32_t m2 = __ballot_sync(FULL, occ4 & 0x800000u), m3 = __ballot_sync(FULL, occ4 & 0x80000000u);
+    const int n0 = __popc(m0), n1 = __popc(m1), n2 = __popc(m2), total = n0 + n1 + n2 + __popc(m3);
+    if (total == 0) return;
+    unsigned int base = 0;
+    if (lane == 0) base = satom_add(cnt, (unsigned int)total);
+    base = __shfl_sync(FULL, base, 0);
+    if (occ4 & 0x80u) list[base + __popc(m0 & lt)] = (uint16_t)idx0;
+    if (occ4 & 0x8000u) list[base + n0 + __popc(m1 & lt)] = (uint16_t)(idx0 + 1u);
+    if (occ4 & 0x800000u) list[base + n0 + n1 + __popc(m2 & lt)] = (uint16_t)(idx0 + 2u);
+    if (occ4 & 0x80000000u) list[base + n0 + n1 + n2 + __popc(m3 & lt)] = (uint16_t)(idx0 + 3u);
+}
+
 // entry i of the payoff table: bits 0-1 the challenger's strategy against my trait, 2-3 my strategy against
 // its trait (:599-600), 4 the challenger's RANDOM coin, 5 mine (:631, :664), 6 the challenger's noise flip,
 // 7 mine (:638-640, :672-674) -> my payoff (:677-689)
@@ -265,7 +294,11 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
                 r4 = make_uint4(rr[0], rr[1], rr[2], rr[3]);
             }
             if (j < NITEM) *reinterpret_cast<uint4*>(s_R + sw[it]) = r4;
+#ifdef PD_EXP_WAPPEND
             if (it * NT < NI) wappend4(&s_n[0], s_cells, j < NI ? occ4 : 0u, v);
+#else
+            if (j < NI) tappend4(&s_n[0], s_cells, occ4, v);
+#endif
         }
     }
     asm volatile("cp.async.wait_all;");
@@ -313,7 +346,9 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
             const bool mover = any_nb == 0u || (!any && (act7_challenge || act0_respond));
             s_out[cl] = (uint8_t)(TF_OCC | ((rme >> 1) & TF_TRAIT));
             s_e[cl] = e;
-            if (mover) { s_mover[satom_add(&s_n[2], 1u)] = (uint16_t)cl; ++n_movers; }
+            // (+1 spelled as my word's OCC bit: for an increment it can prove uniform, ptxas wraps the atomic in a
+            // vote / elect / shuffle sequence of ~15 issue slots)
+            if (mover) { s_mover[satom_add(&s_n[2], rme >> 31)] = (uint16_t)cl; ++n_movers; }
         }
     }
     __syncthreads();
@@ -371,7 +406,9 @@ __global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ P
                 // waits for the CTA's outstanding reductions), with the priority drawn again rather than kept
                 post_claim(p.claim + nb_local(p, x, y, dir), claim_word(step, CLAIM_TRAVEL, rng(p, gcell_of(p, x, y), S_TRAVEL).x, dir));
                 p.cl_cell[base + k] = (y << p.log2W) | x;
-                p.cl_dir[base + k] = (uint8_t)dir;
+                p.cl_e[base + k] = s_e[cl];  // (after the travel cost)
+                // the mover's trait and strategies ride along (bits 1-2 and 3-10 of its word)
+                p.cl_aux[base + k] = (uint16_t)((uint32_t)dir | ((s_R[((cl >> LOG_TW) + 1) * SWR + 4 + (cl & (TW - 1))] & 0x7FEu) << 2));
             }
         }
     }
@@ -447,56 +484,70 @@ __global__ void __launch_bounds__(NT) k_claim_punish(const __grid_constant__ Par
     load_tile_vec<TW, TH, 1>(p, p.tfB, s_tf, x0, y0);
     __syncthreads();
     unsigned int n_occ = 0, n_dead = 0;
+    uint32_t par_bits = 0;  // bit 4 * it + k: cell k of my group of iteration it holds an agent that may reproduce
+    static_assert(4 * NIT <= 32, "parent bits");
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
         const int i = tid + it * NT;
-        if (i >= NC / 4) break;
+        if (i >= NC / 4) break;  // (warp-uniform)
         const int ly = (i * 4) / TW, lx = (i * 4) - ly * TW;
         const int si = (ly + 1) * SW + lx + 16;
         const uint32_t t4 = *reinterpret_cast<const uint32_t*>(s_tf + si);
         const uint32_t occ4 = t4 & 0x80808080u;
         n_occ += __popc(occ4);
         const float4 e4 = e_pre[it];
-        if (occ4 && p.max_children > 0u) {  // :1054
-            // :978-979
-            const uint32_t par4 = occ4 & ((e4.x >= p.reproduce_min_energy ? 0x80u : 0u) | (e4.y >= p.reproduce_min_energy ? 0x8000u : 0u)
-                                          | (e4.z >= p.reproduce_min_energy ? 0x800000u : 0u)
-                                          | (e4.w >= p.reproduce_min_energy ? 0x80000000u : 0u));
-            for (uint32_t m = par4; m; m &= m - 1) s_par[satom_add(&s_n[0], 1u)] = (uint16_t)(i * 4 + ((__ffs(m) - 1) >> 3));
-        }
-        if (owned) {  // ---- cost of living, as non-parents (:1357-1368)
-            float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+        const float ein[4] = {e4.x, e4.y, e4.z, e4.w};
+        // :978-979, :1054 -- the agents that may reproduce, compacted with four ballots per warp
+        uint32_t par4 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) par4 |= ein[k] >= p.reproduce_min_energy ? (0x80u << (8 * k)) : 0u;
+        par4 = p.max_children > 0u ? (par4 & occ4) : 0u;
+        par_bits |= ((par4 >> 7) & 1u) << (4 * it) | ((par4 >> 15) & 1u) << (4 * it + 1) | ((par4 >> 23) & 1u) << (4 * it + 2)
+                    | ((par4 >> 31) & 1u) << (4 * it + 3);
+        if (owned) {  // ---- cost of living, as non-parents (:1357-1368); branch-free per cell
+            float ev[4];
             uint32_t dead4 = 0, risk4 = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t bit = 0x80u << (8 * k);
-                float e = ev[k];
-                const bool alive = punish(p, e);
-                if (occ4 & bit) {
-                    if (!alive) dead4 |= bit;
-                    else if (e <= p.risk_thr) risk4 |= bit;
-                    ev[k] = alive ? e : 0.0f;
-                } else {
-                    ev[k] = 0.0f;
-                }
+                const float e = __fsub_rn(fminf(ein[k], p.max_energy), p.cost_of_living);
+                dead4 |= e > 0.0f ? 0u : bit;
+                risk4 |= e <= p.risk_thr ? bit : 0u;
+                ev[k] = e;
             }
             static_assert(TF_OCC == 0x80u && TF_TRAIT == 0x03u, "flag layout");
+            dead4 &= occ4;
             const uint32_t live4 = occ4 & ~dead4;
+            risk4 &= live4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ev[k] = (live4 >> (8 * k + 7)) & 1u ? ev[k] : 0.0f;
             n_dead += __popc(dead4);
             if (p.want_counts)
                 for (uint32_t m = live4; m; m &= m - 1) {
                     const int b = (__ffs(m) - 1) >> 3;
                     atomicAdd(&s_bins[count_bin((st_pre[it] >> (8 * b)) & 0xFFu, (t4 >> (8 * b)) & TF_TRAIT)], 1u);
                 }
-            for (uint32_t m = risk4; m; m &= m - 1) s_risk[satom_add(&s_n[4], 1u)] = (uint16_t)(i * 4 + ((__ffs(m) - 1) >> 3));
+            if (risk4)  // rare
+                for (uint32_t m = risk4; m; m &= m - 1) s_risk[satom_add(&s_n[4], 1u)] = (uint16_t)(i * 4 + ((__ffs(m) - 1) >> 3));
             const size_t off = ((size_t)(y0 + ly) << p.log2W) + x0 + lx;
             // OCC | trait for the survivors, 0 for the dead, the empty and the vacated
             *reinterpret_cast<uint32_t*>(p.tfA + off) = t4 & (live4 | (live4 >> 6) | (live4 >> 7));
             *reinterpret_cast<float4*>(p.E0 + off) = make_float4(ev[0], ev[1], ev[2], ev[3]);
         }
     }
-    if (n_occ) satom_add(&s_n[3], n_occ);
-    if (n_dead) satom_add(&s_n[6], n_dead);
+    if (par_bits) {  // one shared atomic per thread with its count, then plain stores (no ballots)
+        unsigned int slot = satom_add(&s_n[0], (unsigned int)__popc(par_bits));
+        for (uint32_t m = par_bits; m; m &= m - 1) {
+            const int b = __ffs(m) - 1;
+            s_par[slot++] = (uint16_t)((tid + (b >> 2) * NT) * 4 + (b & 3));
+        }
+    }
+    n_occ = __reduce_add_sync(FULL, n_occ);
+    n_dead = __reduce_add_sync(FULL, n_dead);
+    if ((tid & 31) == 0) {
+        if (n_occ) satom_add(&s_n[3], n_occ);
+        if (n_dead) satom_add(&s_n[6], n_dead);
+    }
     __syncthreads();
     const unsigned int n_par = s_n[0];
     const uint32_t step = __ldg(&p.ctr->step_no);
@@ -542,8 +593,10 @@ __global__ void __launch_bounds__(NT) k_claim_punish(const __grid_constant__ Par
                 // :1123-1130: the request goes to the target cell (posted after the CTA's last barrier: a barrier
                 // waits for the CTA's outstanding reductions)
                 post_claim(p.claim + nb_local(p, x, y, dir), claim_word(step, CLAIM_REPRO, s_prio[k], dir));
-                p.cl_cell[base + k] = (y << p.log2W) | x;
-                p.cl_dir[base + k] = (uint8_t)dir;
+                const uint32_t cell = (y << p.log2W) | x;
+                p.cl_cell[base + k] = cell;
+                p.cl_e[base + k] = p.E1[cell];  // (this CTA has just read the tile: an L2 hit)
+                p.cl_aux[base + k] = (uint16_t)((uint32_t)dir | (((uint32_t)s_tf[(cl / TW + 1) * SW + cl % TW + 16] & TF_TRAIT) << 3));
             }
         }
     }
@@ -562,14 +615,14 @@ __global__ void __launch_bounds__(NT) k_claim_punish(const __grid_constant__ Par
 
 // A parent that has won its claim (god_multiply, :1211-1213) re-derives its layer-7 outcome: k_claim_punish
 // charged it as a non-parent.  e1 = its energy when it entered layer 6 (E1 is read-only), `cell` its cell, owned
-// rows only.  Almost always only the energy changes; deaths, counts and the at-risk list are corrected if not.
-__device__ __forceinline__ void parent_outcome(const Params& p, uint32_t cell, float e1, uint32_t strat, uint32_t trait) {
+// rows only (nobody writes a parent's strat / tfB entries during the reproduction rounds).  Almost always only the energy changes; deaths, counts and the at-risk list are corrected if not.
+__device__ __forceinline__ void parent_outcome(const Params& p, uint32_t cell, float e1, uint32_t trait) {
     const Outcome a = outcome_of(p, e1, false), b = outcome_of(p, e1, true);
     p.E0[cell] = b.e;
     if (a.alive != b.alive) {
         p.tfA[cell] = (uint8_t)(b.alive ? (TF_OCC | trait) : 0u);
         atomicAdd(&p.ctr->living_deaths, b.alive ? ~0ull : 1ull);  // (+1, or -1 if a negative cost revives it)
-        if (p.want_counts) atomicAdd(&p.ctr->bins[count_bin(strat, trait)], b.alive ? 1ull : ~0ull);
+        if (p.want_counts) atomicAdd(&p.ctr->bins[count_bin(p.strat[cell], trait)], b.alive ? 1ull : ~0ull);
     }
     if (b.risk && !a.risk) {  // (an entry that is no longer at risk is harmless: k_risk_resolve replays it exactly)
         const unsigned int slot = atomicAdd(&p.ctr->risk_next_n, 1u);

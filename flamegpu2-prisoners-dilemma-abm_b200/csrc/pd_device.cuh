@@ -124,12 +124,15 @@ struct Params {
     // rounds carry a higher tag).  Replaces the move / reproduction request messages keyed by the target's bucket
     // (:864-868, :1126-1130) and the "highest roll wins" scan of their readers (:929, :1192).
     unsigned long long* claim;
-    // round 1 claimants (the travel phase's, then the reproduction phase's): cell and claimed direction
-    uint32_t* cl_cell; uint8_t* cl_dir;
+    // Round 1 claimants (the travel phase's, then the reproduction phase's).  An entry carries what the commit
+    // needs of the claimant, so that it costs the commit no random reads: cell, energy (E1 of the cell), and
+    // aux = claimed direction | trait << 3 | strategies << 5 (strategies: travel only)
+    uint32_t* cl_cell; float* cl_e; uint16_t* cl_aux;
     uint32_t* rt_cell; uint8_t* rt_state; uint8_t* rt_aux;  // the losers of round 1: rounds 2..8 (travel, then reproduction)
-    uint32_t* nb_cell;
-    float* nb_e; uint16_t* nb_gene;  // the newborn's energy and strategies | trait << 8 (it is written into the
-                                     // planes only if it survives the cull, or when retry rounds must see it)
+    // newborns: the child's cell and the direction the parent claimed (the parent is the child's neighbour 7 - dir).
+    // The child itself -- energy, strategies, trait -- is made from the parent's (unchanged) E1 / strat / tfB only if
+    // it survives the cull: near the carrying capacity 99 % do not
+    uint32_t* nb_cell; uint8_t* nb_dir;
     Counters* ctr;
 };
 
@@ -156,6 +159,10 @@ __device__ __forceinline__ uint32_t nb_row(const Params& p, uint32_t y, int dy) 
 __device__ __forceinline__ uint32_t nb_local(const Params& p, uint32_t x, uint32_t y, int d) {
     const uint32_t nx = (x + (uint32_t)DX(d)) & (p.W - 1);
     return (nb_row(p, y, DY(d)) << p.log2W) | nx;
+}
+// the parent of the newborn at `cell`: it claimed direction `dir`, so it is the child's neighbour 7 - dir
+__device__ __forceinline__ uint32_t parent_of(const Params& p, uint32_t cell, uint32_t dir) {
+    return nb_local(p, cell & (p.W - 1), cell >> p.log2W, 7 - (int)dir);
 }
 __device__ __forceinline__ bool row_owned(const Params& p, uint32_t y) {
     return y >= p.own_y0 && y < p.own_y1;
@@ -184,10 +191,14 @@ __device__ __forceinline__ unsigned long long claim_word(uint32_t step, uint32_t
 // A reduction on a word that misses in the L2 is served far more slowly than a load (measured: 16 M reductions
 // per ms against > 100 M random sector loads): the claimant asks for the word's line ahead of posting
 __device__ __forceinline__ void prefetch_claim(const unsigned long long* word) {
+#ifndef PD_EXP_NO_PREFETCH
     asm volatile("prefetch.global.L2 [%0];" ::"l"(word));
+#endif
 }
 __device__ __forceinline__ void post_claim(unsigned long long* word, unsigned long long v) {
+#ifndef PD_EXP_NO_RED
     asm volatile("red.global.max.u64 [%0], %1;" ::"l"(word), "l"(v) : "memory");
+#endif
 }
 
 // ---- the game as the RESPONDER sees it (play_response, :599-689) --------------------------

@@ -157,9 +157,10 @@ __global__ void __launch_bounds__(BS) k_risk_resolve(const __grid_constant__ Par
 // address, which the L2 serialises (that alone was 2/3 of k_repro_commit's time, profiles/README.md).
 constexpr int COMMIT_NT = 256, COMMIT_K = 4, COMMIT_CHUNK = COMMIT_NT * COMMIT_K;
 
-// k_move_commit: move_response (:881-960), round 1.  A winner relocates -- energy, strategies and trait go to
-// the target cell -- and leaves a GHOST that keeps blocking movers this step (quirk B-13); a loser joins the
-// retry list with the direction it claimed.
+// k_move_commit: move_response (:881-960), round 1.  A winner relocates -- energy, strategies and trait (they
+// came with the list entry) go to the target cell -- and leaves a GHOST that keeps blocking movers this step
+// (quirk B-13); a loser joins the retry list with the direction it claimed.  One random read per claimant (the
+// claim word), four random writes per winner.
 __global__ void __launch_bounds__(COMMIT_NT) k_move_commit(const __grid_constant__ Params p) {
     __shared__ uint32_t s_lost_cell[COMMIT_CHUNK];
     __shared__ uint8_t s_lost_state[COMMIT_CHUNK];
@@ -173,34 +174,32 @@ __global__ void __launch_bounds__(COMMIT_NT) k_move_commit(const __grid_constant
     for (unsigned int c0 = blockIdx.x * COMMIT_CHUNK; c0 < n; c0 += gridDim.x * COMMIT_CHUNK) {
         if (tid == 0) s_n[0] = 0;
         __syncthreads();
-        uint32_t cell[COMMIT_K], tgt[COMMIT_K], st[COMMIT_K], t[COMMIT_K];
-        int d[COMMIT_K];
+        uint32_t cell[COMMIT_K], tgt[COMMIT_K], aux[COMMIT_K];
         unsigned long long top[COMMIT_K];
         float e[COMMIT_K];
 #pragma unroll
         for (int k = 0; k < COMMIT_K; ++k) {
             const unsigned int i = c0 + k * COMMIT_NT + tid;
             cell[k] = i < n ? p.cl_cell[i] : 0u;
-            d[k] = i < n ? (int)p.cl_dir[i] : 0;
+            aux[k] = i < n ? (uint32_t)p.cl_aux[i] : 0u;
+            e[k] = i < n ? p.cl_e[i] : 0.0f;
         }
 #pragma unroll
-        for (int k = 0; k < COMMIT_K; ++k) {  // the payload is requested together with the verdict: one round trip
-            tgt[k] = nb_local(p, cell[k] & (p.W - 1), cell[k] >> p.log2W, d[k]);
+        for (int k = 0; k < COMMIT_K; ++k) {
+            tgt[k] = nb_local(p, cell[k] & (p.W - 1), cell[k] >> p.log2W, (int)(aux[k] & 7u));
             top[k] = __ldcg(p.claim + tgt[k]);
-            e[k] = __ldcg(p.E1 + cell[k]);
-            st[k] = __ldcg(p.strat + cell[k]);
-            t[k] = __ldcg(p.tfB + cell[k]);
         }
 #pragma unroll
         for (int k = 0; k < COMMIT_K; ++k) {
             const bool valid = c0 + k * COMMIT_NT + tid < n;
+            const int d = (int)(aux[k] & 7u);
             const uint32_t x = cell[k] & (p.W - 1), y = cell[k] >> p.log2W;
-            const unsigned long long mine = claim_word(step, CLAIM_TRAVEL, rng(p, gcell_of(p, x, y), S_TRAVEL).x, d[k]);
+            const unsigned long long mine = claim_word(step, CLAIM_TRAVEL, rng(p, gcell_of(p, x, y), S_TRAVEL).x, d);
             const bool won = valid && top[k] == mine;
             if (won) {  // :946-956
                 p.E1[tgt[k]] = e[k];
-                p.strat[tgt[k]] = (uint8_t)st[k];
-                p.tfB[tgt[k]] = (uint8_t)(TF_OCC | (t[k] & TF_TRAIT));
+                p.strat[tgt[k]] = (uint8_t)(aux[k] >> 5);
+                p.tfB[tgt[k]] = (uint8_t)(TF_OCC | ((aux[k] >> 3) & TF_TRAIT));
                 p.tfB[cell[k]] = (uint8_t)TF_GHOST;
                 if (row_owned(p, tgt[k] >> p.log2W)) ++moved;
             }
@@ -208,7 +207,7 @@ __global__ void __launch_bounds__(COMMIT_NT) k_move_commit(const __grid_constant
             const uint32_t slot = wappend(&s_n[0], lost);
             if (lost) {
                 s_lost_cell[slot] = cell[k];
-                s_lost_state[slot] = (uint8_t)(0xC0u | (uint32_t)d[k]);
+                s_lost_state[slot] = (uint8_t)(0xC0u | (uint32_t)d);
             }
         }
         __syncthreads();
@@ -234,17 +233,16 @@ __global__ void __launch_bounds__(COMMIT_NT) k_move_commit(const __grid_constant
 }
 
 // k_repro_commit: god_multiply (:1144-1335), round 1.  A winner pays the reproduction cost (parent_outcome: its
-// layer-7 result is re-derived from E1, which stays read-only) and makes its child from its own energy /
-// strategies.  The child only goes on the newborn list, with its energy and strategies: near the carrying
-// capacity almost every newborn is culled in the same step, so it enters the planes in k_finalize if it survives,
-// or when retry rounds must see its cell blocked.  A child born into a ghost row belongs to the neighbour slab:
-// here it only blocks its cell.
+// layer-7 result is re-derived from its energy, which came with the list entry) and its child goes on the newborn
+// list -- as (cell, direction) only: near the carrying capacity almost every newborn is culled in the same step,
+// so the child is made (make_child) in k_finalize if it survives, from the parent's unchanged E1 / strat / tfB
+// entries; it blocks its cell when retry rounds must see it.  A child born into a ghost row belongs to the
+// neighbour slab: here it only blocks its cell.  One random read per claimant, one random write per winner.
 __global__ void __launch_bounds__(COMMIT_NT) k_repro_commit(const __grid_constant__ Params p) {
     __shared__ uint32_t s_lost_cell[COMMIT_CHUNK];
     __shared__ uint8_t s_lost_state[COMMIT_CHUNK];
     __shared__ uint32_t s_nb_cell[COMMIT_CHUNK];
-    __shared__ float s_nb_e[COMMIT_CHUNK];
-    __shared__ uint16_t s_nb_gene[COMMIT_CHUNK];
+    __shared__ uint8_t s_nb_dir[COMMIT_CHUNK];
     __shared__ unsigned int s_n[4];  // 0 losers of this chunk, 1 newborns, 2 / 3 their bases in the global lists
     Counters* ctr = p.ctr;
     unsigned int n = ctr->rp_n;
@@ -254,55 +252,45 @@ __global__ void __launch_bounds__(COMMIT_NT) k_repro_commit(const __grid_constan
     for (unsigned int c0 = blockIdx.x * COMMIT_CHUNK; c0 < n; c0 += gridDim.x * COMMIT_CHUNK) {
         if (tid < 2) s_n[tid] = 0;
         __syncthreads();
-        uint32_t cell[COMMIT_K], tgt[COMMIT_K], st[COMMIT_K], t[COMMIT_K];
-        int d[COMMIT_K];
+        uint32_t cell[COMMIT_K], tgt[COMMIT_K], aux[COMMIT_K];
         unsigned long long top[COMMIT_K];
         float e[COMMIT_K];
 #pragma unroll
         for (int k = 0; k < COMMIT_K; ++k) {
             const unsigned int i = c0 + k * COMMIT_NT + tid;
             cell[k] = i < n ? p.cl_cell[i] : 0u;
-            d[k] = i < n ? (int)p.cl_dir[i] : 0;
+            aux[k] = i < n ? (uint32_t)p.cl_aux[i] : 0u;
+            e[k] = i < n ? p.cl_e[i] : 0.0f;
         }
 #pragma unroll
         for (int k = 0; k < COMMIT_K; ++k) {
-            tgt[k] = nb_local(p, cell[k] & (p.W - 1), cell[k] >> p.log2W, d[k]);
+            tgt[k] = nb_local(p, cell[k] & (p.W - 1), cell[k] >> p.log2W, (int)(aux[k] & 7u));
             top[k] = __ldcg(p.claim + tgt[k]);
-            e[k] = __ldcg(p.E1 + cell[k]);
-            st[k] = __ldcg(p.strat + cell[k]);
-            t[k] = __ldcg(p.tfB + cell[k]);
         }
 #pragma unroll
         for (int k = 0; k < COMMIT_K; ++k) {
             const bool valid = c0 + k * COMMIT_NT + tid < n;
+            const int d = (int)(aux[k] & 7u);
             const uint32_t x = cell[k] & (p.W - 1), y = cell[k] >> p.log2W;
-            const uint64_t g = gcell_of(p, x, y);
-            const unsigned long long mine = claim_word(step, CLAIM_REPRO, rng(p, g, S_REPRO).x, d[k]);
+            const unsigned long long mine = claim_word(step, CLAIM_REPRO, rng(p, gcell_of(p, x, y), S_REPRO).x, d);
             const bool won = valid && top[k] == mine;
             bool born = false;
-            float ce = 0.0f;
-            uint32_t gene = 0;
-            if (won) {
-                // REPRODUCTION_COMPLETE (:1211-1213, :1331); the child (:1216-1328): my trait, its own energy and strategies
-                const uint32_t trait = t[k] & TF_TRAIT;
-                uint32_t cs;
-                make_child(p, g, st[k], trait, __fsub_rn(e[k], p.reproduce_cost), ce, cs);
-                if (row_owned(p, y)) parent_outcome(p, cell[k], e[k], st[k], trait);
-                gene = cs | (trait << 8);
+            if (won) {  // REPRODUCTION_COMPLETE (:1211-1213, :1331)
+                const uint32_t trait = (aux[k] >> 3) & TF_TRAIT;
+                if (row_owned(p, y)) parent_outcome(p, cell[k], e[k], trait);
                 born = row_owned(p, tgt[k] >> p.log2W);
                 if (!born) p.tfB[tgt[k]] = (uint8_t)(TF_OCC | TF_NEWBORN | trait);
             }
             const uint32_t bslot = wappend(&s_n[1], born);
             if (born) {
                 s_nb_cell[bslot] = tgt[k];
-                s_nb_e[bslot] = ce;
-                s_nb_gene[bslot] = (uint16_t)gene;
+                s_nb_dir[bslot] = (uint8_t)d;
             }
             const bool lost = valid && !won;  // stays ATTEMPTING_REPRODUCTION (:1203-1205)
             const uint32_t lslot = wappend(&s_n[0], lost);
             if (lost) {
                 s_lost_cell[lslot] = cell[k];
-                s_lost_state[lslot] = (uint8_t)(0xC0u | (uint32_t)d[k]);
+                s_lost_state[lslot] = (uint8_t)(0xC0u | (uint32_t)d);
             }
         }
         __syncthreads();
@@ -330,8 +318,7 @@ __global__ void __launch_bounds__(COMMIT_NT) k_repro_commit(const __grid_constan
             } else {
                 for (unsigned int k = tid; k < n_born; k += COMMIT_NT) {
                     p.nb_cell[base + k] = s_nb_cell[k];
-                    p.nb_e[base + k] = s_nb_e[k];
-                    p.nb_gene[base + k] = s_nb_gene[k];
+                    p.nb_dir[base + k] = s_nb_dir[k];
                 }
             }
         }
@@ -434,8 +421,10 @@ __global__ void __launch_bounds__(BS) k_repro_retry(const __grid_constant__ Para
             // the newborns of round 1 are only on the newborn list so far: they must block their cells now
             unsigned int nb1 = __ldcg(&ctr->nb_n);
             if (nb1 > p.list_cap) nb1 = p.list_cap;
-            for (unsigned int i = t0; i < nb1; i += stride)
-                tf[p.nb_cell[i]] = (uint8_t)(TF_OCC | TF_NEWBORN | ((uint32_t)(p.nb_gene[i] >> 8) & TF_TRAIT));
+            for (unsigned int i = t0; i < nb1; i += stride) {
+                const uint32_t c = p.nb_cell[i];
+                tf[c] = (uint8_t)(TF_OCC | TF_NEWBORN | (__ldcg(tf + parent_of(p, c, p.nb_dir[i])) & TF_TRAIT));
+            }
             if (t0 == 0) ctr->nb_flagged = 1u;
             grid_sync(ctr->barrier, gridDim.x);
         }
@@ -470,8 +459,7 @@ __global__ void __launch_bounds__(BS) k_repro_retry(const __grid_constant__ Para
         for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
             const unsigned int i = i0 + threadIdx.x;
             bool born = false;
-            uint32_t tgt = 0, gene = 0;
-            float ce = 0.0f;
+            uint32_t tgt = 0, dir = 0;
             if (i < n && (p.rt_state[i] & 0x80u)) {
                 const uint32_t cell = p.rt_cell[i];
                 const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
@@ -482,13 +470,9 @@ __global__ void __launch_bounds__(BS) k_repro_retry(const __grid_constant__ Para
                 const unsigned long long mine = claim_word(step, CLAIM_REPRO + (uint32_t)round, rng(p, g, S_REPRO).x, d);
                 if (top == mine) {
                     const uint32_t t = __ldcg(tf + cell);
-                    const float e1 = __ldcg(p.E1 + cell);
-                    const uint32_t st = __ldcg(p.strat + cell);
-                    uint32_t cs;
-                    make_child(p, g, st, t & TF_TRAIT, __fsub_rn(e1, p.reproduce_cost), ce, cs);  // :1211-1213
-                    if (row_owned(p, y)) parent_outcome(p, cell, e1, st, t & TF_TRAIT);
+                    if (row_owned(p, y)) parent_outcome(p, cell, __ldcg(p.E1 + cell), t & TF_TRAIT);  // :1211-1213
                     tf[tgt] = (uint8_t)(TF_OCC | TF_NEWBORN | (t & TF_TRAIT));  // blocks its cell in later rounds
-                    gene = cs | ((t & TF_TRAIT) << 8);  // (REPRODUCTION_COMPLETE: it leaves the list -- one child per step, B-6)
+                    dir = (uint32_t)d;  // (REPRODUCTION_COMPLETE: it leaves the list -- one child per step, B-6)
                     born = row_owned(p, tgt >> p.log2W);  // a child in the ghost zone belongs to the neighbour slab
                     p.rt_state[i] = 0x40u;
                 } else {
@@ -499,8 +483,7 @@ __global__ void __launch_bounds__(BS) k_repro_retry(const __grid_constant__ Para
             if (born) {
                 if (slot < p.list_cap) {
                     p.nb_cell[slot] = tgt;
-                    p.nb_e[slot] = ce;
-                    p.nb_gene[slot] = (uint16_t)gene;
+                    p.nb_dir[slot] = (uint8_t)dir;
                 } else atomicExch(&ctr->overflow, 1u);
             }
         }
@@ -716,14 +699,21 @@ __device__ __forceinline__ void fin_apply(const Params& p, unsigned int nb, bool
             const uint32_t cell = p.nb_cell[i];
             bool survive = true;
             if (cull) survive = keep != 0 && cull_key(p, cell) >= tau;
-            if (survive) {  // only now does the newborn enter the planes
-                const uint32_t gene = p.nb_gene[i];
-                const float ce = p.nb_e[i];
-                p.tfA[cell] = (uint8_t)(TF_OCC | ((gene >> 8) & TF_TRAIT));
+            if (survive) {
+                // Only now is the child made (:1216-1328: the parent's trait, its own energy and strategies) and
+                // enters the planes.  Its parent's E1 / strat / tfB entries are as they were when it won its claim
+                // (a parent neither moves nor is overwritten during the reproduction rounds, dead or alive).
+                const uint32_t par = parent_of(p, cell, p.nb_dir[i]);
+                const uint32_t trait = (uint32_t)p.tfB[par] & TF_TRAIT;
+                float ce;
+                uint32_t cs;
+                make_child(p, gcell_of(p, par & (p.W - 1), par >> p.log2W), p.strat[par], trait,
+                           __fsub_rn(p.E1[par], p.reproduce_cost), ce, cs);
+                p.tfA[cell] = (uint8_t)(TF_OCC | trait);
                 p.E0[cell] = ce;
-                p.strat[cell] = (uint8_t)(gene & 0xFFu);
+                p.strat[cell] = (uint8_t)cs;
                 at_risk = ce <= p.risk_thr;
-                if (p.want_counts) atomicAdd(&ctr->bins[count_bin(gene & 0xFFu, (gene >> 8) & TF_TRAIT)], 1ull);
+                if (p.want_counts) atomicAdd(&ctr->bins[count_bin(cs, trait)], 1ull);
             } else {
                 if (flagged) p.tfA[cell] = 0;  // it was marked occupied for the retry rounds
                 ++n_culled;

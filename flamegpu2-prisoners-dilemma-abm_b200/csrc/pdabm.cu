@@ -105,13 +105,13 @@ void drop_graphs(pd_sim* s) {  // the captured launches hold plane / list pointe
 
 void free_lists(pd_sim* s) {  // cudaFree(nullptr) is a no-op: safe on a partially allocated set
     cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.cand);
-    cudaFree(s->P.cl_cell); cudaFree(s->P.cl_dir);
+    cudaFree(s->P.cl_cell); cudaFree(s->P.cl_e); cudaFree(s->P.cl_aux);
     cudaFree(s->P.rt_cell); cudaFree(s->P.rt_state); cudaFree(s->P.rt_aux);
-    cudaFree(s->P.nb_cell); cudaFree(s->P.nb_e); cudaFree(s->P.nb_gene);
+    cudaFree(s->P.nb_cell); cudaFree(s->P.nb_dir);
     s->risk[0] = s->risk[1] = nullptr; s->P.risk_e = nullptr; s->P.cand = nullptr;
-    s->P.cl_cell = nullptr; s->P.cl_dir = nullptr;
+    s->P.cl_cell = nullptr; s->P.cl_e = nullptr; s->P.cl_aux = nullptr;
     s->P.rt_cell = nullptr; s->P.rt_state = s->P.rt_aux = nullptr;
-    s->P.nb_cell = nullptr; s->P.nb_e = nullptr; s->P.nb_gene = nullptr;
+    s->P.nb_cell = nullptr; s->P.nb_dir = nullptr;
     s->lists_allocated = false;
 }
 
@@ -121,13 +121,13 @@ int alloc_lists_raw(pd_sim* s, uint64_t cap) {
     CK(cudaMalloc(&s->P.risk_e, cap * 4));
     CK(cudaMalloc(&s->P.cand, (cap / 2 + 1) * 8));
     CK(cudaMalloc(&s->P.cl_cell, cap * 4));
-    CK(cudaMalloc(&s->P.cl_dir, cap));
+    CK(cudaMalloc(&s->P.cl_e, cap * 4));
+    CK(cudaMalloc(&s->P.cl_aux, cap * 2));
     CK(cudaMalloc(&s->P.rt_cell, cap * 4));
     CK(cudaMalloc(&s->P.rt_state, cap));
     CK(cudaMalloc(&s->P.rt_aux, cap));
     CK(cudaMalloc(&s->P.nb_cell, cap * 4));
-    CK(cudaMalloc(&s->P.nb_e, cap * 4));
-    CK(cudaMalloc(&s->P.nb_gene, cap * 2));
+    CK(cudaMalloc(&s->P.nb_dir, cap));
     return PD_OK;
 }
 

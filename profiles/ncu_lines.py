@@ -14,7 +14,7 @@ def main(rep, kern, top=45):
     inst, samp, text = collections.Counter(), collections.Counter(), {}
     fname, h = None, None
     for r in rows:
-        if len(r) >= 2 and r[0] == "File Name":
+        if len(r) >= 2 and r[0] in ("File Name", "File Path"):
             fname = r[1].split("/")[-1]
             continue
         if len(r) > 6 and r[0] == "Line No":
