@@ -63,7 +63,7 @@ struct Counters {
     unsigned int mv_n, rp_n, nb_n, risk_next_n, cand_n, nb_flagged, dep_n, pad1_;
     unsigned int rt_n[2], pad4_[2];  // retry list: [0] travel, [1] reproduction
     unsigned int mv_active[8], rp_active[8];
-    unsigned long long n_old, culled, living_deaths, pad2_;
+    unsigned long long n_old, admitted, living_deaths, pad2_;  // admitted = newborns that entered the planes
     unsigned long long st_play_deaths, st_movers, st_moved, st_travel_deaths;
     unsigned long long bins[16];
     unsigned int hist[8][256];
@@ -99,7 +99,6 @@ struct Params {
     uint32_t wrap_y;          // 1: H == W, rows wrap (whole world); 0: slab with ghost rows, no wrap
     uint32_t own_y0, own_y1;  // owned local rows [own_y0, own_y1); counters/cull only see these
     uint32_t round0, round1;  // reproduction retry rounds to run in this launch (slab mode)
-    uint32_t hist_force;      // k_fin_hist: histogram the newborns whatever the (not yet global) population says
     uint32_t world;           // number of slabs
     uint32_t cand_cap;        // capacity (keys) of one rank's candidate block
     unsigned long long* step_log;  // [log_cap][18] rows: step, agents, 16 counts; nullptr = off
@@ -133,6 +132,8 @@ struct Params {
     // The child itself -- energy, strategies, trait -- is made from the parent's (unchanged) E1 / strat / tfB only if
     // it survives the cull: near the carrying capacity 99 % do not
     uint32_t* nb_cell; uint8_t* nb_dir;
+    uint32_t* nb_prio;  // the newborn's cull priority (S_CULL word of its cell): drawn once, when it is born, and
+                        // counted into the cull histogram (Counters::hist, 2048 bins of its top 11 bits) on the spot
     Counters* ctr;
 };
 
@@ -230,6 +231,15 @@ __device__ __forceinline__ uint32_t play_word(const Params& p, uint64_t gcell) {
 __device__ __forceinline__ bool roll_higher(uint32_t rn, uint32_t r, int d) {
     const uint32_t kn = rn >> ROLL_SHIFT, k = r >> ROLL_SHIFT;
     return kn > k || (kn == k && d >= 4);
+}
+
+// ---- the newborn cull (replaces the list-index rule :1343/:1354, SURVEY B-4) ----------------
+// priority word of the newborn at local cell `cell`, and its 64-bit key (priority, global cell): higher survives
+__device__ __forceinline__ uint32_t cull_prio(const Params& p, uint32_t cell) {
+    return rng(p, gcell_of(p, cell & (p.W - 1), cell >> p.log2W), S_CULL).x;
+}
+__device__ __forceinline__ unsigned long long cull_key_of(const Params& p, uint32_t prio, uint32_t cell) {
+    return ((unsigned long long)prio << 32) | (uint32_t)gcell_of(p, cell & (p.W - 1), cell >> p.log2W);
 }
 
 // ---- triangular probe (:826-839, :1088-1101) ---------------------------------------------

@@ -243,12 +243,16 @@ __global__ void __launch_bounds__(COMMIT_NT) k_repro_commit(const __grid_constan
     __shared__ uint8_t s_lost_state[COMMIT_CHUNK];
     __shared__ uint32_t s_nb_cell[COMMIT_CHUNK];
     __shared__ uint8_t s_nb_dir[COMMIT_CHUNK];
+    __shared__ uint32_t s_nb_prio[COMMIT_CHUNK];
+    __shared__ unsigned int s_hist[2048];  // this CTA's share of the cull histogram
     __shared__ unsigned int s_n[4];  // 0 losers of this chunk, 1 newborns, 2 / 3 their bases in the global lists
     Counters* ctr = p.ctr;
     unsigned int n = ctr->rp_n;
     if (n > p.list_cap) n = p.list_cap;
     const uint32_t step = __ldg(&ctr->step_no);
     const int tid = threadIdx.x;
+    if (blockIdx.x * COMMIT_CHUNK >= n) return;
+    for (int i = tid; i < 2048; i += COMMIT_NT) s_hist[i] = 0;
     for (unsigned int c0 = blockIdx.x * COMMIT_CHUNK; c0 < n; c0 += gridDim.x * COMMIT_CHUNK) {
         if (tid < 2) s_n[tid] = 0;
         __syncthreads();
@@ -283,8 +287,11 @@ __global__ void __launch_bounds__(COMMIT_NT) k_repro_commit(const __grid_constan
             }
             const uint32_t bslot = wappend(&s_n[1], born);
             if (born) {
+                const uint32_t prio = cull_prio(p, tgt[k]);
+                atomicAdd(&s_hist[prio >> 21], 1u);
                 s_nb_cell[bslot] = tgt[k];
                 s_nb_dir[bslot] = (uint8_t)d;
+                s_nb_prio[bslot] = prio;
             }
             const bool lost = valid && !won;  // stays ATTEMPTING_REPRODUCTION (:1203-1205)
             const uint32_t lslot = wappend(&s_n[0], lost);
@@ -319,10 +326,14 @@ __global__ void __launch_bounds__(COMMIT_NT) k_repro_commit(const __grid_constan
                 for (unsigned int k = tid; k < n_born; k += COMMIT_NT) {
                     p.nb_cell[base + k] = s_nb_cell[k];
                     p.nb_dir[base + k] = s_nb_dir[k];
+                    p.nb_prio[base + k] = s_nb_prio[k];
                 }
             }
         }
     }
+    __syncthreads();
+    for (int i = tid; i < 2048; i += COMMIT_NT)
+        if (s_hist[i]) atomicAdd(&ctr->hist[0][0] + i, s_hist[i]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -482,8 +493,11 @@ __global__ void __launch_bounds__(BS) k_repro_retry(const __grid_constant__ Para
             const uint32_t slot = warp_append(&ctr->nb_n, born);
             if (born) {
                 if (slot < p.list_cap) {
+                    const uint32_t prio = cull_prio(p, tgt);
+                    atomicAdd(&ctr->hist[0][0] + (prio >> 21), 1u);
                     p.nb_cell[slot] = tgt;
                     p.nb_dir[slot] = (uint8_t)dir;
+                    p.nb_prio[slot] = prio;
                 } else atomicExch(&ctr->overflow, 1u);
             }
         }
@@ -504,13 +518,6 @@ __global__ void __launch_bounds__(BS) k_repro_retry(const __grid_constant__ Para
 // Whole world: one kernel (k_finalize).  Row slabs: three kernels (k_fin_hist, k_fin_cand,
 // k_fin_apply) with the caller summing the histogram and gathering the candidates in between.
 // ------------------------------------------------------------------------------------------
-// The priority is recomputed wherever it is needed instead of being stored per newborn: the sparse
-// kernels wait on memory (issue slots ~11 % busy), a Philox call is cheaper than a list round trip.
-__device__ __forceinline__ unsigned long long cull_key(const Params& p, uint32_t cell) {
-    const uint64_t g = gcell_of(p, cell & (p.W - 1), cell >> p.log2W);
-    return ((unsigned long long)rng(p, g, S_CULL).x << 32) | (uint32_t)g;
-}
-
 struct CullPlan {
     bool cull;                 // olds + births exceed the cap
     unsigned long long keep;   // newborns allowed to survive (all slabs together)
@@ -526,27 +533,6 @@ __device__ __forceinline__ CullPlan cull_plan(const Params& p) {
         if (c.keep >= births) c.cull = false;
     }
     return c;
-}
-
-// pass A: histogram of the top 11 key bits of this slab's newborns into `hist` (global memory)
-__device__ __forceinline__ void fin_hist(const Params& p, unsigned int nb, unsigned int* hist, unsigned int* s_hist) {
-    const unsigned int stride = gridDim.x * blockDim.x;
-    const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    for (unsigned int i = threadIdx.x; i < 2048; i += blockDim.x) s_hist[i] = 0;
-    __syncthreads();
-    for (unsigned int i = t0; i < nb; i += 4 * stride) {  // 4 independent loads in flight per thread
-        uint32_t cell[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) cell[u] = (i + u * stride < nb) ? p.nb_cell[i + u * stride] : 0u;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (i + u * stride >= nb) continue;
-            atomicAdd(&s_hist[(unsigned int)(cull_key(p, cell[u]) >> 53)], 1u);
-        }
-    }
-    __syncthreads();
-    for (unsigned int i = threadIdx.x; i < 2048; i += blockDim.x)
-        if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
 }
 
 // Largest bin b such that the number of entries in bins >= b reaches `keep`, found by warp 0 in parallel
@@ -683,58 +669,88 @@ __device__ __forceinline__ unsigned long long fin_select(unsigned int n, unsigne
     return *s_prefix;
 }
 
-// newborns: cull or admit (OWNED rows only)
-__device__ __forceinline__ void fin_apply(const Params& p, unsigned int nb, bool cull,
-                                          unsigned long long keep, unsigned long long tau) {
-    Counters* ctr = p.ctr;
+// candidates of the threshold bin `digit`: their keys are appended to out[0 .. cap) through *counter.  The list
+// walk keeps four independent loads in flight per thread (these kernels run a few CTAs per SM over ~10^7 entries:
+// one load per round trip is pure latency)
+__device__ __forceinline__ void fin_candidates(const Params& p, unsigned int nb, unsigned int digit,
+                                               unsigned int* counter, unsigned long long* out, unsigned int cap) {
     const unsigned int stride = gridDim.x * blockDim.x;
-    const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    // ---- newborns: cull or admit (no living cost in the birth step, :1343)
-    unsigned int n_culled = 0;
-    const bool flagged = __ldcg(&ctr->nb_flagged) != 0u;
-    for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nb; i0 += stride) {
-        const unsigned int i = i0 + threadIdx.x;
-        bool at_risk = false;
-        if (i < nb) {
-            const uint32_t cell = p.nb_cell[i];
-            bool survive = true;
-            if (cull) survive = keep != 0 && cull_key(p, cell) >= tau;
-            if (survive) {
-                // Only now is the child made (:1216-1328: the parent's trait, its own energy and strategies) and
-                // enters the planes.  Its parent's E1 / strat / tfB entries are as they were when it won its claim
-                // (a parent neither moves nor is overwritten during the reproduction rounds, dead or alive).
-                const uint32_t par = parent_of(p, cell, p.nb_dir[i]);
-                const uint32_t trait = (uint32_t)p.tfB[par] & TF_TRAIT;
-                float ce;
-                uint32_t cs;
-                make_child(p, gcell_of(p, par & (p.W - 1), par >> p.log2W), p.strat[par], trait,
-                           __fsub_rn(p.E1[par], p.reproduce_cost), ce, cs);
-                p.tfA[cell] = (uint8_t)(TF_OCC | trait);
-                p.E0[cell] = ce;
-                p.strat[cell] = (uint8_t)cs;
-                at_risk = ce <= p.risk_thr;
-                if (p.want_counts) atomicAdd(&ctr->bins[count_bin(cs, trait)], 1ull);
-            } else {
-                if (flagged) p.tfA[cell] = 0;  // it was marked occupied for the retry rounds
-                ++n_culled;
+    for (unsigned int i0 = blockIdx.x * blockDim.x * 4u; i0 < nb; i0 += stride * 4u) {
+        uint32_t prio[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned int i = i0 + u * blockDim.x + threadIdx.x;
+            prio[u] = i < nb ? p.nb_prio[i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned int i = i0 + u * blockDim.x + threadIdx.x;
+            const bool is_cand = i < nb && (prio[u] >> 21) == digit;
+            const uint32_t slot = warp_append(counter, is_cand);
+            if (is_cand) {
+                if (slot < cap) out[slot] = cull_key_of(p, prio[u], p.nb_cell[i]);
+                else atomicExch(&p.ctr->overflow, 1u);  // > cap newborns in one of 2048 bins: not a real world
             }
         }
-        const uint32_t slot = warp_append(&ctr->risk_next_n, at_risk);
-        if (at_risk) {
-            if (slot < p.list_cap) p.risk_next[slot] = p.nb_cell[i];
-            else atomicExch(&ctr->overflow, 1u);
+    }
+}
+
+// newborns: cull or admit (OWNED rows only; no living cost in the birth step, :1343).  With a cull only the
+// newborns of the bins >= `digit` can survive, so the walk reads the priorities alone (four loads in flight).
+__device__ __forceinline__ void fin_apply(const Params& p, unsigned int nb, bool cull, unsigned long long keep,
+                                          unsigned long long tau, unsigned int digit) {
+    Counters* ctr = p.ctr;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    unsigned int n_admitted = 0;
+    for (unsigned int i0 = blockIdx.x * blockDim.x * 4u; i0 < nb; i0 += stride * 4u) {
+        uint32_t prio[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned int i = i0 + u * blockDim.x + threadIdx.x;
+            prio[u] = i < nb ? p.nb_prio[i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned int i = i0 + u * blockDim.x + threadIdx.x;
+            bool at_risk = false;
+            uint32_t cell = 0;
+            if (i < nb && (!cull || (keep != 0 && (prio[u] >> 21) >= digit))) {
+                cell = p.nb_cell[i];
+                if (!cull || cull_key_of(p, prio[u], cell) >= tau) {
+                    // Only now is the child made (:1216-1328: the parent's trait, its own energy and strategies) and
+                    // enters the planes.  Its parent's E1 / strat / tfB entries are as they were when it won its claim
+                    // (a parent neither moves nor is overwritten during the reproduction rounds, dead or alive).
+                    const uint32_t par = parent_of(p, cell, p.nb_dir[i]);
+                    const uint32_t trait = (uint32_t)p.tfB[par] & TF_TRAIT;
+                    float ce;
+                    uint32_t cs;
+                    make_child(p, gcell_of(p, par & (p.W - 1), par >> p.log2W), p.strat[par], trait,
+                               __fsub_rn(p.E1[par], p.reproduce_cost), ce, cs);
+                    p.tfA[cell] = (uint8_t)(TF_OCC | trait);
+                    p.E0[cell] = ce;
+                    p.strat[cell] = (uint8_t)cs;
+                    at_risk = ce <= p.risk_thr;
+                    if (p.want_counts) atomicAdd(&ctr->bins[count_bin(cs, trait)], 1ull);
+                    ++n_admitted;
+                }  // (a culled newborn never entered tfA / E0: nothing to undo)
+            }
+            const uint32_t slot = warp_append(&ctr->risk_next_n, at_risk);
+            if (at_risk) {
+                if (slot < p.list_cap) p.risk_next[slot] = cell;
+                else atomicExch(&ctr->overflow, 1u);
+            }
         }
     }
-    for (int o = 16; o > 0; o >>= 1) n_culled += __shfl_down_sync(0xFFFFFFFFu, n_culled, o);  // one atomic per warp
-    if ((threadIdx.x & 31) == 0 && n_culled) atomicAdd(&ctr->culled, (unsigned long long)n_culled);
+    for (int o = 16; o > 0; o >>= 1) n_admitted += __shfl_down_sync(0xFFFFFFFFu, n_admitted, o);  // one atomic per warp
+    if ((threadIdx.x & 31) == 0 && n_admitted) atomicAdd(&ctr->admitted, (unsigned long long)n_admitted);
 }
 
 // bookkeeping by one thread after everything else of the step is done
 __device__ __forceinline__ void fin_bookkeeping(const Params& p) {
     Counters* ctr = p.ctr;
-    const unsigned long long culled = __ldcg(&ctr->culled);
     const unsigned long long ld = __ldcg(&ctr->living_deaths);
     const unsigned long long b = __ldcg(&ctr->nb_n);  // births = the newborn list
+    const unsigned long long culled = b - __ldcg(&ctr->admitted);
     ctr->n_agents = __ldcg(&ctr->n_old) + b - culled - ld;  // this slab's agents
     unsigned int rn = __ldcg(&ctr->risk_next_n);
     ctr->risk_n = rn > p.list_cap ? p.list_cap : rn;
@@ -766,13 +782,12 @@ __device__ __forceinline__ void fin_bookkeeping(const Params& p) {
 }
 
 template <int BS>
-__global__ void __launch_bounds__(BS) k_finalize(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(BS, BS == 512 ? 2 : 1) k_finalize(const __grid_constant__ Params p) {
     Counters* ctr = p.ctr;
     __shared__ unsigned int s_hist[2048];
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned long long s_krem;
     __shared__ unsigned int s_digit;
-    const unsigned int stride = gridDim.x * blockDim.x;
     unsigned int nb = ctr->nb_n;
     if (nb > p.list_cap) nb = p.list_cap;
     unsigned int* g_hist = &ctr->hist[0][0];  // 2048 words
@@ -780,20 +795,11 @@ __global__ void __launch_bounds__(BS) k_finalize(const __grid_constant__ Params 
     const unsigned int cand_cap = p.list_cap / 2u;
     const CullPlan plan = cull_plan(p);
     unsigned long long tau = 0;                // survive iff key >= tau
+    unsigned int digit = 0;
     if (plan.cull && plan.keep > 0) {
-        fin_hist(p, nb, g_hist, s_hist);
-        grid_sync(ctr->barrier, gridDim.x);
-        const unsigned int digit = fin_digit(g_hist, plan.keep, s_hist, &s_digit, &s_krem);
-        for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nb; i0 += stride) {
-            const unsigned int i = i0 + threadIdx.x;
-            const unsigned long long key = i < nb ? cull_key(p, p.nb_cell[i]) : 0ull;
-            const bool is_cand = i < nb && (unsigned int)(key >> 53) == digit;
-            const uint32_t slot = warp_append(&ctr->cand_n, is_cand);
-            if (is_cand) {
-                if (slot < cand_cap) cand[slot] = key;
-                else atomicExch(&ctr->overflow, 1u);  // > cap/2 newborns in one of 2048 bins: not a real world
-            }
-        }
+        // (the histogram of the priorities' top 11 bits was built as the newborns were listed)
+        digit = fin_digit(g_hist, plan.keep, s_hist, &s_digit, &s_krem);
+        fin_candidates(p, nb, digit, &ctr->cand_n, cand, cand_cap);
         grid_sync(ctr->barrier, gridDim.x);
         if (blockIdx.x == 0) {
             unsigned int nc = __ldcg(&ctr->cand_n);
@@ -805,38 +811,24 @@ __global__ void __launch_bounds__(BS) k_finalize(const __grid_constant__ Params 
         grid_sync(ctr->barrier, gridDim.x);
         tau = __ldcg(&ctr->tau);
     }
-    fin_apply(p, nb, plan.cull, plan.keep, tau);
+    fin_apply(p, nb, plan.cull, plan.keep, tau, digit);
     grid_sync(ctr->barrier, gridDim.x);
     if (blockIdx.x == 0 && threadIdx.x == 0) fin_bookkeeping(p);
 }
 
-// ---- row slabs, part 1: this slab's histogram into the bound exchange buffer (summed by the caller)
-template <int BS>
-__global__ void __launch_bounds__(BS) k_fin_hist(const __grid_constant__ Params p) {
-    __shared__ unsigned int s_hist[2048];
-    Counters* ctr = p.ctr;
-    const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    for (unsigned int i = t0; i < 2048; i += gridDim.x * blockDim.x) p.ghist[i] = 0;
-    grid_sync(ctr->barrier, gridDim.x);
-    // inside PD_PART_PRE the global population is not known yet: the histogram is computed in any case, so that it
-    // can ride on the same all-reduce as the population (it is final unless further reproduction rounds run)
-    if (!p.hist_force) {
-        const CullPlan plan = cull_plan(p);
-        if (!(plan.cull && plan.keep > 0)) return;
-    }
-    unsigned int nb = ctr->nb_n;
-    if (nb > p.list_cap) nb = p.list_cap;
-    fin_hist(p, nb, p.ghist, s_hist);
+// ---- row slabs, part 1: this slab's histogram (built as the newborns were listed) into the bound exchange
+// buffer, for the caller to sum over the slabs
+__global__ void __launch_bounds__(256) k_fin_hist(const __grid_constant__ Params p) {
+    for (unsigned int i = threadIdx.x; i < 2048; i += blockDim.x) p.ghist[i] = (&p.ctr->hist[0][0])[i];
 }
 
 // ---- part 2 (after the histogram was summed): this slab's candidate keys into cand_out
 template <int BS>
-__global__ void __launch_bounds__(BS) k_fin_cand(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(BS, BS == 512 ? 2 : 1) k_fin_cand(const __grid_constant__ Params p) {
     __shared__ unsigned int s_hist[2048];
     __shared__ unsigned long long s_krem;
     __shared__ unsigned int s_digit;
     Counters* ctr = p.ctr;
-    const unsigned int stride = gridDim.x * blockDim.x;
     const CullPlan plan = cull_plan(p);
     if (!(plan.cull && plan.keep > 0)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) p.cand_out[0] = 0ull;
@@ -845,16 +837,7 @@ __global__ void __launch_bounds__(BS) k_fin_cand(const __grid_constant__ Params 
     unsigned int nb = ctr->nb_n;
     if (nb > p.list_cap) nb = p.list_cap;
     const unsigned int digit = fin_digit(p.ghist, plan.keep, s_hist, &s_digit, &s_krem);
-    for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nb; i0 += stride) {
-        const unsigned int i = i0 + threadIdx.x;
-        const unsigned long long key = i < nb ? cull_key(p, p.nb_cell[i]) : 0ull;
-        const bool is_cand = i < nb && (unsigned int)(key >> 53) == digit;
-        const uint32_t slot = warp_append(&ctr->cand_n, is_cand);
-        if (is_cand) {
-            if (slot < p.cand_cap) p.cand_out[1 + slot] = key;
-            else atomicExch(&ctr->overflow, 1u);
-        }
-    }
+    fin_candidates(p, nb, digit, &ctr->cand_n, p.cand_out + 1, p.cand_cap);
     grid_sync(ctr->barrier, gridDim.x);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const unsigned int n = __ldcg(&ctr->cand_n);
@@ -864,7 +847,7 @@ __global__ void __launch_bounds__(BS) k_fin_cand(const __grid_constant__ Params 
 
 // ---- part 3 (after all slabs' candidates were gathered): threshold, apply, bookkeeping
 template <int BS>
-__global__ void __launch_bounds__(BS) k_fin_apply(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(BS, BS == 512 ? 2 : 1) k_fin_apply(const __grid_constant__ Params p) {
     __shared__ unsigned int s_hist[2048];
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned long long s_krem;
@@ -875,8 +858,9 @@ __global__ void __launch_bounds__(BS) k_fin_apply(const __grid_constant__ Params
     if (nb > p.list_cap) nb = p.list_cap;
     const CullPlan plan = cull_plan(p);
     unsigned long long tau = 0;
+    unsigned int digit = 0;
     if (plan.cull && plan.keep > 0) {
-        const unsigned int digit = fin_digit(p.ghist, plan.keep, s_hist, &s_digit, &s_krem);
+        digit = fin_digit(p.ghist, plan.keep, s_hist, &s_digit, &s_krem);
         if (blockIdx.x == 0) {
             // candidates of slab w live at cand_all[w * (1 + cap) + 1 ...]; flatten by a linear search
             // over the (at most 8) block counts
@@ -903,7 +887,7 @@ __global__ void __launch_bounds__(BS) k_fin_apply(const __grid_constant__ Params
         grid_sync(ctr->barrier, gridDim.x);
         tau = __ldcg(&ctr->tau);
     }
-    fin_apply(p, nb, plan.cull, plan.keep, tau);
+    fin_apply(p, nb, plan.cull, plan.keep, tau, digit);
     grid_sync(ctr->barrier, gridDim.x);
     if (blockIdx.x == 0 && threadIdx.x == 0) fin_bookkeeping(p);
 }

@@ -107,11 +107,11 @@ void free_lists(pd_sim* s) {  // cudaFree(nullptr) is a no-op: safe on a partial
     cudaFree(s->risk[0]); cudaFree(s->risk[1]); cudaFree(s->P.risk_e); cudaFree(s->P.cand);
     cudaFree(s->P.cl_cell); cudaFree(s->P.cl_e); cudaFree(s->P.cl_aux);
     cudaFree(s->P.rt_cell); cudaFree(s->P.rt_state); cudaFree(s->P.rt_aux);
-    cudaFree(s->P.nb_cell); cudaFree(s->P.nb_dir);
+    cudaFree(s->P.nb_cell); cudaFree(s->P.nb_dir); cudaFree(s->P.nb_prio);
     s->risk[0] = s->risk[1] = nullptr; s->P.risk_e = nullptr; s->P.cand = nullptr;
     s->P.cl_cell = nullptr; s->P.cl_e = nullptr; s->P.cl_aux = nullptr;
     s->P.rt_cell = nullptr; s->P.rt_state = s->P.rt_aux = nullptr;
-    s->P.nb_cell = nullptr; s->P.nb_dir = nullptr;
+    s->P.nb_cell = nullptr; s->P.nb_dir = nullptr; s->P.nb_prio = nullptr;
     s->lists_allocated = false;
 }
 
@@ -128,6 +128,7 @@ int alloc_lists_raw(pd_sim* s, uint64_t cap) {
     CK(cudaMalloc(&s->P.rt_aux, cap));
     CK(cudaMalloc(&s->P.nb_cell, cap * 4));
     CK(cudaMalloc(&s->P.nb_dir, cap));
+    CK(cudaMalloc(&s->P.nb_prio, cap * 4));
     return PD_OK;
 }
 
@@ -398,7 +399,7 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     P.row0 = (cfg->row0 + HW - cfg->ghost_rows) & (HW - 1);  // global row of local row 0
     P.wrap_y = slab ? 0u : 1u;
     P.own_y0 = cfg->ghost_rows; P.own_y1 = cfg->ghost_rows + cfg->rows;
-    P.round0 = 1; P.round1 = 8; P.world = 1; P.cand_cap = 0; P.hist_force = 0;
+    P.round0 = 1; P.round1 = 8; P.world = 1; P.cand_cap = 0;
     P.select_cap = cfg->debug_select_cap ? cfg->debug_select_cap : 0xFFFFFFFFu;
     P.step_log = nullptr; P.log_cap = 0;
     P.glb = nullptr; P.ghist = nullptr; P.cand_out = nullptr; P.cand_all = nullptr;
@@ -664,9 +665,7 @@ int pd_step_part(pd_sim* s, int part, int arg, void* stream, int want_counts) {
         PROF(6, { if ((rc = launch_commit(s, k_repro_commit, st))) return rc; });
         k_publish_gate<<<1, 32, 0, st>>>(P, 0);
         // the cull histogram of round 1's newborns rides on the same all-reduce as the gate words
-        P.hist_force = 1;
-        PROF(8, { if ((rc = launch_sparse(s, k_fin_hist, st))) return rc; });
-        P.hist_force = 0;
+        PROF(8, (k_fin_hist<<<1, 256, 0, st>>>(P)));
         break;
     }
     case PD_PART_RETRY:
@@ -677,7 +676,7 @@ int pd_step_part(pd_sim* s, int part, int arg, void* stream, int want_counts) {
         P.round0 = 1; P.round1 = 8;
         break;
     case PD_PART_HIST:  // retry rounds added newborns: this slab's cull histogram again
-        PROF(8, { if ((rc = launch_sparse(s, k_fin_hist, st))) return rc; });
+        PROF(8, (k_fin_hist<<<1, 256, 0, st>>>(P)));
         break;
     case PD_PART_CAND:  // the reproduction rounds are over: this slab's cull candidates
         PROF(8, { if ((rc = launch_sparse(s, k_fin_cand, st))) return rc; });
