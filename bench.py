@@ -185,11 +185,12 @@ def decomp_parity(world, rank, local_rank, steps=70):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from pdabm_b200 import Simulation, SimConfig, DecomposedWorld, DistComm
+    from pdabm_b200 import Simulation, SimConfig, DecomposedWorld, best_comm
     kw = dict(width=256, height=256 * world, seed=77, strategy_per_trait=1, env_noise=0.05, mutation_rate=0.01,
               device=local_rank)
     ref = Simulation(SimConfig(**kw))
-    dec = DecomposedWorld(SimConfig(**kw), DistComm())
+    comm = best_comm()
+    dec = DecomposedWorld(SimConfig(**kw), comm)
     ref.init_population()
     dec.init_population()
     ok = True
@@ -211,10 +212,11 @@ def decomp_parity(world, rank, local_rank, steps=70):
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if int(t[0]) != 1:
         if rank == 0:
-            print(json.dumps({"error": f"decomp_parity FAILED: {world} ranks over NCCL differ from the single-handle run"}),
+            print(json.dumps({"error": f"decomp_parity FAILED: {world} ranks differ from the single-handle run"}),
                   flush=True)
         sys.exit(3)
-    return (f"bit-identical to the single-handle run: {world} ranks over NCCL, {steps} steps of a 256x{256 * world} "
+    via = "peer-memory halo (symmetric memory over NVLink) + NCCL collectives" if type(comm).__name__ == "PeerComm" else "NCCL"
+    return (f"bit-identical to the single-handle run: {world} ranks, {via}, {steps} steps of a 256x{256 * world} "
             f"per-trait world with noise and mutation ({retries} reproduction retry rounds, cap reached: "
             f"{n_end} agents), planes and counts compared every 10 steps")
 
@@ -224,7 +226,7 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from pdabm_b200 import Simulation, SimConfig
 
-    from pdabm_b200 import DecomposedWorld, DistComm
+    from pdabm_b200 import DecomposedWorld, best_comm
     width, overrides, desc = CONFIG5 if args.workload == "config5" else WORKLOADS[args.workload]
     if args.width:
         width = args.width
@@ -238,7 +240,7 @@ def run_ours(args, rank, world, local_rank):
         # GPU owns the same 2^28 cells as the single-GPU run (weak scaling)
         height = args.height or (width if args.workload == "config5" else width * world)
         cfg = SimConfig(width=width, height=height, seed=12345, device=local_rank, **overrides)
-        sim = DecomposedWorld(cfg, DistComm())
+        sim = DecomposedWorld(cfg, best_comm())
         one = sim.slabs[0].sim
         cells = width * (height // world)              # owned cells per GPU
         desc += f"; one {width}x{height} world in {world} row slabs"
@@ -386,7 +388,7 @@ def run_ours(args, rank, world, local_rank):
     if slabs and world == 8 and args.workload == "config3" and not args.no_also:
         sim.close()
         w5, ov5, d5 = CONFIG5
-        big = DecomposedWorld(SimConfig(width=w5, height=w5, seed=12345, device=local_rank, **ov5), DistComm())
+        big = DecomposedWorld(SimConfig(width=w5, height=w5, seed=12345, device=local_rank, **ov5), best_comm())
         big.init_population()
         big.step(args.presteps, want_counts=False)
         big.step(3, want_counts=False)
@@ -459,8 +461,12 @@ def run_ours(args, rank, world, local_rank):
         "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": desc, "width": width, "cells": cells * world if slabs else cells, "cells_per_gpu": cells,
-                   "partitioning": ("row slabs of one world, one per GPU: NVLink halo exchange of 64 boundary rows x 3 planes "
-                                    "+ 4 (gate closed) to 11 small collectives per step" if slabs else
+                   "partitioning": ("row slabs of one world, one per GPU: halo of 64 boundary rows x 3 planes through "
+                                    f"{type(sim.comm).__name__} (PeerComm = packed strips loaded from the neighbours' "
+                                    "symmetric memory over NVLink, one pack kernel + one device barrier + one unpack "
+                                    "kernel; DistComm = NCCL send/recv), one 8 KB all-reduce (gate words + cull "
+                                    "histogram) and one all-gather of cull candidates per step; reproduction retry "
+                                    "rounds add one launch + one all-reduce each while the global gate is open" if slabs else
                                     "one world per GPU (ensemble), no data-path collective" if world > 1 else "single world"),
                    "presteps": args.presteps, "agents_at_start": n_before, "agents_at_end": n_after,
                    "density": n_after / (cells * world if slabs else cells), "counts_every_step": want_counts,

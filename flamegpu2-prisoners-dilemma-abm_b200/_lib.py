@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("PDABM_LIB") or os.path.join(_HERE, "libpdabm.so")
 PD_OK = 0
 PD_TF_TRAIT_MASK = 0x03
 PD_TF_OCCUPIED = 0x80
-PD_PART_PRE, PD_PART_RETRY, PD_PART_HIST, PD_PART_CAND, PD_PART_APPLY = 0, 1, 2, 3, 4
+PD_PART_PRE, PD_PART_RETRY, PD_PART_HIST, PD_PART_CAND, PD_PART_APPLY, PD_PART_DONE = 0, 1, 2, 3, 4, 5
 PD_GLB_WORDS, PD_HIST_WORDS = 20, 2048
 
 
@@ -66,7 +66,7 @@ EXPORTS = (
     "pd_bind_planes", "pd_init_population", "pd_sync_state", "pd_step", "pd_read_counts",
     "pd_read_stats", "pd_get_step", "pd_set_step", "pd_step_host", "pd_read_agent_steps",
     "pd_set_profile", "pd_read_profile", "pd_bind_comm", "pd_step_part", "pd_graph_replays",
-    "pd_set_step_log", "pd_read_step_log",
+    "pd_set_step_log", "pd_read_step_log", "pd_halo_bytes", "pd_halo_pack", "pd_halo_unpack",
 )
 
 _lib = None
@@ -121,6 +121,12 @@ def load() -> C.CDLL:
     lib.pd_bind_comm.argtypes = [vp, vp, vp, vp, vp, u32, u32]
     lib.pd_step_part.restype = i32
     lib.pd_step_part.argtypes = [vp, i32, i32, vp, i32]
+    lib.pd_halo_bytes.restype = i32
+    lib.pd_halo_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.pd_halo_pack.restype = i32
+    lib.pd_halo_pack.argtypes = [vp, vp, vp, vp]
+    lib.pd_halo_unpack.restype = i32
+    lib.pd_halo_unpack.argtypes = [vp, vp, vp, vp]
     lib.pd_set_step_log.restype = i32
     lib.pd_set_step_log.argtypes = [vp, u32, vp]
     lib.pd_read_step_log.restype = i32

@@ -99,6 +99,7 @@ struct Params {
     uint32_t wrap_y;          // 1: H == W, rows wrap (whole world); 0: slab with ghost rows, no wrap
     uint32_t own_y0, own_y1;  // owned local rows [own_y0, own_y1); counters/cull only see these
     uint32_t round0, round1;  // reproduction retry rounds to run in this launch (slab mode)
+    uint32_t speculative;     // k_fin_cand / k_fin_apply: do nothing if the global gate says a retry round is due
     uint32_t world;           // number of slabs
     uint32_t cand_cap;        // capacity (keys) of one rank's candidate block
     unsigned long long* step_log;  // [log_cap][18] rows: step, agents, 16 counts; nullptr = off

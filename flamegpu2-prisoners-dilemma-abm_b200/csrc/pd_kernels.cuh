@@ -518,6 +518,12 @@ __global__ void __launch_bounds__(BS) k_repro_retry(const __grid_constant__ Para
 // Whole world: one kernel (k_finalize).  Row slabs: three kernels (k_fin_hist, k_fin_cand,
 // k_fin_apply) with the caller summing the histogram and gathering the candidates in between.
 // ------------------------------------------------------------------------------------------
+// exit_god_fn's decision after round 1 (:1614-1627), from the words the caller summed over the slabs: another
+// round is due while the population is within the cap and somebody is still trying
+__device__ __forceinline__ bool gate_open(const Params& p) {
+    return __ldcg(&p.glb[0]) + __ldcg(&p.glb[1]) <= p.max_agents && __ldcg(&p.glb[2]) > 0ull;
+}
+
 struct CullPlan {
     bool cull;                 // olds + births exceed the cap
     unsigned long long keep;   // newborns allowed to survive (all slabs together)
@@ -829,6 +835,7 @@ __global__ void __launch_bounds__(BS, BS == 512 ? 2 : 1) k_fin_cand(const __grid
     __shared__ unsigned long long s_krem;
     __shared__ unsigned int s_digit;
     Counters* ctr = p.ctr;
+    if (p.speculative && gate_open(p)) return;  // a further reproduction round is due: the caller comes back later
     const CullPlan plan = cull_plan(p);
     if (!(plan.cull && plan.keep > 0)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) p.cand_out[0] = 0ull;
@@ -854,6 +861,7 @@ __global__ void __launch_bounds__(BS, BS == 512 ? 2 : 1) k_fin_apply(const __gri
     __shared__ unsigned int s_digit;
     __shared__ unsigned int s_cum[PD_MAX_WORLD + 1];
     Counters* ctr = p.ctr;
+    if (p.speculative && gate_open(p)) return;  // (see k_fin_cand)
     unsigned int nb = ctr->nb_n;
     if (nb > p.list_cap) nb = p.list_cap;
     const CullPlan plan = cull_plan(p);
@@ -1028,6 +1036,31 @@ __global__ void __launch_bounds__(NT) k_init_write(const __grid_constant__ Param
         p.tfA[i] = tf;
         p.strat[i] = st;
         p.E0[i] = e;
+    }
+}
+
+// ---- row slabs: halo exchange through peer memory.  A strip = ghost_rows rows of the three state planes, packed
+// as [energy f32 | strat u8 | tf u8].  k_halo_pack copies this slab's first / last owned rows into two strips of
+// an outbox the neighbours can read (symmetric memory over NVLink); k_halo_unpack fills the ghost rows from the
+// neighbours' strips -- the loads go over NVLink, 16 bytes per thread and iteration.
+__global__ void __launch_bounds__(256) k_halo_copy(const __grid_constant__ Params p, uint4* a_strip, uint4* b_strip,
+                                                   uint32_t a_row, uint32_t b_row, uint32_t rows, int unpack) {
+    // strip a <-> local rows [a_row, a_row + rows), strip b <-> [b_row, b_row + rows)
+    const size_t cells = (size_t)rows << p.log2W;
+    const size_t ne = cells / 4, nb = cells / 16;   // 16-byte chunks of the energy part / of a byte plane's part
+    const size_t per = ne + 2 * nb;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per; i += stride) {
+        const bool second = i >= per;
+        const size_t k = second ? i - per : i;
+        uint4* strip = second ? b_strip : a_strip;
+        const size_t row0 = (size_t)(second ? b_row : a_row) << p.log2W;
+        uint4* plane;
+        if (k < ne) plane = reinterpret_cast<uint4*>(p.E0 + row0) + k;
+        else if (k < ne + nb) plane = reinterpret_cast<uint4*>(p.strat + row0) + (k - ne);
+        else plane = reinterpret_cast<uint4*>(p.tfA + row0) + (k - ne - nb);
+        if (unpack) *plane = strip[k];
+        else strip[k] = *plane;
     }
 }
 

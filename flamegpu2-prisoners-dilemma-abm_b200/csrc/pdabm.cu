@@ -399,7 +399,7 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     P.row0 = (cfg->row0 + HW - cfg->ghost_rows) & (HW - 1);  // global row of local row 0
     P.wrap_y = slab ? 0u : 1u;
     P.own_y0 = cfg->ghost_rows; P.own_y1 = cfg->ghost_rows + cfg->rows;
-    P.round0 = 1; P.round1 = 8; P.world = 1; P.cand_cap = 0;
+    P.round0 = 1; P.round1 = 8; P.world = 1; P.cand_cap = 0; P.speculative = 0;
     P.select_cap = cfg->debug_select_cap ? cfg->debug_select_cap : 0xFFFFFFFFu;
     P.step_log = nullptr; P.log_cap = 0;
     P.glb = nullptr; P.ghist = nullptr; P.cand_out = nullptr; P.cand_all = nullptr;
@@ -679,10 +679,19 @@ int pd_step_part(pd_sim* s, int part, int arg, void* stream, int want_counts) {
         PROF(8, (k_fin_hist<<<1, 256, 0, st>>>(P)));
         break;
     case PD_PART_CAND:  // the reproduction rounds are over: this slab's cull candidates
+        P.speculative = arg ? 1u : 0u;
         PROF(8, { if ((rc = launch_sparse(s, k_fin_cand, st))) return rc; });
+        P.speculative = 0;
         break;
     case PD_PART_APPLY:
+        P.speculative = arg ? 1u : 0u;
         PROF(8, { if ((rc = launch_sparse(s, k_fin_apply, st))) return rc; });
+        P.speculative = 0;
+        if (arg) break;  // speculative: the caller confirms with PD_PART_DONE once it has seen the gate
+        s->risk_cur ^= 1;
+        s->step += 1;
+        break;
+    case PD_PART_DONE:  // the speculative CAND / APPLY stood: the step is complete (no launch)
         s->risk_cur ^= 1;
         s->step += 1;
         break;
@@ -691,6 +700,34 @@ int pd_step_part(pd_sim* s, int part, int arg, void* stream, int want_counts) {
     }
     CK(cudaGetLastError());
     return PD_OK;
+}
+
+int pd_halo_bytes(pd_sim* s, uint64_t* strip_bytes) {
+    if (!s || !strip_bytes) return fail(PD_ERR_INVALID, "NULL argument");
+    if (!s->slab) return fail(PD_ERR_STATE, "halo strips exist for row slabs only");
+    *strip_bytes = (uint64_t)s->cfg.ghost_rows * s->cfg.width * 6u;
+    return PD_OK;
+}
+
+static int halo_copy(pd_sim* s, void* a, void* b, uint32_t a_row, uint32_t b_row, int unpack, void* stream) {
+    if (!s || !a || !b) return fail(PD_ERR_INVALID, "NULL argument");
+    if (!s->slab || !s->bound) return fail(PD_ERR_STATE, "halo strips exist for bound row slabs only");
+    if (((uintptr_t)a | (uintptr_t)b) & 15u) return fail(PD_ERR_INVALID, "strips must be 16-byte aligned");
+    CK(cudaSetDevice(s->cfg.device));
+    const size_t chunks = (size_t)s->cfg.ghost_rows * s->cfg.width * 6u / 16u * 2u;
+    const size_t want = (chunks + 255) / 256, cap = (size_t)s->n_sms * 8;
+    k_halo_copy<<<(unsigned int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        s->P, (uint4*)a, (uint4*)b, a_row, b_row, s->cfg.ghost_rows, unpack);
+    CK(cudaGetLastError());
+    return PD_OK;
+}
+int pd_halo_pack(pd_sim* s, void* first_rows, void* last_rows, void* stream) {
+    if (!s) return fail(PD_ERR_INVALID, "NULL argument");
+    return halo_copy(s, first_rows, last_rows, s->P.own_y0, s->P.own_y1 - s->cfg.ghost_rows, 0, stream);
+}
+int pd_halo_unpack(pd_sim* s, const void* top_ghost, const void* bottom_ghost, void* stream) {
+    if (!s) return fail(PD_ERR_INVALID, "NULL argument");
+    return halo_copy(s, const_cast<void*>(top_ghost), const_cast<void*>(bottom_ghost), 0, s->P.own_y1, 1, stream);
 }
 
 int pd_set_profile(pd_sim* s, int on) {

@@ -11,16 +11,20 @@ the cull (:1339-1356):
         -> CAND -> gather(candidates) -> APPLY [-> sum(counts)]
 
 (the bracketed retry branch only runs while the global population is within the cap, i.e. never in the
-saturated state: a step then costs one halo exchange, one 8 KB all-reduce and one all-gather)
+saturated state: a step then costs one halo exchange, one 8 KB all-reduce and one all-gather).  CAND / APPLY
+are queued SPECULATIVELY, before the host has read the gate words: on the device they do nothing if a retry
+round turns out to be due, so the host's read never stalls the device in the saturated state.
 
 Everything else runs on the slab alone: the ghost zone (64 rows) is wider than the deepest
 dependency cone of one step (8 play sub-steps + 2 sweeps + 7 retry rounds of travel and of
 reproduction, <= 56 rows), so the owned rows come out bit-identical to a single-GPU run -- all
 random draws are keyed by the GLOBAL cell index.
 
-Two transports: `DistComm` (one slab per process/GPU, torch.distributed: NCCL on GPUs) and
-`LocalComm` (all slabs in one process on one GPU -- used by the tests to check decomposition
-invariance without a multi-GPU box).
+Three transports: `PeerComm` (one slab per process/GPU; the halo goes through peer memory -- every rank packs
+its boundary rows into a symmetric-memory outbox and its neighbours LOAD them over NVLink inside one kernel;
+the small collectives stay on NCCL), `DistComm` (the same with NCCL send/recv for the halo; also the CPU/gloo
+transport of the tests) and `LocalComm` (all slabs in one process on one GPU -- used by the tests to check
+decomposition invariance without a multi-GPU box).
 """
 from __future__ import annotations
 
@@ -29,8 +33,8 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from . import _lib
-from ._lib import (PD_PART_PRE, PD_PART_RETRY, PD_PART_HIST, PD_PART_CAND, PD_PART_APPLY, PD_GLB_WORDS,
-                   PD_HIST_WORDS)
+from ._lib import (PD_PART_PRE, PD_PART_RETRY, PD_PART_HIST, PD_PART_CAND, PD_PART_APPLY, PD_PART_DONE,
+                   PD_GLB_WORDS, PD_HIST_WORDS)
 from .sim import SimConfig, Simulation, PdabmError
 from .dist import slab_rows, ring_neighbours
 
@@ -132,6 +136,63 @@ class DistComm:
         self.dist.all_gather_into_tensor(outs[0], ins[0])
 
 
+class PeerComm(DistComm):
+    """DistComm with the halo exchange through peer memory (torch symmetric memory: cuMem allocations mapped into
+    every rank of the node, NVLink / NVSwitch underneath).  Per step and rank: ONE kernel packs the boundary rows
+    of the three planes into this rank's outbox, one device-side barrier, ONE kernel loads the two neighbours'
+    strips straight into the ghost rows.  The outbox is double-buffered by step parity, so a rank that runs ahead
+    into the next step's pack never overwrites a strip a neighbour is still reading (it cannot pass the NEXT
+    barrier before that neighbour has arrived there, i.e. has finished reading).
+    NCCL send/recv needs ~0.28 ms for the same 12.6 MB (12 point-to-point operations, profiles/README.md)."""
+
+    def __init__(self):
+        super().__init__()
+        self.hdl = None
+        self.parity = 0
+
+    def _setup(self, s: _Slab):
+        import ctypes as C
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        sim = s.sim
+        nb = C.c_uint64()
+        sim._check(sim.lib.pd_halo_bytes(sim._h, C.byref(nb)))
+        self.strip = int(nb.value)
+        total = 4 * self.strip                       # [parity][first rows | last rows]
+        self.box = symm_mem.empty((total,), dtype=torch.uint8, device=sim.device)
+        self.hdl = symm_mem.rendezvous(self.box, self.dist.group.WORLD)
+        up, down = ring_neighbours(self.rank, self.world)
+        self.up_box = self.hdl.get_buffer(up, (total,), torch.uint8)
+        self.down_box = self.hdl.get_buffer(down, (total,), torch.uint8)
+
+    def exchange(self, slabs: List[_Slab]):
+        s = slabs[0]
+        if self.hdl is None:
+            self._setup(s)
+        sim, n = s.sim, self.strip
+        off = self.parity * 2 * n
+        self.parity ^= 1
+        mine = self.box.data_ptr() + off
+        sim._check(sim.lib.pd_halo_pack(sim._h, mine, mine + n, sim.stream_ptr))
+        self.hdl.barrier(channel=0)
+        # top ghost rows = the upper slab's LAST owned rows, bottom ghost rows = the lower slab's FIRST owned rows
+        sim._check(sim.lib.pd_halo_unpack(sim._h, self.up_box.data_ptr() + off + n, self.down_box.data_ptr() + off,
+                                          sim.stream_ptr))
+
+
+def best_comm():
+    """PeerComm where torch symmetric memory works for this process group (NCCL ranks of one node), else
+    DistComm -- a slower transport for the same data, never a different compute path."""
+    import torch.distributed as dist
+    if dist.get_backend() == "nccl":
+        try:
+            import torch.distributed._symmetric_memory as symm_mem  # noqa: F401
+            return PeerComm()
+        except Exception:
+            pass
+    return DistComm()
+
+
 class DecomposedWorld:
     """`world` row slabs of one width x width world.  Same surface as Simulation where it matters:
     init_population(), step(), counts(), planes() (rank-local rows for DistComm, all rows for LocalComm)."""
@@ -173,13 +234,22 @@ class DecomposedWorld:
             sim.set_state(planes["occ"][rows], planes["energy"][rows], planes["trait"][rows], planes["strat"][rows])
         self._publish_local_counts()
 
-    def _gate(self):
-        """exit_god_fn (model.py:1614-1627) on the host, like the reference: (olds, births, parents still trying),
-        summed over the slabs.  One small pinned copy and one stream synchronisation."""
+    def _gate_request(self):
+        """exit_god_fn (model.py:1614-1627) is decided on the host, like in the reference: (olds, births, parents
+        still trying), summed over the slabs.  The read is asynchronous: a small pinned copy and an event."""
         s = self.slabs[0]
         s.gate_host.copy_(s.glb[:3], non_blocking=True)
-        self.torch.cuda.current_stream(s.sim.device).synchronize()
-        return (int(v) for v in s.gate_host.tolist())
+        ev = self.torch.cuda.Event()
+        ev.record(self.torch.cuda.current_stream(s.sim.device))
+        return ev
+
+    def _gate_open(self, ev=None):
+        s = self.slabs[0]
+        if ev is None:
+            ev = self._gate_request()
+        ev.synchronize()
+        olds, births, active = (int(v) for v in s.gate_host.tolist())
+        return olds + births <= self.cfg.max_agents and active > 0
 
     def step(self, n_steps: int = 1, want_counts: bool = True):
         import contextlib
@@ -193,28 +263,36 @@ class DecomposedWorld:
                 for s in slabs:
                     s.part(PD_PART_PRE, 0, wc)
                 comm.allreduce([s.wire for s in slabs])   # gate words + cull histogram of round 1's newborns
-                retried = False
+                # The rest of the step is queued before the host knows the gate: CAND / APPLY with arg = 1 do nothing
+                # on the device if a retry round is due.  In the saturated state (gate closed) the host's read is
+                # therefore never waited for by the device.
+                ev = self._gate_request()
+                self._finish(1, wc)
+                if not self._gate_open(ev):
+                    for s in slabs:
+                        s.part(PD_PART_DONE)
+                    continue
                 for rnd in range(1, self.retry_rounds + 1):
-                    # another round only while the GLOBAL population is within the cap and somebody is still trying:
-                    # never in the saturated state, where this read is the step's only host synchronisation
-                    olds, births, active = self._gate()
-                    if olds + births > self.cfg.max_agents or active == 0:
+                    # another round only while the GLOBAL population is within the cap and somebody is still trying
+                    if rnd > 1 and not self._gate_open():
                         break
                     for s in slabs:
                         s.part(PD_PART_RETRY, rnd, wc)
                     comm.allreduce([s.glb for s in slabs])
                     self.retry_rounds_run += 1
-                    retried = True
-                if retried:   # more newborns than the histogram saw
-                    for s in slabs:
-                        s.part(PD_PART_HIST, 0, wc)
-                    comm.allreduce([s.ghist for s in slabs])
-                for s in slabs:
-                    s.part(PD_PART_CAND, 0, wc)
-                comm.allgather([s.cand_all for s in slabs], [s.cand_out for s in slabs])
-                for s in slabs:
-                    s.part(PD_PART_APPLY, 0, wc)
+                for s in slabs:   # the retry rounds added newborns: the histogram again
+                    s.part(PD_PART_HIST, 0, wc)
+                comm.allreduce([s.ghist for s in slabs])
+                self._finish(0, wc)
             comm.allreduce([s.glb[3:] for s in slabs])  # agents + 16 counts of the last step
+
+    def _finish(self, speculative: int, wc: bool):
+        comm, slabs = self.comm, self.slabs
+        for s in slabs:
+            s.part(PD_PART_CAND, speculative, wc)
+        comm.allgather([s.cand_all for s in slabs], [s.cand_out for s in slabs])
+        for s in slabs:
+            s.part(PD_PART_APPLY, speculative, wc)
 
     def counts(self):
         """Global (population_strat_count[16], agent count) after the last step()."""

@@ -142,6 +142,10 @@ int pd_read_stats(pd_sim* sim, pd_step_stats* out, void* stream);
  *     PD_PART_HIST           only if retry rounds ran: the histogram again;  caller sums ghist
  *     PD_PART_CAND           this slab's cull candidates into cand_out;  caller gathers all blocks into cand_all
  *     PD_PART_APPLY          cull, bookkeeping; publishes glb[3..19] (agents, 16 counts)
+ * CAND and APPLY with arg = 1 are SPECULATIVE: queued before the caller has looked at the gate words, they do
+ * nothing on the device if a retry round is due (the caller then runs RETRY ... CAND, APPLY with arg = 0), and
+ * if none is due the caller confirms the step with PD_PART_DONE (no launch).  The host's read of the gate is
+ * then off the critical path: the device never waits for it in the saturated state.
  * The ghost zone is wide enough that every other phase needs no communication (DESIGN.md "Multi-GPU");
  * results are bit-identical to the whole-world run because all draws are keyed by the global cell. */
 #define PD_PART_PRE 0
@@ -149,6 +153,7 @@ int pd_read_stats(pd_sim* sim, pd_step_stats* out, void* stream);
 #define PD_PART_HIST 2
 #define PD_PART_CAND 3
 #define PD_PART_APPLY 4
+#define PD_PART_DONE 5
 #define PD_GLB_WORDS 20
 #define PD_HIST_WORDS 2048
 #define PD_MAX_WORLD 256   /* most slabs one world can be cut into */
@@ -157,6 +162,15 @@ int pd_read_stats(pd_sim* sim, pd_step_stats* out, void* stream);
 int pd_bind_comm(pd_sim* sim, uint64_t* glb, uint32_t* ghist, uint64_t* cand_out, const uint64_t* cand_all,
                  uint32_t cand_cap, uint32_t world);
 int pd_step_part(pd_sim* sim, int part, int arg, void* stream, int want_counts);
+
+/* Halo strips for an exchange through peer memory (NVLink loads from a buffer the neighbour slab exposes, e.g.
+ * torch symmetric memory): a strip holds ghost_rows rows of the three planes, packed energy | strat | tf
+ * (pd_halo_bytes bytes, 16-byte aligned).  pd_halo_pack writes this slab's first / last owned rows into two
+ * strips; pd_halo_unpack fills the top / bottom ghost rows from the strips of the upper / lower neighbour --
+ * these may be PEER device pointers.  The caller orders pack -> (all slabs packed) -> unpack. */
+int pd_halo_bytes(pd_sim* sim, uint64_t* strip_bytes);
+int pd_halo_pack(pd_sim* sim, void* first_rows, void* last_rows, void* stream);
+int pd_halo_unpack(pd_sim* sim, const void* top_ghost, const void* bottom_ghost, void* stream);
 
 /* Sum over all executed steps of the population at the START of the step (the numerator of
  * the agent-steps/s metric).  Synchronises `stream`. */

@@ -11,4 +11,4 @@ __path__.insert(0, _pkg)  # noqa: F821  (package attribute)
 
 from .sim import Simulation, SimConfig, PdabmError  # noqa: E402,F401
 from . import model  # noqa: E402,F401
-from .decomp import DecomposedWorld, LocalComm, DistComm  # noqa: E402,F401
+from .decomp import DecomposedWorld, LocalComm, DistComm, PeerComm, best_comm  # noqa: E402,F401

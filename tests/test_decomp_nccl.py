@@ -18,17 +18,17 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, comm_name):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        from pdabm_b200 import Simulation, SimConfig, DecomposedWorld, DistComm
+        from pdabm_b200 import Simulation, SimConfig, DecomposedWorld, DistComm, PeerComm
         kw = dict(width=256, seed=91, env_noise=0.05, mutation_rate=0.01, device=rank)
         ref = Simulation(SimConfig(**kw))
-        dec = DecomposedWorld(SimConfig(**kw), DistComm())
+        dec = DecomposedWorld(SimConfig(**kw), PeerComm() if comm_name == "peer" else DistComm())
         ref.init_population()
         dec.init_population()
         rows = slice(rank * (256 // world), (rank + 1) * (256 // world))
@@ -51,7 +51,8 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_gpus_nccl_equal_whole_world():
+@pytest.mark.parametrize("comm_name", ["nccl", "peer"])
+def test_two_gpus_nccl_equal_whole_world(comm_name):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -59,7 +60,7 @@ def test_two_gpus_nccl_equal_whole_world():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, comm_name)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in range(2)]
