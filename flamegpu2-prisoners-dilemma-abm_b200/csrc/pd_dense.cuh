@@ -31,6 +31,12 @@
 namespace pd {
 
 constexpr int NT = 256;  // threads per CTA of the dense sweeps
+#ifndef PD_PLAY_CTAS
+#define PD_PLAY_CTAS 5   // resident CTAs per SM the play sweep is compiled for (register budget)
+#endif
+#ifndef PD_CLAIM_CTAS
+#define PD_CLAIM_CTAS 8  // (32 registers: 0.80 -> 0.73 ms against 6 CTAs at 40)
+#endif
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
 // living cost for one agent (environmental_punishment, :1357-1368); returns false if it dies
@@ -211,7 +217,7 @@ __device__ __forceinline__ float play_games(const Params& p, const float* s_lut,
 }
 
 template <int TW, int TH>
-__global__ void __launch_bounds__(NT, 5) k_play_travel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_constant__ Params p) {
     // R words: TH + 2 rows of GROW groups of 4 cells -- the groups left and right of the tile hold the ring columns
     constexpr int GROW = TW / 4 + 2, SWR = 4 * GROW, NC = TW * TH;
     constexpr int NI = NC / 4, NITEM = NI + 2 * GROW + 2 * TH;  // interior groups, then the ring's: top, bottom, sides
@@ -449,7 +455,7 @@ __device__ __forceinline__ Outcome outcome_of(const Params& p, float e1, bool pa
 }
 
 template <int TW, int TH>
-__global__ void __launch_bounds__(NT) k_claim_punish(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(NT, PD_CLAIM_CTAS) k_claim_punish(const __grid_constant__ Params p) {
     constexpr int SW = TW + 32, SH = TH + 2, NC = TW * TH;
     __shared__ __align__(16) uint8_t s_tf[SH * SW];
     __shared__ uint16_t s_par[NC];

@@ -156,7 +156,10 @@ __global__ void __launch_bounds__(BS) k_risk_resolve(const __grid_constant__ Par
 // together, stages what it appends to the global lists (losers, newborns) in shared memory and reserves the
 // space with ONE atomic per chunk and list: a warp-level append per entry makes ~10^6 atomics per step on one
 // address, which the L2 serialises (that alone was 2/3 of k_repro_commit's time, profiles/README.md).
-constexpr int COMMIT_NT = 256, COMMIT_K = 4, COMMIT_CHUNK = COMMIT_NT * COMMIT_K;
+#ifndef PD_COMMIT_K
+#define PD_COMMIT_K 4
+#endif
+constexpr int COMMIT_NT = 256, COMMIT_K = PD_COMMIT_K, COMMIT_CHUNK = COMMIT_NT * COMMIT_K;
 
 // k_move_commit: move_response (:881-960), round 1.  A winner relocates -- energy, strategies and trait (they
 // came with the list entry) go to the target cell -- and leaves a GHOST that keeps blocking movers this step

@@ -239,7 +239,10 @@ int push_step(pd_sim* s, cudaStream_t st) {
 // the sparse round-1 commits: independent threads over a device-side list length, grid-stride
 int launch_commit(pd_sim* s, void (*kernel)(const Params), cudaStream_t st) {
     const size_t want = (s->cells / 16 + COMMIT_CHUNK - 1) / COMMIT_CHUNK;  // ~5 % of the cells claim
-    const size_t cap = (size_t)s->n_sms * 8;
+#ifndef PD_COMMIT_CAP
+#define PD_COMMIT_CAP 16  // CTAs per SM of the commit kernels' grid (measured: 8 -> 16 saves 0.02 ms)
+#endif
+    const size_t cap = (size_t)s->n_sms * PD_COMMIT_CAP;
     kernel<<<(unsigned int)(want < cap ? want : cap), COMMIT_NT, 0, st>>>(s->P);
     CK(cudaGetLastError());
     return PD_OK;
