@@ -360,6 +360,7 @@ __global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_c
     __syncthreads();
     // ---- movers: travel cost, death, random start, probe, claim (:794-868)
     const unsigned int n_mover = s_n[2];
+    const uint32_t step = __ldg(&p.ctr->step_no);
     unsigned int n_travel_deaths = 0;
     for (unsigned int k = tid; k < n_mover; k += NT) {
         const int cl = s_mover[k];
@@ -379,8 +380,8 @@ __global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_c
         const Words w = rng(p, gcell_of(p, x0 + lx, y0 + ly), S_TRAVEL);
         int l = (int)(w.y >> 29), seq = 0;  // :810
         const int dir = probe(occ_mask, l, seq);
-        if (dir >= 0 && claim_in_range(p, y0 + ly, dir)) {
-            prefetch_claim(p.claim, nb_local(p, x0 + lx, y0 + ly, dir));
+        if (dir >= 0) {
+            prefetch_claim(p.claim + nb_local(p, x0 + lx, y0 + ly, dir));
             s_cells[satom_add(&s_n[3], 1u)] = (uint32_t)cl | ((uint32_t)dir << 16);  // (the agent list is spent)
         }
     }
@@ -408,8 +409,8 @@ __global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_c
                 const uint32_t x = x0 + (cl & (TW - 1)), y = y0 + (cl >> LOG_TW);
                 const int dir = (int)(ent >> 16);
                 // :861-868: the request goes to the target cell.  Posted here, after the CTA's last barrier (a barrier
-                // waits for the CTA's outstanding reductions)
-                post_claim(p.claim, nb_local(p, x, y, dir), dir);
+                // waits for the CTA's outstanding reductions), with the priority drawn again rather than kept
+                post_claim(p.claim + nb_local(p, x, y, dir), claim_word(step, CLAIM_TRAVEL, rng(p, gcell_of(p, x, y), S_TRAVEL).x, dir));
                 p.cl_cell[base + k] = (y << p.log2W) | x;
                 p.cl_e[base + k] = s_e[cl];  // (after the travel cost)
                 // the mover's trait and strategies ride along (bits 1-2 and 3-10 of its word)
@@ -460,6 +461,7 @@ __global__ void __launch_bounds__(NT, PD_CLAIM_CTAS) k_claim_punish(const __grid
     __shared__ __align__(16) uint8_t s_tf[SH * SW];
     __shared__ uint16_t s_par[NC];
     __shared__ uint32_t s_claim[NC];   // claimants: tile-local cell | direction << 16
+    __shared__ uint32_t s_prio[NC];
     __shared__ uint16_t s_risk[NC];
     __shared__ unsigned int s_bins[16];
     __shared__ unsigned int s_n[8];  // 0 parents, 1 claimants, 2 base of the claim entries, 3 agents, 4 at-risk, 5 their base, 6 deaths
@@ -554,6 +556,7 @@ __global__ void __launch_bounds__(NT, PD_CLAIM_CTAS) k_claim_punish(const __grid
     }
     __syncthreads();
     const unsigned int n_par = s_n[0];
+    const uint32_t step = __ldg(&p.ctr->step_no);
     for (unsigned int k = tid; k < n_par; k += NT) {
         const int cl = s_par[k];
         const int ly = cl / TW, lx = cl - ly * TW;
@@ -566,9 +569,11 @@ __global__ void __launch_bounds__(NT, PD_CLAIM_CTAS) k_claim_punish(const __grid
         const Words w = rng(p, gcell_of(p, x0 + lx, y0 + ly), S_REPRO);
         int l = (int)(w.y >> 29), seq = 0;  // :1079
         const int dir = probe(occ_mask, l, seq);
-        if (dir >= 0 && claim_in_range(p, y0 + ly, dir)) {
-            prefetch_claim(p.claim, nb_local(p, x0 + lx, y0 + ly, dir));
-            s_claim[satom_add(&s_n[1], 1u)] = (uint32_t)cl | ((uint32_t)dir << 16);
+        if (dir >= 0) {
+            prefetch_claim(p.claim + nb_local(p, x0 + lx, y0 + ly, dir));
+            const unsigned int slot = satom_add(&s_n[1], 1u);
+            s_claim[slot] = (uint32_t)cl | ((uint32_t)dir << 16);
+            s_prio[slot] = w.x;
         }
     }
     __syncthreads();
@@ -593,7 +598,7 @@ __global__ void __launch_bounds__(NT, PD_CLAIM_CTAS) k_claim_punish(const __grid
                 const int dir = (int)(ent >> 16);
                 // :1123-1130: the request goes to the target cell (posted after the CTA's last barrier: a barrier
                 // waits for the CTA's outstanding reductions)
-                post_claim(p.claim, nb_local(p, x, y, dir), dir);
+                post_claim(p.claim + nb_local(p, x, y, dir), claim_word(step, CLAIM_REPRO, s_prio[k], dir));
                 const uint32_t cell = (y << p.log2W) | x;
                 p.cl_cell[base + k] = cell;
                 p.cl_e[base + k] = p.E1[cell];  // (this CTA has just read the tile: an L2 hit)

@@ -120,10 +120,10 @@ struct Params {
     // sparse lists
     uint32_t* risk_cur; uint32_t* risk_next; float* risk_e;
     unsigned long long* cand;  // cull select: the threshold bin's candidate keys (list_cap / 2 of them)
-    // One byte per cell: who claims it this round (post_claim / claim_won).  Replaces the move / reproduction
-    // request messages keyed by the target's bucket (:864-868, :1126-1130) and the "highest roll wins" scan of
-    // their readers (:929, :1192).
-    uint8_t* claim;
+    // One 64-bit word per cell: the highest claim posted on it (claim_word; atomic max, never cleared -- newer
+    // rounds carry a higher tag).  Replaces the move / reproduction request messages keyed by the target's bucket
+    // (:864-868, :1126-1130) and the "highest roll wins" scan of their readers (:929, :1192).
+    unsigned long long* claim;
     // Round 1 claimants (the travel phase's, then the reproduction phase's).  An entry carries what the commit
     // needs of the claimant, so that it costs the commit no random reads: cell, energy (E1 of the cell), and
     // aux = claimed direction | trait << 3 | strategies << 5 (strategies: travel only)
@@ -176,46 +176,31 @@ __device__ __forceinline__ uint64_t nb_gcell(const Params& p, uint32_t x, uint32
 }
 
 // ---- claims (move_request :864-868 / move_response :929-935; god_go_forth :1126-1130 / god_multiply :1192-1198) --
-// The claim plane holds ONE BYTE per cell: bit j set = "the agent on my neighbour cell j claims me this round"
-// (j = 7 - the direction it claimed).  A claimant posts its bit with an atomic OR; when the round is resolved it
-// looks at the byte: alone -> it has won; with rivals -> the highest (Philox priority, j) wins (:929 / :1192 --
-// j, unique among the rivals of one cell, takes the place of the reference's id comparison), the rivals'
-// priorities being recomputed from their cells, never communicated.  The winner clears the byte, so the plane is
-// all zero again when the round is over (a rival that looks later finds its bit gone: it has lost).
-// At 1 byte per cell the plane of a 2^28-cell world is 256 MB -- half of it fits in the L2, and one 64-byte
-// DRAM access covers the claims of 64 cells.
-__device__ __forceinline__ void prefetch_claim(const uint8_t* claim, uint32_t tgt) {
-    // (a reduction on a line that misses in the L2 is served far more slowly than a load: ask for the line ahead)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(claim + tgt));
+// A claimant posts ONE word on its target cell with an atomic max and has won iff the cell still holds exactly
+// its word when the round is resolved.  Layout, most significant first:
+//     tag  (29 bits)  (step & 0x1FFFFFF) << 4 | phase << 3 | round   -- phase 0 travel, 1 reproduction; round 0..7
+//     prio (32 bits)  the claimant's Philox priority (:806, :1076): the highest roll wins
+//     j    (3 bits)   7 - claimed direction = where the claimant stands as seen from the cell.  Unique among the
+//                     rivals of one cell; decides a tie of the priorities (it takes the place of the id comparison
+//                     of :929 / :1192, like the direction class does for the play rolls)
+// The tag grows with every round, so a word left over from an earlier round, phase or step always loses: the plane
+// is never cleared (the host zeroes it when the step counter's 25 bits wrap, and whenever the step is set).
+constexpr uint32_t CLAIM_TRAVEL = 0u, CLAIM_REPRO = 8u;
+__device__ __forceinline__ unsigned long long claim_word(uint32_t step, uint32_t phase_round, uint32_t prio, int dir) {
+    const unsigned long long tag = ((unsigned long long)(step & 0x1FFFFFFu) << 4) | phase_round;
+    return (tag << 35) | ((unsigned long long)prio << 3) | (unsigned long long)(7 - dir);
 }
-__device__ __forceinline__ void post_claim(uint8_t* claim, uint32_t tgt, int dir) {
-    uint32_t* word = reinterpret_cast<uint32_t*>(claim) + (tgt >> 2);
-    const uint32_t bit = 1u << (8u * (tgt & 3u) + (uint32_t)(7 - dir));
-    asm volatile("red.global.or.b32 [%0], %1;" ::"l"(word), "r"(bit) : "memory");
+// A reduction on a word that misses in the L2 is served far more slowly than a load (measured: 16 M reductions
+// per ms against > 100 M random sector loads): the claimant asks for the word's line ahead of posting
+__device__ __forceinline__ void prefetch_claim(const unsigned long long* word) {
+#ifndef PD_EXP_NO_PREFETCH
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(word));
+#endif
 }
-// Has the claimant at local (x, y), which claimed direction `dir` with a priority drawn from `stream`, won the
-// cell?  byte = the claim byte of its target as it is now.
-__device__ __forceinline__ bool claim_won(const Params& p, uint32_t byte, uint32_t x, uint32_t y, int dir, uint32_t stream) {
-    const uint32_t me = 1u << (7 - dir);
-    if (!(byte & me)) return false;      // the winner has already cleared the byte
-    uint32_t rivals = byte & ~me;
-    if (!rivals) return true;            // the usual case: no Philox call at all
-    const uint32_t mine = rng(p, gcell_of(p, x, y), stream).x;
-    const uint32_t tx = (x + (uint32_t)DX(dir)) & (p.W - 1);
-    const uint32_t ty = y + (uint32_t)DY(dir);   // (only its global row matters below: nb_gcell reduces it)
-    for (; rivals; rivals &= rivals - 1) {
-        const int j = __ffs(rivals) - 1;
-        const uint32_t pr = rng(p, nb_gcell(p, tx, ty, j), stream).x;
-        if (pr > mine || (pr == mine && j > 7 - dir)) return false;   // the highest (priority, j) wins
-    }
-    return true;
-}
-// A slab does not wrap: a claim from its outermost rows towards a row it does not hold is dropped (those rows
-// are far outside the zone whose results are used)
-__device__ __forceinline__ bool claim_in_range(const Params& p, uint32_t y, int dir) {
-    if (p.wrap_y) return true;
-    const int r = (int)y + DY(dir);
-    return r >= 0 && r < (int)p.H;
+__device__ __forceinline__ void post_claim(unsigned long long* word, unsigned long long v) {
+#ifndef PD_EXP_NO_RED
+    asm volatile("red.global.max.u64 [%0], %1;" ::"l"(word), "l"(v) : "memory");
+#endif
 }
 
 // ---- the game as the RESPONDER sees it (play_response, :599-689) --------------------------

@@ -12,9 +12,8 @@
 //   k_repro_retry   sparse: reproduction rounds 2..8 (gated by the carrying capacity)
 //   k_finalize      sparse: newborn cull (exact k-th selection), the surviving newborns enter the planes
 // Every dense sweep is a pure GATHER on the state planes: a cell reads its neighbourhood and writes only itself.
-// Claims go through ONE extra plane of a byte per cell, written with atomic OR (one bit per claimant position; the
-// north star's "atomicMin on packed (priority, id) per target cell" with the priorities recomputed for the few
-// contested cells instead of stored) and cleared by the winners.
+// Claims go through ONE extra plane of 64-bit words with atomic max (the north star's "atomicMin on packed
+// (priority, id) per target cell"), tagged by step / phase / round so that it never needs clearing.
 // The persistent sparse kernels are templated on their block size: one 1024-thread CTA on small worlds,
 // 512-thread CTAs (128 registers available) in the cooperative multi-CTA launch.
 #pragma once
@@ -141,8 +140,8 @@ __global__ void __launch_bounds__(BS) k_risk_resolve(const __grid_constant__ Par
 
 // ------------------------------------------------------------------------------------------
 // Claim resolution (sparse).  The dense sweeps post round 1's claims on the claim plane and list the claimants;
-// a claimant has won iff it is alone on its target's claim byte or beats its rivals there (pd_device.cuh claim_won).
-//   k_move_commit / k_repro_commit   round 1: independent threads over the listed claimants (claim_won)
+// a claimant has won iff its target's word is still its own (pd_device.cuh claim_word).
+//   k_move_commit / k_repro_commit   round 1: independent threads over the listed claimants
 //   k_move_retry / k_repro_retry     rounds 2..8 for the losers (~5 % of the movers, ~1/3 of the attempting
 //                                    parents -- and at saturation the population gate stops reproduction after
 //                                    round 1), persistent, two phases per round separated by grid barriers:
@@ -172,12 +171,14 @@ __global__ void __launch_bounds__(COMMIT_NT) k_move_commit(const __grid_constant
     Counters* ctr = p.ctr;
     unsigned int n = ctr->mv_n;
     if (n > p.list_cap) n = p.list_cap;
+    const uint32_t step = __ldg(&ctr->step_no);
     const int tid = threadIdx.x;
     unsigned int moved = 0;
     for (unsigned int c0 = blockIdx.x * COMMIT_CHUNK; c0 < n; c0 += gridDim.x * COMMIT_CHUNK) {
         if (tid == 0) s_n[0] = 0;
         __syncthreads();
-        uint32_t cell[COMMIT_K], tgt[COMMIT_K], aux[COMMIT_K], top[COMMIT_K];
+        uint32_t cell[COMMIT_K], tgt[COMMIT_K], aux[COMMIT_K];
+        unsigned long long top[COMMIT_K];
         float e[COMMIT_K];
 #pragma unroll
         for (int k = 0; k < COMMIT_K; ++k) {
@@ -196,9 +197,9 @@ __global__ void __launch_bounds__(COMMIT_NT) k_move_commit(const __grid_constant
             const bool valid = c0 + k * COMMIT_NT + tid < n;
             const int d = (int)(aux[k] & 7u);
             const uint32_t x = cell[k] & (p.W - 1), y = cell[k] >> p.log2W;
-            const bool won = valid && claim_won(p, top[k], x, y, d, S_TRAVEL);
+            const unsigned long long mine = claim_word(step, CLAIM_TRAVEL, rng(p, gcell_of(p, x, y), S_TRAVEL).x, d);
+            const bool won = valid && top[k] == mine;
             if (won) {  // :946-956
-                p.claim[tgt[k]] = 0;
                 p.E1[tgt[k]] = e[k];
                 p.strat[tgt[k]] = (uint8_t)(aux[k] >> 5);
                 p.tfB[tgt[k]] = (uint8_t)(TF_OCC | ((aux[k] >> 3) & TF_TRAIT));
@@ -251,13 +252,15 @@ __global__ void __launch_bounds__(COMMIT_NT) k_repro_commit(const __grid_constan
     Counters* ctr = p.ctr;
     unsigned int n = ctr->rp_n;
     if (n > p.list_cap) n = p.list_cap;
+    const uint32_t step = __ldg(&ctr->step_no);
     const int tid = threadIdx.x;
     if (blockIdx.x * COMMIT_CHUNK >= n) return;
     for (int i = tid; i < 2048; i += COMMIT_NT) s_hist[i] = 0;
     for (unsigned int c0 = blockIdx.x * COMMIT_CHUNK; c0 < n; c0 += gridDim.x * COMMIT_CHUNK) {
         if (tid < 2) s_n[tid] = 0;
         __syncthreads();
-        uint32_t cell[COMMIT_K], tgt[COMMIT_K], aux[COMMIT_K], top[COMMIT_K];
+        uint32_t cell[COMMIT_K], tgt[COMMIT_K], aux[COMMIT_K];
+        unsigned long long top[COMMIT_K];
         float e[COMMIT_K];
 #pragma unroll
         for (int k = 0; k < COMMIT_K; ++k) {
@@ -276,10 +279,10 @@ __global__ void __launch_bounds__(COMMIT_NT) k_repro_commit(const __grid_constan
             const bool valid = c0 + k * COMMIT_NT + tid < n;
             const int d = (int)(aux[k] & 7u);
             const uint32_t x = cell[k] & (p.W - 1), y = cell[k] >> p.log2W;
-            const bool won = valid && claim_won(p, top[k], x, y, d, S_REPRO);
+            const unsigned long long mine = claim_word(step, CLAIM_REPRO, rng(p, gcell_of(p, x, y), S_REPRO).x, d);
+            const bool won = valid && top[k] == mine;
             bool born = false;
             if (won) {  // REPRODUCTION_COMPLETE (:1211-1213, :1331)
-                p.claim[tgt[k]] = 0;
                 const uint32_t trait = (aux[k] >> 3) & TF_TRAIT;
                 if (row_owned(p, y)) parent_outcome(p, cell[k], e[k], trait);
                 born = row_owned(p, tgt[k] >> p.log2W);
@@ -347,6 +350,7 @@ __global__ void __launch_bounds__(BS) k_move_retry(const __grid_constant__ Param
     if (n == 0) return;
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t step = __ldg(&ctr->step_no);
     uint8_t* tf = p.tfB;
     unsigned int moved = 0;
     for (int round = 1; round < 8; ++round) {
@@ -361,15 +365,16 @@ __global__ void __launch_bounds__(BS) k_move_retry(const __grid_constant__ Param
             for (int d = 0; d < 8; ++d)
                 if (__ldcg(tf + nb_local(p, x, y, d)) & (TF_OCC | TF_GHOST)) blocked |= 1u << d;
             int l = (int)(st & 7u), seq = (int)((st >> 3) & 7u) + 1;
+            const Words w = rng(p, gcell_of(p, x, y), S_TRAVEL);  // the roll of the first attempt is kept (:794-807)
             if (st & 0x40u) {  // fresh from round 1: it claimed direction l after probe_pos probes (:848-849)
-                seq = probe_pos((int)(rng(p, gcell_of(p, x, y), S_TRAVEL).y >> 29), l);
+                seq = probe_pos((int)(w.y >> 29), l);
                 l = (l + 1) & 7;
             }
             const int dir = probe(blocked, l, seq);
-            if (dir < 0 || !claim_in_range(p, y, dir)) {
+            if (dir < 0) {
                 p.rt_state[i] = 0;  // no free space: stays put (:842-846)
             } else {
-                post_claim(p.claim, nb_local(p, x, y, dir), dir);
+                post_claim(p.claim + nb_local(p, x, y, dir), claim_word(step, CLAIM_TRAVEL + (uint32_t)round, w.x, dir));
                 p.rt_state[i] = (uint8_t)(0x80u | (uint32_t)((dir + 1) & 7) | ((uint32_t)(seq - 1) << 3));
                 p.rt_aux[i] = (uint8_t)dir;
             }
@@ -383,8 +388,9 @@ __global__ void __launch_bounds__(BS) k_move_retry(const __grid_constant__ Param
             const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
             const int d = (int)(p.rt_aux[i] & 7u);
             const uint32_t tgt = nb_local(p, x, y, d);
-            if (claim_won(p, __ldcg(p.claim + tgt), x, y, d, S_TRAVEL)) {  // the winner relocates (:946-956)
-                p.claim[tgt] = 0;
+            const unsigned long long top = __ldcg(p.claim + tgt);
+            const unsigned long long mine = claim_word(step, CLAIM_TRAVEL + (uint32_t)round, rng(p, gcell_of(p, x, y), S_TRAVEL).x, d);
+            if (top == mine) {  // the winner relocates (:946-956)
                 const uint32_t t = __ldcg(tf + cell);
                 p.E1[tgt] = __ldcg(p.E1 + cell);
                 p.strat[tgt] = __ldcg(p.strat + cell);
@@ -417,6 +423,7 @@ __global__ void __launch_bounds__(BS) k_repro_retry(const __grid_constant__ Para
     if (n == 0) return;
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t step = __ldg(&ctr->step_no);
     uint8_t* tf = p.tfB;
     for (int round = (int)p.round0; round < (int)p.round1; ++round) {
         // overpopulated gate, evaluated after every round (:1616, :1621-1625); in slab mode the caller
@@ -446,15 +453,16 @@ __global__ void __launch_bounds__(BS) k_repro_retry(const __grid_constant__ Para
             for (int d = 0; d < 8; ++d)
                 if (__ldcg(tf + nb_local(p, x, y, d)) & TF_OCC) blocked |= 1u << d;
             int l = (int)(st & 7u), seq = (int)((st >> 3) & 7u) + 1;
+            const Words w = rng(p, gcell_of(p, x, y), S_REPRO);  // the roll of the first attempt is kept (:1074-1076)
             if (st & 0x40u) {  // fresh from round 1: it claimed direction l after probe_pos probes (:1110-1111)
-                seq = probe_pos((int)(rng(p, gcell_of(p, x, y), S_REPRO).y >> 29), l);
+                seq = probe_pos((int)(w.y >> 29), l);
                 l = (l + 1) & 7;
             }
             const int dir = probe(blocked, l, seq);  // also covers reproduce_sequence >= 8 (:1067)
-            if (dir < 0 || !claim_in_range(p, y, dir)) {
+            if (dir < 0) {
                 p.rt_state[i] = 0x40u;  // REPRODUCTION_IMPOSSIBLE (:1104-1108)
             } else {
-                post_claim(p.claim, nb_local(p, x, y, dir), dir);
+                post_claim(p.claim + nb_local(p, x, y, dir), claim_word(step, CLAIM_REPRO + (uint32_t)round, w.x, dir));
                 p.rt_state[i] = (uint8_t)(0x80u | (uint32_t)((dir + 1) & 7) | ((uint32_t)(seq - 1) << 3));
                 p.rt_aux[i] = (uint8_t)dir;
             }
@@ -471,8 +479,10 @@ __global__ void __launch_bounds__(BS) k_repro_retry(const __grid_constant__ Para
                 const uint32_t x = cell & (p.W - 1), y = cell >> p.log2W;
                 const int d = (int)(p.rt_aux[i] & 7u);
                 tgt = nb_local(p, x, y, d);
-                if (claim_won(p, __ldcg(p.claim + tgt), x, y, d, S_REPRO)) {
-                    p.claim[tgt] = 0;
+                const uint64_t g = gcell_of(p, x, y);
+                const unsigned long long top = __ldcg(p.claim + tgt);
+                const unsigned long long mine = claim_word(step, CLAIM_REPRO + (uint32_t)round, rng(p, g, S_REPRO).x, d);
+                if (top == mine) {
                     const uint32_t t = __ldcg(tf + cell);
                     if (row_owned(p, y)) parent_outcome(p, cell, __ldcg(p.E1 + cell), t & TF_TRAIT);  // :1211-1213
                     tf[tgt] = (uint8_t)(TF_OCC | TF_NEWBORN | (t & TF_TRAIT));  // blocks its cell in later rounds

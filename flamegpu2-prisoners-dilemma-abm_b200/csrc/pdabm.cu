@@ -88,7 +88,7 @@ struct pd_sim {
     double kernel_ms[PDABM_NUM_KERNELS];
     uint32_t prof_steps;
     bool step_dirty;               // host step number not yet written to Counters::step_no
-    bool claim_dirty;              // the claim plane may not be all zero (fresh allocation, aborted step): zero it
+    bool claim_dirty;              // the claim plane may hold words with tags that are not in the past: zero it
     // CUDA graphs of one whole step (9 launches), one per (at-risk list parity, want_counts); used for worlds
     // small enough that launch latency matters, on explicit (capturable) streams, when profiling is off
     bool graphs;
@@ -218,11 +218,12 @@ static const bool g_debug_sync = getenv("PDABM_DEBUG_SYNC") != nullptr;
         }                                                                                            \
     } while (0)
 
-// The claim plane is all zero between rounds (every claimed byte is cleared by its winner).  A fresh handle, a
-// (re)initialised population or a state uploaded by the caller starts from a clean plane.
+// Claim words carry (step mod 2^25) in their tag and are never cleared, because a later round always has a higher
+// tag.  That stops being true when the step is set from outside (pd_set_step, pd_init_population) or its 25 bits
+// wrap: the step then starts from a clean plane.
 int begin_claims(pd_sim* s, cudaStream_t st) {
-    if (s->claim_dirty) {
-        CK(cudaMemsetAsync(s->P.claim, 0, s->cells, st));
+    if (s->claim_dirty || (s->step & 0x1FFFFFFu) == 0u) {
+        CK(cudaMemsetAsync(s->P.claim, 0, s->cells * sizeof(unsigned long long), st));
         s->claim_dirty = false;
     }
     return PD_OK;
@@ -448,7 +449,7 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     P.sparse_ctas = (uint32_t)s->sparse_ctas;
     s->graphs = cfg->use_graphs > 0 || (cfg->use_graphs == 0 && !slab && s->cells <= ((size_t)1 << 22));
     if (slab) s->graphs = false;  // a slab is stepped in parts with host decisions in between
-    CK(cudaMalloc(&P.claim, s->cells));
+    CK(cudaMalloc(&P.claim, s->cells * sizeof(unsigned long long)));
     s->claim_dirty = true;  // zeroed on the stream of the first step
     {
         float h_lut[256], *d_lut = nullptr;
@@ -818,6 +819,7 @@ int pd_set_step(pd_sim* s, uint32_t step) {
     if (!s) return fail(PD_ERR_INVALID, "NULL argument");
     s->step = step;
     s->step_dirty = true;  // written to the device at the start of the next step call, on its stream
+    s->claim_dirty = true;
     return PD_OK;
 }
 
