@@ -227,6 +227,7 @@ def run_ours(args, rank, world, local_rank):
     from pdabm_b200 import Simulation, SimConfig
 
     from pdabm_b200 import DecomposedWorld, best_comm
+    from pdabm_b200.dist import reduce_throughput
     width, overrides, desc = CONFIG5 if args.workload == "config5" else WORKLOADS[args.workload]
     if args.width:
         width = args.width
@@ -400,13 +401,10 @@ def run_ours(args, rank, world, local_rank):
             big.step(1, want_counts=False)
         e51.record()
         barrier()
-        t5 = torch.tensor([e50.elapsed_time(e51)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t5, op=dist.ReduceOp.MAX)
-        g5 = torch.tensor([big.agent_steps() - a5], dtype=torch.float64, device="cuda")
-        dist.all_reduce(g5, op=dist.ReduceOp.SUM)
+        g5, t5 = reduce_throughput(big.agent_steps() - a5, e50.elapsed_time(e51), device="cuda")
         also = {"config5": {"workload": d5 + f"; one {w5}x{w5} world in 8 row slabs (2^29 cells per GPU)", "steps": 20,
-                            "ms_per_step": float(t5[0]) / 20, "value": float(g5[0]) / (float(t5[0]) / 1e3),
-                            "unit": "agent-steps/s", "cell_steps_per_s": w5 * w5 * 20 / (float(t5[0]) / 1e3),
+                            "ms_per_step": t5 / 20, "value": g5 / (t5 / 1e3),
+                            "unit": "agent-steps/s", "cell_steps_per_s": w5 * w5 * 20 / (t5 / 1e3),
                             "agents_at_end": big.counts()[1]}}
         sim = big
 
@@ -605,6 +603,7 @@ def run_config4(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from pdabm_b200 import Simulation, SimConfig
+    from pdabm_b200.dist import reduce_throughput
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -649,12 +648,7 @@ def run_config4(args, rank, world, local_rank):
     torch.cuda.synchronize()
     ms = max(start.elapsed_time(e) for e in ends)
     agent_steps = sum(s.agent_steps() for s in sims) - as0
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        a = torch.tensor([agent_steps], dtype=torch.float64, device="cuda")
-        dist.all_reduce(a, op=dist.ReduceOp.SUM)
-        ms, agent_steps = float(t[0]), float(a[0])
+    agent_steps, ms = reduce_throughput(agent_steps, ms, device="cuda")  # SUM of the units, MAX of the times
     if rank == 0:
         line = {"metric": "agent-steps/sec", "value": agent_steps / (ms / 1e3), "unit": "agent-steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

@@ -35,7 +35,7 @@ constexpr int NT = 256;  // threads per CTA of the dense sweeps
 #define PD_PLAY_CTAS 5   // resident CTAs per SM the play sweep is compiled for (register budget)
 #endif
 #ifndef PD_CLAIM_CTAS
-#define PD_CLAIM_CTAS 8  // (32 registers: 0.80 -> 0.73 ms against 6 CTAs at 40)
+#define PD_CLAIM_CTAS 6   // (measured: 6 CTAs at 40 registers 0.87 ms, 8 at 32 registers 0.89 ms)
 #endif
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
@@ -300,11 +300,7 @@ __global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_c
                 r4 = make_uint4(rr[0], rr[1], rr[2], rr[3]);
             }
             if (j < NITEM) *reinterpret_cast<uint4*>(s_R + sw[it]) = r4;
-#ifdef PD_EXP_WAPPEND
-            if (it * NT < NI) wappend4(&s_n[0], s_cells, j < NI ? occ4 : 0u, v);
-#else
             if (j < NI) tappend4(&s_n[0], s_cells, occ4, v);
-#endif
         }
     }
     asm volatile("cp.async.wait_all;");

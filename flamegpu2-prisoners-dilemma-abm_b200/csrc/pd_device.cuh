@@ -185,6 +185,10 @@ __device__ __forceinline__ uint64_t nb_gcell(const Params& p, uint32_t x, uint32
 //                     of :929 / :1192, like the direction class does for the play rolls)
 // The tag grows with every round, so a word left over from an earlier round, phase or step always loses: the plane
 // is never cleared (the host zeroes it when the step counter's 25 bits wrap, and whenever the step is set).
+// (A plane of one BYTE per cell -- a bit per claimant position, OR-ed in, rivals decided by recomputed priorities,
+// cleared by the winner -- is 8 x smaller and was 1 % faster, but row slabs at 2^28 cells then disagreed with the
+// whole world in a few cells every other run, non-deterministically and for reasons not understood; this design
+// has no state to clear and passed every repetition.  profiles/README.md "byte claim plane".)
 constexpr uint32_t CLAIM_TRAVEL = 0u, CLAIM_REPRO = 8u;
 __device__ __forceinline__ unsigned long long claim_word(uint32_t step, uint32_t phase_round, uint32_t prio, int dir) {
     const unsigned long long tag = ((unsigned long long)(step & 0x1FFFFFFu) << 4) | phase_round;
@@ -193,14 +197,10 @@ __device__ __forceinline__ unsigned long long claim_word(uint32_t step, uint32_t
 // A reduction on a word that misses in the L2 is served far more slowly than a load (measured: 16 M reductions
 // per ms against > 100 M random sector loads): the claimant asks for the word's line ahead of posting
 __device__ __forceinline__ void prefetch_claim(const unsigned long long* word) {
-#ifndef PD_EXP_NO_PREFETCH
     asm volatile("prefetch.global.L2 [%0];" ::"l"(word));
-#endif
 }
 __device__ __forceinline__ void post_claim(unsigned long long* word, unsigned long long v) {
-#ifndef PD_EXP_NO_RED
     asm volatile("red.global.max.u64 [%0], %1;" ::"l"(word), "l"(v) : "memory");
-#endif
 }
 
 // ---- the game as the RESPONDER sees it (play_response, :599-689) --------------------------

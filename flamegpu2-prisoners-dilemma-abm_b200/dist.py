@@ -4,12 +4,20 @@ The path shards in two ways:
   * ensemble: independent runs, run i -> rank i mod world; NO data-path collective, the host only
     gathers per-run logs (CUDAEnsemble, /root/reference/src/model.py:1801-1810, :2188);
   * one world in row slabs: rows [row0, row0+rows) per rank, periodic ring of neighbours.
-Only the bookkeeping lives here; it runs on CPU tensors with the gloo backend in the tests and on
-CUDA tensors with NCCL in bench.py.
+Only the bookkeeping lives here (model.run_ensemble, decomp.py and bench.py call it); it runs on CPU tensors
+with the gloo backend in the tests and on CUDA tensors with NCCL on the GPUs.
 """
 from __future__ import annotations
 
 from typing import Dict, List, Sequence, Tuple
+
+
+def rank_world() -> Tuple[int, int]:
+    """(rank, world size) of this process; (0, 1) outside torch.distributed."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
 
 
 def shard_runs(runs: Sequence, rank: int, world: int) -> List:
@@ -41,16 +49,6 @@ def reduce_throughput(agent_steps: float, seconds: float, device=None) -> Tuple[
     dist.all_reduce(a, op=dist.ReduceOp.SUM)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(a.item()), float(t.item())
-
-
-def allreduce_counts(counts, n_agents: int, device=None):
-    """Global population_strat_count[16] + agent count of a row-decomposed world (17 words)."""
-    import torch
-    import torch.distributed as dist
-    v = torch.tensor(list(int(c) for c in counts) + [int(n_agents)], dtype=torch.int64, device=device)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(v, op=dist.ReduceOp.SUM)
-    return v[:16].tolist(), int(v[16].item())
 
 
 def gather_logs(paths: List[str]) -> List[str]:

@@ -205,9 +205,17 @@ def configure_runplan(base: SimConfig, multi_run_count: int, multi_run_steps: in
 def run_ensemble(runs: List[Dict], out_directory: str = "data", devices: Optional[List[int]] = None,
                  streams_per_device: int = 4, output_every_n_steps: int = 1) -> List[str]:
     """CUDAEnsemble.simulate (model.py:1801-1810, :2188): independent runs, round-robin over
-    devices and CUDA streams, one JSON file per run.  No communication between runs."""
+    devices and CUDA streams, one JSON file per run.  No communication between runs.
+    Under torch.distributed (one process per GPU) every rank takes the runs i with i mod world == rank on its
+    own device (dist.shard_runs) and rank 0 gets the list of all log files (dist.gather_logs)."""
     import torch
     from concurrent.futures import ThreadPoolExecutor
+    from .dist import shard_runs, gather_logs, rank_world
+    rank, world = rank_world()
+    if world > 1:
+        runs = shard_runs(runs, rank, world)
+        if devices is None:
+            devices = [torch.cuda.current_device()]
     if devices is None:
         devices = list(range(torch.cuda.device_count()))
     slots = [(d, s) for s in range(streams_per_device) for d in devices]
@@ -229,7 +237,7 @@ def run_ensemble(runs: List[Dict], out_directory: str = "data", devices: Optiona
     with ThreadPoolExecutor(max_workers=len(slots)) as pool:
         for p in pool.map(one, list(enumerate(runs))):
             paths.append(p)
-    return paths
+    return gather_logs(paths)
 
 
 def _parse_argv(argv: List[str]) -> Dict:

@@ -28,9 +28,8 @@ def _worker(rank, world, port, q):
         mine = pdist.shard_runs(runs, rank, world)
         # whole-job throughput: sum of units, max of time
         total, secs = pdist.reduce_throughput(agent_steps=1000.0 * (rank + 1), seconds=1.0 + rank)
-        counts, n = pdist.allreduce_counts([rank + 1] * 16, 100 * (rank + 1))
         paths = pdist.gather_logs([f"rank{rank}/{r['subdir']}" for r in mine])
-        q.put((rank, len(mine), total, secs, counts, n, len(paths), pdist.slab_rows(64, rank, world),
+        q.put((rank, len(mine), total, secs, pdist.rank_world(), len(paths), pdist.slab_rows(64, rank, world),
                pdist.ring_neighbours(rank, world)))
     finally:
         dist.destroy_process_group()
@@ -48,10 +47,10 @@ def test_two_rank_bookkeeping():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, n_mine, total, secs, counts, n, n_paths, slab, ring in res:
+    for rank, n_mine, total, secs, rw, n_paths, slab, ring in res:
         assert n_mine == 6                       # 12 runs over 2 ranks
         assert total == 3000.0 and secs == 2.0   # SUM of units, MAX of time
-        assert counts == [3] * 16 and n == 300
+        assert rw == (rank, 2)
         assert n_paths == 12
         assert slab == (rank * 32, 32)
         assert ring == ((rank - 1) % 2, (rank + 1) % 2)
@@ -63,6 +62,7 @@ def test_shard_and_slab_single_process():
     with pytest.raises(ValueError):
         pdist.slab_rows(100, 0, 3)
     assert pdist.reduce_throughput(5.0, 2.0) == (5.0, 2.0)
+    assert pdist.rank_world() == (0, 1)
 
 
 class _FakeSim:
