@@ -479,7 +479,8 @@ def run_ours(args, rank, world, local_rank):
                      "peak_source": peak_src, "alg_bytes_per_launch": ALG_BYTES[dom] * cells,
                      "launch_ms": kern[dom]["ms_per_step"],
                      # HBM is the roofline this path is held against; what limits the kernel TODAY is named here
-                     "limited_by": "instruction issue (ncu: issue slots ~70 % busy, DRAM ~15 %)"
+                     "limited_by": "instruction issue (ncu, profiles/: issue slots ~74 % busy, 47 registers -> 5 CTAs "
+                                   "per SM, DRAM ~25 % of its peak)"
                                    if (kern[dom]["frac_of_hbm_peak"] or 0) < 0.5 else "HBM bandwidth"},
         "kernels": kern,
         "also": also,
@@ -504,12 +505,24 @@ def run_ours(args, rank, world, local_rank):
         try:
             tr = json.load(open(traffic_file))
             line["roofline"]["traffic"] = tr.get("k_" + dom, {}).get(args.workload)
+            step_traffic = 0.0
             for k, ent in kern.items():  # stored ncu bytes per launch of every kernel, and their ratio to the
                 t_k = tr.get("k_" + k, {}).get(args.workload)  # algorithmic bytes where a per-cell figure exists
                 if t_k is not None:
+                    step_traffic += t_k
                     ent["traffic_bytes_per_launch_ncu_stored"] = t_k
+                    if ent["ms_per_step"] > 0:
+                        ent["traffic_gbs"] = t_k / (ent["ms_per_step"] * 1e-3) / 1e9
+                        ent["traffic_frac_of_hbm_peak"] = ent["traffic_gbs"] / peak
                     if "alg_bytes_per_cell" in ent:
                         ent["traffic_ratio"] = t_k / (ent["alg_bytes_per_cell"] * cells)
+            if step_traffic and args.workload == "config3" and not args.width and not args.height and world == 1:
+                # "bytes moved per cell-step over peak bandwidth": the DRAM bytes ncu saw for ALL kernels of one step
+                # (stored, same workload) over this run's time per step.  The dense sweeps' algorithmic bytes
+                # (step_alg_*) are the floor of this layout; the rest is the claim plane and the sparse commits.
+                line["step_traffic_bytes_per_cell_ncu_stored"] = step_traffic / cells
+                line["step_traffic_gbs"] = step_traffic / (ms / args.steps * 1e-3) / 1e9
+                line["step_traffic_frac_of_hbm_peak"] = line["step_traffic_gbs"] / peak
         except Exception:
             pass
     print(json.dumps(line), flush=True)
