@@ -144,6 +144,12 @@ class Params:
     # reference's own rule (model.py:1343, :1354) under the FLAMEGPU2 list semantics of SURVEY Appendix D-2
     # [FG2-ext]; tests/test_cull_variants.py compares the two statistically
     cull: str = "priority"
+    # ORACLE-ONLY switch (SURVEY B-8): count agents by the reference's agent_strategy_id VARIABLE instead of by
+    # their strategies.  god_multiply sets it for the children of pure and kin/other runs (model.py:1271, :1326) but
+    # not for per-trait runs (:1273-1286), whose children keep the default 0 and are all counted in bin 0 -- this is
+    # what a per-trait log of the reference shows, so a comparison against one needs it.  Reporting only: the
+    # dynamics do not depend on it.  The CUDA path derives the bin (it has no per-agent id state to carry).
+    legacy_counts: bool = False
 
     def __post_init__(self):
         w = self.width
@@ -200,6 +206,7 @@ class Oracle:
         self.roll = np.zeros(0, np.uint32)                  # die_roll
         self.roll_cell = np.zeros(0, np.int64)              # tie-break tag: cell at draw time
         self.coins = np.zeros(0, np.uint32)                 # RANDOM coins of the games I respond to
+        self.sid_bin = np.zeros(0, np.int64)                # count bin of agent_strategy_id (legacy_counts)
         self.bucket = np.zeros(0, np.int64)                 # my_bucket
         self.stats: Dict[str, int] = {}
         self.population_strat_count = np.zeros(16, np.int64)
@@ -212,7 +219,7 @@ class Oracle:
                              self.k0, self.k1)
 
     _ARRS = ("id", "x", "y", "energy", "status", "trait", "strat", "nb_list", "act", "roll",
-             "roll_cell", "bucket", "coins")
+             "roll_cell", "bucket", "coins", "sid_bin")
 
     def _compact(self, alive: np.ndarray, extra: Dict[str, np.ndarray] | None = None):
         """Remove dead agents from every per-agent array (FLAMEGPU2 death compaction)."""
@@ -303,6 +310,7 @@ class Oracle:
         self.roll = np.zeros(n, np.uint32)
         self.roll_cell = np.zeros(n, np.int64)
         self.coins = np.zeros(n, np.uint32)
+        self.sid_bin = self._derived_bin(strat, trait)                         # agent_strategy_id, :1501-1511
         self.bucket = self.x + self.y * W
         self.step_index = 0
         self.population_strat_count = self.strategy_counts()                   # :1517-1522
@@ -324,6 +332,7 @@ class Oracle:
         self.roll = np.zeros(n, np.uint32)
         self.roll_cell = np.zeros(n, np.int64)
         self.coins = np.zeros(n, np.uint32)
+        self.sid_bin = self._derived_bin(self.strat, self.trait)
         self.bucket = self.x + self.y * W
         self.population_strat_count = self.strategy_counts()
 
@@ -741,6 +750,11 @@ class Oracle:
         self.roll = np.concatenate([self.roll, np.zeros(nb, np.uint32)])
         self.roll_cell = np.concatenate([self.roll_cell, np.zeros(nb, np.int64)])
         self.coins = np.concatenate([self.coins, np.zeros(nb, np.uint32)])
+        # agent_strategy_id of the child: set in pure (:1271) and kin/other (:1326) mode, NOT in per-trait mode
+        # (:1273-1286), where it keeps the default 0 = bin 0 (B-8)
+        child_bin = (np.zeros(nb, np.int64) if (p.strategy_per_trait == 1 and p.strategy_pure != 1)
+                     else self._derived_bin(cs, my_trait))
+        self.sid_bin = np.concatenate([self.sid_bin, child_bin])
         self.bucket = np.concatenate([self.bucket, tgt])                        # :1252
         for k, dflt in (("request_bucket", 0), ("last_reproduction_attempt", NDIR + 1),
                         ("reproduce_sequence", 0), ("agents_spawned", 0)):
@@ -801,14 +815,21 @@ class Oracle:
         self._compact(alive)
 
     # ------------------------------------------------------------------ step_fn
+    @staticmethod
+    def _derived_bin(strat, trait) -> np.ndarray:
+        """4*my + other of the strategies an agent holds (:1501-1511)."""
+        rows = np.arange(trait.shape[0])
+        my = strat[rows, trait].astype(np.int64)
+        other = strat[rows, np.where(trait == 0, 1, 0)].astype(np.int64)       # :1501-1508
+        return 4 * my + other
+
     def strategy_counts(self) -> np.ndarray:
-        """step_fn, model.py:1405-1419: bin k = 4*my + other, derived from strategies+trait (B-8)."""
+        """step_fn, model.py:1405-1419: bin k = 4*my + other, derived from strategies+trait (B-8) -- or, with
+        legacy_counts, the bin of the agent_strategy_id variable as the reference maintains it."""
         if self.n == 0:
             return np.zeros(16, np.int64)
-        rows = np.arange(self.n)
-        my = self.strat[rows, self.trait].astype(np.int64)
-        other = self.strat[rows, np.where(self.trait == 0, 1, 0)].astype(np.int64)   # :1501-1508
-        return np.bincount(4 * my + other, minlength=16).astype(np.int64)
+        bins = self.sid_bin if self.p.legacy_counts else self._derived_bin(self.strat, self.trait)
+        return np.bincount(bins, minlength=16).astype(np.int64)
 
     # ------------------------------------------------------------------ one step
     def step(self) -> Dict[str, int]:

@@ -66,3 +66,25 @@ def test_priority_cull_and_list_index_cull_agree_statistically():
     print(f"cull variants: peak list-index population {peak_b} (cap {cap}); max |mean difference| = {z.max():.2f} sd; "
           f"final population {pa[STEPS]:.0f} vs {pb[STEPS]:.0f}")
     assert z.max() < 1.0
+
+
+def test_legacy_counts_switch_reproduces_the_reference_reporting_bug():
+    """SURVEY B-8: with legacy_counts the oracle counts by the agent_strategy_id VARIABLE -- in per-trait mode the
+    children keep the default id (bin 0, model.py:1273-1286), so bin 0 swells while the dynamics (planes, population)
+    are untouched; in kin/other and pure mode the variable equals the derived bin."""
+    from oracle.pd_oracle import Oracle, Params
+    kw = dict(width=64, seed=5, mutation_rate=0.05)
+    for mode in (dict(strategy_per_trait=1), dict(), dict(strategy_pure=1)):
+        a, b = Oracle(Params(**kw, **mode)), Oracle(Params(**kw, **mode, legacy_counts=True))
+        a.init_population(); b.init_population()
+        assert np.array_equal(a.population_strat_count, b.population_strat_count)   # founders carry real ids
+        for _ in range(40):
+            a.step(); b.step()
+        pa, pb = a.planes(), b.planes()
+        assert all(np.array_equal(pa[k], pb[k]) for k in pa) and a.n == b.n          # reporting only
+        ca, cb = a.population_strat_count, b.population_strat_count
+        assert ca.sum() == cb.sum() == a.n
+        if mode.get("strategy_per_trait"):
+            assert cb[0] > ca[0] and (cb[1:] <= ca[1:]).all()    # every child sits in bin 0
+        else:
+            assert np.array_equal(ca, cb)
