@@ -304,6 +304,15 @@ def run_ours(args, rank, world, local_rank):
     counts, n_after = sim.counts()
     agent_steps = as1 - as0
 
+    # ---- row slabs: where a step's time goes on this rank -- CUDA events between the phases of DecomposedWorld.step,
+    # a few extra (untimed) steps in the saturated state; max over ranks per phase
+    slab_phases = None
+    if slabs:
+        slab_phases = _slab_phase_times(sim, 10)
+        tph = torch.tensor(list(slab_phases.values()), dtype=torch.float64, device="cuda")
+        dist.all_reduce(tph, op=dist.ReduceOp.MAX)
+        slab_phases = {k: float(v) for k, v in zip(slab_phases, tph.tolist())}
+
     # ---- e2e: the host-buffer C-ABI call, state round trip through pinned host memory each step
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     rows_local = one.energy.shape[0]
@@ -485,6 +494,7 @@ def run_ours(args, rank, world, local_rank):
         "kernels": kern,
         "also": also,
         "decomp_parity": parity,
+        "slab_phases_ms": slab_phases,   # (row slabs) ms per phase of a step, max over ranks; their sum is the step
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_agents / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
@@ -492,7 +502,11 @@ def run_ours(args, rank, world, local_rank):
                 # the legs of one round trip (max over ranks, CUDA events): the PCIe copies are the floor
                 "h2d_ms": legs[0], "step_ms": legs[1], "d2h_ms": legs[2],
                 "h2d_gbs_per_gpu": h2d / (legs[0] * 1e-3) / 1e9 if legs[0] > 0 else None,
-                "d2h_gbs_per_gpu": d2h / (legs[2] * 1e-3) / 1e9 if legs[2] > 0 else None},
+                "d2h_gbs_per_gpu": d2h / (legs[2] * 1e-3) / 1e9 if legs[2] > 0 else None,
+                "note": ("the state crosses PCIe twice per step: the two copies are > 90 % of the time at N = 1; with "
+                         "N ranks copying at once the per-GPU rates (h2d_gbs_per_gpu / d2h_gbs_per_gpu) drop -- shared "
+                         "host memory / PCIe uplinks of the box, a platform limit -- and step_ms then includes waiting "
+                         "for the slowest rank's upload at the step's first collective")},
         # per step: 9 kernels (whole world; replayed as one CUDA graph on small worlds), or 12 + 2 per
         # reproduction retry round that actually ran (row slab, this rank)
         "gpu_launches": (12 * args.steps + 2 * retry_rounds) if slabs else 9 * args.steps,
@@ -530,6 +544,53 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _slab_phase_times(dw, n_steps):
+    """ms per phase of one slab step (this rank), mean over n_steps steps with the gate closed: halo exchange, the
+    local PRE part, the 8 KB all-reduce, the speculative CAND / all-gather / APPLY.  Events add no synchronisation."""
+    import torch
+    from pdabm_b200._lib import PD_PART_PRE, PD_PART_CAND, PD_PART_APPLY, PD_PART_DONE
+    names = ["halo_exchange", "PRE", "allreduce_gate_hist", "gate_request", "CAND", "allgather_candidates", "APPLY"]
+    acc = dict.fromkeys(names, 0.0)
+    comm, slabs = dw.comm, dw.slabs
+    done = 0
+    dw.step(2, want_counts=False)   # the ranks fall into step with each other again (they were read back one by one)
+    for _ in range(n_steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+        ev[0].record()
+        comm.exchange(slabs); ev[1].record()
+        for s in slabs:
+            s.part(PD_PART_PRE, 0, False)
+        ev[2].record()
+        comm.allreduce([s.wire for s in slabs]); ev[3].record()
+        gev = dw._gate_request(); ev[4].record()
+        for s in slabs:
+            s.part(PD_PART_CAND, 1, False)
+        ev[5].record()
+        comm.allgather([s.cand_all for s in slabs], [s.cand_out for s in slabs]); ev[6].record()
+        for s in slabs:
+            s.part(PD_PART_APPLY, 1, False)
+        ev[7].record()
+        if dw._gate_open(gev):       # not saturated: finish this step the regular way and stop measuring
+            for rnd in range(1, dw.retry_rounds + 1):
+                if rnd > 1 and not dw._gate_open():
+                    break
+                for s in slabs:
+                    s.part(1, rnd, False)   # PD_PART_RETRY
+                comm.allreduce([s.glb for s in slabs])
+            for s in slabs:
+                s.part(2, 0, False)         # PD_PART_HIST
+            comm.allreduce([s.ghist for s in slabs])
+            dw._finish(0, False)
+            break
+        for s in slabs:
+            s.part(PD_PART_DONE)
+        torch.cuda.synchronize()
+        for k, n in enumerate(names):
+            acc[n] += ev[k].elapsed_time(ev[k + 1])
+        done += 1
+    return {n: (v / done if done else None) for n, v in acc.items()}
 
 
 def _small_config_line(name, steps, from_init=True):

@@ -120,3 +120,59 @@ def test_full_size_2p28_slabs_equal_whole_world():
     finally:
         ref.close()
         dec.close()
+
+
+def test_halo_strips_equal_plane_copies():
+    """pd_halo_pack / pd_halo_unpack (the peer-memory transport's two kernels) fill the ghost rows exactly like
+    LocalComm's plane-to-plane copies: pack every slab's boundary rows into strips, unpack the neighbours' strips."""
+    import ctypes as C
+    import torch
+    from pdabm_b200 import SimConfig, DecomposedWorld, LocalComm
+    from pdabm_b200.dist import ring_neighbours
+    cfg = dict(width=256, seed=41, strategy_per_trait=1)
+    a = DecomposedWorld(SimConfig(**cfg), LocalComm(4))
+    b = DecomposedWorld(SimConfig(**cfg), LocalComm(4))
+    try:
+        a.init_population()
+        b.init_population()
+        a.step(3)
+        b.step(3)
+        a.comm.exchange(a.slabs)          # reference: tensor copies
+        strips = []
+        for s in b.slabs:                 # pack ...
+            nb = C.c_uint64()
+            s.sim._check(s.sim.lib.pd_halo_bytes(s.sim._h, C.byref(nb)))
+            assert nb.value == 64 * 256 * 6
+            box = torch.zeros(2 * nb.value, dtype=torch.uint8, device=s.sim.device)
+            s.sim._check(s.sim.lib.pd_halo_pack(s.sim._h, box.data_ptr(), box.data_ptr() + nb.value, s.sim.stream_ptr))
+            strips.append((box, nb.value))
+        for s in b.slabs:                 # ... and unpack the neighbours' strips
+            up, down = ring_neighbours(s.rank, 4)
+            n = strips[0][1]
+            s.sim._check(s.sim.lib.pd_halo_unpack(s.sim._h, strips[up][0].data_ptr() + n, strips[down][0].data_ptr(),
+                                                  s.sim.stream_ptr))
+        torch.cuda.synchronize()
+        for sa, sb in zip(a.slabs, b.slabs):
+            for name in ("energy", "strat", "tf"):
+                assert torch.equal(getattr(sa.sim, name), getattr(sb.sim, name)), (sa.rank, name)
+        a.step(5)                         # and the worlds stay in step afterwards
+        b.step(5)
+        pa, pb = a.planes(), b.planes()
+        assert all(np.array_equal(pa[k], pb[k]) for k in pa)
+    finally:
+        a.close()
+        b.close()
+
+
+def test_speculative_finish_needs_confirmation():
+    """PD_PART_CAND / PD_PART_APPLY with arg = 1 leave the host-side step counter alone until PD_PART_DONE; a
+    non-slab handle rejects the slab API."""
+    from pdabm_b200 import Simulation, SimConfig, PdabmError
+    from pdabm_b200._lib import PD_PART_PRE
+    sim = Simulation(SimConfig(width=64, seed=3))
+    try:
+        sim.init_population()
+        with pytest.raises(PdabmError):
+            sim._check(sim.lib.pd_step_part(sim._h, PD_PART_PRE, 0, sim.stream_ptr, 0))
+    finally:
+        sim.close()
