@@ -770,7 +770,7 @@ __device__ __forceinline__ void fin_bookkeeping(const Params& p) {
     s[2] = __ldcg(&ctr->st_play_deaths); s[3] = __ldcg(&ctr->st_movers);
     s[4] = __ldcg(&ctr->st_moved); s[5] = __ldcg(&ctr->st_travel_deaths);
     s[6] = b; s[7] = culled; s[8] = ld;
-    s[9] = rn; s[10] = __ldcg(&ctr->mv_n); s[11] = __ldcg(&ctr->rp_n);
+    s[9] = rn; s[10] = __ldcg(&ctr->rt_n[0]); s[11] = __ldcg(&ctr->rt_n[1]);  // losers of round 1 (travel, reproduction)
     ctr->step_no += 1u;  // the step is complete
     if (p.want_counts && p.step_log) {  // one row per counted step, read back whenever the host wants
         const unsigned int row = ctr->log_n;
