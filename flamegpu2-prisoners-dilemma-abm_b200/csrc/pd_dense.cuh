@@ -117,24 +117,6 @@ constexpr uint32_t R_OCC = 0x80000000u;
 constexpr uint32_t R_DFLAG = 0x800u;
 constexpr uint32_t R_LOW = 0x7FFFu;  // everything below the roll
 
-// append v[k] for every byte k of `occ4` that has bit 7 set; all 32 lanes call.  Four ballots give every lane its
-// slots without a scan (the order inside the warp's chunk is byte-major, which nobody cares about).
-__device__ __forceinline__ void wappend4(unsigned int* cnt, uint32_t* list, uint32_t occ4, const uint32_t (&v)[4]) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t m0 = __ballot_sync(FULL, occ4 & 0x80u), m1 = __ballot_sync(FULL, occ4 & 0x8000u);
-    const uint32_t m2 = __ballot_sync(FULL, occ4 & 0x800000u), m3 = __ballot_sync(FULL, occ4 & 0x80000000u);
-    const int n0 = __popc(m0), n1 = __popc(m1), n2 = __popc(m2), total = n0 + n1 + n2 + __popc(m3);
-    if (total == 0) return;
-    unsigned int base = 0;
-    if (lane == 0) base = satom_add(cnt, (unsigned int)total);
-    base = __shfl_sync(FULL, base, 0);
-    if (occ4 & 0x80u) list[base + __popc(m0 & lt)] = v[0];
-    if (occ4 & 0x8000u) list[base + n0 + __popc(m1 & lt)] = v[1];
-    if (occ4 & 0x800000u) list[base + n0 + n1 + __popc(m2 & lt)] = v[2];
-    if (occ4 & 0x80000000u) list[base + n0 + n1 + n2 + __popc(m3 & lt)] = v[3];
-}
-
 // Thread-level append of up to four values (byte k of `occ4` has bit 7 set = v[k] goes on the list): ONE shared
 // atomic per thread with its count, then plain stores.  No ballots, and with a per-lane count ptxas leaves the
 // atomic alone (for a uniform increment it wraps it in a vote / elect / shuffle sequence of ~15 issue slots).
@@ -145,23 +127,6 @@ __device__ __forceinline__ void tappend4(unsigned int* cnt, uint32_t* list, uint
     if (occ4 & 0x8000u) list[slot++] = v[1];
     if (occ4 & 0x800000u) list[slot++] = v[2];
     if (occ4 & 0x80000000u) list[slot] = v[3];
-}
-
-// the same for a list of tile-local cell indices: appends idx0 + k for every byte k of `occ4` that has bit 7 set
-__device__ __forceinline__ void wappend4_idx(unsigned int* cnt, uint16_t* list, uint32_t occ4, uint32_t idx0) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t m0 = __ballot_sync(FULL, occ4 & 0x80u), m1 = __ballot_sync(FULL, occ4 & 0x8000u);
-    const uint32_t m2 = __ballot_sync(FULL, occ4 & 0x800000u), m3 = __ballot_sync(FULL, occ4 & 0x80000000u);
-    const int n0 = __popc(m0), n1 = __popc(m1), n2 = __popc(m2), total = n0 + n1 + n2 + __popc(m3);
-    if (total == 0) return;
-    unsigned int base = 0;
-    if (lane == 0) base = satom_add(cnt, (unsigned int)total);
-    base = __shfl_sync(FULL, base, 0);
-    if (occ4 & 0x80u) list[base + __popc(m0 & lt)] = (uint16_t)idx0;
-    if (occ4 & 0x8000u) list[base + n0 + __popc(m1 & lt)] = (uint16_t)(idx0 + 1u);
-    if (occ4 & 0x800000u) list[base + n0 + n1 + __popc(m2 & lt)] = (uint16_t)(idx0 + 2u);
-    if (occ4 & 0x80000000u) list[base + n0 + n1 + n2 + __popc(m3 & lt)] = (uint16_t)(idx0 + 3u);
 }
 
 // entry i of the payoff table: bits 0-1 the challenger's strategy against my trait, 2-3 my strategy against
@@ -281,7 +246,7 @@ __global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_c
     for (int it = 0; it < NIT; ++it) {
         const int j = tid + it * NT;
         if (it * NT >= NITEM) break;
-        if (it * NT < NI || j < NITEM) {  // (the interior iterations are warp-uniform: wappend4 needs whole warps)
+        if (j < NITEM) {
             const uint32_t occ4 = tf4[it] & 0x80808080u;
             uint4 r4 = make_uint4(0, 0, 0, 0);
             uint32_t v[4] = {0, 0, 0, 0};
@@ -299,7 +264,7 @@ __global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_c
                 }
                 r4 = make_uint4(rr[0], rr[1], rr[2], rr[3]);
             }
-            if (j < NITEM) *reinterpret_cast<uint4*>(s_R + sw[it]) = r4;
+            *reinterpret_cast<uint4*>(s_R + sw[it]) = r4;
             if (j < NI) tappend4(&s_n[0], s_cells, occ4, v);
         }
     }

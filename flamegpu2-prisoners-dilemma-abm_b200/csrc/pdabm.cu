@@ -384,10 +384,6 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     CK(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(PD_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
     CK(cudaSetDevice(cfg->device));
-    if (const char* g = getenv("PDABM_L2_FETCH")) {  // experiment: DRAM fetch granularity of the L2 (32 / 64 / 128 bytes)
-        const int v = atoi(g);
-        if (v == 32 || v == 64 || v == 128) CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v));
-    }
     pd_sim* s = new pd_sim();  // value-initialised: every pointer below starts as nullptr
     struct Guard {             // a failure part-way releases what was allocated so far
         pd_sim* s;
