@@ -82,6 +82,10 @@ __device__ __forceinline__ unsigned int satom_add(unsigned int* counter, unsigne
     return old;
 }
 
+__device__ __forceinline__ void satom_or(unsigned int* word, unsigned int v) {
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"((unsigned int)__cvta_generic_to_shared(word)), "r"(v) : "memory");
+}
+
 // warp-aggregated append to a shared-memory counter; all 32 lanes must call
 __device__ __forceinline__ uint32_t wappend(unsigned int* counter, bool pred) {
     const unsigned int m = __ballot_sync(FULL, pred);
@@ -196,11 +200,16 @@ __global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_c
     __shared__ uint32_t s_cells[NC];
     __shared__ uint16_t s_mover[NC];
     __shared__ float s_lut[256];
-    __shared__ unsigned int s_n[4];  // 0 agents, 1 base of this tile's travel-list entries, 2 movers, 3 claimants
+    // travel claims on cells ALL of whose neighbours lie in this tile (everything but the tile's outermost cells):
+    // bit j of a cell's byte = "the agent on its neighbour j claims it".  Nobody outside the tile can claim such a
+    // cell, so an uncontested claim is settled right here, in shared memory (below)
+    __shared__ __align__(16) uint8_t s_cmask[NC];
+    __shared__ unsigned int s_n[8];  // 0 agents, 1 base of this tile's travel-list entries, 2 movers, 3 claimants that go
+                                     // through the claim plane, 4 local claimants, 5 local claimants with rivals
     const int tid = threadIdx.x;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const bool noisy = p.noise_thr != 0ull;
-    if (tid < 4) s_n[tid] = 0;
+    if (tid < 8) s_n[tid] = 0;
     // the energies go straight to shared memory (cp.async); they are first needed after the barrier below
     for (int i = tid; i < NC / 4; i += NT) {
         const int ly = (i * 4) >> LOG_TW, lx = (i * 4) & (TW - 1);
@@ -210,7 +219,10 @@ __global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_c
     asm volatile("cp.async.commit_group;");
     static_assert(NT == 256, "one table entry per thread");
     s_lut[tid] = __ldg(p.lut + tid);  // lut_entry() of every index, filled by pd_create
-    for (int i = tid; i < NC / 16; i += NT) reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < NC / 16; i += NT) {
+        reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(s_cmask)[i] = make_uint4(0, 0, 0, 0);
+    }
     // ---- the word of every cell in reach: per-step die roll (:364) recomputed, not communicated.  One group of 4
     // cells per thread and iteration: flag word + strategy word from global memory, one Philox call, 4 words out.
     constexpr int NIT = (NITEM + NT - 1) / NT;
@@ -341,14 +353,45 @@ __global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_c
         const Words w = rng(p, gcell_of(p, x0 + lx, y0 + ly), S_TRAVEL);
         int l = (int)(w.y >> 29), seq = 0;  // :810
         const int dir = probe(occ_mask, l, seq);
-        if (dir >= 0) {
+        if (dir >= 0) {  // (the agent list is spent: s_cells takes the claimants -- plane-bound from the front, local from the back)
+            const int tx = lx + DX(dir), ty = ly + DY(dir);
+            if (tx >= 1 && tx <= TW - 2 && ty >= 1 && ty <= TH - 2) {
+                const int tc = ty * TW + tx;
+                satom_or(reinterpret_cast<unsigned int*>(s_cmask) + (tc >> 2), 1u << (8 * (tc & 3) + (7 - dir)));
+                s_cells[NC - 1 - satom_add(&s_n[4], 1u)] = (uint32_t)cl | ((uint32_t)dir << 16);
+            } else {
+                prefetch_claim(p.claim + nb_local(p, x0 + lx, y0 + ly, dir));
+                s_cells[satom_add(&s_n[3], 1u)] = (uint32_t)cl | ((uint32_t)dir << 16);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- local claims (move_response, :881-960, for the targets only this tile can reach): a claimant that is alone
+    // on its target's byte has won and relocates inside the tile before the tile is stored -- no claim word, no list
+    // entry, no scattered writes but the strategy byte.  Rivals (they all see the same byte) go through the claim
+    // plane like the claims on the tile's rim: k_move_commit decides by priority.
+    const unsigned int n_local = s_n[4];
+    unsigned int n_moved = 0;
+    for (unsigned int k = tid; k < n_local; k += NT) {
+        const uint32_t ent = s_cells[NC - 1 - k];
+        const int cl = (int)(ent & 0xFFFFu), dir = (int)(ent >> 16);
+        const int ly = cl >> LOG_TW, lx = cl & (TW - 1);
+        const int tx = lx + DX(dir), ty = ly + DY(dir), tc = ty * TW + tx;
+        if ((uint32_t)s_cmask[tc] == (1u << (7 - dir))) {  // :946-956
+            s_out[tc] = s_out[cl];
+            s_e[tc] = s_e[cl];
+            s_out[cl] = (uint8_t)TF_GHOST;  // keeps blocking movers this step (quirk B-13)
+            s_e[cl] = 0.0f;
+            p.strat[((size_t)(y0 + ty) << p.log2W) + x0 + tx] = (uint8_t)(s_R[(ly + 1) * SWR + 4 + lx] >> 3);
+            ++n_moved;
+        } else {
             prefetch_claim(p.claim + nb_local(p, x0 + lx, y0 + ly, dir));
-            s_cells[satom_add(&s_n[3], 1u)] = (uint32_t)cl | ((uint32_t)dir << 16);  // (the agent list is spent)
+            s_mover[satom_add(&s_n[5], 1u)] = (uint16_t)((uint32_t)cl | ((uint32_t)dir << 11));  // (the mover list is spent)
         }
     }
     __syncthreads();
     // ---- coalesced stores
-    const unsigned int n_claim = s_n[3];
+    const unsigned int n_plane = s_n[3], n_claim = n_plane + s_n[5];
     if (tid == 0 && n_claim) s_n[1] = atomicAdd(&p.ctr->mv_n, n_claim);
     for (int i = tid; i < NC / 16; i += NT) {
         const int ly = (i * 16) >> LOG_TW, lx = (i * 16) & (TW - 1);
@@ -366,9 +409,11 @@ __global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_c
             if (tid == 0) atomicExch(&p.ctr->overflow, 1u);
         } else {
             for (unsigned int k = tid; k < n_claim; k += NT) {
-                const uint32_t ent = s_cells[k], cl = ent & 0xFFFFu;
+                uint32_t cl;
+                int dir;
+                if (k < n_plane) { const uint32_t ent = s_cells[k]; cl = ent & 0xFFFFu; dir = (int)(ent >> 16); }
+                else { const uint32_t ent = s_mover[k - n_plane]; cl = ent & 0x7FFu; dir = (int)(ent >> 11); }
                 const uint32_t x = x0 + (cl & (TW - 1)), y = y0 + (cl >> LOG_TW);
-                const int dir = (int)(ent >> 16);
                 // :861-868: the request goes to the target cell.  Posted here, after the CTA's last barrier (a barrier
                 // waits for the CTA's outstanding reductions), with the priority drawn again rather than kept
                 post_claim(p.claim + nb_local(p, x, y, dir), claim_word(step, CLAIM_TRAVEL, rng(p, gcell_of(p, x, y), S_TRAVEL).x, dir));
@@ -382,6 +427,7 @@ __global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_c
     if (p.stats && row_owned(p, y0)) {  // tiles are entirely owned or entirely ghost (16-row granularity)
         if (n_play_deaths) atomicAdd(&p.ctr->st_play_deaths, (unsigned long long)n_play_deaths);
         if (n_movers) atomicAdd(&p.ctr->st_movers, (unsigned long long)n_movers);
+        if (n_moved) atomicAdd(&p.ctr->st_moved, (unsigned long long)n_moved);
         if (n_travel_deaths) atomicAdd(&p.ctr->st_travel_deaths, (unsigned long long)n_travel_deaths);
     }
 }
