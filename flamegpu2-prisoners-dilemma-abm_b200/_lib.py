@@ -51,6 +51,7 @@ class pd_config(C.Structure):
         ("world_height", C.c_uint32),
         ("use_graphs", C.c_int32),
         ("debug_select_cap", C.c_uint32),
+        ("debug_tie_shift", C.c_uint32),
     ]
 
 

@@ -35,7 +35,7 @@ constexpr int NT = 256;  // threads per CTA of the dense sweeps
 #define PD_PLAY_CTAS 5   // resident CTAs per SM the play sweep is compiled for (register budget)
 #endif
 #ifndef PD_CLAIM_CTAS
-#define PD_CLAIM_CTAS 6   // (measured: 6 CTAs at 40 registers 0.87 ms, 8 at 32 registers 0.89 ms)
+#define PD_CLAIM_CTAS 6   // (6 CTAs at 40 registers 0.87 ms, 8 at 32 registers 0.89 ms)
 #endif
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
@@ -462,21 +462,53 @@ __device__ __forceinline__ Outcome outcome_of(const Params& p, float e1, bool pa
     return o;
 }
 
+// A parent that has won its claim (god_multiply, :1211-1213) re-derives its layer-7 outcome: k_claim_punish
+// charged it as a non-parent.  e1 = its energy when it entered layer 6 (E1 is read-only), `cell` its cell, owned
+// rows only (nobody writes a parent's strat / tfB entries during the reproduction rounds).  Almost always only the energy changes; deaths, counts and the at-risk list are corrected if not.
+__device__ __forceinline__ void parent_outcome(const Params& p, uint32_t cell, float e1, uint32_t trait) {
+    const Outcome a = outcome_of(p, e1, false), b = outcome_of(p, e1, true);
+    p.E0[cell] = b.e;
+    if (a.alive != b.alive) {
+        p.tfA[cell] = (uint8_t)(b.alive ? (TF_OCC | trait) : 0u);
+        atomicAdd(&p.ctr->living_deaths, b.alive ? ~0ull : 1ull);  // (+1, or -1 if a negative cost revives it)
+        if (p.want_counts) atomicAdd(&p.ctr->bins[count_bin(p.strat[cell], trait)], b.alive ? 1ull : ~0ull);
+    }
+    if (b.risk && !a.risk) {  // (an entry that is no longer at risk is harmless: k_risk_resolve replays it exactly)
+        const unsigned int slot = atomicAdd(&p.ctr->risk_next_n, 1u);
+        if (slot < p.list_cap) p.risk_next[slot] = cell;
+        else atomicExch(&p.ctr->overflow, 1u);
+    }
+}
+
 template <int TW, int TH>
 __global__ void __launch_bounds__(NT, PD_CLAIM_CTAS) k_claim_punish(const __grid_constant__ Params p) {
     constexpr int SW = TW + 32, SH = TH + 2, NC = TW * TH;
     __shared__ __align__(16) uint8_t s_tf[SH * SW];
-    __shared__ uint16_t s_par[NC];
-    __shared__ uint32_t s_claim[NC];   // claimants: tile-local cell | direction << 16
+    __shared__ uint16_t s_par[NC];     // the agents that may reproduce
+    __shared__ uint16_t s_claim[NC];   // claimants: tile-local cell | direction << 11 -- those that go through the claim
+                                       // plane from the front, the local ones from the back
     __shared__ uint32_t s_prio[NC];
     __shared__ uint16_t s_risk[NC];
+    // Claims on cells ALL of whose neighbours lie in this tile (everything but the tile's outermost cells) cannot
+    // have rivals outside the tile: they are resolved right here, by an atomic max per cell in shared memory, and
+    // never touch the claim plane.  The key is the claimant's priority with its position j in the low 3 bits --
+    // unique among the rivals of a cell, and ordered like claim_word's (priority, j) unless two rivals agree in the
+    // top 29 bits of their priorities.  That case is noticed when it could matter (the atomic returns a value with
+    // my top bits: see below) and sends ALL local claimants of the tile through the claim plane instead, which
+    // compares whole words.
+    __shared__ __align__(16) unsigned int s_max[NC];
     __shared__ unsigned int s_bins[16];
-    __shared__ unsigned int s_n[8];  // 0 parents, 1 claimants, 2 base of the claim entries, 3 agents, 4 at-risk, 5 their base, 6 deaths
+    // 0 parents, 1 claimants for the claim plane, 2 base of their list entries, 3 agents, 4 at-risk, 5 their base,
+    // 6 deaths, 7 local claimants, 8 base of their list entries, 12 set if two local rivals' priorities agree in
+    // their top bits
+    __shared__ unsigned int s_n[13];
+    static_assert(NC <= 2048, "a tile-local cell index takes 11 bits");
     const int tid = threadIdx.x;
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const bool owned = row_owned(p, y0);  // tiles are entirely owned or entirely ghost (16-row granularity)
-    if (tid < 8) s_n[tid] = 0;
+    if (tid < 13) s_n[tid] = 0;
     if (tid < 16) s_bins[tid] = 0;
+    for (int i = tid; i < NC / 4; i += NT) reinterpret_cast<uint4*>(s_max)[i] = make_uint4(0, 0, 0, 0);
     // the energies are requested before the flag tile arrives, so that the two latencies overlap (empty cells
     // hold 0 in E1: loading them is only wasted bandwidth, and only in sparse worlds)
     constexpr int NIT = (NC / 4 + NT - 1) / NT;
@@ -577,35 +609,79 @@ __global__ void __launch_bounds__(NT, PD_CLAIM_CTAS) k_claim_punish(const __grid
         int l = (int)(w.y >> 29), seq = 0;  // :1079
         const int dir = probe(occ_mask, l, seq);
         if (dir >= 0) {
-            prefetch_claim(p.claim + nb_local(p, x0 + lx, y0 + ly, dir));
-            const unsigned int slot = satom_add(&s_n[1], 1u);
-            s_claim[slot] = (uint32_t)cl | ((uint32_t)dir << 16);
+            const int tx = lx + dxr(dir), ty = ly + dyr(dir);
+            unsigned int slot;
+            if (tx >= 1 && tx <= TW - 2 && ty >= 1 && ty <= TH - 2) {
+                // Whoever ends up with the maximum of a cell, a rival with the same top bits either posts after it (and
+                // sees it) or before it (then the later one sees that rival or something in between, which has the same
+                // top bits too).  An empty entry (0) counts as a value: a false alarm only costs the detour.
+                const uint32_t key = (w.x & ~7u) | (uint32_t)(7 - dir);
+                const uint32_t old = atomicMax(&s_max[ty * TW + tx], key);
+                if (((old ^ key) >> p.tie_shift) == 0u) s_n[12] = 1u;
+                slot = NC - 1 - satom_add(&s_n[7], 1u);
+            } else {
+                prefetch_claim(p.claim + nb_local(p, x0 + lx, y0 + ly, dir));
+                slot = satom_add(&s_n[1], 1u);
+            }
+            s_claim[slot] = (uint16_t)((uint32_t)cl | ((uint32_t)dir << 11));
             s_prio[slot] = w.x;
         }
     }
     __syncthreads();
-    const unsigned int n_claim = s_n[1], n_risk = s_n[4];
+    // (on the detour the local claimants join the others: entries n_plane.. of the list below)
+    const bool detour = s_n[12] != 0u;
+    const unsigned int n_plane = s_n[1], n_local = detour ? 0u : s_n[7], n_claim = n_plane + (detour ? s_n[7] : 0u);
+    const unsigned int n_risk = s_n[4];
     if (tid == 0) {
         if (n_claim) s_n[2] = atomicAdd(&p.ctr->rp_n, n_claim);
+        if (n_local) s_n[8] = atomicAdd(&p.ctr->lc_n, n_local);
         if (n_risk) s_n[5] = atomicAdd(&p.ctr->risk_next_n, n_risk);
         if (s_n[3] && owned) atomicAdd(&p.ctr->n_old, (unsigned long long)s_n[3]);
         if (s_n[6]) atomicAdd(&p.ctr->living_deaths, (unsigned long long)s_n[6]);
     }
     if (p.want_counts && tid < 16 && s_bins[tid]) atomicAdd(&p.ctr->bins[tid], (unsigned long long)s_bins[tid]);
-    if (n_claim == 0 && n_risk == 0) return;  // uniform across the CTA
+    if (n_claim == 0 && n_local == 0 && n_risk == 0) return;  // uniform across the CTA
     __syncthreads();
+    // ---- local claims (god_multiply, :1144-1335, for the targets only this tile can reach): the winner pays right
+    // away (parent_outcome: its E0 / tfA entries were written by this CTA, two barriers ago).  Winners and losers are
+    // listed at the BACK of the claim list (entry list_cap - 1 - i) with the verdict in the entry; k_repro_commit
+    // turns them into newborns / retry entries without a random access.
+    if (n_local) {
+        const unsigned int base = s_n[8];
+        if (base + n_local > p.list_cap) {
+            if (tid == 0) atomicExch(&p.ctr->overflow, 1u);
+        } else {
+            for (unsigned int k = tid; k < n_local; k += NT) {
+                const unsigned int slot = NC - 1 - k;
+                const uint32_t ent = s_claim[slot], cl = ent & 0x7FFu;
+                const int dir = (int)(ent >> 11);
+                const uint32_t lx = cl % TW, ly = cl / TW;
+                const uint32_t cell = ((y0 + ly) << p.log2W) | (x0 + lx);
+                const bool won = s_max[(int)cl + dyr(dir) * TW + dxr(dir)] == ((s_prio[slot] & ~7u) | (uint32_t)(7 - dir));
+                if (won) {  // REPRODUCTION_COMPLETE (:1211-1213, :1331)
+                    const uint32_t trait = (uint32_t)s_tf[(ly + 1) * SW + lx + 16] & TF_TRAIT;
+                    if (owned) parent_outcome(p, cell, p.E1[cell], trait);
+                    else  // a child born into a ghost row belongs to the neighbour slab: here it only blocks its cell
+                        p.tfB[(long long)cell + dyr(dir) * (long long)p.W + dxr(dir)] = (uint8_t)(TF_OCC | TF_NEWBORN | trait);
+                }
+                p.cl_cell[p.list_cap - 1u - (base + k)] = cell;
+                p.cl_aux[p.list_cap - 1u - (base + k)] = (uint16_t)((uint32_t)dir | (won ? 8u : 0u));
+            }
+        }
+    }
     if (n_claim) {
         const unsigned int base = s_n[2];
         if (base + n_claim > p.list_cap) {
             if (tid == 0) atomicExch(&p.ctr->overflow, 1u);
         } else {
             for (unsigned int k = tid; k < n_claim; k += NT) {
-                const uint32_t ent = s_claim[k], cl = ent & 0xFFFFu;
+                const unsigned int slot = k < n_plane ? k : NC - 1 - (k - n_plane);
+                const uint32_t ent = s_claim[slot], cl = ent & 0x7FFu;
                 const uint32_t x = x0 + cl % TW, y = y0 + cl / TW;
-                const int dir = (int)(ent >> 16);
+                const int dir = (int)(ent >> 11);
                 // :1123-1130: the request goes to the target cell (posted after the CTA's last barrier: a barrier
                 // waits for the CTA's outstanding reductions)
-                post_claim(p.claim + nb_local(p, x, y, dir), claim_word(step, CLAIM_REPRO, s_prio[k], dir));
+                post_claim(p.claim + nb_local(p, x, y, dir), claim_word(step, CLAIM_REPRO, s_prio[slot], dir));
                 const uint32_t cell = (y << p.log2W) | x;
                 p.cl_cell[base + k] = cell;
                 p.cl_e[base + k] = p.E1[cell];  // (this CTA has just read the tile: an L2 hit)
@@ -623,24 +699,6 @@ __global__ void __launch_bounds__(NT, PD_CLAIM_CTAS) k_claim_punish(const __grid
                 p.risk_next[base + k] = ((y0 + cl / TW) << p.log2W) | (x0 + cl % TW);
             }
         }
-    }
-}
-
-// A parent that has won its claim (god_multiply, :1211-1213) re-derives its layer-7 outcome: k_claim_punish
-// charged it as a non-parent.  e1 = its energy when it entered layer 6 (E1 is read-only), `cell` its cell, owned
-// rows only (nobody writes a parent's strat / tfB entries during the reproduction rounds).  Almost always only the energy changes; deaths, counts and the at-risk list are corrected if not.
-__device__ __forceinline__ void parent_outcome(const Params& p, uint32_t cell, float e1, uint32_t trait) {
-    const Outcome a = outcome_of(p, e1, false), b = outcome_of(p, e1, true);
-    p.E0[cell] = b.e;
-    if (a.alive != b.alive) {
-        p.tfA[cell] = (uint8_t)(b.alive ? (TF_OCC | trait) : 0u);
-        atomicAdd(&p.ctr->living_deaths, b.alive ? ~0ull : 1ull);  // (+1, or -1 if a negative cost revives it)
-        if (p.want_counts) atomicAdd(&p.ctr->bins[count_bin(p.strat[cell], trait)], b.alive ? 1ull : ~0ull);
-    }
-    if (b.risk && !a.risk) {  // (an entry that is no longer at risk is harmless: k_risk_resolve replays it exactly)
-        const unsigned int slot = atomicAdd(&p.ctr->risk_next_n, 1u);
-        if (slot < p.list_cap) p.risk_next[slot] = cell;
-        else atomicExch(&p.ctr->overflow, 1u);
     }
 }
 

@@ -54,13 +54,21 @@ constexpr uint32_t I_ENERGY = 2;  // initial energy normal deviate (:1460-1465)
 __host__ __device__ constexpr int DX(int d) { return (d + (d >= 4 ? 1 : 0)) / 3 - 1; }
 __host__ __device__ constexpr int DY(int d) { return (d + (d >= 4 ? 1 : 0)) % 3 - 1; }
 static_assert(DX(0) == -1 && DX(2) == -1 && DX(3) == 0 && DX(4) == 0 && DX(5) == 1 && DX(7) == 1, "dx");
+// the same for a direction only known at run time: two bits per direction, packed
+__host__ __device__ constexpr int dxr(int d) { return (int)((0xA940u >> (2 * d)) & 3u) - 1; }
+__host__ __device__ constexpr int dyr(int d) { return (int)((0x9224u >> (2 * d)) & 3u) - 1; }
+static_assert(dxr(0) == DX(0) && dxr(1) == DX(1) && dxr(2) == DX(2) && dxr(3) == DX(3) && dxr(4) == DX(4) &&
+              dxr(5) == DX(5) && dxr(6) == DX(6) && dxr(7) == DX(7), "dxr");
+static_assert(dyr(0) == DY(0) && dyr(1) == DY(1) && dyr(2) == DY(2) && dyr(3) == DY(3) && dyr(4) == DY(4) &&
+              dyr(5) == DY(5) && dyr(6) == DY(6) && dyr(7) == DY(7), "dyr");
 static_assert(DY(0) == -1 && DY(1) == 0 && DY(2) == 1 && DY(3) == -1 && DY(4) == 1 && DY(5) == -1 &&
               DY(6) == 0 && DY(7) == 1, "dy");
 
 // ---- device-resident counters -----------------------------------------------------------
 struct Counters {
     // zeroed at the start of every step (k_begin_step)
-    unsigned int mv_n, rp_n, nb_n, risk_next_n, cand_n, nb_flagged, dep_n, pad1_;
+    unsigned int mv_n, rp_n, nb_n, risk_next_n, cand_n, nb_flagged, dep_n;
+    unsigned int lc_n;  // reproduction claims k_claim_punish resolved inside its tiles: listed from the BACK of the claim list
     unsigned int rt_n[2], pad4_[2];  // retry list: [0] travel, [1] reproduction
     unsigned int mv_active[8], rp_active[8];
     unsigned long long n_old, admitted, living_deaths, pad2_;  // admitted = newborns that entered the planes
@@ -105,6 +113,8 @@ struct Params {
     unsigned long long* step_log;  // [log_cap][18] rows: step, agents, 16 counts; nullptr = off
     uint32_t log_cap;
     uint32_t select_cap;      // cull select: most keys resolved in shared memory (tests lower it to reach the fallback)
+    uint32_t tie_shift;       // k_claim_punish: local claims whose priorities agree above this bit are a near-tie (3;
+                              // tests raise it to reach the detour through the claim plane)
     unsigned long long* glb;        // [0] olds [1] births [2] active repro losers [3] agents [4..19] bins,
                                     // summed over all slabs by the caller between the step's parts
     unsigned int* ghist;            // 2048-bin cull histogram, summed over all slabs by the caller

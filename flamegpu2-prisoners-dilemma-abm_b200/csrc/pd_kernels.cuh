@@ -241,23 +241,25 @@ __global__ void __launch_bounds__(COMMIT_NT) k_move_commit(const __grid_constant
 // so the child is made (make_child) in k_finalize if it survives, from the parent's unchanged E1 / strat / tfB
 // entries; it blocks its cell when retry rounds must see it.  A child born into a ghost row belongs to the
 // neighbour slab: here it only blocks its cell.  One random read per claimant, one random write per winner.
-__global__ void __launch_bounds__(COMMIT_NT) k_repro_commit(const __grid_constant__ Params p) {
-    __shared__ uint32_t s_lost_cell[COMMIT_CHUNK];
-    __shared__ uint8_t s_lost_state[COMMIT_CHUNK];
-    __shared__ uint32_t s_nb_cell[COMMIT_CHUNK];
-    __shared__ uint8_t s_nb_dir[COMMIT_CHUNK];
-    __shared__ uint32_t s_nb_prio[COMMIT_CHUNK];
-    __shared__ unsigned int s_hist[2048];  // this CTA's share of the cull histogram
-    __shared__ unsigned int s_n[4];  // 0 losers of this chunk, 1 newborns, 2 / 3 their bases in the global lists
+// Two lists: the claimants that went through the claim plane (front of the claim list), and the ones k_claim_punish
+// has already judged inside its tiles (LOCAL: back of the list, verdict in the entry, the winner has paid) -- for
+// those only the appends are left: no random access at all.
+struct CommitShared {
+    uint32_t lost_cell[COMMIT_CHUNK];
+    uint8_t lost_state[COMMIT_CHUNK];
+    uint32_t nb_cell[COMMIT_CHUNK];
+    uint8_t nb_dir[COMMIT_CHUNK];
+    uint32_t nb_prio[COMMIT_CHUNK];
+    unsigned int hist[2048];  // this CTA's share of the cull histogram
+    unsigned int n[4];        // 0 losers of this chunk, 1 newborns, 2 / 3 their bases in the global lists
+};
+
+template <bool LOCAL>
+__device__ __forceinline__ void repro_commit_list(const Params& p, CommitShared& s, unsigned int n, uint32_t step) {
     Counters* ctr = p.ctr;
-    unsigned int n = ctr->rp_n;
-    if (n > p.list_cap) n = p.list_cap;
-    const uint32_t step = __ldg(&ctr->step_no);
     const int tid = threadIdx.x;
-    if (blockIdx.x * COMMIT_CHUNK >= n) return;
-    for (int i = tid; i < 2048; i += COMMIT_NT) s_hist[i] = 0;
     for (unsigned int c0 = blockIdx.x * COMMIT_CHUNK; c0 < n; c0 += gridDim.x * COMMIT_CHUNK) {
-        if (tid < 2) s_n[tid] = 0;
+        if (tid < 2) s.n[tid] = 0;
         __syncthreads();
         uint32_t cell[COMMIT_K], tgt[COMMIT_K], aux[COMMIT_K];
         unsigned long long top[COMMIT_K];
@@ -265,78 +267,100 @@ __global__ void __launch_bounds__(COMMIT_NT) k_repro_commit(const __grid_constan
 #pragma unroll
         for (int k = 0; k < COMMIT_K; ++k) {
             const unsigned int i = c0 + k * COMMIT_NT + tid;
-            cell[k] = i < n ? p.cl_cell[i] : 0u;
-            aux[k] = i < n ? (uint32_t)p.cl_aux[i] : 0u;
-            e[k] = i < n ? p.cl_e[i] : 0.0f;
+            const unsigned int at = LOCAL ? p.list_cap - 1u - i : i;
+            cell[k] = i < n ? p.cl_cell[at] : 0u;
+            aux[k] = i < n ? (uint32_t)p.cl_aux[at] : 0u;
+            e[k] = !LOCAL && i < n ? p.cl_e[at] : 0.0f;
         }
 #pragma unroll
         for (int k = 0; k < COMMIT_K; ++k) {
             tgt[k] = nb_local(p, cell[k] & (p.W - 1), cell[k] >> p.log2W, (int)(aux[k] & 7u));
-            top[k] = __ldcg(p.claim + tgt[k]);
+            top[k] = LOCAL ? 0ull : __ldcg(p.claim + tgt[k]);
         }
 #pragma unroll
         for (int k = 0; k < COMMIT_K; ++k) {
             const bool valid = c0 + k * COMMIT_NT + tid < n;
             const int d = (int)(aux[k] & 7u);
             const uint32_t x = cell[k] & (p.W - 1), y = cell[k] >> p.log2W;
-            const unsigned long long mine = claim_word(step, CLAIM_REPRO, rng(p, gcell_of(p, x, y), S_REPRO).x, d);
-            const bool won = valid && top[k] == mine;
-            bool born = false;
-            if (won) {  // REPRODUCTION_COMPLETE (:1211-1213, :1331)
-                const uint32_t trait = (aux[k] >> 3) & TF_TRAIT;
-                if (row_owned(p, y)) parent_outcome(p, cell[k], e[k], trait);
-                born = row_owned(p, tgt[k] >> p.log2W);
-                if (!born) p.tfB[tgt[k]] = (uint8_t)(TF_OCC | TF_NEWBORN | trait);
+            bool won, born = false;
+            if (LOCAL) {
+                won = valid && (aux[k] & 8u) != 0u;
+                born = won && row_owned(p, tgt[k] >> p.log2W);
+            } else {
+                const unsigned long long mine = claim_word(step, CLAIM_REPRO, rng(p, gcell_of(p, x, y), S_REPRO).x, d);
+                won = valid && top[k] == mine;
+                if (won) {  // REPRODUCTION_COMPLETE (:1211-1213, :1331)
+                    const uint32_t trait = (aux[k] >> 3) & TF_TRAIT;
+                    if (row_owned(p, y)) parent_outcome(p, cell[k], e[k], trait);
+                    born = row_owned(p, tgt[k] >> p.log2W);
+                    if (!born) p.tfB[tgt[k]] = (uint8_t)(TF_OCC | TF_NEWBORN | trait);
+                }
             }
-            const uint32_t bslot = wappend(&s_n[1], born);
+            const uint32_t bslot = wappend(&s.n[1], born);
             if (born) {
                 const uint32_t prio = cull_prio(p, tgt[k]);
-                atomicAdd(&s_hist[prio >> 21], 1u);
-                s_nb_cell[bslot] = tgt[k];
-                s_nb_dir[bslot] = (uint8_t)d;
-                s_nb_prio[bslot] = prio;
+                atomicAdd(&s.hist[prio >> 21], 1u);
+                s.nb_cell[bslot] = tgt[k];
+                s.nb_dir[bslot] = (uint8_t)d;
+                s.nb_prio[bslot] = prio;
             }
             const bool lost = valid && !won;  // stays ATTEMPTING_REPRODUCTION (:1203-1205)
-            const uint32_t lslot = wappend(&s_n[0], lost);
+            const uint32_t lslot = wappend(&s.n[0], lost);
             if (lost) {
-                s_lost_cell[lslot] = cell[k];
-                s_lost_state[lslot] = (uint8_t)(0xC0u | (uint32_t)d);
+                s.lost_cell[lslot] = cell[k];
+                s.lost_state[lslot] = (uint8_t)(0xC0u | (uint32_t)d);
             }
         }
         __syncthreads();
-        const unsigned int n_lost = s_n[0], n_born = s_n[1];
+        const unsigned int n_lost = s.n[0], n_born = s.n[1];
         if (tid == 0) {
-            if (n_lost) s_n[2] = atomicAdd(&ctr->rt_n[1], n_lost);
-            if (n_born) s_n[3] = atomicAdd(&ctr->nb_n, n_born);
+            if (n_lost) s.n[2] = atomicAdd(&ctr->rt_n[1], n_lost);
+            if (n_born) s.n[3] = atomicAdd(&ctr->nb_n, n_born);
         }
         __syncthreads();
         if (n_lost) {  // uniform across the CTA
-            const unsigned int base = s_n[2];
+            const unsigned int base = s.n[2];
             if (base + n_lost > p.list_cap) {
                 if (tid == 0) atomicExch(&ctr->overflow, 1u);
             } else {
                 for (unsigned int k = tid; k < n_lost; k += COMMIT_NT) {
-                    p.rt_cell[base + k] = s_lost_cell[k];
-                    p.rt_state[base + k] = s_lost_state[k];
+                    p.rt_cell[base + k] = s.lost_cell[k];
+                    p.rt_state[base + k] = s.lost_state[k];
                 }
             }
         }
         if (n_born) {
-            const unsigned int base = s_n[3];
+            const unsigned int base = s.n[3];
             if (base + n_born > p.list_cap) {
                 if (tid == 0) atomicExch(&ctr->overflow, 1u);
             } else {
                 for (unsigned int k = tid; k < n_born; k += COMMIT_NT) {
-                    p.nb_cell[base + k] = s_nb_cell[k];
-                    p.nb_dir[base + k] = s_nb_dir[k];
-                    p.nb_prio[base + k] = s_nb_prio[k];
+                    p.nb_cell[base + k] = s.nb_cell[k];
+                    p.nb_dir[base + k] = s.nb_dir[k];
+                    p.nb_prio[base + k] = s.nb_prio[k];
                 }
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(COMMIT_NT) k_repro_commit(const __grid_constant__ Params p) {
+    __shared__ CommitShared s;
+    Counters* ctr = p.ctr;
+    unsigned int n = ctr->rp_n, n_loc = ctr->lc_n;
+    if (n > p.list_cap) n = p.list_cap;
+    if (n_loc > p.list_cap) n_loc = p.list_cap;
+    const uint32_t step = __ldg(&ctr->step_no);
+    const int tid = threadIdx.x;
+    if (blockIdx.x * COMMIT_CHUNK >= n && blockIdx.x * COMMIT_CHUNK >= n_loc) return;
+    // the two ends of the claim list have met: entries were overwritten
+    if (blockIdx.x == 0 && tid == 0 && (unsigned long long)n + n_loc > p.list_cap) atomicExch(&ctr->overflow, 1u);
+    for (int i = tid; i < 2048; i += COMMIT_NT) s.hist[i] = 0;
+    repro_commit_list<false>(p, s, n, step);
+    repro_commit_list<true>(p, s, n_loc, step);
     __syncthreads();
     for (int i = tid; i < 2048; i += COMMIT_NT)
-        if (s_hist[i]) atomicAdd(&ctr->hist[0][0] + i, s_hist[i]);
+        if (s.hist[i]) atomicAdd(&ctr->hist[0][0] + i, s.hist[i]);
 }
 
 // ------------------------------------------------------------------------------------------

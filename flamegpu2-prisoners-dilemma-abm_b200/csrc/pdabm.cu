@@ -380,6 +380,7 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
         wsum += (double)cfg->strategy_weights[i];
     }
     if (!(wsum > 0)) return fail(PD_ERR_INVALID, "strategy_weights sum to 0");
+    if (cfg->debug_tie_shift > 31u) return fail(PD_ERR_INVALID, "debug_tie_shift must be in [0, 31]");
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(PD_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
@@ -400,6 +401,7 @@ int pd_create(const pd_config* cfg, pd_sim** out) {
     P.own_y0 = cfg->ghost_rows; P.own_y1 = cfg->ghost_rows + cfg->rows;
     P.round0 = 1; P.round1 = 8; P.world = 1; P.cand_cap = 0; P.speculative = 0;
     P.select_cap = cfg->debug_select_cap ? cfg->debug_select_cap : 0xFFFFFFFFu;
+    P.tie_shift = cfg->debug_tie_shift ? cfg->debug_tie_shift : 3u;
     P.step_log = nullptr; P.log_cap = 0;
     P.glb = nullptr; P.ghist = nullptr; P.cand_out = nullptr; P.cand_all = nullptr;
     P.log2W = 0;

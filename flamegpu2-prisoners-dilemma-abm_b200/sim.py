@@ -53,6 +53,7 @@ class SimConfig:
     sparse_ctas: int = 0
     use_graphs: int = 0                    # 0 auto, 1 always, -1 never (one CUDA graph per step; needs a stream)
     debug_select_cap: int = 0              # tests only: force the cull select's global-memory fallback
+    debug_tie_shift: int = 0               # tests only: force the claim-plane route of tile-local reproduction claims
 
     def __post_init__(self):
         if self.height < 0:
@@ -88,6 +89,7 @@ class SimConfig:
         c.sparse_ctas = int(self.sparse_ctas)
         c.use_graphs = int(self.use_graphs)
         c.debug_select_cap = int(self.debug_select_cap)
+        c.debug_tie_shift = int(self.debug_tie_shift)
         return c
 
 

@@ -82,6 +82,9 @@ typedef struct pd_config {
                                        (capturable) streams and while per-kernel profiling is off. */
     uint32_t debug_select_cap;      /* 0 = default; tests: cap of the cull select's shared-memory stage, to force its
                                        global-memory fallback */
+    uint32_t debug_tie_shift;       /* 0 = default (3); tests: two reproduction claims settled inside a tile count as a
+                                       near-tie -- the tile's claims then take the exact route through the claim plane --
+                                       when their priorities agree above this bit: 24..31 forces that route often */
 } pd_config;
 
 /* Per-step event counters of the LAST executed step (debug / parity aid; the

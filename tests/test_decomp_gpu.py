@@ -26,6 +26,8 @@ CASES = {
                            init_energy_mu=4.0, init_energy_sigma=2.0, init_energy_min=1.0, init_agent_count=24000), 30),
     "select_fallback": (dict(width=256, seed=37, debug_select_cap=1, init_agent_count=30000, max_agents=31000,
                              reproduce_min_energy=40.0, reproduce_cost=10.0), 30),
+    "claim_detour": (dict(width=256, seed=38, debug_tie_shift=26, init_agent_count=30000, max_agents=40000,
+                          reproduce_min_energy=40.0, reproduce_cost=10.0), 30),
     "inherit": (dict(width=256, seed=35, reproduction_inheritence=0.5, env_noise=0.2, mutation_rate=0.2), 70),
 }
 

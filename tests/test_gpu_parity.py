@@ -30,7 +30,7 @@ def _pair(**kw):
     from pdabm_b200 import Simulation, SimConfig
     from oracle.pd_oracle import Oracle, Params
     sim = Simulation(SimConfig(collect_stats=True, **kw))
-    okw = {k: v for k, v in kw.items() if k not in ("sparse_ctas", "debug_select_cap")}
+    okw = {k: v for k, v in kw.items() if k not in ("sparse_ctas", "debug_select_cap", "debug_tie_shift")}
     orc = Oracle(Params(**okw))
     return sim, orc
 
@@ -140,6 +140,17 @@ def test_cull_select_fallback_path():
     _run(75, width=128, seed=41, debug_select_cap=1)
     _run(40, width=128, seed=42, debug_select_cap=1, sparse_ctas=8, init_agent_count=7000, max_agents=7200,
          reproduce_min_energy=40.0, reproduce_cost=10.0)
+
+
+def test_local_claim_detour_path():
+    """Reproduction claims on cells only one tile can reach are settled in shared memory by an atomic max of
+    (priority top 29 bits | position); if two rivals agree in those bits the tile's claims take the exact route through
+    the claim plane.  With the near-tie test widened to the top 4 / 8 bits almost every / every few tiles take that
+    route -- the same winners either way."""
+    _run(75, width=128, seed=43, debug_tie_shift=28)
+    _run(75, width=256, seed=44, debug_tie_shift=24, strategy_per_trait=1, env_noise=0.05, mutation_rate=0.01)
+    _run(25, width=128, seed=45, debug_tie_shift=30, init_agent_count=7000, max_agents=12000,
+         reproduce_min_energy=40.0, reproduce_cost=10.0, payoff_cc=10.0)
 
 
 def test_dense_world_conflicts():
