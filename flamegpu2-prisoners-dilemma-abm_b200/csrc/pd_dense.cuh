@@ -45,30 +45,6 @@ __device__ __forceinline__ bool punish(const Params& p, float& e) {
     return e > 0.0f;
 }
 
-// ---- shared-memory tile of a u8 plane: (TH + 2*HALO) rows of TW+32 bytes, interior at column 16
-template <int TW, int TH, int HALO>
-__device__ __forceinline__ void load_tile_vec(const Params& p, const uint8_t* __restrict__ plane,
-                                              uint8_t* s, uint32_t x0, uint32_t y0) {
-    constexpr int NCH = TW / 16 + 2;
-    constexpr int SW = TW + 32;
-    constexpr int SH = TH + 2 * HALO;
-    const uint32_t wch = p.W >> 4;  // 16-byte chunks per row
-    for (int i = threadIdx.x; i < SH * NCH; i += NT) {
-        const int r = i / NCH, j = i - r * NCH;
-        const uint32_t cx = ((x0 >> 4) + (uint32_t)(j - 1)) & (wch - 1);
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (p.wrap_y) {
-            const uint32_t gy = (y0 + (uint32_t)(r - HALO)) & (p.H - 1);
-            v = *reinterpret_cast<const uint4*>(plane + ((size_t)gy << p.log2W) + ((size_t)cx << 4));
-        } else {  // slab: rows beyond the local planes read as empty (they are outside the valid zone)
-            const int gy = (int)y0 + r - HALO;
-            if (gy >= 0 && gy < (int)p.H)
-                v = *reinterpret_cast<const uint4*>(plane + ((size_t)gy << p.log2W) + ((size_t)cx << 4));
-        }
-        *reinterpret_cast<uint4*>(s + r * SW + j * 16) = v;
-    }
-}
-
 // Shared-memory atomic add that the compiler leaves alone.  For `atomicAdd(&counter, 1)` in divergent code nvcc
 // emits a warp-aggregation sequence (vote, popc, leader election, shuffle: ~20 issue slots per site); with the
 // handful of lanes that append to a queue at any one site here, letting the hardware serialise the lanes of one
@@ -210,15 +186,6 @@ __global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_c
     const uint32_t x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const bool noisy = p.noise_thr != 0ull;
     if (tid < 8) s_n[tid] = 0;
-    // the energies go straight to shared memory (cp.async); they are first needed after the barrier below
-    for (int i = tid; i < NC / 4; i += NT) {
-        const int ly = (i * 4) >> LOG_TW, lx = (i * 4) & (TW - 1);
-        const float* src = p.E0 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(s_e + i * 4)), "l"(src));
-    }
-    asm volatile("cp.async.commit_group;");
-    static_assert(NT == 256, "one table entry per thread");
-    s_lut[tid] = __ldg(p.lut + tid);  // lut_entry() of every index, filled by pd_create
     for (int i = tid; i < NC / 16; i += NT) {
         reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0, 0, 0, 0);
         reinterpret_cast<uint4*>(s_cmask)[i] = make_uint4(0, 0, 0, 0);
@@ -253,6 +220,16 @@ __global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_c
             st4[it] = *reinterpret_cast<const uint32_t*>(p.strat + off);
         }
     }
+    // the energies go straight to shared memory (cp.async), requested after the flag / strategy words (which the next
+    // phase waits for); they are first needed by the agents
+    for (int i = tid; i < NC / 4; i += NT) {
+        const int ly = (i * 4) >> LOG_TW, lx = (i * 4) & (TW - 1);
+        const float* src = p.E0 + ((size_t)(y0 + ly) << p.log2W) + x0 + lx;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(s_e + i * 4)), "l"(src));
+    }
+    asm volatile("cp.async.commit_group;");
+    static_assert(NT == 256, "one table entry per thread");
+    s_lut[tid] = __ldg(p.lut + tid);  // lut_entry() of every index, filled by pd_create
     __syncthreads();  // the list counters are zero (the loads above are in flight meanwhile)
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
@@ -509,8 +486,19 @@ __global__ void __launch_bounds__(NT, PD_CLAIM_CTAS) k_claim_punish(const __grid
     if (tid < 13) s_n[tid] = 0;
     if (tid < 16) s_bins[tid] = 0;
     for (int i = tid; i < NC / 4; i += NT) reinterpret_cast<uint4*>(s_max)[i] = make_uint4(0, 0, 0, 0);
-    // the energies are requested before the flag tile arrives, so that the two latencies overlap (empty cells
-    // hold 0 in E1: loading them is only wasted bandwidth, and only in sparse worlds)
+    // The flag tile first -- the whole CTA waits for it at the barrier -- then the energies, all in flight together
+    // (empty cells hold 0 in E1: loading them is only wasted bandwidth, and only in sparse worlds)
+    constexpr int NCH = TW / 16 + 2;  // 16-byte chunks per tile row incl. the ring's
+    static_assert(SH * NCH <= NT, "one chunk of the flag tile per thread");
+    uint4 tile_v = make_uint4(0, 0, 0, 0);
+    if (tid < SH * NCH) {
+        const int r = tid / NCH, j = tid - r * NCH;
+        const uint32_t cx = ((x0 >> 4) + (uint32_t)(j - 1)) & ((p.W >> 4) - 1);
+        const int gy = (int)y0 + r - 1;  // a slab reads rows beyond its planes as empty (they are outside the valid zone)
+        if (p.wrap_y || (gy >= 0 && gy < (int)p.H))
+            tile_v = *reinterpret_cast<const uint4*>(p.tfB + ((size_t)(p.wrap_y ? (uint32_t)gy & (p.H - 1) : (uint32_t)gy) << p.log2W) +
+                                                     ((size_t)cx << 4));
+    }
     constexpr int NIT = (NC / 4 + NT - 1) / NT;
     float4 e_pre[NIT];
     uint32_t st_pre[NIT];
@@ -526,7 +514,7 @@ __global__ void __launch_bounds__(NT, PD_CLAIM_CTAS) k_claim_punish(const __grid
             if (p.want_counts && owned) st_pre[it] = *reinterpret_cast<const uint32_t*>(p.strat + off);
         }
     }
-    load_tile_vec<TW, TH, 1>(p, p.tfB, s_tf, x0, y0);
+    if (tid < SH * NCH) *reinterpret_cast<uint4*>(s_tf + (tid / NCH) * SW + (tid % NCH) * 16) = tile_v;
     __syncthreads();
     unsigned int n_occ = 0, n_dead = 0;
     uint32_t par_bits = 0;  // bit 4 * it + k: cell k of my group of iteration it holds an agent that may reproduce
@@ -632,10 +620,11 @@ __global__ void __launch_bounds__(NT, PD_CLAIM_CTAS) k_claim_punish(const __grid
     const bool detour = s_n[12] != 0u;
     const unsigned int n_plane = s_n[1], n_local = detour ? 0u : s_n[7], n_claim = n_plane + (detour ? s_n[7] : 0u);
     const unsigned int n_risk = s_n[4];
-    if (tid == 0) {
-        if (n_claim) s_n[2] = atomicAdd(&p.ctr->rp_n, n_claim);
-        if (n_local) s_n[8] = atomicAdd(&p.ctr->lc_n, n_local);
-        if (n_risk) s_n[5] = atomicAdd(&p.ctr->risk_next_n, n_risk);
+    // (one warp each: a thread's second atomic would wait for the first one's answer to be stored)
+    if (tid == 0 && n_claim) s_n[2] = atomicAdd(&p.ctr->rp_n, n_claim);
+    if (tid == 32 && n_local) s_n[8] = atomicAdd(&p.ctr->lc_n, n_local);
+    if (tid == 64 && n_risk) s_n[5] = atomicAdd(&p.ctr->risk_next_n, n_risk);
+    if (tid == 96) {
         if (s_n[3] && owned) atomicAdd(&p.ctr->n_old, (unsigned long long)s_n[3]);
         if (s_n[6]) atomicAdd(&p.ctr->living_deaths, (unsigned long long)s_n[6]);
     }

@@ -313,10 +313,8 @@ __device__ __forceinline__ void repro_commit_list(const Params& p, CommitShared&
         }
         __syncthreads();
         const unsigned int n_lost = s.n[0], n_born = s.n[1];
-        if (tid == 0) {
-            if (n_lost) s.n[2] = atomicAdd(&ctr->rt_n[1], n_lost);
-            if (n_born) s.n[3] = atomicAdd(&ctr->nb_n, n_born);
-        }
+        if (tid == 0 && n_lost) s.n[2] = atomicAdd(&ctr->rt_n[1], n_lost);
+        if (tid == 32 && n_born) s.n[3] = atomicAdd(&ctr->nb_n, n_born);
         __syncthreads();
         if (n_lost) {  // uniform across the CTA
             const unsigned int base = s.n[2];
