@@ -80,7 +80,7 @@ __device__ __forceinline__ uint32_t wappend(unsigned int* counter, bool pred) {
 // terminal rule, and the first move_request (:784-872).
 //
 // Per cell of tile + 1-ring ONE 32-bit word R is staged in shared memory:
-//     empty cell: 0
+//     empty cell: bit 31 clear (the rest is 0 or leftover roll / strategy bits)
 //     occupied:   bit 31 | roll (16 bits) << 15 | has-D-code << 11 | strategies (8) << 3 | trait (2) << 1
 // so one shared-memory load per neighbour answers "occupied?", "does it challenge me?" (an unsigned
 // compare of the whole word against one of two thresholds: a tie of the rolls goes to the neighbour in a
@@ -243,13 +243,24 @@ __global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_c
                 const uint64_t g4 = (((uint64_t)gyv[it] << p.log2W) | gq[it]) >> 2;
                 const Words w = rng(p, g4, S_ROLL);
                 const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+                // Branch-free, straight from the two plane words (shift + mask-and-merge per field).  Only bit 31 says
+                // "occupied": an EMPTY cell of the group keeps roll and strategy bits (its flag byte is 0, so no trait,
+                // no D flag) -- such a word compares below every threshold and is never looked at otherwise.
+                static_assert(ROLL_SHIFT == 16 && TF_OCC == 0x80u && TF_TRAIT == 0x03u, "word layout");
+                const uint32_t T = tf4[it], S = st4[it];
                 uint32_t rr[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t t = (tf4[it] >> (8 * k)) & 0xFFu, sb = (st4[it] >> (8 * k)) & 0xFFu;
-                    rr[k] = (t & TF_OCC) ? (R_OCC | ((ww[k] >> ROLL_SHIFT) << 15) | ((t & TF_D) ? R_DFLAG : 0u) | (sb << 3) |
-                                            ((t & TF_TRAIT) << 1)) : 0u;
+                    uint32_t r = ((k == 3 ? T : T << (24 - 8 * k)) & R_OCC) | ((ww[k] >> 1) & 0x7FFF8000u);
+                    r |= (k == 0 ? S << 3 : S >> (8 * k - 3)) & 0x7F8u;
+                    r |= (k == 0 ? T << 1 : T >> (8 * k - 1)) & 0x6u;
+                    rr[k] = r;
                     v[k] = ((uint32_t)(j * 4 + k)) | (ww[k] << 16);  // (interior: j * 4 + k is the tile-local cell)
+                }
+                if (T & (TF_D * 0x01010101u)) {  // rare: an at-risk agent that dies during play (k_risk_resolve)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if ((T >> (8 * k)) & TF_D) rr[k] |= R_DFLAG;
                 }
                 r4 = make_uint4(rr[0], rr[1], rr[2], rr[3]);
             }
@@ -277,7 +288,7 @@ __global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_c
         // act[7] / act[0] of the terminal rule come from the roll order alone (get_game_list, :413): a
         // challenger that dies early still "would have challenged".
         // act[7]==1 <=> neighbour 7 exists and does not challenge me; act[0]==0 <=> neighbour 0 challenges me
-        const bool act7_challenge = rn[7] != 0u && !(rn[7] > tB);
+        const bool act7_challenge = (rn[7] & R_OCC) && !(rn[7] > tB);
         const bool act0_respond = rn[0] > tA;
         if (any_nb & R_DFLAG) {  // rare: a neighbour dies during play (D code = sub-step of death + 1)
 #pragma unroll
@@ -299,7 +310,7 @@ __global__ void __launch_bounds__(NT, PD_PLAY_CTAS) k_play_travel(const __grid_c
         } else {
             // terminal rule (:547-556, :719-730, :486-496) or no neighbours (:429-433); games_played (:710) of an
             // agent that is still alive counts all its games as the responder
-            const bool mover = any_nb == 0u || (!any && (act7_challenge || act0_respond));
+            const bool mover = !(any_nb & R_OCC) || (!any && (act7_challenge || act0_respond));
             s_out[cl] = (uint8_t)(TF_OCC | ((rme >> 1) & TF_TRAIT));
             s_e[cl] = e;
             // (+1 spelled as my word's OCC bit: for an increment it can prove uniform, ptxas wraps the atomic in a
