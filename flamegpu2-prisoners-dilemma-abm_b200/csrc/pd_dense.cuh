@@ -7,11 +7,16 @@
 //                                                          its claim and goes on the claim list; fused with
 //                                                          environmental_punishment + counts (cell-local)
 //
-// The claims themselves -- move_response / god_multiply, all 8 rounds of each -- are resolved by SPARSE kernels
-// (pd_kernels.cuh) over those lists, in place on tfB: a claimant has won iff its target's claim word is still its
-// own (atomic max, pd_device.cuh claim_word), one independent thread per claimant, no barriers.
-// (Round 1 of both used to be two more dense sweeps that staged every tile to resolve a 4-5 % claimant rate:
-// 1.8 ms of a 5.3 ms step, latency-bound on the per-tile barrier phases -- profiles/README.md.)
+// Round 1 of the claims (move_response / god_multiply) is decided WHERE IT CAN BE DECIDED: a target cell all of
+// whose eight neighbours lie in the claimant's tile -- every cell but the tile's outermost ring, 86 % of them --
+// cannot have a rival outside the tile, so such a claim is settled in shared memory inside the sweep that makes it
+// (a byte mask per cell for the movers, who relocate within the tile before it is stored; an atomic max per cell
+// for the parents, who pay at once).  Only claims on the rim, movers with rivals, and rounds 2..8 go through the
+// claim plane and the SPARSE kernels (pd_kernels.cuh): a claimant has won iff its target's claim word is still
+// its own (atomic max, pd_device.cuh claim_word), one independent thread per claimant, no barriers.
+// (History: round 1 as two more dense sweeps that staged every tile for a 4-5 % claimant rate cost 1.8 ms of a
+// 5.3 ms step; all claims through the plane cost 0.6 + 0.4 ms in the commit kernels, bound by random DRAM sectors;
+// now 0.18 + 0.16 ms -- profiles/README.md.)
 //
 // Design rules learned from the profiles:
 //   * u8 planes enter shared memory as 16-byte chunks (interior at column 16 of a TW+32 wide row);

@@ -3,12 +3,14 @@
 // One model step (main layers 1-7, /root/reference/src/model.py:2140-2163) is
 //   k_begin_step    zero the per-step counters
 //   k_risk_resolve  sparse: exact death sub-step of the few agents that CAN die in play
-//   k_play_travel   dense sweep 1: roll + roles + 8 play sub-steps + mover decision + travel claim
-//   k_move_commit   sparse: resolve the travel claims of round 1 (one thread per claimant), winners relocate
+//   k_play_travel   dense sweep 1: roll + roles + 8 play sub-steps + mover decision + travel claim; a mover alone
+//                   on a target only its tile can reach relocates inside the tile
+//   k_move_commit   sparse: resolve the other travel claims of round 1 (one thread per claimant), winners relocate
 //   k_move_retry    sparse: travel rounds 2..8 for the claim losers
-//   k_claim_punish  dense sweep 2: eligibility + reproduction claim, fused with cost of living, death, counts
-//                   and the next step's at-risk list (a winning parent corrects its own outcome afterwards)
-//   k_repro_commit  sparse: resolve the reproduction claims of round 1, births
+//   k_claim_punish  dense sweep 2: eligibility + reproduction claim (judged inside the tile where only the tile can
+//                   reach the target), fused with cost of living, death, counts and the next step's at-risk list
+//                   (a winning parent corrects its own outcome afterwards)
+//   k_repro_commit  sparse: resolve the other reproduction claims of round 1; births and retry entries of all
 //   k_repro_retry   sparse: reproduction rounds 2..8 (gated by the carrying capacity)
 //   k_finalize      sparse: newborn cull (exact k-th selection), the surviving newborns enter the planes
 // Every dense sweep is a pure GATHER on the state planes: a cell reads its neighbourhood and writes only itself.
