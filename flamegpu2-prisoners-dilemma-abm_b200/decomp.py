@@ -28,6 +28,7 @@ decomposition invariance without a multi-GPU box).
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -207,6 +208,7 @@ class DecomposedWorld:
         self.slabs = [_Slab(cfg, r, comm.world, ghost_rows, cand_cap, stream) for r in comm.local_ranks]
         self.retry_rounds_run = 0  # reproduction retry rounds executed so far (2 launches + 1 all-reduce each)
         self._counts = None
+        self._glb_summed = True    # glb[3:] (agents + 16 counts) holds the sum over the slabs
 
     def close(self):
         for s in self.slabs:
@@ -223,6 +225,7 @@ class DecomposedWorld:
             c, n = s.sim.counts()
             s.glb[3:] = torch.tensor([n] + [int(v) for v in c], dtype=torch.int64, device=s.glb.device)
         self.comm.allreduce([s.glb[3:] for s in self.slabs])
+        self._glb_summed = True
 
     def set_state_from(self, planes: Dict[str, np.ndarray]):
         """Upload a whole-world state (oracle-style planes) -- each slab takes its rows; test helper."""
@@ -252,7 +255,6 @@ class DecomposedWorld:
         return olds + births <= self.cfg.max_agents and active > 0
 
     def step(self, n_steps: int = 1, want_counts: bool = True):
-        import contextlib
         comm, slabs = self.comm, self.slabs
         # everything -- kernels, halo copies, collectives -- is ordered on ONE stream: the handle's, if it has one
         ctx = self.torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
@@ -284,7 +286,19 @@ class DecomposedWorld:
                     s.part(PD_PART_HIST, 0, wc)
                 comm.allreduce([s.ghist for s in slabs])
                 self._finish(0, wc)
-            comm.allreduce([s.glb[3:] for s in slabs])  # agents + 16 counts of the last step
+            # agents + 16 counts of the last step: summed right away when the caller logs them, else on demand
+            # (counts()) -- one small collective less per step, and less host work between a step's gate read and
+            # the next step's first launches
+            self._glb_summed = False
+            if want_counts:
+                self._sum_counts()
+
+    def _sum_counts(self):
+        if not self._glb_summed:
+            ctx = self.torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
+            with ctx:
+                self.comm.allreduce([s.glb[3:] for s in self.slabs])
+            self._glb_summed = True
 
     def _finish(self, speculative: int, wc: bool):
         comm, slabs = self.comm, self.slabs
@@ -295,7 +309,9 @@ class DecomposedWorld:
             s.part(PD_PART_APPLY, speculative, wc)
 
     def counts(self):
-        """Global (population_strat_count[16], agent count) after the last step()."""
+        """Global (population_strat_count[16], agent count) after the last step().  COLLECTIVE after a step() with
+        want_counts=False: every rank must call it."""
+        self._sum_counts()
         v = self.slabs[0].glb.cpu().numpy()
         for s in self.slabs:
             s.sim.counts()  # raises on a list overflow in any slab
