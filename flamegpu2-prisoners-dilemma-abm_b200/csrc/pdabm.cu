@@ -82,9 +82,14 @@ struct pd_sim {
     bool lists_allocated;
     // optional per-kernel timing (pd_set_profile): events around every launch of a step
     bool profile;
-    std::vector<cudaEvent_t> ev;   // (start, end) event pairs, consumed by pd_read_profile
-    std::vector<int> ev_slot;      // kernel slot of pair k
-    size_t ev_used;                // events used (2 per pair)
+    // One event BETWEEN consecutive profiled launches of a call (the end of one kernel is the start of the next):
+    // 10 records per step, not 18 -- every record in the stream keeps the next kernel from starting back to back
+    // (measured: 18 records cost 0.065 ms per step at 2^28 cells).
+    std::vector<cudaEvent_t> ev;
+    struct ProfSpan { uint32_t start, end; int slot; };
+    std::vector<ProfSpan> spans;   // consumed by pd_read_profile
+    size_t ev_used;                // events recorded since the last read
+    bool ev_chain;                 // the last recorded event ended a span and nothing was launched since
     double kernel_ms[PDABM_NUM_KERNELS];
     uint32_t prof_steps;
     bool step_dirty;               // host step number not yet written to Counters::step_no
@@ -184,22 +189,31 @@ int launch_sparse_k(pd_sim* s, K kernel, cudaStream_t st) {
     ((s)->sparse_threads == 1024 ? launch_sparse_k(s, kernel<1024>, st) : launch_sparse_k(s, kernel<512>, st))
 
 // per-kernel timing: a (start, end) CUDA event pair around one or more launches, tagged with a kernel slot
-int prof_begin(pd_sim* s, int slot, cudaStream_t st) {
-    if (!s->profile) return PD_OK;
-    while (s->ev_used + 2 > s->ev.size()) {
+int prof_record(pd_sim* s, cudaStream_t st) {
+    if (s->ev_used == s->ev.size()) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));
         s->ev.push_back(e);
     }
-    if (s->ev_slot.size() < s->ev.size() / 2) s->ev_slot.resize(s->ev.size() / 2);
-    s->ev_slot[s->ev_used / 2] = slot;
     CK(cudaEventRecord(s->ev[s->ev_used], st));
+    s->ev_used += 1;
+    return PD_OK;
+}
+int prof_begin(pd_sim* s, int slot, cudaStream_t st) {
+    if (!s->profile) return PD_OK;
+    if (!s->ev_chain) {
+        const int rc = prof_record(s, st);
+        if (rc) return rc;
+    }
+    s->spans.push_back({(uint32_t)(s->ev_used - 1), 0u, slot});
     return PD_OK;
 }
 int prof_end(pd_sim* s, cudaStream_t st) {
     if (!s->profile) return PD_OK;
-    CK(cudaEventRecord(s->ev[s->ev_used + 1], st));
-    s->ev_used += 2;
+    const int rc = prof_record(s, st);
+    if (rc) return rc;
+    s->spans.back().end = (uint32_t)(s->ev_used - 1);
+    s->ev_chain = true;
     return PD_OK;
 }
 // PDABM_DEBUG_SYNC=1 in the environment: synchronise after every kernel and name the one that failed
@@ -257,6 +271,7 @@ int launch_commit(pd_sim* s, void (*kernel)(const Params), cudaStream_t st) {
 int launch_step(pd_sim* s, cudaStream_t st) {
     Params& P = s->P;
     int rc = PD_OK;
+    s->ev_chain = false;  // (whatever the caller launched since the last span is not the first kernel's time)
     PROF(0, (k_begin_step<<<1, 256, 0, st>>>(P.ctr, 1)));
     PROF(1, { if ((rc = launch_sparse(s, k_risk_resolve, st))) return rc; });
     PROF(2, DENSE(k_play_travel));
@@ -651,6 +666,7 @@ int pd_step_part(pd_sim* s, int part, int arg, void* stream, int want_counts) {
     P.want_counts = want_counts ? 1u : 0u;
     P.risk_cur = s->risk[s->risk_cur];
     P.risk_next = s->risk[s->risk_cur ^ 1];
+    s->ev_chain = false;  // (the caller's exchange / collectives ran since the last span)
     switch (part) {
     case PD_PART_PRE: {
         if ((rc = begin_claims(s, st))) return rc;
@@ -735,6 +751,8 @@ int pd_set_profile(pd_sim* s, int on) {
     if (!s) return fail(PD_ERR_INVALID, "NULL argument");
     s->profile = on != 0;
     s->ev_used = 0;
+    s->spans.clear();
+    s->ev_chain = false;
     s->prof_steps = 0;
     for (int i = 0; i < PDABM_NUM_KERNELS; ++i) s->kernel_ms[i] = 0.0;
     return PD_OK;
@@ -744,13 +762,15 @@ int pd_read_profile(pd_sim* s, double kernel_ms[PDABM_NUM_KERNELS], uint32_t* st
     if (!s || !kernel_ms) return fail(PD_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
-    for (size_t k = 0; 2 * k + 1 < s->ev_used; ++k) {
+    for (const pd_sim::ProfSpan& sp : s->spans) {
         float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, s->ev[2 * k], s->ev[2 * k + 1]));
-        s->kernel_ms[s->ev_slot[k]] += (double)ms;
-        if (s->ev_slot[k] == 2) s->prof_steps += 1;  // one play sweep per step
+        CK(cudaEventElapsedTime(&ms, s->ev[sp.start], s->ev[sp.end]));
+        s->kernel_ms[sp.slot] += (double)ms;
+        if (sp.slot == 2) s->prof_steps += 1;  // one play sweep per step
     }
+    s->spans.clear();
     s->ev_used = 0;
+    s->ev_chain = false;
     for (int i = 0; i < PDABM_NUM_KERNELS; ++i) kernel_ms[i] = s->kernel_ms[i];
     if (steps) *steps = s->prof_steps;
     return PD_OK;
