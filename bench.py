@@ -488,8 +488,8 @@ def run_ours(args, rank, world, local_rank):
                      "peak_source": peak_src, "alg_bytes_per_launch": ALG_BYTES[dom] * cells,
                      "launch_ms": kern[dom]["ms_per_step"],
                      # HBM is the roofline this path is held against; what limits the kernel TODAY is named here
-                     "limited_by": "instruction issue (ncu, profiles/: issue slots ~75 % busy, 48 registers -> 5 CTAs "
-                                   "per SM, DRAM ~20 % of its peak)"
+                     "limited_by": "instruction issue (ncu, profiles/: issue slots ~75 % busy, the integer ALU pipe "
+                                   "~73 % of its cycles, 48 registers -> 5 CTAs per SM, DRAM ~20 % of its peak)"
                                    if (kern[dom]["frac_of_hbm_peak"] or 0) < 0.5 else "HBM bandwidth"},
         "kernels": kern,
         "also": also,
